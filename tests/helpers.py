@@ -1,0 +1,66 @@
+"""Shared fixture plumbing: rebuild the seeded weights / inputs a golden .npz was generated from."""
+import os
+
+import numpy as np
+import torch
+
+from case_rg_b200 import synthetic as syn
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+V_SMALL, V_GTTP_SMALL, H = 1000, 1200, 256
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + '.npz'))
+    cfg = dict(zip([str(k) for k in z['cfg_keys']], [float(v) for v in z['cfg']]))
+    return z, cfg
+
+
+def case_state_for(name, cfg):
+    w = int(cfg['wseed'])
+    if name == 'case_module_greedy_xavier':
+        return syn.make_case_decoder_state(w, V_SMALL, H)
+    if name in ('case_module_greedy_peaked', 'case_teacher_forced_pad'):
+        return syn.make_case_decoder_state(w, V_SMALL, H, peaked=cfg['peaked'], boost={0: cfg['pad_boost']},
+                                           gen_gate_bias=cfg['gate'])
+    if name == 'case_generations':
+        return syn.make_case_decoder_state(w, V_SMALL, H, peaked=cfg['peaked'], boost={syn.EOS: cfg['eos_boost']},
+                                           gen_gate_bias=cfg['gate'])
+    if name == 'case_model_forward_capture':
+        return syn.make_case_decoder_state(w, V_SMALL, H, peaked=0.3, gen_gate_bias=2.0)
+    raise KeyError(name)
+
+
+def build_case(name):
+    """-> (npz, cfg, state_dict, CaseInputs) with the weight checksum verified."""
+    z, cfg = load_golden(name)
+    sd = case_state_for(name, cfg)
+    assert abs(syn.state_checksum(sd) - float(z['wsum'])) < 1e-6 * max(1.0, abs(float(z['wsum']))), \
+        'seeded weights differ from the ones the golden was generated with (torch RNG drift?)'
+    inp = syn.make_case_inputs(int(cfg['iseed']), int(cfg['B']), int(cfg['Lq']), int(cfg['NP']), int(cfg['Lp']),
+                               V_SMALL, H)
+    return z, cfg, sd, inp
+
+
+def build_gttp(name='gttp_generations'):
+    z, cfg = load_golden(name)
+    sd = syn.make_gttp_state(int(cfg['wseed']), V_GTTP_SMALL, H, H, peaked=cfg['peaked'],
+                             boost={syn.EOS: cfg['eos_boost']})
+    assert abs(syn.state_checksum(sd) - float(z['wsum'])) < 1e-6 * max(1.0, abs(float(z['wsum'])))
+    inp = syn.make_gttp_inputs(int(cfg['iseed']), int(cfg['B']), int(cfg['Lc']), int(cfg['NP']), int(cfg['Lp']),
+                               V_GTTP_SMALL, H)
+    return z, cfg, sd, inp
+
+
+def captured_inputs(z):
+    """CaseInputs rebuilt from what the reference's CaSE.forward handed to its decoder."""
+    t = lambda k: torch.from_numpy(z[k])
+    B = z['query'].shape[0]
+    return syn.CaseInputs(t('query'), t('passage'), t('source_map'), t('mem_q'), t('mem_p'), t('w_q'), t('w_p'),
+                          t('feat'), torch.arange(B), V_SMALL)
+
+
+def pad_to(tokens, L):
+    out = torch.zeros(tokens.size(0), L, dtype=torch.long)
+    out[:, :tokens.size(1)] = tokens
+    return out
