@@ -1,0 +1,395 @@
+// Memory-streaming attention kernels of the decode step.
+//
+//  * cross_attn_partial : multi-head cross-attention of the newest position over a projected memory
+//    (TransformerDecoder.py:81).  One CTA per (query, head, key split) streams that head's K and V
+//    exactly once and serves all W beam rows of the query from the same shared-memory tile.
+//  * additive_attn      : the "BilinearAttention" of the reference (actually additive/Bahdanau,
+//    BilinearAttention.py:24-60) fused with its softmax statistics, the prior re-weighting sums of
+//    CaSE/Model.py:110-111 and the context reduction.  One CTA per (query, key split).
+//
+// Both are HBM-bound on their K/V (resp. Uk.mem / mem) streams; algorithmic bytes per launch are
+// B * 2 * S * H * sizeof(T).
+#include "common.cuh"
+
+namespace cb {
+
+// ------------------------------------------------------------------------------------------ cross attention
+constexpr int XT = 128;   // keys per tile == threads per CTA
+
+template <typename T, int WMAX>
+__global__ __launch_bounds__(XT) void cross_attn_partial_kernel(
+    const float* __restrict__ q2, const T* __restrict__ Kmem, const T* __restrict__ Vmem,
+    const uint8_t* __restrict__ mask, int W, int S, int nsplit, float* __restrict__ part_ml,
+    float* __restrict__ part_acc) {
+  __shared__ float qs[WMAX][HD];
+  __shared__ float Ks[XT][HD + 1];
+  __shared__ __align__(16) float Vs[XT][HD];
+  __shared__ float ps[WMAX][XT];
+  __shared__ float wred[2][XT / 32][WMAX];
+  const int b = blockIdx.x, hh = blockIdx.y, sp = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = split_chunk(S, nsplit, XT);
+  const int s_begin = sp * chunk, s_end = min(S, s_begin + chunk);
+
+  for (int i = tid; i < W * HD; i += XT) {
+    const int w = i / HD, d = i % HD;
+    qs[w][d] = q2[((size_t)(b * W + w)) * H + hh * HD + d];
+  }
+  float m[WMAX], l[WMAX], acc[(WMAX + 3) / 4];
+#pragma unroll
+  for (int w = 0; w < WMAX; ++w) { m[w] = -INFINITY; l[w] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < (WMAX + 3) / 4; ++i) acc[i] = 0.f;
+  const T* Kb = Kmem + ((size_t)(b * NH + hh)) * S * HD;
+  const T* Vb = Vmem + ((size_t)(b * NH + hh)) * S * HD;
+  const uint8_t* mb = mask + (size_t)b * S;
+  __syncthreads();
+
+  for (int s0 = s_begin; s0 < s_end; s0 += XT) {
+    const int cnt = min(XT, s_end - s0);
+    // tile = cnt*HD contiguous elements of K and of V
+    for (int e = tid * 8; e < cnt * HD; e += XT * 8) {
+      float kv[8], vv[8];
+      ld8(Kb + (size_t)s0 * HD + e, kv);
+      ld8(Vb + (size_t)s0 * HD + e, vv);
+      const int s = e / HD, d = e % HD;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { Ks[s][d + u] = kv[u]; Vs[s][d + u] = vv[u]; }
+    }
+    __syncthreads();
+    // phase 1: thread = key
+    float sc[WMAX];
+    const bool valid = tid < cnt && mb[s0 + tid] != 0;
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w) sc[w] = 0.f;
+    if (valid) {
+#pragma unroll
+      for (int d = 0; d < HD; ++d) {
+        const float kd = Ks[tid][d];
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w) sc[w] = fmaf(qs[w][d], kd, sc[w]);   // rows >= W read zeros/garbage, unused
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w) {
+      sc[w] = valid ? sc[w] : -INFINITY;
+      const float mx = warp_max(sc[w]);
+      if (lane == 0) wred[0][warp][w] = mx;
+    }
+    __syncthreads();
+    float scale[WMAX];
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w) {
+      float tm = fmaxf(fmaxf(wred[0][0][w], wred[0][1][w]), fmaxf(wred[0][2][w], wred[0][3][w]));
+      const float mn = fmaxf(m[w], tm);
+      scale[w] = (m[w] == -INFINITY) ? 0.f : fexp(m[w] - mn);
+      m[w] = mn;
+      const float p = (sc[w] == -INFINITY) ? 0.f : fexp(sc[w] - mn);
+      ps[w][tid] = p;
+      const float su = warp_sum(p);
+      if (lane == 0) wred[1][warp][w] = su;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w)
+      l[w] = fmaf(l[w], scale[w], (wred[1][0][w] + wred[1][1][w]) + (wred[1][2][w] + wred[1][3][w]));
+    // phase 2: thread = (w group, d)
+#pragma unroll
+    for (int i = 0; i < (WMAX + 3) / 4; ++i) {
+      const int w = warp + 4 * i;
+      if (w < WMAX && w < W) {
+        float a = acc[i] * scale[w];
+        for (int s = 0; s < cnt; ++s) a = fmaf(ps[w][s], Vs[s][lane], a);
+        acc[i] = a;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < (WMAX + 3) / 4; ++i) {
+    const int w = warp + 4 * i;
+    if (w < WMAX && w < W) {
+      const size_t o = (((size_t)(b * W + w)) * NH + hh) * nsplit + sp;
+      part_acc[o * HD + lane] = acc[i];
+    }
+  }
+  if (tid < W) {
+    float mm = -INFINITY, ll = 0.f;
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w)
+      if (w == tid) { mm = m[w]; ll = l[w]; }
+    const size_t o = (((size_t)(b * W + tid)) * NH + hh) * nsplit + sp;
+    part_ml[o * 2] = mm;
+    part_ml[o * 2 + 1] = ll;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ additive attention
+constexpr int AT = 256;    // threads
+constexpr int ATB = 128;   // keys per tile in pass B
+
+template <typename T> struct ATile { static constexpr int TS = 32; static constexpr int PAD = 4; };
+template <> struct ATile<bf16> { static constexpr int TS = 64; static constexpr int PAD = 8; };
+
+template <typename T, int WMAX, bool FAST>
+__global__ __launch_bounds__(AT) void additive_attn_kernel(
+    const float* __restrict__ qa, const T* __restrict__ U, const T* __restrict__ Mv,
+    const float* __restrict__ vvec, const uint8_t* __restrict__ mask, const float* __restrict__ prior,
+    const int32_t* __restrict__ tok, int tok_ld, int t, int W, int S, int DV, int nsplit,
+    float* attn_un, float* __restrict__ stats, float* __restrict__ ctx_part) {
+  constexpr int TS = ATile<T>::TS, LD = H + ATile<T>::PAD, NG = AT / TS, HG = H / NG;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* qas = reinterpret_cast<float*>(smem_raw);             // [WMAX][H]
+  float* vs = qas + WMAX * H;                                  // [H]
+  float* er = vs + H;                                          // [NG][WMAX][TS]  (pass A) / scratch (pass B)
+  float* mrow = er + NG * WMAX * TS;                           // [8] block max per row
+  float* wsum = mrow + 8;                                      // [8 warps][8]
+  T* Us = reinterpret_cast<T*>(wsum + 128);                    // [TS][LD]
+  const int b = blockIdx.x, sp = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = split_chunk(S, nsplit, ATB);
+  const int s_begin = sp * chunk, s_end = min(S, s_begin + chunk);
+  const int r0 = b * W;
+
+  for (int i = tid; i < W * H; i += AT) qas[i] = qa[(size_t)r0 * H + i];
+  for (int i = tid; i < H; i += AT) vs[i] = vvec[i];
+  __syncthreads();
+
+  // ---------------- pass A: raw masked scores -> attn_un
+  const T* Ub = U + (size_t)b * S * H;
+  const uint8_t* mb = mask + (size_t)b * S;
+  for (int s0 = s_begin; s0 < s_end; s0 += TS) {
+    const int cnt = min(TS, s_end - s0);
+    for (int e = tid * 8; e < cnt * H; e += AT * 8) {
+      const int s = e / H, c = e % H;
+      // raw copy of 8 elements (16 B bf16 / 32 B fp32)
+      if (sizeof(T) == 2) {
+        *reinterpret_cast<uint4*>(Us + s * LD + c) = __ldg(reinterpret_cast<const uint4*>(Ub + (size_t)s0 * H + e));
+      } else {
+        const float4* src = reinterpret_cast<const float4*>(Ub + (size_t)s0 * H + e);
+        float4* dst = reinterpret_cast<float4*>(Us + s * LD + c);
+        dst[0] = __ldg(src); dst[1] = __ldg(src + 1);
+      }
+    }
+    __syncthreads();
+    {
+      const int s = tid % TS, g = tid / TS;
+      float e[WMAX];
+#pragma unroll
+      for (int w = 0; w < WMAX; ++w) e[w] = 0.f;
+      if (s < cnt) {
+        const T* up = Us + s * LD + g * HG;
+        for (int k = 0; k < HG; k += 8) {
+          float u[8];
+          ld8c(up + k, u);
+          const int hh = g * HG + k;
+#pragma unroll
+          for (int w = 0; w < WMAX; ++w) {
+            if (w < W) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float x = qas[w * H + hh + i] + u[i];
+                e[w] = fmaf(vs[hh + i], FAST ? tanh_fast(x) : tanh_acc(x), e[w]);
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int w = 0; w < WMAX; ++w) er[(g * WMAX + w) * TS + s] = e[w];
+    }
+    __syncthreads();
+    for (int i = tid; i < W * cnt; i += AT) {
+      const int w = i / cnt, s = i % cnt;
+      float e = 0.f;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) e += er[(g * WMAX + w) * TS + s];
+      const bool rv = tok ? tok[(size_t)(r0 + w) * tok_ld + t] != 0 : true;
+      const bool ok = rv && mb[s0 + s] != 0;
+      attn_un[(size_t)(r0 + w) * S + s0 + s] = ok ? e : -INFINITY;
+    }
+    __syncthreads();
+  }
+
+  // ---------------- block max per row over this split
+  for (int w = 0; w < W; ++w) {
+    float mx = -INFINITY;
+    for (int s = s_begin + tid; s < s_end; s += AT) mx = fmaxf(mx, attn_un[(size_t)(r0 + w) * S + s]);
+    mx = warp_max(mx);
+    if (lane == 0) wsum[warp * 8 + w] = mx;
+  }
+  __syncthreads();
+  if (tid < W) {
+    float mx = -INFINITY;
+    for (int i = 0; i < AT / 32; ++i) mx = fmaxf(mx, wsum[i * 8 + tid]);
+    mrow[tid] = mx;
+  }
+  __syncthreads();
+
+  // ---------------- pass B: p = exp(e - m), sums, context partial
+  float* pt = er;                                   // [WMAX][ATB]
+  const int ncol2 = DV / 2;                         // column pairs
+  const int npc = ncol2 / 128;                      // pairs per thread (1 for DV=256, 2 for DV=512)
+  const int hp = tid & 127, kp = tid >> 7;
+  float acc[WMAX][2][2];
+#pragma unroll
+  for (int w = 0; w < WMAX; ++w)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) { acc[w][c][0] = 0.f; acc[w][c][1] = 0.f; }
+  float lsum = 0.f, lwsum = 0.f;                    // this thread's (w = tid / ATB... ) partial sums
+  const T* Mb = Mv + (size_t)b * S * DV;
+  const float* pb = prior ? prior + (size_t)b * S : nullptr;
+  for (int s0 = s_begin; s0 < s_end; s0 += ATB) {
+    const int cnt = min(ATB, s_end - s0);
+    for (int i = tid; i < W * ATB; i += AT) {
+      const int w = i / ATB, s = i % ATB;
+      float p = 0.f;
+      if (s < cnt) {
+        const float e = attn_un[(size_t)(r0 + w) * S + s0 + s];
+        p = (e == -INFINITY) ? 0.f : fexp(e - mrow[w]);
+        attn_un[(size_t)(r0 + w) * S + s0 + s] = p;
+        // per-row sums: accumulate through shared atomics-free path below
+      }
+      pt[w * ATB + s] = p;
+    }
+    __syncthreads();
+    // row sums of this tile: warp w' handles row w' (W <= 8 warps)
+    if (warp < W) {
+      float a = 0.f, aw = 0.f;
+      for (int s = lane; s < cnt; s += 32) {
+        const float p = pt[warp * ATB + s];
+        a += p;
+        aw = fmaf(pb ? pb[s0 + s] : 1.f, p, aw);
+      }
+      lsum += a; lwsum += aw;
+    }
+    for (int s = kp; s < cnt; s += 2) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (c < npc) {
+          float mv[2];
+          ld2(Mb + (size_t)(s0 + s) * DV + (c * 128 + hp) * 2, mv);
+#pragma unroll
+          for (int w = 0; w < WMAX; ++w) {
+            if (w < W) {
+              const float p = pt[w * ATB + s];
+              acc[w][c][0] = fmaf(p, mv[0], acc[w][c][0]);
+              acc[w][c][1] = fmaf(p, mv[1], acc[w][c][1]);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (warp < W) {
+    lsum = warp_sum(lsum);
+    lwsum = warp_sum(lwsum);
+    if (lane == 0) {
+      float* st = stats + ((size_t)(r0 + warp) * nsplit + sp) * 4;
+      st[0] = mrow[warp]; st[1] = lsum; st[2] = lwsum; st[3] = 0.f;
+    }
+  }
+  // combine the two key-parity halves through shared memory (reuses the U tile region)
+  float* cred = reinterpret_cast<float*>(Us);      // [WMAX][DV] needs WMAX*DV*4 <= TS*LD*sizeof(T)
+  for (int w = 0; w < W; ++w) {
+    if (kp == 1) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        if (c < npc) {
+          cred[(c * 128 + hp) * 2] = acc[w][c][0];
+          cred[(c * 128 + hp) * 2 + 1] = acc[w][c][1];
+        }
+    }
+    __syncthreads();
+    if (kp == 0) {
+      float* dst = ctx_part + ((size_t)(r0 + w) * nsplit + sp) * DV;
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        if (c < npc) {
+          const int col = (c * 128 + hp) * 2;
+          dst[col] = acc[w][c][0] + cred[col];
+          dst[col + 1] = acc[w][c][1] + cred[col + 1];
+        }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T, int WMAX, bool FAST>
+static int launch_additive(const float* qa, const void* U, const void* Mv, const float* v, const uint8_t* mask,
+                           const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S, int DV,
+                           int nsplit, float* attn_un, float* stats, float* ctx_part, cudaStream_t st) {
+  constexpr int TS = ATile<T>::TS, LD = H + ATile<T>::PAD, NG = AT / TS;
+  static_assert(NG * TS >= ATB, "pass-B tile must fit in the pass-A reduction buffer");
+  const size_t fl = (size_t)WMAX * H + H + (size_t)NG * WMAX * TS + 8 + 128;
+  const size_t smem = fl * sizeof(float) + (size_t)TS * LD * sizeof(T);
+  auto kern = additive_attn_kernel<T, WMAX, FAST>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set = true;
+  }
+  kern<<<dim3(B, nsplit), AT, smem, st>>>(qa, (const T*)U, (const T*)Mv, v, mask, prior, tok, tok_ld, t, W, S, DV,
+                                          nsplit, attn_un, stats, ctx_part);
+  return check_launch("case_additive_attn");
+}
+
+template <typename T, bool FAST>
+static int dispatch_additive_w(int W, const float* qa, const void* U, const void* Mv, const float* v,
+                               const uint8_t* mask, const float* prior, const int32_t* tok, int tok_ld, int t, int B,
+                               int S, int DV, int nsplit, float* attn_un, float* stats, float* ctx_part,
+                               cudaStream_t st) {
+  if (W <= 1) return launch_additive<T, 1, FAST>(qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, W, S, DV, nsplit, attn_un, stats, ctx_part, st);
+  if (W <= 2) return launch_additive<T, 2, FAST>(qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, W, S, DV, nsplit, attn_un, stats, ctx_part, st);
+  if (W <= 4) return launch_additive<T, 4, FAST>(qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, W, S, DV, nsplit, attn_un, stats, ctx_part, st);
+  return launch_additive<T, 8, FAST>(qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, W, S, DV, nsplit, attn_un, stats, ctx_part, st);
+}
+
+template <typename T, int WMAX>
+static int launch_cross(const float* q2, const void* K, const void* V, const uint8_t* mask, int B, int W, int S,
+                        int nsplit, float* part_ml, float* part_acc, cudaStream_t st) {
+  cross_attn_partial_kernel<T, WMAX><<<dim3(B, NH, nsplit), XT, 0, st>>>(q2, (const T*)K, (const T*)V, mask, W, S,
+                                                                          nsplit, part_ml, part_acc);
+  return check_launch("case_cross_attn_partial");
+}
+
+template <typename T>
+static int dispatch_cross_w(const float* q2, const void* K, const void* V, const uint8_t* mask, int B, int W, int S,
+                            int nsplit, float* part_ml, float* part_acc, cudaStream_t st) {
+  if (W <= 1) return launch_cross<T, 1>(q2, K, V, mask, B, W, S, nsplit, part_ml, part_acc, st);
+  if (W <= 2) return launch_cross<T, 2>(q2, K, V, mask, B, W, S, nsplit, part_ml, part_acc, st);
+  if (W <= 4) return launch_cross<T, 4>(q2, K, V, mask, B, W, S, nsplit, part_ml, part_acc, st);
+  return launch_cross<T, 8>(q2, K, V, mask, B, W, S, nsplit, part_ml, part_acc, st);
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" int case_cross_attn_partial(const float* q2, const void* Kmem, const void* Vmem, const uint8_t* mask,
+                                       int B, int W, int S, int nsplit, float* part_ml, float* part_acc, int dtype,
+                                       case_stream_t stream) {
+  CB_REQUIRE(q2 && Kmem && Vmem && mask && part_ml && part_acc, "case_cross_attn_partial: null pointer");
+  CB_REQUIRE(B > 0 && W >= 1 && W <= CASE_MAX_W && S > 0, "case_cross_attn_partial: bad sizes");
+  CB_REQUIRE(nsplit >= 1 && nsplit <= CASE_MAX_SPLIT, "case_cross_attn_partial: nsplit out of range");
+  if (dtype == CASE_BF16)
+    return dispatch_cross_w<bf16>(q2, Kmem, Vmem, mask, B, W, S, nsplit, part_ml, part_acc, (cudaStream_t)stream);
+  return dispatch_cross_w<float>(q2, Kmem, Vmem, mask, B, W, S, nsplit, part_ml, part_acc, (cudaStream_t)stream);
+}
+
+extern "C" int case_additive_attn(const float* qa, const void* U, const void* Mv, const float* v,
+                                  const uint8_t* mask, const float* prior, const int32_t* tok, int tok_ld, int t,
+                                  int B, int W, int S, int DV, int nsplit, float* attn_un, float* stats,
+                                  float* ctx_part, int fast_tanh, int dtype, case_stream_t stream) {
+  CB_REQUIRE(qa && U && Mv && v && mask && attn_un && stats && ctx_part, "case_additive_attn: null pointer");
+  CB_REQUIRE(B > 0 && W >= 1 && W <= CASE_MAX_W && S > 0, "case_additive_attn: bad sizes");
+  CB_REQUIRE(DV == 256 || DV == 512, "case_additive_attn: DV must be 256 or 512");
+  CB_REQUIRE(nsplit >= 1 && nsplit <= CASE_MAX_SPLIT, "case_additive_attn: nsplit out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == CASE_BF16) {
+    if (fast_tanh) return dispatch_additive_w<bf16, true>(W, qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, S, DV, nsplit, attn_un, stats, ctx_part, st);
+    return dispatch_additive_w<bf16, false>(W, qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, S, DV, nsplit, attn_un, stats, ctx_part, st);
+  }
+  if (fast_tanh) return dispatch_additive_w<float, true>(W, qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, S, DV, nsplit, attn_un, stats, ctx_part, st);
+  return dispatch_additive_w<float, false>(W, qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, S, DV, nsplit, attn_un, stats, ctx_part, st);
+}

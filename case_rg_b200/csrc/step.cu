@@ -1,0 +1,201 @@
+// Error plumbing and the whole-step orchestrators: one C call enqueues every kernel of a decode
+// step on the caller's stream (so a step, or a whole decode, can be captured in a CUDA graph).
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace cb {
+
+static thread_local char g_err[512] = "ok";
+
+void set_error(const char* msg) {
+  strncpy(g_err, msg, sizeof(g_err) - 1);
+  g_err[sizeof(g_err) - 1] = 0;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" int case_abi_version(void) { return 1; }
+extern "C" const char* case_last_error(void) { return g_err; }
+
+#define TRY(x)            \
+  do {                    \
+    int _e = (x);         \
+    if (_e) return _e;    \
+  } while (0)
+
+static case_seg_t seg(const float* p, int ld, int width, int div, int gather = 0) {
+  case_seg_t s;
+  s.p = p; s.ld = ld; s.width = width; s.div = div; s.gather = gather;
+  return s;
+}
+
+static int select_step(int mode, int B, int W, int t, int max_len, int Tmax, int BOS, int EOS, int UNK, int PAD,
+                       const float* top_vals, const int32_t* top_idx, int32_t* live, double* cum, int32_t* length,
+                       int32_t* tok, int32_t* const anc[2], int32_t* parent, int32_t* ended, double* best_key,
+                       int32_t* best_len, int32_t* out_tokens, int32_t* n_live, cudaStream_t st) {
+  case_select_args_t s;
+  memset(&s, 0, sizeof(s));
+  s.mode = mode; s.B = B; s.W = W; s.t = t; s.max_len = max_len; s.Tmax = Tmax;
+  s.BOS = BOS; s.EOS = EOS; s.UNK = UNK; s.PAD = PAD;
+  s.top_vals = top_vals; s.top_idx = top_idx; s.live = live; s.cum = cum; s.length = length; s.tok = tok;
+  s.anc_in = anc[t & 1]; s.anc_out = anc[(t + 1) & 1]; s.parent = parent; s.ended = ended;
+  s.best_key = best_key; s.best_len = best_len; s.out_tokens = out_tokens; s.n_live = n_live;
+  cudaError_t e = cudaMemsetAsync(n_live, 0, sizeof(int32_t), st);
+  if (e != cudaSuccess) { set_error("select_step: cudaMemsetAsync failed"); return (int)e; }
+  return case_beam_select(&s, st);
+}
+
+extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t stream) {
+  CB_REQUIRE(a, "case_decode_step: null args");
+  CB_REQUIRE(a->R == a->B * a->W && a->W >= 1 && a->W <= CASE_MAX_W, "case_decode_step: R != B*W or W out of range");
+  CB_REQUIRE(t >= 0 && t < a->Tmax && a->Tmax <= CASE_MAX_T, "case_decode_step: t out of range");
+  CB_REQUIRE(a->materialize_only || t < a->max_len, "case_decode_step: t >= max_len");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = a->R, B = a->B, W = a->W, TL = a->Tmax + 1, dt = a->dtype;
+  const int32_t* anc = a->anc[t & 1];
+
+  TRY(case_embed_rows(a->E, a->pe, a->tok, TL, t, 16.0f /* sqrt(256) */, a->x_in, R, st));
+  const float* hin = a->x_in;
+  for (int i = 0; i < 2; ++i) {
+    for (int l = 0; l < 4; ++l) {
+      const int L = i * 4 + l;
+      TRY(case_layer_front(hin, &a->layers[L], a->kcache[L], a->vcache[L], anc, TL, a->tok, TL, t, a->Tmax,
+                           a->bbuf, a->q2, R, dt, st));
+      TRY(case_cross_attn_partial(a->q2, a->Kx[L], a->Vx[L], a->mask[i], B, W, a->S[i], a->nsplit_x[i], a->part_ml,
+                                  a->part_acc, dt, st));
+      TRY(case_layer_back(a->bbuf, a->part_ml, a->part_acc, a->nsplit_x[i], &a->layers[L], a->h, R, dt, st));
+      hin = a->h;
+    }
+    // attns[i]: query = [dec_out ; norm2(answer_rep)]   (Model.py:108)
+    case_rowlin_args_t q;
+    memset(&q, 0, sizeof(q));
+    q.seg[0] = seg(a->h, H, H, 1);
+    q.seg[1] = seg(a->feat, H, H, W);
+    q.nseg = 2; q.K = 2 * H; q.Wt = a->Wqa_t[i]; q.bias = a->bqa[i]; q.N = H; q.out = a->qa; q.ldo = H;
+    q.R = R; q.dtype = dt;
+    TRY(case_row_linear(&q, st));
+    TRY(case_additive_attn(a->qa, a->U[i], a->Mv[i], a->va[i], a->mask[i], a->prior[i], a->tok, TL, t, B, W, a->S[i],
+                           H, a->nsplit_a[i], a->attn_un[i], a->stats[i], a->ctxp[i], a->fast_tanh, dt, st));
+  }
+  TRY(case_finalize_rows(a->h, a->lnN_g, a->lnN_b, a->stats[0], a->ctxp[0], a->nsplit_a[0], a->stats[1], a->ctxp[1],
+                         a->nsplit_a[1], a->Wm, a->bm, a->hN, a->ctx[0], a->ctx[1], a->gates, a->fac, R, st));
+  {  // gen.0 on [dec_input ; norm1(dec_out) ; feat]   (Model.py:115)
+    case_rowlin_args_t g;
+    memset(&g, 0, sizeof(g));
+    g.seg[0] = seg(a->x_in, H, H, 1);
+    g.seg[1] = seg(a->hN, H, H, 1);
+    g.seg[2] = seg(a->feat, H, H, W);
+    g.nseg = 3; g.K = 3 * H; g.Wt = a->Wg_t; g.bias = a->bg; g.N = H; g.out = a->gfeat; g.ldo = H;
+    g.R = R; g.dtype = dt;
+    TRY(case_row_linear(&g, st));
+  }
+  TRY(case_vocab_gemm(a->gfeat, a->Wv, nullptr, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, st));
+  TRY(case_softmax_mix(a->logits, a->ldv, a->gates, a->dist, a->ldv, R, a->V, 0, st));
+  for (int i = 0; i < 2; ++i) {
+    TRY(case_copy_scatter(a->map, a->map_ld, a->map_off[i], a->prior[i], a->attn_un[i],
+                          a->fac + (size_t)i * CASE_MAX_SPLIT, 2 * CASE_MAX_SPLIT,
+                          split_chunk(a->S[i], a->nsplit_a[i], AATTN_TILE), a->dist, a->ldv, B, W, a->S[i], a->V, st));
+  }
+  if (a->materialize_only) return 0;
+  TRY(case_topk_rows(a->dist, a->ldv, R, a->V, W, a->top_vals, a->top_idx, st));
+  return select_step(a->mode, B, W, t, a->max_len, a->Tmax, a->BOS, a->EOS, a->UNK, a->PAD, a->top_vals, a->top_idx,
+                     a->live, a->cum, a->length, a->tok, a->anc, a->parent, a->ended, a->best_key, a->best_len,
+                     a->out_tokens, a->n_live, st);
+}
+
+extern "C" int gttp_decode_step(const gttp_step_args_t* a, int t, case_stream_t stream) {
+  CB_REQUIRE(a, "gttp_decode_step: null args");
+  CB_REQUIRE(a->R == a->B * a->W && a->W >= 1 && a->W <= CASE_MAX_W, "gttp_decode_step: R != B*W or W out of range");
+  CB_REQUIRE(t >= 0 && t < a->Tmax && a->Tmax <= CASE_MAX_T, "gttp_decode_step: t out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = a->R, B = a->B, W = a->W, TL = a->Tmax + 1, dt = a->dtype;
+  const float* s_in = a->state[t & 1];
+  float* s_out = a->state[(t + 1) & 1];
+
+  TRY(case_embed_rows(a->E, nullptr, a->tok, TL, t, 1.0f, a->emb, R, st));
+  // two additive attentions with the previous GRU state as query (GTTP/Model.py:117-122)
+  const void* Wq[2] = {a->Wqs_t, a->Wqb_t};
+  const float* bq[2] = {a->bqs, a->bqb};
+  const float* vv[2] = {a->vs, a->vb};
+  const void* U[2] = {a->Us, a->Ub};
+  const void* M[2] = {a->Ms, a->Mb};
+  const uint8_t* mk[2] = {a->mask_c, a->mask_b};
+  const int L[2] = {a->Lc, a->Lb};
+  const int ns[2] = {a->nsplit_c, a->nsplit_b};
+  for (int i = 0; i < 2; ++i) {
+    case_rowlin_args_t q;
+    memset(&q, 0, sizeof(q));
+    q.seg[0] = seg(s_in, H, H, 1, 1);
+    q.nseg = 1; q.K = H; q.Wt = Wq[i]; q.bias = bq[i]; q.N = H; q.out = a->qa; q.ldo = H;
+    q.gather_idx = a->parent; q.R = R; q.dtype = dt;
+    TRY(case_row_linear(&q, st));
+    TRY(case_additive_attn(a->qa, U[i], M[i], vv[i], mk[i], nullptr, nullptr, 0, t, B, W, L[i], 2 * H, ns[i],
+                           a->attn_un[i], a->stats[i], a->ctxp[i], a->fast_tanh, dt, st));
+    TRY(case_attn_merge(a->stats[i], a->ctxp[i], ns[i], 2 * H, a->ctx[i], i == 1 ? a->fac : nullptr, CASE_MAX_SPLIT,
+                        R, st));
+  }
+  {  // GRU cell on [emb ; src_ctx ; bg_ctx]   (Model.py:124-126)
+    case_rowlin_args_t g;
+    memset(&g, 0, sizeof(g));
+    g.seg[0] = seg(a->emb, H, H, 1);
+    g.seg[1] = seg(a->ctx[0], 2 * H, 2 * H, 1);
+    g.seg[2] = seg(a->ctx[1], 2 * H, 2 * H, 1);
+    g.nseg = 3; g.K = 5 * H; g.Wt = a->Wih_t; g.bias = a->bih; g.N = 3 * H; g.out = a->gi; g.ldo = 3 * H;
+    g.R = R; g.dtype = dt;
+    TRY(case_row_linear(&g, st));
+    case_rowlin_args_t hh;
+    memset(&hh, 0, sizeof(hh));
+    hh.seg[0] = seg(s_in, H, H, 1, 1);
+    hh.nseg = 1; hh.K = H; hh.Wt = a->Whh_t; hh.bias = a->bhh; hh.N = 3 * H; hh.out = a->gh; hh.ldo = 3 * H;
+    hh.gather_idx = a->parent; hh.R = R; hh.dtype = dt;
+    TRY(case_row_linear(&hh, st));
+    TRY(case_gru_cell(a->gi, a->gh, s_in, a->parent, s_out, R, st));
+  }
+  {  // readout on [emb ; h' ; src_ctx ; bg_ctx]   (Model.py:128-130)
+    case_rowlin_args_t r;
+    memset(&r, 0, sizeof(r));
+    r.seg[0] = seg(a->emb, H, H, 1);
+    r.seg[1] = seg(s_out, H, H, 1);
+    r.seg[2] = seg(a->ctx[0], 2 * H, 2 * H, 1);
+    r.seg[3] = seg(a->ctx[1], 2 * H, 2 * H, 1);
+    r.nseg = 4; r.K = 6 * H; r.Wt = a->Wr_t; r.bias = a->br; r.N = H; r.out = a->feat; r.ldo = H;
+    r.R = R; r.dtype = dt;
+    TRY(case_row_linear(&r, st));
+  }
+  TRY(case_vocab_gemm(a->feat, a->Wv, a->bv, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, st));
+  TRY(case_gttp_gates(a->feat, a->wc, a->bc, a->gates, a->fac, CASE_MAX_SPLIT, ns[1], R, st));
+  TRY(case_softmax_mix(a->logits, a->ldv, a->gates, a->dist, a->ldv, R, a->V, 1, st));
+  TRY(case_copy_scatter(a->map, a->map_ld, 0, nullptr, a->attn_un[1], a->fac, CASE_MAX_SPLIT,
+                        split_chunk(a->Lb, ns[1], AATTN_TILE), a->dist, a->ldv, B, W, a->Lb, a->V, st));
+  if (a->materialize_only) return 0;
+  TRY(case_topk_rows(a->dist, a->ldv, R, a->V, W, a->top_vals, a->top_idx, st));
+  return select_step(a->mode, B, W, t, a->max_len, a->Tmax, a->BOS, a->EOS, a->UNK, a->PAD, a->top_vals, a->top_idx,
+                     a->live, a->cum, a->length, a->tok, a->anc, a->parent, a->ended, a->best_key, a->best_len,
+                     a->out_tokens, a->n_live, st);
+}
+
+/* layout self-check for FFI bindings: sizeof of each argument struct, by index */
+extern "C" size_t case_struct_size(int which) {
+  switch (which) {
+    case 0: return sizeof(case_seg_t);
+    case 1: return sizeof(case_rowlin_args_t);
+    case 2: return sizeof(case_layer_weights_t);
+    case 3: return sizeof(case_select_args_t);
+    case 4: return sizeof(case_step_args_t);
+    case 5: return sizeof(gttp_step_args_t);
+    default: return 0;
+  }
+}

@@ -1,0 +1,178 @@
+"""Module face of the drop-in: ``FastCaSEDecoder`` stands where the reference builds
+``CaSETransformerSeqDecoder`` (CaSE/Model.py:265) and keeps its constructor, parameter names
+(so ``load_state_dict`` of a reference checkpoint works, CaSE/Run.py:55) and ``forward`` signature
+/ 4-tuple return (CaSE/Model.py:50,125).
+
+Differences, all in test mode only (training stays on the reference module):
+  * ``source_map`` is taken in its int64 index form [B,S] (what CaSEDataset / collate_fn produce,
+    CaSE/CaSEDataset.py:98-104,140).  The dense one-hot of ``build_map`` (Utils.py:344-355) is still
+    accepted and converted back, but at BASELINE sizes it does not fit (20 GB at B=64, S=2620), so
+    ``install_fast_decoder`` also stops ``CaSE.forward`` from building it.
+  * the first three returned tensors cover the last decoded position only ([B,1,.]); the reference
+    returns all T positions of its last step, and its only test-mode consumer reads element [3]
+    (CaSE/Model.py:331).
+  * ``beam_width`` (default 1 = the reference's in-module greedy loop) selects Generations.beam
+    semantics on the device.
+"""
+import math
+import types
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .engine import CaseDecodeEngine, CaseWeights
+
+
+class _PositionalTable(nn.Module):
+    """Holds the ``pe`` buffer under the reference's key ``embedding.1.pe`` (PositionalEmbedding.py:27-32)."""
+
+    def __init__(self, H, max_len=1000):
+        super().__init__()
+        pe = torch.zeros(max_len, H)
+        pos = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+        div = torch.exp(torch.arange(0, H, 2).float() * (-math.log(10000.0) / H))
+        pe[:, 0::2] = torch.sin(pos * div)
+        pe[:, 1::2] = torch.cos(pos * div)
+        self.register_buffer('pe', pe)
+
+
+class _LayerParams(nn.Module):
+    def __init__(self, H, nhead):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(H, nhead)
+        self.multihead_attn = nn.MultiheadAttention(H, nhead)
+        self.linear1, self.linear2 = nn.Linear(H, H), nn.Linear(H, H)
+        self.norm1, self.norm2, self.norm3 = nn.LayerNorm(H), nn.LayerNorm(H), nn.LayerNorm(H)
+
+
+class _StackParams(nn.Module):
+    def __init__(self, H, nhead, num_layers):
+        super().__init__()
+        self.layers = nn.ModuleList([_LayerParams(H, nhead) for _ in range(num_layers)])
+
+
+class _AdditiveParams(nn.Module):
+    def __init__(self, q, k, h):
+        super().__init__()
+        self.linear_key = nn.Linear(k, h, bias=False)
+        self.linear_query = nn.Linear(q, h, bias=True)
+        self.v = nn.Linear(h, 1, bias=False)
+
+
+class FastCaSEDecoder(nn.Module):
+    """Parameter container with the reference's state_dict layout + the CUDA decode path."""
+
+    def __init__(self, num_memories, num_layers, nhead, tgt_vocab_size, hidden_size, emb_matrix=None,
+                 beam_width: int = 1, dtype: str = 'bf16', vocab_impl: Optional[int] = None, use_graph: bool = True):
+        super().__init__()
+        if (num_memories, num_layers, nhead, hidden_size) != (2, 4, 8, L.H):
+            raise ValueError('FastCaSEDecoder is built for the shipped configuration: num_memories=2, '
+                             f'num_layers=4, nhead=8, hidden_size={L.H} (CaSE/Model.py:265, Run.py:71)')
+        H = hidden_size
+        self.tgt_vocab_size, self.num_layers, self.hidden_size = tgt_vocab_size, num_layers, hidden_size
+        self.embedding = nn.Sequential(nn.Embedding(tgt_vocab_size, H, padding_idx=0), _PositionalTable(H))
+        if emb_matrix is not None:
+            self.embedding[0].weight.data.copy_(torch.as_tensor(emb_matrix))
+        self.decs = nn.ModuleList([_StackParams(H, nhead, num_layers) for _ in range(num_memories)])
+        self.norm1, self.norm2 = nn.LayerNorm(H), nn.LayerNorm(H)
+        self.attns = nn.ModuleList([_AdditiveParams(2 * H, H, H) for _ in range(num_memories)])
+        self.gen = nn.Sequential(nn.Linear(3 * H, H), nn.Dropout(0.1), nn.Linear(H, tgt_vocab_size, bias=False),
+                                 nn.Softmax(dim=-1))
+        self.mix = nn.Linear(3 * H, num_memories + 1)
+        self.beam_width, self.dtype, self.vocab_impl, self.use_graph = beam_width, dtype, vocab_impl, use_graph
+        self._weights = None
+        self._engines: Dict[tuple, CaseDecodeEngine] = {}
+
+    # ---------------------------------------------------------------- construction helpers
+    @classmethod
+    def from_reference(cls, ref_decoder: nn.Module, **kw) -> "FastCaSEDecoder":
+        """Build from a reference ``CaSETransformerSeqDecoder`` instance (weights copied)."""
+        sd = ref_decoder.state_dict()
+        V, H = sd['embedding.0.weight'].shape
+        m = cls(len(ref_decoder.decs), ref_decoder.num_layers, 8, V, H, **kw)
+        m.load_state_dict(sd)
+        return m.to(sd['embedding.0.weight'].device).eval()
+
+    @classmethod
+    def from_state_dict(cls, sd: Dict[str, torch.Tensor], **kw) -> "FastCaSEDecoder":
+        V, H = sd['embedding.0.weight'].shape
+        m = cls(2, 4, 8, V, H, **kw)
+        m.load_state_dict(sd)
+        return m.eval()
+
+    def _load_from_state_dict(self, *a, **k):
+        self._weights = None          # re-pack on next use
+        self._engines = {}
+        return super()._load_from_state_dict(*a, **k)
+
+    def refresh_weights(self):
+        self._weights, self._engines = None, {}
+
+    def _packed(self, device) -> CaseWeights:
+        if self._weights is None or self._weights.device != device or self._weights.dtype_name != self.dtype:
+            self._weights = CaseWeights(self.state_dict(), device=device, dtype=self.dtype)
+            self._engines = {}
+        return self._weights
+
+    def engine_for(self, B, W, S0, S1, T, device) -> CaseDecodeEngine:
+        key = (B, W, S0, S1, T, str(device), self.dtype, self.vocab_impl)
+        e = self._engines.get(key)
+        if e is None:
+            if len(self._engines) >= 4:       # shapes are few in practice (full batches + one tail batch)
+                self._engines.clear()
+            e = CaseDecodeEngine(self._packed(device), B, W, S0, S1, T, vocab_impl=self.vocab_impl)
+            self._engines[key] = e
+        return e
+
+    # ---------------------------------------------------------------- reference signature
+    def forward(self, encode_memories, BOS, UNK, source_map, groundtruth_index=None, additional_decoder_feature=None,
+                encode_weights=None, encode_masks=None, init_decoder_state=None, max_target_length=None):
+        if self.training:
+            raise NotImplementedError('FastCaSEDecoder covers the test-mode decode path only; train with the '
+                                      'reference CaSETransformerSeqDecoder and load its checkpoint here')
+        if BOS != 1:
+            raise ValueError('BOS id must be 1 ([unused0], common/Constants.py:2)')
+        dev = encode_memories[0].device
+        if dev.type != 'cuda':
+            raise RuntimeError('FastCaSEDecoder needs CUDA tensors: there is no CPU fallback')
+        B = source_map.size(0)
+        if source_map.dim() == 3:                 # dense one-hot from build_map: recover the indices
+            source_map = source_map.argmax(dim=-1)
+        if max_target_length is None:
+            max_target_length = groundtruth_index.size(1)
+        H = self.hidden_size
+        mems = [m.reshape(B, -1, H) for m in encode_memories]
+        W = int(self.beam_width)
+        eng = self.engine_for(B, W, mems[0].size(1), mems[1].size(1), int(max_target_length), dev)
+        eng.prefill(encode_memories[0], encode_memories[1], encode_masks[0], encode_masks[1], encode_weights[0],
+                    encode_weights[1], additional_decoder_feature, source_map)
+        mode = L.MODE_MODULE_GREEDY if W == 1 else L.MODE_BEAM
+        tokens = eng.decode(int(max_target_length), mode, use_graph=self.use_graph)
+        sel = slice(0, None, W)
+        dec_outputs = eng.hN[sel].unsqueeze(1)
+        ext = eng.dist[sel, :self.tgt_vocab_size].unsqueeze(1)
+        return dec_outputs, None, ext, tokens
+
+
+def install_fast_decoder(model: nn.Module, beam_width: int = 1, dtype: str = 'bf16', **kw) -> nn.Module:
+    """Swap the decoder of a reference ``CaSE`` model (CaSE/Model.py:255-339) for the CUDA path, in place.
+
+    * ``model.response_generation.decoder`` becomes a ``FastCaSEDecoder`` holding the same weights;
+    * ``model.forward`` keeps ``data['source_map']`` in index form instead of calling ``build_map``
+      (Model.py:334-335) when ``method == 'test'``; training goes through the original forward.
+    """
+    ref_dec = model.response_generation.decoder
+    fast = FastCaSEDecoder.from_reference(ref_dec, beam_width=beam_width, dtype=dtype, **kw)
+    model.response_generation.decoder = fast
+    orig_forward = model.forward
+
+    def forward(self, data, method='mle_train'):
+        if method == 'test':
+            return self.do_test(data)
+        return orig_forward(data, method=method)
+
+    model.forward = types.MethodType(forward, model)
+    model._reference_decoder = [ref_dec]     # list: keeps it out of the module tree / state_dict
+    return model

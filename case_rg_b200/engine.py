@@ -1,0 +1,455 @@
+"""Device-side engines for the CaSE and GTTP answer decoders.
+
+An engine owns every device buffer of one (B, W, S, Tmax, V) problem shape, fills the C argument
+struct once, and then a decode is: ``prefill(inputs)`` (once per batch: project the memories,
+build masks / priors / copy map) followed by ``max_len`` calls of ``case_decode_step`` /
+``gttp_decode_step`` - optionally replayed from a captured CUDA graph.  torch is used for device
+memory, streams and the per-batch prefill GEMMs only; every per-step op is a kernel of
+libcase_b200.so.  There is no CPU path.
+
+Reference being replaced: the eval loop of CaSETransformerSeqDecoder.forward (CaSE/Model.py:91-123),
+Generations.greedy/beam (common/Generations.py:66-190) and the GTTP step (GTTP/Model.py:113-131,
+14-43, 176-193).
+"""
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+
+PAD, BOS, EOS, UNK = 0, 1, 2, 100
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError('case_rg_b200 needs a CUDA device: the decode path has no CPU fallback')
+    return torch.device(device if device is not None else 'cuda')
+
+
+def _storage(dtype: str):
+    if dtype in ('bf16', 'bfloat16'):
+        return torch.bfloat16, L.BF16
+    if dtype in ('fp32', 'float32', 'f32'):
+        return torch.float32, L.F32
+    raise ValueError(f'dtype must be "bf16" or "fp32", got {dtype!r}')
+
+
+def _nsplit(units_per_split_group: int, S: int, tile: int, target_ctas: int) -> int:
+    """splits so that units*nsplit >= target CTAs, bounded by the tile count and the ABI limit"""
+    n = max(1, -(-target_ctas // max(1, units_per_split_group)))
+    return int(max(1, min(n, L.MAX_SPLIT, -(-S // tile))))
+
+
+def split_chunk(S, nsplit, tile=128):
+    c = -(-S // nsplit)
+    return -(-c // tile) * tile
+
+
+class CaseWeights:
+    """Weights of CaSETransformerSeqDecoder re-laid-out for the kernels (CaSE/Model.py:14-36 names).
+
+    Matrices are transposed to [K][N] in the storage dtype; the 1/sqrt(hd) attention scale is
+    folded into the query projections; cross-attention K/V and attns.*.linear_key weights are kept
+    fp32 [K][N] for the per-batch prefill GEMMs."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], device=None, dtype: str = 'bf16', prefix: str = ''):
+        dev = _require_cuda(device)
+        self.device, self.dtype_name = dev, dtype
+        self.tdtype, self.cdtype = _storage(dtype)
+        g = lambda k: sd[prefix + k].detach().to(dev, torch.float32)
+        self.H = H = g('embedding.0.weight').size(1)
+        if H != L.H:
+            raise ValueError(f'hidden_size must be {L.H} (got {H})')
+        self.V = g('gen.2.weight').size(0)
+        self.M = len({k[len(prefix):].split('.')[1] for k in sd if k.startswith(prefix + 'decs.')})
+        self.Ln = len({k[len(prefix):].split('.')[3] for k in sd if k.startswith(prefix + 'decs.0.layers.')})
+        if self.M != 2 or self.Ln != 4:
+            raise ValueError('the fused step is built for num_memories=2, num_layers=4 (CaSE/Model.py:265)')
+        scale = math.sqrt(1.0 / L.HD)
+        mat = lambda w: w.t().contiguous().to(self.tdtype)        # [N,K] -> [K][N]
+        vec = lambda b: b.contiguous()
+        self.keep = []            # keeps every tensor alive
+        self.layers = (L.LayerWeights * 8)()
+        self.kv_w, self.kv_b = [], []                              # per stack: [H][Ln*2*H], [Ln*2*H]
+        for i in range(2):
+            kvw, kvb = [], []
+            for l in range(4):
+                p = f'decs.{i}.layers.{l}.'
+                Wi, bi = g(p + 'self_attn.in_proj_weight').clone(), g(p + 'self_attn.in_proj_bias').clone()
+                Wi[:H] *= scale
+                bi[:H] *= scale
+                Wx, bx = g(p + 'multihead_attn.in_proj_weight'), g(p + 'multihead_attn.in_proj_bias')
+                t = dict(Wqkv_t=mat(Wi), bqkv=vec(bi),
+                         Wo_t=mat(g(p + 'self_attn.out_proj.weight')), bo=vec(g(p + 'self_attn.out_proj.bias')),
+                         Wq2_t=mat(Wx[:H] * scale), bq2=vec(bx[:H] * scale),
+                         Wo2_t=mat(g(p + 'multihead_attn.out_proj.weight')),
+                         bo2=vec(g(p + 'multihead_attn.out_proj.bias')),
+                         W1_t=mat(g(p + 'linear1.weight')), b1=vec(g(p + 'linear1.bias')),
+                         W2_t=mat(g(p + 'linear2.weight')), b2=vec(g(p + 'linear2.bias')),
+                         ln1_g=vec(g(p + 'norm1.weight')), ln1_b=vec(g(p + 'norm1.bias')),
+                         ln2_g=vec(g(p + 'norm2.weight')), ln2_b=vec(g(p + 'norm2.bias')),
+                         ln3_g=vec(g(p + 'norm3.weight')), ln3_b=vec(g(p + 'norm3.bias')))
+                self.keep.append(t)
+                lw = self.layers[i * 4 + l]
+                for k, v in t.items():
+                    setattr(lw, k, v.data_ptr())
+                kvw.append(Wx[H:].t())                            # [H][2H]: K cols then V cols
+                kvb.append(bx[H:])
+            self.kv_w.append(torch.cat(kvw, dim=1).contiguous())  # [H][Ln*2H]
+            self.kv_b.append(torch.cat(kvb).contiguous())
+        self.E = g('embedding.0.weight').contiguous()
+        self.pe = g('embedding.1.pe').contiguous()
+        self.lnN_g, self.lnN_b = vec(g('norm1.weight')), vec(g('norm1.bias'))
+        self.ln2_g, self.ln2_b = vec(g('norm2.weight')), vec(g('norm2.bias'))
+        self.Wqa_t = [mat(g(f'attns.{i}.linear_query.weight')) for i in range(2)]
+        self.bqa = [vec(g(f'attns.{i}.linear_query.bias')) for i in range(2)]
+        self.va = [g(f'attns.{i}.v.weight').reshape(-1).contiguous() for i in range(2)]
+        self.Uk_t = [g(f'attns.{i}.linear_key.weight').t().contiguous() for i in range(2)]   # fp32 [H][H]
+        self.Wg_t, self.bg = mat(g('gen.0.weight')), vec(g('gen.0.bias'))
+        self.Wv = g('gen.2.weight').contiguous().to(self.tdtype)                               # [V][H]
+        self.Wm, self.bm = g('mix.weight').contiguous(), vec(g('mix.bias'))
+
+
+class _SearchState:
+    """Buffers shared by both engines for the on-device greedy / beam bookkeeping."""
+
+    def __init__(self, dev, B, W, Tmax):
+        R, TL = B * W, Tmax + 1
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.tok = torch.zeros(R, TL, **i32)
+        self.anc = [torch.zeros(R, TL, **i32), torch.zeros(R, TL, **i32)]
+        self.live = torch.zeros(R, **i32)
+        self.cum = torch.zeros(R, dtype=torch.float64, device=dev)
+        self.length = torch.zeros(R, **i32)
+        self.parent = torch.zeros(R, **i32)
+        self.ended = torch.zeros(B, **i32)
+        self.best_key = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.best_len = torch.zeros(B, **i32)
+        self.out_tokens = torch.zeros(B, Tmax, **i32)
+        self.n_live = torch.zeros(1, **i32)
+        self.B, self.W, self.R, self.Tmax = B, W, R, Tmax
+        self._arange = torch.arange(R, **i32)
+        self._slot0 = (self._arange % W == 0).to(torch.int32)
+
+    def reset(self, bos=BOS):
+        self.tok.zero_()
+        self.tok[:, 0] = bos
+        self.anc[0].copy_(self._arange[:, None].expand_as(self.anc[0]))   # every row is its own history
+        self.anc[1].copy_(self.anc[0])
+        self.live.copy_(self._slot0)            # one root hypothesis per query (Generations.py:132-134)
+        self.cum.zero_()
+        self.length.fill_(1)
+        self.parent.copy_(self._arange)
+        self.ended.zero_()
+        self.best_key.fill_(float('inf'))
+        self.best_len.zero_()
+        self.out_tokens.zero_()
+        self.n_live.zero_()
+
+    def bind(self, a):
+        a.anc[0], a.anc[1] = self.anc[0].data_ptr(), self.anc[1].data_ptr()
+        for n in ('tok', 'live', 'cum', 'length', 'parent', 'ended', 'best_key', 'best_len', 'out_tokens', 'n_live'):
+            setattr(a, n, getattr(self, n).data_ptr())
+
+
+class _EngineBase:
+    def _run_steps(self, max_len: int):
+        stream = torch.cuda.current_stream(self.device)
+        for t in range(max_len):
+            L.check(self._step_fn(C.byref(self.args), t, stream.cuda_stream), self._step_name)
+
+    def _capture(self, max_len, mode):
+        """Capture all ``max_len`` steps into one CUDA graph (t is a by-value kernel argument)."""
+        stream = torch.cuda.current_stream(self.device)
+        L.check(self._step_fn(C.byref(self.args), 0, stream.cuda_stream), self._step_name)   # warm-up, not captured
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            cs = torch.cuda.current_stream(self.device)
+            for t in range(max_len):
+                L.check(self._step_fn(C.byref(self.args), t, cs.cuda_stream), self._step_name)
+        self._graphs[(max_len, mode)] = g
+
+    def _finish_tokens(self, max_len: int, mode: int) -> torch.Tensor:
+        st = self.state
+        out = st.out_tokens[:, :max_len].to(torch.int64)
+        if mode == L.MODE_BEAM:
+            # merge1D (Utils.py:366-377): pad to the longest answer of the batch
+            Lmax = int(st.best_len.max().item())
+            out = out[:, :max(Lmax, 1)]
+        return out
+
+
+class CaseDecodeEngine(_EngineBase):
+    """All buffers + the step argument block for one CaSE problem shape."""
+
+    def __init__(self, weights: CaseWeights, B: int, W: int, S0: int, S1: int, Tmax: int = 40,
+                 fast_tanh: Optional[bool] = None, vocab_impl: Optional[int] = None, target_ctas: int = 296):
+        if not (1 <= W <= L.MAX_W):
+            raise ValueError(f'beam width must be 1..{L.MAX_W}')
+        if not (1 <= Tmax <= L.MAX_T):
+            raise ValueError(f'max_target_length must be 1..{L.MAX_T}')
+        self.w = weights
+        self.device = dev = weights.device
+        self.B, self.W, self.R, self.S, self.Tmax, self.V = B, W, B * W, (S0, S1), Tmax, weights.V
+        R, V, H = self.R, self.V, L.H
+        self.ldv = -(-V // 8) * 8
+        td = weights.tdtype
+        self.fast_tanh = int(weights.cdtype == L.BF16 if fast_tanh is None else fast_tanh)
+        self.vocab_impl = int(0 if vocab_impl is None else vocab_impl)
+        f32 = dict(dtype=torch.float32, device=dev)
+        z = lambda *s: torch.zeros(*s, **f32)
+        self.nsx = [_nsplit(B * L.NH, s, L.XATTN_TILE, target_ctas) for s in self.S]
+        self.nsa = [_nsplit(B, s, L.AATTN_TILE, 2 * target_ctas) for s in self.S]
+        # per-batch tensors
+        self.feat = z(B, H)
+        self.Kx = [torch.zeros(B, L.NH, self.S[l // 4], L.HD, dtype=td, device=dev) for l in range(8)]
+        self.Vx = [torch.zeros(B, L.NH, self.S[l // 4], L.HD, dtype=td, device=dev) for l in range(8)]
+        self.U = [torch.zeros(B, s, H, dtype=td, device=dev) for s in self.S]
+        self.Mv = [torch.zeros(B, s, H, dtype=td, device=dev) for s in self.S]
+        self.mask = [torch.zeros(B, s, dtype=torch.uint8, device=dev) for s in self.S]
+        self.prior = [z(B, s) for s in self.S]
+        self.map = torch.zeros(B, S0 + S1, dtype=torch.int32, device=dev)
+        # state
+        self.kcache = [torch.zeros(R, Tmax, H, dtype=td, device=dev) for _ in range(8)]
+        self.vcache = [torch.zeros(R, Tmax, H, dtype=td, device=dev) for _ in range(8)]
+        self.state = _SearchState(dev, B, W, Tmax)
+        # scratch
+        nsx = max(self.nsx)
+        self.x_in, self.h, self.bbuf, self.q2 = z(R, H), z(R, H), z(R, H), z(R, H)
+        self.part_ml, self.part_acc = z(R, L.NH, nsx, 2), z(R, L.NH, nsx, L.HD)
+        self.qa = z(R, H)
+        self.attn_un = [z(R, s) for s in self.S]
+        self.stats = [z(R, n, 4) for n in self.nsa]
+        self.ctxp = [z(R, n, H) for n in self.nsa]
+        self.hN, self.ctx = z(R, H), [z(R, H), z(R, H)]
+        self.gates, self.fac, self.gfeat = z(R, 4), z(R, 2, L.MAX_SPLIT), z(R, H)
+        self.logits, self.dist = z(R, self.ldv), z(R, self.ldv)
+        self.top_vals = z(R, W)
+        self.top_idx = torch.zeros(R, W, dtype=torch.int32, device=dev)
+        self._graphs = {}
+        self._step_fn = L.load().case_decode_step
+        self._step_name = 'case_decode_step'
+        self._fill_args()
+
+    def _fill_args(self):
+        a = self.args = L.StepArgs()
+        w = self.w
+        a.B, a.W, a.R, a.V, a.ldv, a.Tmax = self.B, self.W, self.R, self.V, self.ldv, self.Tmax
+        a.dtype, a.fast_tanh, a.vocab_impl, a.mode = w.cdtype, self.fast_tanh, self.vocab_impl, L.MODE_MODULE_GREEDY
+        for i in range(2):
+            a.S[i], a.nsplit_x[i], a.nsplit_a[i] = self.S[i], self.nsx[i], self.nsa[i]
+            a.Wqa_t[i], a.bqa[i], a.va[i] = w.Wqa_t[i].data_ptr(), w.bqa[i].data_ptr(), w.va[i].data_ptr()
+            a.U[i], a.Mv[i] = self.U[i].data_ptr(), self.Mv[i].data_ptr()
+            a.mask[i], a.prior[i] = self.mask[i].data_ptr(), self.prior[i].data_ptr()
+            a.attn_un[i], a.stats[i], a.ctxp[i] = (self.attn_un[i].data_ptr(), self.stats[i].data_ptr(),
+                                                   self.ctxp[i].data_ptr())
+            a.ctx[i] = self.ctx[i].data_ptr()
+        a.map_off[0], a.map_off[1] = 0, self.S[0]
+        a.max_len, a.BOS, a.EOS, a.UNK, a.PAD, a.materialize_only = self.Tmax, BOS, EOS, UNK, PAD, 0
+        a.E, a.pe = w.E.data_ptr(), w.pe.data_ptr()
+        for l in range(8):
+            C.memmove(C.byref(a.layers[l]), C.byref(w.layers[l]), C.sizeof(L.LayerWeights))
+            a.Kx[l], a.Vx[l] = self.Kx[l].data_ptr(), self.Vx[l].data_ptr()
+            a.kcache[l], a.vcache[l] = self.kcache[l].data_ptr(), self.vcache[l].data_ptr()
+        a.lnN_g, a.lnN_b = w.lnN_g.data_ptr(), w.lnN_b.data_ptr()
+        a.Wg_t, a.bg, a.Wv, a.Wm, a.bm = (w.Wg_t.data_ptr(), w.bg.data_ptr(), w.Wv.data_ptr(), w.Wm.data_ptr(),
+                                          w.bm.data_ptr())
+        a.feat = self.feat.data_ptr()
+        a.map, a.map_ld = self.map.data_ptr(), self.map.size(1)
+        self.state.bind(a)
+        for n in ('x_in', 'h', 'bbuf', 'q2', 'part_ml', 'part_acc', 'qa', 'hN', 'gates', 'fac', 'gfeat', 'logits',
+                  'dist', 'top_vals', 'top_idx'):
+            setattr(a, n, getattr(self, n).data_ptr())
+
+    # ------------------------------------------------------------------ per batch
+    @torch.no_grad()
+    def prefill(self, mem_q, mem_p, mask_q, mask_p, prior_q, prior_p, answer_rep, source_map):
+        """Once per batch: flatten (Model.py:56-58), norm2(answer_rep) (:98), and everything the
+        reference recomputes every step although it never changes - the cross-attention K/V
+        projections of both memories for all 8 layers (TransformerDecoder.py:81) and Uk.mem
+        (BilinearAttention.py:34)."""
+        B, H, w, dev = self.B, L.H, self.w, self.device
+        mems = [mem_q.reshape(B, -1, H), mem_p.reshape(B, -1, H)]
+        masks = [mask_q.reshape(B, -1), mask_p.reshape(B, -1)]
+        priors = [prior_q.reshape(B, -1), prior_p.reshape(B, -1)]
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ar = answer_rep.to(dev, torch.float32).contiguous()
+        L.call('case_layernorm_rows', ar.data_ptr(), w.ln2_g.data_ptr(), w.ln2_b.data_ptr(), self.feat.data_ptr(),
+               B, stream)
+        for i in range(2):
+            S = self.S[i]
+            m = mems[i].to(dev, torch.float32)
+            if m.size(1) != S:
+                raise ValueError(f'memory {i} has {m.size(1)} positions, engine was built for {S}')
+            flat = m.reshape(B * S, H)
+            kv = torch.addmm(w.kv_b[i], flat, w.kv_w[i])                       # [B*S, 4*2*H]
+            kv = kv.view(B, S, 4, 2, L.NH, L.HD).permute(2, 3, 0, 4, 1, 5)     # [l][k/v][B][NH][S][HD]
+            for l in range(4):
+                self.Kx[i * 4 + l].copy_(kv[l, 0])
+                self.Vx[i * 4 + l].copy_(kv[l, 1])
+            self.U[i].copy_((flat @ w.Uk_t[i]).view(B, S, H))
+            self.Mv[i].copy_(m)
+            self.mask[i].copy_(masks[i].to(dev).to(torch.uint8))
+            self.prior[i].copy_(priors[i].to(dev, torch.float32))
+        self.map.copy_(source_map.to(dev).to(torch.int32))
+
+    @torch.no_grad()
+    def decode(self, max_len: int, mode: int = L.MODE_MODULE_GREEDY, use_graph: bool = True) -> torch.Tensor:
+        """Run ``max_len`` steps; returns int64 tokens [B, max_len] (beam: trimmed to the longest answer)."""
+        if max_len > self.Tmax:
+            raise ValueError('max_len exceeds the engine Tmax')
+        if mode != L.MODE_BEAM and self.W != 1:
+            raise ValueError('greedy modes need an engine built with W == 1')
+        self.args.mode, self.args.max_len, self.args.materialize_only = mode, max_len, 0
+        self.state.reset()
+        if use_graph and (max_len, mode) not in self._graphs:
+            self._capture(max_len, mode)
+            self.state.reset()
+        if use_graph:
+            self._graphs[(max_len, mode)].replay()
+        else:
+            self._run_steps(max_len)
+        return self._finish_tokens(max_len, mode)
+
+    @torch.no_grad()
+    def step_distribution(self, t: int) -> torch.Tensor:
+        """Protocol ``generate`` face: run step t up to the finished distribution and return a view
+        [R, V] of it (no top-k / select); the caller drives tok/anc through ``state``."""
+        self.args.materialize_only = 1
+        stream = torch.cuda.current_stream(self.device)
+        L.check(self._step_fn(C.byref(self.args), t, stream.cuda_stream), self._step_name)
+        self.args.materialize_only = 0
+        return self.dist[:, :self.V]
+
+    def kernel_launches_per_step(self) -> int:
+        # embed + 8 x (front, cross, back) + 2 x (row_linear, additive) + finalize + gen.0 + vocab + softmax
+        # + 2 scatter + topk + select (+1 memset node)
+        return 1 + 24 + 4 + 1 + 1 + 1 + 1 + 2 + 1 + 1
+
+
+class GttpWeights:
+    """Step-side GTTP weights (dec.*, gen.*; GTTP/Model.py:96-111, 8-9) laid out for the kernels."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], device=None, dtype: str = 'bf16', prefix: str = ''):
+        dev = _require_cuda(device)
+        self.device, self.dtype_name = dev, dtype
+        self.tdtype, self.cdtype = _storage(dtype)
+        g = lambda k: sd[prefix + k].detach().to(dev, torch.float32)
+        H = g('dec.gru.weight_hh_l0').size(1)
+        if H != L.H or g('dec.embedding.weight').size(1) != L.H:
+            raise ValueError(f'hidden and embedding size must be {L.H}')
+        self.V = g('gen.linear.weight').size(0)
+        mat = lambda w: w.t().contiguous().to(self.tdtype)
+        self.E = g('dec.embedding.weight').contiguous()
+        self.Wq_t = [mat(g(f'dec.{a}.linear_query.weight')) for a in ('src_attn', 'bg_attn')]
+        self.bq = [g(f'dec.{a}.linear_query.bias').contiguous() for a in ('src_attn', 'bg_attn')]
+        self.v = [g(f'dec.{a}.v.weight').reshape(-1).contiguous() for a in ('src_attn', 'bg_attn')]
+        self.Uk_t = [g(f'dec.{a}.linear_key.weight').t().contiguous() for a in ('src_attn', 'bg_attn')]  # [2H][H]
+        self.Wih_t, self.bih = mat(g('dec.gru.weight_ih_l0')), g('dec.gru.bias_ih_l0').contiguous()
+        self.Whh_t, self.bhh = mat(g('dec.gru.weight_hh_l0')), g('dec.gru.bias_hh_l0').contiguous()
+        self.Wr_t, self.br = mat(g('dec.readout.weight')), g('dec.readout.bias').contiguous()
+        self.Wv, self.bv = g('gen.linear.weight').contiguous().to(self.tdtype), g('gen.linear.bias').contiguous()
+        self.wc = g('gen.linear_copy.weight').reshape(-1).contiguous()
+        self.bc = g('gen.linear_copy.bias').reshape(-1).contiguous()
+
+
+class GttpDecodeEngine(_EngineBase):
+    def __init__(self, weights: GttpWeights, B: int, W: int, Lc: int, Lb: int, Tmax: int = 40,
+                 fast_tanh: Optional[bool] = None, vocab_impl: Optional[int] = None, target_ctas: int = 296):
+        if not (1 <= W <= L.MAX_W):
+            raise ValueError(f'beam width must be 1..{L.MAX_W}')
+        self.w = weights
+        self.device = dev = weights.device
+        self.B, self.W, self.R, self.Lc, self.Lb, self.Tmax, self.V = B, W, B * W, Lc, Lb, Tmax, weights.V
+        R, V, H = self.R, self.V, L.H
+        self.ldv = -(-V // 8) * 8
+        td = weights.tdtype
+        self.fast_tanh = int(weights.cdtype == L.BF16 if fast_tanh is None else fast_tanh)
+        self.vocab_impl = int(0 if vocab_impl is None else vocab_impl)
+        f32 = dict(dtype=torch.float32, device=dev)
+        z = lambda *s: torch.zeros(*s, **f32)
+        self.ns = [_nsplit(B, s, L.AATTN_TILE, 2 * target_ctas) for s in (Lc, Lb)]
+        self.U = [torch.zeros(B, s, H, dtype=td, device=dev) for s in (Lc, Lb)]
+        self.Mv = [torch.zeros(B, s, 2 * H, dtype=td, device=dev) for s in (Lc, Lb)]
+        self.mask = [torch.zeros(B, s, dtype=torch.uint8, device=dev) for s in (Lc, Lb)]
+        self.map = torch.zeros(B, Lb, dtype=torch.int32, device=dev)
+        self.gstate = [z(R, H), z(R, H)]
+        self.state = _SearchState(dev, B, W, Tmax)
+        self.emb, self.qa = z(R, H), z(R, H)
+        self.attn_un = [z(R, Lc), z(R, Lb)]
+        self.stats = [z(R, n, 4) for n in self.ns]
+        self.ctxp = [z(R, n, 2 * H) for n in self.ns]
+        self.ctx = [z(R, 2 * H), z(R, 2 * H)]
+        self.gi, self.gh, self.feat = z(R, 3 * H), z(R, 3 * H), z(R, H)
+        self.gates, self.fac = z(R, 4), z(R, L.MAX_SPLIT)
+        self.logits, self.dist = z(R, self.ldv), z(R, self.ldv)
+        self.top_vals = z(R, W)
+        self.top_idx = torch.zeros(R, W, dtype=torch.int32, device=dev)
+        self._graphs = {}
+        self._step_fn = L.load().gttp_decode_step
+        self._step_name = 'gttp_decode_step'
+        a = self.args = L.GttpStepArgs()
+        w = weights
+        a.B, a.W, a.R, a.V, a.ldv, a.dtype = B, W, R, V, self.ldv, w.cdtype
+        a.fast_tanh, a.vocab_impl, a.mode = self.fast_tanh, self.vocab_impl, L.MODE_PROTO_GREEDY
+        a.Lc, a.Lb, a.nsplit_c, a.nsplit_b = Lc, Lb, self.ns[0], self.ns[1]
+        a.max_len, a.BOS, a.EOS, a.UNK, a.PAD, a.materialize_only, a.Tmax = Tmax, BOS, EOS, UNK, PAD, 0, Tmax
+        a.E = w.E.data_ptr()
+        a.Wqs_t, a.bqs, a.vs = w.Wq_t[0].data_ptr(), w.bq[0].data_ptr(), w.v[0].data_ptr()
+        a.Wqb_t, a.bqb, a.vb = w.Wq_t[1].data_ptr(), w.bq[1].data_ptr(), w.v[1].data_ptr()
+        a.Wih_t, a.bih, a.Whh_t, a.bhh = w.Wih_t.data_ptr(), w.bih.data_ptr(), w.Whh_t.data_ptr(), w.bhh.data_ptr()
+        a.Wr_t, a.br = w.Wr_t.data_ptr(), w.br.data_ptr()
+        a.Wv, a.bv, a.wc, a.bc = w.Wv.data_ptr(), w.bv.data_ptr(), w.wc.data_ptr(), w.bc.data_ptr()
+        a.Us, a.Ms, a.Ub, a.Mb = self.U[0].data_ptr(), self.Mv[0].data_ptr(), self.U[1].data_ptr(), self.Mv[1].data_ptr()
+        a.mask_c, a.mask_b = self.mask[0].data_ptr(), self.mask[1].data_ptr()
+        a.map, a.map_ld = self.map.data_ptr(), Lb
+        a.state[0], a.state[1] = self.gstate[0].data_ptr(), self.gstate[1].data_ptr()
+        self.state.bind(a)
+        for i in range(2):
+            a.attn_un[i], a.stats[i], a.ctxp[i], a.ctx[i] = (self.attn_un[i].data_ptr(), self.stats[i].data_ptr(),
+                                                             self.ctxp[i].data_ptr(), self.ctx[i].data_ptr())
+        for n in ('emb', 'qa', 'gi', 'gh', 'feat', 'gates', 'fac', 'logits', 'dist', 'top_vals', 'top_idx'):
+            setattr(a, n, getattr(self, n).data_ptr())
+
+    @torch.no_grad()
+    def prefill(self, src_output, bg_output, context, background, background_map, init_state):
+        """Once per batch: Uk.memory for both attentions (BilinearAttention.py:34), value copies,
+        masks (GTTP/Model.py:177-178) and the initial GRU state (:170-174), replicated per beam slot."""
+        B, H, w, dev = self.B, L.H, self.w, self.device
+        for i, (m, ids) in enumerate(((src_output, context), (bg_output, background))):
+            m = m.to(dev, torch.float32)
+            S = m.size(1)
+            self.U[i].copy_((m.reshape(B * S, 2 * H) @ w.Uk_t[i]).view(B, S, H))
+            self.Mv[i].copy_(m)
+            self.mask[i].copy_(ids.to(dev).ne(0).to(torch.uint8))
+        self.map.copy_(background_map.to(dev).to(torch.int32))
+        st = init_state.to(dev, torch.float32).reshape(B, 1, H).expand(B, self.W, H).reshape(self.R, H)
+        self._init_state = st.contiguous()
+
+    @torch.no_grad()
+    def decode(self, max_len: int, mode: int = L.MODE_PROTO_GREEDY, use_graph: bool = True) -> torch.Tensor:
+        if max_len > self.Tmax:
+            raise ValueError('max_len exceeds the engine Tmax')
+        if mode != L.MODE_BEAM and self.W != 1:
+            raise ValueError('greedy modes need an engine built with W == 1')
+        self.args.mode, self.args.max_len, self.args.materialize_only = mode, max_len, 0
+        self._reset()
+        if use_graph and (max_len, mode) not in self._graphs:
+            self._capture(max_len, mode)
+            self._reset()
+        if use_graph:
+            self._graphs[(max_len, mode)].replay()
+        else:
+            self._run_steps(max_len)
+        return self._finish_tokens(max_len, mode)
+
+    def _reset(self):
+        self.state.reset()
+        self.gstate[0].copy_(self._init_state)
+        self.gstate[1].zero_()
+
+    def kernel_launches_per_step(self) -> int:
+        return 1 + 2 * 3 + 3 + 1 + 1 + 1 + 1 + 1 + 1 + 1

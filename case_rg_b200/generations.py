@@ -1,0 +1,135 @@
+"""Protocol face: ``greedy`` / ``beam`` with the signatures of common/Generations.py:66,112, and the
+models they drive.
+
+The reference drives an ``EncDecModel`` (GTTP/EncDecModel.py:11-42) from Python, one ``.item()``
+per hypothesis per step.  Here the whole search runs on the device; the functions below only hand
+the model's encoder outputs to an engine and return the same LongTensor the reference returns
+(``[B, max_len]`` for greedy; for beam the best hypothesis per query without BOS, EOS kept,
+zero-padded to the longest answer - ``merge1D``, common/Utils.py:366-377).
+
+``FastCaSE`` gives the unchanged CaSE decoder the protocol the reference never implemented for it
+(SURVEY.md §8c adapter); ``FastGTTP`` replaces ``GTTP.decode/generate/to_word`` + the search
+(GTTP/Model.py:176-193).  Both take the *encoder-side outputs* as inputs: the encoders are outside
+the hot path and stay on the reference's own code.
+"""
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+from .engine import CaseDecodeEngine, CaseWeights, GttpDecodeEngine, GttpWeights
+
+PAD_WORD, BOS_WORD, UNK_WORD, EOS_WORD = '[PAD]', '[unused0]', '[UNK]', '[unused1]'
+
+
+def _check_vocab(vocab2id):
+    if vocab2id is None:
+        return
+    want = {PAD_WORD: 0, BOS_WORD: 1, EOS_WORD: 2, UNK_WORD: 100}
+    for w, i in want.items():
+        if vocab2id.get(w, i) != i:
+            raise ValueError(f'special token {w} must have id {i} (BERT-uncased ids, common/Constants.py:1-7)')
+
+
+def greedy(model, data, vocab2id=None, max_len=20, encode_outputs=None, init_decoder_states=None):
+    """Generations.greedy (Generations.py:66-110) on the device."""
+    _check_vocab(vocab2id)
+    return model.fast_search(data, max_len, 1, L.MODE_PROTO_GREEDY, encode_outputs, init_decoder_states)
+
+
+def beam(model, data, vocab2id=None, max_len=20, width=5, encode_outputs=None, init_decoder_states=None):
+    """Generations.beam (Generations.py:112-190) on the device."""
+    _check_vocab(vocab2id)
+    return model.fast_search(data, max_len, width, L.MODE_BEAM, encode_outputs, init_decoder_states)
+
+
+class _FastModel:
+    beam_width = 1
+    max_dec_len = 40
+
+    def greedy(self, data):                       # EncDecModel.greedy / .beam (EncDecModel.py:38-42)
+        return greedy(self, data, None, self.max_dec_len)
+
+    def beam(self, data):
+        return beam(self, data, None, self.max_dec_len, self.beam_width)
+
+    def forward(self, data, method='test'):       # GTTP.forward test branch (GTTP/Model.py:204-212)
+        if method != 'test':
+            raise NotImplementedError('only the test-mode decode path is implemented on the device')
+        return {'answer': self.greedy(data) if self.beam_width == 1 else self.beam(data)}
+
+    __call__ = forward
+
+
+class FastCaSE(_FastModel):
+    """EncDecModel-protocol driver for the CaSE decoder.
+
+    ``data`` carries what ``ResponseGeneration.action`` hands the decoder (CaSE/Model.py:247-251):
+    'mem_q' [B,1,Lq,H], 'mem_p' [B,NP,Lp,H], 'query' / 'passage' ids (masks = ids != 0),
+    'prior_q', 'prior_p', 'answer_rep' [B,H], 'source_map' int64 [B,S]."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device=None, dtype='bf16', max_dec_len=40,
+                 beam_width=1, vocab_impl: Optional[int] = None, use_graph=True, prefix=''):
+        self.weights = CaseWeights(state_dict, device=device, dtype=dtype, prefix=prefix)
+        self.max_dec_len, self.beam_width, self.vocab_impl, self.use_graph = max_dec_len, beam_width, vocab_impl, use_graph
+        self._engines = {}
+
+    def engine_for(self, B, W, S0, S1, T):
+        key = (B, W, S0, S1, T)
+        if key not in self._engines:
+            if len(self._engines) >= 4:
+                self._engines.clear()
+            self._engines[key] = CaseDecodeEngine(self.weights, B, W, S0, S1, T, vocab_impl=self.vocab_impl)
+        return self._engines[key]
+
+    def encode(self, data):
+        return data
+
+    def fast_search(self, data, max_len, width, mode, encode_outputs=None, init_decoder_states=None):
+        d = encode_outputs if encode_outputs is not None else data
+        B = d['source_map'].size(0)
+        S0 = d['mem_q'].reshape(B, -1, L.H).size(1)
+        S1 = d['mem_p'].reshape(B, -1, L.H).size(1)
+        eng = self.engine_for(B, width, S0, S1, max_len)
+        eng.prefill(d['mem_q'], d['mem_p'], d['query'].ne(0), d['passage'].ne(0), d['prior_q'], d['prior_p'],
+                    d['answer_rep'], d['source_map'])
+        self.last_engine = eng
+        return eng.decode(max_len, mode, use_graph=self.use_graph)
+
+    def module_greedy(self, data, max_len):
+        """The in-module loop of CaSETransformerSeqDecoder.forward (no EOS handling, Model.py:91-123)."""
+        return self.fast_search(data, max_len, 1, L.MODE_MODULE_GREEDY)
+
+
+class FastGTTP(_FastModel):
+    """Step side of GTTP on the device.  ``data``: 'context' [B,Lc], 'background' [B,Lb],
+    'background_map' int64 [B,Lb] (index form, never one-hot), and the encoder outputs
+    'src_output' [B,Lc,2H], 'bg_output' [B,Lb,2H], 'init_state' [B,1,H] (GTTP/Model.py:156-174)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device=None, dtype='bf16', max_dec_len=40,
+                 beam_width=1, vocab_impl: Optional[int] = None, use_graph=True, prefix=''):
+        self.weights = GttpWeights(state_dict, device=device, dtype=dtype, prefix=prefix)
+        self.max_dec_len, self.beam_width, self.vocab_impl, self.use_graph = max_dec_len, beam_width, vocab_impl, use_graph
+        self._engines = {}
+
+    def engine_for(self, B, W, Lc, Lb, T):
+        key = (B, W, Lc, Lb, T)
+        if key not in self._engines:
+            if len(self._engines) >= 4:
+                self._engines.clear()
+            self._engines[key] = GttpDecodeEngine(self.weights, B, W, Lc, Lb, T, vocab_impl=self.vocab_impl)
+        return self._engines[key]
+
+    def fast_search(self, data, max_len, width, mode, encode_outputs=None, init_decoder_states=None):
+        d = dict(data)
+        if encode_outputs is not None:
+            d.update(encode_outputs)
+        if init_decoder_states is not None:
+            d['init_state'] = init_decoder_states
+        B, Lc = d['context'].shape
+        Lb = d['background'].size(1)
+        eng = self.engine_for(B, width, Lc, Lb, max_len)
+        eng.prefill(d['src_output'], d['bg_output'], d['context'], d['background'], d['background_map'],
+                    d['init_state'])
+        self.last_engine = eng
+        return eng.decode(max_len, mode, use_graph=self.use_graph)

@@ -1,0 +1,280 @@
+/*
+ * case_b200.h - C ABI of libcase_b200.so: the B200 (sm_100a) kernels behind the CaSE_RG
+ * answer-decode hot path.
+ *
+ * The reference (PengjieRen/CaSE_RG) is pure Python/PyTorch and has no FFI of its own; the
+ * drop-in boundary is the Python module face (CaSE/Model.py:50,125; GTTP/EncDecModel.py:11-42).
+ * This header is the layer *under* that face: what a maintainer binds (ctypes / cffi / a torch
+ * custom op) to replace the ATen calls of the reference's per-step decoder.  Each entry point
+ * names the reference code it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller; nothing here allocates or frees;
+ *  - launch-only: functions enqueue work on `stream` and return immediately (no sync);
+ *  - return value: 0 on success, otherwise a cudaError_t (or CASE_EINVAL for bad arguments);
+ *    case_last_error() gives a static message for the calling thread;
+ *  - `dtype` selects the storage type of caches and weight matrices: CASE_F32 or CASE_BF16.
+ *    Activations, softmax statistics and distributions are always fp32;
+ *  - hidden size is fixed at 256 with 8 heads of 32 (CaSE/Model.py:261-265, Run.py:71);
+ *  - rows: R = B * W, row r = b * W + w (query b, beam slot w).
+ */
+#ifndef CASE_B200_H
+#define CASE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CASE_H 256
+#define CASE_NH 8
+#define CASE_HD 32
+#define CASE_MAX_W 8
+#define CASE_MAX_T 128
+#define CASE_MAX_SPLIT 16
+
+#define CASE_F32 0
+#define CASE_BF16 1
+#define CASE_EINVAL 100001
+
+typedef void* case_stream_t; /* cudaStream_t */
+
+/* select modes (case_beam_select) */
+#define CASE_MODE_MODULE_GREEDY 0 /* CaSE/Model.py:119-122: argmax, no EOS handling          */
+#define CASE_MODE_PROTO_GREEDY 1  /* Generations.py:96-107: EOS->UNK at t0, PAD after the end */
+#define CASE_MODE_BEAM 2          /* Generations.py:136-185                                   */
+
+int case_abi_version(void);
+const char* case_last_error(void);
+/* sizeof() of the argument structs below, for binding self-checks: 0 case_seg_t, 1 case_rowlin_args_t,
+ * 2 case_layer_weights_t, 3 case_select_args_t, 4 case_step_args_t, 5 gttp_step_args_t */
+size_t case_struct_size(int which);
+
+/* ---------------------------------------------------------------- row-wise building blocks */
+
+/* x[r] = E[tok[r*tok_ld + t]] * sqrt(H) + pe[t]   (nn.Embedding + PositionalEmbedding,
+ * CaSE/Model.py:96, common/PositionalEmbedding.py:44-48).  pe == NULL -> plain gather * scale. */
+int case_embed_rows(const float* E, const float* pe, const int32_t* tok, int tok_ld, int t, float scale,
+                    float* x, int R, case_stream_t stream);
+
+/* y = LayerNorm(x) row-wise, eps 1e-5 (norm2(answer_rep), CaSE/Model.py:98). */
+int case_layernorm_rows(const float* x, const float* g, const float* b, float* y, int R, case_stream_t stream);
+
+/* Generic row linear: y[r,:] = act( cat_j seg_j[r / div_j] . Wt + bias ) + res[r,:]
+ * (nn.Linear call sites: BilinearAttention.py:31, Model.py:34, GTTP/Model.py:124-131).
+ * Wt is the weight TRANSPOSED to [K][N] (k-major) in `dtype`; K = sum of segment widths, K%8==0,
+ * N%256==0.  act: 0 none, 1 gelu(erf).  */
+typedef struct {
+  const float* p;
+  int32_t ld;
+  int32_t width;
+  int32_t div; /* row index = r / div (1 for per-row tensors, W for per-query tensors) */
+  int32_t gather; /* 0: none; 1: row index taken from gather_idx[r] (GTTP state under reorder) */
+} case_seg_t;
+
+typedef struct {
+  case_seg_t seg[4];
+  int32_t nseg;
+  int32_t K;
+  const void* Wt;
+  const float* bias;
+  int32_t N;
+  int32_t act;
+  const float* res;
+  int32_t ldres;
+  float* out;
+  int32_t ldo;
+  const int32_t* gather_idx;
+  int32_t R;
+  int32_t dtype;
+} case_rowlin_args_t;
+
+int case_row_linear(const case_rowlin_args_t* a, case_stream_t stream);
+
+/* ---------------------------------------------------------------- decoder layer (CaSE) */
+
+/* Weights of one TransformerDecoderLayer (common/TransformerDecoder.py:43-59), matrices
+ * transposed to [K][N] in `dtype`, vectors fp32.  Wq* and bq* are pre-multiplied by 1/sqrt(hd). */
+typedef struct {
+  const void* Wqkv_t; const float* bqkv;   /* self_attn.in_proj  [H][3H] */
+  const void* Wo_t;   const float* bo;     /* self_attn.out_proj [H][H]  */
+  const void* Wq2_t;  const float* bq2;    /* multihead_attn.in_proj[:H] */
+  const void* Wo2_t;  const float* bo2;    /* multihead_attn.out_proj    */
+  const void* W1_t;   const float* b1;     /* linear1 */
+  const void* W2_t;   const float* b2;     /* linear2 */
+  const float* ln1_g; const float* ln1_b;
+  const float* ln2_g; const float* ln2_b;
+  const float* ln3_g; const float* ln3_b;
+} case_layer_weights_t;
+
+/* First half of a layer for the newest position t of every row (TransformerDecoder.py:76-80):
+ *   a = LN1(h); qkv = a.Wqkv; K/V -> self cache at (row r, position t);
+ *   c = self-attention of q over positions 0..t of the row's ancestry (keys whose input token is
+ *       PAD are masked, Model.py:106); h1 = a + c.Wo; b = LN2(h1); q2 = b.Wq2 (pre-scaled)
+ * kcache/vcache: [R][Tmax][H] in dtype for this layer; anc: int32 [R][anc_ld] physical row that
+ * holds position j of row r's history; tok: int32 [R][tok_ld] input token of (physical row, pos). */
+int case_layer_front(const float* h, const case_layer_weights_t* w, void* kcache, void* vcache,
+                     const int32_t* anc, int anc_ld, const int32_t* tok, int tok_ld, int t, int Tmax,
+                     float* b_out, float* q2_out, int R, int dtype, case_stream_t stream);
+
+/* Cross-attention of q2 over one memory, flash-decoding style (TransformerDecoder.py:81, K4):
+ * Kmem/Vmem: [B][NH][S][HD] in dtype (projected once per query); mask: uint8 [B][S] 1 = valid key;
+ * the W rows of query b share every K/V tile.  Writes per-(row, head, split) partials:
+ * part_ml [R][NH][nsplit][2] (max, sum) and part_acc [R][NH][nsplit][HD]. */
+int case_cross_attn_partial(const float* q2, const void* Kmem, const void* Vmem, const uint8_t* mask,
+                            int B, int W, int S, int nsplit, float* part_ml, float* part_acc, int dtype,
+                            case_stream_t stream);
+
+/* Second half (TransformerDecoder.py:82-89): ctx = merge(partials); h2 = b + ctx.Wo2;
+ * c = LN3(h2); h_out = c + W2.gelu(W1.c). */
+int case_layer_back(const float* b_in, const float* part_ml, const float* part_acc, int nsplit,
+                    const case_layer_weights_t* w, float* h_out, int R, int dtype, case_stream_t stream);
+
+/* ---------------------------------------------------------------- additive ("bilinear") attention */
+
+/* Fused score + softmax-partials + context partials (BilinearAttention.py:24-60, K6-K8):
+ *   e[r,s] = v . tanh(qa[r] + U[b,s]),  masked where !mask[b,s] or !rowvalid[r]
+ * qa: [R][H] = Wq.query + b (from case_row_linear); U: [B][S][H] (= Uk.mem) and Mv: [B][S][DV]
+ * (values) in dtype; prior: fp32 [B][S] or NULL (CaSE/Model.py:110).  rowvalid: row r is valid iff
+ * tok[r*tok_ld + t] != 0 (tok == NULL -> all valid).
+ * Outputs: attn_un [R][S] = exp(e - m_split) (unnormalised), stats [R][nsplit][4] =
+ * (m, sum exp, sum prior*exp, 0), ctx_part [R][nsplit][DV].  fast_tanh: 1 = tanh.approx.f32. */
+int case_additive_attn(const float* qa, const void* U, const void* Mv, const float* v, const uint8_t* mask,
+                       const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S, int DV,
+                       int nsplit, float* attn_un, float* stats, float* ctx_part, int fast_tanh, int dtype,
+                       case_stream_t stream);
+
+/* CaSE row finaliser (Model.py:110-113, 39): hN = LN(h); merges both attentions' partials into
+ * ctx0/ctx1, computes the mixture gates softmax(Wm.[hN;ctx0;ctx1]+bm) and the per-split scale
+ * factors so that copy weight(r,i,s) = fac[r][i][split(s)] * prior_i[b,s] * attn_un_i[r,s]
+ * equals gate_{i+1} * p_i[r,s] of the reference.  gates: [R][4], fac: [R][2][CASE_MAX_SPLIT]. */
+int case_finalize_rows(const float* h, const float* lnN_g, const float* lnN_b, const float* stats0,
+                       const float* ctxp0, int nsplit0, const float* stats1, const float* ctxp1, int nsplit1,
+                       const float* Wm, const float* bm, float* hN, float* ctx0, float* ctx1, float* gates,
+                       float* fac, int R, case_stream_t stream);
+
+/* ---------------------------------------------------------------- vocabulary side */
+
+/* logits[R][ldl] = f[R][H] . Wv[V][H]^T (+ bias)   (gen.2, Model.py:34 / gen.linear GTTP/Model.py:8).
+ * impl: 0 = fp32 SIMT tile kernel (Wv in dtype); 1 = tcgen05 bf16 tensor-core kernel (Wv bf16). */
+int case_vocab_gemm(const float* f, const void* Wv, const float* bias, float* logits, int R, int V, int ldl,
+                    int dtype, int impl, case_stream_t stream);
+
+/* dist[r,v] = gates[r][0] * softmax(logits[r,:V])[v]; mask_col0 sets logit 0 to -inf first
+ * (GTTP/Model.py:26).  (Softmax of Model.py:34 fused with the first term of Model.py:41.) */
+int case_softmax_mix(const float* logits, int ldl, const float* gates, float* dist, int ldd, int R, int V,
+                     int mask_col0, case_stream_t stream);
+
+/* dist[r, map[b,s]] += fac[r][which][s / split_len] * prior[b,s] * attn_un[r,s]
+ * (replaces the one-hot bmm of Model.py:43 / GTTP Model.py:37-40 and build_map Utils.py:344-355;
+ * indices are used exactly as given, so targets are bit-exact).  prior may be NULL (=1). */
+int case_copy_scatter(const int32_t* map, int map_ld, int map_off, const float* prior, const float* attn_un,
+                      const float* fac, int fac_ld, int split_len, float* dist, int ldd, int B, int W, int S,
+                      int V, case_stream_t stream);
+
+/* Per-row top-k, values descending, ties -> lower index first (Utils.topk, Utils.py:156-168). */
+int case_topk_rows(const float* dist, int ldd, int R, int V, int k, float* vals, int32_t* idx,
+                   case_stream_t stream);
+
+/* ---------------------------------------------------------------- search bookkeeping */
+
+typedef struct {
+  int32_t mode, B, W, t, max_len, Tmax;
+  int32_t BOS, EOS, UNK, PAD;
+  const float* top_vals;   /* [R][W] */
+  const int32_t* top_idx;  /* [R][W] */
+  int32_t* live;           /* [R]  1 = slot holds a live hypothesis                      */
+  double* cum;             /* [R]  cumulative cost (Node.cum_cost, Generations.py:198)   */
+  int32_t* length;         /* [R]  node count incl. BOS (Node.length :199)               */
+  int32_t* tok;            /* [R][Tmax+1] input token of (physical row, position)        */
+  const int32_t* anc_in;   /* [R][Tmax+1]                                                */
+  int32_t* anc_out;        /* [R][Tmax+1]                                                */
+  int32_t* parent;         /* [R] physical parent row of the hypothesis now in slot r    */
+  int32_t* ended;          /* [B] proto-greedy: row has emitted EOS                      */
+  double* best_key;        /* [B] beam: best finished cum/length so far (+inf initially) */
+  int32_t* best_len;       /* [B] tokens in best_seq                                     */
+  int32_t* out_tokens;     /* [B][Tmax] greedy: per-step token; beam: best sequence      */
+  int32_t* n_live;         /* [1] number of live rows after this step (early-exit hint)  */
+} case_select_args_t;
+
+int case_beam_select(const case_select_args_t* a, case_stream_t stream);
+
+/* ---------------------------------------------------------------- GTTP step pieces */
+
+/* nn.GRU cell, gate order r,z,n (GTTP/Model.py:125): gi = x.Wih+bih, gh = h.Whh+bhh given. */
+int case_gru_cell(const float* gi, const float* gh, const float* h_prev, const int32_t* gather_idx,
+                  float* h_out, int R, case_stream_t stream);
+
+/* GTTP row finaliser: merges one attention's partials -> ctx [R][DV]; optionally the per-split
+ * factors fac[r][split] = exp(m_split - M) / Z (bg_attn, normalised) */
+int case_attn_merge(const float* stats, const float* ctx_part, int nsplit, int DV, float* ctx, float* fac,
+                    int fac_ld, int R, case_stream_t stream);
+
+/* p_copy = sigmoid(wc.f + bc); gates[r] = (1-p_copy, p_copy, 0, 0); fac[r][*] *= p_copy
+ * (GTTP/Model.py:31-41). */
+int case_gttp_gates(const float* f, const float* wc, const float* bc, float* gates, float* fac, int fac_ld,
+                    int nsplit, int R, case_stream_t stream);
+
+/* ---------------------------------------------------------------- whole-step orchestrators */
+
+typedef struct {
+  int32_t B, W, R, V, ldv, Tmax, dtype, fast_tanh, vocab_impl, mode;
+  int32_t S[2], nsplit_x[2], nsplit_a[2], map_off[2];
+  int32_t max_len, BOS, EOS, UNK, PAD, materialize_only;
+  /* weights */
+  const float* E; const float* pe;
+  case_layer_weights_t layers[8];       /* decs.{0,1}.layers.{0..3} */
+  const float* lnN_g; const float* lnN_b;            /* norm1 */
+  const void* Wqa_t[2]; const float* bqa[2]; const float* va[2];   /* attns.i.linear_query, v */
+  const void* Wg_t; const float* bg;                 /* gen.0 */
+  const void* Wv; const float* Wm; const float* bm;  /* gen.2 [V][H] row-major, mix */
+  /* per-batch (prefill) tensors */
+  const float* feat;                    /* [B][H] = norm2(answer_rep) */
+  const void* Kx[8]; const void* Vx[8]; /* [B][NH][S_i][HD] per layer */
+  const void* U[2]; const void* Mv[2];  /* [B][S_i][H] */
+  const uint8_t* mask[2]; const float* prior[2]; const int32_t* map; int32_t map_ld;
+  /* state */
+  void* kcache[8]; void* vcache[8];
+  int32_t* anc[2]; int32_t* tok; int32_t* live; double* cum; int32_t* length; int32_t* parent;
+  int32_t* ended; double* best_key; int32_t* best_len; int32_t* out_tokens; int32_t* n_live;
+  /* scratch (fp32 unless noted) */
+  float* x_in; float* h; float* bbuf; float* q2; float* part_ml; float* part_acc;
+  float* qa; float* attn_un[2]; float* stats[2]; float* ctxp[2]; float* hN; float* ctx[2];
+  float* gates; float* fac; float* gfeat; float* logits; float* dist; float* top_vals; int32_t* top_idx;
+} case_step_args_t;
+
+/* Enqueue one full decode step t (embedding .. select) for all R rows: the body of the eval loop
+ * CaSE/Model.py:94-122 for the newest position only, plus the search bookkeeping of
+ * Generations.py:136-185 when mode == CASE_MODE_BEAM.  materialize_only: stop after the
+ * distribution is complete (the `generate` face of the protocol). */
+int case_decode_step(const case_step_args_t* a, int t, case_stream_t stream);
+
+typedef struct {
+  int32_t B, W, R, V, ldv, dtype, fast_tanh, vocab_impl, mode;
+  int32_t Lc, Lb, nsplit_c, nsplit_b, max_len, BOS, EOS, UNK, PAD, materialize_only, Tmax;
+  const float* E;                                        /* dec.embedding [V][E=H] */
+  const void* Wqs_t; const float* bqs; const float* vs;  /* dec.src_attn  */
+  const void* Wqb_t; const float* bqb; const float* vb;  /* dec.bg_attn   */
+  const void* Wih_t; const float* bih; const void* Whh_t; const float* bhh;   /* dec.gru */
+  const void* Wr_t; const float* br;                     /* dec.readout */
+  const void* Wv; const float* bv; const float* wc; const float* bc;          /* gen.linear / linear_copy */
+  const void* Us; const void* Ms; const void* Ub; const void* Mb;  /* [B][L][H], [B][L][2H] */
+  const uint8_t* mask_c; const uint8_t* mask_b; const int32_t* map; int32_t map_ld;
+  float* state[2];                                       /* [R][H] double-buffered by step parity */
+  int32_t* anc[2]; int32_t* tok; int32_t* live; double* cum; int32_t* length; int32_t* parent;
+  int32_t* ended; double* best_key; int32_t* best_len; int32_t* out_tokens; int32_t* n_live;
+  float* emb; float* qa; float* attn_un[2]; float* stats[2]; float* ctxp[2]; float* ctx[2];
+  float* gi; float* gh; float* feat; float* gates; float* fac; float* logits; float* dist;
+  float* top_vals; int32_t* top_idx;
+} gttp_step_args_t;
+
+/* One GTTP decode step (GTTP/Model.py:176-193 -> BBCDecoder.forward :113-131 ->
+ * CopyGenerator.forward :14-43 -> topk) plus the same search bookkeeping. */
+int gttp_decode_step(const gttp_step_args_t* a, int t, case_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CASE_B200_H */

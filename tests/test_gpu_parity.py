@@ -1,0 +1,335 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libcase_b200.so) against the CPU oracle and
+the golden fixtures generated from the unmodified reference.  Run on the B200 box:
+    python -m pytest tests -m gpu -x -q
+
+Tolerances (north_star): fp32 storage - logits / distributions within 1e-4 relative, tokens and all
+indices identical; bf16 storage - within 2e-2 relative, tokens compared as agreement rates.
+"""
+import numpy as np
+import pytest
+import torch
+
+from case_rg_b200 import synthetic as syn
+from helpers import build_case, build_gttp, captured_inputs, load_golden, case_state_for, H
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def _case_data(inp, dev=DEV):
+    d = inp.to(dev)
+    return dict(mem_q=d.mem_q, mem_p=d.mem_p, query=d.query, passage=d.passage, prior_q=d.prior_q,
+                prior_p=d.prior_p, answer_rep=d.answer_rep, source_map=d.source_map)
+
+
+def _gttp_data(inp, dev=DEV):
+    d = inp.to(dev)
+    return dict(context=d.context, background=d.background, background_map=d.background_map,
+                src_output=d.src_output, bg_output=d.bg_output, init_state=d.init_state)
+
+
+def _teacher_force(model, inp, prefix, W=1):
+    """Drive the engine step by step on a given prefix; returns per-position dict of device tensors."""
+    from case_rg_b200 import _lib as L
+    B, n = prefix.shape
+    d = _case_data(inp)
+    S0, S1 = inp.mem_q.shape[1] * inp.mem_q.shape[2], inp.mem_p.shape[1] * inp.mem_p.shape[2]
+    eng = model.engine_for(B, 1, S0, S1, max(n, 2))
+    eng.prefill(d['mem_q'], d['mem_p'], d['query'].ne(0), d['passage'].ne(0), d['prior_q'], d['prior_p'],
+                d['answer_rep'], d['source_map'])
+    eng.state.reset()
+    outs = []
+    for t in range(n):
+        eng.state.tok[:, t] = prefix[:, t].to(DEV, torch.int32)
+        dist = eng.step_distribution(t)
+        torch.cuda.synchronize()
+        outs.append(dict(dist=dist.clone(), logits=eng.logits[:, :eng.V].clone(), hN=eng.hN.clone(),
+                         gates=eng.gates[:, :3].clone(), ctx0=eng.ctx[0].clone(), ctx1=eng.ctx[1].clone(),
+                         x_in=eng.x_in.clone(), gfeat=eng.gfeat.clone()))
+    return outs
+
+
+# --------------------------------------------------------------------------- fp32: golden + intermediates
+@pytest.mark.parametrize('name', ['case_module_greedy_xavier', 'case_module_greedy_peaked'])
+def test_fp32_step_intermediates_vs_oracle_and_golden(name):
+    from case_rg_b200.generations import FastCaSE
+    from oracle.case_decoder import CaseOracle
+    z, cfg, sd, inp = build_case(name)
+    T = int(cfg['T'])
+    model = FastCaSE(sd, device=DEV, dtype='fp32', use_graph=False)
+    B = inp.query.size(0)
+    prefix = torch.cat([torch.full((B, 1), syn.BOS), torch.from_numpy(z['tokens'])[:, :T - 1]], 1)
+    outs = _teacher_force(model, inp, prefix)
+    st = CaseOracle(sd).incremental(inp)
+    for t in range(T):
+        st.advance(torch.arange(B), prefix[:, t])
+        o, g = st.last, outs[t]
+        assert rel_err(g['x_in'], o['x_in']) < 1e-6, t
+        assert rel_err(g['hN'], o['dec_out']) < 1e-4, (t, rel_err(g['hN'], o['dec_out']))
+        assert rel_err(g['ctx0'], o['ctx'][0]) < 1e-4 and rel_err(g['ctx1'], o['ctx'][1]) < 1e-4, t
+        assert rel_err(g['gates'], o['gates']) < 1e-4, t
+        assert rel_err(g['gfeat'], o['gen_feat']) < 1e-4, t
+        assert rel_err(g['logits'], o['logits']) < 1e-4, (t, rel_err(g['logits'], o['logits']))
+        # against the reference's own numbers
+        gold = torch.from_numpy(z['dist'][:, t])
+        assert rel_err(g['dist'], gold) < 1e-4, (t, rel_err(g['dist'], gold))
+        np.testing.assert_allclose(g['dist'].cpu().numpy(), z['dist'][:, t], rtol=2e-3, atol=2e-6)
+        assert np.array_equal(g['dist'].argmax(1).cpu().numpy(), z['tokens'][:, t])
+        np.testing.assert_allclose(g['dist'].sum(1).cpu().numpy(), 1.0, atol=1e-5)
+
+
+def test_fp32_teacher_forced_pad_prefix():
+    from case_rg_b200.generations import FastCaSE
+    z, cfg, sd, inp = build_case('case_teacher_forced_pad')
+    model = FastCaSE(sd, device=DEV, dtype='fp32', use_graph=False)
+    prefix = torch.from_numpy(z['prefix'])
+    outs = _teacher_force(model, inp, prefix)
+    for j in range(prefix.size(1)):
+        gold = torch.from_numpy(z['dist'][:, j])
+        assert torch.isfinite(outs[j]['dist']).all()
+        assert rel_err(outs[j]['dist'], gold) < 1e-4, (j, rel_err(outs[j]['dist'], gold))
+    # PAD input -> both copy contexts are exactly zero for that row (Model.py:108)
+    assert float(outs[3]['ctx0'][0].abs().max()) == 0.0 and float(outs[3]['ctx1'][0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('use_graph', [False, True])
+@pytest.mark.parametrize('name', ['case_module_greedy_xavier', 'case_module_greedy_peaked'])
+def test_fp32_module_greedy_tokens(name, use_graph):
+    from case_rg_b200.generations import FastCaSE
+    z, cfg, sd, inp = build_case(name)
+    model = FastCaSE(sd, device=DEV, dtype='fp32', use_graph=use_graph)
+    toks = model.module_greedy(_case_data(inp), int(cfg['T']))
+    assert toks.dtype == torch.int64 and tuple(toks.shape) == z['tokens'].shape
+    assert np.array_equal(toks.cpu().numpy(), z['tokens'])
+    # second call re-uses engine and graph
+    toks2 = model.module_greedy(_case_data(inp), int(cfg['T']))
+    assert torch.equal(toks, toks2)
+
+
+def test_fp32_module_face_matches_model_forward_capture():
+    """FastCaSEDecoder.forward with the reference signature reproduces CaSE.forward(...)['answer']."""
+    from case_rg_b200.decoder import FastCaSEDecoder
+    z, cfg = load_golden('case_model_forward_capture')
+    sd = case_state_for('case_model_forward_capture', cfg)
+    inp = captured_inputs(z).to(DEV)
+    dec = FastCaSEDecoder.from_state_dict(sd, dtype='fp32').to(DEV).eval()
+    out = dec(inp.encode_memories, int(z['BOS']), int(z['UNK']), inp.source_map,
+              additional_decoder_feature=inp.answer_rep, encode_weights=inp.encode_weights,
+              encode_masks=[torch.from_numpy(z['mask_q']).to(DEV), torch.from_numpy(z['mask_p']).to(DEV)],
+              max_target_length=int(z['max_target_length']))
+    assert len(out) == 4
+    assert np.array_equal(out[3].cpu().numpy(), z['answer'])
+    # the dense one-hot form the reference passes is accepted too
+    oh = torch.zeros(inp.source_map.size(0), inp.source_map.size(1), 1000, device=DEV)
+    oh.scatter_(2, inp.source_map.unsqueeze(2), 1.0)
+    out2 = dec(inp.encode_memories, 1, 100, oh, additional_decoder_feature=inp.answer_rep,
+               encode_weights=inp.encode_weights, encode_masks=inp.encode_masks,
+               max_target_length=int(z['max_target_length']))
+    assert torch.equal(out[3], out2[3])
+    dec.train()
+    with pytest.raises(NotImplementedError):
+        dec(inp.encode_memories, 1, 100, inp.source_map, additional_decoder_feature=inp.answer_rep,
+            encode_weights=inp.encode_weights, encode_masks=inp.encode_masks, max_target_length=3)
+
+
+# --------------------------------------------------------------------------- Generations semantics
+def test_fp32_generations_over_case_golden():
+    from case_rg_b200 import generations as FG
+    z, cfg, sd, inp = build_case('case_generations')
+    T = int(cfg['T'])
+    model = FG.FastCaSE(sd, device=DEV, dtype='fp32')
+    vocab2id, _ = syn.make_vocab(1000)
+    data = _case_data(inp)
+    got = FG.greedy(model, data, vocab2id, T)
+    assert np.array_equal(got.cpu().numpy(), z['greedy']), (got.cpu().numpy(), z['greedy'])
+    for w in (1, 2, 4, 8):
+        got = FG.beam(model, data, vocab2id, T, w).cpu().numpy()
+        assert np.array_equal(got, z[f'beam{w}']), (w, got, z[f'beam{w}'])
+
+
+def test_fp32_generations_over_gttp_golden():
+    from case_rg_b200 import generations as FG
+    z, cfg, sd, inp = build_gttp()
+    T = int(cfg['T'])
+    model = FG.FastGTTP(sd, device=DEV, dtype='fp32', use_graph=False)
+    data = _gttp_data(inp)
+    # first-step distribution through the step engine
+    eng = model.engine_for(inp.context.size(0), 1, inp.context.size(1), inp.background.size(1), T)
+    eng.prefill(data['src_output'], data['bg_output'], data['context'], data['background'], data['background_map'],
+                data['init_state'])
+    eng._reset()
+    eng.args.materialize_only = 1
+    from case_rg_b200 import _lib as L
+    import ctypes as C
+    L.check(eng._step_fn(C.byref(eng.args), 0, torch.cuda.current_stream().cuda_stream), 'gttp step')
+    eng.args.materialize_only = 0
+    torch.cuda.synchronize()
+    assert rel_err(eng.feat, torch.from_numpy(z['feat0'])) < 1e-4
+    assert rel_err(eng.gstate[1], torch.from_numpy(z['state0'][:, 0])) < 1e-4
+    assert rel_err(eng.dist[:, :eng.V], torch.from_numpy(z['dist0'])) < 1e-4
+    got = FG.greedy(model, data, None, T)
+    assert np.array_equal(got.cpu().numpy(), z['greedy']), (got.cpu().numpy(), z['greedy'])
+    model_g = FG.FastGTTP(sd, device=DEV, dtype='fp32', use_graph=True)
+    for w in (1, 4, 8):
+        got = FG.beam(model_g, data, None, T, w).cpu().numpy()
+        assert np.array_equal(got, z[f'beam{w}']), (w, got, z[f'beam{w}'])
+
+
+# --------------------------------------------------------------------------- bigger shapes vs the oracle
+def _oracle_greedy_tokens(sd, inp, T):
+    from oracle.case_decoder import CaseOracle
+    st = CaseOracle(sd).incremental(inp)
+    B = inp.query.size(0)
+    par, tok = torch.arange(B), torch.full((B,), syn.BOS)
+    toks, dists = [], []
+    for _ in range(T):
+        d = st.advance(par, tok)
+        tok = d.argmax(1)
+        toks.append(tok)
+        dists.append(d)
+    return torch.stack(toks, 1), dists
+
+
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+def test_c1_shape_full_vocab_vs_oracle(dtype):
+    """BASELINE config 1 shape (B=8, Lq=60, 10x100, V=30522) for a few steps, peaked weights."""
+    from case_rg_b200.generations import FastCaSE
+    torch.set_num_threads(8)
+    V, B, T = syn.BERT_VOCAB, 8, 5
+    sd = syn.make_case_decoder_state(31, V, H, peaked=0.3, gen_gate_bias=2.0)
+    inp = syn.make_case_inputs(41, B, 60, 10, 100, V, H)
+    ref_toks, ref_dists = _oracle_greedy_tokens(sd, inp, T)
+    model = FastCaSE(sd, device=DEV, dtype=dtype, use_graph=False)
+    prefix = torch.cat([torch.full((B, 1), syn.BOS), ref_toks[:, :T - 1]], 1)
+    outs = _teacher_force(model, inp, prefix)
+    tol = 1e-4 if dtype == 'fp32' else 2e-2
+    agree = 0
+    for t in range(T):
+        e = rel_err(outs[t]['dist'], ref_dists[t])
+        assert e < tol, (dtype, t, e)
+        agree += int((outs[t]['dist'].argmax(1).cpu() == ref_toks[:, t]).sum())
+    if dtype == 'fp32':
+        assert agree == B * T
+        toks = model.module_greedy(_case_data(inp), T)
+        assert torch.equal(toks.cpu(), ref_toks)
+    else:
+        assert agree >= 0.9 * B * T, agree
+
+
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+def test_beam_vs_oracle_midsize(dtype):
+    """Beam 4 over a mid-size problem against the oracle's Generations restatement."""
+    from case_rg_b200 import generations as FG
+    from oracle import generations as OG
+    from oracle.case_decoder import CaseOracle
+    V, B, T, W = 5000, 6, 8, 4
+    sd = syn.make_case_decoder_state(32, V, H, peaked=0.3, boost={syn.EOS: 12.0}, gen_gate_bias=2.0)
+    inp = syn.make_case_inputs(42, B, 24, 4, 40, V, H)
+    want = OG.beam(CaseOracle(sd).incremental(inp), T, W)
+    model = FG.FastCaSE(sd, device=DEV, dtype=dtype)
+    got = FG.beam(model, _case_data(inp), None, T, W).cpu()
+    if dtype == 'fp32':
+        assert torch.equal(got, want), (got, want)
+    else:
+        L = min(got.size(1), want.size(1))
+        same = sum(int(torch.equal(got[i, :L], want[i, :L])) for i in range(B))
+        assert same >= B - 2, (got, want)
+
+
+# --------------------------------------------------------------------------- properties at BASELINE size
+def test_c2_properties_full_size():
+    """Config 2 (B=64, W=4, 10x256 passages, V=30522): size-independent properties."""
+    from case_rg_b200 import generations as FG
+    from case_rg_b200 import _lib as L
+    V, B, T, W = syn.BERT_VOCAB, 64, 6, 4
+    sd = syn.make_case_decoder_state(33, V, H)
+    inp = syn.make_case_inputs(43, B, 60, 10, 256, V, H)
+    data = _case_data(inp)
+    model = FG.FastCaSE(sd, device=DEV, dtype='bf16')
+    out = FG.beam(model, data, None, T, W)
+    assert out.shape[0] == B and out.shape[1] <= T and int(out.min()) >= 0 and int(out.max()) < V
+    eng = model.last_engine
+    torch.cuda.synchronize()
+    # 1. every live row's distribution sums to 1 (gates sum to 1; copy weights renormalised)
+    live = eng.state.live.bool()
+    sums = eng.dist[:, :V].sum(1)
+    assert torch.allclose(sums[live], torch.ones_like(sums[live]), atol=2e-3), sums[live]
+    # 2. determinism of the search (atomics only reorder fp32 adds; ties aside the tokens repeat)
+    out2 = FG.beam(model, data, None, T, W)
+    assert (out == out2).float().mean() > 0.99
+    # 3. beam width 1 == protocol greedy unless EOS shows up first (Generations.py:99-100)
+    g = FG.greedy(model, data, None, T)
+    b1 = FG.beam(model, data, None, T, 1)
+    rows = (g != syn.EOS).all(1).cpu() & (g[:, 0] != syn.UNK).cpu()
+    Lb = b1.size(1)
+    assert (g[rows][:, :Lb] == b1[rows]).float().mean() > 0.98
+    # 4. queries are independent: decoding a slice gives the same tokens as the full batch
+    sub = FG.FastCaSE(sd, device=DEV, dtype='bf16')
+    out_sub = FG.beam(sub, _case_data(inp.slice(8, 16)), None, T, W)
+    Ls = min(out_sub.size(1), out.size(1))
+    assert (out_sub[:, :Ls] == out[8:16, :Ls]).float().mean() > 0.97
+
+
+def test_scatter_linearity_and_exact_targets():
+    """copy-scatter: integer targets exact; result linear in the weights; equals dense one-hot bmm."""
+    from case_rg_b200 import _lib as L
+    B, W, S, V = 3, 2, 260, 777
+    ldd = 784
+    g = torch.Generator().manual_seed(7)
+    mp = torch.randint(0, V, (B, S), generator=g, dtype=torch.int32).to(DEV)
+    attn = torch.rand(B * W, S, generator=g).to(DEV)
+    prior = torch.rand(B, S, generator=g).to(DEV)
+    fac = torch.rand(B * W, L.MAX_SPLIT, generator=g).to(DEV)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run(a):
+        d = torch.zeros(B * W, ldd, device=DEV)
+        L.call('case_copy_scatter', mp.data_ptr(), S, 0, prior.data_ptr(), a.data_ptr(), fac.data_ptr(), L.MAX_SPLIT,
+               128, d.data_ptr(), ldd, B, W, S, V, st)
+        torch.cuda.synchronize()
+        return d[:, :V]
+    d1 = run(attn)
+    coef = fac[:, :3].repeat_interleave(128, dim=1)[:, :S] * prior.repeat_interleave(W, 0) * attn
+    oh = torch.zeros(B, S, V, device=DEV).scatter_(2, mp.long().unsqueeze(2), 1.0)
+    want = torch.bmm(coef.view(B, W, S), oh).view(B * W, V)
+    assert rel_err(d1, want) < 1e-5
+    touched = torch.zeros(B, V, dtype=torch.bool, device=DEV).scatter_(1, mp.long(), True).repeat_interleave(W, 0)
+    assert float(d1[~touched].abs().max()) == 0.0          # nothing lands off-target
+    d2 = run(attn * 2)
+    assert rel_err(d2, d1 * 2) < 1e-5
+
+
+def test_topk_matches_torch_with_ties():
+    from case_rg_b200 import _lib as L
+    R, V, ldd = 37, 30522, 30528
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(R, ldd, generator=g)
+    x[:, ::7] = 0.5                                        # many exact ties
+    x[3, 100] = x[3, 20000] = 2.0
+    xd = x.to(DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    for k in (1, 2, 4, 5, 8):
+        vals = torch.zeros(R, k, device=DEV)
+        idx = torch.zeros(R, k, dtype=torch.int32, device=DEV)
+        L.call('case_topk_rows', xd.data_ptr(), ldd, R, V, k, vals.data_ptr(), idx.data_ptr(), st)
+        torch.cuda.synchronize()
+        # reference order: value descending, index ascending
+        xs = x[:, :V].double()
+        key = xs - torch.arange(V).double() * 1e-12
+        want_idx = key.topk(k, dim=1).indices
+        assert torch.equal(idx.cpu().long(), want_idx), k
+        assert torch.equal(vals.cpu(), x[:, :V].gather(1, want_idx))
+    assert int(idx[3, 0]) == 100 and int(idx[3, 1]) == 20000
+
+
+def test_api_errors_are_loud():
+    from case_rg_b200 import _lib as L
+    with pytest.raises(RuntimeError):
+        L.call('case_topk_rows', None, 8, 1, 8, 1, None, None, None)
+    with pytest.raises(RuntimeError):
+        L.call('case_embed_rows', None, None, None, 1, 0, 1.0, None, 1, None)
