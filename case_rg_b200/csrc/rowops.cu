@@ -2,8 +2,7 @@
 // fused halves of a decoder layer, the row finalisers and the GRU cell.
 //
 // Everything here works on RB rows per CTA with the activations in shared memory and streams the
-// (L2-resident) weight matrices once per CTA.  Weight matrices are stored transposed, [K][N], so a
-// warp reads 32 x 4 consecutive outputs of one k - a fully coalesced 256/512 B request.
+// (L2-resident) weight matrices once per CTA through a bulk-async-copy ring (see WStream).
 #include "common.cuh"
 
 namespace cb {
@@ -12,36 +11,126 @@ constexpr int RB = 4;       // rows per CTA
 constexpr int NT = 256;     // threads per CTA (== one output tile of 256 columns)
 
 // ------------------------------------------------------------------------------------------
-// partial products of one 256-column tile: thread (kg = tid/64, n4 = tid%64) accumulates columns
-// n0 + 4*n4 .. +3 over its quarter of K for all RB rows, then parks them in red[kg][rb][col].
+// Weight streaming.  Every weight matrix is stored "n-tile major": [N/256][K][256] in T, so the
+// weights one CTA needs for a 256-column output tile are one contiguous run, cut into 16 KB tiles
+// of KT k-rows.  A single thread feeds a ring of NSTAGE shared-memory stages with 1-D bulk async
+// copies (cp.async.bulk -> UBLKCP, completion on an mbarrier); all 256 threads consume a tile, hit
+// one __syncthreads and the freed stage is re-armed for the tile NSTAGE ahead.  The stream runs
+// across the consecutive linears of a fused kernel, so the next matrix is already in flight while
+// LayerNorm / self-attention run.
+constexpr int TILE_BYTES = 16384;
+constexpr int NSTAGE = 6;
+template <typename T> struct KTile { static constexpr int KT = TILE_BYTES / (256 * (int)sizeof(T)); };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+struct WStream {
+  const char* base[3];
+  int end[3];          // cumulative tile counts of the (up to 3) weight matrices, in consumption order
+  int total;
+  uint64_t* full;      // [NSTAGE] mbarriers (shared)
+  char* stage;         // [NSTAGE][TILE_BYTES] (shared)
+  int g;               // next tile to consume (block-uniform)
+
+  __device__ __forceinline__ const char* src(int p) const {
+    int s = 0, first = 0;
+    if (p >= end[0]) { s = 1; first = end[0]; }
+    if (p >= end[1]) { s = 2; first = end[1]; }
+    return base[s] + (size_t)(p - first) * TILE_BYTES;
+  }
+  __device__ __forceinline__ void issue(int p) const {
+    const int s = p % NSTAGE;
+    mbar_expect_tx(&full[s], TILE_BYTES);
+    bulk_g2s(stage + (size_t)s * TILE_BYTES, src(p), TILE_BYTES, &full[s]);
+  }
+  // call once by all threads, before any consumption
+  __device__ __forceinline__ void start() {
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int p = 0; p < NSTAGE && p < total; ++p) issue(p);
+    g = 0;
+  }
+};
+
+__device__ __forceinline__ void lds4(const float* p, float (&o)[4]) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+__device__ __forceinline__ void lds4(const bf16* p, float (&o)[4]) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  o[0] = __uint_as_float(v.x << 16); o[1] = __uint_as_float(v.x & 0xffff0000u);
+  o[2] = __uint_as_float(v.y << 16); o[3] = __uint_as_float(v.y & 0xffff0000u);
+}
+
+// One 256-column output tile over K inputs for RB rows: consumes K/KT tiles of the stream.  Thread
+// (kg = tid/64, n4 = tid%64) owns columns 4*n4..+3 and a quarter of each tile's k-rows; the four
+// k-quarters are parked in red[kg][rb][col] for the caller to sum after a __syncthreads().
 template <typename T>
-__device__ __forceinline__ void rows_linear_tile(const float* __restrict__ xs, int ldx, int K,
-                                                 const T* __restrict__ Wt, int ldw, int n0,
-                                                 float* __restrict__ red) {
+__device__ __forceinline__ void rows_linear_stream(WStream& ws, const float* __restrict__ xs, int ldx, int K,
+                                                   float* __restrict__ red) {
+  constexpr int KT = KTile<T>::KT, KPT = KT / 4;
   const int tid = threadIdx.x, n4 = tid & 63, kg = tid >> 6;
-  const int kper = K >> 2, k0 = kg * kper;
   float acc[RB][4];
 #pragma unroll
   for (int rb = 0; rb < RB; ++rb)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[rb][j] = 0.f;
-  const T* wp = Wt + (size_t)k0 * ldw + n0 + n4 * 4;
-  const float* xp = xs + k0;
-  for (int k = 0; k < kper; k += 4) {
-    float w[4][4];
+  for (int kt = 0; kt < K / KT; ++kt) {
+    const int g = ws.g, s = g % NSTAGE;
+    const uint32_t par = (uint32_t)(g / NSTAGE) & 1u;
+    while (!mbar_try_wait(&ws.full[s], par)) {}
+    const T* wt = reinterpret_cast<const T*>(ws.stage + (size_t)s * TILE_BYTES) + (kg * KPT) * 256 + n4 * 4;
+    const float* xp = xs + kt * KT + kg * KPT;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) ld4(wp + (size_t)(k + u) * ldw, w[u]);
+    for (int kk = 0; kk < KPT; kk += 4) {
+      float w[4][4];
 #pragma unroll
-    for (int rb = 0; rb < RB; ++rb) {
-      const float4 xv = *reinterpret_cast<const float4*>(xp + rb * ldx + k);
+      for (int u = 0; u < 4; ++u) lds4(wt + (kk + u) * 256, w[u]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        acc[rb][j] = fmaf(xv.x, w[0][j], acc[rb][j]);
-        acc[rb][j] = fmaf(xv.y, w[1][j], acc[rb][j]);
-        acc[rb][j] = fmaf(xv.z, w[2][j], acc[rb][j]);
-        acc[rb][j] = fmaf(xv.w, w[3][j], acc[rb][j]);
+      for (int rb = 0; rb < RB; ++rb) {
+        const float4 xv = *reinterpret_cast<const float4*>(xp + rb * ldx + kk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[rb][j] = fmaf(xv.x, w[0][j], acc[rb][j]);
+          acc[rb][j] = fmaf(xv.y, w[1][j], acc[rb][j]);
+          acc[rb][j] = fmaf(xv.z, w[2][j], acc[rb][j]);
+          acc[rb][j] = fmaf(xv.w, w[3][j], acc[rb][j]);
+        }
       }
     }
+    __syncthreads();                                   // every thread is done reading stage s
+    if (tid == 0 && g + NSTAGE < ws.total) ws.issue(g + NSTAGE);
+    ws.g = g + 1;
   }
 #pragma unroll
   for (int rb = 0; rb < RB; ++rb)
@@ -108,13 +197,29 @@ __global__ void layernorm_rows_kernel(const float* __restrict__ x, const float* 
   }
 }
 
+// ------------------------------------------------------------------------------------------ shared memory plan
+// [ring: NSTAGE x 16 KB][mbarriers: 64 B][kernel-specific floats]
+constexpr int RING_BYTES = NSTAGE * TILE_BYTES + 64;
+
+__device__ __forceinline__ void stream_setup(WStream& ws, unsigned char* smem_raw) {
+  ws.stage = reinterpret_cast<char*>(smem_raw);
+  ws.full = reinterpret_cast<uint64_t*>(smem_raw + NSTAGE * TILE_BYTES);
+}
+
 // ------------------------------------------------------------------------------------------ generic
 template <typename T>
 __global__ __launch_bounds__(NT) void row_linear_kernel(case_rowlin_args_t a) {
-  extern __shared__ __align__(16) float smem[];
-  float* xs = smem;                 // [RB][K]
-  float* red = smem + RB * a.K;     // [4][RB][256]
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* xs = reinterpret_cast<float*>(smem_raw + RING_BYTES);   // [RB][K]
+  float* red = xs + RB * a.K;                                    // [4][RB][256]
   const int r0 = blockIdx.x * RB, n0 = blockIdx.y * 256, tid = threadIdx.x;
+  WStream ws;
+  stream_setup(ws, smem_raw);
+  ws.base[0] = ws.base[1] = ws.base[2] =
+      reinterpret_cast<const char*>(a.Wt) + (size_t)blockIdx.y * a.K * 256 * sizeof(T);
+  ws.total = a.K / KTile<T>::KT;
+  ws.end[0] = ws.end[1] = ws.end[2] = ws.total;
+  ws.start();
   int off = 0;
   for (int s = 0; s < a.nseg; ++s) {
     const case_seg_t sg = a.seg[s];
@@ -131,7 +236,7 @@ __global__ __launch_bounds__(NT) void row_linear_kernel(case_rowlin_args_t a) {
     off += sg.width;
   }
   __syncthreads();
-  rows_linear_tile<T>(xs, a.K, a.K, reinterpret_cast<const T*>(a.Wt), a.N, n0, red);
+  rows_linear_stream<T>(ws, xs, a.K, a.K, red);
   __syncthreads();
   const int n = n0 + tid;
   const float bias = a.bias ? __ldg(a.bias + n) : 0.f;
@@ -147,6 +252,9 @@ __global__ __launch_bounds__(NT) void row_linear_kernel(case_rowlin_args_t a) {
 }
 
 // ------------------------------------------------------------------------------------------ layer front
+constexpr int FRONT_FLOATS = RB * H + RB * 3 * H + RB * H + 4 * RB * 256 + (NT / 32) * CASE_MAX_T;
+constexpr int BACK_FLOATS = 3 * RB * H + 4 * RB * 256;
+
 template <typename T>
 __global__ __launch_bounds__(NT) void layer_front_kernel(const float* __restrict__ h, case_layer_weights_t w,
                                                          T* kc, T* vc,
@@ -154,13 +262,25 @@ __global__ __launch_bounds__(NT) void layer_front_kernel(const float* __restrict
                                                          const int32_t* __restrict__ tok, int tok_ld, int t,
                                                          int Tmax, float* __restrict__ b_out,
                                                          float* __restrict__ q2_out, int R) {
-  __shared__ __align__(16) float xs[RB][H];        // h -> a = LN1(h)
-  __shared__ __align__(16) float qkv[RB][3 * H];   // q | k | v, later h1 -> b in [:, :H]
-  __shared__ __align__(16) float cs[RB][H];        // self-attention context
-  __shared__ __align__(16) float red[4 * RB * 256];
-  __shared__ float sc[NT / 32][CASE_MAX_T];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* fl = reinterpret_cast<float*>(smem_raw + RING_BYTES);
+  float (*xs)[H] = reinterpret_cast<float (*)[H]>(fl);                          // h -> a = LN1(h)
+  float (*qkv)[3 * H] = reinterpret_cast<float (*)[3 * H]>(fl + RB * H);        // q | k | v, later h1 -> b
+  float (*cs)[H] = reinterpret_cast<float (*)[H]>(fl + RB * H + RB * 3 * H);    // self-attention context
+  float* red = fl + RB * H + RB * 3 * H + RB * H;
+  float (*sc)[CASE_MAX_T] = reinterpret_cast<float (*)[CASE_MAX_T]>(red + 4 * RB * 256);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r0 = blockIdx.x * RB;
+  constexpr int TPM = H / KTile<T>::KT;     // tiles per 256x256 matrix
+
+  WStream ws;
+  stream_setup(ws, smem_raw);
+  ws.base[0] = reinterpret_cast<const char*>(w.Wqkv_t);
+  ws.base[1] = reinterpret_cast<const char*>(w.Wo_t);
+  ws.base[2] = reinterpret_cast<const char*>(w.Wq2_t);
+  ws.end[0] = 3 * TPM; ws.end[1] = 4 * TPM; ws.end[2] = 5 * TPM;
+  ws.total = 5 * TPM;
+  ws.start();
 
   for (int i = tid; i < RB * H; i += NT) {
     const int rb = i / H, r = r0 + rb;
@@ -170,9 +290,8 @@ __global__ __launch_bounds__(NT) void layer_front_kernel(const float* __restrict
   ln_rows_smem(&xs[0][0], H, w.ln1_g, w.ln1_b);
   __syncthreads();
 
-  const T* Wqkv = reinterpret_cast<const T*>(w.Wqkv_t);
   for (int tile = 0; tile < 3; ++tile) {
-    rows_linear_tile<T>(&xs[0][0], H, H, Wqkv, 3 * H, tile * 256, red);
+    rows_linear_stream<T>(ws, &xs[0][0], H, H, red);
     __syncthreads();
     const float bias = __ldg(w.bqkv + tile * 256 + tid);
 #pragma unroll
@@ -233,7 +352,7 @@ __global__ __launch_bounds__(NT) void layer_front_kernel(const float* __restrict
   __syncthreads();
 
   // h1 = a + c.Wo + bo   (residual on the normalised tensor, TransformerDecoder.py:76-79)
-  rows_linear_tile<T>(&cs[0][0], H, H, reinterpret_cast<const T*>(w.Wo_t), H, 0, red);
+  rows_linear_stream<T>(ws, &cs[0][0], H, H, red);
   __syncthreads();
   {
     const float bias = __ldg(w.bo + tid);
@@ -243,7 +362,7 @@ __global__ __launch_bounds__(NT) void layer_front_kernel(const float* __restrict
   __syncthreads();
   ln_rows_smem(&qkv[0][0], 3 * H, w.ln2_g, w.ln2_b);
   __syncthreads();
-  rows_linear_tile<T>(&qkv[0][0], 3 * H, H, reinterpret_cast<const T*>(w.Wq2_t), H, 0, red);
+  rows_linear_stream<T>(ws, &qkv[0][0], 3 * H, H, red);
   __syncthreads();
   {
     const float bias = __ldg(w.bq2 + tid);
@@ -264,12 +383,25 @@ __global__ __launch_bounds__(NT) void layer_back_kernel(const float* __restrict_
                                                         const float* __restrict__ part_ml,
                                                         const float* __restrict__ part_acc, int nsplit,
                                                         case_layer_weights_t w, float* __restrict__ h_out, int R) {
-  __shared__ __align__(16) float bs[RB][H];
-  __shared__ __align__(16) float cs[RB][H];
-  __shared__ __align__(16) float ys[RB][H];
-  __shared__ __align__(16) float red[4 * RB * 256];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* fl = reinterpret_cast<float*>(smem_raw + RING_BYTES);
+  float (*bs)[H] = reinterpret_cast<float (*)[H]>(fl);
+  float (*cs)[H] = reinterpret_cast<float (*)[H]>(fl + RB * H);
+  float (*ys)[H] = reinterpret_cast<float (*)[H]>(fl + 2 * RB * H);
+  float* red = fl + 3 * RB * H;
   const int tid = threadIdx.x, r0 = blockIdx.x * RB;
   const int hh = tid / HD, d = tid % HD;
+  constexpr int TPM = H / KTile<T>::KT;
+
+  WStream ws;
+  stream_setup(ws, smem_raw);
+  ws.base[0] = reinterpret_cast<const char*>(w.Wo2_t);
+  ws.base[1] = reinterpret_cast<const char*>(w.W1_t);
+  ws.base[2] = reinterpret_cast<const char*>(w.W2_t);
+  ws.end[0] = TPM; ws.end[1] = 2 * TPM; ws.end[2] = 3 * TPM;
+  ws.total = 3 * TPM;
+  ws.start();
+
 #pragma unroll
   for (int rb = 0; rb < RB; ++rb) {
     const int r = r0 + rb;
@@ -292,7 +424,7 @@ __global__ __launch_bounds__(NT) void layer_back_kernel(const float* __restrict_
     cs[rb][tid] = c;
   }
   __syncthreads();
-  rows_linear_tile<T>(&cs[0][0], H, H, reinterpret_cast<const T*>(w.Wo2_t), H, 0, red);
+  rows_linear_stream<T>(ws, &cs[0][0], H, H, red);
   __syncthreads();
   {
     const float bias = __ldg(w.bo2 + tid);
@@ -302,7 +434,7 @@ __global__ __launch_bounds__(NT) void layer_back_kernel(const float* __restrict_
   __syncthreads();
   ln_rows_smem(&ys[0][0], H, w.ln3_g, w.ln3_b);
   __syncthreads();
-  rows_linear_tile<T>(&ys[0][0], H, H, reinterpret_cast<const T*>(w.W1_t), H, 0, red);
+  rows_linear_stream<T>(ws, &ys[0][0], H, H, red);
   __syncthreads();
   {
     const float bias = __ldg(w.b1 + tid);
@@ -310,7 +442,7 @@ __global__ __launch_bounds__(NT) void layer_back_kernel(const float* __restrict_
     for (int rb = 0; rb < RB; ++rb) cs[rb][tid] = gelu_erf(red_sum(red, rb, tid) + bias);
   }
   __syncthreads();
-  rows_linear_tile<T>(&cs[0][0], H, H, reinterpret_cast<const T*>(w.W2_t), H, 0, red);
+  rows_linear_stream<T>(ws, &cs[0][0], H, H, red);
   __syncthreads();
   {
     const float bias = __ldg(w.b2 + tid);
@@ -468,10 +600,16 @@ extern "C" int case_row_linear(const case_rowlin_args_t* a, case_stream_t stream
     CB_REQUIRE(!a->seg[s].gather || a->gather_idx, "case_row_linear: gather without gather_idx");
     K += a->seg[s].width;
   }
-  CB_REQUIRE(K == a->K && K % 16 == 0 && K <= 2048, "case_row_linear: K must equal the segment widths, %16, <=2048");
+  CB_REQUIRE(K == a->K && K % 32 == 0 && K <= 2048, "case_row_linear: K must equal the segment widths, %32, <=2048");
   CB_REQUIRE(a->N % 256 == 0 && a->N > 0, "case_row_linear: N must be a multiple of 256");
-  const size_t smem = (size_t)(RB * a->K + 4 * RB * 256) * sizeof(float);
+  const size_t smem = RING_BYTES + (size_t)(RB * a->K + 4 * RB * 256) * sizeof(float);
   dim3 grid((a->R + RB - 1) / RB, a->N / 256);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(row_linear_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(row_linear_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
   if (a->dtype == CASE_BF16) {
     row_linear_kernel<bf16><<<grid, NT, smem, (cudaStream_t)stream>>>(*a);
   } else {
@@ -486,11 +624,18 @@ extern "C" int case_layer_front(const float* h, const case_layer_weights_t* w, v
   CB_REQUIRE(h && w && kcache && vcache && anc && tok && b_out && q2_out && R > 0, "case_layer_front: null pointer");
   CB_REQUIRE(t >= 0 && t < Tmax && Tmax <= CASE_MAX_T, "case_layer_front: t / Tmax out of range");
   const int grid = (R + RB - 1) / RB;
+  const size_t smem = RING_BYTES + (size_t)FRONT_FLOATS * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(layer_front_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(layer_front_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
   if (dtype == CASE_BF16)
-    layer_front_kernel<bf16><<<grid, NT, 0, (cudaStream_t)stream>>>(h, *w, (bf16*)kcache, (bf16*)vcache, anc, anc_ld,
+    layer_front_kernel<bf16><<<grid, NT, smem, (cudaStream_t)stream>>>(h, *w, (bf16*)kcache, (bf16*)vcache, anc, anc_ld,
                                                                      tok, tok_ld, t, Tmax, b_out, q2_out, R);
   else
-    layer_front_kernel<float><<<grid, NT, 0, (cudaStream_t)stream>>>(h, *w, (float*)kcache, (float*)vcache, anc,
+    layer_front_kernel<float><<<grid, NT, smem, (cudaStream_t)stream>>>(h, *w, (float*)kcache, (float*)vcache, anc,
                                                                       anc_ld, tok, tok_ld, t, Tmax, b_out, q2_out, R);
   return check_launch("case_layer_front");
 }
@@ -501,10 +646,17 @@ extern "C" int case_layer_back(const float* b_in, const float* part_ml, const fl
   CB_REQUIRE(b_in && part_ml && part_acc && w && h_out && R > 0, "case_layer_back: null pointer");
   CB_REQUIRE(nsplit >= 1 && nsplit <= CASE_MAX_SPLIT, "case_layer_back: nsplit out of range");
   const int grid = (R + RB - 1) / RB;
+  const size_t smem = RING_BYTES + (size_t)BACK_FLOATS * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(layer_back_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(layer_back_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
   if (dtype == CASE_BF16)
-    layer_back_kernel<bf16><<<grid, NT, 0, (cudaStream_t)stream>>>(b_in, part_ml, part_acc, nsplit, *w, h_out, R);
+    layer_back_kernel<bf16><<<grid, NT, smem, (cudaStream_t)stream>>>(b_in, part_ml, part_acc, nsplit, *w, h_out, R);
   else
-    layer_back_kernel<float><<<grid, NT, 0, (cudaStream_t)stream>>>(b_in, part_ml, part_acc, nsplit, *w, h_out, R);
+    layer_back_kernel<float><<<grid, NT, smem, (cudaStream_t)stream>>>(b_in, part_ml, part_acc, nsplit, *w, h_out, R);
   return check_launch("case_layer_back");
 }
 

@@ -42,6 +42,15 @@ def _nsplit(units_per_split_group: int, S: int, tile: int, target_ctas: int) -> 
     return int(max(1, min(n, L.MAX_SPLIT, -(-S // tile))))
 
 
+def pack_tiled(w: torch.Tensor, dtype) -> torch.Tensor:
+    """nn.Linear weight [N, K] -> the kernels' streaming layout [N/256][K][256] (n-tile major): the
+    weights one CTA needs for 256 output columns are one contiguous run of 16 KB tiles."""
+    N, K = w.shape
+    if N % 256 or K % 32:
+        raise ValueError(f'weight {tuple(w.shape)}: N must be a multiple of 256 and K of 32')
+    return w.t().reshape(K, N // 256, 256).permute(1, 0, 2).contiguous().to(dtype)
+
+
 def split_chunk(S, nsplit, tile=128):
     c = -(-S // nsplit)
     return -(-c // tile) * tile
@@ -50,7 +59,7 @@ def split_chunk(S, nsplit, tile=128):
 class CaseWeights:
     """Weights of CaSETransformerSeqDecoder re-laid-out for the kernels (CaSE/Model.py:14-36 names).
 
-    Matrices are transposed to [K][N] in the storage dtype; the 1/sqrt(hd) attention scale is
+    Matrices are re-tiled to [N/256][K][256] in the storage dtype; the 1/sqrt(hd) attention scale is
     folded into the query projections; cross-attention K/V and attns.*.linear_key weights are kept
     fp32 [K][N] for the per-batch prefill GEMMs."""
 
@@ -68,7 +77,7 @@ class CaseWeights:
         if self.M != 2 or self.Ln != 4:
             raise ValueError('the fused step is built for num_memories=2, num_layers=4 (CaSE/Model.py:265)')
         scale = math.sqrt(1.0 / L.HD)
-        mat = lambda w: w.t().contiguous().to(self.tdtype)        # [N,K] -> [K][N]
+        mat = lambda w: pack_tiled(w, self.tdtype)
         vec = lambda b: b.contiguous()
         self.keep = []            # keeps every tensor alive
         self.layers = (L.LayerWeights * 8)()
@@ -342,7 +351,7 @@ class GttpWeights:
         if H != L.H or g('dec.embedding.weight').size(1) != L.H:
             raise ValueError(f'hidden and embedding size must be {L.H}')
         self.V = g('gen.linear.weight').size(0)
-        mat = lambda w: w.t().contiguous().to(self.tdtype)
+        mat = lambda w: pack_tiled(w, self.tdtype)
         self.E = g('dec.embedding.weight').contiguous()
         self.Wq_t = [mat(g(f'dec.{a}.linear_query.weight')) for a in ('src_attn', 'bg_attn')]
         self.bq = [g(f'dec.{a}.linear_query.bias').contiguous() for a in ('src_attn', 'bg_attn')]

@@ -64,8 +64,9 @@ int case_layernorm_rows(const float* x, const float* g, const float* b, float* y
 
 /* Generic row linear: y[r,:] = act( cat_j seg_j[r / div_j] . Wt + bias ) + res[r,:]
  * (nn.Linear call sites: BilinearAttention.py:31, Model.py:34, GTTP/Model.py:124-131).
- * Wt is the weight TRANSPOSED to [K][N] (k-major) in `dtype`; K = sum of segment widths, K%8==0,
- * N%256==0.  act: 0 none, 1 gelu(erf).  */
+ * Wt is the nn.Linear weight [N][K] re-tiled to [N/256][K][256] ("n-tile major") in `dtype`, so the
+ * 256 output columns one CTA produces read one contiguous run that is streamed as 16 KB tiles;
+ * K = sum of segment widths, K%32==0, N%256==0.  act: 0 none, 1 gelu(erf).  */
 typedef struct {
   const float* p;
   int32_t ld;
@@ -95,8 +96,9 @@ int case_row_linear(const case_rowlin_args_t* a, case_stream_t stream);
 
 /* ---------------------------------------------------------------- decoder layer (CaSE) */
 
-/* Weights of one TransformerDecoderLayer (common/TransformerDecoder.py:43-59), matrices
- * transposed to [K][N] in `dtype`, vectors fp32.  Wq* and bq* are pre-multiplied by 1/sqrt(hd). */
+/* Weights of one TransformerDecoderLayer (common/TransformerDecoder.py:43-59), matrices re-tiled
+ * to [N/256][K][256] in `dtype` (see case_row_linear), vectors fp32.  Wq* and bq* are pre-multiplied
+ * by 1/sqrt(hd). */
 typedef struct {
   const void* Wqkv_t; const float* bqkv;   /* self_attn.in_proj  [H][3H] */
   const void* Wo_t;   const float* bo;     /* self_attn.out_proj [H][H]  */
