@@ -311,9 +311,14 @@ def roofline(model, eng, args, torch):
     st = torch.cuda.current_stream()
     reps = 20
     def launch(l):
-        L.call('case_cross_attn_partial', eng.q2.data_ptr(), eng.Kx[l].data_ptr(), eng.Vx[l].data_ptr(),
-               eng.mask[1].data_ptr(), B, W, S1, eng.nsx[1], eng.part_ml.data_ptr(), eng.part_acc.data_ptr(),
-               eng.w.cdtype, st.cuda_stream)
+        if eng.w.cdtype == L.BF16:
+            L.call('case_cross_attn_partial_tc', eng.q2.data_ptr(), eng.Kx[l].data_ptr(), eng.Vx[l].data_ptr(),
+                   eng.mask[1].data_ptr(), B, W, S1, eng.nsx[1], eng.part_ml.data_ptr(), eng.part_acc.data_ptr(),
+                   st.cuda_stream)
+        else:
+            L.call('case_cross_attn_partial', eng.q2.data_ptr(), eng.Kx[l].data_ptr(), eng.Vx[l].data_ptr(),
+                   eng.mask[1].data_ptr(), B, W, S1, eng.nsx[1], eng.part_ml.data_ptr(), eng.part_acc.data_ptr(),
+                   eng.w.cdtype, st.cuda_stream)
     for l in range(4, 8):
         launch(l)
     torch.cuda.synchronize()
@@ -326,7 +331,7 @@ def roofline(model, eng, args, torch):
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / (reps * 4)
     ach = alg / (us * 1e-6) / 1e9
-    return dict(kernel='cross_attn_partial (passage memory)', bound='hbm', achieved=ach, peak=peak, unit='GB/s',
+    return dict(kernel='cross_attn_mma_kernel (passage memory)' if eng.w.cdtype == L.BF16 else 'cross_attn_partial_kernel (passage memory)', bound='hbm', achieved=ach, peak=peak, unit='GB/s',
                 frac=ach / peak, traffic=None, peak_source=which, algorithmic_bytes_per_launch=alg,
                 us_per_launch=us, launches_per_decode_step=4)
 

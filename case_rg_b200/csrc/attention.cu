@@ -393,3 +393,169 @@ extern "C" int case_additive_attn(const float* qa, const void* U, const void* Mv
   if (fast_tanh) return dispatch_additive_w<float, true>(W, qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, S, DV, nsplit, attn_un, stats, ctx_part, st);
   return dispatch_additive_w<float, false>(W, qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, S, DV, nsplit, attn_un, stats, ctx_part, st);
 }
+
+// =============================================================================== tensor-core cross attention
+// bf16 K/V only.  FlashAttention-2 style decode step on mma.sync.m16n8k16 tiles: the W (<= 8) beam rows
+// of one query are the M rows 0..7 of the tile (rows 8..15 are zero padding), so one pass over a
+// head's K/V serves every beam.  Each warp owns a strided set of 64-key tiles with its own cp.async
+// double buffer and its own running (max, sum, acc); warps never synchronise with each other and
+// each writes its own partial, merged later by case_layer_back.  HBM traffic = K and V once.
+namespace cb {
+
+constexpr int XM_WARPS = 4;
+constexpr int XM_TILE = 32;                       // keys per warp tile
+constexpr int XM_TILE_BYTES = XM_TILE * HD * 2;   // 2 KB for K, same for V
+constexpr int XM_SMEM = XM_WARPS * 2 * 2 * XM_TILE_BYTES;
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// byte offset of (key row, 16-byte chunk) inside a [64][32] bf16 tile, XOR-swizzled so that both the
+// row-wise (K) and transposed (V) ldmatrix reads are bank-conflict free
+__device__ __forceinline__ uint32_t xm_swz(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
+
+__global__ __launch_bounds__(XM_WARPS * 32) void cross_attn_mma_kernel(
+    const float* __restrict__ q2, const bf16* __restrict__ Kmem, const bf16* __restrict__ Vmem,
+    const uint8_t* __restrict__ mask, int W, int S, int nsplit, float* __restrict__ part_ml,
+    float* __restrict__ part_acc) {
+  extern __shared__ __align__(128) unsigned char xm_smem[];   // [warp][stage][K|V][XM_TILE_BYTES]
+  const int b = blockIdx.x, hh = blockIdx.y, sp = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int chunk = split_chunk(S, nsplit, XM_TILE * XM_WARPS);
+  const int s_begin = sp * chunk, s_end = min(S, s_begin + chunk);
+  const bf16* Kb = Kmem + ((size_t)(b * NH + hh)) * S * HD;
+  const bf16* Vb = Vmem + ((size_t)(b * NH + hh)) * S * HD;
+  const uint8_t* mb = mask + (size_t)b * S;
+
+  // Q fragments (A operand), rows >= W are zero
+  uint32_t qa[2][2];
+  {
+    const float* qp = q2 + ((size_t)(b * W + (g < W ? g : 0))) * H + hh * HD;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const float2 lo = *reinterpret_cast<const float2*>(qp + ks * 16 + 2 * t);
+      const float2 hi = *reinterpret_cast<const float2*>(qp + ks * 16 + 8 + 2 * t);
+      qa[ks][0] = g < W ? pack_bf16(lo.x, lo.y) : 0u;
+      qa[ks][1] = g < W ? pack_bf16(hi.x, hi.y) : 0u;
+    }
+  }
+  float m = -INFINITY, l = 0.f;
+  float o[4][4];
+#pragma unroll
+  for (int nb = 0; nb < 4; ++nb) { o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f; }
+
+  const uint32_t sbase = smem_u32(xm_smem + (size_t)warp * 4 * XM_TILE_BYTES);
+  auto load_tile = [&](int tile_s0, int stage) {
+    const uint32_t kdst = sbase + stage * 2 * XM_TILE_BYTES, vdst = kdst + XM_TILE_BYTES;
+#pragma unroll
+    for (int i = 0; i < XM_TILE / 8; ++i) {
+      const int ci = lane + 32 * i, row = ci >> 2, ch = ci & 3;
+      const int s = tile_s0 + row;
+      const int nbytes = s < s_end ? 16 : 0;                 // zero-fill rows past the range
+      const size_t goff = (size_t)(s < s_end ? s : s_begin) * HD + ch * 8;
+      cp_async16(kdst + xm_swz(row, ch), Kb + goff, nbytes);
+      cp_async16(vdst + xm_swz(row, ch), Vb + goff, nbytes);
+    }
+    cp_async_commit();
+  };
+
+  int tile_s0 = s_begin + warp * XM_TILE;
+  const int stride = XM_WARPS * XM_TILE;
+  int stage = 0;
+  if (tile_s0 < s_end) load_tile(tile_s0, 0);
+  for (; tile_s0 < s_end; tile_s0 += stride, stage ^= 1) {
+    const int next = tile_s0 + stride;
+    if (next < s_end) { load_tile(next, stage ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncwarp();
+    const uint32_t kt = sbase + stage * 2 * XM_TILE_BYTES, vt = kt + XM_TILE_BYTES;
+    // ---- S = Q K^T for 8 key blocks of 8
+    float sc[XM_TILE / 8][2];
+    float tmax = -INFINITY;
+#pragma unroll
+    for (int kb = 0; kb < XM_TILE / 8; ++kb) {
+      uint32_t kf[4];
+      ldsm_x4(kf, kt + xm_swz(kb * 8 + (lane & 7), lane >> 3));
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_bf16_16816(c, qa[0][0], 0u, qa[0][1], 0u, kf[0], kf[1]);
+      mma_bf16_16816(c, qa[1][0], 0u, qa[1][1], 0u, kf[2], kf[3]);
+      const int s = tile_s0 + kb * 8 + 2 * t;
+      const bool v0 = s < s_end && mb[min(s, S - 1)] != 0;
+      const bool v1 = s + 1 < s_end && mb[min(s + 1, S - 1)] != 0;
+      sc[kb][0] = v0 ? c[0] : -INFINITY;
+      sc[kb][1] = v1 ? c[1] : -INFINITY;
+      tmax = fmaxf(tmax, fmaxf(sc[kb][0], sc[kb][1]));
+    }
+    tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
+    tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 2));
+    const float mn = fmaxf(m, tmax);
+    const float scale = (m == -INFINITY) ? 0.f : fexp(m - mn);
+    m = mn;
+    l *= scale;
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) { o[nb][0] *= scale; o[nb][1] *= scale; }
+    // ---- P (bf16) and O += P V, 16 keys at a time
+#pragma unroll
+    for (int kk = 0; kk < XM_TILE / 16; ++kk) {
+      float p[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float s = sc[2 * kk + (u >> 1)][u & 1];
+        p[u] = (s == -INFINITY) ? 0.f : fexp(s - mn);
+        l += p[u];
+      }
+      const uint32_t pa0 = pack_bf16(p[0], p[1]), pa2 = pack_bf16(p[2], p[3]);
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        uint32_t vf[4];
+        const int mi = lane >> 3;
+        ldsm_x4_t(vf, vt + xm_swz(kk * 16 + (mi & 1) * 8 + (lane & 7), c2 * 2 + (mi >> 1)));
+        mma_bf16_16816(o[c2 * 2], pa0, 0u, pa2, 0u, vf[0], vf[1]);
+        mma_bf16_16816(o[c2 * 2 + 1], pa0, 0u, pa2, 0u, vf[2], vf[3]);
+      }
+    }
+    __syncwarp();
+  }
+  l += __shfl_xor_sync(0xffffffffu, l, 1);
+  l += __shfl_xor_sync(0xffffffffu, l, 2);
+  if (g < W) {
+    const size_t oidx = (((size_t)(b * W + g)) * NH + hh) * (nsplit * XM_WARPS) + sp * XM_WARPS + warp;
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb)
+      *reinterpret_cast<float2*>(part_acc + oidx * HD + nb * 8 + 2 * t) = make_float2(o[nb][0], o[nb][1]);
+    if (t == 0) { part_ml[oidx * 2] = m; part_ml[oidx * 2 + 1] = l; }
+  }
+}
+
+}  // namespace cb
+
+extern "C" int case_cross_attn_partial_tc(const float* q2, const void* Kmem, const void* Vmem, const uint8_t* mask,
+                                          int B, int W, int S, int nsplit, float* part_ml, float* part_acc,
+                                          case_stream_t stream) {
+  CB_REQUIRE(q2 && Kmem && Vmem && mask && part_ml && part_acc, "case_cross_attn_partial_tc: null pointer");
+  CB_REQUIRE(B > 0 && W >= 1 && W <= CASE_MAX_W && S > 0, "case_cross_attn_partial_tc: bad sizes");
+  CB_REQUIRE(nsplit >= 1 && nsplit * cb::XM_WARPS <= CASE_MAX_XSPLIT, "case_cross_attn_partial_tc: nsplit out of range");
+  cb::cross_attn_mma_kernel<<<dim3(B, cb::NH, nsplit), cb::XM_WARPS * 32, cb::XM_SMEM, (cudaStream_t)stream>>>(
+      q2, (const cb::bf16*)Kmem, (const cb::bf16*)Vmem, mask, W, S, nsplit, part_ml, part_acc);
+  return cb::check_launch("case_cross_attn_partial_tc");
+}

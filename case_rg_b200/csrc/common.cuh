@@ -87,6 +87,8 @@ __device__ __forceinline__ void ld8c(const bf16* p, float (&o)[8]) {
   o[6] = __uint_as_float(v.w << 16); o[7] = __uint_as_float(v.w & 0xffff0000u);
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 // ---- reductions
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

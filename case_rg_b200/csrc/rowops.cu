@@ -22,7 +22,6 @@ constexpr int TILE_BYTES = 16384;
 constexpr int NSTAGE = 6;
 template <typename T> struct KTile { static constexpr int KT = TILE_BYTES / (256 * (int)sizeof(T)); };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -644,7 +643,7 @@ extern "C" int case_layer_back(const float* b_in, const float* part_ml, const fl
                                const case_layer_weights_t* w, float* h_out, int R, int dtype,
                                case_stream_t stream) {
   CB_REQUIRE(b_in && part_ml && part_acc && w && h_out && R > 0, "case_layer_back: null pointer");
-  CB_REQUIRE(nsplit >= 1 && nsplit <= CASE_MAX_SPLIT, "case_layer_back: nsplit out of range");
+  CB_REQUIRE(nsplit >= 1 && nsplit <= CASE_MAX_XSPLIT, "case_layer_back: nsplit out of range");
   const int grid = (R + RB - 1) / RB;
   const size_t smem = RING_BYTES + (size_t)BACK_FLOATS * sizeof(float);
   static bool attr = false;

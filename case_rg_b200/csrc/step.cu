@@ -74,9 +74,16 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       const int L = i * 4 + l;
       TRY(case_layer_front(hin, &a->layers[L], a->kcache[L], a->vcache[L], anc, TL, a->tok, TL, t, a->Tmax,
                            a->bbuf, a->q2, R, dt, st));
-      TRY(case_cross_attn_partial(a->q2, a->Kx[L], a->Vx[L], a->mask[i], B, W, a->S[i], a->nsplit_x[i], a->part_ml,
-                                  a->part_acc, dt, st));
-      TRY(case_layer_back(a->bbuf, a->part_ml, a->part_acc, a->nsplit_x[i], &a->layers[L], a->h, R, dt, st));
+      int nparts = a->nsplit_x[i];
+      if (dt == CASE_BF16) {   // tensor-core tiles; one partial per warp
+        TRY(case_cross_attn_partial_tc(a->q2, a->Kx[L], a->Vx[L], a->mask[i], B, W, a->S[i], a->nsplit_x[i],
+                                       a->part_ml, a->part_acc, st));
+        nparts *= 4;
+      } else {
+        TRY(case_cross_attn_partial(a->q2, a->Kx[L], a->Vx[L], a->mask[i], B, W, a->S[i], a->nsplit_x[i],
+                                    a->part_ml, a->part_acc, dt, st));
+      }
+      TRY(case_layer_back(a->bbuf, a->part_ml, a->part_acc, nparts, &a->layers[L], a->h, R, dt, st));
       hin = a->h;
     }
     // attns[i]: query = [dec_out ; norm2(answer_rep)]   (Model.py:108)

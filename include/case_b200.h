@@ -33,7 +33,8 @@ extern "C" {
 #define CASE_HD 32
 #define CASE_MAX_W 8
 #define CASE_MAX_T 128
-#define CASE_MAX_SPLIT 16
+#define CASE_MAX_SPLIT 16   /* additive-attention key splits */
+#define CASE_MAX_XSPLIT 64  /* cross-attention partials per (row, head) */
 
 #define CASE_F32 0
 #define CASE_BF16 1
@@ -128,6 +129,13 @@ int case_layer_front(const float* h, const case_layer_weights_t* w, void* kcache
 int case_cross_attn_partial(const float* q2, const void* Kmem, const void* Vmem, const uint8_t* mask,
                             int B, int W, int S, int nsplit, float* part_ml, float* part_acc, int dtype,
                             case_stream_t stream);
+
+/* Tensor-core form of the above for bf16 K/V (mma.sync m16n8k16 tiles, FlashAttention-2 style; the W
+ * beam rows are the M rows of the tile).  Every warp of a CTA writes its own partial, so the partial
+ * count per (row, head) is nsplit * 4: part_ml [R][NH][nsplit*4][2], part_acc [R][NH][nsplit*4][HD]. */
+int case_cross_attn_partial_tc(const float* q2, const void* Kmem, const void* Vmem, const uint8_t* mask,
+                               int B, int W, int S, int nsplit, float* part_ml, float* part_acc,
+                               case_stream_t stream);
 
 /* Second half (TransformerDecoder.py:82-89): ctx = merge(partials); h2 = b + ctx.Wo2;
  * c = LN3(h2); h_out = c + W2.gelu(W1.c). */

@@ -333,3 +333,54 @@ def test_api_errors_are_loud():
         L.call('case_topk_rows', None, 8, 1, 8, 1, None, None, None)
     with pytest.raises(RuntimeError):
         L.call('case_embed_rows', None, None, None, 1, 0, 1.0, None, 1, None)
+
+
+def _merge_partials(ml, acc):
+    """[R,NH,P,2], [R,NH,P,HD] -> [R, NH*HD] (what case_layer_back does before its out-projection)."""
+    m, l = ml[..., 0], ml[..., 1]
+    M = m.max(dim=2, keepdim=True).values
+    e = torch.where(torch.isinf(m), torch.zeros_like(m), torch.exp(m - M))
+    Z = (l * e).sum(2)
+    o = (acc * e.unsqueeze(-1)).sum(2) / Z.unsqueeze(-1)
+    return o.reshape(o.size(0), -1)
+
+
+@pytest.mark.parametrize('W,S,nsplit', [(1, 60, 1), (4, 2560, 1), (4, 1000, 3), (8, 333, 2), (3, 64, 1)])
+def test_cross_attention_kernels_vs_torch(W, S, nsplit):
+    """Both cross-attention kernels (fp32 SIMT, bf16 tensor-core tiles) against torch softmax attention."""
+    from case_rg_b200 import _lib as L
+    B, NH, HD = 5, 8, 32
+    g = torch.Generator().manual_seed(W * 1000 + S)
+    q = (torch.randn(B * W, 256, generator=g) * 0.5).to(DEV)
+    K = torch.randn(B, NH, S, HD, generator=g).to(DEV)
+    V = torch.randn(B, NH, S, HD, generator=g).to(DEV)
+    mask = (torch.rand(B, S, generator=g) > 0.2)
+    mask[:, 0] = True
+    mask[1, S // 2:] = False
+    mask = mask.to(DEV)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def ref(Kr, Vr):
+        qh = q.view(B, W, NH, HD).permute(0, 2, 1, 3)                       # [B,NH,W,HD]
+        s = qh @ Kr.transpose(-1, -2)
+        s = s.masked_fill(~mask[:, None, None, :], float('-inf'))
+        return (torch.softmax(s, -1) @ Vr).permute(0, 2, 1, 3).reshape(B * W, 256)
+
+    P = nsplit
+    ml = torch.zeros(B * W, NH, P, 2, device=DEV)
+    acc = torch.zeros(B * W, NH, P, HD, device=DEV)
+    m8 = mask.to(torch.uint8)
+    L.call('case_cross_attn_partial', q.data_ptr(), K.data_ptr(), V.data_ptr(), m8.data_ptr(), B, W, S, nsplit,
+           ml.data_ptr(), acc.data_ptr(), L.F32, st)
+    torch.cuda.synchronize()
+    assert rel_err(_merge_partials(ml, acc), ref(K, V)) < 1e-5
+    Kb, Vb = K.bfloat16().contiguous(), V.bfloat16().contiguous()
+    ml = torch.zeros(B * W, NH, P * 4, 2, device=DEV)
+    acc = torch.zeros(B * W, NH, P * 4, HD, device=DEV)
+    L.call('case_cross_attn_partial_tc', q.data_ptr(), Kb.data_ptr(), Vb.data_ptr(), m8.data_ptr(), B, W, S, nsplit,
+           ml.data_ptr(), acc.data_ptr(), st)
+    torch.cuda.synchronize()
+    got = _merge_partials(ml, acc)
+    assert torch.isfinite(got).all()
+    # q and p are rounded to bf16 inside the tile kernel
+    assert rel_err(got, ref(Kb.float(), Vb.float())) < 1.5e-2, rel_err(got, ref(Kb.float(), Vb.float()))
