@@ -185,7 +185,7 @@ def main():
     B, W, T, V = args.batch, args.beam, w['T'], w['V']
 
     sd = syn.make_case_decoder_state(WSEED, V, w['H'])
-    vocab_impl = args.vocab_impl if args.vocab_impl is not None else 0
+    vocab_impl = args.vocab_impl if args.vocab_impl is not None else (1 if args.dtype == 'bf16' else 0)
     model = FG.FastCaSE(sd, device=dev, dtype=args.dtype, max_dec_len=T, beam_width=W, vocab_impl=vocab_impl,
                         use_graph=not args.no_graph)
     host = syn.make_case_inputs(ISEED + rank, B, w['Lq'], w['NP'], w['Lp'], V, w['H'], id_base=rank * B).pin()

@@ -52,7 +52,7 @@ class StepArgs(C.Structure):
                 ('out_tokens', vp), ('n_live', vp),
                 ('x_in', vp), ('h', vp), ('bbuf', vp), ('q2', vp), ('part_ml', vp), ('part_acc', vp), ('qa', vp),
                 ('attn_un', vp * 2), ('stats', vp * 2), ('ctxp', vp * 2), ('hN', vp), ('ctx', vp * 2), ('gates', vp),
-                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp)]
+                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp)]
 
 
 class GttpStepArgs(C.Structure):
@@ -66,7 +66,7 @@ class GttpStepArgs(C.Structure):
                [(n, vp) for n in ('tok', 'live', 'cum', 'length', 'parent', 'ended', 'best_key', 'best_len',
                                   'out_tokens', 'n_live', 'emb', 'qa')] + \
                [('attn_un', vp * 2), ('stats', vp * 2), ('ctxp', vp * 2), ('ctx', vp * 2)] + \
-               [(n, vp) for n in ('gi', 'gh', 'feat', 'gates', 'fac', 'logits', 'dist', 'top_vals', 'top_idx')]
+               [(n, vp) for n in ('gi', 'gh', 'feat', 'gates', 'fac', 'logits', 'dist', 'top_vals', 'top_idx', 'vocab_ws')]
 
 
 # name -> argtypes (return type is int for all but the three listed below)
@@ -80,7 +80,8 @@ _PROTOS = {
     'case_layer_back': [vp, vp, vp, i32, C.POINTER(LayerWeights), vp, i32, i32, vp],
     'case_additive_attn': [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp],
     'case_finalize_rows': [vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp],
-    'case_vocab_gemm': [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+    'case_vocab_gemm': [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp],
+    'case_vocab_gemm_tc': [vp, vp, vp, vp, i32, i32, i32, vp, vp],
     'case_softmax_mix': [vp, i32, vp, vp, i32, i32, i32, i32, vp],
     'case_copy_scatter': [vp, i32, i32, vp, vp, vp, i32, i32, vp, i32, i32, i32, i32, i32, vp],
     'case_topk_rows': [vp, i32, i32, i32, i32, vp, vp, vp],
@@ -91,7 +92,8 @@ _PROTOS = {
     'case_decode_step': [C.POINTER(StepArgs), i32, vp],
     'gttp_decode_step': [C.POINTER(GttpStepArgs), i32, vp],
 }
-EXPORTS = sorted(list(_PROTOS) + ['case_abi_version', 'case_last_error', 'case_struct_size'])
+_SIZE_FNS = ['case_vocab_tc_workspace_bytes', 'case_vocab_tc_packed_weight_bytes']
+EXPORTS = sorted(list(_PROTOS) + ['case_abi_version', 'case_last_error', 'case_struct_size'] + _SIZE_FNS)
 _STRUCTS = [Seg, RowLinArgs, LayerWeights, SelectArgs, StepArgs, GttpStepArgs]
 
 _lib = None
@@ -115,6 +117,9 @@ def load():
     for i, st in enumerate(_STRUCTS):
         if lib.case_struct_size(i) != C.sizeof(st):
             raise RuntimeError(f'ABI mismatch for {st.__name__}: C {lib.case_struct_size(i)} != ctypes {C.sizeof(st)}')
+    for name in _SIZE_FNS:
+        getattr(lib, name).restype = C.c_size_t
+        getattr(lib, name).argtypes = [C.c_int]
     for name, argtypes in _PROTOS.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

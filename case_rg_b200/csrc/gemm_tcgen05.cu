@@ -1,6 +1,235 @@
-// placeholder until the tcgen05 kernel lands
+// Vocabulary projection on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a only.
+//
+//   logits[r][v] = sum_k f[r][k] * Wv[v][k] (+ bias[v])        r < R, v < V, K = 256
+//
+// The weight side is the big, static operand, so it is the UMMA "A" (M) operand: one CTA owns a
+// tile of 128 vocabulary rows, the decode rows are the "B" (N) operand in blocks of up to 256, and
+// the fp32 accumulator D[128 x N] lives in tensor memory.  Both operands are K-major and are stored
+// in global memory already in the no-swizzle UMMA canonical layout (8x8 core matrices of 128 B,
+// k-chunk major), so plain 1-D bulk async copies (cp.async.bulk -> UBLKCP) land them ready for the
+// tensor core; no tensor maps are needed.  K is split into 4 chunks with one mbarrier each so the
+// first MMAs start while later chunks are still in flight.  The epilogue reads TMEM with
+// tcgen05.ld (32 lanes x 32 columns per warp) - lane = vocabulary row, so every store instruction
+// writes 32 consecutive floats of one logits row.
+//
+// Packed layouts (bf16, element (row, k) of a tile with ROWS rows):
+//   byte offset = (k / 8) * (ROWS / 8) * 128 + (row / 8) * 128 + (row % 8) * 16 + (k % 8) * 2
+//   weights:     [ceil(V/128)] tiles of ROWS = 128   (64 KB each; rows >= V are zero)
+//   activations: [ceil(R/256)] blocks of ROWS = 256  (128 KB each; rows >= R are zero)
 #include "common.cuh"
-int case_vocab_gemm_tc(const float*, const void*, const float*, float*, int, int, int, cudaStream_t) {
-  cb::set_error("case_vocab_gemm: tensor-core path not built");
-  return CASE_EINVAL;
+
+namespace cb {
+
+constexpr int TC_K = 256;
+constexpr int TC_M = 128;                       // vocabulary rows per CTA
+constexpr int TC_NB = 256;                      // decode rows per block
+constexpr int TC_KCH = 4;                       // K chunks (pipeline stages)
+constexpr int TC_W_BYTES = TC_M * TC_K * 2;     // 64 KB
+constexpr int TC_A_BYTES = TC_NB * TC_K * 2;    // 128 KB
+constexpr int TC_SMEM = TC_W_BYTES + TC_A_BYTES + 128;
+
+__device__ __forceinline__ void tc_mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void tc_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ bool tc_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity) {
+  while (!tc_try_wait(bar, parity)) {}
+}
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// [0,14) start>>4, [16,30) leading-dim byte offset>>4 (between the two 8-element k-chunks of one
+// K=16 MMA), [32,46) stride byte offset>>4 (between 8-row groups), [46,48) version = 1, [61,64) layout = 0.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = bf16, both K-major
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// fp32 [R][256] -> bf16 canonical blocks of 256 rows (zero padded)
+__global__ void pack_activations_kernel(const float* __restrict__ f, bf16* __restrict__ out, int R) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;        // one thread per (row, k-chunk of 8)
+  const int nblk = (R + TC_NB - 1) / TC_NB;
+  if (idx >= nblk * TC_NB * (TC_K / 8)) return;
+  const int kc = idx % (TC_K / 8), row = idx / (TC_K / 8);
+  const int blk = row / TC_NB, rr = row % TC_NB;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (row < R) {
+    const float4 a = *reinterpret_cast<const float4*>(f + (size_t)row * TC_K + kc * 8);
+    const float4 b = *reinterpret_cast<const float4*>(f + (size_t)row * TC_K + kc * 8 + 4);
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+    v.x = *reinterpret_cast<uint32_t*>(&p0); v.y = *reinterpret_cast<uint32_t*>(&p1);
+    v.z = *reinterpret_cast<uint32_t*>(&p2); v.w = *reinterpret_cast<uint32_t*>(&p3);
+  }
+  const size_t off = (size_t)blk * TC_A_BYTES + (size_t)kc * (TC_NB / 8) * 128 + (rr / 8) * 128 + (rr % 8) * 16;
+  *reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + off) = v;
+}
+
+__global__ __launch_bounds__(128, 1) void vocab_gemm_tc_kernel(const bf16* __restrict__ Wp, const bf16* __restrict__ Ap,
+                                                               const float* __restrict__ bias,
+                                                               float* __restrict__ logits, int R, int V, int ldl) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t s_w = smem_u32(smem), s_a = s_w + TC_W_BYTES;
+  const uint32_t s_bar = s_a + TC_A_BYTES;             // [0..3] chunk-full, [4] mma-done
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + TC_W_BYTES + TC_A_BYTES + 64);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x;
+  const int nblk = (R + TC_NB - 1) / TC_NB;
+
+  if (tid == 0) {
+    for (int i = 0; i < TC_KCH + 1; ++i) tc_mbar_init(s_bar + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  constexpr uint32_t W_CH = TC_W_BYTES / TC_KCH;       // 16 KB of weights per K chunk
+  constexpr uint32_t A_CH = TC_A_BYTES / TC_KCH;       // 32 KB of activations per K chunk (full 256-row block)
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int rows = min(TC_NB, R - blk * TC_NB);
+    const int N = (rows + 15) & ~15;
+    const uint32_t par = blk & 1;
+    if (tid == 0) {
+      const char* wsrc = reinterpret_cast<const char*>(Wp) + (size_t)tile * TC_W_BYTES;
+      const char* asrc = reinterpret_cast<const char*>(Ap) + (size_t)blk * TC_A_BYTES;
+      const uint32_t rg_bytes = (uint32_t)(N / 8) * 128;     // live row groups of one k-chunk column
+      for (int c = 0; c < TC_KCH; ++c) {
+        const uint32_t bar = s_bar + 8 * c;
+        if (N == TC_NB) {
+          tc_expect_tx(bar, (blk == 0 ? W_CH : 0) + A_CH);
+          tc_bulk_g2s(s_a + c * A_CH, asrc + (size_t)c * A_CH, A_CH, bar);
+        } else {
+          tc_expect_tx(bar, (blk == 0 ? W_CH : 0) + 8 * rg_bytes);
+          for (int kc = 0; kc < 8; ++kc) {
+            const uint32_t o = (uint32_t)(c * 8 + kc) * (TC_NB / 8) * 128;
+            tc_bulk_g2s(s_a + o, asrc + o, rg_bytes, bar);
+          }
+        }
+        if (blk == 0) tc_bulk_g2s(s_w + c * W_CH, wsrc + (size_t)c * W_CH, W_CH, bar);
+      }
+      const uint32_t idesc = umma_idesc(TC_M, N);
+      for (int c = 0; c < TC_KCH; ++c) {
+        tc_wait(s_bar + 8 * c, par);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {                     // 4 MMAs of K = 16 per 64-wide chunk
+          const int kc = c * 8 + ks * 2;                     // first 8-element k-chunk of this MMA
+          const uint64_t ad = umma_desc(s_w + kc * (TC_M / 8) * 128, (TC_M / 8) * 128, 128);
+          const uint64_t bd = umma_desc(s_a + kc * (TC_NB / 8) * 128, (TC_NB / 8) * 128, 128);
+          umma_bf16(tmem, ad, bd, idesc, (c | ks) != 0);
+        }
+      }
+      umma_commit(s_bar + 8 * TC_KCH);
+    }
+    // ---- epilogue: every warp drains its 32 TMEM lanes (= 32 vocabulary rows)
+    tc_wait(s_bar + 8 * TC_KCH, par);
+    __syncwarp();         // lane 0 of warp 0 arrives here from the issue path; tcgen05.ld is .aligned
+    tc_fence_after();
+    const int v = tile * TC_M + warp * 32 + lane;
+    const float bv = (bias && v < V) ? __ldg(bias + v) : 0.f;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t acc[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, acc);
+      tmem_ld_wait();
+      if (v < V) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int r = blk * TC_NB + c0 + j;
+          if (r < R) logits[(size_t)r * ldl + v] = __uint_as_float(acc[j]) + bv;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();      // TMEM and the activation buffer are free for the next block
+    tc_fence_after();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+  }
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" size_t case_vocab_tc_workspace_bytes(int R) { return (size_t)((R + TC_NB - 1) / TC_NB) * TC_A_BYTES; }
+extern "C" size_t case_vocab_tc_packed_weight_bytes(int V) { return (size_t)((V + TC_M - 1) / TC_M) * TC_W_BYTES; }
+
+// Wp: packed weights (see header comment); workspace: case_vocab_tc_workspace_bytes(R) bytes, 16-byte aligned.
+extern "C" int case_vocab_gemm_tc(const float* f, const void* Wp, const float* bias, float* logits, int R, int V,
+                                  int ldl, void* workspace, case_stream_t stream) {
+  CB_REQUIRE(f && Wp && logits && workspace && R > 0 && V > 0 && ldl >= V, "case_vocab_gemm_tc: bad arguments");
+  CB_REQUIRE(((uintptr_t)Wp % 16 == 0) && ((uintptr_t)workspace % 16 == 0), "case_vocab_gemm_tc: 16-byte alignment required");
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(vocab_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    attr = true;
+  }
+  const int nblk = (R + TC_NB - 1) / TC_NB;
+  const int n = nblk * TC_NB * (TC_K / 8);
+  pack_activations_kernel<<<(n + 255) / 256, 256, 0, st>>>(f, (bf16*)workspace, R);
+  int rc = check_launch("case_vocab_gemm_tc(pack)");
+  if (rc) return rc;
+  vocab_gemm_tc_kernel<<<(V + TC_M - 1) / TC_M, 128, TC_SMEM, st>>>((const bf16*)Wp, (const bf16*)workspace, bias,
+                                                                     logits, R, V, ldl);
+  return check_launch("case_vocab_gemm_tc");
 }

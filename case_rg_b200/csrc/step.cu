@@ -109,7 +109,7 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
     g.R = R; g.dtype = dt;
     TRY(case_row_linear(&g, st));
   }
-  TRY(case_vocab_gemm(a->gfeat, a->Wv, nullptr, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, st));
+  TRY(case_vocab_gemm(a->gfeat, a->Wv, nullptr, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, a->vocab_ws, st));
   TRY(case_softmax_mix(a->logits, a->ldv, a->gates, a->dist, a->ldv, R, a->V, 0, st));
   for (int i = 0; i < 2; ++i) {
     TRY(case_copy_scatter(a->map, a->map_ld, a->map_off[i], a->prior[i], a->attn_un[i],
@@ -182,7 +182,7 @@ extern "C" int gttp_decode_step(const gttp_step_args_t* a, int t, case_stream_t 
     r.R = R; r.dtype = dt;
     TRY(case_row_linear(&r, st));
   }
-  TRY(case_vocab_gemm(a->feat, a->Wv, a->bv, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, st));
+  TRY(case_vocab_gemm(a->feat, a->Wv, a->bv, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, a->vocab_ws, st));
   TRY(case_gttp_gates(a->feat, a->wc, a->bc, a->gates, a->fac, CASE_MAX_SPLIT, ns[1], R, st));
   TRY(case_softmax_mix(a->logits, a->ldv, a->gates, a->dist, a->ldv, R, a->V, 1, st));
   TRY(case_copy_scatter(a->map, a->map_ld, 0, nullptr, a->attn_un[1], a->fac, CASE_MAX_SPLIT,

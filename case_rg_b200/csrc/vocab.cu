@@ -207,15 +207,12 @@ __global__ __launch_bounds__(256) void topk_rows_kernel(const float* __restrict_
 
 using namespace cb;
 
-int case_vocab_gemm_tc(const float* f, const void* Wv, const float* bias, float* logits, int R, int V, int ldl,
-                       cudaStream_t stream);   // gemm_tcgen05.cu
-
 extern "C" int case_vocab_gemm(const float* f, const void* Wv, const float* bias, float* logits, int R, int V,
-                               int ldl, int dtype, int impl, case_stream_t stream) {
+                               int ldl, int dtype, int impl, void* workspace, case_stream_t stream) {
   CB_REQUIRE(f && Wv && logits && R > 0 && V > 0 && ldl >= V, "case_vocab_gemm: bad arguments");
   if (impl == 1) {
     CB_REQUIRE(dtype == CASE_BF16, "case_vocab_gemm: the tensor-core path needs bf16 weights");
-    return case_vocab_gemm_tc(f, Wv, bias, logits, R, V, ldl, (cudaStream_t)stream);
+    return case_vocab_gemm_tc(f, Wv, bias, logits, R, V, ldl, workspace, stream);
   }
   dim3 grid((V + 63) / 64, (R + 63) / 64);
   if (dtype == CASE_BF16)

@@ -51,6 +51,16 @@ def pack_tiled(w: torch.Tensor, dtype) -> torch.Tensor:
     return w.t().reshape(K, N // 256, 256).permute(1, 0, 2).contiguous().to(dtype)
 
 
+def pack_vocab_tc(w: torch.Tensor) -> torch.Tensor:
+    """[V, 256] output-projection weight -> bf16 tiles of 128 rows in the UMMA K-major no-swizzle
+    canonical layout the tcgen05 kernel bulk-copies straight into shared memory (case_b200.h)."""
+    V, K = w.shape
+    VT = -(-V // 128)
+    wp = torch.zeros(VT * 128, K, dtype=torch.bfloat16, device=w.device)
+    wp[:V] = w.to(torch.bfloat16)
+    return wp.view(VT, 16, 8, K // 8, 8).permute(0, 3, 1, 2, 4).contiguous()   # [tile][k/8][row/8][row%8][k%8]
+
+
 def split_chunk(S, nsplit, tile=128):
     c = -(-S // nsplit)
     return -(-c // tile) * tile
@@ -118,6 +128,7 @@ class CaseWeights:
         self.Uk_t = [g(f'attns.{i}.linear_key.weight').t().contiguous() for i in range(2)]   # fp32 [H][H]
         self.Wg_t, self.bg = mat(g('gen.0.weight')), vec(g('gen.0.bias'))
         self.Wv = g('gen.2.weight').contiguous().to(self.tdtype)                               # [V][H]
+        self.Wv_tc = pack_vocab_tc(g('gen.2.weight')) if self.cdtype == L.BF16 else None
         self.Wm, self.bm = g('mix.weight').contiguous(), vec(g('mix.bias'))
 
 
@@ -207,7 +218,11 @@ class CaseDecodeEngine(_EngineBase):
         self.ldv = -(-V // 8) * 8
         td = weights.tdtype
         self.fast_tanh = int(weights.cdtype == L.BF16 if fast_tanh is None else fast_tanh)
-        self.vocab_impl = int(0 if vocab_impl is None else vocab_impl)
+        self.vocab_impl = int((1 if weights.cdtype == L.BF16 else 0) if vocab_impl is None else vocab_impl)
+        if self.vocab_impl == 1 and weights.cdtype != L.BF16:
+            raise ValueError('the tcgen05 vocabulary GEMM needs bf16 storage')
+        self.vocab_ws = torch.zeros(max(16, L.load().case_vocab_tc_workspace_bytes(self.R)), dtype=torch.uint8,
+                                    device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
         z = lambda *s: torch.zeros(*s, **f32)
         self.nsx = [_nsplit(B * L.NH, s, L.XATTN_TILE, target_ctas) for s in self.S]
@@ -264,8 +279,10 @@ class CaseDecodeEngine(_EngineBase):
             a.Kx[l], a.Vx[l] = self.Kx[l].data_ptr(), self.Vx[l].data_ptr()
             a.kcache[l], a.vcache[l] = self.kcache[l].data_ptr(), self.vcache[l].data_ptr()
         a.lnN_g, a.lnN_b = w.lnN_g.data_ptr(), w.lnN_b.data_ptr()
-        a.Wg_t, a.bg, a.Wv, a.Wm, a.bm = (w.Wg_t.data_ptr(), w.bg.data_ptr(), w.Wv.data_ptr(), w.Wm.data_ptr(),
+        wv = w.Wv_tc if self.vocab_impl == 1 else w.Wv
+        a.Wg_t, a.bg, a.Wv, a.Wm, a.bm = (w.Wg_t.data_ptr(), w.bg.data_ptr(), wv.data_ptr(), w.Wm.data_ptr(),
                                           w.bm.data_ptr())
+        a.vocab_ws = self.vocab_ws.data_ptr()
         a.feat = self.feat.data_ptr()
         a.map, a.map_ld = self.map.data_ptr(), self.map.size(1)
         self.state.bind(a)
@@ -361,6 +378,7 @@ class GttpWeights:
         self.Whh_t, self.bhh = mat(g('dec.gru.weight_hh_l0')), g('dec.gru.bias_hh_l0').contiguous()
         self.Wr_t, self.br = mat(g('dec.readout.weight')), g('dec.readout.bias').contiguous()
         self.Wv, self.bv = g('gen.linear.weight').contiguous().to(self.tdtype), g('gen.linear.bias').contiguous()
+        self.Wv_tc = pack_vocab_tc(g('gen.linear.weight')) if self.cdtype == L.BF16 else None
         self.wc = g('gen.linear_copy.weight').reshape(-1).contiguous()
         self.bc = g('gen.linear_copy.bias').reshape(-1).contiguous()
 
@@ -377,7 +395,11 @@ class GttpDecodeEngine(_EngineBase):
         self.ldv = -(-V // 8) * 8
         td = weights.tdtype
         self.fast_tanh = int(weights.cdtype == L.BF16 if fast_tanh is None else fast_tanh)
-        self.vocab_impl = int(0 if vocab_impl is None else vocab_impl)
+        self.vocab_impl = int((1 if weights.cdtype == L.BF16 else 0) if vocab_impl is None else vocab_impl)
+        if self.vocab_impl == 1 and weights.cdtype != L.BF16:
+            raise ValueError('the tcgen05 vocabulary GEMM needs bf16 storage')
+        self.vocab_ws = torch.zeros(max(16, L.load().case_vocab_tc_workspace_bytes(self.R)), dtype=torch.uint8,
+                                    device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
         z = lambda *s: torch.zeros(*s, **f32)
         self.ns = [_nsplit(B, s, L.AATTN_TILE, 2 * target_ctas) for s in (Lc, Lb)]
@@ -411,7 +433,9 @@ class GttpDecodeEngine(_EngineBase):
         a.Wqb_t, a.bqb, a.vb = w.Wq_t[1].data_ptr(), w.bq[1].data_ptr(), w.v[1].data_ptr()
         a.Wih_t, a.bih, a.Whh_t, a.bhh = w.Wih_t.data_ptr(), w.bih.data_ptr(), w.Whh_t.data_ptr(), w.bhh.data_ptr()
         a.Wr_t, a.br = w.Wr_t.data_ptr(), w.br.data_ptr()
-        a.Wv, a.bv, a.wc, a.bc = w.Wv.data_ptr(), w.bv.data_ptr(), w.wc.data_ptr(), w.bc.data_ptr()
+        wv = w.Wv_tc if self.vocab_impl == 1 else w.Wv
+        a.Wv, a.bv, a.wc, a.bc = wv.data_ptr(), w.bv.data_ptr(), w.wc.data_ptr(), w.bc.data_ptr()
+        a.vocab_ws = self.vocab_ws.data_ptr()
         a.Us, a.Ms, a.Ub, a.Mb = self.U[0].data_ptr(), self.Mv[0].data_ptr(), self.U[1].data_ptr(), self.Mv[1].data_ptr()
         a.mask_c, a.mask_b = self.mask[0].data_ptr(), self.mask[1].data_ptr()
         a.map, a.map_ld = self.map.data_ptr(), Lb

@@ -168,9 +168,18 @@ int case_finalize_rows(const float* h, const float* lnN_g, const float* lnN_b, c
 /* ---------------------------------------------------------------- vocabulary side */
 
 /* logits[R][ldl] = f[R][H] . Wv[V][H]^T (+ bias)   (gen.2, Model.py:34 / gen.linear GTTP/Model.py:8).
- * impl: 0 = fp32 SIMT tile kernel (Wv in dtype); 1 = tcgen05 bf16 tensor-core kernel (Wv bf16). */
+ * impl 0: fp32-accumulate SIMT tile kernel, Wv = [V][H] row-major in dtype, workspace unused.
+ * impl 1: tcgen05 tensor-core kernel (bf16 x bf16 -> fp32 in TMEM).  Wv = the weight re-packed into
+ *   128-row tiles in the UMMA K-major no-swizzle canonical layout: element (v, k) at byte
+ *   (v/128)*65536 + (k/8)*2048 + ((v%128)/8)*128 + (v%8)*16 + (k%8)*2, rows >= V zero
+ *   (case_vocab_tc_packed_weight_bytes(V) bytes); workspace = case_vocab_tc_workspace_bytes(R) bytes
+ *   (holds the bf16 re-pack of f), both 16-byte aligned. */
 int case_vocab_gemm(const float* f, const void* Wv, const float* bias, float* logits, int R, int V, int ldl,
-                    int dtype, int impl, case_stream_t stream);
+                    int dtype, int impl, void* workspace, case_stream_t stream);
+int case_vocab_gemm_tc(const float* f, const void* Wp, const float* bias, float* logits, int R, int V, int ldl,
+                       void* workspace, case_stream_t stream);
+size_t case_vocab_tc_workspace_bytes(int R);
+size_t case_vocab_tc_packed_weight_bytes(int V);
 
 /* dist[r,v] = gates[r][0] * softmax(logits[r,:V])[v]; mask_col0 sets logit 0 to -inf first
  * (GTTP/Model.py:26).  (Softmax of Model.py:34 fused with the first term of Model.py:41.) */
@@ -253,6 +262,7 @@ typedef struct {
   float* x_in; float* h; float* bbuf; float* q2; float* part_ml; float* part_acc;
   float* qa; float* attn_un[2]; float* stats[2]; float* ctxp[2]; float* hN; float* ctx[2];
   float* gates; float* fac; float* gfeat; float* logits; float* dist; float* top_vals; int32_t* top_idx;
+  void* vocab_ws;                       /* case_vocab_tc_workspace_bytes(R) bytes when vocab_impl == 1 */
 } case_step_args_t;
 
 /* Enqueue one full decode step t (embedding .. select) for all R rows: the body of the eval loop
@@ -278,6 +288,7 @@ typedef struct {
   float* emb; float* qa; float* attn_un[2]; float* stats[2]; float* ctxp[2]; float* ctx[2];
   float* gi; float* gh; float* feat; float* gates; float* fac; float* logits; float* dist;
   float* top_vals; int32_t* top_idx;
+  void* vocab_ws;
 } gttp_step_args_t;
 
 /* One GTTP decode step (GTTP/Model.py:176-193 -> BBCDecoder.forward :113-131 ->

@@ -1,0 +1,85 @@
+"""Kernel-level GPU checks through the C ABI (the end-to-end parity tests live in test_gpu_parity.py)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize('R,V,bias', [(8, 1000, False), (64, 30522, False), (256, 30522, False), (300, 5000, True),
+                                      (512, 50000, True), (17, 130, True)])
+def test_vocab_gemm_tcgen05_vs_torch(R, V, bias):
+    """tcgen05 output projection (bf16 x bf16 -> fp32 in TMEM) against torch on the same bf16-rounded operands."""
+    from case_rg_b200 import _lib as L
+    from case_rg_b200.engine import pack_vocab_tc
+    g = torch.Generator().manual_seed(R * 7 + V)
+    f = torch.randn(R, 256, generator=g).to(DEV)
+    W = (torch.randn(V, 256, generator=g) * 0.1).to(DEV)
+    b = torch.randn(V, generator=g).to(DEV) if bias else None
+    ldl = -(-V // 8) * 8
+    out = torch.full((R, ldl), float('nan'), device=DEV)
+    Wp = pack_vocab_tc(W)
+    lib = L.load()
+    assert Wp.numel() * 2 == lib.case_vocab_tc_packed_weight_bytes(V)
+    ws = torch.zeros(lib.case_vocab_tc_workspace_bytes(R), dtype=torch.uint8, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    L.call('case_vocab_gemm', f.data_ptr(), Wp.data_ptr(), L.ptr(b), out.data_ptr(), R, V, ldl, L.BF16, 1,
+           ws.data_ptr(), st)
+    torch.cuda.synchronize()
+    want = f.bfloat16().float() @ W.bfloat16().float().t()
+    if bias:
+        want = want + b
+    got = out[:, :V]
+    assert torch.isfinite(got).all()
+    assert rel_err(got, want) < 2e-5, rel_err(got, want)
+    # and the SIMT kernel on the same inputs (fp32 activations, bf16 weights)
+    out2 = torch.zeros(R, ldl, device=DEV)
+    Wb = W.bfloat16().contiguous()
+    L.call('case_vocab_gemm', f.data_ptr(), Wb.data_ptr(), L.ptr(b), out2.data_ptr(), R, V, ldl, L.BF16, 0, None, st)
+    torch.cuda.synchronize()
+    want2 = f @ W.bfloat16().float().t() + (b if bias else 0)
+    assert rel_err(out2[:, :V], want2) < 2e-5
+
+
+@pytest.mark.parametrize('K,N,nseg', [(256, 256, 1), (512, 256, 2), (768, 256, 3), (1280, 768, 3), (1536, 256, 4)])
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+def test_row_linear_stream_vs_torch(K, N, nseg, dtype):
+    """Generic row linear (bulk-copy weight streaming) against torch, incl. concat / per-query segments."""
+    import ctypes as C
+    from case_rg_b200 import _lib as L
+    from case_rg_b200.engine import pack_tiled
+    R, W = 37, 2
+    g = torch.Generator().manual_seed(K + N)
+    widths = {1: [K], 2: [256, K - 256], 3: [256, (K - 256) // 2, (K - 256) // 2], 4: [256, 256, 512, 512]}[nseg]
+    segs = []
+    for i, wd in enumerate(widths):
+        per_query = (i == len(widths) - 1 and nseg > 1)
+        rows = -(-R // W) if per_query else R
+        segs.append((torch.randn(rows, wd, generator=g).to(DEV), W if per_query else 1))
+    Wt = (torch.randn(N, K, generator=g) * 0.05).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(R, N, generator=g).to(DEV)
+    td, cd = (torch.float32, L.F32) if dtype == 'fp32' else (torch.bfloat16, L.BF16)
+    Wp = pack_tiled(Wt, td)
+    out = torch.zeros(R, N, device=DEV)
+    a = L.RowLinArgs()
+    for i, (t, div) in enumerate(segs):
+        a.seg[i].p, a.seg[i].ld, a.seg[i].width, a.seg[i].div, a.seg[i].gather = t.data_ptr(), t.size(1), t.size(1), div, 0
+    a.nseg, a.K, a.Wt, a.bias, a.N, a.act = nseg, K, Wp.data_ptr(), bias.data_ptr(), N, 1
+    a.res, a.ldres, a.out, a.ldo, a.R, a.dtype = res.data_ptr(), N, out.data_ptr(), N, R, cd
+    L.call('case_row_linear', C.byref(a), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    x = torch.cat([t if d == 1 else t.repeat_interleave(d, 0)[:R] for t, d in segs], 1)
+    want = torch.nn.functional.gelu(x @ Wp_to_dense(Wp, N, K).t() + bias) + res
+    assert rel_err(out, want) < 2e-5, rel_err(out, want)
+
+
+def Wp_to_dense(Wp, N, K):
+    """inverse of pack_tiled: [N/256][K][256] -> [N, K] fp32 (so the bf16 rounding is shared with the kernel)"""
+    return Wp.float().permute(0, 2, 1).reshape(N, K)
