@@ -590,6 +590,13 @@ extern "C" int case_layernorm_rows(const float* x, const float* g, const float* 
   return check_launch("case_layernorm_rows");
 }
 
+int case_row_linear_tc(const case_rowlin_args_t* a, cudaStream_t st);
+int case_layer_front_tc(const float* h, const case_layer_weights_t* w, void* kcache, void* vcache, const int32_t* anc,
+                        int anc_ld, const int32_t* tok, int tok_ld, int t, int Tmax, float* b_out, float* q2_out, int R,
+                        cudaStream_t st);
+int case_layer_back_tc(const float* b_in, const float* part_ml, const float* part_acc, int nsplit,
+                       const case_layer_weights_t* w, float* h_out, int R, cudaStream_t st);
+
 extern "C" int case_row_linear(const case_rowlin_args_t* a, case_stream_t stream) {
   CB_REQUIRE(a && a->Wt && a->out && a->R > 0, "case_row_linear: null pointer");
   CB_REQUIRE(a->nseg >= 1 && a->nseg <= 4, "case_row_linear: nseg must be 1..4");
@@ -601,6 +608,7 @@ extern "C" int case_row_linear(const case_rowlin_args_t* a, case_stream_t stream
   }
   CB_REQUIRE(K == a->K && K % 32 == 0 && K <= 2048, "case_row_linear: K must equal the segment widths, %32, <=2048");
   CB_REQUIRE(a->N % 256 == 0 && a->N > 0, "case_row_linear: N must be a multiple of 256");
+  if (a->dtype == CASE_BF16) return case_row_linear_tc(a, (cudaStream_t)stream);
   const size_t smem = RING_BYTES + (size_t)(RB * a->K + 4 * RB * 256) * sizeof(float);
   dim3 grid((a->R + RB - 1) / RB, a->N / 256);
   static bool attr = false;
@@ -622,6 +630,9 @@ extern "C" int case_layer_front(const float* h, const case_layer_weights_t* w, v
                                 float* b_out, float* q2_out, int R, int dtype, case_stream_t stream) {
   CB_REQUIRE(h && w && kcache && vcache && anc && tok && b_out && q2_out && R > 0, "case_layer_front: null pointer");
   CB_REQUIRE(t >= 0 && t < Tmax && Tmax <= CASE_MAX_T, "case_layer_front: t / Tmax out of range");
+  if (dtype == CASE_BF16)
+    return case_layer_front_tc(h, w, kcache, vcache, anc, anc_ld, tok, tok_ld, t, Tmax, b_out, q2_out, R,
+                               (cudaStream_t)stream);
   const int grid = (R + RB - 1) / RB;
   const size_t smem = RING_BYTES + (size_t)FRONT_FLOATS * sizeof(float);
   static bool attr = false;
@@ -644,6 +655,7 @@ extern "C" int case_layer_back(const float* b_in, const float* part_ml, const fl
                                case_stream_t stream) {
   CB_REQUIRE(b_in && part_ml && part_acc && w && h_out && R > 0, "case_layer_back: null pointer");
   CB_REQUIRE(nsplit >= 1 && nsplit <= CASE_MAX_XSPLIT, "case_layer_back: nsplit out of range");
+  if (dtype == CASE_BF16) return case_layer_back_tc(b_in, part_ml, part_acc, nsplit, w, h_out, R, (cudaStream_t)stream);
   const int grid = (R + RB - 1) / RB;
   const size_t smem = RING_BYTES + (size_t)BACK_FLOATS * sizeof(float);
   static bool attr = false;

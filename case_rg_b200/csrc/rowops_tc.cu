@@ -1,0 +1,512 @@
+// Tensor-core forms of the row-local kernels for bf16 storage (rowops.cu keeps the fp32 CUDA-core
+// forms).  A CTA owns RB = 8 decode rows, held as the first 8 rows of a 16-row bf16 A tile; every
+// linear is D[16 x 256] += A[16 x K] . W^T on mma.sync.m16n8k16 with the eight consumer warps each
+// owning 32 output columns.  Weights arrive as 16 KB slabs [256 n][32 k] (pre-swizzled in global
+// memory so ldmatrix is bank-conflict free) through a ring of bulk async copies driven by a ninth,
+// producer-only warp: full/empty mbarriers per stage, no block-wide barrier inside a linear.
+//
+// Packed weight layout (bf16), nn.Linear weight W[N][K]:
+//   [N/256][K/32] slabs of 16 KB; inside a slab element (n, k) sits at byte
+//   (n%256)*64 + ((((k%32)/8) ^ (((n%256)>>1)&3)) * 16) + (k%8)*2
+#include "common.cuh"
+
+namespace cb {
+
+constexpr int TRB = 8;              // real rows per CTA (rows 8..15 of the MMA tile are zero)
+constexpr int TCT = 256;            // consumer threads (8 warps)
+constexpr int TNT = TCT + 32;       // + producer warp
+constexpr int TSLAB = 16384;
+constexpr int TNS = 6;              // ring stages
+constexpr int ALD = H + 8;          // bf16 A-tile row stride for K = 256 (conflict-free ldmatrix)
+constexpr int FLD = H + 4;          // fp32 row stride of the row buffers
+
+__device__ __forceinline__ void tmb_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void tmb_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tmb_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool tmb_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tmb_wait(uint64_t* bar, uint32_t parity) {
+  while (!tmb_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tbulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void tmma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void tldsm4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t tpack(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+struct Ring {
+  uint64_t* full;     // [TNS]
+  uint64_t* empty;    // [TNS]
+  char* stage;        // [TNS][TSLAB]
+  int g;              // consumer: next slab (warp-uniform)
+};
+
+struct SlabSrc {      // up to 3 weight matrices consumed back to back
+  const char* base[3];
+  int end[3];
+  int total;
+  __device__ __forceinline__ const char* at(int p) const {
+    int s = 0, first = 0;
+    if (p >= end[0]) { s = 1; first = end[0]; }
+    if (p >= end[1]) { s = 2; first = end[1]; }
+    return base[s] + (size_t)(p - first) * TSLAB;
+  }
+};
+
+__device__ __forceinline__ void ring_setup(Ring& rg, unsigned char* smem_raw) {
+  rg.stage = reinterpret_cast<char*>(smem_raw);
+  rg.full = reinterpret_cast<uint64_t*>(smem_raw + TNS * TSLAB);
+  rg.empty = rg.full + TNS;
+  rg.g = 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TNS; ++s) { tmb_init(&rg.full[s], 1); tmb_init(&rg.empty[s], TCT / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();     // all 288 threads, once
+}
+
+// producer warp: feed every slab of the kernel, then exit
+__device__ __forceinline__ void producer_run(const Ring& rg, const SlabSrc& src) {
+  if ((threadIdx.x & 31) == 0) {
+    for (int p = 0; p < src.total; ++p) {
+      const int s = p % TNS;
+      if (p >= TNS) tmb_wait(&rg.empty[s], (uint32_t)((p / TNS) - 1) & 1u);
+      tmb_expect_tx(&rg.full[s], TSLAB);
+      tbulk_g2s(rg.stage + (size_t)s * TSLAB, src.at(p), TSLAB, &rg.full[s]);
+    }
+  }
+}
+
+// D[16 x 256] = A[16 x K] . Wtile^T : warp w accumulates columns 32w .. 32w+31 (4 n-subtiles of 8)
+// abuf: bf16 [16][lda] in shared memory; consumes K/32 slabs of the ring.
+__device__ __forceinline__ void linear16(Ring& rg, const bf16* abuf, int lda, int K, float (&acc)[4][4]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) { acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.f; }
+  const uint32_t a_base = smem_u32(abuf) + (uint32_t)((lane & 15) * lda + (lane >> 4) * 8) * 2;
+  const int brow = warp * 32 + (lane & 7), bch = lane >> 3;
+  for (int kt = 0; kt < K / 32; ++kt) {
+    const int g = rg.g, st = g % TNS;
+    tmb_wait(&rg.full[st], (uint32_t)(g / TNS) & 1u);
+    const uint32_t sb = smem_u32(rg.stage + (size_t)st * TSLAB);
+    uint32_t a0[4], a1[4];
+    tldsm4(a0, a_base + (uint32_t)(kt * 32) * 2);
+    tldsm4(a1, a_base + (uint32_t)(kt * 32 + 16) * 2);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int n = brow + 8 * s;
+      uint32_t b[4];
+      tldsm4(b, sb + (uint32_t)(n * 64 + ((bch ^ ((n >> 1) & 3)) << 4)));
+      tmma(acc[s], a0, b[0], b[1]);
+      tmma(acc[s], a1, b[2], b[3]);
+    }
+    __syncwarp();
+    if (lane == 0) tmb_arrive(&rg.empty[st]);
+    rg.g = g + 1;
+  }
+}
+
+// LayerNorm of row `warp` (8 consumer warps <-> 8 rows), fp32 in place, and its bf16 copy into the A tile
+__device__ __forceinline__ void ln_row_warp(float* x /*[FLD]*/, const float* __restrict__ g,
+                                            const float* __restrict__ b, bf16* arow /*[ALD]*/) {
+  const int lane = threadIdx.x & 31;
+  float v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { v[i] = x[lane * 8 + i]; s += v[i]; }
+  const float mean = warp_sum(s) * (1.f / H);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / H) + LN_EPS);
+  float y[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int n = lane * 8 + i;
+    y[i] = (v[i] - mean) * rstd * __ldg(g + n) + __ldg(b + n);
+    x[n] = y[i];
+  }
+  uint4 pk = make_uint4(tpack(y[0], y[1]), tpack(y[2], y[3]), tpack(y[4], y[5]), tpack(y[6], y[7]));
+  *reinterpret_cast<uint4*>(arow + lane * 8) = pk;
+}
+
+// ------------------------------------------------------------------------------------------ generic
+__global__ __launch_bounds__(TNT) void row_linear_tc_kernel(case_rowlin_args_t a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Ring rg;
+  ring_setup(rg, smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int lda = a.K + 8;
+  bf16* abuf = reinterpret_cast<bf16*>(smem_raw + TNS * TSLAB + 128);
+  if (warp == TCT / 32) {
+    SlabSrc src;
+    src.base[0] = src.base[1] = src.base[2] = reinterpret_cast<const char*>(a.Wt) + (size_t)blockIdx.y * (a.K / 32) * TSLAB;
+    src.total = a.K / 32;
+    src.end[0] = src.end[1] = src.end[2] = src.total;
+    producer_run(rg, src);
+    return;
+  }
+  const int r0 = blockIdx.x * TRB;
+  // gather + convert the input rows; rows >= TRB (and rows past R) are zero
+  for (int i = tid; i < 16 * (a.K / 2); i += TCT) {
+    const int rb = i / (a.K / 2), c = (i - rb * (a.K / 2)) * 2, r = r0 + rb;
+    float2 v = make_float2(0.f, 0.f);
+    if (rb < TRB && r < a.R) {
+      int off = 0;
+#pragma unroll 1
+      for (int s = 0; s < a.nseg; ++s) {
+        const case_seg_t sg = a.seg[s];
+        if (c < off + sg.width) {
+          int rr = sg.gather ? a.gather_idx[r] : r;
+          rr /= sg.div;
+          v = *reinterpret_cast<const float2*>(sg.p + (size_t)rr * sg.ld + (c - off));
+          break;
+        }
+        off += sg.width;
+      }
+    }
+    *reinterpret_cast<uint32_t*>(abuf + rb * lda + c) = tpack(v.x, v.y);
+  }
+  consumer_sync();
+  float acc[4][4];
+  linear16(rg, abuf, lda, a.K, acc);
+  const int g = lane >> 2, t = lane & 3, r = r0 + g;
+  if (r < a.R) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int n = blockIdx.y * 256 + warp * 32 + s * 8 + 2 * t;
+      float y0 = acc[s][0] + (a.bias ? __ldg(a.bias + n) : 0.f);
+      float y1 = acc[s][1] + (a.bias ? __ldg(a.bias + n + 1) : 0.f);
+      if (a.act == 1) { y0 = gelu_erf(y0); y1 = gelu_erf(y1); }
+      if (a.res) { y0 += a.res[(size_t)r * a.ldres + n]; y1 += a.res[(size_t)r * a.ldres + n + 1]; }
+      *reinterpret_cast<float2*>(a.out + (size_t)r * a.ldo + n) = make_float2(y0, y1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ layer front
+// smem after the ring: [abuf0][abuf1] bf16 16 x ALD | xs, qs, hs fp32 8 x FLD | sc fp32 [8][8][CASE_MAX_T]
+constexpr int T_ABUF_BYTES = 16 * ALD * 2;
+constexpr int T_FRONT_SMEM = TNS * TSLAB + 128 + 2 * T_ABUF_BYTES + 3 * TRB * FLD * 4 + TRB * NH * CASE_MAX_T * 4;
+constexpr int T_BACK_SMEM = TNS * TSLAB + 128 + 2 * T_ABUF_BYTES + 2 * TRB * FLD * 4;
+
+__global__ __launch_bounds__(TNT) void layer_front_tc_kernel(const float* __restrict__ h, case_layer_weights_t w,
+                                                             bf16* kc, bf16* vc, const int32_t* __restrict__ anc,
+                                                             int anc_ld, const int32_t* __restrict__ tok, int tok_ld,
+                                                             int t, int Tmax, float* __restrict__ b_out,
+                                                             float* __restrict__ q2_out, int R) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Ring rg;
+  ring_setup(rg, smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  if (warp == TCT / 32) {
+    SlabSrc src;
+    src.base[0] = reinterpret_cast<const char*>(w.Wqkv_t);
+    src.base[1] = reinterpret_cast<const char*>(w.Wo_t);
+    src.base[2] = reinterpret_cast<const char*>(w.Wq2_t);
+    src.end[0] = 24; src.end[1] = 32; src.end[2] = 40;
+    src.total = 40;
+    producer_run(rg, src);
+    return;
+  }
+  unsigned char* p = smem_raw + TNS * TSLAB + 128;
+  bf16* abuf0 = reinterpret_cast<bf16*>(p);
+  bf16* abuf1 = reinterpret_cast<bf16*>(p + T_ABUF_BYTES);
+  float* xs = reinterpret_cast<float*>(p + 2 * T_ABUF_BYTES);     // a = LN1(h)
+  float* qs = xs + TRB * FLD;                                     // q (pre-scaled)
+  float* hs = qs + TRB * FLD;                                     // h1, then b = LN2(h1)
+  float* sc = hs + TRB * FLD;                                     // [row][head][key]
+  const int r0 = blockIdx.x * TRB, g = lane >> 2, tq = lane & 3;
+
+  // zero the padding rows of both A tiles, load the 8 input rows
+  for (int i = tid; i < 8 * ALD / 2; i += TCT) {
+    reinterpret_cast<uint32_t*>(abuf0 + 8 * ALD)[i] = 0u;
+    reinterpret_cast<uint32_t*>(abuf1 + 8 * ALD)[i] = 0u;
+  }
+  {
+    const int r = r0 + warp;
+    float4 v0 = make_float4(0, 0, 0, 0), v1 = v0;
+    if (r < R) {
+      v0 = *reinterpret_cast<const float4*>(h + (size_t)r * H + lane * 8);
+      v1 = *reinterpret_cast<const float4*>(h + (size_t)r * H + lane * 8 + 4);
+    }
+    *reinterpret_cast<float4*>(xs + warp * FLD + lane * 8) = v0;
+    *reinterpret_cast<float4*>(xs + warp * FLD + lane * 8 + 4) = v1;
+    __syncwarp();
+    ln_row_warp(xs + warp * FLD, w.ln1_g, w.ln1_b, abuf0 + warp * ALD);
+  }
+  consumer_sync();
+
+  float acc[4][4];
+  const int rrow = r0 + g;
+  for (int nt = 0; nt < 3; ++nt) {          // q | k | v
+    linear16(rg, abuf0, ALD, H, acc);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int n = warp * 32 + s * 8 + 2 * tq;
+      const float y0 = acc[s][0] + __ldg(w.bqkv + nt * 256 + n), y1 = acc[s][1] + __ldg(w.bqkv + nt * 256 + n + 1);
+      if (nt == 0) {
+        *reinterpret_cast<float2*>(qs + g * FLD + n) = make_float2(y0, y1);
+      } else if (rrow < R) {
+        bf16* dst = (nt == 1 ? kc : vc) + ((size_t)rrow * Tmax + t) * H + n;
+        *reinterpret_cast<uint32_t*>(dst) = tpack(y0, y1);
+      }
+    }
+  }
+  consumer_sync();      // q in shared memory, newest K/V rows visible to the whole CTA
+
+  // self-attention: warp <-> row; lane = (head, quarter of the head's 32 dims)
+  {
+    const int r = r0 + warp, hh = lane >> 2, qd = lane & 3;
+    float* scr = sc + (size_t)warp * NH * CASE_MAX_T;
+    float ctx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (r < R) {
+      float q[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = qs[warp * FLD + hh * HD + qd * 8 + i];
+      // physical row and validity of every history position, one position per lane; masked
+      // positions still load (from the row itself) so the loop body is branch-free and its
+      // loads can be issued ahead of the reductions
+      float mx = -INFINITY;
+      for (int j0 = 0; j0 <= t; j0 += 32) {
+        const int j = j0 + lane;
+        int pr = r, ok = 0;
+        if (j <= t) {
+          pr = (j == t) ? r : anc[(size_t)r * anc_ld + j];
+          ok = tok[(size_t)pr * tok_ld + j] != 0;                  // PAD key -> masked (Model.py:106)
+        }
+        const int cnt = min(32, t + 1 - j0);
+#pragma unroll 4
+        for (int jj = 0; jj < cnt; ++jj) {
+          const int prj = __shfl_sync(0xffffffffu, pr, jj);
+          const int okj = __shfl_sync(0xffffffffu, ok, jj);
+          float kv[8];
+          ld8c(kc + ((size_t)prj * Tmax + j0 + jj) * H + hh * HD + qd * 8, kv);
+          float d = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d = fmaf(q[i], kv[i], d);
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          d += __shfl_xor_sync(0xffffffffu, d, 2);
+          const float sv = okj ? d : -INFINITY;
+          if (qd == 0) scr[hh * CASE_MAX_T + j0 + jj] = sv;
+          mx = fmaxf(mx, sv);
+        }
+      }
+      __syncwarp();
+      float sum = 0.f;
+      for (int j0 = 0; j0 <= t; j0 += 32) {
+        const int j = j0 + lane;
+        int pr = r;
+        if (j <= t) pr = (j == t) ? r : anc[(size_t)r * anc_ld + j];
+        const int cnt = min(32, t + 1 - j0);
+#pragma unroll 4
+        for (int jj = 0; jj < cnt; ++jj) {
+          const int prj = __shfl_sync(0xffffffffu, pr, jj);
+          const float sv = scr[hh * CASE_MAX_T + j0 + jj];
+          const float pexp = (sv == -INFINITY) ? 0.f : fexp(sv - mx);
+          sum += pexp;
+          float vv[8];
+          ld8c(vc + ((size_t)prj * Tmax + j0 + jj) * H + hh * HD + qd * 8, vv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ctx[i] = fmaf(pexp, vv[i], ctx[i]);
+        }
+      }
+      const float inv = sum > 0.f ? 1.f / sum : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ctx[i] *= inv;
+    }
+    uint4 pk = make_uint4(tpack(ctx[0], ctx[1]), tpack(ctx[2], ctx[3]), tpack(ctx[4], ctx[5]), tpack(ctx[6], ctx[7]));
+    *reinterpret_cast<uint4*>(abuf1 + warp * ALD + hh * HD + qd * 8) = pk;
+  }
+  consumer_sync();
+
+  // h1 = a + c.Wo + bo
+  linear16(rg, abuf1, ALD, H, acc);
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int n = warp * 32 + s * 8 + 2 * tq;
+    const float2 a2 = *reinterpret_cast<const float2*>(xs + g * FLD + n);
+    *reinterpret_cast<float2*>(hs + g * FLD + n) =
+        make_float2(a2.x + acc[s][0] + __ldg(w.bo + n), a2.y + acc[s][1] + __ldg(w.bo + n + 1));
+  }
+  consumer_sync();
+  ln_row_warp(hs + warp * FLD, w.ln2_g, w.ln2_b, abuf0 + warp * ALD);
+  {
+    const int r = r0 + warp;
+    if (r < R) {
+      __syncwarp();
+      *reinterpret_cast<float4*>(b_out + (size_t)r * H + lane * 8) = *reinterpret_cast<const float4*>(hs + warp * FLD + lane * 8);
+      *reinterpret_cast<float4*>(b_out + (size_t)r * H + lane * 8 + 4) = *reinterpret_cast<const float4*>(hs + warp * FLD + lane * 8 + 4);
+    }
+  }
+  consumer_sync();
+  linear16(rg, abuf0, ALD, H, acc);
+  if (rrow < R) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int n = warp * 32 + s * 8 + 2 * tq;
+      *reinterpret_cast<float2*>(q2_out + (size_t)rrow * H + n) =
+          make_float2(acc[s][0] + __ldg(w.bq2 + n), acc[s][1] + __ldg(w.bq2 + n + 1));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ layer back
+__global__ __launch_bounds__(TNT) void layer_back_tc_kernel(const float* __restrict__ b_in,
+                                                            const float* __restrict__ part_ml,
+                                                            const float* __restrict__ part_acc, int nsplit,
+                                                            case_layer_weights_t w, float* __restrict__ h_out, int R) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Ring rg;
+  ring_setup(rg, smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  if (warp == TCT / 32) {
+    SlabSrc src;
+    src.base[0] = reinterpret_cast<const char*>(w.Wo2_t);
+    src.base[1] = reinterpret_cast<const char*>(w.W1_t);
+    src.base[2] = reinterpret_cast<const char*>(w.W2_t);
+    src.end[0] = 8; src.end[1] = 16; src.end[2] = 24;
+    src.total = 24;
+    producer_run(rg, src);
+    return;
+  }
+  unsigned char* p = smem_raw + TNS * TSLAB + 128;
+  bf16* abuf0 = reinterpret_cast<bf16*>(p);
+  bf16* abuf1 = reinterpret_cast<bf16*>(p + T_ABUF_BYTES);
+  float* bs = reinterpret_cast<float*>(p + 2 * T_ABUF_BYTES);    // b (residual of the cross-attention block)
+  float* ys = bs + TRB * FLD;                                    // h2 -> c = LN3(h2)
+  const int r0 = blockIdx.x * TRB, g = lane >> 2, tq = lane & 3, rrow = r0 + g;
+  for (int i = tid; i < 8 * ALD / 2; i += TCT) {
+    reinterpret_cast<uint32_t*>(abuf0 + 8 * ALD)[i] = 0u;
+    reinterpret_cast<uint32_t*>(abuf1 + 8 * ALD)[i] = 0u;
+  }
+  // merge the cross-attention partials: thread = column, 8 rows
+  {
+    const int hh = tid / HD, d = tid % HD;
+#pragma unroll 2
+    for (int rb = 0; rb < TRB; ++rb) {
+      const int r = r0 + rb;
+      float c = 0.f, bv = 0.f;
+      if (r < R) {
+        bv = b_in[(size_t)r * H + tid];
+        const size_t base = ((size_t)r * NH + hh) * nsplit;
+        float M = -INFINITY;
+        for (int j = 0; j < nsplit; ++j) M = fmaxf(M, part_ml[(base + j) * 2]);
+        float Z = 0.f, a = 0.f;
+        for (int j = 0; j < nsplit; ++j) {
+          const float mj = part_ml[(base + j) * 2];
+          const float e = (mj == -INFINITY) ? 0.f : fexp(mj - M);
+          Z = fmaf(part_ml[(base + j) * 2 + 1], e, Z);
+          a = fmaf(part_acc[(base + j) * HD + d], e, a);
+        }
+        c = Z > 0.f ? a / Z : 0.f;
+      }
+      bs[rb * FLD + tid] = bv;
+      abuf0[rb * ALD + tid] = __float2bfloat16_rn(c);
+    }
+  }
+  consumer_sync();
+  float acc[4][4];
+  linear16(rg, abuf0, ALD, H, acc);
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int n = warp * 32 + s * 8 + 2 * tq;
+    const float2 b2 = *reinterpret_cast<const float2*>(bs + g * FLD + n);
+    *reinterpret_cast<float2*>(ys + g * FLD + n) =
+        make_float2(b2.x + acc[s][0] + __ldg(w.bo2 + n), b2.y + acc[s][1] + __ldg(w.bo2 + n + 1));
+  }
+  consumer_sync();
+  ln_row_warp(ys + warp * FLD, w.ln3_g, w.ln3_b, abuf1 + warp * ALD);
+  consumer_sync();
+  linear16(rg, abuf1, ALD, H, acc);
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int n = warp * 32 + s * 8 + 2 * tq;
+    *reinterpret_cast<uint32_t*>(abuf0 + g * ALD + n) =
+        tpack(gelu_erf(acc[s][0] + __ldg(w.b1 + n)), gelu_erf(acc[s][1] + __ldg(w.b1 + n + 1)));
+  }
+  consumer_sync();
+  linear16(rg, abuf0, ALD, H, acc);
+  if (rrow < R) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int n = warp * 32 + s * 8 + 2 * tq;
+      const float2 c2 = *reinterpret_cast<const float2*>(ys + g * FLD + n);
+      *reinterpret_cast<float2*>(h_out + (size_t)rrow * H + n) =
+          make_float2(c2.x + acc[s][0] + __ldg(w.b2 + n), c2.y + acc[s][1] + __ldg(w.b2 + n + 1));
+    }
+  }
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+int case_row_linear_tc(const case_rowlin_args_t* a, cudaStream_t st) {
+  const size_t smem = (size_t)TNS * TSLAB + 128 + (size_t)16 * (a->K + 8) * 2;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(row_linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  dim3 grid((a->R + TRB - 1) / TRB, a->N / 256);
+  row_linear_tc_kernel<<<grid, TNT, smem, st>>>(*a);
+  return check_launch("case_row_linear(tc)");
+}
+
+int case_layer_front_tc(const float* h, const case_layer_weights_t* w, void* kcache, void* vcache, const int32_t* anc,
+                        int anc_ld, const int32_t* tok, int tok_ld, int t, int Tmax, float* b_out, float* q2_out, int R,
+                        cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(layer_front_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_FRONT_SMEM);
+    attr = true;
+  }
+  layer_front_tc_kernel<<<(R + TRB - 1) / TRB, TNT, T_FRONT_SMEM, st>>>(h, *w, (bf16*)kcache, (bf16*)vcache, anc, anc_ld,
+                                                                        tok, tok_ld, t, Tmax, b_out, q2_out, R);
+  return check_launch("case_layer_front(tc)");
+}
+
+int case_layer_back_tc(const float* b_in, const float* part_ml, const float* part_acc, int nsplit,
+                       const case_layer_weights_t* w, float* h_out, int R, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(layer_back_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_BACK_SMEM);
+    attr = true;
+  }
+  layer_back_tc_kernel<<<(R + TRB - 1) / TRB, TNT, T_BACK_SMEM, st>>>(b_in, part_ml, part_acc, nsplit, *w, h_out, R);
+  return check_launch("case_layer_back(tc)");
+}

@@ -43,12 +43,29 @@ def _nsplit(units_per_split_group: int, S: int, tile: int, target_ctas: int) -> 
 
 
 def pack_tiled(w: torch.Tensor, dtype) -> torch.Tensor:
-    """nn.Linear weight [N, K] -> the kernels' streaming layout [N/256][K][256] (n-tile major): the
-    weights one CTA needs for 256 output columns are one contiguous run of 16 KB tiles."""
+    """nn.Linear weight [N, K] -> the kernels' streaming layout (one contiguous run of 16 KB tiles per
+    256 output columns).  fp32: [N/256][K][256] for the CUDA-core kernels.  bf16: [N/256][K/32] slabs
+    of [256 n][32 k] for the mma.sync kernels, the four 16-byte k-chunks of every row XOR-swizzled
+    with ((n >> 1) & 3) so ldmatrix reads are bank-conflict free (layout: csrc/rowops_tc.cu)."""
     N, K = w.shape
     if N % 256 or K % 32:
         raise ValueError(f'weight {tuple(w.shape)}: N must be a multiple of 256 and K of 32')
+    if dtype == torch.bfloat16:
+        t = w.to(torch.bfloat16).reshape(N // 256, 256, K // 32, 4, 8).permute(0, 2, 1, 3, 4)   # [nt][slab][n][chunk][8]
+        n = torch.arange(256, device=w.device)
+        src = torch.arange(4, device=w.device)[None, :] ^ ((n >> 1) & 3)[:, None]                # [n][chunk'] -> chunk
+        return t[:, :, n[:, None], src].contiguous()
     return w.t().reshape(K, N // 256, 256).permute(1, 0, 2).contiguous().to(dtype)
+
+
+def unpack_tiled(wp: torch.Tensor, N: int, K: int) -> torch.Tensor:
+    """Inverse of pack_tiled -> fp32 [N, K] (used by tests to share the storage rounding)."""
+    if wp.dtype == torch.bfloat16:
+        n = torch.arange(256, device=wp.device)
+        src = torch.arange(4, device=wp.device)[None, :] ^ ((n >> 1) & 3)[:, None]               # the XOR is an involution
+        t = wp.view(N // 256, K // 32, 256, 4, 8)[:, :, n[:, None], src]
+        return t.permute(0, 2, 1, 3, 4).reshape(N, K).float()
+    return wp.float().permute(0, 2, 1).reshape(N, K)
 
 
 def pack_vocab_tc(w: torch.Tensor) -> torch.Tensor:
