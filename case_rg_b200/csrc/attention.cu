@@ -398,8 +398,9 @@ extern "C" int case_additive_attn(const float* qa, const void* U, const void* Mv
 // bf16 K/V only.  FlashAttention-2 style decode step on mma.sync.m16n8k16 tiles: the W (<= 8) beam rows
 // of one query are the M rows 0..7 of the tile (rows 8..15 are zero padding), so one pass over a
 // head's K/V serves every beam.  Each warp owns a strided set of 64-key tiles with its own cp.async
-// double buffer and its own running (max, sum, acc); warps never synchronise with each other and
-// each writes its own partial, merged later by case_layer_back.  HBM traffic = K and V once.
+// double buffer and its own running (max, sum, acc); warps never synchronise with each other until
+// the end, where the CTA merges its four warps and writes one partial per (row, head, split) for
+// case_layer_back.  HBM traffic = K and V once.
 namespace cb {
 
 constexpr int XM_WARPS = 4;
@@ -538,12 +539,37 @@ __global__ __launch_bounds__(XM_WARPS * 32) void cross_attn_mma_kernel(
   }
   l += __shfl_xor_sync(0xffffffffu, l, 1);
   l += __shfl_xor_sync(0xffffffffu, l, 2);
-  if (g < W) {
-    const size_t oidx = (((size_t)(b * W + g)) * NH + hh) * (nsplit * XM_WARPS) + sp * XM_WARPS + warp;
+  // merge the four warps of the CTA through shared memory (each warp parks its result in its own,
+  // now idle, staging region) so the CTA writes ONE partial per (row, head, split)
+  __syncwarp();
+  float* scr = reinterpret_cast<float*>(xm_smem + (size_t)warp * 4 * XM_TILE_BYTES);   // [8 rows][2 + 32]
+  if (t == 0) { scr[g * 34] = m; scr[g * 34 + 1] = l; }
 #pragma unroll
-    for (int nb = 0; nb < 4; ++nb)
-      *reinterpret_cast<float2*>(part_acc + oidx * HD + nb * 8 + 2 * t) = make_float2(o[nb][0], o[nb][1]);
-    if (t == 0) { part_ml[oidx * 2] = m; part_ml[oidx * 2 + 1] = l; }
+  for (int nb = 0; nb < 4; ++nb)
+    *reinterpret_cast<float2*>(scr + g * 34 + 2 + nb * 8 + 2 * t) = make_float2(o[nb][0], o[nb][1]);
+  __syncthreads();
+  {
+    const int row = threadIdx.x >> 4, dp = threadIdx.x & 15;       // 8 rows x 16 column pairs
+    if (row < W) {
+      float mw[XM_WARPS], M = -INFINITY;
+#pragma unroll
+      for (int w2 = 0; w2 < XM_WARPS; ++w2) {
+        mw[w2] = reinterpret_cast<const float*>(xm_smem + (size_t)w2 * 4 * XM_TILE_BYTES)[row * 34];
+        M = fmaxf(M, mw[w2]);
+      }
+      float L = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < XM_WARPS; ++w2) {
+        const float* sw = reinterpret_cast<const float*>(xm_smem + (size_t)w2 * 4 * XM_TILE_BYTES) + row * 34;
+        const float e = (mw[w2] == -INFINITY) ? 0.f : fexp(mw[w2] - M);
+        L = fmaf(sw[1], e, L);
+        o0 = fmaf(sw[2 + 2 * dp], e, o0);
+        o1 = fmaf(sw[3 + 2 * dp], e, o1);
+      }
+      const size_t oidx = (((size_t)(b * W + row)) * NH + hh) * nsplit + sp;
+      *reinterpret_cast<float2*>(part_acc + oidx * HD + 2 * dp) = make_float2(o0, o1);
+      if (dp == 0) { part_ml[oidx * 2] = M; part_ml[oidx * 2 + 1] = L; }
+    }
   }
 }
 
@@ -554,7 +580,7 @@ extern "C" int case_cross_attn_partial_tc(const float* q2, const void* Kmem, con
                                           case_stream_t stream) {
   CB_REQUIRE(q2 && Kmem && Vmem && mask && part_ml && part_acc, "case_cross_attn_partial_tc: null pointer");
   CB_REQUIRE(B > 0 && W >= 1 && W <= CASE_MAX_W && S > 0, "case_cross_attn_partial_tc: bad sizes");
-  CB_REQUIRE(nsplit >= 1 && nsplit * cb::XM_WARPS <= CASE_MAX_XSPLIT, "case_cross_attn_partial_tc: nsplit out of range");
+  CB_REQUIRE(nsplit >= 1 && nsplit <= CASE_MAX_XSPLIT, "case_cross_attn_partial_tc: nsplit out of range");
   cb::cross_attn_mma_kernel<<<dim3(B, cb::NH, nsplit), cb::XM_WARPS * 32, cb::XM_SMEM, (cudaStream_t)stream>>>(
       q2, (const cb::bf16*)Kmem, (const cb::bf16*)Vmem, mask, W, S, nsplit, part_ml, part_acc);
   return cb::check_launch("case_cross_attn_partial_tc");

@@ -180,25 +180,27 @@ __global__ __launch_bounds__(TNT) void row_linear_tc_kernel(case_rowlin_args_t a
     return;
   }
   const int r0 = blockIdx.x * TRB;
-  // gather + convert the input rows; rows >= TRB (and rows past R) are zero
-  for (int i = tid; i < 16 * (a.K / 2); i += TCT) {
-    const int rb = i / (a.K / 2), c = (i - rb * (a.K / 2)) * 2, r = r0 + rb;
-    float2 v = make_float2(0.f, 0.f);
-    if (rb < TRB && r < a.R) {
-      int off = 0;
-#pragma unroll 1
-      for (int s = 0; s < a.nseg; ++s) {
-        const case_seg_t sg = a.seg[s];
-        if (c < off + sg.width) {
+  // gather + convert the input rows (one simple strided loop per segment so the loads pipeline);
+  // rows >= TRB (and rows past R) are zero
+  for (int i = tid; i < 8 * lda / 2; i += TCT) reinterpret_cast<uint32_t*>(abuf + 8 * lda)[i] = 0u;
+  {
+    int off = 0;
+    for (int s = 0; s < a.nseg; ++s) {
+      const case_seg_t sg = a.seg[s];
+      const int hw = sg.width >> 1;
+#pragma unroll 4
+      for (int i = tid; i < TRB * hw; i += TCT) {
+        const int rb = i / hw, c = (i - rb * hw) * 2, r = r0 + rb;
+        float2 v = make_float2(0.f, 0.f);
+        if (r < a.R) {
           int rr = sg.gather ? a.gather_idx[r] : r;
           rr /= sg.div;
-          v = *reinterpret_cast<const float2*>(sg.p + (size_t)rr * sg.ld + (c - off));
-          break;
+          v = *reinterpret_cast<const float2*>(sg.p + (size_t)rr * sg.ld + c);
         }
-        off += sg.width;
+        *reinterpret_cast<uint32_t*>(abuf + rb * lda + off + c) = tpack(v.x, v.y);
       }
+      off += sg.width;
     }
-    *reinterpret_cast<uint32_t*>(abuf + rb * lda + c) = tpack(v.x, v.y);
   }
   consumer_sync();
   float acc[4][4];
@@ -220,7 +222,8 @@ __global__ __launch_bounds__(TNT) void row_linear_tc_kernel(case_rowlin_args_t a
 // ------------------------------------------------------------------------------------------ layer front
 // smem after the ring: [abuf0][abuf1] bf16 16 x ALD | xs, qs, hs fp32 8 x FLD | sc fp32 [8][8][CASE_MAX_T]
 constexpr int T_ABUF_BYTES = 16 * ALD * 2;
-constexpr int T_FRONT_SMEM = TNS * TSLAB + 128 + 2 * T_ABUF_BYTES + 3 * TRB * FLD * 4 + TRB * NH * CASE_MAX_T * 4;
+constexpr int T_FRONT_SMEM =
+    TNS * TSLAB + 128 + 2 * T_ABUF_BYTES + 3 * TRB * FLD * 4 + TRB * NH * CASE_MAX_T * 4 + TRB * CASE_MAX_T * 4;
 constexpr int T_BACK_SMEM = TNS * TSLAB + 128 + 2 * T_ABUF_BYTES + 2 * TRB * FLD * 4;
 
 __global__ __launch_bounds__(TNT) void layer_front_tc_kernel(const float* __restrict__ h, case_layer_weights_t w,
@@ -297,51 +300,65 @@ __global__ __launch_bounds__(TNT) void layer_front_tc_kernel(const float* __rest
       float q[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) q[i] = qs[warp * FLD + hh * HD + qd * 8 + i];
-      // physical row and validity of every history position, one position per lane; masked
-      // positions still load (from the row itself) so the loop body is branch-free and its
-      // loads can be issued ahead of the reductions
+      // physical row (bit 30 set = masked: PAD key, Model.py:106) of every history position
+      int* prow = reinterpret_cast<int*>(sc + (size_t)TRB * NH * CASE_MAX_T) + warp * CASE_MAX_T;
+      for (int j = lane; j <= t; j += 32) {
+        const int pr = (j == t) ? r : anc[(size_t)r * anc_ld + j];
+        prow[j] = pr | (tok[(size_t)pr * tok_ld + j] != 0 ? 0 : 0x40000000);
+      }
+      __syncwarp();
+      // scores: 8 keys per batch, all loads of a batch issued before any reduction
       float mx = -INFINITY;
-      for (int j0 = 0; j0 <= t; j0 += 32) {
-        const int j = j0 + lane;
-        int pr = r, ok = 0;
-        if (j <= t) {
-          pr = (j == t) ? r : anc[(size_t)r * anc_ld + j];
-          ok = tok[(size_t)pr * tok_ld + j] != 0;                  // PAD key -> masked (Model.py:106)
-        }
-        const int cnt = min(32, t + 1 - j0);
-#pragma unroll 4
-        for (int jj = 0; jj < cnt; ++jj) {
-          const int prj = __shfl_sync(0xffffffffu, pr, jj);
-          const int okj = __shfl_sync(0xffffffffu, ok, jj);
-          float kv[8];
-          ld8c(kc + ((size_t)prj * Tmax + j0 + jj) * H + hh * HD + qd * 8, kv);
-          float d = 0.f;
+      const size_t coff = (size_t)hh * HD + qd * 8;
+      for (int jb = 0; jb <= t; jb += 8) {
+        uint4 raw[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) d = fmaf(q[i], kv[i], d);
-          d += __shfl_xor_sync(0xffffffffu, d, 1);
-          d += __shfl_xor_sync(0xffffffffu, d, 2);
-          const float sv = okj ? d : -INFINITY;
-          if (qd == 0) scr[hh * CASE_MAX_T + j0 + jj] = sv;
-          mx = fmaxf(mx, sv);
+        for (int u = 0; u < 8; ++u) {
+          const int j = min(jb + u, t);
+          raw[u] = *reinterpret_cast<const uint4*>(kc + ((size_t)(prow[j] & 0x3fffffff) * Tmax + j) * H + coff);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = jb + u;
+          if (j <= t) {
+            const uint32_t w4[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+            float d = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              d = fmaf(q[2 * i], __uint_as_float(w4[i] << 16), d);
+              d = fmaf(q[2 * i + 1], __uint_as_float(w4[i] & 0xffff0000u), d);
+            }
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            const float sv = (prow[j] & 0x40000000) ? -INFINITY : d;
+            if (qd == 0) scr[hh * CASE_MAX_T + j] = sv;
+            mx = fmaxf(mx, sv);
+          }
         }
       }
       __syncwarp();
       float sum = 0.f;
-      for (int j0 = 0; j0 <= t; j0 += 32) {
-        const int j = j0 + lane;
-        int pr = r;
-        if (j <= t) pr = (j == t) ? r : anc[(size_t)r * anc_ld + j];
-        const int cnt = min(32, t + 1 - j0);
-#pragma unroll 4
-        for (int jj = 0; jj < cnt; ++jj) {
-          const int prj = __shfl_sync(0xffffffffu, pr, jj);
-          const float sv = scr[hh * CASE_MAX_T + j0 + jj];
-          const float pexp = (sv == -INFINITY) ? 0.f : fexp(sv - mx);
-          sum += pexp;
-          float vv[8];
-          ld8c(vc + ((size_t)prj * Tmax + j0 + jj) * H + hh * HD + qd * 8, vv);
+      for (int jb = 0; jb <= t; jb += 8) {
+        uint4 raw[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) ctx[i] = fmaf(pexp, vv[i], ctx[i]);
+        for (int u = 0; u < 8; ++u) {
+          const int j = min(jb + u, t);
+          raw[u] = *reinterpret_cast<const uint4*>(vc + ((size_t)(prow[j] & 0x3fffffff) * Tmax + j) * H + coff);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = jb + u;
+          if (j <= t) {
+            const float sv = scr[hh * CASE_MAX_T + j];
+            const float pexp = (sv == -INFINITY) ? 0.f : fexp(sv - mx);
+            sum += pexp;
+            const uint32_t w4[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              ctx[2 * i] = fmaf(pexp, __uint_as_float(w4[i] << 16), ctx[2 * i]);
+              ctx[2 * i + 1] = fmaf(pexp, __uint_as_float(w4[i] & 0xffff0000u), ctx[2 * i + 1]);
+            }
+          }
         }
       }
       const float inv = sum > 0.f ? 1.f / sum : 0.f;
@@ -413,29 +430,62 @@ __global__ __launch_bounds__(TNT) void layer_back_tc_kernel(const float* __restr
     reinterpret_cast<uint32_t*>(abuf0 + 8 * ALD)[i] = 0u;
     reinterpret_cast<uint32_t*>(abuf1 + 8 * ALD)[i] = 0u;
   }
-  // merge the cross-attention partials: thread = column, 8 rows
+  // merge the cross-attention partials: thread = column, 8 rows.  All loads of a phase are
+  // independent and issued together (this prologue is pure L2 latency otherwise).
   {
     const int hh = tid / HD, d = tid % HD;
-#pragma unroll 2
+    float* wgt = bs;                                   // [TRB][NH][nsplit] merge weights e_j / Z (bs | ys are free here)
+    if (nsplit == 1) {
+      if (tid < TRB * NH) {
+        const int rb = tid / NH, r = r0 + rb;
+        const float l = r < R ? part_ml[((size_t)r * NH + tid % NH) * 2 + 1] : 0.f;
+        wgt[tid] = l > 0.f ? 1.f / l : 0.f;
+      }
+    } else {
+      float* mls = wgt + TRB * NH * nsplit;            // staged (m, l) pairs
+      for (int i = tid; i < TRB * NH * nsplit; i += TCT) {
+        const int rb = i / (NH * nsplit), r = r0 + rb;
+        float2 ml = make_float2(-INFINITY, 0.f);
+        if (r < R) ml = *reinterpret_cast<const float2*>(part_ml + ((size_t)r * NH * nsplit + (i - rb * NH * nsplit)) * 2);
+        mls[2 * i] = ml.x; mls[2 * i + 1] = ml.y;
+      }
+      consumer_sync();
+      if (tid < TRB * NH) {
+        float M = -INFINITY, Z = 0.f;
+        for (int j = 0; j < nsplit; ++j) M = fmaxf(M, mls[2 * (tid * nsplit + j)]);
+        for (int j = 0; j < nsplit; ++j) {
+          const float mj = mls[2 * (tid * nsplit + j)];
+          Z = fmaf(mls[2 * (tid * nsplit + j) + 1], (mj == -INFINITY) ? 0.f : fexp(mj - M), Z);
+        }
+        for (int j = 0; j < nsplit; ++j) {
+          const float mj = mls[2 * (tid * nsplit + j)];
+          wgt[tid * nsplit + j] = (Z > 0.f && mj != -INFINITY) ? fexp(mj - M) / Z : 0.f;
+        }
+      }
+    }
+    float bv[TRB], cacc[TRB];
+#pragma unroll
     for (int rb = 0; rb < TRB; ++rb) {
       const int r = r0 + rb;
-      float c = 0.f, bv = 0.f;
-      if (r < R) {
-        bv = b_in[(size_t)r * H + tid];
-        const size_t base = ((size_t)r * NH + hh) * nsplit;
-        float M = -INFINITY;
-        for (int j = 0; j < nsplit; ++j) M = fmaxf(M, part_ml[(base + j) * 2]);
-        float Z = 0.f, a = 0.f;
-        for (int j = 0; j < nsplit; ++j) {
-          const float mj = part_ml[(base + j) * 2];
-          const float e = (mj == -INFINITY) ? 0.f : fexp(mj - M);
-          Z = fmaf(part_ml[(base + j) * 2 + 1], e, Z);
-          a = fmaf(part_acc[(base + j) * HD + d], e, a);
-        }
-        c = Z > 0.f ? a / Z : 0.f;
+      bv[rb] = r < R ? b_in[(size_t)r * H + tid] : 0.f;
+      cacc[rb] = 0.f;
+    }
+    consumer_sync();
+    for (int j = 0; j < nsplit; ++j) {
+      float a[TRB];
+#pragma unroll
+      for (int rb = 0; rb < TRB; ++rb) {
+        const int r = r0 + rb;
+        a[rb] = r < R ? part_acc[(((size_t)r * NH + hh) * nsplit + j) * HD + d] : 0.f;
       }
-      bs[rb * FLD + tid] = bv;
-      abuf0[rb * ALD + tid] = __float2bfloat16_rn(c);
+#pragma unroll
+      for (int rb = 0; rb < TRB; ++rb) cacc[rb] = fmaf(a[rb], wgt[(rb * NH + hh) * nsplit + j], cacc[rb]);
+    }
+    consumer_sync();                                   // wgt (aliasing bs | ys) is dead from here on
+#pragma unroll
+    for (int rb = 0; rb < TRB; ++rb) {
+      bs[rb * FLD + tid] = bv[rb];
+      abuf0[rb * ALD + tid] = __float2bfloat16_rn(cacc[rb]);
     }
   }
   consumer_sync();
@@ -502,6 +552,7 @@ int case_layer_front_tc(const float* h, const case_layer_weights_t* w, void* kca
 
 int case_layer_back_tc(const float* b_in, const float* part_ml, const float* part_acc, int nsplit,
                        const case_layer_weights_t* w, float* h_out, int R, cudaStream_t st) {
+  CB_REQUIRE(nsplit <= 16, "case_layer_back: the tensor-core path merges at most 16 partials per (row, head)");
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(layer_back_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_BACK_SMEM);

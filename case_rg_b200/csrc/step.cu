@@ -75,10 +75,9 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       TRY(case_layer_front(hin, &a->layers[L], a->kcache[L], a->vcache[L], anc, TL, a->tok, TL, t, a->Tmax,
                            a->bbuf, a->q2, R, dt, st));
       int nparts = a->nsplit_x[i];
-      if (dt == CASE_BF16) {   // tensor-core tiles; one partial per warp
+      if (dt == CASE_BF16) {   // tensor-core tiles
         TRY(case_cross_attn_partial_tc(a->q2, a->Kx[L], a->Vx[L], a->mask[i], B, W, a->S[i], a->nsplit_x[i],
                                        a->part_ml, a->part_acc, st));
-        nparts *= 4;
       } else {
         TRY(case_cross_attn_partial(a->q2, a->Kx[L], a->Vx[L], a->mask[i], B, W, a->S[i], a->nsplit_x[i],
                                     a->part_ml, a->part_acc, dt, st));

@@ -258,7 +258,7 @@ class CaseDecodeEngine(_EngineBase):
         self.vcache = [torch.zeros(R, Tmax, H, dtype=td, device=dev) for _ in range(8)]
         self.state = _SearchState(dev, B, W, Tmax)
         # scratch
-        nsx = max(self.nsx) * 4          # the tensor-core cross-attention writes one partial per warp
+        nsx = max(self.nsx)
         self.x_in, self.h, self.bbuf, self.q2 = z(R, H), z(R, H), z(R, H), z(R, H)
         self.part_ml, self.part_acc = z(R, L.NH, nsx, 2), z(R, L.NH, nsx, L.HD)
         self.qa = z(R, H)

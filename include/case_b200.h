@@ -131,8 +131,8 @@ int case_cross_attn_partial(const float* q2, const void* Kmem, const void* Vmem,
                             case_stream_t stream);
 
 /* Tensor-core form of the above for bf16 K/V (mma.sync m16n8k16 tiles, FlashAttention-2 style; the W
- * beam rows are the M rows of the tile).  Every warp of a CTA writes its own partial, so the partial
- * count per (row, head) is nsplit * 4: part_ml [R][NH][nsplit*4][2], part_acc [R][NH][nsplit*4][HD]. */
+ * beam rows are the M rows of the tile).  Same outputs as case_cross_attn_partial: one partial per
+ * (row, head, split). */
 int case_cross_attn_partial_tc(const float* q2, const void* Kmem, const void* Vmem, const uint8_t* mask,
                                int B, int W, int S, int nsplit, float* part_ml, float* part_acc,
                                case_stream_t stream);
