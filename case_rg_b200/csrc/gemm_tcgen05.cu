@@ -15,7 +15,8 @@
 // Packed layouts (bf16, element (row, k) of a tile with ROWS rows):
 //   byte offset = (k / 8) * (ROWS / 8) * 128 + (row / 8) * 128 + (row % 8) * 16 + (k % 8) * 2
 //   weights:     [ceil(V/128)] tiles of ROWS = 128   (64 KB each; rows >= V are zero)
-//   activations: [ceil(R/256)] blocks of ROWS = 256  (128 KB each; rows >= R are zero)
+//   activations: [ceil(R/256)] blocks at a 128 KB stride, ROWS = the block's row count rounded up
+//                to 16 (rows >= R are zero), so each 64-wide K chunk of a block is one contiguous run
 #include "common.cuh"
 
 namespace cb {
@@ -104,6 +105,8 @@ __global__ void pack_activations_kernel(const float* __restrict__ f, bf16* __res
   if (idx >= nblk * TC_NB * (TC_K / 8)) return;
   const int kc = idx % (TC_K / 8), row = idx / (TC_K / 8);
   const int blk = row / TC_NB, rr = row % TC_NB;
+  const int npad = (min(TC_NB, R - blk * TC_NB) + 15) & ~15;     // rows of this block, padded to the MMA N granule
+  if (rr >= npad) return;
   uint4 v = make_uint4(0, 0, 0, 0);
   if (row < R) {
     const float4 a = *reinterpret_cast<const float4*>(f + (size_t)row * TC_K + kc * 8);
@@ -113,7 +116,7 @@ __global__ void pack_activations_kernel(const float* __restrict__ f, bf16* __res
     v.x = *reinterpret_cast<uint32_t*>(&p0); v.y = *reinterpret_cast<uint32_t*>(&p1);
     v.z = *reinterpret_cast<uint32_t*>(&p2); v.w = *reinterpret_cast<uint32_t*>(&p3);
   }
-  const size_t off = (size_t)blk * TC_A_BYTES + (size_t)kc * (TC_NB / 8) * 128 + (rr / 8) * 128 + (rr % 8) * 16;
+  const size_t off = (size_t)blk * TC_A_BYTES + (size_t)kc * (npad / 8) * 128 + (rr / 8) * 128 + (rr % 8) * 16;
   *reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + off) = v;
 }
 
@@ -142,29 +145,23 @@ __global__ __launch_bounds__(128, 1) void vocab_gemm_tc_kernel(const bf16* __res
   const uint32_t tmem = *s_tmem;
 
   constexpr uint32_t W_CH = TC_W_BYTES / TC_KCH;       // 16 KB of weights per K chunk
-  constexpr uint32_t A_CH = TC_A_BYTES / TC_KCH;       // 32 KB of activations per K chunk (full 256-row block)
   for (int blk = 0; blk < nblk; ++blk) {
     const int rows = min(TC_NB, R - blk * TC_NB);
     const int N = (rows + 15) & ~15;
     const uint32_t par = blk & 1;
-    if (tid == 0) {
+    // one issuing lane per K chunk, in four different warps: a warp keeps only one bulk copy in
+    // flight at a time (profiles/micro/bulk_bench.cu), so spreading the issue overlaps the chunks
+    if (lane == 0) {
+      const int c = warp;                                    // TC_KCH == number of warps
       const char* wsrc = reinterpret_cast<const char*>(Wp) + (size_t)tile * TC_W_BYTES;
       const char* asrc = reinterpret_cast<const char*>(Ap) + (size_t)blk * TC_A_BYTES;
-      const uint32_t rg_bytes = (uint32_t)(N / 8) * 128;     // live row groups of one k-chunk column
-      for (int c = 0; c < TC_KCH; ++c) {
-        const uint32_t bar = s_bar + 8 * c;
-        if (N == TC_NB) {
-          tc_expect_tx(bar, (blk == 0 ? W_CH : 0) + A_CH);
-          tc_bulk_g2s(s_a + c * A_CH, asrc + (size_t)c * A_CH, A_CH, bar);
-        } else {
-          tc_expect_tx(bar, (blk == 0 ? W_CH : 0) + 8 * rg_bytes);
-          for (int kc = 0; kc < 8; ++kc) {
-            const uint32_t o = (uint32_t)(c * 8 + kc) * (TC_NB / 8) * 128;
-            tc_bulk_g2s(s_a + o, asrc + o, rg_bytes, bar);
-          }
-        }
-        if (blk == 0) tc_bulk_g2s(s_w + c * W_CH, wsrc + (size_t)c * W_CH, W_CH, bar);
-      }
+      const uint32_t a_ch = (uint32_t)N * (TC_K / TC_KCH) * 2;     // N rows x 64 k of bf16, contiguous
+      const uint32_t bar = s_bar + 8 * c;
+      tc_expect_tx(bar, (blk == 0 ? W_CH : 0) + a_ch);
+      tc_bulk_g2s(s_a + c * a_ch, asrc + (size_t)c * a_ch, a_ch, bar);
+      if (blk == 0) tc_bulk_g2s(s_w + c * W_CH, wsrc + (size_t)c * W_CH, W_CH, bar);
+    }
+    if (tid == 0) {
       const uint32_t idesc = umma_idesc(TC_M, N);
       for (int c = 0; c < TC_KCH; ++c) {
         tc_wait(s_bar + 8 * c, par);
@@ -173,7 +170,7 @@ __global__ __launch_bounds__(128, 1) void vocab_gemm_tc_kernel(const bf16* __res
         for (int ks = 0; ks < 4; ++ks) {                     // 4 MMAs of K = 16 per 64-wide chunk
           const int kc = c * 8 + ks * 2;                     // first 8-element k-chunk of this MMA
           const uint64_t ad = umma_desc(s_w + kc * (TC_M / 8) * 128, (TC_M / 8) * 128, 128);
-          const uint64_t bd = umma_desc(s_a + kc * (TC_NB / 8) * 128, (TC_NB / 8) * 128, 128);
+          const uint64_t bd = umma_desc(s_a + kc * (N / 8) * 128, (N / 8) * 128, 128);
           umma_bf16(tmem, ad, bd, idesc, (c | ks) != 0);
         }
       }

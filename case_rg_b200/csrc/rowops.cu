@@ -75,8 +75,11 @@ struct WStream {
       fence_barrier_init();
     }
     __syncthreads();
-    if (threadIdx.x == 0)
-      for (int p = 0; p < NSTAGE && p < total; ++p) issue(p);
+    // a warp keeps one bulk copy in flight at a time (profiles/micro/bulk_bench.cu): spread the issue
+    if ((threadIdx.x & 31) == 0) {
+      const int p = threadIdx.x >> 5;
+      if (p < NSTAGE && p < total) issue(p);
+    }
     g = 0;
   }
 };
@@ -128,7 +131,7 @@ __device__ __forceinline__ void rows_linear_stream(WStream& ws, const float* __r
       }
     }
     __syncthreads();                                   // every thread is done reading stage s
-    if (tid == 0 && g + NSTAGE < ws.total) ws.issue(g + NSTAGE);
+    if ((tid & 31) == 0 && (tid >> 5) == (g & 7) && g + NSTAGE < ws.total) ws.issue(g + NSTAGE);
     ws.g = g + 1;
   }
 #pragma unroll

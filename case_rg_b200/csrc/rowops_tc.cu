@@ -2,8 +2,8 @@
 // forms).  A CTA owns RB = 8 decode rows, held as the first 8 rows of a 16-row bf16 A tile; every
 // linear is D[16 x 256] += A[16 x K] . W^T on mma.sync.m16n8k16 with the eight consumer warps each
 // owning 32 output columns.  Weights arrive as 16 KB slabs [256 n][32 k] (pre-swizzled in global
-// memory so ldmatrix is bank-conflict free) through a ring of bulk async copies driven by a ninth,
-// producer-only warp: full/empty mbarriers per stage, no block-wide barrier inside a linear.
+// memory so ldmatrix is bank-conflict free) through a ring of bulk async copies driven by four
+// producer-only warps: full/empty mbarriers per stage, no block-wide barrier inside a linear.
 //
 // Packed weight layout (bf16), nn.Linear weight W[N][K]:
 //   [N/256][K/32] slabs of 16 KB; inside a slab element (n, k) sits at byte
@@ -14,7 +14,9 @@ namespace cb {
 
 constexpr int TRB = 8;              // real rows per CTA (rows 8..15 of the MMA tile are zero)
 constexpr int TCT = 256;            // consumer threads (8 warps)
-constexpr int TNT = TCT + 32;       // + producer warp
+constexpr int TPW = 4;              // producer warps: a warp has ONE bulk copy in flight at a time
+                                    // (~0.36 us each, profiles/micro/bulk_bench.cu), so the ring is fed by four
+constexpr int TNT = TCT + 32 * TPW;
 constexpr int TSLAB = 16384;
 constexpr int TNS = 6;              // ring stages
 constexpr int ALD = H + 8;          // bf16 A-tile row stride for K = 256 (conflict-free ldmatrix)
@@ -95,13 +97,13 @@ __device__ __forceinline__ void ring_setup(Ring& rg, unsigned char* smem_raw) {
     for (int s = 0; s < TNS; ++s) { tmb_init(&rg.full[s], 1); tmb_init(&rg.empty[s], TCT / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();     // all 288 threads, once
+  __syncthreads();     // all TNT threads, once
 }
 
-// producer warp: feed every slab of the kernel, then exit
+// producer warps: warp i feeds slabs i, i + TPW, ... of the kernel, then exits
 __device__ __forceinline__ void producer_run(const Ring& rg, const SlabSrc& src) {
   if ((threadIdx.x & 31) == 0) {
-    for (int p = 0; p < src.total; ++p) {
+    for (int p = (threadIdx.x >> 5) - TCT / 32; p < src.total; p += TPW) {
       const int s = p % TNS;
       if (p >= TNS) tmb_wait(&rg.empty[s], (uint32_t)((p / TNS) - 1) & 1u);
       tmb_expect_tx(&rg.full[s], TSLAB);
@@ -171,7 +173,7 @@ __global__ __launch_bounds__(TNT) void row_linear_tc_kernel(case_rowlin_args_t a
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   const int lda = a.K + 8;
   bf16* abuf = reinterpret_cast<bf16*>(smem_raw + TNS * TSLAB + 128);
-  if (warp == TCT / 32) {
+  if (warp >= TCT / 32) {
     SlabSrc src;
     src.base[0] = src.base[1] = src.base[2] = reinterpret_cast<const char*>(a.Wt) + (size_t)blockIdx.y * (a.K / 32) * TSLAB;
     src.total = a.K / 32;
@@ -235,7 +237,7 @@ __global__ __launch_bounds__(TNT) void layer_front_tc_kernel(const float* __rest
   Ring rg;
   ring_setup(rg, smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  if (warp == TCT / 32) {
+  if (warp >= TCT / 32) {
     SlabSrc src;
     src.base[0] = reinterpret_cast<const char*>(w.Wqkv_t);
     src.base[1] = reinterpret_cast<const char*>(w.Wo_t);
@@ -410,7 +412,7 @@ __global__ __launch_bounds__(TNT) void layer_back_tc_kernel(const float* __restr
   Ring rg;
   ring_setup(rg, smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  if (warp == TCT / 32) {
+  if (warp >= TCT / 32) {
     SlabSrc src;
     src.base[0] = reinterpret_cast<const char*>(w.Wo2_t);
     src.base[1] = reinterpret_cast<const char*>(w.W1_t);
