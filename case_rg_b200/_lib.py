@@ -83,7 +83,7 @@ _PROTOS = {
     'case_vocab_gemm': [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp],
     'case_vocab_gemm_tc': [vp, vp, vp, vp, i32, i32, i32, vp, vp],
     'case_softmax_mix': [vp, i32, vp, vp, i32, i32, i32, i32, vp],
-    'case_copy_scatter': [vp, i32, i32, vp, vp, vp, i32, i32, vp, i32, i32, i32, i32, i32, vp],
+    'case_copy_scatter': [vp, i32, i32, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp],
     'case_topk_rows': [vp, i32, i32, i32, i32, vp, vp, vp],
     'case_beam_select': [C.POINTER(SelectArgs), vp],
     'case_gru_cell': [vp, vp, vp, vp, vp, i32, vp],

@@ -1,0 +1,273 @@
+// Additive ("bilinear") attention, fused single pass for bf16 storage (BilinearAttention.py:24-60 +
+// CaSE/Model.py:110-111 sums).  attention.cu keeps the two-pass fp32 form.
+//
+// One CTA per (query, key split) walks its keys in tiles of 32 with a cp.async double buffer holding
+// the tile of Uk.mem rows AND the tile of value rows, so the HBM stream of the next tile hides under
+// the MUFU-bound tanh work of the current one.  Per tile:
+//   scores   warp g <-> 32 hidden units, lane <-> key:  partial e[w][key] over the warp's units
+//   softmax  warp w <-> beam row: sum the 8 partials, mask, write the raw score, online (max, sum,
+//            prior-weighted sum) update, p = exp(e - running max)
+//   context  warp kp <-> 4 keys of the tile, lane <-> 8 value columns: acc[w] = acc[w]*scale + p*Mv
+// Tiles whose 32 keys are all padding are skipped outright (no loads, no tanh).
+// Outputs: raw masked scores e [R][S], per split (max, sum, prior-weighted sum) and the context
+// partial relative to that max.  The tanh count (R*S*H per launch, one MUFU op each at 16/clk/SM)
+// is the floor of this kernel; its HBM stream is B*2*S*H*2 bytes.
+#include "common.cuh"
+
+namespace cb {
+
+constexpr int A2T = 256;      // threads
+constexpr int A2K = 32;       // keys per tile
+constexpr int A2ULD = H + 8;  // padded bf16 row of the U tile
+
+__device__ __forceinline__ void a2_cp16(uint32_t dst, const void* src, int nbytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void a2_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void a2_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int WMAX, int DV, bool FAST>
+__global__ __launch_bounds__(A2T) void additive_attn_v2_kernel(
+    const float* __restrict__ qa, const bf16* __restrict__ U, const bf16* __restrict__ Mv,
+    const float* __restrict__ vvec, const uint8_t* __restrict__ mask, const float* __restrict__ prior,
+    const int32_t* __restrict__ tok, int tok_ld, int t, int W, int S, int nsplit, float* __restrict__ scores,
+    float* __restrict__ stats, float* __restrict__ ctx_part) {
+  constexpr int CG = DV / 256;                 // 8-column groups per lane in the context phase
+  constexpr int U_STAGE = A2K * A2ULD * 2;     // bytes
+  constexpr int M_STAGE = A2K * DV * 2;
+  extern __shared__ __align__(128) unsigned char sm[];
+  bf16* Us = reinterpret_cast<bf16*>(sm);                                   // [2][A2K][A2ULD]
+  bf16* Ms = reinterpret_cast<bf16*>(sm + 2 * U_STAGE);                     // [2][A2K][DV]
+  float* qas = reinterpret_cast<float*>(sm + 2 * U_STAGE + 2 * M_STAGE);    // [WMAX][H]
+  float* vs = qas + WMAX * H;                                               // [H]
+  float* er = vs + H;                                                       // [8 groups][WMAX][A2K]
+  float* ps = er + 8 * WMAX * A2K;                                          // [WMAX][A2K]
+  float* sscale = ps + WMAX * A2K;                                          // [8]
+  uint32_t* tvalid = reinterpret_cast<uint32_t*>(sscale + 8);               // [ntiles] any-valid flags
+  const int b = blockIdx.x, sp = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = split_chunk(S, nsplit, AATTN_TILE);
+  const int s_begin = sp * chunk, s_end = min(S, s_begin + chunk);
+  const int ntiles = s_end > s_begin ? (s_end - s_begin + A2K - 1) / A2K : 0;
+  const int r0 = b * W;
+  const uint8_t* mb = mask + (size_t)b * S;
+  const bf16* Ub = U + (size_t)b * S * H;
+  const bf16* Mb = Mv + (size_t)b * S * DV;
+  const float* pb = prior ? prior + (size_t)b * S : nullptr;
+
+  for (int i = tid; i < W * H; i += A2T) qas[i] = qa[(size_t)r0 * H + i];
+  for (int i = tid; i < H; i += A2T) vs[i] = vvec[i];
+  for (int i = warp; i < ntiles; i += A2T / 32) {
+    const int s = s_begin + i * A2K + lane;
+    const unsigned any = __ballot_sync(0xffffffffu, s < s_end && mb[s] != 0);
+    if (lane == 0) tvalid[i] = any;
+  }
+  __syncthreads();
+
+  auto load_tile = [&](int ti, int stage) {
+    const int s0 = s_begin + ti * A2K;
+    const uint32_t ud = smem_u32(Us) + stage * U_STAGE, md = smem_u32(Ms) + stage * M_STAGE;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                         // U: 32 rows x 32 chunks of 16 B
+      const int ci = tid + A2T * i, row = ci >> 5, ch = ci & 31, s = s0 + row;
+      a2_cp16(ud + row * (A2ULD * 2) + ch * 16, Ub + (size_t)min(s, S - 1) * H + ch * 8, s < s_end ? 16 : 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 4 * CG; ++i) {                    // Mv: 32 rows x (DV/8) chunks
+      const int ci = tid + A2T * i, row = ci / (DV / 8), ch = ci % (DV / 8), s = s0 + row;
+      a2_cp16(md + row * (DV * 2) + ch * 16, Mb + (size_t)min(s, S - 1) * DV + ch * 8, s < s_end ? 16 : 0);
+    }
+  };
+  int next = 0;                                           // next tile to load (skipping all-padding tiles)
+  while (next < ntiles && tvalid[next] == 0) ++next;
+  if (next < ntiles) load_tile(next, 0);
+  a2_commit();
+
+  // per-row running statistics live in the lanes of warp w (uniform across the warp)
+  float m_run = -INFINITY, l_run = 0.f, lw_run = 0.f;
+  bool rowvalid = true;
+  if (warp < W && tok) rowvalid = tok[(size_t)(r0 + warp) * tok_ld + t] != 0;
+  float acc[WMAX][CG][8];
+#pragma unroll
+  for (int w = 0; w < WMAX; ++w)
+#pragma unroll
+    for (int c = 0; c < CG; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[w][c][i] = 0.f;
+
+  int stage = 0;
+  for (int ti = 0; ti < ntiles; ++ti) {
+    const int s0 = s_begin + ti * A2K;
+    if (tvalid[ti] == 0) {                               // all padding: scores are -inf, nothing else to do
+      if (warp < W && s0 + lane < s_end) scores[(size_t)(r0 + warp) * S + s0 + lane] = -INFINITY;
+      continue;
+    }
+    int nn = ti + 1;
+    while (nn < ntiles && tvalid[nn] == 0) ++nn;
+    if (nn < ntiles) load_tile(nn, stage ^ 1);
+    a2_commit();
+    a2_wait<1>();
+    __syncthreads();                                      // tile ti (U and Mv) visible to every warp
+
+    // ---- scores: warp = 32 hidden units, lane = key
+    {
+      const bf16* up = Us + (size_t)stage * (A2K * A2ULD) + lane * A2ULD + warp * 32;
+      float e[WMAX];
+#pragma unroll
+      for (int w = 0; w < WMAX; ++w) e[w] = 0.f;
+      if ((tvalid[ti] >> lane) & 1u) {
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) {
+          float u[8];
+          ld8c(up + k, u);
+          const float4 v0 = *reinterpret_cast<const float4*>(vs + warp * 32 + k);
+          const float4 v1 = *reinterpret_cast<const float4*>(vs + warp * 32 + k + 4);
+          const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+          for (int w = 0; w < WMAX; ++w) {
+            if (w < W) {
+              const float4 q0 = *reinterpret_cast<const float4*>(qas + w * H + warp * 32 + k);
+              const float4 q1 = *reinterpret_cast<const float4*>(qas + w * H + warp * 32 + k + 4);
+              const float qq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float x = qq[i] + u[i];
+                e[w] = fmaf(vv[i], FAST ? tanh_fast(x) : tanh_acc(x), e[w]);
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int w = 0; w < WMAX; ++w) er[(warp * WMAX + w) * A2K + lane] = e[w];
+    }
+    __syncthreads();
+    // ---- softmax bookkeeping: warp w = beam row w, lane = key
+    if (warp < W) {
+      const int s = s0 + lane;
+      float e = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) e += er[(g * WMAX + warp) * A2K + lane];
+      const bool ok = rowvalid && ((tvalid[ti] >> lane) & 1u);
+      e = ok ? e : -INFINITY;
+      if (s < s_end) scores[(size_t)(r0 + warp) * S + s] = e;
+      const float tmax = warp_max(e);
+      const float mn = fmaxf(m_run, tmax);
+      const float sc = (m_run == -INFINITY) ? 0.f : fexp(m_run - mn);
+      const float p = (e == -INFINITY) ? 0.f : fexp(e - mn);
+      const float pw = (pb && s < s_end) ? pb[s] * p : p;
+      l_run = fmaf(l_run, sc, warp_sum(p));
+      lw_run = fmaf(lw_run, sc, warp_sum(pw));
+      m_run = mn;
+      ps[warp * A2K + lane] = p;
+      if (lane == 0) sscale[warp] = sc;
+    }
+    __syncthreads();
+    // ---- context: warp = 4 keys of the tile, lane = 8 (x CG) value columns
+    {
+      const bf16* mp = Ms + (size_t)stage * (A2K * DV);
+#pragma unroll
+      for (int w = 0; w < WMAX; ++w) {
+        if (w < W) {
+          const float sc = sscale[w];
+#pragma unroll
+          for (int c = 0; c < CG; ++c)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[w][c][i] *= sc;
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int key = warp * 4 + kk;
+#pragma unroll
+        for (int c = 0; c < CG; ++c) {
+          float mv[8];
+          ld8c(mp + key * DV + c * 256 + lane * 8, mv);
+#pragma unroll
+          for (int w = 0; w < WMAX; ++w) {
+            if (w < W) {
+              const float p = ps[w * A2K + key];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[w][c][i] = fmaf(p, mv[i], acc[w][c][i]);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();                                      // stage and er / ps may be overwritten next iteration
+    stage ^= 1;
+  }
+  a2_wait<0>();
+  __syncthreads();
+  // ---- reduce the 8 key-phase warps: cred[warp][w][DV] through the (now idle) tile buffers
+  float* cred = reinterpret_cast<float*>(sm);             // needs 8 * W * DV * 4 bytes <= 2*U_STAGE + 2*M_STAGE (W <= 4)
+  constexpr int CRED_ROWS = (2 * U_STAGE + 2 * M_STAGE) / (8 * DV * 4);   // rows of W that fit at once
+  for (int w0 = 0; w0 < W; w0 += CRED_ROWS) {
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w) {
+      if (w >= w0 && w < w0 + CRED_ROWS && w < W) {
+#pragma unroll
+        for (int c = 0; c < CG; ++c) {
+          float* d = cred + ((size_t)(warp * CRED_ROWS + (w - w0)) * DV) + c * 256 + lane * 8;
+          *reinterpret_cast<float4*>(d) = make_float4(acc[w][c][0], acc[w][c][1], acc[w][c][2], acc[w][c][3]);
+          *reinterpret_cast<float4*>(d + 4) = make_float4(acc[w][c][4], acc[w][c][5], acc[w][c][6], acc[w][c][7]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < min(CRED_ROWS, W - w0) * DV; i += A2T) {
+      const int wl = i / DV, col = i % DV;
+      float s = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) s += cred[(size_t)(g * CRED_ROWS + wl) * DV + col];
+      ctx_part[((size_t)(r0 + w0 + wl) * nsplit + sp) * DV + col] = s;
+    }
+    __syncthreads();
+  }
+  if (warp < W && lane == 0) {
+    float* st = stats + ((size_t)(r0 + warp) * nsplit + sp) * 4;
+    st[0] = m_run; st[1] = l_run; st[2] = lw_run; st[3] = 0.f;
+  }
+}
+
+template <int WMAX, int DV, bool FAST>
+static int launch_v2(const float* qa, const void* U, const void* Mv, const float* v, const uint8_t* mask,
+                     const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S, int nsplit,
+                     float* scores, float* stats, float* ctx_part, cudaStream_t st) {
+  const int chunk = split_chunk(S, nsplit, AATTN_TILE);
+  const size_t smem = (size_t)2 * A2K * A2ULD * 2 + (size_t)2 * A2K * DV * 2 +
+                      sizeof(float) * ((size_t)WMAX * H + H + 8 * WMAX * A2K + WMAX * A2K + 8) +
+                      sizeof(uint32_t) * (size_t)(chunk / A2K + 1);
+  auto kern = additive_attn_v2_kernel<WMAX, DV, FAST>;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr = true;
+  }
+  kern<<<dim3(B, nsplit), A2T, smem, st>>>(qa, (const bf16*)U, (const bf16*)Mv, v, mask, prior, tok, tok_ld, t, W, S,
+                                           nsplit, scores, stats, ctx_part);
+  return check_launch("case_additive_attn(v2)");
+}
+
+template <int DV, bool FAST>
+static int dispatch_v2(int W, const float* qa, const void* U, const void* Mv, const float* v, const uint8_t* mask,
+                       const float* prior, const int32_t* tok, int tok_ld, int t, int B, int S, int nsplit,
+                       float* scores, float* stats, float* ctx_part, cudaStream_t st) {
+  if (W <= 1) return launch_v2<1, DV, FAST>(qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, scores, stats, ctx_part, st);
+  if (W <= 2) return launch_v2<2, DV, FAST>(qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, scores, stats, ctx_part, st);
+  if (W <= 4) return launch_v2<4, DV, FAST>(qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, scores, stats, ctx_part, st);
+  return launch_v2<8, DV, FAST>(qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, scores, stats, ctx_part, st);
+}
+
+}  // namespace cb
+
+int case_additive_attn_v2(const float* qa, const void* U, const void* Mv, const float* v, const uint8_t* mask,
+                          const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S, int DV,
+                          int nsplit, float* scores, float* stats, float* ctx_part, int fast_tanh, cudaStream_t st) {
+  using namespace cb;
+  if (DV == 256) {
+    if (fast_tanh) return dispatch_v2<256, true>(W, qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, S, nsplit, scores, stats, ctx_part, st);
+    return dispatch_v2<256, false>(W, qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, S, nsplit, scores, stats, ctx_part, st);
+  }
+  if (fast_tanh) return dispatch_v2<512, true>(W, qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, S, nsplit, scores, stats, ctx_part, st);
+  return dispatch_v2<512, false>(W, qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, S, nsplit, scores, stats, ctx_part, st);
+}

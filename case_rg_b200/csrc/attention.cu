@@ -245,9 +245,7 @@ __global__ __launch_bounds__(AT) void additive_attn_kernel(
       float p = 0.f;
       if (s < cnt) {
         const float e = attn_un[(size_t)(r0 + w) * S + s0 + s];
-        p = (e == -INFINITY) ? 0.f : fexp(e - mrow[w]);
-        attn_un[(size_t)(r0 + w) * S + s0 + s] = p;
-        // per-row sums: accumulate through shared atomics-free path below
+        p = (e == -INFINITY) ? 0.f : fexp(e - mrow[w]);     // attn_un keeps the raw score for the scatter
       }
       pt[w * ATB + s] = p;
     }
@@ -377,6 +375,10 @@ extern "C" int case_cross_attn_partial(const float* q2, const void* Kmem, const 
   return dispatch_cross_w<float>(q2, Kmem, Vmem, mask, B, W, S, nsplit, part_ml, part_acc, (cudaStream_t)stream);
 }
 
+int case_additive_attn_v2(const float* qa, const void* U, const void* Mv, const float* v, const uint8_t* mask,
+                          const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S, int DV,
+                          int nsplit, float* scores, float* stats, float* ctx_part, int fast_tanh, cudaStream_t st);
+
 extern "C" int case_additive_attn(const float* qa, const void* U, const void* Mv, const float* v,
                                   const uint8_t* mask, const float* prior, const int32_t* tok, int tok_ld, int t,
                                   int B, int W, int S, int DV, int nsplit, float* attn_un, float* stats,
@@ -386,6 +388,9 @@ extern "C" int case_additive_attn(const float* qa, const void* U, const void* Mv
   CB_REQUIRE(DV == 256 || DV == 512, "case_additive_attn: DV must be 256 or 512");
   CB_REQUIRE(nsplit >= 1 && nsplit <= CASE_MAX_SPLIT, "case_additive_attn: nsplit out of range");
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == CASE_BF16)
+    return case_additive_attn_v2(qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, W, S, DV, nsplit, attn_un, stats,
+                                 ctx_part, fast_tanh, st);
   if (dtype == CASE_BF16) {
     if (fast_tanh) return dispatch_additive_w<bf16, true>(W, qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, S, DV, nsplit, attn_un, stats, ctx_part, st);
     return dispatch_additive_w<bf16, false>(W, qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, S, DV, nsplit, attn_un, stats, ctx_part, st);

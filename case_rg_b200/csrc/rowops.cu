@@ -469,11 +469,11 @@ __device__ __forceinline__ float block_sum_256(float v, float* sh /*[8]*/) {
 }
 
 // merge the per-split partials of one additive attention for row r, column n (DV columns looped by caller)
-struct MergeStat { float e[CASE_MAX_SPLIT]; float Z, Q; };
+struct MergeStat { float e[CASE_MAX_SPLIT]; float Z, Q, M; };
 __device__ __forceinline__ void merge_stats(const float* __restrict__ stats, int r, int nsplit, MergeStat& ms) {
   float M = -INFINITY;
   for (int j = 0; j < nsplit; ++j) M = fmaxf(M, stats[((size_t)r * nsplit + j) * 4]);
-  ms.Z = 0.f; ms.Q = 0.f;
+  ms.Z = 0.f; ms.Q = 0.f; ms.M = M;
   for (int j = 0; j < nsplit; ++j) {
     const float* s = stats + ((size_t)r * nsplit + j) * 4;
     const float e = (s[0] == -INFINITY) ? 0.f : fexp(s[0] - M);
@@ -524,13 +524,14 @@ __global__ __launch_bounds__(NT) void finalize_rows_kernel(
     gates[(size_t)r * 4 + 0] = g0; gates[(size_t)r * 4 + 1] = g1;
     gates[(size_t)r * 4 + 2] = g2; gates[(size_t)r * 4 + 3] = 0.f;
   }
-  // copy weight(r,i,s) = fac * prior * attn_un  ==  gate_{i+1} * (w a) / (1e-8 + sum w a)   (Model.py:110-111,42)
-  if (n < CASE_MAX_SPLIT) {
-    float f0 = 0.f, f1 = 0.f;
-    if (n < ns0 && m0.Z > 0.f) f0 = g1 * (m0.e[n] / m0.Z) / (1e-8f + m0.Q / m0.Z);
-    if (n < ns1 && m1.Z > 0.f) f1 = g2 * (m1.e[n] / m1.Z) / (1e-8f + m1.Q / m1.Z);
-    fac[((size_t)r * 2 + 0) * CASE_MAX_SPLIT + n] = f0;
-    fac[((size_t)r * 2 + 1) * CASE_MAX_SPLIT + n] = f1;
+  // copy weight(r,i,s) = F_i * prior_i[s] * exp(e_i[s] - M_i)  ==  gate_{i+1} * (w a) / (1e-8 + sum w a)
+  // (Model.py:110-111,42) with a = softmax(e): F_i = gate_{i+1} / (Z_i * (1e-8 + Q_i / Z_i))
+  if (n == 0) {
+    float* f = fac + (size_t)r * 2 * CASE_MAX_SPLIT;
+    f[0] = m0.Z > 0.f ? g1 / (m0.Z * (1e-8f + m0.Q / m0.Z)) : 0.f;
+    f[1] = m0.Z > 0.f ? m0.M : 0.f;
+    f[CASE_MAX_SPLIT] = m1.Z > 0.f ? g2 / (m1.Z * (1e-8f + m1.Q / m1.Z)) : 0.f;
+    f[CASE_MAX_SPLIT + 1] = m1.Z > 0.f ? m1.M : 0.f;
   }
 }
 
@@ -544,7 +545,10 @@ __global__ void attn_merge_kernel(const float* __restrict__ stats, const float* 
     for (int j = 0; j < nsplit; ++j) c = fmaf(ctxp[((size_t)r * nsplit + j) * DV + n], ms.e[j], c);
     ctx[(size_t)r * DV + n] = ms.Z > 0.f ? c / ms.Z : 0.f;
   }
-  if (fac && threadIdx.x < nsplit) fac[(size_t)r * fac_ld + threadIdx.x] = ms.Z > 0.f ? ms.e[threadIdx.x] / ms.Z : 0.f;
+  if (fac && threadIdx.x == 0) {     // normalised attention(r, s) = fac[0] * exp(e[s] - fac[1])
+    fac[(size_t)r * fac_ld] = ms.Z > 0.f ? 1.f / ms.Z : 0.f;
+    fac[(size_t)r * fac_ld + 1] = ms.Z > 0.f ? ms.M : 0.f;
+  }
 }
 
 __global__ void gttp_gates_kernel(const float* __restrict__ f, const float* __restrict__ wc,
@@ -558,7 +562,7 @@ __global__ void gttp_gates_kernel(const float* __restrict__ f, const float* __re
     gates[(size_t)r * 4 + 0] = 1.f - pc; gates[(size_t)r * 4 + 1] = pc;
     gates[(size_t)r * 4 + 2] = 0.f; gates[(size_t)r * 4 + 3] = 0.f;
   }
-  if (n < nsplit) fac[(size_t)r * fac_ld + n] *= pc;
+  if (n == 0) fac[(size_t)r * fac_ld] *= pc;
 }
 
 __global__ void gru_cell_kernel(const float* __restrict__ gi, const float* __restrict__ gh,

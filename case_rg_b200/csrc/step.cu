@@ -112,8 +112,8 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
   TRY(case_softmax_mix(a->logits, a->ldv, a->gates, a->dist, a->ldv, R, a->V, 0, st));
   for (int i = 0; i < 2; ++i) {
     TRY(case_copy_scatter(a->map, a->map_ld, a->map_off[i], a->prior[i], a->attn_un[i],
-                          a->fac + (size_t)i * CASE_MAX_SPLIT, 2 * CASE_MAX_SPLIT,
-                          split_chunk(a->S[i], a->nsplit_a[i], AATTN_TILE), a->dist, a->ldv, B, W, a->S[i], a->V, st));
+                          a->fac + (size_t)i * CASE_MAX_SPLIT, 2 * CASE_MAX_SPLIT, a->dist, a->ldv, B, W, a->S[i],
+                          a->V, st));
   }
   if (a->materialize_only) return 0;
   TRY(case_topk_rows(a->dist, a->ldv, R, a->V, W, a->top_vals, a->top_idx, st));
@@ -184,8 +184,8 @@ extern "C" int gttp_decode_step(const gttp_step_args_t* a, int t, case_stream_t 
   TRY(case_vocab_gemm(a->feat, a->Wv, a->bv, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, a->vocab_ws, st));
   TRY(case_gttp_gates(a->feat, a->wc, a->bc, a->gates, a->fac, CASE_MAX_SPLIT, ns[1], R, st));
   TRY(case_softmax_mix(a->logits, a->ldv, a->gates, a->dist, a->ldv, R, a->V, 1, st));
-  TRY(case_copy_scatter(a->map, a->map_ld, 0, nullptr, a->attn_un[1], a->fac, CASE_MAX_SPLIT,
-                        split_chunk(a->Lb, ns[1], AATTN_TILE), a->dist, a->ldv, B, W, a->Lb, a->V, st));
+  TRY(case_copy_scatter(a->map, a->map_ld, 0, nullptr, a->attn_un[1], a->fac, CASE_MAX_SPLIT, a->dist, a->ldv, B, W,
+                        a->Lb, a->V, st));
   if (a->materialize_only) return 0;
   TRY(case_topk_rows(a->dist, a->ldv, R, a->V, W, a->top_vals, a->top_idx, st));
   return select_step(a->mode, B, W, t, a->max_len, a->Tmax, a->BOS, a->EOS, a->UNK, a->PAD, a->top_vals, a->top_idx,

@@ -108,7 +108,7 @@ __global__ __launch_bounds__(SMT) void softmax_mix_kernel(const float* __restric
 __global__ __launch_bounds__(256) void copy_scatter_kernel(const int32_t* __restrict__ map, int map_ld, int map_off,
                                                            const float* __restrict__ prior,
                                                            const float* __restrict__ attn_un,
-                                                           const float* __restrict__ fac, int fac_ld, int split_len,
+                                                           const float* __restrict__ fac, int fac_ld,
                                                            float* __restrict__ dist, int ldd, int W, int S, int V,
                                                            int vec_ok) {
   const int r = blockIdx.y, b = r / W;
@@ -117,7 +117,8 @@ __global__ __launch_bounds__(256) void copy_scatter_kernel(const int32_t* __rest
   const float* a = attn_un + (size_t)r * S;
   const float* p = prior ? prior + (size_t)b * S : nullptr;
   const int32_t* mp = map + (size_t)b * map_ld + map_off;
-  const float* f = fac + (size_t)r * fac_ld;
+  const float F = fac[(size_t)r * fac_ld], M = fac[(size_t)r * fac_ld + 1];
+  if (F == 0.f) return;
   float* d = dist + (size_t)r * ldd;
   float av[4], pv[4] = {1.f, 1.f, 1.f, 1.f};
   int iv[4];
@@ -130,7 +131,7 @@ __global__ __launch_bounds__(256) void copy_scatter_kernel(const int32_t* __rest
     iv[0] = ii.x; iv[1] = ii.y; iv[2] = ii.z; iv[3] = ii.w;
   } else {
     for (int u = 0; u < 4; ++u) {
-      av[u] = u < n ? a[s4 + u] : 0.f;
+      av[u] = u < n ? a[s4 + u] : -INFINITY;
       if (p) pv[u] = u < n ? p[s4 + u] : 0.f;
       iv[u] = u < n ? mp[s4 + u] : 0;
     }
@@ -138,7 +139,8 @@ __global__ __launch_bounds__(256) void copy_scatter_kernel(const int32_t* __rest
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     if (u >= n) break;
-    const float c = f[(s4 + u) / split_len] * pv[u] * av[u];
+    if (av[u] == -INFINITY) continue;                       // masked source position
+    const float c = F * pv[u] * fexp(av[u] - M);
     if (c != 0.f && (unsigned)iv[u] < (unsigned)V) atomicAdd(d + iv[u], c);
   }
 }
@@ -232,14 +234,14 @@ extern "C" int case_softmax_mix(const float* logits, int ldl, const float* gates
 }
 
 extern "C" int case_copy_scatter(const int32_t* map, int map_ld, int map_off, const float* prior,
-                                 const float* attn_un, const float* fac, int fac_ld, int split_len, float* dist,
+                                 const float* attn_un, const float* fac, int fac_ld, float* dist,
                                  int ldd, int B, int W, int S, int V, case_stream_t stream) {
-  CB_REQUIRE(map && attn_un && fac && dist && B > 0 && W > 0 && S > 0 && split_len > 0, "case_copy_scatter: bad arguments");
+  CB_REQUIRE(map && attn_un && fac && dist && B > 0 && W > 0 && S > 0 && fac_ld >= 2, "case_copy_scatter: bad arguments");
   const int vec_ok = (S % 4 == 0) && (map_ld % 4 == 0) && (map_off % 4 == 0) && ((uintptr_t)map % 16 == 0) &&
                      ((uintptr_t)attn_un % 16 == 0) && (!prior || (uintptr_t)prior % 16 == 0);
   dim3 grid((S + 1023) / 1024, B * W);
   copy_scatter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(map, map_ld, map_off, prior, attn_un, fac, fac_ld,
-                                                              split_len, dist, ldd, W, S, V, vec_ok);
+                                                              dist, ldd, W, S, V, vec_ok);
   return check_launch("case_copy_scatter");
 }
 

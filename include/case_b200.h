@@ -145,20 +145,21 @@ int case_layer_back(const float* b_in, const float* part_ml, const float* part_a
 /* ---------------------------------------------------------------- additive ("bilinear") attention */
 
 /* Fused score + softmax-partials + context partials (BilinearAttention.py:24-60, K6-K8):
- *   e[r,s] = v . tanh(qa[r] + U[b,s]),  masked where !mask[b,s] or !rowvalid[r]
+ *   e[r,s] = v . tanh(qa[r] + U[b,s]),  -inf where !mask[b,s] or !rowvalid[r]
  * qa: [R][H] = Wq.query + b (from case_row_linear); U: [B][S][H] (= Uk.mem) and Mv: [B][S][DV]
  * (values) in dtype; prior: fp32 [B][S] or NULL (CaSE/Model.py:110).  rowvalid: row r is valid iff
  * tok[r*tok_ld + t] != 0 (tok == NULL -> all valid).
- * Outputs: attn_un [R][S] = exp(e - m_split) (unnormalised), stats [R][nsplit][4] =
- * (m, sum exp, sum prior*exp, 0), ctx_part [R][nsplit][DV].  fast_tanh: 1 = tanh.approx.f32. */
+ * Outputs: attn_un [R][S] = the raw masked scores e; per key split stats [R][nsplit][4] =
+ * (m = max e, sum exp(e-m), sum prior*exp(e-m), 0) and ctx_part [R][nsplit][DV] = sum exp(e-m)*Mv.
+ * fast_tanh: 1 = tanh.approx.f32. */
 int case_additive_attn(const float* qa, const void* U, const void* Mv, const float* v, const uint8_t* mask,
                        const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S, int DV,
                        int nsplit, float* attn_un, float* stats, float* ctx_part, int fast_tanh, int dtype,
                        case_stream_t stream);
 
 /* CaSE row finaliser (Model.py:110-113, 39): hN = LN(h); merges both attentions' partials into
- * ctx0/ctx1, computes the mixture gates softmax(Wm.[hN;ctx0;ctx1]+bm) and the per-split scale
- * factors so that copy weight(r,i,s) = fac[r][i][split(s)] * prior_i[b,s] * attn_un_i[r,s]
+ * ctx0/ctx1, computes the mixture gates softmax(Wm.[hN;ctx0;ctx1]+bm) and, per memory i, the pair
+ * (F_i, M_i) = fac[r][i][0..1] such that copy weight(r,i,s) = F_i * prior_i[b,s] * exp(e_i[r,s] - M_i)
  * equals gate_{i+1} * p_i[r,s] of the reference.  gates: [R][4], fac: [R][2][CASE_MAX_SPLIT]. */
 int case_finalize_rows(const float* h, const float* lnN_g, const float* lnN_b, const float* stats0,
                        const float* ctxp0, int nsplit0, const float* stats1, const float* ctxp1, int nsplit1,
@@ -186,12 +187,13 @@ size_t case_vocab_tc_packed_weight_bytes(int V);
 int case_softmax_mix(const float* logits, int ldl, const float* gates, float* dist, int ldd, int R, int V,
                      int mask_col0, case_stream_t stream);
 
-/* dist[r, map[b,s]] += fac[r][which][s / split_len] * prior[b,s] * attn_un[r,s]
+/* dist[r, map[b,s]] += F[r] * prior[b,s] * exp(e[r,s] - M[r])   with (F, M) = fac[r*fac_ld + 0..1]
  * (replaces the one-hot bmm of Model.py:43 / GTTP Model.py:37-40 and build_map Utils.py:344-355;
- * indices are used exactly as given, so targets are bit-exact).  prior may be NULL (=1). */
+ * indices are used exactly as given, so targets are bit-exact).  prior may be NULL (=1); e = -inf
+ * marks a masked source position. */
 int case_copy_scatter(const int32_t* map, int map_ld, int map_off, const float* prior, const float* attn_un,
-                      const float* fac, int fac_ld, int split_len, float* dist, int ldd, int B, int W, int S,
-                      int V, case_stream_t stream);
+                      const float* fac, int fac_ld, float* dist, int ldd, int B, int W, int S, int V,
+                      case_stream_t stream);
 
 /* Per-row top-k, values descending, ties -> lower index first (Utils.topk, Utils.py:156-168). */
 int case_topk_rows(const float* dist, int ldd, int R, int V, int k, float* vals, int32_t* idx,
@@ -226,12 +228,12 @@ int case_beam_select(const case_select_args_t* a, case_stream_t stream);
 int case_gru_cell(const float* gi, const float* gh, const float* h_prev, const int32_t* gather_idx,
                   float* h_out, int R, case_stream_t stream);
 
-/* GTTP row finaliser: merges one attention's partials -> ctx [R][DV]; optionally the per-split
- * factors fac[r][split] = exp(m_split - M) / Z (bg_attn, normalised) */
+/* GTTP row finaliser: merges one attention's partials -> ctx [R][DV]; optionally (fac != NULL)
+ * fac[r][0..1] = (1/Z, M) so that the normalised attention is fac[0] * exp(e - fac[1]) */
 int case_attn_merge(const float* stats, const float* ctx_part, int nsplit, int DV, float* ctx, float* fac,
                     int fac_ld, int R, case_stream_t stream);
 
-/* p_copy = sigmoid(wc.f + bc); gates[r] = (1-p_copy, p_copy, 0, 0); fac[r][*] *= p_copy
+/* p_copy = sigmoid(wc.f + bc); gates[r] = (1-p_copy, p_copy, 0, 0); fac[r][0] *= p_copy
  * (GTTP/Model.py:31-41). */
 int case_gttp_gates(const float* f, const float* wc, const float* bc, float* gates, float* fac, int fac_ld,
                     int nsplit, int R, case_stream_t stream);

@@ -82,3 +82,58 @@ def test_row_linear_stream_vs_torch(K, N, nseg, dtype):
     assert rel_err(out, want) < 2e-5, rel_err(out, want)
 
 
+
+
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+@pytest.mark.parametrize('W,S,DV,nsplit,use_prior', [(1, 60, 256, 1, True), (4, 2560, 256, 10, True), (4, 1000, 512, 3, False),
+                                                      (8, 333, 256, 2, True), (2, 130, 512, 2, False)])
+def test_additive_attention_vs_torch(W, S, DV, nsplit, use_prior, dtype):
+    """Fused additive attention (scores, softmax partials, context partials) against torch, including
+    all-padding tiles, a PAD-input row and the prior-weighted sum."""
+    from case_rg_b200 import _lib as L
+    B, H = 3, 256
+    g = torch.Generator().manual_seed(W * 100 + S)
+    td, cd = (torch.float32, L.F32) if dtype == 'fp32' else (torch.bfloat16, L.BF16)
+    qa = torch.randn(B * W, H, generator=g).to(DEV)
+    U = torch.randn(B, S, H, generator=g).to(DEV).to(td)
+    Mv = torch.randn(B, S, DV, generator=g).to(DEV).to(td)
+    v = (torch.randn(H, generator=g) * 0.3).to(DEV)
+    mask = torch.rand(B, S, generator=g) > 0.25
+    mask[:, 0] = True
+    if S > 200:
+        mask[1, 64:192] = False            # whole tiles of padding
+    mask = mask.to(DEV)
+    prior = torch.rand(B, S, generator=g).to(DEV) if use_prior else None
+    tok = torch.ones(B * W, 4, dtype=torch.int32, device=DEV)
+    tok[0, 2] = 0                          # row 0 consumes a PAD token at t = 2 -> fully masked row
+    scores = torch.full((B * W, S), float('nan'), device=DEV)
+    stats = torch.zeros(B * W, nsplit, 4, device=DEV)
+    ctxp = torch.zeros(B * W, nsplit, DV, device=DEV)
+    L.call('case_additive_attn', qa.data_ptr(), U.data_ptr(), Mv.data_ptr(), v.data_ptr(), mask.to(torch.uint8).data_ptr(),
+           L.ptr(prior), tok.data_ptr(), 4, 2, B, W, S, DV, nsplit, scores.data_ptr(), stats.data_ptr(), ctxp.data_ptr(),
+           0, cd, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    Uf, Mf = U.float(), Mv.float()
+    e = (torch.tanh(qa.view(B, W, 1, H) + Uf.view(B, 1, S, H)) @ v).view(B * W, S)
+    ok = mask.repeat_interleave(W, 0).clone()
+    ok[0] = False
+    e = e.masked_fill(~ok, float('-inf'))
+    assert torch.equal(torch.isinf(scores), torch.isinf(e))
+    fin = ~torch.isinf(e)
+    tol = 1e-5 if dtype == 'fp32' else 1e-5
+    assert float((scores[fin] - e[fin]).abs().max()) < 1e-4 * max(1.0, float(e[fin].abs().max()))
+    # merge the partials the way the finalisers do and compare with a plain softmax attention
+    m = stats[..., 0]
+    M = m.max(1, keepdim=True).values
+    w = torch.where(torch.isinf(m), torch.zeros_like(m), torch.exp(m - M))
+    Z = (stats[..., 1] * w).sum(1)
+    Q = (stats[..., 2] * w).sum(1)
+    ctx = (ctxp * w.unsqueeze(-1)).sum(1) / Z.clamp_min(1e-30).unsqueeze(-1)
+    a = torch.softmax(e, 1)
+    a = torch.where(torch.isnan(a), torch.zeros_like(a), a)
+    want_ctx = torch.bmm(a.view(B, W, S), Mf).view(B * W, DV)
+    live = Z > 0
+    assert bool((~live)[0]) and bool(live[1:].all())
+    assert rel_err(ctx[live], want_ctx[live]) < 2e-4
+    pr = prior.repeat_interleave(W, 0) if use_prior else torch.ones_like(a)
+    assert rel_err((Q / Z.clamp_min(1e-30))[live], (pr * a).sum(1)[live]) < 2e-4

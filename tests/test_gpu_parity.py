@@ -282,25 +282,30 @@ def test_scatter_linearity_and_exact_targets():
     ldd = 784
     g = torch.Generator().manual_seed(7)
     mp = torch.randint(0, V, (B, S), generator=g, dtype=torch.int32).to(DEV)
-    attn = torch.rand(B * W, S, generator=g).to(DEV)
+    e = (torch.randn(B * W, S, generator=g) * 2).to(DEV)          # raw attention scores
+    e[:, ::11] = float('-inf')                                    # masked source positions
     prior = torch.rand(B, S, generator=g).to(DEV)
-    fac = torch.rand(B * W, L.MAX_SPLIT, generator=g).to(DEV)
+    fac = torch.zeros(B * W, L.MAX_SPLIT, device=DEV)
+    fac[:, 0] = torch.rand(B * W, generator=g).to(DEV) + 0.1      # F
+    fac[:, 1] = e.max(1).values                                   # M
     st = torch.cuda.current_stream().cuda_stream
 
-    def run(a):
+    def run(f):
         d = torch.zeros(B * W, ldd, device=DEV)
-        L.call('case_copy_scatter', mp.data_ptr(), S, 0, prior.data_ptr(), a.data_ptr(), fac.data_ptr(), L.MAX_SPLIT,
-               128, d.data_ptr(), ldd, B, W, S, V, st)
+        L.call('case_copy_scatter', mp.data_ptr(), S, 0, prior.data_ptr(), e.data_ptr(), f.data_ptr(), L.MAX_SPLIT,
+               d.data_ptr(), ldd, B, W, S, V, st)
         torch.cuda.synchronize()
         return d[:, :V]
-    d1 = run(attn)
-    coef = fac[:, :3].repeat_interleave(128, dim=1)[:, :S] * prior.repeat_interleave(W, 0) * attn
+    d1 = run(fac)
+    coef = fac[:, :1] * prior.repeat_interleave(W, 0) * torch.exp(e - fac[:, 1:2])
     oh = torch.zeros(B, S, V, device=DEV).scatter_(2, mp.long().unsqueeze(2), 1.0)
     want = torch.bmm(coef.view(B, W, S), oh).view(B * W, V)
     assert rel_err(d1, want) < 1e-5
     touched = torch.zeros(B, V, dtype=torch.bool, device=DEV).scatter_(1, mp.long(), True).repeat_interleave(W, 0)
     assert float(d1[~touched].abs().max()) == 0.0          # nothing lands off-target
-    d2 = run(attn * 2)
+    fac2 = fac.clone()
+    fac2[:, 0] *= 2
+    d2 = run(fac2)
     assert rel_err(d2, d1 * 2) < 1e-5
 
 
