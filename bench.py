@@ -39,6 +39,7 @@ def parse():
     ap.add_argument('--vocab-impl', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-pdl', action='store_true', help='disable programmatic dependent launch (A/B)')
     ap.add_argument('--batch', type=int, default=WORKLOAD['B'])
     ap.add_argument('--beam', type=int, default=WORKLOAD['W'])
     ap.add_argument('--profile', type=int, default=0,
@@ -183,6 +184,8 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     w = WORKLOAD
     B, W, T, V = args.batch, args.beam, w['T'], w['V']
+    if args.no_pdl:
+        L.load().case_set_pdl(0)
 
     sd = syn.make_case_decoder_state(WSEED, V, w['H'])
     vocab_impl = args.vocab_impl if args.vocab_impl is not None else (1 if args.dtype == 'bf16' else 0)
@@ -283,7 +286,7 @@ def main():
     line = dict(metric='answer_tokens_per_s', value=value, unit='tokens/s', n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype=args.dtype if args.dtype == 'bf16' else 'f32', data='synthetic',
-                config=config_dict(args, dict(cuda_graph=not args.no_graph, vocab_gemm='tcgen05' if vocab_impl == 1 else 'simt')),
+                config=config_dict(args, dict(cuda_graph=not args.no_graph, pdl=not args.no_pdl, vocab_gemm='tcgen05' if vocab_impl == 1 else 'simt')),
                 ms_per_decode_step=ms / args.steps / T, answer_tokens_per_step=tokens_per_step,
                 e2e=dict(value=e2e_value, unit='tokens/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          ms_per_step=ms_e2e / args.steps),

@@ -89,6 +89,7 @@ _PROTOS = {
     'case_gru_cell': [vp, vp, vp, vp, vp, i32, vp],
     'case_attn_merge': [vp, vp, i32, i32, vp, vp, i32, i32, vp],
     'case_gttp_gates': [vp, vp, vp, vp, vp, i32, i32, i32, vp],
+    'case_set_pdl': [i32],
     'case_decode_step': [C.POINTER(StepArgs), i32, vp],
     'gttp_decode_step': [C.POINTER(GttpStepArgs), i32, vp],
 }

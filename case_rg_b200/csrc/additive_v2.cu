@@ -44,6 +44,8 @@ __global__ __launch_bounds__(A2T) void additive_attn_v2_kernel(
   float* ps = er + 8 * WMAX * A2K;                                          // [WMAX][A2K]
   float* sscale = ps + WMAX * A2K;                                          // [8]
   uint32_t* tvalid = reinterpret_cast<uint32_t*>(sscale + 8);               // [ntiles] any-valid flags
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, sp = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int chunk = split_chunk(S, nsplit, AATTN_TILE);
   const int s_begin = sp * chunk, s_end = min(S, s_begin + chunk);
@@ -243,7 +245,7 @@ static int launch_v2(const float* qa, const void* U, const void* Mv, const float
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     attr = true;
   }
-  kern<<<dim3(B, nsplit), A2T, smem, st>>>(qa, (const bf16*)U, (const bf16*)Mv, v, mask, prior, tok, tok_ld, t, W, S,
+  launch_k(kern, dim3(B, nsplit), A2T, smem, st, qa, (const bf16*)U, (const bf16*)Mv, v, mask, prior, tok, tok_ld, t, W, S,
                                            nsplit, scores, stats, ctx_part);
   return check_launch("case_additive_attn(v2)");
 }

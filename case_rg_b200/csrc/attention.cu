@@ -26,6 +26,8 @@ __global__ __launch_bounds__(XT) void cross_attn_partial_kernel(
   __shared__ __align__(16) float Vs[XT][HD];
   __shared__ float ps[WMAX][XT];
   __shared__ float wred[2][XT / 32][WMAX];
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, hh = blockIdx.y, sp = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int chunk = split_chunk(S, nsplit, XT);
@@ -145,6 +147,8 @@ __global__ __launch_bounds__(AT) void additive_attn_kernel(
   float* mrow = er + NG * WMAX * TS;                           // [8] block max per row
   float* wsum = mrow + 8;                                      // [8 warps][8]
   T* Us = reinterpret_cast<T*>(wsum + 128);                    // [TS][LD]
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, sp = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int chunk = split_chunk(S, nsplit, ATB);
   const int s_begin = sp * chunk, s_end = min(S, s_begin + chunk);
@@ -327,7 +331,7 @@ static int launch_additive(const float* qa, const void* U, const void* Mv, const
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr_set = true;
   }
-  kern<<<dim3(B, nsplit), AT, smem, st>>>(qa, (const T*)U, (const T*)Mv, v, mask, prior, tok, tok_ld, t, W, S, DV,
+  launch_k(kern, dim3(B, nsplit), AT, smem, st, qa, (const T*)U, (const T*)Mv, v, mask, prior, tok, tok_ld, t, W, S, DV,
                                           nsplit, attn_un, stats, ctx_part);
   return check_launch("case_additive_attn");
 }
@@ -346,7 +350,7 @@ static int dispatch_additive_w(int W, const float* qa, const void* U, const void
 template <typename T, int WMAX>
 static int launch_cross(const float* q2, const void* K, const void* V, const uint8_t* mask, int B, int W, int S,
                         int nsplit, float* part_ml, float* part_acc, cudaStream_t st) {
-  cross_attn_partial_kernel<T, WMAX><<<dim3(B, NH, nsplit), XT, 0, st>>>(q2, (const T*)K, (const T*)V, mask, W, S,
+  launch_k(cross_attn_partial_kernel<T, WMAX>, dim3(B, NH, nsplit), XT, 0, st, q2, (const T*)K, (const T*)V, mask, W, S,
                                                                           nsplit, part_ml, part_acc);
   return check_launch("case_cross_attn_partial");
 }
@@ -446,6 +450,8 @@ __global__ __launch_bounds__(XM_WARPS * 32) void cross_attn_mma_kernel(
     const uint8_t* __restrict__ mask, int W, int S, int nsplit, float* __restrict__ part_ml,
     float* __restrict__ part_acc) {
   extern __shared__ __align__(128) unsigned char xm_smem[];   // [warp][stage][K|V][XM_TILE_BYTES]
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, hh = blockIdx.y, sp = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int chunk = split_chunk(S, nsplit, XM_TILE * XM_WARPS);
@@ -586,7 +592,7 @@ extern "C" int case_cross_attn_partial_tc(const float* q2, const void* Kmem, con
   CB_REQUIRE(q2 && Kmem && Vmem && mask && part_ml && part_acc, "case_cross_attn_partial_tc: null pointer");
   CB_REQUIRE(B > 0 && W >= 1 && W <= CASE_MAX_W && S > 0, "case_cross_attn_partial_tc: bad sizes");
   CB_REQUIRE(nsplit >= 1 && nsplit <= CASE_MAX_XSPLIT, "case_cross_attn_partial_tc: nsplit out of range");
-  cb::cross_attn_mma_kernel<<<dim3(B, cb::NH, nsplit), cb::XM_WARPS * 32, cb::XM_SMEM, (cudaStream_t)stream>>>(
+  launch_k(cb::cross_attn_mma_kernel, dim3(B, cb::NH, nsplit), cb::XM_WARPS * 32, cb::XM_SMEM, (cudaStream_t)stream, 
       q2, (const cb::bf16*)Kmem, (const cb::bf16*)Vmem, mask, W, S, nsplit, part_ml, part_acc);
   return cb::check_launch("case_cross_attn_partial_tc");
 }

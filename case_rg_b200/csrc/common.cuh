@@ -16,6 +16,26 @@ constexpr float LN_EPS = 1e-5f;
 
 void set_error(const char* msg);
 int check_launch(const char* what);
+extern int g_use_pdl;          // programmatic dependent launch on every kernel of the step (step.cu)
+extern cudaError_t g_launch_err;
+
+// Launch helper: same as kernel<<<grid, block, smem, stream>>>(args...) plus the programmatic
+// stream-serialization attribute, so the next kernel's CTAs may be scheduled (and run their
+// prologue: barrier init, weight prefetch) while this kernel drains.  Every kernel calls
+// pdl_wait() before it touches anything an earlier kernel wrote.
+template <typename T> struct ident { typedef T type; };
+template <typename... KA>
+inline void launch_k(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                     typename ident<KA>::type... args) {
+  void* pa[] = {(void*)&args...};
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 1 : 0;
+  g_launch_err = cudaLaunchKernelExC(&cfg, (const void*)kern, pa);
+}
 
 #define CB_REQUIRE(cond, msg)        \
   do {                               \
@@ -88,6 +108,10 @@ __device__ __forceinline__ void ld8c(const bf16* p, float (&o)[8]) {
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// programmatic dependent launch: let the dependent grid start early / wait for the producer grid
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- reductions
 __device__ __forceinline__ float warp_sum(float v) {

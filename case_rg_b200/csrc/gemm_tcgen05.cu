@@ -35,6 +35,9 @@ __device__ __forceinline__ void tc_mbar_init(uint32_t bar, int count) {
 __device__ __forceinline__ void tc_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void tc_expect_tx_only(uint32_t bar, uint32_t bytes) {   // no arrival
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tc_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
@@ -100,6 +103,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // fp32 [R][256] -> bf16 canonical blocks of 256 rows (zero padded)
 __global__ void pack_activations_kernel(const float* __restrict__ f, bf16* __restrict__ out, int R) {
+  pdl_trigger();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;        // one thread per (row, k-chunk of 8)
   const int nblk = (R + TC_NB - 1) / TC_NB;
   if (idx >= nblk * TC_NB * (TC_K / 8)) return;
@@ -145,21 +150,27 @@ __global__ __launch_bounds__(128, 1) void vocab_gemm_tc_kernel(const bf16* __res
   const uint32_t tmem = *s_tmem;
 
   constexpr uint32_t W_CH = TC_W_BYTES / TC_KCH;       // 16 KB of weights per K chunk
+  // one issuing lane per K chunk, in four different warps: a warp keeps only one bulk copy in
+  // flight at a time (profiles/micro/bulk_bench.cu), so spreading the issue overlaps the chunks.
+  // The weight tile is a constant: it is requested before the dependency wait.
+  if (lane == 0) {
+    const char* wsrc = reinterpret_cast<const char*>(Wp) + (size_t)tile * TC_W_BYTES;
+    tc_expect_tx_only(s_bar + 8 * warp, W_CH);
+    tc_bulk_g2s(s_w + warp * W_CH, wsrc + (size_t)warp * W_CH, W_CH, s_bar + 8 * warp);
+  }
+  pdl_trigger();
+  pdl_wait();
   for (int blk = 0; blk < nblk; ++blk) {
     const int rows = min(TC_NB, R - blk * TC_NB);
     const int N = (rows + 15) & ~15;
     const uint32_t par = blk & 1;
-    // one issuing lane per K chunk, in four different warps: a warp keeps only one bulk copy in
-    // flight at a time (profiles/micro/bulk_bench.cu), so spreading the issue overlaps the chunks
     if (lane == 0) {
       const int c = warp;                                    // TC_KCH == number of warps
-      const char* wsrc = reinterpret_cast<const char*>(Wp) + (size_t)tile * TC_W_BYTES;
       const char* asrc = reinterpret_cast<const char*>(Ap) + (size_t)blk * TC_A_BYTES;
       const uint32_t a_ch = (uint32_t)N * (TC_K / TC_KCH) * 2;     // N rows x 64 k of bf16, contiguous
       const uint32_t bar = s_bar + 8 * c;
-      tc_expect_tx(bar, (blk == 0 ? W_CH : 0) + a_ch);
+      tc_expect_tx(bar, a_ch);                               // the (single) arrival of this phase
       tc_bulk_g2s(s_a + c * a_ch, asrc + (size_t)c * a_ch, a_ch, bar);
-      if (blk == 0) tc_bulk_g2s(s_w + c * W_CH, wsrc + (size_t)c * W_CH, W_CH, bar);
     }
     if (tid == 0) {
       const uint32_t idesc = umma_idesc(TC_M, N);
@@ -223,10 +234,10 @@ extern "C" int case_vocab_gemm_tc(const float* f, const void* Wp, const float* b
   }
   const int nblk = (R + TC_NB - 1) / TC_NB;
   const int n = nblk * TC_NB * (TC_K / 8);
-  pack_activations_kernel<<<(n + 255) / 256, 256, 0, st>>>(f, (bf16*)workspace, R);
+  launch_k(pack_activations_kernel, (n + 255) / 256, 256, 0, st, f, (bf16*)workspace, R);
   int rc = check_launch("case_vocab_gemm_tc(pack)");
   if (rc) return rc;
-  vocab_gemm_tc_kernel<<<(V + TC_M - 1) / TC_M, 128, TC_SMEM, st>>>((const bf16*)Wp, (const bf16*)workspace, bias,
+  launch_k(vocab_gemm_tc_kernel, (V + TC_M - 1) / TC_M, 128, TC_SMEM, st, (const bf16*)Wp, (const bf16*)workspace, bias,
                                                                      logits, R, V, ldl);
   return check_launch("case_vocab_gemm_tc");
 }

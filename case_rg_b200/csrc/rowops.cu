@@ -172,6 +172,8 @@ __device__ __forceinline__ void ln_rows_smem(float* xs, int ld, const float* __r
 __global__ void embed_kernel(const float* __restrict__ E, const float* __restrict__ pe,
                              const int32_t* __restrict__ tok, int tok_ld, int t, float scale,
                              float* __restrict__ x, int R) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x * 4 + (threadIdx.x >> 6);
   if (r >= R) return;
   const int c = (threadIdx.x & 63) * 4;
@@ -185,6 +187,8 @@ __global__ void embed_kernel(const float* __restrict__ E, const float* __restric
 __global__ void layernorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                       const float* __restrict__ b, float* __restrict__ y, int R) {
   __shared__ __align__(16) float xs[RB][H];
+  pdl_trigger();
+  pdl_wait();
   const int r0 = blockIdx.x * RB;
   for (int i = threadIdx.x; i < RB * H; i += NT) {
     const int rb = i / H, r = r0 + rb;
@@ -221,7 +225,9 @@ __global__ __launch_bounds__(NT) void row_linear_kernel(case_rowlin_args_t a) {
       reinterpret_cast<const char*>(a.Wt) + (size_t)blockIdx.y * a.K * 256 * sizeof(T);
   ws.total = a.K / KTile<T>::KT;
   ws.end[0] = ws.end[1] = ws.end[2] = ws.total;
-  ws.start();
+  ws.start();          // weights are constants: their stream starts before the dependency wait
+  pdl_trigger();
+  pdl_wait();
   int off = 0;
   for (int s = 0; s < a.nseg; ++s) {
     const case_seg_t sg = a.seg[s];
@@ -282,7 +288,9 @@ __global__ __launch_bounds__(NT) void layer_front_kernel(const float* __restrict
   ws.base[2] = reinterpret_cast<const char*>(w.Wq2_t);
   ws.end[0] = 3 * TPM; ws.end[1] = 4 * TPM; ws.end[2] = 5 * TPM;
   ws.total = 5 * TPM;
-  ws.start();
+  ws.start();          // weights are constants: their stream starts before the dependency wait
+  pdl_trigger();
+  pdl_wait();
 
   for (int i = tid; i < RB * H; i += NT) {
     const int rb = i / H, r = r0 + rb;
@@ -402,7 +410,9 @@ __global__ __launch_bounds__(NT) void layer_back_kernel(const float* __restrict_
   ws.base[2] = reinterpret_cast<const char*>(w.W2_t);
   ws.end[0] = TPM; ws.end[1] = 2 * TPM; ws.end[2] = 3 * TPM;
   ws.total = 3 * TPM;
-  ws.start();
+  ws.start();          // weights are constants: their stream starts before the dependency wait
+  pdl_trigger();
+  pdl_wait();
 
 #pragma unroll
   for (int rb = 0; rb < RB; ++rb) {
@@ -490,6 +500,8 @@ __global__ __launch_bounds__(NT) void finalize_rows_kernel(
     const float* __restrict__ Wm, const float* __restrict__ bm, float* __restrict__ hN,
     float* __restrict__ ctx0, float* __restrict__ ctx1, float* __restrict__ gates, float* __restrict__ fac) {
   __shared__ float sh[8];
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x, n = threadIdx.x;
   const float x = h[(size_t)r * H + n];
   const float mean = block_sum_256(x, sh) * (1.f / H);
@@ -537,6 +549,8 @@ __global__ __launch_bounds__(NT) void finalize_rows_kernel(
 
 __global__ void attn_merge_kernel(const float* __restrict__ stats, const float* __restrict__ ctxp, int nsplit,
                                   int DV, float* __restrict__ ctx, float* __restrict__ fac, int fac_ld) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x;
   MergeStat ms;
   merge_stats(stats, r, nsplit, ms);
@@ -555,6 +569,8 @@ __global__ void gttp_gates_kernel(const float* __restrict__ f, const float* __re
                                   const float* __restrict__ bc, float* __restrict__ gates,
                                   float* __restrict__ fac, int fac_ld, int nsplit) {
   __shared__ float sh[8];
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x, n = threadIdx.x;
   const float z = block_sum_256(f[(size_t)r * H + n] * __ldg(wc + n), sh) + __ldg(bc);
   const float pc = 1.f / (1.f + expf(-z));
@@ -568,6 +584,8 @@ __global__ void gttp_gates_kernel(const float* __restrict__ f, const float* __re
 __global__ void gru_cell_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
                                 const float* __restrict__ hp, const int32_t* __restrict__ gidx,
                                 float* __restrict__ ho) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x, n = threadIdx.x;
   const float* a = gi + (size_t)r * 3 * H;
   const float* c = gh + (size_t)r * 3 * H;
@@ -586,14 +604,14 @@ using namespace cb;
 extern "C" int case_embed_rows(const float* E, const float* pe, const int32_t* tok, int tok_ld, int t,
                                float scale, float* x, int R, case_stream_t stream) {
   CB_REQUIRE(E && tok && x && R > 0 && t >= 0, "case_embed_rows: bad arguments");
-  embed_kernel<<<(R + 3) / 4, 256, 0, (cudaStream_t)stream>>>(E, pe, tok, tok_ld, t, scale, x, R);
+  launch_k(embed_kernel, (R + 3) / 4, 256, 0, (cudaStream_t)stream, E, pe, tok, tok_ld, t, scale, x, R);
   return check_launch("case_embed_rows");
 }
 
 extern "C" int case_layernorm_rows(const float* x, const float* g, const float* b, float* y, int R,
                                    case_stream_t stream) {
   CB_REQUIRE(x && g && b && y && R > 0, "case_layernorm_rows: bad arguments");
-  layernorm_rows_kernel<<<(R + RB - 1) / RB, NT, 0, (cudaStream_t)stream>>>(x, g, b, y, R);
+  launch_k(layernorm_rows_kernel, (R + RB - 1) / RB, NT, 0, (cudaStream_t)stream, x, g, b, y, R);
   return check_launch("case_layernorm_rows");
 }
 
@@ -625,9 +643,9 @@ extern "C" int case_row_linear(const case_rowlin_args_t* a, case_stream_t stream
     attr = true;
   }
   if (a->dtype == CASE_BF16) {
-    row_linear_kernel<bf16><<<grid, NT, smem, (cudaStream_t)stream>>>(*a);
+    launch_k(row_linear_kernel<bf16>, grid, NT, smem, (cudaStream_t)stream, *a);
   } else {
-    row_linear_kernel<float><<<grid, NT, smem, (cudaStream_t)stream>>>(*a);
+    launch_k(row_linear_kernel<float>, grid, NT, smem, (cudaStream_t)stream, *a);
   }
   return check_launch("case_row_linear");
 }
@@ -649,10 +667,10 @@ extern "C" int case_layer_front(const float* h, const case_layer_weights_t* w, v
     attr = true;
   }
   if (dtype == CASE_BF16)
-    layer_front_kernel<bf16><<<grid, NT, smem, (cudaStream_t)stream>>>(h, *w, (bf16*)kcache, (bf16*)vcache, anc, anc_ld,
+    launch_k(layer_front_kernel<bf16>, grid, NT, smem, (cudaStream_t)stream, h, *w, (bf16*)kcache, (bf16*)vcache, anc, anc_ld,
                                                                      tok, tok_ld, t, Tmax, b_out, q2_out, R);
   else
-    layer_front_kernel<float><<<grid, NT, smem, (cudaStream_t)stream>>>(h, *w, (float*)kcache, (float*)vcache, anc,
+    launch_k(layer_front_kernel<float>, grid, NT, smem, (cudaStream_t)stream, h, *w, (float*)kcache, (float*)vcache, anc,
                                                                       anc_ld, tok, tok_ld, t, Tmax, b_out, q2_out, R);
   return check_launch("case_layer_front");
 }
@@ -672,9 +690,9 @@ extern "C" int case_layer_back(const float* b_in, const float* part_ml, const fl
     attr = true;
   }
   if (dtype == CASE_BF16)
-    layer_back_kernel<bf16><<<grid, NT, smem, (cudaStream_t)stream>>>(b_in, part_ml, part_acc, nsplit, *w, h_out, R);
+    launch_k(layer_back_kernel<bf16>, grid, NT, smem, (cudaStream_t)stream, b_in, part_ml, part_acc, nsplit, *w, h_out, R);
   else
-    layer_back_kernel<float><<<grid, NT, smem, (cudaStream_t)stream>>>(b_in, part_ml, part_acc, nsplit, *w, h_out, R);
+    launch_k(layer_back_kernel<float>, grid, NT, smem, (cudaStream_t)stream, b_in, part_ml, part_acc, nsplit, *w, h_out, R);
   return check_launch("case_layer_back");
 }
 
@@ -686,7 +704,7 @@ extern "C" int case_finalize_rows(const float* h, const float* lnN_g, const floa
                  gates && fac && R > 0, "case_finalize_rows: null pointer");
   CB_REQUIRE(nsplit0 >= 1 && nsplit0 <= CASE_MAX_SPLIT && nsplit1 >= 1 && nsplit1 <= CASE_MAX_SPLIT,
              "case_finalize_rows: nsplit out of range");
-  finalize_rows_kernel<<<R, NT, 0, (cudaStream_t)stream>>>(h, lnN_g, lnN_b, stats0, ctxp0, nsplit0, stats1, ctxp1,
+  launch_k(finalize_rows_kernel, R, NT, 0, (cudaStream_t)stream, h, lnN_g, lnN_b, stats0, ctxp0, nsplit0, stats1, ctxp1,
                                                             nsplit1, Wm, bm, hN, ctx0, ctx1, gates, fac);
   return check_launch("case_finalize_rows");
 }
@@ -695,20 +713,20 @@ extern "C" int case_attn_merge(const float* stats, const float* ctx_part, int ns
                                float* fac, int fac_ld, int R, case_stream_t stream) {
   CB_REQUIRE(stats && ctx_part && ctx && R > 0 && DV > 0, "case_attn_merge: bad arguments");
   CB_REQUIRE(nsplit >= 1 && nsplit <= CASE_MAX_SPLIT, "case_attn_merge: nsplit out of range");
-  attn_merge_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(stats, ctx_part, nsplit, DV, ctx, fac, fac_ld);
+  launch_k(attn_merge_kernel, R, 256, 0, (cudaStream_t)stream, stats, ctx_part, nsplit, DV, ctx, fac, fac_ld);
   return check_launch("case_attn_merge");
 }
 
 extern "C" int case_gttp_gates(const float* f, const float* wc, const float* bc, float* gates, float* fac,
                                int fac_ld, int nsplit, int R, case_stream_t stream) {
   CB_REQUIRE(f && wc && bc && gates && fac && R > 0, "case_gttp_gates: bad arguments");
-  gttp_gates_kernel<<<R, NT, 0, (cudaStream_t)stream>>>(f, wc, bc, gates, fac, fac_ld, nsplit);
+  launch_k(gttp_gates_kernel, R, NT, 0, (cudaStream_t)stream, f, wc, bc, gates, fac, fac_ld, nsplit);
   return check_launch("case_gttp_gates");
 }
 
 extern "C" int case_gru_cell(const float* gi, const float* gh, const float* h_prev, const int32_t* gather_idx,
                              float* h_out, int R, case_stream_t stream) {
   CB_REQUIRE(gi && gh && h_prev && h_out && R > 0, "case_gru_cell: bad arguments");
-  gru_cell_kernel<<<R, NT, 0, (cudaStream_t)stream>>>(gi, gh, h_prev, gather_idx, h_out);
+  launch_k(gru_cell_kernel, R, NT, 0, (cudaStream_t)stream, gi, gh, h_prev, gather_idx, h_out);
   return check_launch("case_gru_cell");
 }

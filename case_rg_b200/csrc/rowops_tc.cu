@@ -181,6 +181,8 @@ __global__ __launch_bounds__(TNT) void row_linear_tc_kernel(case_rowlin_args_t a
     producer_run(rg, src);
     return;
   }
+  pdl_trigger();
+  pdl_wait();
   const int r0 = blockIdx.x * TRB;
   // gather + convert the input rows (one simple strided loop per segment so the loads pipeline);
   // rows >= TRB (and rows past R) are zero
@@ -247,6 +249,8 @@ __global__ __launch_bounds__(TNT) void layer_front_tc_kernel(const float* __rest
     producer_run(rg, src);
     return;
   }
+  pdl_trigger();
+  pdl_wait();
   unsigned char* p = smem_raw + TNS * TSLAB + 128;
   bf16* abuf0 = reinterpret_cast<bf16*>(p);
   bf16* abuf1 = reinterpret_cast<bf16*>(p + T_ABUF_BYTES);
@@ -422,6 +426,8 @@ __global__ __launch_bounds__(TNT) void layer_back_tc_kernel(const float* __restr
     producer_run(rg, src);
     return;
   }
+  pdl_trigger();
+  pdl_wait();
   unsigned char* p = smem_raw + TNS * TSLAB + 128;
   bf16* abuf0 = reinterpret_cast<bf16*>(p);
   bf16* abuf1 = reinterpret_cast<bf16*>(p + T_ABUF_BYTES);
@@ -535,7 +541,7 @@ int case_row_linear_tc(const case_rowlin_args_t* a, cudaStream_t st) {
     attr = true;
   }
   dim3 grid((a->R + TRB - 1) / TRB, a->N / 256);
-  row_linear_tc_kernel<<<grid, TNT, smem, st>>>(*a);
+  launch_k(row_linear_tc_kernel, grid, TNT, smem, st, *a);
   return check_launch("case_row_linear(tc)");
 }
 
@@ -547,7 +553,7 @@ int case_layer_front_tc(const float* h, const case_layer_weights_t* w, void* kca
     cudaFuncSetAttribute(layer_front_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_FRONT_SMEM);
     attr = true;
   }
-  layer_front_tc_kernel<<<(R + TRB - 1) / TRB, TNT, T_FRONT_SMEM, st>>>(h, *w, (bf16*)kcache, (bf16*)vcache, anc, anc_ld,
+  launch_k(layer_front_tc_kernel, (R + TRB - 1) / TRB, TNT, T_FRONT_SMEM, st, h, *w, (bf16*)kcache, (bf16*)vcache, anc, anc_ld,
                                                                         tok, tok_ld, t, Tmax, b_out, q2_out, R);
   return check_launch("case_layer_front(tc)");
 }
@@ -560,6 +566,6 @@ int case_layer_back_tc(const float* b_in, const float* part_ml, const float* par
     cudaFuncSetAttribute(layer_back_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_BACK_SMEM);
     attr = true;
   }
-  layer_back_tc_kernel<<<(R + TRB - 1) / TRB, TNT, T_BACK_SMEM, st>>>(b_in, part_ml, part_acc, nsplit, *w, h_out, R);
+  launch_k(layer_back_tc_kernel, (R + TRB - 1) / TRB, TNT, T_BACK_SMEM, st, b_in, part_ml, part_acc, nsplit, *w, h_out, R);
   return check_launch("case_layer_back(tc)");
 }

@@ -13,6 +13,8 @@
 namespace cb {
 
 __global__ __launch_bounds__(32) void beam_select_kernel(case_select_args_t a) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, lane = threadIdx.x;
   const int W = a.W, t = a.t, TL = a.Tmax + 1;
   const int r0 = b * W;
@@ -31,7 +33,7 @@ __global__ __launch_bounds__(32) void beam_select_kernel(case_select_args_t a) {
       a.tok[(size_t)r0 * TL + t + 1] = tk;
       a.parent[r0] = r0;
       a.live[r0] = 1;
-      atomicAdd(a.n_live, 1);
+      a.n_live[b] = 1;
     }
     for (int j = lane; j <= t; j += 32) a.anc_out[(size_t)r0 * TL + j] = r0;
     return;
@@ -80,7 +82,7 @@ __global__ __launch_bounds__(32) void beam_select_kernel(case_select_args_t a) {
     s_nlive = nn;
     s_best = bc;
     if (bc >= 0) a.best_key[b] = bk;
-    atomicAdd(a.n_live, nn);
+    a.n_live[b] = nn;
   }
   __syncwarp();
   // read everything the new slots need from the old state before any slot is overwritten
@@ -138,6 +140,6 @@ extern "C" int case_beam_select(const case_select_args_t* a, case_stream_t strea
     CB_REQUIRE(a->W == 1, "case_beam_select: greedy modes need W == 1");
     CB_REQUIRE(a->mode != CASE_MODE_PROTO_GREEDY || a->ended, "case_beam_select: proto-greedy needs ended[]");
   }
-  beam_select_kernel<<<a->B, 32, 0, (cudaStream_t)stream>>>(*a);
+  launch_k(beam_select_kernel, a->B, 32, 0, (cudaStream_t)stream, *a);
   return check_launch("case_beam_select");
 }

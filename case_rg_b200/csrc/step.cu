@@ -8,6 +8,8 @@
 namespace cb {
 
 static thread_local char g_err[512] = "ok";
+int g_use_pdl = 1;
+cudaError_t g_launch_err = cudaSuccess;
 
 void set_error(const char* msg) {
   strncpy(g_err, msg, sizeof(g_err) - 1);
@@ -16,6 +18,8 @@ void set_error(const char* msg) {
 
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = g_launch_err;
+  g_launch_err = cudaSuccess;
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
     return (int)e;
@@ -28,6 +32,11 @@ int check_launch(const char* what) {
 using namespace cb;
 
 extern "C" int case_abi_version(void) { return 1; }
+extern "C" int case_set_pdl(int on) {
+  const int old = g_use_pdl;
+  g_use_pdl = on ? 1 : 0;
+  return old;
+}
 extern "C" const char* case_last_error(void) { return g_err; }
 
 #define TRY(x)            \
@@ -53,8 +62,6 @@ static int select_step(int mode, int B, int W, int t, int max_len, int Tmax, int
   s.top_vals = top_vals; s.top_idx = top_idx; s.live = live; s.cum = cum; s.length = length; s.tok = tok;
   s.anc_in = anc[t & 1]; s.anc_out = anc[(t + 1) & 1]; s.parent = parent; s.ended = ended;
   s.best_key = best_key; s.best_len = best_len; s.out_tokens = out_tokens; s.n_live = n_live;
-  cudaError_t e = cudaMemsetAsync(n_live, 0, sizeof(int32_t), st);
-  if (e != cudaSuccess) { set_error("select_step: cudaMemsetAsync failed"); return (int)e; }
   return case_beam_select(&s, st);
 }
 

@@ -13,6 +13,8 @@ __global__ __launch_bounds__(256) void vocab_gemm_simt_kernel(const float* __res
   constexpr int BM = 64, BN = 64, BK = 16;
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const int lr = tid >> 2, lk = (tid & 3) * 4;       // loader: row lr (0..63), k offset lk (0,4,8,12)
@@ -58,6 +60,8 @@ __global__ __launch_bounds__(SMT) void softmax_mix_kernel(const float* __restric
                                                           int ldd, int V, int mask_col0) {
   __shared__ float sm[SMT / 32], ss[SMT / 32];
   __shared__ float bm, bs;
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* x = logits + (size_t)r * ldl;
   const int V4 = V & ~3;
@@ -111,6 +115,8 @@ __global__ __launch_bounds__(256) void copy_scatter_kernel(const int32_t* __rest
                                                            const float* __restrict__ fac, int fac_ld,
                                                            float* __restrict__ dist, int ldd, int W, int S, int V,
                                                            int vec_ok) {
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.y, b = r / W;
   const int s4 = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (s4 >= S) return;
@@ -155,6 +161,8 @@ __global__ __launch_bounds__(256) void topk_rows_kernel(const float* __restrict_
   __shared__ float sv[8];
   __shared__ int si[8];
   __shared__ int swin;
+  pdl_trigger();
+  pdl_wait();
   const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* x = dist + (size_t)r * ldd;
   float tv[K];
@@ -218,9 +226,9 @@ extern "C" int case_vocab_gemm(const float* f, const void* Wv, const float* bias
   }
   dim3 grid((V + 63) / 64, (R + 63) / 64);
   if (dtype == CASE_BF16)
-    vocab_gemm_simt_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(f, (const bf16*)Wv, bias, logits, R, V, ldl);
+    launch_k(vocab_gemm_simt_kernel<bf16>, grid, 256, 0, (cudaStream_t)stream, f, (const bf16*)Wv, bias, logits, R, V, ldl);
   else
-    vocab_gemm_simt_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(f, (const float*)Wv, bias, logits, R, V, ldl);
+    launch_k(vocab_gemm_simt_kernel<float>, grid, 256, 0, (cudaStream_t)stream, f, (const float*)Wv, bias, logits, R, V, ldl);
   return check_launch("case_vocab_gemm");
 }
 
@@ -229,7 +237,7 @@ extern "C" int case_softmax_mix(const float* logits, int ldl, const float* gates
   CB_REQUIRE(logits && gates && dist && R > 0 && V > 0, "case_softmax_mix: bad arguments");
   CB_REQUIRE(ldl % 4 == 0 && ldd % 4 == 0 && ldl >= V && ldd >= V, "case_softmax_mix: row strides must be multiples of 4");
   CB_REQUIRE(((uintptr_t)logits % 16 == 0) && ((uintptr_t)dist % 16 == 0), "case_softmax_mix: 16-byte alignment required");
-  softmax_mix_kernel<<<R, SMT, 0, (cudaStream_t)stream>>>(logits, ldl, gates, dist, ldd, V, mask_col0);
+  launch_k(softmax_mix_kernel, R, SMT, 0, (cudaStream_t)stream, logits, ldl, gates, dist, ldd, V, mask_col0);
   return check_launch("case_softmax_mix");
 }
 
@@ -240,7 +248,7 @@ extern "C" int case_copy_scatter(const int32_t* map, int map_ld, int map_off, co
   const int vec_ok = (S % 4 == 0) && (map_ld % 4 == 0) && (map_off % 4 == 0) && ((uintptr_t)map % 16 == 0) &&
                      ((uintptr_t)attn_un % 16 == 0) && (!prior || (uintptr_t)prior % 16 == 0);
   dim3 grid((S + 1023) / 1024, B * W);
-  copy_scatter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(map, map_ld, map_off, prior, attn_un, fac, fac_ld,
+  launch_k(copy_scatter_kernel, grid, 256, 0, (cudaStream_t)stream, map, map_ld, map_off, prior, attn_un, fac, fac_ld,
                                                               dist, ldd, W, S, V, vec_ok);
   return check_launch("case_copy_scatter");
 }
@@ -252,14 +260,14 @@ extern "C" int case_topk_rows(const float* dist, int ldd, int R, int V, int k, f
   cudaStream_t st = (cudaStream_t)stream;
   // vals / idx are [R][k]; kernels are instantiated for k = 1, 2, 4, 8 and others fall to the next size up
   switch (k) {
-    case 1: topk_rows_kernel<1><<<R, 256, 0, st>>>(dist, ldd, V, vals, idx); break;
-    case 2: topk_rows_kernel<2><<<R, 256, 0, st>>>(dist, ldd, V, vals, idx); break;
-    case 3: topk_rows_kernel<3><<<R, 256, 0, st>>>(dist, ldd, V, vals, idx); break;
-    case 4: topk_rows_kernel<4><<<R, 256, 0, st>>>(dist, ldd, V, vals, idx); break;
-    case 5: topk_rows_kernel<5><<<R, 256, 0, st>>>(dist, ldd, V, vals, idx); break;
-    case 6: topk_rows_kernel<6><<<R, 256, 0, st>>>(dist, ldd, V, vals, idx); break;
-    case 7: topk_rows_kernel<7><<<R, 256, 0, st>>>(dist, ldd, V, vals, idx); break;
-    default: topk_rows_kernel<8><<<R, 256, 0, st>>>(dist, ldd, V, vals, idx); break;
+    case 1: launch_k(topk_rows_kernel<1>, R, 256, 0, st, dist, ldd, V, vals, idx); break;
+    case 2: launch_k(topk_rows_kernel<2>, R, 256, 0, st, dist, ldd, V, vals, idx); break;
+    case 3: launch_k(topk_rows_kernel<3>, R, 256, 0, st, dist, ldd, V, vals, idx); break;
+    case 4: launch_k(topk_rows_kernel<4>, R, 256, 0, st, dist, ldd, V, vals, idx); break;
+    case 5: launch_k(topk_rows_kernel<5>, R, 256, 0, st, dist, ldd, V, vals, idx); break;
+    case 6: launch_k(topk_rows_kernel<6>, R, 256, 0, st, dist, ldd, V, vals, idx); break;
+    case 7: launch_k(topk_rows_kernel<7>, R, 256, 0, st, dist, ldd, V, vals, idx); break;
+    default: launch_k(topk_rows_kernel<8>, R, 256, 0, st, dist, ldd, V, vals, idx); break;
   }
   return check_launch("case_topk_rows");
 }

@@ -165,7 +165,7 @@ class _SearchState:
         self.best_key = torch.zeros(B, dtype=torch.float64, device=dev)
         self.best_len = torch.zeros(B, **i32)
         self.out_tokens = torch.zeros(B, Tmax, **i32)
-        self.n_live = torch.zeros(1, **i32)
+        self.n_live = torch.zeros(B, **i32)
         self.B, self.W, self.R, self.Tmax = B, W, R, Tmax
         self._arange = torch.arange(R, **i32)
         self._slot0 = (self._arange % W == 0).to(torch.int32)

@@ -52,6 +52,8 @@ const char* case_last_error(void);
 /* sizeof() of the argument structs below, for binding self-checks: 0 case_seg_t, 1 case_rowlin_args_t,
  * 2 case_layer_weights_t, 3 case_select_args_t, 4 case_step_args_t, 5 gttp_step_args_t */
 size_t case_struct_size(int which);
+/* Programmatic dependent launch for every kernel of a step (default on); returns the old setting. */
+int case_set_pdl(int on);
 
 /* ---------------------------------------------------------------- row-wise building blocks */
 
@@ -217,7 +219,7 @@ typedef struct {
   double* best_key;        /* [B] beam: best finished cum/length so far (+inf initially) */
   int32_t* best_len;       /* [B] tokens in best_seq                                     */
   int32_t* out_tokens;     /* [B][Tmax] greedy: per-step token; beam: best sequence      */
-  int32_t* n_live;         /* [1] number of live rows after this step (early-exit hint)  */
+  int32_t* n_live;         /* [B] live hypotheses per query after this step (early-exit hint) */
 } case_select_args_t;
 
 int case_beam_select(const case_select_args_t* a, case_stream_t stream);
