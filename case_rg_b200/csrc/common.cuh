@@ -110,7 +110,14 @@ __device__ __forceinline__ void ld8c(const bf16* p, float (&o)[8]) {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // programmatic dependent launch: let the dependent grid start early / wait for the producer grid
+// (an explicit early trigger made the step slower: dependents that are resident but blocked in
+//  pdl_wait() take shared memory / CTA slots from multi-wave producers such as the cross-attention,
+//  so the trigger is left implicit - it fires as each producer CTA exits)
+#ifdef CASE_PDL_EARLY_TRIGGER
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+__device__ __forceinline__ void pdl_trigger() {}
+#endif
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- reductions

@@ -169,9 +169,9 @@ __global__ __launch_bounds__(256) void topk_rows_kernel(const float* __restrict_
   int ti[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) { tv[k] = -INFINITY; ti[k] = 0x7fffffff; }
-  // indices visited in increasing order per thread -> strict '>' keeps the lower index on ties
-  for (int i = tid; i < V; i += 256) {
-    const float v = x[i];
+  // indices visited in increasing order per thread -> strict '>' keeps the lower index on ties;
+  // 16-byte loads, two in flight per thread (rows are 16-byte aligned: ldd % 4 == 0)
+  auto push = [&](float v, int i) {
     if (v > tv[K - 1]) {
       tv[K - 1] = v; ti[K - 1] = i;
 #pragma unroll
@@ -182,7 +182,20 @@ __global__ __launch_bounds__(256) void topk_rows_kernel(const float* __restrict_
         }
       }
     }
+  };
+  const int V4 = V & ~3;
+  int i = tid * 4;
+  for (; i + 1024 < V4; i += 2048) {
+    const float4 a = *reinterpret_cast<const float4*>(x + i);
+    const float4 b = *reinterpret_cast<const float4*>(x + i + 1024);
+    push(a.x, i); push(a.y, i + 1); push(a.z, i + 2); push(a.w, i + 3);
+    push(b.x, i + 1024); push(b.y, i + 1025); push(b.z, i + 1026); push(b.w, i + 1027);
   }
+  for (; i < V4; i += 1024) {
+    const float4 a = *reinterpret_cast<const float4*>(x + i);
+    push(a.x, i); push(a.y, i + 1); push(a.z, i + 2); push(a.w, i + 3);
+  }
+  for (int j = V4 + tid; j < V; j += 256) push(x[j], j);
   for (int round = 0; round < K; ++round) {
     float bv = tv[0];
     int bi = ti[0];
@@ -257,6 +270,7 @@ extern "C" int case_topk_rows(const float* dist, int ldd, int R, int V, int k, f
                               case_stream_t stream) {
   CB_REQUIRE(dist && vals && idx && R > 0 && V > 0, "case_topk_rows: bad arguments");
   CB_REQUIRE(k >= 1 && k <= CASE_MAX_W && k <= V, "case_topk_rows: k out of range");
+  CB_REQUIRE(ldd % 4 == 0 && (uintptr_t)dist % 16 == 0, "case_topk_rows: rows must be 16-byte aligned (ldd % 4 == 0)");
   cudaStream_t st = (cudaStream_t)stream;
   // vals / idx are [R][k]; kernels are instantiated for k = 1, 2, 4, 8 and others fall to the next size up
   switch (k) {

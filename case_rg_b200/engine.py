@@ -242,7 +242,8 @@ class CaseDecodeEngine(_EngineBase):
                                     device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
         z = lambda *s: torch.zeros(*s, **f32)
-        self.nsx = [_nsplit(B * L.NH, s, L.XATTN_TILE, target_ctas) for s in self.S]
+        # cross-attention CTAs are (query, head, split): aim for ~6 resident CTAs per SM so the tail is short
+        self.nsx = [_nsplit(B * L.NH, s, L.XATTN_TILE, 6 * 148) for s in self.S]
         self.nsa = [_nsplit(B, s, L.AATTN_TILE, 2 * target_ctas) for s in self.S]
         # per-batch tensors
         self.feat = z(B, H)
