@@ -334,8 +334,11 @@ def roofline(model, eng, args, torch):
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / (reps * 4)
     ach = alg / (us * 1e-6) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed
+    # `ncu --set full` capture (profiles/r1_top_kernels_ncu_summary.txt): 168.3 MB read + 5.4 MB written
+    traffic = 173.7e6 if (eng.w.cdtype == L.BF16 and (B, W, S1) == (64, 4, 2560)) else None
     return dict(kernel='cross_attn_mma_kernel (passage memory)' if eng.w.cdtype == L.BF16 else 'cross_attn_partial_kernel (passage memory)', bound='hbm', achieved=ach, peak=peak, unit='GB/s',
-                frac=ach / peak, traffic=None, peak_source=which, algorithmic_bytes_per_launch=alg,
+                frac=ach / peak, traffic=traffic, peak_source=which, algorithmic_bytes_per_launch=alg,
                 us_per_launch=us, launches_per_decode_step=4)
 
 
