@@ -315,9 +315,8 @@ def roofline(model, eng, args, torch):
     reps = 20
     def launch(l):
         if eng.w.cdtype == L.BF16:
-            L.call('case_cross_attn_partial_tc', eng.q2.data_ptr(), eng.Kx[l].data_ptr(), eng.Vx[l].data_ptr(),
-                   eng.mask[1].data_ptr(), B, W, S1, eng.nsx[1], eng.part_ml.data_ptr(), eng.part_acc.data_ptr(),
-                   st.cuda_stream)
+            L.call('case_cross_attn_partial_tc', eng.q2.data_ptr(), eng.Kx[l].data_ptr(), eng.mask[1].data_ptr(), B, W,
+                   S1, eng.nsx[1], eng.part_ml.data_ptr(), eng.part_acc.data_ptr(), st.cuda_stream)
         else:
             L.call('case_cross_attn_partial', eng.q2.data_ptr(), eng.Kx[l].data_ptr(), eng.Vx[l].data_ptr(),
                    eng.mask[1].data_ptr(), B, W, S1, eng.nsx[1], eng.part_ml.data_ptr(), eng.part_acc.data_ptr(),

@@ -406,16 +406,22 @@ extern "C" int case_additive_attn(const float* qa, const void* U, const void* Mv
 // =============================================================================== tensor-core cross attention
 // bf16 K/V only.  FlashAttention-2 style decode step on mma.sync.m16n8k16 tiles: the W (<= 8) beam rows
 // of one query are the M rows 0..7 of the tile (rows 8..15 are zero padding), so one pass over a
-// head's K/V serves every beam.  Each warp owns a strided set of 64-key tiles with its own cp.async
-// double buffer and its own running (max, sum, acc); warps never synchronise with each other until
-// the end, where the CTA merges its four warps and writes one partial per (row, head, split) for
-// case_layer_back.  HBM traffic = K and V once.
+// head's K/V serves every beam.  K and V of a head live interleaved in ONE array, tile by tile
+// ([64 keys x 32] K then [64 x 32] V, 16-byte chunks XOR-swizzled by ((key >> 1) & 3) so both the
+// row-wise and the transposed ldmatrix reads are bank-conflict free), which lets each warp stream its
+// tiles with one 8 KB bulk async copy per stage into a private 3-stage ring (mbarrier per stage; a
+// warp keeps one bulk copy in flight, eight warps per SM saturate HBM - profiles/micro/
+// hbm_stream_bench.cu).  Warps never synchronise until the end, where the CTA merges its four
+// warps and writes one partial per (row, head, split) for case_layer_back.  HBM traffic = K and V once.
 namespace cb {
 
 constexpr int XM_WARPS = 4;
-constexpr int XM_TILE = 32;                       // keys per warp tile
-constexpr int XM_TILE_BYTES = XM_TILE * HD * 2;   // 2 KB for K, same for V
-constexpr int XM_SMEM = XM_WARPS * 2 * 2 * XM_TILE_BYTES;
+constexpr int XM_TILE = 64;                        // keys per tile
+constexpr int XM_TILE_BYTES = XM_TILE * HD * 2;    // 4 KB of K, then 4 KB of V
+constexpr int XM_STAGE = 2 * XM_TILE_BYTES;        // 8 KB per stage
+constexpr int XM_NS = 3;                           // ring depth per warp
+constexpr int XM_WARP_BYTES = XM_NS * XM_STAGE + 64;
+constexpr int XM_SMEM = XM_WARPS * XM_WARP_BYTES;
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -435,30 +441,59 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+__device__ __forceinline__ void xm_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// byte offset of (key row, 16-byte chunk) inside a [64][32] bf16 tile, XOR-swizzled so that both the
-// row-wise (K) and transposed (V) ldmatrix reads are bank-conflict free
+__device__ __forceinline__ void xm_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ bool xm_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// byte offset of (key row, 16-byte chunk) inside a [64][32] bf16 tile (the swizzle is already in memory)
 __device__ __forceinline__ uint32_t xm_swz(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
 
 __global__ __launch_bounds__(XM_WARPS * 32) void cross_attn_mma_kernel(
-    const float* __restrict__ q2, const bf16* __restrict__ Kmem, const bf16* __restrict__ Vmem,
-    const uint8_t* __restrict__ mask, int W, int S, int nsplit, float* __restrict__ part_ml,
-    float* __restrict__ part_acc) {
-  extern __shared__ __align__(128) unsigned char xm_smem[];   // [warp][stage][K|V][XM_TILE_BYTES]
-  pdl_trigger();
-  pdl_wait();
+    const float* __restrict__ q2, const bf16* __restrict__ KV, const uint8_t* __restrict__ mask, int W, int S,
+    int nsplit, float* __restrict__ part_ml, float* __restrict__ part_acc) {
+  extern __shared__ __align__(128) unsigned char xm_smem[];   // [warp][XM_NS stages of K|V][barriers]
   const int b = blockIdx.x, hh = blockIdx.y, sp = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int ntile_all = (S + XM_TILE - 1) / XM_TILE;
   const int chunk = split_chunk(S, nsplit, XM_TILE * XM_WARPS);
   const int s_begin = sp * chunk, s_end = min(S, s_begin + chunk);
-  const bf16* Kb = Kmem + ((size_t)(b * NH + hh)) * S * HD;
-  const bf16* Vb = Vmem + ((size_t)(b * NH + hh)) * S * HD;
+  const int tile0 = s_begin / XM_TILE + warp;                           // this warp's first tile
+  const int tile_end = (s_end + XM_TILE - 1) / XM_TILE;
+  const int my_tiles = tile0 < tile_end ? (tile_end - tile0 + XM_WARPS - 1) / XM_WARPS : 0;
+  const char* kvb = reinterpret_cast<const char*>(KV) + ((size_t)(b * NH + hh)) * ntile_all * XM_STAGE;
   const uint8_t* mb = mask + (size_t)b * S;
+  unsigned char* wsm = xm_smem + (size_t)warp * XM_WARP_BYTES;
+  const uint32_t sbase = smem_u32(wsm), bars = sbase + XM_NS * XM_STAGE;
+
+  if (lane == 0) {
+    for (int i = 0; i < XM_NS; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8 * i));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  pdl_trigger();
+  pdl_wait();            // K/V come from the prefill, q2 from the preceding layer_front
+  if (lane == 0)
+    for (int p = 0; p < XM_NS && p < my_tiles; ++p) {
+      xm_expect(bars + 8 * p, XM_STAGE);
+      xm_bulk(sbase + p * XM_STAGE, kvb + (size_t)(tile0 + p * XM_WARPS) * XM_STAGE, XM_STAGE, bars + 8 * p);
+    }
 
   // Q fragments (A operand), rows >= W are zero
   uint32_t qa[2][2];
@@ -477,30 +512,11 @@ __global__ __launch_bounds__(XM_WARPS * 32) void cross_attn_mma_kernel(
 #pragma unroll
   for (int nb = 0; nb < 4; ++nb) { o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f; }
 
-  const uint32_t sbase = smem_u32(xm_smem + (size_t)warp * 4 * XM_TILE_BYTES);
-  auto load_tile = [&](int tile_s0, int stage) {
-    const uint32_t kdst = sbase + stage * 2 * XM_TILE_BYTES, vdst = kdst + XM_TILE_BYTES;
-#pragma unroll
-    for (int i = 0; i < XM_TILE / 8; ++i) {
-      const int ci = lane + 32 * i, row = ci >> 2, ch = ci & 3;
-      const int s = tile_s0 + row;
-      const int nbytes = s < s_end ? 16 : 0;                 // zero-fill rows past the range
-      const size_t goff = (size_t)(s < s_end ? s : s_begin) * HD + ch * 8;
-      cp_async16(kdst + xm_swz(row, ch), Kb + goff, nbytes);
-      cp_async16(vdst + xm_swz(row, ch), Vb + goff, nbytes);
-    }
-    cp_async_commit();
-  };
-
-  int tile_s0 = s_begin + warp * XM_TILE;
-  const int stride = XM_WARPS * XM_TILE;
-  int stage = 0;
-  if (tile_s0 < s_end) load_tile(tile_s0, 0);
-  for (; tile_s0 < s_end; tile_s0 += stride, stage ^= 1) {
-    const int next = tile_s0 + stride;
-    if (next < s_end) { load_tile(next, stage ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncwarp();
-    const uint32_t kt = sbase + stage * 2 * XM_TILE_BYTES, vt = kt + XM_TILE_BYTES;
+  for (int i = 0; i < my_tiles; ++i) {
+    const int stage = i % XM_NS;
+    const int tile_s0 = (tile0 + i * XM_WARPS) * XM_TILE;
+    while (!xm_try_wait(bars + 8 * stage, (uint32_t)(i / XM_NS) & 1u)) {}
+    const uint32_t kt = sbase + stage * XM_STAGE, vt = kt + XM_TILE_BYTES;
     // ---- S = Q K^T for 8 key blocks of 8
     float sc[XM_TILE / 8][2];
     float tmax = -INFINITY;
@@ -512,8 +528,8 @@ __global__ __launch_bounds__(XM_WARPS * 32) void cross_attn_mma_kernel(
       mma_bf16_16816(c, qa[0][0], 0u, qa[0][1], 0u, kf[0], kf[1]);
       mma_bf16_16816(c, qa[1][0], 0u, qa[1][1], 0u, kf[2], kf[3]);
       const int s = tile_s0 + kb * 8 + 2 * t;
-      const bool v0 = s < s_end && mb[min(s, S - 1)] != 0;
-      const bool v1 = s + 1 < s_end && mb[min(s + 1, S - 1)] != 0;
+      const bool v0 = s >= s_begin && s < s_end && mb[s] != 0;
+      const bool v1 = s + 1 >= s_begin && s + 1 < s_end && mb[min(s + 1, S - 1)] != 0;
       sc[kb][0] = v0 ? c[0] : -INFINITY;
       sc[kb][1] = v1 ? c[1] : -INFINITY;
       tmax = fmaxf(tmax, fmaxf(sc[kb][0], sc[kb][1]));
@@ -532,8 +548,8 @@ __global__ __launch_bounds__(XM_WARPS * 32) void cross_attn_mma_kernel(
       float p[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float s = sc[2 * kk + (u >> 1)][u & 1];
-        p[u] = (s == -INFINITY) ? 0.f : fexp(s - mn);
+        const float sv = sc[2 * kk + (u >> 1)][u & 1];
+        p[u] = (sv == -INFINITY) ? 0.f : fexp(sv - mn);
         l += p[u];
       }
       const uint32_t pa0 = pack_bf16(p[0], p[1]), pa2 = pack_bf16(p[2], p[3]);
@@ -546,14 +562,19 @@ __global__ __launch_bounds__(XM_WARPS * 32) void cross_attn_mma_kernel(
         mma_bf16_16816(o[c2 * 2 + 1], pa0, 0u, pa2, 0u, vf[2], vf[3]);
       }
     }
-    __syncwarp();
+    __syncwarp();                                         // every lane is done with this stage
+    if (lane == 0 && i + XM_NS < my_tiles) {
+      xm_expect(bars + 8 * stage, XM_STAGE);
+      xm_bulk(sbase + stage * XM_STAGE, kvb + (size_t)(tile0 + (i + XM_NS) * XM_WARPS) * XM_STAGE, XM_STAGE,
+              bars + 8 * stage);
+    }
   }
   l += __shfl_xor_sync(0xffffffffu, l, 1);
   l += __shfl_xor_sync(0xffffffffu, l, 2);
   // merge the four warps of the CTA through shared memory (each warp parks its result in its own,
   // now idle, staging region) so the CTA writes ONE partial per (row, head, split)
   __syncwarp();
-  float* scr = reinterpret_cast<float*>(xm_smem + (size_t)warp * 4 * XM_TILE_BYTES);   // [8 rows][2 + 32]
+  float* scr = reinterpret_cast<float*>(wsm);             // [8 rows][2 + 32]
   if (t == 0) { scr[g * 34] = m; scr[g * 34 + 1] = l; }
 #pragma unroll
   for (int nb = 0; nb < 4; ++nb)
@@ -565,13 +586,13 @@ __global__ __launch_bounds__(XM_WARPS * 32) void cross_attn_mma_kernel(
       float mw[XM_WARPS], M = -INFINITY;
 #pragma unroll
       for (int w2 = 0; w2 < XM_WARPS; ++w2) {
-        mw[w2] = reinterpret_cast<const float*>(xm_smem + (size_t)w2 * 4 * XM_TILE_BYTES)[row * 34];
+        mw[w2] = reinterpret_cast<const float*>(xm_smem + (size_t)w2 * XM_WARP_BYTES)[row * 34];
         M = fmaxf(M, mw[w2]);
       }
       float L = 0.f, o0 = 0.f, o1 = 0.f;
 #pragma unroll
       for (int w2 = 0; w2 < XM_WARPS; ++w2) {
-        const float* sw = reinterpret_cast<const float*>(xm_smem + (size_t)w2 * 4 * XM_TILE_BYTES) + row * 34;
+        const float* sw = reinterpret_cast<const float*>(xm_smem + (size_t)w2 * XM_WARP_BYTES) + row * 34;
         const float e = (mw[w2] == -INFINITY) ? 0.f : fexp(mw[w2] - M);
         L = fmaf(sw[1], e, L);
         o0 = fmaf(sw[2 + 2 * dp], e, o0);
@@ -586,13 +607,18 @@ __global__ __launch_bounds__(XM_WARPS * 32) void cross_attn_mma_kernel(
 
 }  // namespace cb
 
-extern "C" int case_cross_attn_partial_tc(const float* q2, const void* Kmem, const void* Vmem, const uint8_t* mask,
-                                          int B, int W, int S, int nsplit, float* part_ml, float* part_acc,
-                                          case_stream_t stream) {
-  CB_REQUIRE(q2 && Kmem && Vmem && mask && part_ml && part_acc, "case_cross_attn_partial_tc: null pointer");
+extern "C" int case_cross_attn_partial_tc(const float* q2, const void* KV, const uint8_t* mask, int B, int W, int S,
+                                          int nsplit, float* part_ml, float* part_acc, case_stream_t stream) {
+  CB_REQUIRE(q2 && KV && mask && part_ml && part_acc, "case_cross_attn_partial_tc: null pointer");
   CB_REQUIRE(B > 0 && W >= 1 && W <= CASE_MAX_W && S > 0, "case_cross_attn_partial_tc: bad sizes");
   CB_REQUIRE(nsplit >= 1 && nsplit <= CASE_MAX_XSPLIT, "case_cross_attn_partial_tc: nsplit out of range");
-  launch_k(cb::cross_attn_mma_kernel, dim3(B, cb::NH, nsplit), cb::XM_WARPS * 32, cb::XM_SMEM, (cudaStream_t)stream, 
-      q2, (const cb::bf16*)Kmem, (const cb::bf16*)Vmem, mask, W, S, nsplit, part_ml, part_acc);
+  CB_REQUIRE((uintptr_t)KV % 16 == 0, "case_cross_attn_partial_tc: KV must be 16-byte aligned");
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(cb::cross_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cb::XM_SMEM);
+    attr = true;
+  }
+  launch_k(cb::cross_attn_mma_kernel, dim3(B, cb::NH, nsplit), cb::XM_WARPS * 32, cb::XM_SMEM, (cudaStream_t)stream,
+           q2, (const cb::bf16*)KV, mask, W, S, nsplit, part_ml, part_acc);
   return cb::check_launch("case_cross_attn_partial_tc");
 }

@@ -83,8 +83,8 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
                            a->bbuf, a->q2, R, dt, st));
       int nparts = a->nsplit_x[i];
       if (dt == CASE_BF16) {   // tensor-core tiles
-        TRY(case_cross_attn_partial_tc(a->q2, a->Kx[L], a->Vx[L], a->mask[i], B, W, a->S[i], a->nsplit_x[i],
-                                       a->part_ml, a->part_acc, st));
+        TRY(case_cross_attn_partial_tc(a->q2, a->Kx[L], a->mask[i], B, W, a->S[i], a->nsplit_x[i], a->part_ml,
+                                       a->part_acc, st));                 // Kx holds the interleaved K|V tiles
       } else {
         TRY(case_cross_attn_partial(a->q2, a->Kx[L], a->Vx[L], a->mask[i], B, W, a->S[i], a->nsplit_x[i],
                                     a->part_ml, a->part_acc, dt, st));

@@ -78,6 +78,32 @@ def pack_vocab_tc(w: torch.Tensor) -> torch.Tensor:
     return wp.view(VT, 16, 8, K // 8, 8).permute(0, 3, 1, 2, 4).contiguous()   # [tile][k/8][row/8][row%8][k%8]
 
 
+_SWZ = {}
+
+
+def _swizzle_index(device):
+    """[64 keys][4 chunks] source chunk for each stored chunk position: c ^ ((key >> 1) & 3) (an involution)."""
+    if device not in _SWZ:
+        key = torch.arange(64, device=device)
+        _SWZ[device] = (key[:, None], torch.arange(4, device=device)[None, :] ^ ((key >> 1) & 3)[:, None])
+    return _SWZ[device]
+
+
+def pack_kv_tiles(k: torch.Tensor, v: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """K, V [B, NH, S, 32] -> the tensor-core cross-attention layout (case_b200.h): bf16
+    [B][NH][ceil(S/64)][2][64][32], keys >= S zero, 16-byte chunks of each key row XOR-swizzled."""
+    B, NH, S, HD = k.shape
+    nt = -(-S // 64)
+    if out is None:
+        out = torch.zeros(B, NH, nt, 2, 64, HD, dtype=torch.bfloat16, device=k.device)
+    kidx, cidx = _swizzle_index(k.device)
+    for j, src in enumerate((k, v)):
+        pad = torch.zeros(B, NH, nt * 64, HD, dtype=torch.bfloat16, device=k.device)
+        pad[:, :, :S] = src
+        out[:, :, :, j] = pad.view(B, NH, nt, 64, 4, 8)[:, :, :, kidx, cidx].reshape(B, NH, nt, 64, HD)
+    return out
+
+
 def split_chunk(S, nsplit, tile=128):
     c = -(-S // nsplit)
     return -(-c // tile) * tile
@@ -247,8 +273,13 @@ class CaseDecodeEngine(_EngineBase):
         self.nsa = [_nsplit(B, s, L.AATTN_TILE, 2 * target_ctas) for s in self.S]
         # per-batch tensors
         self.feat = z(B, H)
-        self.Kx = [torch.zeros(B, L.NH, self.S[l // 4], L.HD, dtype=td, device=dev) for l in range(8)]
-        self.Vx = [torch.zeros(B, L.NH, self.S[l // 4], L.HD, dtype=td, device=dev) for l in range(8)]
+        if weights.cdtype == L.BF16:      # interleaved, swizzled K|V tiles for the tensor-core kernel
+            self.Kx = [torch.zeros(B, L.NH, -(-self.S[l // 4] // 64), 2, 64, L.HD, dtype=td, device=dev)
+                       for l in range(8)]
+            self.Vx = [None] * 8
+        else:
+            self.Kx = [torch.zeros(B, L.NH, self.S[l // 4], L.HD, dtype=td, device=dev) for l in range(8)]
+            self.Vx = [torch.zeros(B, L.NH, self.S[l // 4], L.HD, dtype=td, device=dev) for l in range(8)]
         self.U = [torch.zeros(B, s, H, dtype=td, device=dev) for s in self.S]
         self.Mv = [torch.zeros(B, s, H, dtype=td, device=dev) for s in self.S]
         self.mask = [torch.zeros(B, s, dtype=torch.uint8, device=dev) for s in self.S]
@@ -294,7 +325,7 @@ class CaseDecodeEngine(_EngineBase):
         a.E, a.pe = w.E.data_ptr(), w.pe.data_ptr()
         for l in range(8):
             C.memmove(C.byref(a.layers[l]), C.byref(w.layers[l]), C.sizeof(L.LayerWeights))
-            a.Kx[l], a.Vx[l] = self.Kx[l].data_ptr(), self.Vx[l].data_ptr()
+            a.Kx[l], a.Vx[l] = self.Kx[l].data_ptr(), (self.Vx[l].data_ptr() if self.Vx[l] is not None else None)
             a.kcache[l], a.vcache[l] = self.kcache[l].data_ptr(), self.vcache[l].data_ptr()
         a.lnN_g, a.lnN_b = w.lnN_g.data_ptr(), w.lnN_b.data_ptr()
         wv = w.Wv_tc if self.vocab_impl == 1 else w.Wv
@@ -332,8 +363,11 @@ class CaseDecodeEngine(_EngineBase):
             kv = torch.addmm(w.kv_b[i], flat, w.kv_w[i])                       # [B*S, 4*2*H]
             kv = kv.view(B, S, 4, 2, L.NH, L.HD).permute(2, 3, 0, 4, 1, 5)     # [l][k/v][B][NH][S][HD]
             for l in range(4):
-                self.Kx[i * 4 + l].copy_(kv[l, 0])
-                self.Vx[i * 4 + l].copy_(kv[l, 1])
+                if w.cdtype == L.BF16:
+                    pack_kv_tiles(kv[l, 0], kv[l, 1], out=self.Kx[i * 4 + l])
+                else:
+                    self.Kx[i * 4 + l].copy_(kv[l, 0])
+                    self.Vx[i * 4 + l].copy_(kv[l, 1])
             self.U[i].copy_((flat @ w.Uk_t[i]).view(B, S, H))
             self.Mv[i].copy_(m)
             self.mask[i].copy_(masks[i].to(dev).to(torch.uint8))

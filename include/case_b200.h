@@ -134,10 +134,11 @@ int case_cross_attn_partial(const float* q2, const void* Kmem, const void* Vmem,
 
 /* Tensor-core form of the above for bf16 K/V (mma.sync m16n8k16 tiles, FlashAttention-2 style; the W
  * beam rows are the M rows of the tile).  Same outputs as case_cross_attn_partial: one partial per
- * (row, head, split). */
-int case_cross_attn_partial_tc(const float* q2, const void* Kmem, const void* Vmem, const uint8_t* mask,
-                               int B, int W, int S, int nsplit, float* part_ml, float* part_acc,
-                               case_stream_t stream);
+ * (row, head, split).  KV holds K and V of a head interleaved tile by tile so that one 8 KB bulk copy
+ * fetches a whole stage: bf16 [B][NH][ceil(S/64)][2 (K,V)][64 keys][32], keys >= S zero, and inside
+ * every 64-byte key row the four 16-byte chunks are stored at position chunk ^ ((key >> 1) & 3). */
+int case_cross_attn_partial_tc(const float* q2, const void* KV, const uint8_t* mask, int B, int W, int S,
+                               int nsplit, float* part_ml, float* part_acc, case_stream_t stream);
 
 /* Second half (TransformerDecoder.py:82-89): ctx = merge(partials); h2 = b + ctx.Wo2;
  * c = LN3(h2); h_out = c + W2.gelu(W1.c). */
@@ -255,7 +256,8 @@ typedef struct {
   const void* Wv; const float* Wm; const float* bm;  /* gen.2 [V][H] row-major, mix */
   /* per-batch (prefill) tensors */
   const float* feat;                    /* [B][H] = norm2(answer_rep) */
-  const void* Kx[8]; const void* Vx[8]; /* [B][NH][S_i][HD] per layer */
+  const void* Kx[8]; const void* Vx[8]; /* fp32: [B][NH][S_i][HD] per layer; bf16: Kx = interleaved K|V tiles
+                                           (case_cross_attn_partial_tc), Vx unused */
   const void* U[2]; const void* Mv[2];  /* [B][S_i][H] */
   const uint8_t* mask[2]; const float* prior[2]; const int32_t* map; int32_t map_ld;
   /* state */

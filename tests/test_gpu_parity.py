@@ -384,10 +384,12 @@ def test_cross_attention_kernels_vs_torch(W, S, nsplit):
            ml.data_ptr(), acc.data_ptr(), L.F32, st)
     torch.cuda.synchronize()
     assert rel_err(_merge_partials(ml, acc), ref(K, V)) < 1e-5
+    from case_rg_b200.engine import pack_kv_tiles
     Kb, Vb = K.bfloat16().contiguous(), V.bfloat16().contiguous()
+    KV = pack_kv_tiles(Kb, Vb)
     ml = torch.zeros(B * W, NH, P, 2, device=DEV)
     acc = torch.zeros(B * W, NH, P, HD, device=DEV)
-    L.call('case_cross_attn_partial_tc', q.data_ptr(), Kb.data_ptr(), Vb.data_ptr(), m8.data_ptr(), B, W, S, nsplit,
+    L.call('case_cross_attn_partial_tc', q.data_ptr(), KV.data_ptr(), m8.data_ptr(), B, W, S, nsplit,
            ml.data_ptr(), acc.data_ptr(), st)
     torch.cuda.synchronize()
     got = _merge_partials(ml, acc)
