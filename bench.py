@@ -265,6 +265,20 @@ def main():
     ms_e2e, wall_e2e, out_e = timed(step_e2e, args.steps)
     clk = clocks.stop() if rank == 0 else None
 
+    # where the step goes: prefill (once per batch) vs the T decode steps, timed separately
+    def _ev(fn, n=3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+    prefill_ms = _ev(lambda: eng.prefill(d.mem_q, d.mem_p, d.query.ne(0), d.passage.ne(0), d.prior_q, d.prior_p,
+                                         d.answer_rep, d.source_map))
+    decode_ms = _ev(lambda: eng.decode(T, mode, use_graph=not args.no_graph))
+
     # result gather (the path's only exchange): ids + answers to every rank
     ids, answers = gather_answers(d.ids, out, T, world * B)
 
@@ -287,7 +301,8 @@ def main():
                 warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype=args.dtype if args.dtype == 'bf16' else 'f32', data='synthetic',
                 config=config_dict(args, dict(cuda_graph=not args.no_graph, pdl=not args.no_pdl, vocab_gemm='tcgen05' if vocab_impl == 1 else 'simt')),
-                ms_per_decode_step=ms / args.steps / T, answer_tokens_per_step=tokens_per_step,
+                ms_per_decode_step=decode_ms / T, prefill_ms=prefill_ms, decode_ms=decode_ms,
+                answer_tokens_per_step=tokens_per_step,
                 e2e=dict(value=e2e_value, unit='tokens/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          ms_per_step=ms_e2e / args.steps),
                 gpu_launches=launches, clocks=clk, roofline=roof, cpu_baseline=cpu,

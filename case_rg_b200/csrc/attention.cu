@@ -411,11 +411,12 @@ extern "C" int case_additive_attn(const float* qa, const void* U, const void* Mv
 // row-wise and the transposed ldmatrix reads are bank-conflict free), which lets each warp stream its
 // tiles with one 8 KB bulk async copy per stage into a private 3-stage ring (mbarrier per stage; a
 // warp keeps one bulk copy in flight, eight warps per SM saturate HBM - profiles/micro/
-// hbm_stream_bench.cu).  Warps never synchronise until the end, where the CTA merges its four
-// warps and writes one partial per (row, head, split) for case_layer_back.  HBM traffic = K and V once.
+// hbm_stream_bench.cu).  A CTA is one (query, key split); its eight warps are the eight heads, each
+// walking its head's tiles on its own - no block-level synchronisation at all - and writing its own
+// partial per (row, head, split) for case_layer_back.  HBM traffic = K and V once.
 namespace cb {
 
-constexpr int XM_WARPS = 4;
+constexpr int XM_WARPS = 8;                        // one warp per head
 constexpr int XM_TILE = 64;                        // keys per tile
 constexpr int XM_TILE_BYTES = XM_TILE * HD * 2;    // 4 KB of K, then 4 KB of V
 constexpr int XM_STAGE = 2 * XM_TILE_BYTES;        // 8 KB per stage
@@ -469,14 +470,15 @@ __global__ __launch_bounds__(XM_WARPS * 32) void cross_attn_mma_kernel(
     const float* __restrict__ q2, const bf16* __restrict__ KV, const uint8_t* __restrict__ mask, int W, int S,
     int nsplit, float* __restrict__ part_ml, float* __restrict__ part_acc) {
   extern __shared__ __align__(128) unsigned char xm_smem[];   // [warp][XM_NS stages of K|V][barriers]
-  const int b = blockIdx.x, hh = blockIdx.y, sp = blockIdx.z;
+  const int b = blockIdx.x, sp = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int hh = warp;
   const int ntile_all = (S + XM_TILE - 1) / XM_TILE;
-  const int chunk = split_chunk(S, nsplit, XM_TILE * XM_WARPS);
+  const int chunk = split_chunk(S, nsplit, XM_TILE);
   const int s_begin = sp * chunk, s_end = min(S, s_begin + chunk);
-  const int tile0 = s_begin / XM_TILE + warp;                           // this warp's first tile
+  const int tile0 = s_begin / XM_TILE;                                  // this split's first tile
   const int tile_end = (s_end + XM_TILE - 1) / XM_TILE;
-  const int my_tiles = tile0 < tile_end ? (tile_end - tile0 + XM_WARPS - 1) / XM_WARPS : 0;
+  const int my_tiles = tile0 < tile_end ? tile_end - tile0 : 0;
   const char* kvb = reinterpret_cast<const char*>(KV) + ((size_t)(b * NH + hh)) * ntile_all * XM_STAGE;
   const uint8_t* mb = mask + (size_t)b * S;
   unsigned char* wsm = xm_smem + (size_t)warp * XM_WARP_BYTES;
@@ -492,7 +494,7 @@ __global__ __launch_bounds__(XM_WARPS * 32) void cross_attn_mma_kernel(
   if (lane == 0)
     for (int p = 0; p < XM_NS && p < my_tiles; ++p) {
       xm_expect(bars + 8 * p, XM_STAGE);
-      xm_bulk(sbase + p * XM_STAGE, kvb + (size_t)(tile0 + p * XM_WARPS) * XM_STAGE, XM_STAGE, bars + 8 * p);
+      xm_bulk(sbase + p * XM_STAGE, kvb + (size_t)(tile0 + p) * XM_STAGE, XM_STAGE, bars + 8 * p);
     }
 
   // Q fragments (A operand), rows >= W are zero
@@ -512,9 +514,20 @@ __global__ __launch_bounds__(XM_WARPS * 32) void cross_attn_mma_kernel(
 #pragma unroll
   for (int nb = 0; nb < 4; ++nb) { o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f; }
 
+  // key-validity bits of a tile: lane owns keys 2*lane, 2*lane+1 -> two ballots (even keys, odd keys).
+  // The bytes of tile i+1 are requested before waiting for tile i, so their latency is never exposed.
+  auto key_ok = [&](int s) { return s >= s_begin && s < s_end && mb[s] != 0; };
+  uint32_t be = 0, bo = 0;
+  if (my_tiles > 0) {
+    const int s = tile0 * XM_TILE + 2 * lane;
+    be = __ballot_sync(0xffffffffu, key_ok(s));
+    bo = __ballot_sync(0xffffffffu, key_ok(s + 1));
+  }
   for (int i = 0; i < my_tiles; ++i) {
     const int stage = i % XM_NS;
-    const int tile_s0 = (tile0 + i * XM_WARPS) * XM_TILE;
+    const int tile_s0 = (tile0 + i) * XM_TILE;
+    const int ns = tile_s0 + XM_TILE + 2 * lane;            // this lane's keys in the next tile
+    const bool ne = (i + 1 < my_tiles) && key_ok(ns), no = (i + 1 < my_tiles) && key_ok(ns + 1);
     while (!xm_try_wait(bars + 8 * stage, (uint32_t)(i / XM_NS) & 1u)) {}
     const uint32_t kt = sbase + stage * XM_STAGE, vt = kt + XM_TILE_BYTES;
     // ---- S = Q K^T for 8 key blocks of 8
@@ -527,11 +540,8 @@ __global__ __launch_bounds__(XM_WARPS * 32) void cross_attn_mma_kernel(
       float c[4] = {0.f, 0.f, 0.f, 0.f};
       mma_bf16_16816(c, qa[0][0], 0u, qa[0][1], 0u, kf[0], kf[1]);
       mma_bf16_16816(c, qa[1][0], 0u, qa[1][1], 0u, kf[2], kf[3]);
-      const int s = tile_s0 + kb * 8 + 2 * t;
-      const bool v0 = s >= s_begin && s < s_end && mb[s] != 0;
-      const bool v1 = s + 1 >= s_begin && s + 1 < s_end && mb[min(s + 1, S - 1)] != 0;
-      sc[kb][0] = v0 ? c[0] : -INFINITY;
-      sc[kb][1] = v1 ? c[1] : -INFINITY;
+      sc[kb][0] = ((be >> (kb * 4 + t)) & 1u) ? c[0] : -INFINITY;
+      sc[kb][1] = ((bo >> (kb * 4 + t)) & 1u) ? c[1] : -INFINITY;
       tmax = fmaxf(tmax, fmaxf(sc[kb][0], sc[kb][1]));
     }
     tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
@@ -562,46 +572,21 @@ __global__ __launch_bounds__(XM_WARPS * 32) void cross_attn_mma_kernel(
         mma_bf16_16816(o[c2 * 2 + 1], pa0, 0u, pa2, 0u, vf[2], vf[3]);
       }
     }
-    __syncwarp();                                         // every lane is done with this stage
+    be = __ballot_sync(0xffffffffu, ne);                  // also: every lane is done with this stage
+    bo = __ballot_sync(0xffffffffu, no);
     if (lane == 0 && i + XM_NS < my_tiles) {
       xm_expect(bars + 8 * stage, XM_STAGE);
-      xm_bulk(sbase + stage * XM_STAGE, kvb + (size_t)(tile0 + (i + XM_NS) * XM_WARPS) * XM_STAGE, XM_STAGE,
-              bars + 8 * stage);
+      xm_bulk(sbase + stage * XM_STAGE, kvb + (size_t)(tile0 + i + XM_NS) * XM_STAGE, XM_STAGE, bars + 8 * stage);
     }
   }
   l += __shfl_xor_sync(0xffffffffu, l, 1);
   l += __shfl_xor_sync(0xffffffffu, l, 2);
-  // merge the four warps of the CTA through shared memory (each warp parks its result in its own,
-  // now idle, staging region) so the CTA writes ONE partial per (row, head, split)
-  __syncwarp();
-  float* scr = reinterpret_cast<float*>(wsm);             // [8 rows][2 + 32]
-  if (t == 0) { scr[g * 34] = m; scr[g * 34 + 1] = l; }
+  if (g < W) {
+    const size_t oidx = (((size_t)(b * W + g)) * NH + hh) * nsplit + sp;
 #pragma unroll
-  for (int nb = 0; nb < 4; ++nb)
-    *reinterpret_cast<float2*>(scr + g * 34 + 2 + nb * 8 + 2 * t) = make_float2(o[nb][0], o[nb][1]);
-  __syncthreads();
-  {
-    const int row = threadIdx.x >> 4, dp = threadIdx.x & 15;       // 8 rows x 16 column pairs
-    if (row < W) {
-      float mw[XM_WARPS], M = -INFINITY;
-#pragma unroll
-      for (int w2 = 0; w2 < XM_WARPS; ++w2) {
-        mw[w2] = reinterpret_cast<const float*>(xm_smem + (size_t)w2 * XM_WARP_BYTES)[row * 34];
-        M = fmaxf(M, mw[w2]);
-      }
-      float L = 0.f, o0 = 0.f, o1 = 0.f;
-#pragma unroll
-      for (int w2 = 0; w2 < XM_WARPS; ++w2) {
-        const float* sw = reinterpret_cast<const float*>(xm_smem + (size_t)w2 * XM_WARP_BYTES) + row * 34;
-        const float e = (mw[w2] == -INFINITY) ? 0.f : fexp(mw[w2] - M);
-        L = fmaf(sw[1], e, L);
-        o0 = fmaf(sw[2 + 2 * dp], e, o0);
-        o1 = fmaf(sw[3 + 2 * dp], e, o1);
-      }
-      const size_t oidx = (((size_t)(b * W + row)) * NH + hh) * nsplit + sp;
-      *reinterpret_cast<float2*>(part_acc + oidx * HD + 2 * dp) = make_float2(o0, o1);
-      if (dp == 0) { part_ml[oidx * 2] = M; part_ml[oidx * 2 + 1] = L; }
-    }
+    for (int nb = 0; nb < 4; ++nb)
+      *reinterpret_cast<float2*>(part_acc + oidx * HD + nb * 8 + 2 * t) = make_float2(o[nb][0], o[nb][1]);
+    if (t == 0) { part_ml[oidx * 2] = m; part_ml[oidx * 2 + 1] = l; }
   }
 }
 
@@ -618,7 +603,7 @@ extern "C" int case_cross_attn_partial_tc(const float* q2, const void* KV, const
     cudaFuncSetAttribute(cb::cross_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cb::XM_SMEM);
     attr = true;
   }
-  launch_k(cb::cross_attn_mma_kernel, dim3(B, cb::NH, nsplit), cb::XM_WARPS * 32, cb::XM_SMEM, (cudaStream_t)stream,
+  launch_k(cb::cross_attn_mma_kernel, dim3(B, nsplit), cb::XM_WARPS * 32, cb::XM_SMEM, (cudaStream_t)stream,
            q2, (const cb::bf16*)KV, mask, W, S, nsplit, part_ml, part_acc);
   return cb::check_launch("case_cross_attn_partial_tc");
 }

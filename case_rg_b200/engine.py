@@ -268,8 +268,10 @@ class CaseDecodeEngine(_EngineBase):
                                     device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
         z = lambda *s: torch.zeros(*s, **f32)
-        # cross-attention CTAs are (query, head, split): aim for ~6 resident CTAs per SM so the tail is short
-        self.nsx = [_nsplit(B * L.NH, s, L.XATTN_TILE, 6 * 148) for s in self.S]
+        if weights.cdtype == L.BF16:   # tensor-core kernel: CTA = (query, split), one warp per head, 1 CTA per SM
+            self.nsx = [_nsplit(B, s, 2 * 64, 128) for s in self.S]
+        else:                          # SIMT kernel: CTA = (query, head, split)
+            self.nsx = [_nsplit(B * L.NH, s, L.XATTN_TILE, 6 * 148) for s in self.S]
         self.nsa = [_nsplit(B, s, L.AATTN_TILE, 2 * target_ctas) for s in self.S]
         # per-batch tensors
         self.feat = z(B, H)
@@ -361,11 +363,12 @@ class CaseDecodeEngine(_EngineBase):
                 raise ValueError(f'memory {i} has {m.size(1)} positions, engine was built for {S}')
             flat = m.reshape(B * S, H)
             kv = torch.addmm(w.kv_b[i], flat, w.kv_w[i])                       # [B*S, 4*2*H]
-            kv = kv.view(B, S, 4, 2, L.NH, L.HD).permute(2, 3, 0, 4, 1, 5)     # [l][k/v][B][NH][S][HD]
-            for l in range(4):
-                if w.cdtype == L.BF16:
-                    pack_kv_tiles(kv[l, 0], kv[l, 1], out=self.Kx[i * 4 + l])
-                else:
+            if w.cdtype == L.BF16:        # one pass: fp32 GEMM rows -> swizzled bf16 K|V tiles of all 4 layers
+                outs = (C.c_void_p * 4)(*[self.Kx[i * 4 + l].data_ptr() for l in range(4)])
+                L.call('case_pack_kv_tiles', kv.data_ptr(), kv.size(1), B, S, 4, outs, stream)
+            else:
+                kv = kv.view(B, S, 4, 2, L.NH, L.HD).permute(2, 3, 0, 4, 1, 5)     # [l][k/v][B][NH][S][HD]
+                for l in range(4):
                     self.Kx[i * 4 + l].copy_(kv[l, 0])
                     self.Vx[i * 4 + l].copy_(kv[l, 1])
             self.U[i].copy_((flat @ w.Uk_t[i]).view(B, S, H))
