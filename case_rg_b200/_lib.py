@@ -77,7 +77,7 @@ _PROTOS = {
     'case_layer_front': [vp, C.POINTER(LayerWeights), vp, vp, vp, i32, vp, i32, i32, i32, vp, vp, i32, i32, vp],
     'case_cross_attn_partial': [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp],
     'case_cross_attn_partial_tc': [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp],
-    'case_pack_kv_tiles': [vp, i32, i32, i32, i32, vp, vp],
+    'case_pack_kv_tiles': [vp, i32, i32, i32, i32, i32, vp, vp],
     'case_layer_back': [vp, vp, vp, i32, C.POINTER(LayerWeights), vp, i32, i32, vp],
     'case_additive_attn': [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp],
     'case_finalize_rows': [vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp],

@@ -293,7 +293,8 @@ extern "C" int case_topk_rows(const float* dist, int ldd, int R, int V, int k, f
 // threads walk one source row, so reads are fully coalesced and writes land as 64-byte runs.
 namespace cb {
 struct KvOut { bf16* p[4]; };
-__global__ __launch_bounds__(256) void pack_kv_tiles_kernel(const float* __restrict__ kv, int ldkv, int B, int S,
+template <typename TS>
+__global__ __launch_bounds__(256) void pack_kv_tiles_kernel(const TS* __restrict__ kv, int ldkv, int B, int S,
                                                             int nl, KvOut out) {
   pdl_trigger();
   pdl_wait();
@@ -307,12 +308,16 @@ __global__ __launch_bounds__(256) void pack_kv_tiles_kernel(const float* __restr
     const int s = tile * 64 + key;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (s < S) {
-      const float* src = kv + ((size_t)b * S + s) * ldkv + ((l * 2 + j) * NH + hh) * HD + c * 8;
-      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), d = __ldg(reinterpret_cast<const float4*>(src) + 1);
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
-      __nv_bfloat162 p2 = __floats2bfloat162_rn(d.x, d.y), p3 = __floats2bfloat162_rn(d.z, d.w);
-      v.x = *reinterpret_cast<uint32_t*>(&p0); v.y = *reinterpret_cast<uint32_t*>(&p1);
-      v.z = *reinterpret_cast<uint32_t*>(&p2); v.w = *reinterpret_cast<uint32_t*>(&p3);
+      const TS* src = kv + ((size_t)b * S + s) * ldkv + ((l * 2 + j) * NH + hh) * HD + c * 8;
+      if (sizeof(TS) == 2) {
+        v = __ldg(reinterpret_cast<const uint4*>(src));
+      } else {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src)), d = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(d.x, d.y), p3 = __floats2bfloat162_rn(d.z, d.w);
+        v.x = *reinterpret_cast<uint32_t*>(&p0); v.y = *reinterpret_cast<uint32_t*>(&p1);
+        v.z = *reinterpret_cast<uint32_t*>(&p2); v.w = *reinterpret_cast<uint32_t*>(&p3);
+      }
     }
     char* dst = reinterpret_cast<char*>(out.p[l]) + ((((size_t)(b * NH + hh) * ntile + tile) * 2 + j) * 64 + key) * 64 +
                 ((c ^ ((key >> 1) & 3)) << 4);
@@ -321,12 +326,16 @@ __global__ __launch_bounds__(256) void pack_kv_tiles_kernel(const float* __restr
 }
 }  // namespace cb
 
-extern "C" int case_pack_kv_tiles(const float* kv, int ldkv, int B, int S, int nl, void* const* out,
+extern "C" int case_pack_kv_tiles(const void* kv, int src_dtype, int ldkv, int B, int S, int nl, void* const* out,
                                   case_stream_t stream) {
   CB_REQUIRE(kv && out && B > 0 && S > 0 && nl >= 1 && nl <= 4, "case_pack_kv_tiles: bad arguments");
-  CB_REQUIRE(ldkv % 4 == 0 && (uintptr_t)kv % 16 == 0, "case_pack_kv_tiles: source rows must be 16-byte aligned");
+  CB_REQUIRE(ldkv % 8 == 0 && (uintptr_t)kv % 16 == 0, "case_pack_kv_tiles: source rows must be 16-byte aligned");
   cb::KvOut o;
   for (int l = 0; l < 4; ++l) o.p[l] = l < nl ? (cb::bf16*)out[l] : nullptr;
-  launch_k(cb::pack_kv_tiles_kernel, 148 * 8, 256, 0, (cudaStream_t)stream, kv, ldkv, B, S, nl, o);
+  if (src_dtype == CASE_BF16)
+    launch_k(cb::pack_kv_tiles_kernel<cb::bf16>, 148 * 8, 256, 0, (cudaStream_t)stream, (const cb::bf16*)kv, ldkv, B, S,
+             nl, o);
+  else
+    launch_k(cb::pack_kv_tiles_kernel<float>, 148 * 8, 256, 0, (cudaStream_t)stream, (const float*)kv, ldkv, B, S, nl, o);
   return cb::check_launch("case_pack_kv_tiles");
 }

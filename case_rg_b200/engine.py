@@ -159,8 +159,8 @@ class CaseWeights:
                     setattr(lw, k, v.data_ptr())
                 kvw.append(Wx[H:].t())                            # [H][2H]: K cols then V cols
                 kvb.append(bx[H:])
-            self.kv_w.append(torch.cat(kvw, dim=1).contiguous())  # [H][Ln*2H]
-            self.kv_b.append(torch.cat(kvb).contiguous())
+            self.kv_w.append(torch.cat(kvw, dim=1).contiguous().to(self.tdtype))  # [H][Ln*2H]
+            self.kv_b.append(torch.cat(kvb).contiguous().to(self.tdtype))
         self.E = g('embedding.0.weight').contiguous()
         self.pe = g('embedding.1.pe').contiguous()
         self.lnN_g, self.lnN_b = vec(g('norm1.weight')), vec(g('norm1.bias'))
@@ -168,7 +168,7 @@ class CaseWeights:
         self.Wqa_t = [mat(g(f'attns.{i}.linear_query.weight')) for i in range(2)]
         self.bqa = [vec(g(f'attns.{i}.linear_query.bias')) for i in range(2)]
         self.va = [g(f'attns.{i}.v.weight').reshape(-1).contiguous() for i in range(2)]
-        self.Uk_t = [g(f'attns.{i}.linear_key.weight').t().contiguous() for i in range(2)]   # fp32 [H][H]
+        self.Uk_t = [g(f'attns.{i}.linear_key.weight').t().contiguous().to(self.tdtype) for i in range(2)]   # [H][H]
         self.Wg_t, self.bg = mat(g('gen.0.weight')), vec(g('gen.0.bias'))
         self.Wv = g('gen.2.weight').contiguous().to(self.tdtype)                               # [V][H]
         self.Wv_tc = pack_vocab_tc(g('gen.2.weight')) if self.cdtype == L.BF16 else None
@@ -358,20 +358,20 @@ class CaseDecodeEngine(_EngineBase):
                B, stream)
         for i in range(2):
             S = self.S[i]
-            m = mems[i].to(dev, torch.float32)
+            m = mems[i].to(dev, w.tdtype)         # bf16 storage: the prefill GEMMs run on bf16 tensor cores
             if m.size(1) != S:
                 raise ValueError(f'memory {i} has {m.size(1)} positions, engine was built for {S}')
             flat = m.reshape(B * S, H)
             kv = torch.addmm(w.kv_b[i], flat, w.kv_w[i])                       # [B*S, 4*2*H]
-            if w.cdtype == L.BF16:        # one pass: fp32 GEMM rows -> swizzled bf16 K|V tiles of all 4 layers
+            if w.cdtype == L.BF16:        # one pass: GEMM rows -> swizzled bf16 K|V tiles of all 4 layers
                 outs = (C.c_void_p * 4)(*[self.Kx[i * 4 + l].data_ptr() for l in range(4)])
-                L.call('case_pack_kv_tiles', kv.data_ptr(), kv.size(1), B, S, 4, outs, stream)
+                L.call('case_pack_kv_tiles', kv.data_ptr(), L.BF16, kv.size(1), B, S, 4, outs, stream)
             else:
                 kv = kv.view(B, S, 4, 2, L.NH, L.HD).permute(2, 3, 0, 4, 1, 5)     # [l][k/v][B][NH][S][HD]
                 for l in range(4):
                     self.Kx[i * 4 + l].copy_(kv[l, 0])
                     self.Vx[i * 4 + l].copy_(kv[l, 1])
-            self.U[i].copy_((flat @ w.Uk_t[i]).view(B, S, H))
+            torch.mm(flat, w.Uk_t[i], out=self.U[i].view(B * S, H))
             self.Mv[i].copy_(m)
             self.mask[i].copy_(masks[i].to(dev).to(torch.uint8))
             self.prior[i].copy_(priors[i].to(dev, torch.float32))
@@ -428,7 +428,7 @@ class GttpWeights:
         self.Wq_t = [mat(g(f'dec.{a}.linear_query.weight')) for a in ('src_attn', 'bg_attn')]
         self.bq = [g(f'dec.{a}.linear_query.bias').contiguous() for a in ('src_attn', 'bg_attn')]
         self.v = [g(f'dec.{a}.v.weight').reshape(-1).contiguous() for a in ('src_attn', 'bg_attn')]
-        self.Uk_t = [g(f'dec.{a}.linear_key.weight').t().contiguous() for a in ('src_attn', 'bg_attn')]  # [2H][H]
+        self.Uk_t = [g(f'dec.{a}.linear_key.weight').t().contiguous().to(self.tdtype) for a in ('src_attn', 'bg_attn')]  # [2H][H]
         self.Wih_t, self.bih = mat(g('dec.gru.weight_ih_l0')), g('dec.gru.bias_ih_l0').contiguous()
         self.Whh_t, self.bhh = mat(g('dec.gru.weight_hh_l0')), g('dec.gru.bias_hh_l0').contiguous()
         self.Wr_t, self.br = mat(g('dec.readout.weight')), g('dec.readout.bias').contiguous()
@@ -508,9 +508,9 @@ class GttpDecodeEngine(_EngineBase):
         masks (GTTP/Model.py:177-178) and the initial GRU state (:170-174), replicated per beam slot."""
         B, H, w, dev = self.B, L.H, self.w, self.device
         for i, (m, ids) in enumerate(((src_output, context), (bg_output, background))):
-            m = m.to(dev, torch.float32)
+            m = m.to(dev, w.tdtype)
             S = m.size(1)
-            self.U[i].copy_((m.reshape(B * S, 2 * H) @ w.Uk_t[i]).view(B, S, H))
+            torch.mm(m.reshape(B * S, 2 * H), w.Uk_t[i], out=self.U[i].view(B * S, H))
             self.Mv[i].copy_(m)
             self.mask[i].copy_(ids.to(dev).ne(0).to(torch.uint8))
         self.map.copy_(background_map.to(dev).to(torch.int32))

@@ -140,10 +140,12 @@ int case_cross_attn_partial(const float* q2, const void* Kmem, const void* Vmem,
 int case_cross_attn_partial_tc(const float* q2, const void* KV, const uint8_t* mask, int B, int W, int S,
                                int nsplit, float* part_ml, float* part_acc, case_stream_t stream);
 
-/* Prefill helper: the fp32 output rows of the memory K/V projection GEMM, kv [B*S][ldkv] with columns
- * (layer, K|V, head, dim), re-packed into the KV layout above for `nl` (<= 4) layers; out[l] = that
- * layer's buffer.  (The projection itself, TransformerDecoder.py:81, is a plain GEMM done once per batch.) */
-int case_pack_kv_tiles(const float* kv, int ldkv, int B, int S, int nl, void* const* out, case_stream_t stream);
+/* Prefill helper: the output rows of the memory K/V projection GEMM, kv [B*S][ldkv] (fp32 or bf16,
+ * src_dtype) with columns (layer, K|V, head, dim), re-packed into the KV layout above for `nl` (<= 4)
+ * layers; out[l] = that layer's buffer.  (The projection itself, TransformerDecoder.py:81, is a plain
+ * GEMM done once per batch.) */
+int case_pack_kv_tiles(const void* kv, int src_dtype, int ldkv, int B, int S, int nl, void* const* out,
+                       case_stream_t stream);
 
 /* Second half (TransformerDecoder.py:82-89): ctx = merge(partials); h2 = b + ctx.Wo2;
  * c = LN3(h2); h_out = c + W2.gelu(W1.c). */
