@@ -30,7 +30,7 @@ class RowLinArgs(C.Structure):
 
 class LayerWeights(C.Structure):
     _fields_ = [(n, vp) for n in ('Wqkv_t', 'bqkv', 'Wo_t', 'bo', 'Wq2_t', 'bq2', 'Wo2_t', 'bo2', 'W1_t', 'b1',
-                                  'W2_t', 'b2', 'ln1_g', 'ln1_b', 'ln2_g', 'ln2_b', 'ln3_g', 'ln3_b')]
+                                  'W2_t', 'b2', 'ln1_g', 'ln1_b', 'ln2_g', 'ln2_b', 'ln3_g', 'ln3_b', 'Wc')]
 
 
 class SelectArgs(C.Structure):
@@ -52,7 +52,7 @@ class StepArgs(C.Structure):
                 ('out_tokens', vp), ('n_live', vp),
                 ('x_in', vp), ('h', vp), ('bbuf', vp), ('q2', vp), ('part_ml', vp), ('part_acc', vp), ('qa', vp),
                 ('attn_un', vp * 2), ('stats', vp * 2), ('ctxp', vp * 2), ('hN', vp), ('ctx', vp * 2), ('gates', vp),
-                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp)]
+                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp), ('prow', vp), ('h0', vp), ('qa1', vp)]
 
 
 class GttpStepArgs(C.Structure):
@@ -79,6 +79,9 @@ _PROTOS = {
     'case_cross_attn_partial_tc': [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp],
     'case_pack_kv_tiles': [vp, i32, i32, i32, i32, i32, vp, vp],
     'case_layer_back': [vp, vp, vp, i32, C.POINTER(LayerWeights), vp, i32, i32, vp],
+    'case_layer_chain': [C.POINTER(LayerWeights), C.POINTER(LayerWeights), vp, vp, vp, C.c_float, vp, vp, vp, vp, i32,
+                         vp, vp, vp, vp, i32, vp, i32, vp, i32, i32, vp, vp, i32, i32, vp],
+    'case_layer_chain_max_tmax': [],
     'case_additive_attn': [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp],
     'case_finalize_rows': [vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp],
     'case_vocab_gemm': [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp],
@@ -91,6 +94,8 @@ _PROTOS = {
     'case_attn_merge': [vp, vp, i32, i32, vp, vp, i32, i32, vp],
     'case_gttp_gates': [vp, vp, vp, vp, vp, i32, i32, i32, vp],
     'case_set_pdl': [i32],
+    'case_set_chain': [i32],
+    'case_set_fork': [i32],
     'case_decode_step': [C.POINTER(StepArgs), i32, vp],
     'gttp_decode_step': [C.POINTER(GttpStepArgs), i32, vp],
 }

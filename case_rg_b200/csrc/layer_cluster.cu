@@ -1,0 +1,675 @@
+// Cluster form of the decoder-layer row work (bf16 storage): layer_back(L-1) + layer_front(L) of
+// TransformerDecoderLayer.forward (common/TransformerDecoder.py:61-90) in ONE kernel between two
+// cross-attention launches (the first launch of a step also does the embedding, Model.py:96).
+//
+// Why: the row-block kernels of rowops_tc.cu make every CTA stream all eight 256x256 matrices of a
+// layer (1 MB) plus the self-attention history of all eight heads through one SM, so a layer costs
+// ~30 us of L2->SM latency however few rows a CTA owns.  Here a thread-block cluster of 4 CTAs owns 8
+// decode rows and CTA c of the cluster owns output columns [64c, 64c+64) of EVERY linear - exactly
+// heads 2c and 2c+1 of the attention - so a CTA ingests a quarter of every matrix (a [64 n][256 k]
+// slice, 32 KB, requested long before it is needed) and a quarter of the KV history (prefetched into
+// shared memory with cp.async while the preceding cross-attention is still running).  Between
+// dependent linears the 8 x 64 result slices are exchanged through distributed shared memory with
+// st.async: every store carries its byte count to an mbarrier in the destination CTA, so a consumer
+// waits exactly for the bytes it needs (one DSMEM hop) instead of a cluster-wide barrier.  Slices
+// travel as bf16 when the consumer is an MMA operand and as fp32 when it is a LayerNorm (each CTA then
+// normalises the 8 full rows redundantly).  Self-attention needs no exchange.
+//   (4 x 8 rather than 8 x 16: at one CTA per SM only 15 clusters of 8 can be co-resident on a B200 -
+//    cudaOccupancyMaxActiveClusters - which is one short of the 16 that 256 decode rows need.)
+//
+// Buffer reuse is safe without any barrier: a CTA writes exchange k+2 into a peer's tile only after it
+// has received that peer's exchange k+1, which the peer sent after it finished reading exchange k.
+//
+// Weight layout ("cluster-packed", one blob per layer): bf16 [4 ranks][8 matrices][64 n][256 k],
+// matrices in the order Wq, Wk, Wv, Wo, Wq2, Wo2, W1, W2 (rows 64c..64c+63 of the nn.Linear weight
+// [out][in]); inside a 512-byte row the 16-byte chunk kc is stored at position kc ^ (n & 7) so the
+// ldmatrix reads of eight consecutive rows are bank-conflict free.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace cb {
+
+constexpr int CL = 4;              // CTAs per cluster
+constexpr int CROWS = 8;           // decode rows per cluster (rows 8..15 of the MMA tile are zero)
+constexpr int CCOL = 64;           // output columns (two heads) per CTA
+constexpr int CT = 256;            // threads per CTA
+constexpr int CNS = 3;             // weight slots
+constexpr int CWB = CCOL * H * 2;  // bytes of one matrix slice (32 KB)
+constexpr int CALD = H + 8;        // bf16 A-tile row stride
+constexpr int CFLD = H + 4;        // fp32 tile row stride
+constexpr int CTMAX = 48;          // largest Tmax the shared-memory KV history supports
+constexpr int CSCLD = CTMAX + 1;   // score row stride
+constexpr uint32_t CMASKED = 0x40000000u;
+constexpr uint32_t XA_BYTES = CROWS * H * 2, XF_BYTES = CROWS * H * 4;   // payload of one exchange
+
+constexpr int OFF_W = 0;
+constexpr int OFF_XA = OFF_W + CNS * CWB;
+constexpr int OFF_LA = OFF_XA + CROWS * CALD * 2;
+constexpr int OFF_XF = OFF_LA + CROWS * CALD * 2;
+constexpr int OFF_OWN = OFF_XF + CROWS * CFLD * 4;
+constexpr int OFF_Q = OFF_OWN + CROWS * CCOL * 4;
+constexpr int OFF_SC = OFF_Q + CROWS * CCOL * 4;
+constexpr int OFF_PAR = OFF_SC + 2 * CROWS * CSCLD * 4;
+constexpr int OFF_PROW = OFF_PAR + (8 * CCOL + 6 * H) * 4;
+constexpr int OFF_BAR = OFF_PROW + CROWS * CTMAX * 4;
+constexpr int OFF_KV = OFF_BAR + 64;           // K history [8 rows][2 heads][Tmax][32] bf16, then V history
+
+struct ChainArgs {
+  int R, t, Tmax, nsplit, has_back, has_front, first;
+  // back half (layer Lb)
+  const float* b_in; const float* part_ml; const float* part_acc;
+  const char* wb;
+  const float *bo2, *b1, *b2, *ln3_g, *ln3_b;
+  float* h_out;
+  // front half (layer Lf)
+  const float* h_in;                                   // front-only launch without embedding
+  const float* E; const float* pe; float emb_scale; float* x_out;   // front-only launch with embedding
+  const char* wf;
+  const float *bqkv, *bo, *bq2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  bf16* kc; bf16* vc;
+  const int32_t* anc; int anc_ld;
+  const int32_t* tok; int tok_ld;
+  int32_t* prow_g;                                     // [R][Tmax] history row table of this step (may be NULL)
+  float* b_out; float* q2_out;
+  long long* dbg;      // optional stage clock stamps of CTA 0 (case_debug_chain_timing)
+};
+
+static long long* g_chain_dbg = nullptr;
+
+// ---- PTX helpers
+__device__ __forceinline__ void c_mb_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void c_mb_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void c_mb_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void c_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void c_cpasync16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void c_cpasync_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t c_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// 16-byte store into a peer's shared memory that reports its bytes to the peer's mbarrier
+__device__ __forceinline__ void c_st_async16(uint32_t raddr, uint32_t rbar, uint32_t x, uint32_t y, uint32_t z,
+                                             uint32_t w) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   raddr),
+               "r"(x), "r"(y), "r"(z), "r"(w), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void c_ldsm4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void c_ldsm2(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+// rows 8..15 of the A tile are zero: a1 = a3 = 0
+__device__ __forceinline__ void c_mma8(float (&c)[4], const uint32_t (&a)[2], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(0u), "r"(a[1]), "r"(0u), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t c_pack(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// D[8 x 8] = A[8 x 256] . W[8 n][256 k]^T for n-subtile `ns` of a weight slot: 16 k-steps on two
+// independent accumulators.  Lane (g = lane / 4, tq = lane % 4) ends up with row g, columns 8 ns + 2 tq, +1.
+__device__ __forceinline__ float2 mma_cols8(uint32_t a_tile, uint32_t w_slot, int ns) {
+  const int lane = threadIdx.x & 31;
+  float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint32_t a_base = a_tile + (uint32_t)((lane & 7) * CALD + ((lane >> 3) & 1) * 8) * 2;
+  const int n = ns * 8 + (lane & 7), mi = lane >> 3;
+  const uint32_t b_row = w_slot + (uint32_t)n * 512;
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    uint32_t a0[2], a1[2], b[4];
+    c_ldsm2(a0, a_base + (uint32_t)(2 * kk) * 32);
+    c_ldsm2(a1, a_base + (uint32_t)(2 * kk + 1) * 32);
+    c_ldsm4(b, b_row + (uint32_t)(((4 * kk + mi) ^ (n & 7)) << 4));
+    c_mma8(acc0, a0, b[0], b[1]);
+    c_mma8(acc1, a1, b[2], b[3]);
+  }
+  return make_float2(acc0[0] + acc1[0], acc0[1] + acc1[1]);
+}
+
+// q | k | v of the same 8 columns from three weight slots, sharing the A fragments (6 accumulators)
+__device__ __forceinline__ void mma_cols8x3(uint32_t a_tile, const uint32_t (&w_slot)[3], int ns, float2 (&out)[3]) {
+  const int lane = threadIdx.x & 31;
+  float acc[3][2][4];
+#pragma unroll
+  for (int m = 0; m < 3; ++m)
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) { acc[m][h2][0] = acc[m][h2][1] = acc[m][h2][2] = acc[m][h2][3] = 0.f; }
+  const uint32_t a_base = a_tile + (uint32_t)((lane & 7) * CALD + ((lane >> 3) & 1) * 8) * 2;
+  const int n = ns * 8 + (lane & 7), mi = lane >> 3;
+  const uint32_t b_off = (uint32_t)n * 512;
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    uint32_t a0[2], a1[2];
+    c_ldsm2(a0, a_base + (uint32_t)(2 * kk) * 32);
+    c_ldsm2(a1, a_base + (uint32_t)(2 * kk + 1) * 32);
+    const uint32_t ch = (uint32_t)(((4 * kk + mi) ^ (n & 7)) << 4);
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      uint32_t b[4];
+      c_ldsm4(b, w_slot[m] + b_off + ch);
+      c_mma8(acc[m][0], a0, b[0], b[1]);
+      c_mma8(acc[m][1], a1, b[2], b[3]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 3; ++m) out[m] = make_float2(acc[m][0][0] + acc[m][1][0], acc[m][0][1] + acc[m][1][1]);
+}
+
+// ---- exchanges.  MMA-epilogue role: lane (g, tq) of warp w holds row g, columns 64c + 8w + 2tq, +1.
+// fp32: lane pairs build a 16-byte store; even tq feeds ranks 0,1 and odd tq ranks 2,3.
+__device__ __forceinline__ void bcast_f32(uint32_t xf_local, uint32_t bar_local, int c, float v0, float v1) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, tq = lane & 3;
+  const float p0 = __shfl_xor_sync(0xffffffffu, v0, 1), p1 = __shfl_xor_sync(0xffffffffu, v1, 1);
+  const bool odd = tq & 1;
+  const uint32_t x = __float_as_uint(odd ? p0 : v0), y = __float_as_uint(odd ? p1 : v1);
+  const uint32_t z = __float_as_uint(odd ? v0 : p0), ww = __float_as_uint(odd ? v1 : p1);
+  const uint32_t la = xf_local + (uint32_t)(g * CFLD + CCOL * c + 8 * w + 4 * (tq >> 1)) * 4;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const uint32_t rk = (uint32_t)((odd ? 2 : 0) + k);
+    c_st_async16(c_mapa(la, rk), c_mapa(bar_local, rk), x, y, z, ww);
+  }
+}
+// bf16: the four lanes of a quad hold 8 consecutive columns = one 16-byte store; lane q feeds rank q.
+// (row, col8) = tile row and first of the 8 columns (multiple of 8) the quad covers.
+__device__ __forceinline__ void bcast_bf16(uint32_t xa_local, uint32_t bar_local, int row, int col8, uint32_t packed) {
+  const int lane = threadIdx.x & 31, base = lane & ~3;
+  const uint32_t x = __shfl_sync(0xffffffffu, packed, base), y = __shfl_sync(0xffffffffu, packed, base + 1);
+  const uint32_t z = __shfl_sync(0xffffffffu, packed, base + 2), w = __shfl_sync(0xffffffffu, packed, base + 3);
+  const uint32_t la = xa_local + (uint32_t)(row * CALD + col8) * 2;
+  const uint32_t rk = (uint32_t)(lane & 3);
+  c_st_async16(c_mapa(la, rk), c_mapa(bar_local, rk), x, y, z, w);
+}
+
+// LayerNorm of the 8 full fp32 rows in xf (warp w: row w) -> bf16 A tile `la`; the CTA's own 64 columns
+// are kept in fp32 (`own`, the residual of the next linear) and optionally stored to gout.
+__device__ __forceinline__ void ln_rows(const float* xf, const float* g, const float* b, bf16* la, float* own, int c,
+                                        float* gout, int r0, int R) {
+  const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4 x0 = *reinterpret_cast<const float4*>(xf + i * CFLD + lane * 8);
+  const float4 x1 = *reinterpret_cast<const float4*>(xf + i * CFLD + lane * 8 + 4);
+  const float4 g0 = *reinterpret_cast<const float4*>(g + lane * 8), g1 = *reinterpret_cast<const float4*>(g + lane * 8 + 4);
+  const float4 b0 = *reinterpret_cast<const float4*>(b + lane * 8), b1 = *reinterpret_cast<const float4*>(b + lane * 8 + 4);
+  const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += v[k];
+  const float mean = warp_sum(s) * (1.f / H);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { const float d = v[k] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / H) + LN_EPS);
+  float y[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) y[k] = (v[k] - mean) * rstd * gg[k] + bb[k];
+  *reinterpret_cast<uint4*>(la + i * CALD + lane * 8) =
+      make_uint4(c_pack(y[0], y[1]), c_pack(y[2], y[3]), c_pack(y[4], y[5]), c_pack(y[6], y[7]));
+  if ((lane >> 3) == c) {
+    float* o = own + i * CCOL + (lane & 7) * 8;
+    *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+    if (gout != nullptr && r0 + i < R) {
+      float* go = gout + (size_t)(r0 + i) * H + lane * 8;
+      *reinterpret_cast<float4*>(go) = make_float4(y[0], y[1], y[2], y[3]);
+      *reinterpret_cast<float4*>(go + 4) = make_float4(y[4], y[5], y[6], y[7]);
+    }
+  }
+}
+
+__global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t rank_u;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank_u));
+  const int c = (int)rank_u;                         // rank in the cluster: columns [64c, 64c+64), heads 2c, 2c+1
+  const int r0 = (blockIdx.x / CL) * CROWS;
+  const int t = a.t, Tmax = a.Tmax;
+  // MMA / epilogue role: warp = 8-column subtile, lane = (row g, column pair tq)
+  const int g = lane >> 2, tq = lane & 3;
+  const int er = r0 + g, erl = min(er, a.R - 1);     // rows past R replay row R-1 and store nothing
+  const int ecol = CCOL * c + 8 * warp + 2 * tq;     // global column of the lane's pair
+  // attention role: 16 lanes per (row, local head)
+  const int ai = tid >> 5, ahl = (tid >> 4) & 1, acp = tid & 15;
+  const int arl = min(r0 + ai, a.R - 1);
+
+  int dbg_n = 0;
+  auto stamp = [&]() {
+    if (a.dbg != nullptr && blockIdx.x == 0 && tid == 0) a.dbg[dbg_n++] = clock64();
+  };
+  stamp();
+  const uint32_t s_base = smem_u32(sm);
+  const uint32_t s_w = s_base + OFF_W, s_xa = s_base + OFF_XA, s_la = s_base + OFF_LA, s_xf = s_base + OFF_XF;
+  const uint32_t s_bar = s_base + OFF_BAR;           // [0..2] weight slots, [3] XA exchange, [4] XF exchange
+  const uint32_t s_bxa = s_bar + 24, s_bxf = s_bar + 32;
+  bf16* la = reinterpret_cast<bf16*>(sm + OFF_LA);
+  float* xf = reinterpret_cast<float*>(sm + OFF_XF);
+  float* own = reinterpret_cast<float*>(sm + OFF_OWN);
+  float* q_s = reinterpret_cast<float*>(sm + OFF_Q);
+  float* sc = reinterpret_cast<float*>(sm + OFF_SC);
+  float* par = reinterpret_cast<float*>(sm + OFF_PAR);   // 8 bias slices of 64, then 6 LN vectors of 256
+  uint32_t* prow = reinterpret_cast<uint32_t*>(sm + OFF_PROW);
+  bf16* kh_s = reinterpret_cast<bf16*>(sm + OFF_KV);
+  bf16* vh_s = kh_s + (size_t)CROWS * 2 * Tmax * 32;
+
+  // ---- weight sequence of this launch: [Wo2 W1 W2] then [Wq Wk Wv Wo Wq2]
+  const int nback = a.has_back ? 3 : 0;
+  const int nseq = nback + (a.has_front ? 5 : 0);
+  auto seq_ptr = [&](int k) -> const char* {
+    return k < nback ? a.wb + (size_t)(c * 8 + 5 + k) * CWB : a.wf + (size_t)(c * 8 + (k - nback)) * CWB;
+  };
+  int issued = 0;                                    // thread 0 only
+  auto refill = [&](int consumed) {
+    if (tid == 0) {
+      while (issued < nseq && issued < consumed + CNS) {
+        const int slot = issued % CNS;
+        c_mb_expect(s_bar + 8 * slot, CWB);
+        c_bulk(s_w + slot * CWB, seq_ptr(issued), CWB, s_bar + 8 * slot);
+        ++issued;
+      }
+    }
+  };
+  auto wait_w = [&](int k) -> uint32_t {             // returns the shared address of matrix k of the sequence
+    c_mb_wait(s_bar + 8 * (k % CNS), (uint32_t)(k / CNS) & 1u);
+    return s_w + (k % CNS) * CWB;
+  };
+  // exchange barriers: thread 0 arms the next phase as soon as the current one has completed
+  uint32_t ph_xa = 0, ph_xf = 0;
+  auto wait_xa = [&]() {
+    c_mb_wait(s_bxa, ph_xa & 1u);
+    ++ph_xa;
+    if (tid == 0) c_mb_expect(s_bxa, XA_BYTES);
+  };
+  auto wait_xf = [&]() {
+    c_mb_wait(s_bxf, ph_xf & 1u);
+    ++ph_xf;
+    if (tid == 0) c_mb_expect(s_bxf, XF_BYTES);
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < 5; ++s) c_mb_init(s_bar + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    c_mb_expect(s_bxa, XA_BYTES);
+    c_mb_expect(s_bxf, XF_BYTES);
+  }
+  __syncthreads();
+  refill(0);
+
+  // ---- constants: bias slices and LayerNorm vectors
+  {
+    const float* bsrc[8] = {a.bqkv, a.bqkv ? a.bqkv + H : nullptr, a.bqkv ? a.bqkv + 2 * H : nullptr, a.bo, a.bq2,
+                            a.bo2, a.b1, a.b2};
+#pragma unroll
+    for (int m2 = 0; m2 < 2; ++m2) {
+      const int idx = tid + m2 * CT, m = idx >> 6, k = idx & 63;
+      par[idx] = bsrc[m] ? __ldg(bsrc[m] + CCOL * c + k) : 0.f;
+    }
+    const float* lsrc[6] = {a.ln1_g, a.ln1_b, a.ln2_g, a.ln2_b, a.ln3_g, a.ln3_b};
+#pragma unroll
+    for (int m2 = 0; m2 < 6; ++m2) par[8 * CCOL + m2 * H + tid] = lsrc[m2] ? __ldg(lsrc[m2] + tid) : 0.f;
+  }
+  const float* b_q = par, *b_k = par + 64, *b_v = par + 128, *b_o = par + 192, *b_q2 = par + 256, *b_o2 = par + 320;
+  const float* b_1 = par + 384, *b_2 = par + 448;
+  const float* ln1g = par + 512, *ln1b = ln1g + H, *ln2g = ln1b + H, *ln2b = ln2g + H, *ln3g = ln2b + H, *ln3b = ln3g + H;
+  const int lcol = 8 * warp + 2 * tq;                // the lane's column pair inside the CTA slice
+
+  // ---- KV-cache history of heads 2c, 2c+1 for the 8 rows -> shared memory (positions 0..t-1), and the
+  // table prow[row][j] = physical row | masked bit for j = 0..t.  The first launch of a step derives it
+  // from anc/tok (written by the launch right before it, hence after the wait) and publishes it.
+  auto load_history = [&](bool derive) {
+    for (int idx = tid; idx < CROWS * (t + 1); idx += CT) {
+      const int ii = idx / (t + 1), j = idx - ii * (t + 1);
+      const int rr = min(r0 + ii, a.R - 1);
+      uint32_t pv;
+      if (derive) {
+        const int pr = j < t ? a.anc[(size_t)rr * a.anc_ld + j] : rr;
+        pv = (uint32_t)pr | (a.tok[(size_t)pr * a.tok_ld + j] != 0 ? 0u : CMASKED);
+        if (a.prow_g != nullptr && c == 0 && r0 + ii < a.R) a.prow_g[(size_t)rr * Tmax + j] = (int32_t)pv;
+      } else {
+        pv = (uint32_t)a.prow_g[(size_t)rr * Tmax + j];
+      }
+      prow[ii * CTMAX + j] = pv;
+      if (j < t) {
+        const size_t goff = ((size_t)(pv & ~CMASKED) * Tmax + j) * H + CCOL * c;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {   // chunks 0..3: head 2c, 4..7: head 2c+1
+          const uint32_t soff = (uint32_t)((((ii * 2 + (q >> 2)) * Tmax + j) * 32 + (q & 3) * 8) * 2);
+          c_cpasync16(smem_u32(kh_s) + soff, a.kc + goff + q * 8);
+          c_cpasync16(smem_u32(vh_s) + soff, a.vc + goff + q * 8);
+        }
+      }
+    }
+  };
+  const bool early_hist = a.has_front && !a.first && a.prow_g != nullptr;
+  if (early_hist) load_history(false);
+
+  float2 bres = make_float2(0.f, 0.f);               // residual b of the cross-attention block (own columns)
+  if (a.has_back) bres = *reinterpret_cast<const float2*>(a.b_in + (size_t)erl * H + ecol);
+
+  cluster_sync_all();      // every CTA of the cluster is resident (barriers initialised) before any remote store
+  stamp();
+  pdl_wait();              // partials / tokens come from the kernel launched just before this one
+  stamp();
+
+  int consumed = 0;
+  if (a.has_back) {
+    // ---- B0: merge the cross-attention partials of heads 2c, 2c+1, broadcast ctx (bf16)
+    {
+      const int ns = a.nsplit;
+      const size_t pb = ((size_t)arl * NH + 2 * c + ahl) * ns;
+      float M = -INFINITY, Z = 0.f, c0 = 0.f, c1 = 0.f;
+      for (int jb = 0; jb < ns; jb += 4) {
+        float2 ml[4], pa[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = min(jb + u, ns - 1);
+          ml[u] = *reinterpret_cast<const float2*>(a.part_ml + (pb + j) * 2);
+          pa[u] = *reinterpret_cast<const float2*>(a.part_acc + (pb + j) * HD + 2 * acp);
+        }
+        float bm = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) bm = fmaxf(bm, ml[u].x);
+        const float Mn = fmaxf(M, bm);
+        const float rs = (M == -INFINITY) ? 0.f : fexp(M - Mn);
+        Z *= rs; c0 *= rs; c1 *= rs;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float e = (jb + u < ns && ml[u].x != -INFINITY) ? fexp(ml[u].x - Mn) : 0.f;
+          Z = fmaf(ml[u].y, e, Z);
+          c0 = fmaf(pa[u].x, e, c0);
+          c1 = fmaf(pa[u].y, e, c1);
+        }
+        M = Mn;
+      }
+      const float inv = Z > 0.f ? 1.f / Z : 0.f;
+      bcast_bf16(s_xa, s_bxa, ai, CCOL * c + 32 * ahl + 8 * (acp >> 2), c_pack(c0 * inv, c1 * inv));
+    }
+    wait_xa();
+    stamp();
+    // ---- B1: h2 = b + ctx.Wo2 + bo2 -> fp32 broadcast
+    {
+      const float2 d = mma_cols8(s_xa, wait_w(consumed), warp);
+      bcast_f32(s_xf, s_bxf, c, bres.x + d.x + b_o2[lcol], bres.y + d.y + b_o2[lcol + 1]);
+      __syncthreads();
+      ++consumed;
+      refill(consumed);
+    }
+    wait_xf();
+    stamp();
+    // ---- B2: c = LN3(h2)
+    ln_rows(xf, ln3g, ln3b, la, own, c, nullptr, r0, a.R);
+    __syncthreads();
+    stamp();
+    // ---- B3: gelu(c.W1 + b1) -> bf16 broadcast
+    {
+      const float2 d = mma_cols8(s_la, wait_w(consumed), warp);
+      bcast_bf16(s_xa, s_bxa, g, CCOL * c + 8 * warp, c_pack(gelu_erf(d.x + b_1[lcol]), gelu_erf(d.y + b_1[lcol + 1])));
+      __syncthreads();
+      ++consumed;
+      refill(consumed);
+    }
+    wait_xa();
+    stamp();
+    // ---- B4: h3 = c + f.W2 + b2 -> global (own columns) and fp32 broadcast
+    {
+      const float2 d = mma_cols8(s_xa, wait_w(consumed), warp);
+      const float2 cres = *reinterpret_cast<const float2*>(own + g * CCOL + lcol);
+      const float h0 = cres.x + d.x + b_2[lcol], h1 = cres.y + d.y + b_2[lcol + 1];
+      if (er < a.R) *reinterpret_cast<float2*>(a.h_out + (size_t)er * H + ecol) = make_float2(h0, h1);
+      if (a.has_front) bcast_f32(s_xf, s_bxf, c, h0, h1);
+      __syncthreads();
+      ++consumed;
+      refill(consumed);
+    }
+    if (!a.has_front) return;          // uniform over the cluster; nothing is in flight towards this CTA
+    wait_xf();
+  } else {
+    // first layer of the step: every CTA builds all 8 input rows locally (no exchange)
+    for (int idx = tid; idx < CROWS * (H / 4); idx += CT) {
+      const int ii = idx / (H / 4), k4 = idx - ii * (H / 4);
+      const int rr = min(r0 + ii, a.R - 1);
+      float4 x;
+      if (a.E != nullptr) {            // x = E[tok] * sqrt(H) + pe[t]   (Model.py:96, PositionalEmbedding.py:44-48)
+        const int tk = a.tok[(size_t)rr * a.tok_ld + t];
+        x = *reinterpret_cast<const float4*>(a.E + (size_t)tk * H + k4 * 4);
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.pe != nullptr) p = *reinterpret_cast<const float4*>(a.pe + (size_t)t * H + k4 * 4);
+        x = make_float4(fmaf(x.x, a.emb_scale, p.x), fmaf(x.y, a.emb_scale, p.y), fmaf(x.z, a.emb_scale, p.z),
+                        fmaf(x.w, a.emb_scale, p.w));
+        if (c == 0 && r0 + ii < a.R) *reinterpret_cast<float4*>(a.x_out + (size_t)rr * H + k4 * 4) = x;
+      } else {
+        x = *reinterpret_cast<const float4*>(a.h_in + (size_t)rr * H + k4 * 4);
+      }
+      *reinterpret_cast<float4*>(xf + ii * CFLD + k4 * 4) = x;
+    }
+    __syncthreads();
+  }
+  if (!early_hist) load_history(a.first || a.prow_g == nullptr);
+
+  stamp();
+  // ---- F0: a = LN1(h)
+  ln_rows(xf, ln1g, ln1b, la, own, c, nullptr, r0, a.R);
+  __syncthreads();
+  stamp();
+  // ---- F1: q | k | v of heads 2c, 2c+1 (warp w: the same 8 columns of all three)
+  {
+    const uint32_t wqkv[3] = {wait_w(consumed), wait_w(consumed + 1), wait_w(consumed + 2)};
+    float2 qkv[3];
+    mma_cols8x3(s_la, wqkv, warp, qkv);
+    const float2 dq = qkv[0], dk = qkv[1], dv = qkv[2];
+    *reinterpret_cast<float2*>(q_s + g * CCOL + lcol) = make_float2(dq.x + b_q[lcol], dq.y + b_q[lcol + 1]);
+    const uint32_t kp = c_pack(dk.x + b_k[lcol], dk.y + b_k[lcol + 1]);
+    const uint32_t vp = c_pack(dv.x + b_v[lcol], dv.y + b_v[lcol + 1]);
+    const int hl = warp >> 2, dcol = lcol & 31;
+    *reinterpret_cast<uint32_t*>(kh_s + (size_t)((g * 2 + hl) * Tmax + t) * 32 + dcol) = kp;
+    *reinterpret_cast<uint32_t*>(vh_s + (size_t)((g * 2 + hl) * Tmax + t) * 32 + dcol) = vp;
+    if (er < a.R) {
+      const size_t goff = ((size_t)er * Tmax + t) * H + ecol;
+      *reinterpret_cast<uint32_t*>(a.kc + goff) = kp;
+      *reinterpret_cast<uint32_t*>(a.vc + goff) = vp;
+    }
+    c_cpasync_wait_all();
+    __syncthreads();
+    consumed += 3;
+    refill(consumed);
+  }
+  stamp();
+  // ---- F2: self-attention of (row ai, head 2c + ahl) over positions 0..t (16 lanes), ctx -> bf16 broadcast
+  {
+    const float* qr = q_s + ai * CCOL + 32 * ahl;
+    float qv[32];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 x = *reinterpret_cast<const float4*>(qr + k * 4);
+      qv[4 * k] = x.x; qv[4 * k + 1] = x.y; qv[4 * k + 2] = x.z; qv[4 * k + 3] = x.w;
+    }
+    const bf16* kb = kh_s + (size_t)(ai * 2 + ahl) * Tmax * 32;
+    const bf16* vb = vh_s + (size_t)(ai * 2 + ahl) * Tmax * 32;
+    float* scr = sc + (ai * 2 + ahl) * CSCLD;
+    float sv[3];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int j = acp + 16 * u;
+      sv[u] = -INFINITY;
+      if (j <= t) {
+        const uint4* kr = reinterpret_cast<const uint4*>(kb + (size_t)j * 32);
+        float d = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 x = kr[q];
+          const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            d = fmaf(qv[q * 8 + 2 * e], __uint_as_float(w4[e] << 16), d);
+            d = fmaf(qv[q * 8 + 2 * e + 1], __uint_as_float(w4[e] & 0xffff0000u), d);
+          }
+        }
+        sv[u] = (prow[ai * CTMAX + j] & CMASKED) ? -INFINITY : d;
+      }
+      mx = fmaxf(mx, sv[u]);
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int j = acp + 16 * u;
+      const float p = (sv[u] == -INFINITY) ? 0.f : fexp(sv[u] - mx);
+      sum += p;
+      if (j <= t) scr[j] = p;
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    float c0 = 0.f, c1 = 0.f, d0 = 0.f, d1 = 0.f;
+    int j = 0;
+    for (; j + 1 <= t; j += 2) {
+      const float p0 = scr[j], p1 = scr[j + 1];
+      const uint32_t x0 = *reinterpret_cast<const uint32_t*>(vb + (size_t)j * 32 + 2 * acp);
+      const uint32_t x1 = *reinterpret_cast<const uint32_t*>(vb + (size_t)(j + 1) * 32 + 2 * acp);
+      c0 = fmaf(p0, __uint_as_float(x0 << 16), c0);
+      c1 = fmaf(p0, __uint_as_float(x0 & 0xffff0000u), c1);
+      d0 = fmaf(p1, __uint_as_float(x1 << 16), d0);
+      d1 = fmaf(p1, __uint_as_float(x1 & 0xffff0000u), d1);
+    }
+    if (j <= t) {
+      const float p0 = scr[j];
+      const uint32_t x0 = *reinterpret_cast<const uint32_t*>(vb + (size_t)j * 32 + 2 * acp);
+      c0 = fmaf(p0, __uint_as_float(x0 << 16), c0);
+      c1 = fmaf(p0, __uint_as_float(x0 & 0xffff0000u), c1);
+    }
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    bcast_bf16(s_xa, s_bxa, ai, CCOL * c + 32 * ahl + 8 * (acp >> 2), c_pack((c0 + d0) * inv, (c1 + d1) * inv));
+  }
+  wait_xa();
+  stamp();
+  // ---- F3: h1 = a + ctx.Wo + bo -> fp32 broadcast
+  {
+    const float2 d = mma_cols8(s_xa, wait_w(consumed), warp);
+    const float2 ares = *reinterpret_cast<const float2*>(own + g * CCOL + lcol);
+    bcast_f32(s_xf, s_bxf, c, ares.x + d.x + b_o[lcol], ares.y + d.y + b_o[lcol + 1]);
+    ++consumed;
+  }
+  wait_xf();
+  stamp();
+  // ---- F4: b = LN2(h1) (own columns -> global: the residual of the next launch's back half)
+  ln_rows(xf, ln2g, ln2b, la, own, c, a.b_out, r0, a.R);
+  __syncthreads();
+  stamp();
+  // ---- F5: q2 = b.Wq2 + bq2 (pre-scaled) -> global, consumed by the cross-attention
+  {
+    const float2 d = mma_cols8(s_la, wait_w(consumed), warp);
+    if (er < a.R)
+      *reinterpret_cast<float2*>(a.q2_out + (size_t)er * H + ecol) = make_float2(d.x + b_q2[lcol], d.y + b_q2[lcol + 1]);
+  }
+  stamp();
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" int case_layer_chain_max_tmax(void) { return CTMAX; }
+/* debugging aid (not part of the stable ABI): device buffer of >= 32 int64 that receives the clock64()
+ * stamps of CTA 0 at every stage boundary of the next case_layer_chain launches; NULL switches it off */
+extern "C" int case_debug_chain_timing(void* buf) { g_chain_dbg = (long long*)buf; return 0; }
+
+/* debugging aid: how many clusters of `cluster` CTAs of layer_chain_kernel with `smem` bytes can be
+ * co-resident on the device (cudaOccupancyMaxActiveClusters) */
+extern "C" int case_debug_chain_max_clusters(int smem, int cluster) {
+  cudaFuncSetAttribute(layer_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OFF_KV + 4 * CROWS * CTMAX * 64);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cluster * 64); cfg.blockDim = dim3(CT); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = -1;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, (const void*)layer_chain_kernel, &cfg);
+  return e == cudaSuccess ? n : -(int)e;
+}
+
+extern "C" int case_layer_chain(const case_layer_weights_t* wb, const case_layer_weights_t* wf, const float* h_in,
+                                const float* E, const float* pe, float emb_scale, float* x_out, const float* b_in,
+                                const float* part_ml, const float* part_acc, int nsplit, float* h_out, void* kcache,
+                                void* vcache, const int32_t* anc, int anc_ld, const int32_t* tok, int tok_ld,
+                                int32_t* prow, int t, int Tmax, float* b_out, float* q2_out, int R, int first,
+                                case_stream_t stream) {
+  CB_REQUIRE(wb || wf, "case_layer_chain: neither a back nor a front layer given");
+  CB_REQUIRE(R > 0 && Tmax >= 1 && Tmax <= CTMAX && t >= 0 && t < Tmax, "case_layer_chain: bad R / t / Tmax (Tmax <= 48)");
+  CB_REQUIRE(!wb || (wb->Wc && b_in && part_ml && part_acc && h_out && nsplit >= 1), "case_layer_chain: back half needs Wc, b_in, partials, h_out");
+  CB_REQUIRE(!wf || (wf->Wc && kcache && vcache && anc && tok && b_out && q2_out), "case_layer_chain: front half needs Wc, caches, anc, tok, b_out, q2_out");
+  CB_REQUIRE(wb || h_in || (E && x_out), "case_layer_chain: a front-only launch needs h_in or (E, x_out)");
+  ChainArgs a;
+  memset(&a, 0, sizeof(a));
+  a.R = R; a.t = t; a.Tmax = Tmax; a.nsplit = nsplit; a.has_back = wb != nullptr; a.has_front = wf != nullptr;
+  a.first = first;
+  a.dbg = g_chain_dbg;
+  if (wb) {
+    a.b_in = b_in; a.part_ml = part_ml; a.part_acc = part_acc; a.wb = reinterpret_cast<const char*>(wb->Wc);
+    a.bo2 = wb->bo2; a.b1 = wb->b1; a.b2 = wb->b2; a.ln3_g = wb->ln3_g; a.ln3_b = wb->ln3_b; a.h_out = h_out;
+  }
+  if (wf) {
+    a.h_in = h_in; a.E = E; a.pe = pe; a.emb_scale = emb_scale; a.x_out = x_out;
+    a.wf = reinterpret_cast<const char*>(wf->Wc);
+    a.bqkv = wf->bqkv; a.bo = wf->bo; a.bq2 = wf->bq2; a.ln1_g = wf->ln1_g; a.ln1_b = wf->ln1_b;
+    a.ln2_g = wf->ln2_g; a.ln2_b = wf->ln2_b;
+    a.kc = (bf16*)kcache; a.vc = (bf16*)vcache; a.anc = anc; a.anc_ld = anc_ld; a.tok = tok; a.tok_ld = tok_ld;
+    a.prow_g = prow; a.b_out = b_out; a.q2_out = q2_out;
+  }
+  const size_t smem = (size_t)OFF_KV + (wf ? (size_t)4 * CROWS * Tmax * 64 : 0);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(layer_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OFF_KV + 4 * CROWS * CTMAX * 64);
+    attr = true;
+  }
+  const int nclusters = (R + CROWS - 1) / CROWS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nclusters * CL); cfg.blockDim = dim3(CT); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 2 : 1;
+  void* pa[] = {(void*)&a};
+  g_launch_err = cudaLaunchKernelExC(&cfg, (const void*)layer_chain_kernel, pa);
+  return check_launch("case_layer_chain");
+}

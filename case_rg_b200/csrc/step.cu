@@ -9,6 +9,21 @@ namespace cb {
 
 static thread_local char g_err[512] = "ok";
 int g_use_pdl = 1;
+int g_use_chain = 1;
+int g_use_fork = 1;
+// side stream + events for the fork/join inside a step (created on first use, outside any capture: the
+// engines run one uncaptured warm-up step before they capture)
+static cudaStream_t g_aux = nullptr;
+static cudaEvent_t g_ev_fork[2] = {nullptr, nullptr}, g_ev_join[2] = {nullptr, nullptr};
+static bool aux_ready() {
+  if (g_aux) return true;
+  if (cudaStreamCreateWithFlags(&g_aux, cudaStreamNonBlocking) != cudaSuccess) { g_aux = nullptr; return false; }
+  for (int i = 0; i < 2; ++i) {
+    if (cudaEventCreateWithFlags(&g_ev_fork[i], cudaEventDisableTiming) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&g_ev_join[i], cudaEventDisableTiming) != cudaSuccess) return false;
+  }
+  return true;
+}
 cudaError_t g_launch_err = cudaSuccess;
 
 void set_error(const char* msg) {
@@ -35,6 +50,16 @@ extern "C" int case_abi_version(void) { return 1; }
 extern "C" int case_set_pdl(int on) {
   const int old = g_use_pdl;
   g_use_pdl = on ? 1 : 0;
+  return old;
+}
+extern "C" int case_set_chain(int on) {
+  const int old = g_use_chain;
+  g_use_chain = on ? 1 : 0;
+  return old;
+}
+extern "C" int case_set_fork(int on) {
+  const int old = g_use_fork;
+  g_use_fork = on ? 1 : 0;
   return old;
 }
 extern "C" const char* case_last_error(void) { return g_err; }
@@ -74,6 +99,81 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
   const int R = a->R, B = a->B, W = a->W, TL = a->Tmax + 1, dt = a->dtype;
   const int32_t* anc = a->anc[t & 1];
 
+  // attns[i]: query = [dec_out ; norm2(answer_rep)]   (Model.py:108), then the fused additive attention
+  auto stack_attention = [&](int i, const float* hsrc, float* qa, cudaStream_t s2) -> int {
+    case_rowlin_args_t q;
+    memset(&q, 0, sizeof(q));
+    q.seg[0] = seg(hsrc, H, H, 1);
+    q.seg[1] = seg(a->feat, H, H, W);
+    q.nseg = 2; q.K = 2 * H; q.Wt = a->Wqa_t[i]; q.bias = a->bqa[i]; q.N = H; q.out = qa; q.ldo = H;
+    q.R = R; q.dtype = dt;
+    TRY(case_row_linear(&q, s2));
+    return case_additive_attn(qa, a->U[i], a->Mv[i], a->va[i], a->mask[i], a->prior[i], a->tok, TL, t, B, W, a->S[i],
+                              H, a->nsplit_a[i], a->attn_un[i], a->stats[i], a->ctxp[i], a->fast_tanh, dt, s2);
+  };
+  auto gen0 = [&]() -> int {   // gen.0 on [dec_input ; norm1(dec_out) ; feat]   (Model.py:115)
+    case_rowlin_args_t g;
+    memset(&g, 0, sizeof(g));
+    g.seg[0] = seg(a->x_in, H, H, 1);
+    g.seg[1] = seg(a->hN, H, H, 1);
+    g.seg[2] = seg(a->feat, H, H, W);
+    g.nseg = 3; g.K = 3 * H; g.Wt = a->Wg_t; g.bias = a->bg; g.N = H; g.out = a->gfeat; g.ldo = H;
+    g.R = R; g.dtype = dt;
+    return case_row_linear(&g, st);
+  };
+  auto finalize = [&]() -> int {
+    return case_finalize_rows(a->h, a->lnN_g, a->lnN_b, a->stats[0], a->ctxp[0], a->nsplit_a[0], a->stats[1],
+                              a->ctxp[1], a->nsplit_a[1], a->Wm, a->bm, a->hN, a->ctx[0], a->ctx[1], a->gates, a->fac, R,
+                              st);
+  };
+#define CUTRY(x)                                                         \
+  do {                                                                   \
+    cudaError_t _ce = (x);                                               \
+    if (_ce != cudaSuccess) {                                            \
+      set_error(cudaGetErrorString(_ce));                                \
+      return (int)_ce;                                                   \
+    }                                                                    \
+  } while (0)
+  const bool chain = dt == CASE_BF16 && g_use_chain && a->layers[0].Wc != nullptr && a->Tmax <= case_layer_chain_max_tmax();
+  if (chain) {
+    // Cluster kernels: [embed + front 0] x [back 0 + front 1] x ... x [back 7], one launch between
+    // cross-attentions.  The two additive attentions only feed the mixture gates and the copy scatter,
+    // so they run on a side stream: attns[0] beside the whole second stack, attns[1] beside norm1 ->
+    // gen.0 -> vocabulary GEMM (fork/join by events, captured into the graph like any other edge).
+    const bool fork = g_use_fork && a->h0 != nullptr && a->qa1 != nullptr && aux_ready();
+    for (int L = 0; L <= 8; ++L) {
+      const case_layer_weights_t* wb = L > 0 ? &a->layers[L - 1] : nullptr;
+      const case_layer_weights_t* wf = L < 8 ? &a->layers[L] : nullptr;
+      float* hdst = (L == 4 && fork) ? a->h0 : a->h;
+      TRY(case_layer_chain(wb, wf, nullptr, a->E, a->pe, 16.0f /* sqrt(256) */, a->x_in, a->bbuf, a->part_ml,
+                           a->part_acc, L > 0 ? a->nsplit_x[(L - 1) / 4] : 1, hdst, wf ? a->kcache[L] : nullptr,
+                           wf ? a->vcache[L] : nullptr, anc, TL, a->tok, TL, a->prow, t, a->Tmax, a->bbuf, a->q2, R,
+                           L == 0, st));
+      if (L == 4 || L == 8) {
+        const int i = L / 4 - 1;
+        if (fork) {
+          CUTRY(cudaEventRecord(g_ev_fork[i], st));
+          CUTRY(cudaStreamWaitEvent(g_aux, g_ev_fork[i], 0));
+          TRY(stack_attention(i, hdst, i == 0 ? a->qa : a->qa1, g_aux));
+          CUTRY(cudaEventRecord(g_ev_join[i], g_aux));
+        } else {
+          TRY(stack_attention(i, hdst, a->qa, st));
+        }
+      }
+      if (L == 8) break;
+      const int i = L / 4;
+      TRY(case_cross_attn_partial_tc(a->q2, a->Kx[L], a->mask[i], B, W, a->S[i], a->nsplit_x[i], a->part_ml,
+                                     a->part_acc, st));
+    }
+    TRY(case_layernorm_rows(a->h, a->lnN_g, a->lnN_b, a->hN, R, st));
+    TRY(gen0());
+    TRY(case_vocab_gemm(a->gfeat, a->Wv, nullptr, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, a->vocab_ws, st));
+    if (fork) {
+      CUTRY(cudaStreamWaitEvent(st, g_ev_join[0], 0));
+      CUTRY(cudaStreamWaitEvent(st, g_ev_join[1], 0));
+    }
+    TRY(finalize());
+  } else {
   TRY(case_embed_rows(a->E, a->pe, a->tok, TL, t, 16.0f /* sqrt(256) */, a->x_in, R, st));
   const float* hin = a->x_in;
   for (int i = 0; i < 2; ++i) {
@@ -92,30 +192,12 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       TRY(case_layer_back(a->bbuf, a->part_ml, a->part_acc, nparts, &a->layers[L], a->h, R, dt, st));
       hin = a->h;
     }
-    // attns[i]: query = [dec_out ; norm2(answer_rep)]   (Model.py:108)
-    case_rowlin_args_t q;
-    memset(&q, 0, sizeof(q));
-    q.seg[0] = seg(a->h, H, H, 1);
-    q.seg[1] = seg(a->feat, H, H, W);
-    q.nseg = 2; q.K = 2 * H; q.Wt = a->Wqa_t[i]; q.bias = a->bqa[i]; q.N = H; q.out = a->qa; q.ldo = H;
-    q.R = R; q.dtype = dt;
-    TRY(case_row_linear(&q, st));
-    TRY(case_additive_attn(a->qa, a->U[i], a->Mv[i], a->va[i], a->mask[i], a->prior[i], a->tok, TL, t, B, W, a->S[i],
-                           H, a->nsplit_a[i], a->attn_un[i], a->stats[i], a->ctxp[i], a->fast_tanh, dt, st));
+    TRY(stack_attention(i, a->h, a->qa, st));
   }
-  TRY(case_finalize_rows(a->h, a->lnN_g, a->lnN_b, a->stats[0], a->ctxp[0], a->nsplit_a[0], a->stats[1], a->ctxp[1],
-                         a->nsplit_a[1], a->Wm, a->bm, a->hN, a->ctx[0], a->ctx[1], a->gates, a->fac, R, st));
-  {  // gen.0 on [dec_input ; norm1(dec_out) ; feat]   (Model.py:115)
-    case_rowlin_args_t g;
-    memset(&g, 0, sizeof(g));
-    g.seg[0] = seg(a->x_in, H, H, 1);
-    g.seg[1] = seg(a->hN, H, H, 1);
-    g.seg[2] = seg(a->feat, H, H, W);
-    g.nseg = 3; g.K = 3 * H; g.Wt = a->Wg_t; g.bias = a->bg; g.N = H; g.out = a->gfeat; g.ldo = H;
-    g.R = R; g.dtype = dt;
-    TRY(case_row_linear(&g, st));
-  }
+  TRY(finalize());
+  TRY(gen0());
   TRY(case_vocab_gemm(a->gfeat, a->Wv, nullptr, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, a->vocab_ws, st));
+  }
   TRY(case_softmax_mix(a->logits, a->ldv, a->gates, a->dist, a->ldv, R, a->V, 0, st));
   for (int i = 0; i < 2; ++i) {
     TRY(case_copy_scatter(a->map, a->map_ld, a->map_off[i], a->prior[i], a->attn_un[i],

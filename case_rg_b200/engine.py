@@ -68,6 +68,19 @@ def unpack_tiled(wp: torch.Tensor, N: int, K: int) -> torch.Tensor:
     return wp.float().permute(0, 2, 1).reshape(N, K)
 
 
+def pack_cluster(mats) -> torch.Tensor:
+    """Eight nn.Linear weights [256 out][256 in] (Wq, Wk, Wv, Wo, Wq2, Wo2, W1, W2) -> the layout of
+    case_layer_chain: bf16 [4 ranks][8 matrices][64 n][256 k], rank c = output rows 64c..64c+63, the
+    16-byte chunk kc of row n stored at chunk position kc ^ (n & 7) (csrc/layer_cluster.cu)."""
+    w = torch.stack([m.to(torch.bfloat16) for m in mats])              # [m][256 n][256 k]
+    if tuple(w.shape) != (8, 256, 256):
+        raise ValueError(f'pack_cluster needs eight 256x256 matrices, got {tuple(w.shape)}')
+    w = w.view(8, 4, 64, 32, 8)                                          # [m][rank][n][kc][8]
+    n = torch.arange(64, device=w.device)
+    src = torch.arange(32, device=w.device)[None, :] ^ (n & 7)[:, None]  # stored position p holds chunk p ^ (n & 7)
+    return w[:, :, n[:, None], src].permute(1, 0, 2, 3, 4).contiguous()
+
+
 def pack_vocab_tc(w: torch.Tensor) -> torch.Tensor:
     """[V, 256] output-projection weight -> bf16 tiles of 128 rows in the UMMA K-major no-swizzle
     canonical layout the tcgen05 kernel bulk-copies straight into shared memory (case_b200.h)."""
@@ -153,6 +166,10 @@ class CaseWeights:
                          ln1_g=vec(g(p + 'norm1.weight')), ln1_b=vec(g(p + 'norm1.bias')),
                          ln2_g=vec(g(p + 'norm2.weight')), ln2_b=vec(g(p + 'norm2.bias')),
                          ln3_g=vec(g(p + 'norm3.weight')), ln3_b=vec(g(p + 'norm3.bias')))
+                if self.cdtype == L.BF16:
+                    t['Wc'] = pack_cluster([Wi[:H], Wi[H:2 * H], Wi[2 * H:], g(p + 'self_attn.out_proj.weight'),
+                                            Wx[:H] * scale, g(p + 'multihead_attn.out_proj.weight'),
+                                            g(p + 'linear1.weight'), g(p + 'linear2.weight')])
                 self.keep.append(t)
                 lw = self.layers[i * 4 + l]
                 for k, v in t.items():
@@ -304,6 +321,8 @@ class CaseDecodeEngine(_EngineBase):
         self.logits, self.dist = z(R, self.ldv), z(R, self.ldv)
         self.top_vals = z(R, W)
         self.top_idx = torch.zeros(R, W, dtype=torch.int32, device=dev)
+        self.prow = torch.zeros(R, Tmax, dtype=torch.int32, device=dev)
+        self.h0, self.qa1 = z(R, H), z(R, H)
         self._graphs = {}
         self._step_fn = L.load().case_decode_step
         self._step_name = 'case_decode_step'
@@ -338,7 +357,7 @@ class CaseDecodeEngine(_EngineBase):
         a.map, a.map_ld = self.map.data_ptr(), self.map.size(1)
         self.state.bind(a)
         for n in ('x_in', 'h', 'bbuf', 'q2', 'part_ml', 'part_acc', 'qa', 'hN', 'gates', 'fac', 'gfeat', 'logits',
-                  'dist', 'top_vals', 'top_idx'):
+                  'dist', 'top_vals', 'top_idx', 'prow', 'h0', 'qa1'):
             setattr(a, n, getattr(self, n).data_ptr())
 
     # ------------------------------------------------------------------ per batch
@@ -406,8 +425,12 @@ class CaseDecodeEngine(_EngineBase):
         return self.dist[:, :self.V]
 
     def kernel_launches_per_step(self) -> int:
+        if self.w.cdtype == L.BF16 and self.Tmax <= L.load().case_layer_chain_max_tmax():
+            # 9 x layer_chain + 8 x cross + 2 x (row_linear, additive) + norm1 + gen.0 + vocab + finalize + softmax
+            # + 2 scatter + topk + select (+1: the activation re-pack inside the vocabulary GEMM call)
+            return 9 + 8 + 4 + 1 + 1 + 1 + 1 + 1 + 2 + 1 + 1
         # embed + 8 x (front, cross, back) + 2 x (row_linear, additive) + finalize + gen.0 + vocab + softmax
-        # + 2 scatter + topk + select (+1 memset node)
+        # + 2 scatter + topk + select (+1: the activation re-pack inside the vocabulary GEMM call)
         return 1 + 24 + 4 + 1 + 1 + 1 + 1 + 2 + 1 + 1
 
 

@@ -54,6 +54,12 @@ const char* case_last_error(void);
 size_t case_struct_size(int which);
 /* Programmatic dependent launch for every kernel of a step (default on); returns the old setting. */
 int case_set_pdl(int on);
+/* Cluster layer kernels (case_layer_chain) in case_decode_step for bf16 storage (default on; 0 = the
+ * row-block kernels case_layer_front / case_layer_back); returns the old setting. */
+int case_set_chain(int on);
+/* Fork/join of the additive attentions onto a library-owned side stream inside case_decode_step
+ * (cluster path only; default on); returns the old setting. */
+int case_set_fork(int on);
 
 /* ---------------------------------------------------------------- row-wise building blocks */
 
@@ -112,6 +118,7 @@ typedef struct {
   const float* ln1_g; const float* ln1_b;
   const float* ln2_g; const float* ln2_b;
   const float* ln3_g; const float* ln3_b;
+  const void* Wc;     /* bf16 only, may be NULL: the eight matrices "cluster-packed" for case_layer_chain */
 } case_layer_weights_t;
 
 /* First half of a layer for the newest position t of every row (TransformerDecoder.py:76-80):
@@ -151,6 +158,27 @@ int case_pack_kv_tiles(const void* kv, int src_dtype, int ldkv, int B, int S, in
  * c = LN3(h2); h_out = c + W2.gelu(W1.c). */
 int case_layer_back(const float* b_in, const float* part_ml, const float* part_acc, int nsplit,
                     const case_layer_weights_t* w, float* h_out, int R, int dtype, case_stream_t stream);
+
+/* Cluster form of the two calls above for bf16 storage: ONE launch runs the second half of layer Lb
+ * (wb, may be NULL) followed by the first half of layer Lf (wf, may be NULL) for all rows, i.e. all row
+ * work between two cross-attention launches (TransformerDecoder.py:82-89 of layer Lb, then :76-80 of
+ * layer Lf).  A thread-block cluster of 4 CTAs owns 8 rows; CTA c owns columns [64c, 64c+64) of every
+ * linear (= heads 2c, 2c+1) and ingests only its slice of the weights and of the KV history; results
+ * are exchanged through distributed shared memory.  Needs w->Wc: bf16 [4 ranks][8 matrices Wq,Wk,Wv,
+ * Wo,Wq2,Wo2,W1,W2][64 n][256 k] with the 16-byte chunk kc of row n stored at chunk position
+ * kc ^ (n & 7) (Wq/Wq2 pre-scaled like Wqkv_t/Wq2_t).
+ * Input rows: wb != NULL -> h_out of the back half (also written to global memory); else E != NULL ->
+ * the embedding x = E[tok[r][t]] * emb_scale + pe[t] (case_embed_rows), also written to x_out; else h_in.
+ * prow (int32 [R][Tmax], may be NULL): per-step table "physical row | masked bit" of every history
+ * position; the launch with first = 1 (the first of a step: anc/tok were written by the launch right
+ * before it) derives it from anc/tok and publishes it, later launches of the step read it early.
+ * Tmax <= case_layer_chain_max_tmax() (the KV history of the 8 rows lives in shared memory). */
+int case_layer_chain(const case_layer_weights_t* wb, const case_layer_weights_t* wf, const float* h_in,
+                     const float* E, const float* pe, float emb_scale, float* x_out, const float* b_in,
+                     const float* part_ml, const float* part_acc, int nsplit, float* h_out, void* kcache,
+                     void* vcache, const int32_t* anc, int anc_ld, const int32_t* tok, int tok_ld, int32_t* prow,
+                     int t, int Tmax, float* b_out, float* q2_out, int R, int first, case_stream_t stream);
+int case_layer_chain_max_tmax(void);
 
 /* ---------------------------------------------------------------- additive ("bilinear") attention */
 
@@ -276,6 +304,9 @@ typedef struct {
   float* qa; float* attn_un[2]; float* stats[2]; float* ctxp[2]; float* hN; float* ctx[2];
   float* gates; float* fac; float* gfeat; float* logits; float* dist; float* top_vals; int32_t* top_idx;
   void* vocab_ws;                       /* case_vocab_tc_workspace_bytes(R) bytes when vocab_impl == 1 */
+  int32_t* prow;                        /* [R][Tmax] scratch of case_layer_chain (may be NULL) */
+  float* h0; float* qa1;                /* [R][H] each (may be NULL): stack-0 output and second attention query,
+                                           private copies that let the additive attentions run on a side stream */
 } case_step_args_t;
 
 /* Enqueue one full decode step t (embedding .. select) for all R rows: the body of the eval loop

@@ -137,3 +137,117 @@ def test_additive_attention_vs_torch(W, S, DV, nsplit, use_prior, dtype):
     assert rel_err(ctx[live], want_ctx[live]) < 2e-4
     pr = prior.repeat_interleave(W, 0) if use_prior else torch.ones_like(a)
     assert rel_err((Q / Z.clamp_min(1e-30))[live], (pr * a).sum(1)[live]) < 2e-4
+
+
+# --------------------------------------------------------------------------- cluster layer kernels
+def _chain_case(B, W, T, V=3000, seeds=(51, 52)):
+    from case_rg_b200 import synthetic as syn
+    sd = syn.make_case_decoder_state(seeds[0], V, 256, peaked=0.3, boost={syn.EOS: 6.0}, gen_gate_bias=2.0)
+    inp = syn.make_case_inputs(seeds[1], B, 20, 3, 40, V, 256).to('cuda')
+    data = dict(mem_q=inp.mem_q, mem_p=inp.mem_p, query=inp.query, passage=inp.passage, prior_q=inp.prior_q,
+                prior_p=inp.prior_p, answer_rep=inp.answer_rep, source_map=inp.source_map)
+    return sd, data
+
+
+def _teacher_forced_states(model, data, prefix):
+    """Drive an engine on a fixed token prefix (W = 1): per step (h, q2, logits, dist)."""
+    B, n = prefix.shape
+    S0 = data['mem_q'].reshape(B, -1, 256).size(1)
+    S1 = data['mem_p'].reshape(B, -1, 256).size(1)
+    eng = model.engine_for(B, 1, S0, S1, max(n, 2))
+    eng.prefill(data['mem_q'], data['mem_p'], data['query'].ne(0), data['passage'].ne(0), data['prior_q'],
+                data['prior_p'], data['answer_rep'], data['source_map'])
+    eng.state.reset()
+    outs = []
+    for t in range(n):
+        eng.state.tok[:, t] = prefix[:, t].to('cuda', torch.int32)
+        dist = eng.step_distribution(t)
+        torch.cuda.synchronize()
+        outs.append(dict(h=eng.h.clone(), q2=eng.q2.clone(), logits=eng.logits[:, :eng.V].clone(), dist=dist.clone()))
+    return outs
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('B,T', [(3, 6), (20, 12), (64, 5), (1, 48)])
+def test_layer_chain_vs_fp32_and_row_block_kernels(B, T):
+    """case_layer_chain (4-CTA clusters, DSMEM exchange) computes what case_layer_front/back compute from
+    the same bf16 operands; only summation order differs.  On a teacher-forced prefix (with PAD tokens,
+    so masked history keys occur) every step of both bf16 paths is compared with the fp32 engine: the
+    cluster path must be as close to fp32 as the row-block path is (bf16 noise level)."""
+    from case_rg_b200 import _lib as L
+    from case_rg_b200.generations import FastCaSE
+    sd, data = _chain_case(B, 1, T)
+    g = torch.Generator().manual_seed(77)
+    prefix = torch.randint(1000, 3000, (B, T), generator=g)
+    prefix[:, 0] = 1
+    if T > 3:
+        prefix[::2, 2] = 0           # PAD inside the history of every other row
+    lib = L.load()
+    ref = _teacher_forced_states(FastCaSE(sd, device='cuda', dtype='fp32', use_graph=False), data, prefix)
+    model = FastCaSE(sd, device='cuda', dtype='bf16', use_graph=False)
+    outs = {}
+    for chain in (0, 1):
+        old = lib.case_set_chain(chain)
+        try:
+            outs[chain] = _teacher_forced_states(model, data, prefix)
+        finally:
+            lib.case_set_chain(old)
+    worst = {}
+    for t in range(T):
+        for k in ('h', 'q2', 'logits', 'dist'):
+            assert torch.isfinite(outs[1][t][k]).all(), (t, k)
+            e0, e1 = rel_err(outs[0][t][k], ref[t][k]), rel_err(outs[1][t][k], ref[t][k])
+            worst[k] = max(worst.get(k, 0.0), e1)
+            assert e1 < (8e-2 if k == 'dist' else 3e-2), (t, k, e0, e1)
+            assert e1 < 2.0 * e0 + 3e-3, (t, k, e0, e1)
+    print(worst)
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize('B,W', [(5, 4), (9, 8), (64, 4), (2, 3)])
+def test_layer_chain_first_step_beam_rows(B, W):
+    """Step 0 of a beam search (no token feedback yet): all W slots of a query, partial last cluster."""
+    from case_rg_b200 import _lib as L
+    from case_rg_b200.generations import FastCaSE
+    sd, data = _chain_case(B, W, 1)
+    lib = L.load()
+    m32 = FastCaSE(sd, device='cuda', dtype='fp32', use_graph=False)
+    m32.fast_search(data, 1, W, L.MODE_BEAM)
+    ref = dict(h=m32.last_engine.h.clone(), logits=m32.last_engine.logits[:, :3000].clone())
+    model = FastCaSE(sd, device='cuda', dtype='bf16', use_graph=False)
+    err = {}
+    for chain in (0, 1):
+        old = lib.case_set_chain(chain)
+        try:
+            model.fast_search(data, 1, W, L.MODE_BEAM)
+            torch.cuda.synchronize()
+            eng = model.last_engine
+            err[chain] = dict(h=rel_err(eng.h, ref['h']), logits=rel_err(eng.logits[:, :3000], ref['logits']))
+        finally:
+            lib.case_set_chain(old)
+    for k in ('h', 'logits'):
+        assert err[1][k] < 3e-2 and err[1][k] < 2.0 * err[0][k] + 3e-3, err
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('B,W,T', [(64, 4, 40), (7, 1, 48), (6, 2, 50)])
+def test_layer_chain_full_search_agrees(B, W, T):
+    """Whole searches (CUDA graph, T up to the shared-memory history limit of 48; T = 50 exercises the
+    automatic fallback to the row-block kernels): the answers of the two bf16 paths agree on nearly all
+    queries (beam re-ranking of bf16 near-ties may differ)."""
+    from case_rg_b200 import _lib as L
+    from case_rg_b200.generations import FastCaSE
+    sd, data = _chain_case(B, W, T, seeds=(53, 54))
+    mode = L.MODE_BEAM if W > 1 else L.MODE_PROTO_GREEDY
+    lib = L.load()
+    toks = {}
+    for chain in (0, 1):
+        old = lib.case_set_chain(chain)
+        try:
+            model = FastCaSE(sd, device='cuda', dtype='bf16', use_graph=True)
+            toks[chain] = model.fast_search(data, T, W, mode).cpu()
+        finally:
+            lib.case_set_chain(old)
+    n = min(toks[0].size(1), toks[1].size(1))
+    same = sum(int(torch.equal(toks[0][i, :n], toks[1][i, :n])) for i in range(B))
+    assert same >= 0.85 * B, (same, B)
