@@ -40,6 +40,9 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-pdl', action='store_true', help='disable programmatic dependent launch (A/B)')
+    ap.add_argument('--no-chain', action='store_true', help='row-block layer kernels instead of the cluster kernels (A/B)')
+    ap.add_argument('--no-fork', action='store_true', help='no side stream for the additive attentions (A/B)')
+    ap.add_argument('--streams', type=int, default=1, help='batch slices decoded concurrently on their own streams')
     ap.add_argument('--batch', type=int, default=WORKLOAD['B'])
     ap.add_argument('--beam', type=int, default=WORKLOAD['W'])
     ap.add_argument('--profile', type=int, default=0,
@@ -186,11 +189,17 @@ def main():
     B, W, T, V = args.batch, args.beam, w['T'], w['V']
     if args.no_pdl:
         L.load().case_set_pdl(0)
+    if args.no_chain:
+        L.load().case_set_chain(0)
+    if args.no_fork:
+        L.load().case_set_fork(0)
+    if args.profile:
+        args.streams = 1
 
     sd = syn.make_case_decoder_state(WSEED, V, w['H'])
     vocab_impl = args.vocab_impl if args.vocab_impl is not None else (1 if args.dtype == 'bf16' else 0)
     model = FG.FastCaSE(sd, device=dev, dtype=args.dtype, max_dec_len=T, beam_width=W, vocab_impl=vocab_impl,
-                        use_graph=not args.no_graph)
+                        use_graph=not args.no_graph, streams=args.streams)
     host = syn.make_case_inputs(ISEED + rank, B, w['Lq'], w['NP'], w['Lp'], V, w['H'], id_base=rank * B).pin()
     d = host.to(dev)
     data_dev = dict(mem_q=d.mem_q, mem_p=d.mem_p, query=d.query, passage=d.passage, prior_q=d.prior_q,
@@ -256,7 +265,7 @@ def main():
         step_e2e()
     # answer tokens of one step: best-sequence lengths (EOS kept), per Generations.py:188
     eng = model.last_engine
-    tokens_per_step = int(eng.state.best_len.sum().item())
+    tokens_per_step = eng.answer_tokens()
 
     clocks = ClockSampler(local)
     if rank == 0:
@@ -300,7 +309,8 @@ def main():
     line = dict(metric='answer_tokens_per_s', value=value, unit='tokens/s', n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype=args.dtype if args.dtype == 'bf16' else 'f32', data='synthetic',
-                config=config_dict(args, dict(cuda_graph=not args.no_graph, pdl=not args.no_pdl, vocab_gemm='tcgen05' if vocab_impl == 1 else 'simt')),
+                config=config_dict(args, dict(cuda_graph=not args.no_graph, pdl=not args.no_pdl, vocab_gemm='tcgen05' if vocab_impl == 1 else 'simt',
+                                              layer_kernels='row-block' if args.no_chain else 'cluster', streams=args.streams)),
                 ms_per_decode_step=decode_ms / T, prefill_ms=prefill_ms, decode_ms=decode_ms,
                 answer_tokens_per_step=tokens_per_step,
                 e2e=dict(value=e2e_value, unit='tokens/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
@@ -323,6 +333,7 @@ def roofline(model, eng, args, torch):
     except Exception:
         pass
     peak, which = (peaks['hbm_gbs'], 'measured') if 'hbm_gbs' in peaks else (6650.0, 'fallback')
+    eng = eng.subs[0] if hasattr(eng, 'subs') else eng    # the launch shape of one stream's slice
     B, W, S1 = eng.B, eng.W, eng.S[1]
     esz = 2 if eng.w.cdtype == L.BF16 else 4
     alg = B * 2 * S1 * L.H * esz
@@ -350,7 +361,7 @@ def roofline(model, eng, args, torch):
     ach = alg / (us * 1e-6) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed
     # `ncu --set full` capture (profiles/r1_top_kernels_ncu_summary.txt): 168.3 MB read + 5.4 MB written
-    traffic = 173.7e6 if (eng.w.cdtype == L.BF16 and (B, W, S1) == (64, 4, 2560)) else None
+    traffic = 173.7e6 * B / 64 if (eng.w.cdtype == L.BF16 and (W, S1) == (4, 2560)) else None
     return dict(kernel='cross_attn_mma_kernel (passage memory)' if eng.w.cdtype == L.BF16 else 'cross_attn_partial_kernel (passage memory)', bound='hbm', achieved=ach, peak=peak, unit='GB/s',
                 frac=ach / peak, traffic=traffic, peak_source=which, algorithmic_bytes_per_launch=alg,
                 us_per_launch=us, launches_per_decode_step=4)

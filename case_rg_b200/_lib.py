@@ -39,6 +39,15 @@ class SelectArgs(C.Structure):
                                   'parent', 'ended', 'best_key', 'best_len', 'out_tokens', 'n_live')]
 
 
+class TailArgs(C.Structure):
+    _fields_ = [(n, i32) for n in ('R', 'V', 'W', 'K', 'ldl', 'ldd', 'mask_col0', 'nmem', 'do_finalize', 'fac_ld',
+                                   'map_ld')] + \
+               [('ns', i32 * 2), ('fac_off', i32 * 2), ('map_off', i32 * 2), ('S', i32 * 2),
+                ('logits', vp), ('hN', vp), ('stats', vp * 2), ('ctxp', vp * 2), ('Wm', vp), ('bm', vp),
+                ('ctx', vp * 2), ('gates', vp), ('fac', vp), ('map', vp), ('prior', vp * 2), ('attn_un', vp * 2),
+                ('top_vals', vp), ('top_idx', vp), ('dist', vp)]
+
+
 class StepArgs(C.Structure):
     _fields_ = [(n, i32) for n in ('B', 'W', 'R', 'V', 'ldv', 'Tmax', 'dtype', 'fast_tanh', 'vocab_impl', 'mode')] + \
                [('S', i32 * 2), ('nsplit_x', i32 * 2), ('nsplit_a', i32 * 2), ('map_off', i32 * 2)] + \
@@ -89,6 +98,8 @@ _PROTOS = {
     'case_softmax_mix': [vp, i32, vp, vp, i32, i32, i32, i32, vp],
     'case_copy_scatter': [vp, i32, i32, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp],
     'case_topk_rows': [vp, i32, i32, i32, i32, vp, vp, vp],
+    'case_row_tail': [C.POINTER(TailArgs), vp],
+    'case_row_tail_max_vocab': [],
     'case_beam_select': [C.POINTER(SelectArgs), vp],
     'case_gru_cell': [vp, vp, vp, vp, vp, i32, vp],
     'case_attn_merge': [vp, vp, i32, i32, vp, vp, i32, i32, vp],
@@ -96,12 +107,13 @@ _PROTOS = {
     'case_set_pdl': [i32],
     'case_set_chain': [i32],
     'case_set_fork': [i32],
+    'case_set_fused_tail': [i32],
     'case_decode_step': [C.POINTER(StepArgs), i32, vp],
     'gttp_decode_step': [C.POINTER(GttpStepArgs), i32, vp],
 }
 _SIZE_FNS = ['case_vocab_tc_workspace_bytes', 'case_vocab_tc_packed_weight_bytes']
 EXPORTS = sorted(list(_PROTOS) + ['case_abi_version', 'case_last_error', 'case_struct_size'] + _SIZE_FNS)
-_STRUCTS = [Seg, RowLinArgs, LayerWeights, SelectArgs, StepArgs, GttpStepArgs]
+_STRUCTS = [Seg, RowLinArgs, LayerWeights, SelectArgs, StepArgs, GttpStepArgs, TailArgs]
 
 _lib = None
 

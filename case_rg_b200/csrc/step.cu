@@ -11,6 +11,7 @@ static thread_local char g_err[512] = "ok";
 int g_use_pdl = 1;
 int g_use_chain = 1;
 int g_use_fork = 1;
+int g_use_tail = 1;
 // side stream + events for the fork/join inside a step (created on first use, outside any capture: the
 // engines run one uncaptured warm-up step before they capture)
 static cudaStream_t g_aux = nullptr;
@@ -55,6 +56,11 @@ extern "C" int case_set_pdl(int on) {
 extern "C" int case_set_chain(int on) {
   const int old = g_use_chain;
   g_use_chain = on ? 1 : 0;
+  return old;
+}
+extern "C" int case_set_fused_tail(int on) {
+  const int old = g_use_tail;
+  g_use_tail = on ? 1 : 0;
   return old;
 }
 extern "C" int case_set_fork(int on) {
@@ -172,7 +178,6 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       CUTRY(cudaStreamWaitEvent(st, g_ev_join[0], 0));
       CUTRY(cudaStreamWaitEvent(st, g_ev_join[1], 0));
     }
-    TRY(finalize());
   } else {
   TRY(case_embed_rows(a->E, a->pe, a->tok, TL, t, 16.0f /* sqrt(256) */, a->x_in, R, st));
   const float* hin = a->x_in;
@@ -194,18 +199,38 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
     }
     TRY(stack_attention(i, a->h, a->qa, st));
   }
-  TRY(finalize());
+  TRY(case_layernorm_rows(a->h, a->lnN_g, a->lnN_b, a->hN, R, st));
   TRY(gen0());
   TRY(case_vocab_gemm(a->gfeat, a->Wv, nullptr, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, a->vocab_ws, st));
   }
-  TRY(case_softmax_mix(a->logits, a->ldv, a->gates, a->dist, a->ldv, R, a->V, 0, st));
-  for (int i = 0; i < 2; ++i) {
-    TRY(case_copy_scatter(a->map, a->map_ld, a->map_off[i], a->prior[i], a->attn_un[i],
-                          a->fac + (size_t)i * CASE_MAX_SPLIT, 2 * CASE_MAX_SPLIT, a->dist, a->ldv, B, W, a->S[i],
-                          a->V, st));
+  if (g_use_tail && a->V <= case_row_tail_max_vocab()) {
+    // one launch: attention merge + gates, softmax x gate, both copy scatters, top-k; the [R, V]
+    // distribution is written only for the `generate` face
+    case_tail_args_t ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.R = R; ta.V = a->V; ta.W = W; ta.K = W; ta.ldl = a->ldv; ta.ldd = a->ldv; ta.mask_col0 = 0; ta.nmem = 2;
+    ta.do_finalize = 1; ta.fac_ld = 2 * CASE_MAX_SPLIT; ta.map_ld = a->map_ld;
+    ta.logits = a->logits; ta.hN = a->hN; ta.Wm = a->Wm; ta.bm = a->bm; ta.gates = a->gates; ta.fac = a->fac;
+    ta.map = a->map;
+    for (int i = 0; i < 2; ++i) {
+      ta.ns[i] = a->nsplit_a[i]; ta.fac_off[i] = i * CASE_MAX_SPLIT; ta.map_off[i] = a->map_off[i]; ta.S[i] = a->S[i];
+      ta.stats[i] = a->stats[i]; ta.ctxp[i] = a->ctxp[i]; ta.ctx[i] = a->ctx[i]; ta.prior[i] = a->prior[i];
+      ta.attn_un[i] = a->attn_un[i];
+    }
+    if (a->materialize_only) { ta.dist = a->dist; } else { ta.top_vals = a->top_vals; ta.top_idx = a->top_idx; }
+    TRY(case_row_tail(&ta, st));
+    if (a->materialize_only) return 0;
+  } else {
+    TRY(finalize());
+    TRY(case_softmax_mix(a->logits, a->ldv, a->gates, a->dist, a->ldv, R, a->V, 0, st));
+    for (int i = 0; i < 2; ++i) {
+      TRY(case_copy_scatter(a->map, a->map_ld, a->map_off[i], a->prior[i], a->attn_un[i],
+                            a->fac + (size_t)i * CASE_MAX_SPLIT, 2 * CASE_MAX_SPLIT, a->dist, a->ldv, B, W, a->S[i],
+                            a->V, st));
+    }
+    if (a->materialize_only) return 0;
+    TRY(case_topk_rows(a->dist, a->ldv, R, a->V, W, a->top_vals, a->top_idx, st));
   }
-  if (a->materialize_only) return 0;
-  TRY(case_topk_rows(a->dist, a->ldv, R, a->V, W, a->top_vals, a->top_idx, st));
   return select_step(a->mode, B, W, t, a->max_len, a->Tmax, a->BOS, a->EOS, a->UNK, a->PAD, a->top_vals, a->top_idx,
                      a->live, a->cum, a->length, a->tok, a->anc, a->parent, a->ended, a->best_key, a->best_len,
                      a->out_tokens, a->n_live, st);
@@ -272,11 +297,23 @@ extern "C" int gttp_decode_step(const gttp_step_args_t* a, int t, case_stream_t 
   }
   TRY(case_vocab_gemm(a->feat, a->Wv, a->bv, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, a->vocab_ws, st));
   TRY(case_gttp_gates(a->feat, a->wc, a->bc, a->gates, a->fac, CASE_MAX_SPLIT, ns[1], R, st));
-  TRY(case_softmax_mix(a->logits, a->ldv, a->gates, a->dist, a->ldv, R, a->V, 1, st));
-  TRY(case_copy_scatter(a->map, a->map_ld, 0, nullptr, a->attn_un[1], a->fac, CASE_MAX_SPLIT, a->dist, a->ldv, B, W,
-                        a->Lb, a->V, st));
-  if (a->materialize_only) return 0;
-  TRY(case_topk_rows(a->dist, a->ldv, R, a->V, W, a->top_vals, a->top_idx, st));
+  if (g_use_tail && a->V <= case_row_tail_max_vocab()) {
+    case_tail_args_t ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.R = R; ta.V = a->V; ta.W = W; ta.K = W; ta.ldl = a->ldv; ta.ldd = a->ldv; ta.mask_col0 = 1; ta.nmem = 1;
+    ta.do_finalize = 0; ta.fac_ld = CASE_MAX_SPLIT; ta.map_ld = a->map_ld;
+    ta.logits = a->logits; ta.gates = a->gates; ta.fac = a->fac; ta.map = a->map;
+    ta.S[0] = a->Lb; ta.attn_un[0] = a->attn_un[1];
+    if (a->materialize_only) { ta.dist = a->dist; } else { ta.top_vals = a->top_vals; ta.top_idx = a->top_idx; }
+    TRY(case_row_tail(&ta, st));
+    if (a->materialize_only) return 0;
+  } else {
+    TRY(case_softmax_mix(a->logits, a->ldv, a->gates, a->dist, a->ldv, R, a->V, 1, st));
+    TRY(case_copy_scatter(a->map, a->map_ld, 0, nullptr, a->attn_un[1], a->fac, CASE_MAX_SPLIT, a->dist, a->ldv, B, W,
+                          a->Lb, a->V, st));
+    if (a->materialize_only) return 0;
+    TRY(case_topk_rows(a->dist, a->ldv, R, a->V, W, a->top_vals, a->top_idx, st));
+  }
   return select_step(a->mode, B, W, t, a->max_len, a->Tmax, a->BOS, a->EOS, a->UNK, a->PAD, a->top_vals, a->top_idx,
                      a->live, a->cum, a->length, a->tok, a->anc, a->parent, a->ended, a->best_key, a->best_len,
                      a->out_tokens, a->n_live, st);
@@ -291,6 +328,7 @@ extern "C" size_t case_struct_size(int which) {
     case 3: return sizeof(case_select_args_t);
     case 4: return sizeof(case_step_args_t);
     case 5: return sizeof(gttp_step_args_t);
+    case 6: return sizeof(case_tail_args_t);
     default: return 0;
   }
 }

@@ -403,16 +403,28 @@ class CaseDecodeEngine(_EngineBase):
             raise ValueError('max_len exceeds the engine Tmax')
         if mode != L.MODE_BEAM and self.W != 1:
             raise ValueError('greedy modes need an engine built with W == 1')
+        self.launch(max_len, mode, use_graph)
+        return self._finish_tokens(max_len, mode)
+
+    @torch.no_grad()
+    def launch(self, max_len: int, mode: int = L.MODE_MODULE_GREEDY, use_graph: bool = True) -> None:
+        """Enqueue a whole decode on the current stream without any host synchronisation (the result is
+        read later with ``_finish_tokens``); lets several engines decode concurrently on several streams."""
+        if max_len > self.Tmax:
+            raise ValueError('max_len exceeds the engine Tmax')
         self.args.mode, self.args.max_len, self.args.materialize_only = mode, max_len, 0
+        self.ensure_graph(max_len, mode, use_graph)
         self.state.reset()
-        if use_graph and (max_len, mode) not in self._graphs:
-            self._capture(max_len, mode)
-            self.state.reset()
         if use_graph:
             self._graphs[(max_len, mode)].replay()
         else:
             self._run_steps(max_len)
-        return self._finish_tokens(max_len, mode)
+
+    def ensure_graph(self, max_len, mode, use_graph=True):
+        if use_graph and (max_len, mode) not in self._graphs:
+            self.args.mode, self.args.max_len, self.args.materialize_only = mode, max_len, 0
+            self.state.reset()
+            self._capture(max_len, mode)
 
     @torch.no_grad()
     def step_distribution(self, t: int) -> torch.Tensor:
@@ -424,14 +436,68 @@ class CaseDecodeEngine(_EngineBase):
         self.args.materialize_only = 0
         return self.dist[:, :self.V]
 
+    def answer_tokens(self) -> int:
+        return int(self.state.best_len.sum().item())
+
     def kernel_launches_per_step(self) -> int:
+        # (+1 in bench.py: the activation re-pack inside the vocabulary GEMM call)
         if self.w.cdtype == L.BF16 and self.Tmax <= L.load().case_layer_chain_max_tmax():
-            # 9 x layer_chain + 8 x cross + 2 x (row_linear, additive) + norm1 + gen.0 + vocab + finalize + softmax
-            # + 2 scatter + topk + select (+1: the activation re-pack inside the vocabulary GEMM call)
-            return 9 + 8 + 4 + 1 + 1 + 1 + 1 + 1 + 2 + 1 + 1
-        # embed + 8 x (front, cross, back) + 2 x (row_linear, additive) + finalize + gen.0 + vocab + softmax
-        # + 2 scatter + topk + select (+1: the activation re-pack inside the vocabulary GEMM call)
-        return 1 + 24 + 4 + 1 + 1 + 1 + 1 + 2 + 1 + 1
+            # 9 x layer_chain + 8 x cross + 2 x (row_linear, additive) + norm1 + gen.0 + vocab + row_tail + select
+            return 9 + 8 + 4 + 1 + 1 + 1 + 1 + 1
+        # embed + 8 x (front, cross, back) + 2 x (row_linear, additive) + norm1 + gen.0 + vocab + row_tail + select
+        return 1 + 24 + 4 + 1 + 1 + 1 + 1 + 1
+
+
+class CaseEngineGroup:
+    """Several CaSE engines over contiguous slices of one batch, decoded CONCURRENTLY on their own
+    streams.  Queries are independent (Generations.py:163-180 groups hypotheses by query), so a batch
+    can be cut anywhere; while one slice is in the latency-bound part of a step (the layer chain, the
+    vocabulary tail) the other streams K/V from HBM, which is what fills the machine at decode sizes.
+    Same prefill / decode interface as ``CaseDecodeEngine``."""
+
+    def __init__(self, weights: CaseWeights, B: int, W: int, S0: int, S1: int, Tmax: int = 40, parts: int = 2, **kw):
+        parts = max(1, min(parts, B))
+        sizes = [B // parts + (1 if i < B % parts else 0) for i in range(parts)]
+        self.bounds = [0]
+        for n in sizes:
+            self.bounds.append(self.bounds[-1] + n)
+        self.subs = [CaseDecodeEngine(weights, n, W, S0, S1, Tmax, **kw) for n in sizes]
+        self.device, self.w = weights.device, weights
+        self.B, self.W, self.R, self.S, self.Tmax, self.V = B, W, B * W, (S0, S1), Tmax, weights.V
+        self.streams = [torch.cuda.Stream(self.device) for _ in self.subs]
+
+    def _cut(self, x, i):
+        return x[self.bounds[i]:self.bounds[i + 1]]
+
+    @torch.no_grad()
+    def prefill(self, *tensors):
+        for i, sub in enumerate(self.subs):
+            sub.prefill(*[self._cut(x, i) for x in tensors])
+
+    @torch.no_grad()
+    def decode(self, max_len: int, mode: int = L.MODE_MODULE_GREEDY, use_graph: bool = True) -> torch.Tensor:
+        if mode != L.MODE_BEAM and self.W != 1:
+            raise ValueError('greedy modes need an engine built with W == 1')
+        for sub in self.subs:                      # captures (host-synchronous) happen before anything runs
+            sub.ensure_graph(max_len, mode, use_graph)
+        main = torch.cuda.current_stream(self.device)
+        for sub, st in zip(self.subs, self.streams):
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                sub.launch(max_len, mode, use_graph)
+        for st in self.streams:
+            main.wait_stream(st)
+        out = torch.cat([sub.state.out_tokens[:, :max_len] for sub in self.subs]).to(torch.int64)
+        if mode == L.MODE_BEAM:                    # merge1D (Utils.py:366-377): pad to the longest answer of the batch
+            Lmax = int(torch.stack([sub.state.best_len.max() for sub in self.subs]).max().item())
+            out = out[:, :max(Lmax, 1)]
+        return out
+
+    def answer_tokens(self) -> int:
+        return int(sum(int(sub.state.best_len.sum().item()) for sub in self.subs))
+
+    def kernel_launches_per_step(self) -> int:
+        return sum(sub.kernel_launches_per_step() for sub in self.subs)
 
 
 class GttpWeights:
@@ -563,4 +629,5 @@ class GttpDecodeEngine(_EngineBase):
         self.gstate[1].zero_()
 
     def kernel_launches_per_step(self) -> int:
-        return 1 + 2 * 3 + 3 + 1 + 1 + 1 + 1 + 1 + 1 + 1
+        # embed, 2 x (query linear, additive, merge), gi, gh, gru, readout, vocab, gates, row_tail, select
+        return 1 + 2 * 3 + 3 + 1 + 1 + 1 + 1 + 1

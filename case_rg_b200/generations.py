@@ -17,7 +17,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib as L
-from .engine import CaseDecodeEngine, CaseWeights, GttpDecodeEngine, GttpWeights
+from .engine import CaseDecodeEngine, CaseEngineGroup, CaseWeights, GttpDecodeEngine, GttpWeights
 
 PAD_WORD, BOS_WORD, UNK_WORD, EOS_WORD = '[PAD]', '[unused0]', '[UNK]', '[unused1]'
 
@@ -69,17 +69,24 @@ class FastCaSE(_FastModel):
     'prior_q', 'prior_p', 'answer_rep' [B,H], 'source_map' int64 [B,S]."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device=None, dtype='bf16', max_dec_len=40,
-                 beam_width=1, vocab_impl: Optional[int] = None, use_graph=True, prefix=''):
+                 beam_width=1, vocab_impl: Optional[int] = None, use_graph=True, prefix='', streams: int = 1):
+        """streams > 1: the batch is cut into that many slices decoded concurrently on their own CUDA
+        streams (CaseEngineGroup) - worthwhile from about 128 decode rows (B * W) up."""
         self.weights = CaseWeights(state_dict, device=device, dtype=dtype, prefix=prefix)
         self.max_dec_len, self.beam_width, self.vocab_impl, self.use_graph = max_dec_len, beam_width, vocab_impl, use_graph
+        self.streams = int(streams)
         self._engines = {}
 
-    def engine_for(self, B, W, S0, S1, T):
-        key = (B, W, S0, S1, T)
+    def engine_for(self, B, W, S0, S1, T, streams: int = 1):
+        key = (B, W, S0, S1, T, streams)
         if key not in self._engines:
             if len(self._engines) >= 4:
                 self._engines.clear()
-            self._engines[key] = CaseDecodeEngine(self.weights, B, W, S0, S1, T, vocab_impl=self.vocab_impl)
+            if streams > 1 and B >= streams:
+                self._engines[key] = CaseEngineGroup(self.weights, B, W, S0, S1, T, parts=streams,
+                                                     vocab_impl=self.vocab_impl)
+            else:
+                self._engines[key] = CaseDecodeEngine(self.weights, B, W, S0, S1, T, vocab_impl=self.vocab_impl)
         return self._engines[key]
 
     def encode(self, data):
@@ -90,7 +97,7 @@ class FastCaSE(_FastModel):
         B = d['source_map'].size(0)
         S0 = d['mem_q'].reshape(B, -1, L.H).size(1)
         S1 = d['mem_p'].reshape(B, -1, L.H).size(1)
-        eng = self.engine_for(B, width, S0, S1, max_len)
+        eng = self.engine_for(B, width, S0, S1, max_len, self.streams)
         eng.prefill(d['mem_q'], d['mem_p'], d['query'].ne(0), d['passage'].ne(0), d['prior_q'], d['prior_p'],
                     d['answer_rep'], d['source_map'])
         self.last_engine = eng

@@ -50,7 +50,7 @@ typedef void* case_stream_t; /* cudaStream_t */
 int case_abi_version(void);
 const char* case_last_error(void);
 /* sizeof() of the argument structs below, for binding self-checks: 0 case_seg_t, 1 case_rowlin_args_t,
- * 2 case_layer_weights_t, 3 case_select_args_t, 4 case_step_args_t, 5 gttp_step_args_t */
+ * 2 case_layer_weights_t, 3 case_select_args_t, 4 case_step_args_t, 5 gttp_step_args_t, 6 case_tail_args_t */
 size_t case_struct_size(int which);
 /* Programmatic dependent launch for every kernel of a step (default on); returns the old setting. */
 int case_set_pdl(int on);
@@ -60,6 +60,9 @@ int case_set_chain(int on);
 /* Fork/join of the additive attentions onto a library-owned side stream inside case_decode_step
  * (cluster path only; default on); returns the old setting. */
 int case_set_fork(int on);
+/* case_row_tail instead of finalize + softmax_mix + copy_scatter + topk_rows inside the step
+ * orchestrators (default on); returns the old setting. */
+int case_set_fused_tail(int on);
 
 /* ---------------------------------------------------------------- row-wise building blocks */
 
@@ -236,6 +239,25 @@ int case_copy_scatter(const int32_t* map, int map_ld, int map_off, const float* 
 /* Per-row top-k, values descending, ties -> lower index first (Utils.topk, Utils.py:156-168). */
 int case_topk_rows(const float* dist, int ldd, int R, int V, int k, float* vals, int32_t* idx,
                    case_stream_t stream);
+
+/* Fused tail of a step, one CTA per row with the row's distribution in shared memory:
+ *   [do_finalize: case_finalize_rows without the LayerNorm (hN is an input)] -> case_softmax_mix ->
+ *   case_copy_scatter for nmem memories -> case_topk_rows (k = K),
+ * reading the logits once and never writing the [R, V] tile unless dist != NULL.  top_idx == NULL skips
+ * the top-k (then dist must be given).  Without do_finalize, gates[r][0] and the (F, M) pairs
+ * fac[r*fac_ld + fac_off[i] + 0..1] are inputs (GTTP: case_attn_merge + case_gttp_gates).
+ * V <= case_row_tail_max_vocab(); logits rows 16-byte aligned, ldl >= V rounded up to 4. */
+typedef struct {
+  int32_t R, V, W, K, ldl, ldd, mask_col0, nmem, do_finalize, fac_ld, map_ld;
+  int32_t ns[2], fac_off[2], map_off[2], S[2];
+  const float* logits;
+  const float* hN; const float* stats[2]; const float* ctxp[2]; const float* Wm; const float* bm;
+  float* ctx[2]; float* gates; float* fac;
+  const int32_t* map; const float* prior[2]; const float* attn_un[2];
+  float* top_vals; int32_t* top_idx; float* dist;
+} case_tail_args_t;
+int case_row_tail(const case_tail_args_t* a, case_stream_t stream);
+int case_row_tail_max_vocab(void);
 
 /* ---------------------------------------------------------------- search bookkeeping */
 

@@ -91,3 +91,31 @@ def test_config5_long_context_per_gpu_share():
     out_sub = FG.beam(sub, _case_data(inp.slice(0, 4)), None, T, W)
     L = min(out_sub.size(1), out.size(1))
     assert (out_sub[:, :L] == out[:4, :L]).float().mean() > 0.9
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+@pytest.mark.parametrize('B,W,streams', [(9, 4, 2), (8, 1, 3), (3, 2, 4)])
+def test_stream_sliced_batch_gives_the_same_answers(B, W, streams, dtype):
+    """CaseEngineGroup: the batch cut into slices decoded concurrently on several streams returns what
+    the single-engine decode returns (queries are independent; fp32 exactly, bf16 up to split-merge
+    rounding on near-ties)."""
+    from case_rg_b200 import generations as FG
+    V, T = 3000, 10
+    sd = syn.make_case_decoder_state(61, V, 256, peaked=0.3, boost={syn.EOS: 8.0}, gen_gate_bias=2.0)
+    inp = syn.make_case_inputs(62, B, 24, 3, 50, V, 256)
+    data = _case_data(inp)
+    outs = []
+    for n in (1, streams):
+        model = FG.FastCaSE(sd, device='cuda:0', dtype=dtype, streams=n)
+        outs.append((FG.beam(model, data, None, T, W) if W > 1 else FG.greedy(model, data, None, T)).cpu())
+        if n > 1 and B >= n:
+            assert len(model.last_engine.subs) == n
+            assert model.last_engine.answer_tokens() > 0 if W > 1 else True
+    a, b = outs
+    if dtype == 'fp32':
+        assert torch.equal(a, b), (a, b)
+    else:
+        n = min(a.size(1), b.size(1))
+        same = sum(int(torch.equal(a[i, :n], b[i, :n])) for i in range(B))
+        assert same >= B - 1, (a, b)
