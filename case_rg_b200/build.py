@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libcase_b200.so')
-SOURCES = ['rowops.cu', 'rowops_tc.cu', 'layer_cluster.cu', 'attention.cu', 'additive_v2.cu', 'vocab.cu', 'tail.cu', 'select.cu', 'step.cu', 'gemm_tcgen05.cu']
+SOURCES = ['rowops.cu', 'rowops_tc.cu', 'layer_cluster.cu', 'attention.cu', 'additive_v2.cu', 'vocab.cu', 'tail.cu', 'sparse_tail.cu', 'select.cu', 'step.cu', 'gemm_tcgen05.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 
@@ -20,7 +20,8 @@ def _stale(target, deps):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    hdrs = [os.path.join(CSRC, 'common.cuh'), os.path.join(HERE, '..', 'include', 'case_b200.h')]
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh')] + \
+           [os.path.join(HERE, '..', 'include', 'case_b200.h')]
     objs = []
     os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
     procs = []

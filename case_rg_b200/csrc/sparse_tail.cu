@@ -1,0 +1,401 @@
+// Sparse form of the vocabulary tail for the search path (the [R, V] mixture is never built).
+//
+//   dist[r, v] = g0[r] * softmax(logits[r])[v] + sum over source positions s with map[b, s] == v of
+//                gate_i[r] * p_i[r, s]                          (Model.py:34-43, Utils.build_map)
+//   followed by top-k per row                                   (Utils.topk, Utils.py:156-168)
+//
+// Every id of the final top-k is either one of the (at most S0 + S1) copy targets of the row or one of
+// the top-k ids of the base softmax: an id that receives no copy mass keeps the order it has in the
+// base distribution.  So the step splits into
+//   case_vocab_base  - per row: max, sum of exp and the 2k largest base entries (k extra entries
+//                      absorb ties created when the gate scale rounds two neighbouring values onto
+//                      one float).  Needs only the logits, so it runs beside the additive attention;
+//   case_sparse_tail - after the attentions: [CaSE gates] -> a shared-memory hash table keyed by
+//                      vocabulary id accumulates the copy mass of both memories -> every touched id
+//                      gets g0 * exp(logit - max) / sum + mass (one gather from the logits) -> top-k
+//                      over touched ids + base candidates.
+// Work after the attentions drops from three passes over the 31 MB tile to ~2.7 k entries per row.
+#include "common.cuh"
+#include "topk.cuh"
+
+namespace cb {
+
+constexpr int ST = 256;          // vocab_base threads
+constexpr int SW = ST / 32;
+constexpr int TS = 512;          // sparse_tail threads
+constexpr int TSW = TS / 32;
+
+// ------------------------------------------------------------------------------------------ base statistics
+// grid = R x SP_PARTS: CTA (r, c) reduces the quarter [c*Vq, (c+1)*Vq) of row r in ONE read, with all of a
+// thread's 16-byte loads of a batch in flight together: local (max, sum exp(l - max)) and the k2 largest
+// logits of the quarter (value desc, index asc).  The consumer merges the four partials.
+constexpr int SP_PARTS = 4;
+constexpr int SP_BATCH = 8;      // float4 loads in flight per thread
+
+// fast exp for the softmax terms: one ex2.approx (results below 2^-126 flush to zero, which no top-k sees)
+__device__ __forceinline__ float sp_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
+__device__ __forceinline__ float4 vb_load(const float* x, int q, int nf4, int nv, bool mask0) {
+  float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  if (q < nf4) {
+    v = *reinterpret_cast<const float4*>(x + q * 4);
+    const int i = q * 4;
+    if (i + 3 >= nv) {                                   // tail chunk: slots past the quarter do not exist
+      if (i + 1 >= nv) v.y = -INFINITY;
+      if (i + 2 >= nv) v.z = -INFINITY;
+      if (i + 3 >= nv) v.w = -INFINITY;
+    }
+    if (mask0 && q == 0) v.x = -INFINITY;
+  }
+  return v;
+}
+
+__global__ __launch_bounds__(ST) void vocab_base_kernel(const float* __restrict__ logits, int ldl, int V, int Vq,
+                                                        int mask_col0, int k2, float* __restrict__ base_ms,
+                                                        float* __restrict__ base_l, int32_t* __restrict__ base_i) {
+  __shared__ float shm[SW], shs[SW];
+  __shared__ TopKScratch<SW, 256> sc;
+  pdl_wait();
+  const int r = blockIdx.x / SP_PARTS, c = blockIdx.x % SP_PARTS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int v0 = c * Vq, nv = max(0, min(V, v0 + Vq) - v0);
+  const float* x = logits + (size_t)r * ldl + v0;       // 16-byte aligned: Vq % 4 == 0
+  const int nf4 = (nv + 3) / 4;                          // the row is padded to a multiple of 4 (ldl)
+  const bool mask0 = mask_col0 && c == 0;
+  // ---- pass A: per-thread max and sum of exp (online), all loads of a batch in flight together
+  float m = -INFINITY, s = 0.f;
+  for (int base = 0; base < nf4; base += SP_BATCH * ST) {
+    float4 v[SP_BATCH];
+#pragma unroll
+    for (int u = 0; u < SP_BATCH; ++u) v[u] = vb_load(x, base + u * ST + tid, nf4, nv, mask0);
+    float bm = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < SP_BATCH; ++u) bm = fmaxf(bm, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
+    if (bm > m) { s *= sp_exp(m - bm); m = bm; }         // m = -inf: s was 0 and exp(-inf) = 0
+    const float mm = (m > -INFINITY) ? m : 0.f;
+#pragma unroll
+    for (int u = 0; u < SP_BATCH; ++u)
+      s += (sp_exp(v[u].x - mm) + sp_exp(v[u].y - mm)) + (sp_exp(v[u].z - mm) + sp_exp(v[u].w - mm));
+  }
+  {
+    const float Mw = warp_max(m);
+    float sw = (m > -INFINITY) ? s * sp_exp(m - Mw) : 0.f;
+    sw = warp_sum(sw);
+    if (lane == 0) { shm[warp] = Mw; shs[warp] = sw; }
+  }
+  // ---- the k2-th largest thread maximum bounds the top-k2 from below; collect everything >= it
+  const float T = block_kth_max(sc, k2, m);
+  if (tid == 0) {
+    float MM = shm[0];
+#pragma unroll
+    for (int w = 1; w < SW; ++w) MM = fmaxf(MM, shm[w]);
+    float t2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < SW; ++w) t2 += (shm[w] > -INFINITY) ? shs[w] * sp_exp(shm[w] - MM) : 0.f;
+    base_ms[((size_t)r * SP_PARTS + c) * 2] = MM;
+    base_ms[((size_t)r * SP_PARTS + c) * 2 + 1] = t2;
+  }
+  if (m >= T && m > -INFINITY) {                        // only threads that own a candidate look again
+    for (int q = tid; q < nf4; q += ST) {
+      const float4 v = vb_load(x, q, nf4, nv, mask0);
+      const int i = v0 + q * 4;
+      if (v.x >= T) topk_append(sc, v.x, i);
+      if (v.y >= T) topk_append(sc, v.y, i + 1);
+      if (v.z >= T) topk_append(sc, v.z, i + 2);
+      if (v.w >= T) topk_append(sc, v.w, i + 3);
+    }
+  }
+  __syncthreads();
+  float ov = -INFINITY;
+  int oi = 0x7fffffff;
+  if (!block_select(sc, k2, ov, oi)) {                   // massive ties: offer every element
+    WarpTopK wl;
+    wl.init();
+    for (int q0 = 0; q0 < nf4; q0 += ST) {
+      const int q = q0 + tid;
+      const float4 v = vb_load(x, q, nf4, nv, mask0);
+      const int i = v0 + q * 4;
+      wl.offer(k2, v.x, i); wl.offer(k2, v.y, i + 1); wl.offer(k2, v.z, i + 2); wl.offer(k2, v.w, i + 3);
+    }
+    block_merge_lists(sc, wl, k2);
+    ov = wl.ev; oi = wl.ei;
+  }
+  if (warp == 0 && lane < k2) {
+    base_l[((size_t)r * SP_PARTS + c) * k2 + lane] = ov;
+    base_i[((size_t)r * SP_PARTS + c) * k2 + lane] = oi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ sparse tail
+// double hashing over a power-of-two table: start = high bits of a multiplicative hash, odd step
+__device__ __forceinline__ uint32_t sp_hash(int id, int shift) { return ((uint32_t)id * 2654435761u) >> shift; }
+__device__ __forceinline__ uint32_t sp_step(int id) { return (((uint32_t)id * 40503u) >> 4) | 1u; }
+
+__global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t a, const float* __restrict__ base_ms,
+                                                         const float* __restrict__ base_e,
+                                                         const int32_t* __restrict__ base_i, int k2, int nslots,
+                                                         long long* dbg) {
+  extern __shared__ __align__(16) int hkeys[];            // [nslots] ids (-1 = empty), then [nslots] float masses
+  float* hvals = reinterpret_cast<float*>(hkeys + nslots);
+  __shared__ float sh[TSW * 3];
+  __shared__ TopKScratch<TSW, 256> sc;
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = r / a.W, V = a.V;
+  const uint32_t hmask = (uint32_t)nslots - 1;
+  const int hshift = 32 - (31 - __clz(nslots));            // nslots is a power of two
+  int dbg_n = 0;
+  auto stamp = [&]() { if (dbg != nullptr && blockIdx.x == 0 && tid == 0) dbg[dbg_n++] = clock64(); };
+  stamp();
+  for (int i = tid; i < nslots; i += TS) { hkeys[i] = -1; hvals[i] = 0.f; }
+  pdl_wait();
+  stamp();
+  float g0, F[2] = {0.f, 0.f}, M[2] = {0.f, 0.f};
+  if (a.do_finalize) {
+    // every thread merges the split statistics itself (a few broadcast loads), column tid of the contexts
+    int wn = 0;
+    auto wstamp = [&]() { if (dbg != nullptr && blockIdx.x == 0 && lane == 0) dbg[32 + warp * 8 + wn++] = clock64(); };
+    wstamp();
+    const int col = tid < H ? tid : 0;                     // threads past H repeat column 0 and contribute nothing
+    const float y = a.hN[(size_t)r * H + col];
+    float Z[2], Q[2], cx[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int ns = a.ns[i];
+      const float4* st = reinterpret_cast<const float4*>(a.stats[i]) + (size_t)r * ns;
+      const float* cp = a.ctxp[i] + (size_t)r * ns * H + col;
+      float Mx = -INFINITY;
+#pragma unroll 4
+      for (int j = 0; j < ns; ++j) Mx = fmaxf(Mx, __ldg(st + j).x);
+      float z = 0.f, q = 0.f, acc = 0.f;
+#pragma unroll 4
+      for (int j = 0; j < ns; ++j) {
+        const float4 sj = __ldg(st + j);
+        const float cj = cp[(size_t)j * H];
+        const float e = (sj.x == -INFINITY) ? 0.f : fexp(sj.x - Mx);
+        z = fmaf(sj.y, e, z);
+        q = fmaf(sj.z, e, q);
+        acc = fmaf(cj, e, acc);
+      }
+      M[i] = Mx; Z[i] = z; Q[i] = q;
+      cx[i] = z > 0.f ? acc / z : 0.f;
+      if (tid < H) a.ctx[i][(size_t)r * H + tid] = cx[i];
+      wstamp();
+    }
+    float part[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float* wr = a.Wm + (size_t)k * 3 * H;
+      const float pk = fmaf(__ldg(wr + col), y, fmaf(__ldg(wr + H + col), cx[0], __ldg(wr + 2 * H + col) * cx[1]));
+      part[k] = warp_sum(tid < H ? pk : 0.f);
+    }
+    if (lane == 0) { sh[warp * 3] = part[0]; sh[warp * 3 + 1] = part[1]; sh[warp * 3 + 2] = part[2]; }
+    wstamp();
+    __syncthreads();
+    wstamp();
+    float lg[3] = {__ldg(a.bm), __ldg(a.bm + 1), __ldg(a.bm + 2)};
+#pragma unroll
+    for (int w = 0; w < TSW; ++w) { lg[0] += sh[w * 3]; lg[1] += sh[w * 3 + 1]; lg[2] += sh[w * 3 + 2]; }
+    const float mx = fmaxf(lg[0], fmaxf(lg[1], lg[2]));
+    const float e0 = expf(lg[0] - mx), e1 = expf(lg[1] - mx), e2 = expf(lg[2] - mx);
+    const float inv = 1.f / (e0 + e1 + e2);
+    g0 = e0 * inv;
+    const float gi[2] = {e1 * inv, e2 * inv};
+    // copy weight(r,i,s) = F_i * prior_i[s] * exp(e_i[s] - M_i) == gate_{i+1} * (w a) / (1e-8 + sum w a)
+    // (Model.py:110-111, 42) with a = softmax(e): F_i = gate_{i+1} / (Z_i * (1e-8 + Q_i / Z_i))
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      F[i] = Z[i] > 0.f ? gi[i] / (Z[i] * (1e-8f + Q[i] / Z[i])) : 0.f;
+      M[i] = Z[i] > 0.f ? M[i] : 0.f;
+    }
+    if (tid == 0) {
+      float* gt = a.gates + (size_t)r * 4;
+      gt[0] = g0; gt[1] = gi[0]; gt[2] = gi[1]; gt[3] = 0.f;
+      float* f = a.fac + (size_t)r * a.fac_ld;
+      f[a.fac_off[0]] = F[0]; f[a.fac_off[0] + 1] = M[0];
+      f[a.fac_off[1]] = F[1]; f[a.fac_off[1] + 1] = M[1];
+    }
+    wstamp();
+  } else {
+    g0 = a.gates[(size_t)r * 4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (i < a.nmem) {
+        F[i] = a.fac[(size_t)r * a.fac_ld + a.fac_off[i]];
+        M[i] = a.fac[(size_t)r * a.fac_ld + a.fac_off[i] + 1];
+      }
+    }
+    __syncthreads();       // the table is initialised
+  }
+  stamp();
+  // ---- copy mass of both memories into the hash table (linear probing, ids are exact)
+#pragma unroll 1
+  for (int i = 0; i < 2; ++i) {
+    if (i >= a.nmem) break;
+    const float Fi = i == 0 ? F[0] : F[1], Mi = i == 0 ? M[0] : M[1];
+    if (Fi == 0.f) continue;
+    const int S = a.S[i];
+    const float* at = a.attn_un[i] + (size_t)r * S;
+    const float* pr = a.prior[i] ? a.prior[i] + (size_t)b * S : nullptr;
+    const int32_t* mp = a.map + (size_t)b * a.map_ld + a.map_off[i];
+    for (int s0 = tid; s0 < S; s0 += 4 * TS) {
+      int id[4];
+      float ev[4], pv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int sidx = s0 + u * TS;
+        const bool in = sidx < S;
+        id[u] = in ? __ldg(mp + sidx) : -1;
+        ev[u] = in ? at[sidx] : -INFINITY;
+        pv[u] = (in && pr) ? __ldg(pr + sidx) : 1.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (ev[u] == -INFINITY || (unsigned)id[u] >= (unsigned)V) continue;   // masked source position
+        const float cw = Fi * pv[u] * fexp(ev[u] - Mi);
+        if (cw == 0.f) continue;
+        uint32_t slot = sp_hash(id[u], hshift);
+        const uint32_t step = sp_step(id[u]);
+        while (true) {
+          const int old = atomicCAS(hkeys + slot, -1, id[u]);
+          if (old == -1 || old == id[u]) { atomicAdd(hvals + slot, cw); break; }
+          slot = (slot + step) & hmask;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  stamp();
+  // ---- candidates: every touched id (base value gathered from the logits) and the base top entries
+  float mrow = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < SP_PARTS; ++k) mrow = fmaxf(mrow, base_ms[((size_t)r * SP_PARTS + k) * 2]);
+  float srow = 0.f;
+#pragma unroll
+  for (int k = 0; k < SP_PARTS; ++k) {
+    const float mk = base_ms[((size_t)r * SP_PARTS + k) * 2];
+    srow += (mk > -INFINITY) ? base_ms[((size_t)r * SP_PARTS + k) * 2 + 1] * sp_exp(mk - mrow) : 0.f;
+  }
+  const float mm = (mrow > -INFINITY) ? mrow : 0.f;
+  const float scl = g0 / srow;
+  const float* x = a.logits + (size_t)r * a.ldl;
+  const int K = a.K;
+  // pass A: the final value of every touched id replaces its mass in the table; thread maximum
+  float tmax = -INFINITY;
+  for (int s0 = tid; s0 < nslots; s0 += 4 * TS) {        // nslots is a multiple of 4 * TS
+    int id[4];
+    float lv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      id[u] = hkeys[s0 + u * TS];
+      lv[u] = id[u] >= 0 ? x[id[u]] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (id[u] < 0) continue;
+      const float e = (a.mask_col0 && id[u] == 0) ? 0.f : sp_exp(lv[u] - mm);
+      const float f = fmaf(scl, e, hvals[s0 + u * TS]);
+      hvals[s0 + u * TS] = f;
+      tmax = fmaxf(tmax, f);
+    }
+  }
+  stamp();
+  float fb = -INFINITY;                                  // base candidates that received no copy mass
+  int idb = 0x7fffffff;
+  if (tid < SP_PARTS * k2) {
+    const int id = base_i[(size_t)r * SP_PARTS * k2 + tid];
+    const float l = base_e[(size_t)r * SP_PARTS * k2 + tid];
+    if ((unsigned)id < (unsigned)V && l > -INFINITY) {
+      bool found = false;
+      uint32_t slot = sp_hash(id, hshift);
+      const uint32_t step = sp_step(id);
+      while (true) {
+        const int key = hkeys[slot];
+        if (key == id) { found = true; break; }
+        if (key == -1) break;
+        slot = (slot + step) & hmask;
+      }
+      if (!found) { fb = scl * sp_exp(l - mm); idb = id; }
+    }
+  }
+  tmax = fmaxf(tmax, fb);
+  const float T = block_kth_max(sc, K, tmax);
+  if (tmax >= T && tmax > -INFINITY) {
+    for (int sl = tid; sl < nslots; sl += TS) {
+      const int id = hkeys[sl];
+      if (id >= 0 && hvals[sl] >= T) topk_append(sc, hvals[sl], id);
+    }
+    if (fb >= T) topk_append(sc, fb, idb);
+  }
+  __syncthreads();
+  stamp();
+  float ov = -INFINITY;
+  int oi = 0x7fffffff;
+  if (!block_select(sc, K, ov, oi)) {                    // massive ties: offer every candidate
+    WarpTopK wl;
+    wl.init();
+    for (int s0 = 0; s0 < nslots; s0 += TS) {
+      const int id = hkeys[s0 + tid];
+      wl.offer(K, id >= 0 ? hvals[s0 + tid] : -INFINITY, id >= 0 ? id : 0x7fffffff);
+    }
+    wl.offer(K, fb, idb);
+    block_merge_lists(sc, wl, K);
+    ov = wl.ev; oi = wl.ei;
+  }
+  if (warp == 0 && lane < K) {
+    a.top_vals[(size_t)r * K + lane] = ov;
+    a.top_idx[(size_t)r * K + lane] = oi;
+  }
+  stamp();
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" int case_vocab_base(const float* logits, int ldl, int R, int V, int mask_col0, int k2, float* base_ms,
+                               float* base_l, int32_t* base_i, case_stream_t stream) {
+  CB_REQUIRE(logits && base_ms && base_l && base_i && R > 0 && V > 0, "case_vocab_base: bad arguments");
+  CB_REQUIRE(k2 >= 1 && k2 <= 2 * CASE_MAX_W, "case_vocab_base: k2 out of range (1..16)");
+  CB_REQUIRE(ldl % 4 == 0 && ldl >= ((V + 3) / 4) * 4 && (uintptr_t)logits % 16 == 0, "case_vocab_base: logits rows must be 16-byte aligned and padded to a multiple of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Vq = (((V + SP_PARTS - 1) / SP_PARTS) + 3) / 4 * 4;
+  const int grid = R * SP_PARTS;
+  launch_k(vocab_base_kernel, grid, ST, 0, st, logits, ldl, V, Vq, mask_col0, k2, base_ms, base_l, base_i);
+  return check_launch("case_vocab_base");
+}
+
+static long long* g_sp_dbg = nullptr;
+extern "C" int case_debug_sparse_tail_timing(void* buf) { g_sp_dbg = (long long*)buf; return 0; }
+
+extern "C" int case_sparse_tail_max_sources(void) { return 10900; }   // 16384 slots at load factor <= 2/3
+
+extern "C" int case_sparse_tail(const case_tail_args_t* a, const float* base_ms, const float* base_e,
+                                const int32_t* base_i, int k2, case_stream_t stream) {
+  CB_REQUIRE(a && a->logits && a->gates && a->fac && a->map && base_ms && base_e && base_i, "case_sparse_tail: null pointer");
+  CB_REQUIRE(a->R > 0 && a->W >= 1 && a->V > 0 && a->top_vals && a->top_idx, "case_sparse_tail: bad sizes / outputs");
+  CB_REQUIRE(a->K >= 1 && a->K <= CASE_MAX_W && k2 >= a->K && k2 <= 2 * CASE_MAX_W, "case_sparse_tail: need K <= k2 <= 16");
+  CB_REQUIRE(a->nmem >= 1 && a->nmem <= 2, "case_sparse_tail: nmem must be 1 or 2");
+  CB_REQUIRE(!a->do_finalize || (a->nmem == 2 && a->hN && a->stats[0] && a->stats[1] && a->ctxp[0] && a->ctxp[1] && a->Wm && a->bm && a->ctx[0] && a->ctx[1] && a->ns[0] >= 1 && a->ns[1] >= 1 && a->ns[0] <= CASE_MAX_SPLIT && a->ns[1] <= CASE_MAX_SPLIT),
+             "case_sparse_tail: the CaSE finaliser needs hN, stats, ctxp, Wm, bm, ctx for both memories");
+  int total = 0;
+  for (int i = 0; i < a->nmem; ++i) {
+    CB_REQUIRE(a->attn_un[i] && a->S[i] > 0, "case_sparse_tail: attn_un / S missing");
+    total += a->S[i];
+  }
+  CB_REQUIRE(total <= case_sparse_tail_max_sources(), "case_sparse_tail: too many source positions for the shared-memory table");
+  int nslots = 4 * TS;
+  while (nslots < 3 * total && nslots < 16384) nslots *= 2;  // load factor ~1/3 (<= 2/3 at the size limit)
+  const size_t smem = (size_t)nslots * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(sparse_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    attr = true;
+  }
+  launch_k(sparse_tail_kernel, a->R, TS, smem, st, *a, base_ms, base_e, base_i, k2, nslots, g_sp_dbg);
+  return check_launch("case_sparse_tail");
+}

@@ -1,6 +1,7 @@
 // Error plumbing and the whole-step orchestrators: one C call enqueues every kernel of a decode
 // step on the caller's stream (so a step, or a whole decode, can be captured in a CUDA graph).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -11,7 +12,7 @@ static thread_local char g_err[512] = "ok";
 int g_use_pdl = 1;
 int g_use_chain = 1;
 int g_use_fork = 1;
-int g_use_tail = 1;
+int g_use_tail = 2;
 // side stream + events for the fork/join inside a step (created on first use, outside any capture: the
 // engines run one uncaptured warm-up step before they capture)
 static cudaStream_t g_aux = nullptr;
@@ -60,7 +61,7 @@ extern "C" int case_set_chain(int on) {
 }
 extern "C" int case_set_fused_tail(int on) {
   const int old = g_use_tail;
-  g_use_tail = on ? 1 : 0;
+  g_use_tail = on < 0 ? 0 : (on > 2 ? 2 : on);
   return old;
 }
 extern "C" int case_set_fork(int on) {
@@ -140,6 +141,10 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       return (int)_ce;                                                   \
     }                                                                    \
   } while (0)
+  // search path: the sparse tail (touched ids + base candidates); `generate` face: the dense fused tail
+  const int k2 = 2 * W;
+  const bool sparse = g_use_tail == 2 && !a->materialize_only && a->base_ms && a->base_e && a->base_i && a->V >= k2 &&
+                      a->S[0] + a->S[1] <= case_sparse_tail_max_sources();
   const bool chain = dt == CASE_BF16 && g_use_chain && a->layers[0].Wc != nullptr && a->Tmax <= case_layer_chain_max_tmax();
   if (chain) {
     // Cluster kernels: [embed + front 0] x [back 0 + front 1] x ... x [back 7], one launch between
@@ -174,6 +179,7 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
     TRY(case_layernorm_rows(a->h, a->lnN_g, a->lnN_b, a->hN, R, st));
     TRY(gen0());
     TRY(case_vocab_gemm(a->gfeat, a->Wv, nullptr, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, a->vocab_ws, st));
+    if (sparse && !getenv("CASE_SKIP_BASE")) TRY(case_vocab_base(a->logits, a->ldv, R, a->V, 0, k2, a->base_ms, a->base_e, a->base_i, st));
     if (fork) {
       CUTRY(cudaStreamWaitEvent(st, g_ev_join[0], 0));
       CUTRY(cudaStreamWaitEvent(st, g_ev_join[1], 0));
@@ -202,8 +208,9 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
   TRY(case_layernorm_rows(a->h, a->lnN_g, a->lnN_b, a->hN, R, st));
   TRY(gen0());
   TRY(case_vocab_gemm(a->gfeat, a->Wv, nullptr, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, a->vocab_ws, st));
+  if (sparse) TRY(case_vocab_base(a->logits, a->ldv, R, a->V, 0, k2, a->base_ms, a->base_e, a->base_i, st));
   }
-  if (g_use_tail && a->V <= case_row_tail_max_vocab()) {
+  if (sparse || (g_use_tail && a->V <= case_row_tail_max_vocab())) {
     // one launch: attention merge + gates, softmax x gate, both copy scatters, top-k; the [R, V]
     // distribution is written only for the `generate` face
     case_tail_args_t ta;
@@ -218,7 +225,11 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       ta.attn_un[i] = a->attn_un[i];
     }
     if (a->materialize_only) { ta.dist = a->dist; } else { ta.top_vals = a->top_vals; ta.top_idx = a->top_idx; }
-    TRY(case_row_tail(&ta, st));
+    if (sparse) {
+      TRY(case_sparse_tail(&ta, a->base_ms, a->base_e, a->base_i, k2, st));
+    } else {
+      TRY(case_row_tail(&ta, st));
+    }
     if (a->materialize_only) return 0;
   } else {
     TRY(finalize());

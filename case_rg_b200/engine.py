@@ -323,6 +323,8 @@ class CaseDecodeEngine(_EngineBase):
         self.top_idx = torch.zeros(R, W, dtype=torch.int32, device=dev)
         self.prow = torch.zeros(R, Tmax, dtype=torch.int32, device=dev)
         self.h0, self.qa1 = z(R, H), z(R, H)
+        self.base_ms, self.base_e = z(R, 4, 2), z(R, 4, 16)
+        self.base_i = torch.zeros(R, 4, 16, dtype=torch.int32, device=dev)
         self._graphs = {}
         self._step_fn = L.load().case_decode_step
         self._step_name = 'case_decode_step'
@@ -357,7 +359,7 @@ class CaseDecodeEngine(_EngineBase):
         a.map, a.map_ld = self.map.data_ptr(), self.map.size(1)
         self.state.bind(a)
         for n in ('x_in', 'h', 'bbuf', 'q2', 'part_ml', 'part_acc', 'qa', 'hN', 'gates', 'fac', 'gfeat', 'logits',
-                  'dist', 'top_vals', 'top_idx', 'prow', 'h0', 'qa1'):
+                  'dist', 'top_vals', 'top_idx', 'prow', 'h0', 'qa1', 'base_ms', 'base_e', 'base_i'):
             setattr(a, n, getattr(self, n).data_ptr())
 
     # ------------------------------------------------------------------ per batch

@@ -60,8 +60,9 @@ int case_set_chain(int on);
 /* Fork/join of the additive attentions onto a library-owned side stream inside case_decode_step
  * (cluster path only; default on); returns the old setting. */
 int case_set_fork(int on);
-/* case_row_tail instead of finalize + softmax_mix + copy_scatter + topk_rows inside the step
- * orchestrators (default on); returns the old setting. */
+/* Tail of the step orchestrators: 0 = finalize + softmax_mix + copy_scatter + topk_rows, 1 = case_row_tail,
+ * 2 (default) = case_vocab_base + case_sparse_tail where the scratch buffers are given, else 1; returns
+ * the old setting. */
 int case_set_fused_tail(int on);
 
 /* ---------------------------------------------------------------- row-wise building blocks */
@@ -259,6 +260,20 @@ typedef struct {
 int case_row_tail(const case_tail_args_t* a, case_stream_t stream);
 int case_row_tail_max_vocab(void);
 
+/* Sparse form of the tail for the search path (never builds the [R, V] mixture): every id of the final
+ * top-k is a copy target of the row or one of the top entries of the base softmax.
+ * case_vocab_base: the row is cut into 4 quarters; per (row, quarter) base_ms[r][4][2] = (max logit, sum
+ *   exp(l - max)) and the k2 (K <= k2 <= 16; use 2K) largest logits base_l[r][4][k2] with their ids
+ *   base_i[r][4][k2] (value desc, index asc; -inf / out-of-range id = no entry).  Needs only the logits,
+ *   so it can run beside the additive attention.
+ * case_sparse_tail: same inputs/outputs as case_row_tail (top_vals / top_idx required, dist ignored)
+ *   plus the base statistics; sum of S[i] <= case_sparse_tail_max_sources(). */
+int case_vocab_base(const float* logits, int ldl, int R, int V, int mask_col0, int k2, float* base_ms,
+                    float* base_l, int32_t* base_i, case_stream_t stream);
+int case_sparse_tail(const case_tail_args_t* a, const float* base_ms, const float* base_l, const int32_t* base_i,
+                     int k2, case_stream_t stream);
+int case_sparse_tail_max_sources(void);
+
 /* ---------------------------------------------------------------- search bookkeeping */
 
 typedef struct {
@@ -329,6 +344,7 @@ typedef struct {
   int32_t* prow;                        /* [R][Tmax] scratch of case_layer_chain (may be NULL) */
   float* h0; float* qa1;                /* [R][H] each (may be NULL): stack-0 output and second attention query,
                                            private copies that let the additive attentions run on a side stream */
+  float* base_ms; float* base_e; int32_t* base_i;   /* [R][4][2], [R][4][16], [R][4][16] (may be NULL): case_vocab_base */
 } case_step_args_t;
 
 /* Enqueue one full decode step t (embedding .. select) for all R rows: the body of the eval loop

@@ -75,7 +75,54 @@ def stamps(**kw):
             print(f'   {n:16s} {s[i + 1] - s[i]:7d} cyc')
 
 
+def sparse_stamps(R=256, W=4, V=30522, S=(60, 2560), K=4):
+    a, keep = build(R=R, W=W, V=V, S=S, K=K)
+    lib = L.load()
+    lib.case_debug_sparse_tail_timing.argtypes = [C.c_void_p]
+    f32 = dict(dtype=torch.float32, device='cuda')
+    k2 = 2 * K
+    ldv = -(-V // 8) * 8
+    bms, bl = torch.zeros(R, 4, 2, **f32), torch.zeros(R, 4, k2, **f32)
+    bi = torch.zeros(R, 4, k2, dtype=torch.int32, device='cuda')
+    st = torch.cuda.current_stream().cuda_stream
+    dbg = torch.zeros(128, dtype=torch.int64, device='cuda')
+    names = ['init+pdl wait', 'finalize', 'hash inserts', 'pass A (gather)', 'threshold+append', 'select']
+
+    def base():
+        L.call('case_vocab_base', keep['logits'].data_ptr(), ldv, R, V, 0, k2, bms.data_ptr(), bl.data_ptr(), bi.data_ptr(), st)
+
+    def tail():
+        L.check(lib.case_sparse_tail(C.byref(a), bms.data_ptr(), bl.data_ptr(), bi.data_ptr(), k2, st), 'sparse')
+    base()
+    for rep in range(2):
+        dbg.zero_()
+        lib.case_debug_sparse_tail_timing(dbg.data_ptr())
+        tail()
+        torch.cuda.synchronize()
+        lib.case_debug_sparse_tail_timing(None)
+        s = dbg.cpu().tolist()
+        print('sparse rep', rep, 'total', s[len(names)] - s[0])
+        for i, n in enumerate(names):
+            print(f'   {n:16s} {s[i + 1] - s[i]:7d} cyc')
+        for w in range(8):
+            ws = s[32 + w * 8: 32 + w * 8 + 6]
+            print(f'   warp {w}: start+{ws[0] - s[1]:6d}  mem0 {ws[1] - ws[0]:6d}  mem1 {ws[2] - ws[1]:6d}  sums {ws[3] - ws[2]:6d}  barrier {ws[4] - ws[3]:6d}  gates {ws[5] - ws[4]:6d}')
+    for name, fn in (('case_vocab_base', base), ('case_sparse_tail', tail)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f'{name:40s} {e0.elapsed_time(e1) / 20 * 1e3:8.1f} us')
+
+
 if __name__ == '__main__':
+    sparse_stamps()
+    sys.exit(0)
     stamps()
     time_it('full (finalize, 2 scatters, top-4)')
     time_it('no finalize', finalize=0)

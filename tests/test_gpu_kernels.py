@@ -346,3 +346,93 @@ def test_row_tail_matches_unfused_kernels(R, W, V, S0, S1, K):
     assert torch.equal(tv_f.cpu(), torch.gather(dist_f[:, :V].cpu(), 1, want))
     agree = (ti_f == ti_r).float().mean().item()
     assert agree > 0.95, agree
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize('R,W,V,S0,S1,K,finalize', [(8, 1, 1000, 12, 40, 1, 1), (12, 4, 30522, 60, 2560, 4, 1),
+                                                     (6, 2, 50000, 7, 333, 2, 1), (8, 8, 5003, 16, 100, 8, 1),
+                                                     (3, 3, 2000, 5, 9, 3, 1), (4, 4, 30522, 60, 10240, 4, 1),
+                                                     (6, 2, 4000, 1, 500, 2, 0)])
+def test_sparse_tail_matches_dense_tail(R, W, V, S0, S1, K, finalize):
+    """case_vocab_base + case_sparse_tail give the top-k of the dense distribution (case_row_tail with dist
+    written out): identical indices, values equal up to the summation order of repeated copy targets.
+    Includes exact base ties, masked positions, ids repeated across both memories, source ids that hit
+    the base top entries, and (finalize = 0) the GTTP form with column 0 masked."""
+    import ctypes as C
+    from case_rg_b200 import _lib as L
+    torch.manual_seed(R * 7919 + V + S1)
+    dev, f32 = 'cuda', dict(dtype=torch.float32, device='cuda')
+    B, H, MS = R // W, 256, L.MAX_SPLIT
+    ldv = -(-V // 8) * 8
+    ns = (1, 3)
+    S = (S0, S1)
+    nmem = 2 if finalize else 1
+    logits = torch.randn(R, ldv, **f32) * 3
+    logits[:, 7] = logits[:, 3]
+    logits[:, 11] = logits[:, 3]                             # exact ties in the base distribution
+    top_ids = logits[:, :V].topk(4, dim=1).indices           # some copy targets ARE base top entries
+    hN = torch.randn(R, H, **f32)
+    Wm, bm = torch.randn(3, 3 * H, **f32) * 0.05, torch.randn(3, **f32)
+    stats = [torch.rand(R, n, 4, **f32) + 0.1 for n in ns]
+    ctxp = [torch.randn(R, n, H, **f32) for n in ns]
+    attn = [torch.randn(R, s, **f32) for s in S]
+    attn[1][:, ::5] = float('-inf')
+    prior = [torch.rand(B, s, **f32) for s in S]
+    smap = torch.randint(0, V, (B, S0 + S1), device=dev, dtype=torch.int32)
+    smap[:, S0:S0 + 3] = smap[:, :1]                         # repeated ids across and inside the memories
+    smap[:, S0 + 3] = top_ids[::W, 0].int()
+    smap[:, S0 + 4] = 0
+    st = torch.cuda.current_stream().cuda_stream
+    gates, fac = torch.rand(R, 4, **f32), torch.rand(R, 2, MS, **f32)
+    fac[:, :, 1] = 0.5
+
+    def args():
+        a = L.TailArgs()
+        a.R, a.V, a.W, a.K, a.ldl, a.ldd, a.mask_col0, a.nmem, a.do_finalize = R, V, W, K, ldv, ldv, 1 - finalize, nmem, finalize
+        a.fac_ld, a.map_ld = 2 * MS, S0 + S1
+        keep = dict(ctx=[torch.zeros(R, H, **f32) for _ in range(2)], gates=gates.clone(), fac=fac.clone(),
+                    tv=torch.zeros(R, K, **f32), ti=torch.zeros(R, K, dtype=torch.int32, device=dev),
+                    dist=torch.zeros(R, ldv, **f32))
+        for i in range(nmem):
+            j = i if finalize else 1                          # GTTP form: one memory (the big one)
+            a.ns[i], a.fac_off[i], a.map_off[i], a.S[i] = ns[j], i * MS, (0, S0)[j], S[j]
+            a.stats[i], a.ctxp[i], a.ctx[i] = stats[j].data_ptr(), ctxp[j].data_ptr(), keep['ctx'][i].data_ptr()
+            a.prior[i], a.attn_un[i] = (prior[j].data_ptr() if finalize else None), attn[j].data_ptr()
+        a.logits, a.hN, a.Wm, a.bm = logits.data_ptr(), hN.data_ptr(), Wm.data_ptr(), bm.data_ptr()
+        a.gates, a.fac, a.map = keep['gates'].data_ptr(), keep['fac'].data_ptr(), smap.data_ptr()
+        a.top_vals, a.top_idx = keep['tv'].data_ptr(), keep['ti'].data_ptr()
+        return a, keep
+
+    lib = L.load()
+    a, dense = args()
+    a.dist = dense['dist'].data_ptr()
+    L.check(lib.case_row_tail(C.byref(a), st), 'case_row_tail')
+    k2 = 2 * K
+    base_ms, base_e = torch.zeros(R, 4, 2, **f32), torch.zeros(R, 4, k2, **f32)
+    base_i = torch.zeros(R, 4, k2, dtype=torch.int32, device=dev)
+    L.call('case_vocab_base', logits.data_ptr(), ldv, R, V, 1 - finalize, k2, base_ms.data_ptr(), base_e.data_ptr(),
+           base_i.data_ptr(), st)
+    a2, sparse = args()
+    L.check(lib.case_sparse_tail(C.byref(a2), base_ms.data_ptr(), base_e.data_ptr(), base_i.data_ptr(), k2, st),
+            'case_sparse_tail')
+    torch.cuda.synchronize()
+    # base statistics against torch
+    lg = logits[:, :V].clone()
+    if not finalize:
+        lg[:, 0] = float('-inf')
+    mrow = base_ms[:, :, 0].max(1).values
+    srow = (base_ms[:, :, 1] * (base_ms[:, :, 0] - mrow[:, None]).exp()).sum(1)
+    assert torch.allclose(mrow, lg.max(1).values)
+    assert torch.allclose(srow, (lg - lg.max(1, keepdim=True).values).exp().sum(1), rtol=1e-5)
+    assert torch.allclose(sparse['gates'], dense['gates'], rtol=1e-5) and torch.allclose(sparse['fac'], dense['fac'], rtol=1e-5)
+    # the dense tile is the reference: exact top-k (value desc, index asc) of it
+    d = dense['dist'][:, :V].double().cpu()
+    want = torch.argsort(torch.argsort(torch.argsort(-d, dim=1, stable=True), dim=1), dim=1)[:, :K]
+    assert torch.equal(dense['ti'].cpu().long(), want)
+    got_i, got_v = sparse['ti'].cpu().long(), sparse['tv'].cpu()
+    ref_v = torch.gather(dense['dist'][:, :V].cpu(), 1, got_i)
+    assert torch.allclose(got_v, ref_v, rtol=1e-5, atol=0), (got_v, ref_v)
+    same = (got_i == want)
+    if not bool(same.all()):   # only allowed where summation order flipped two values that agree to 2 ulp
+        wv = torch.gather(dense['dist'][:, :V].cpu(), 1, want)
+        assert torch.allclose(wv[~same], ref_v[~same], rtol=1e-5, atol=0), (got_i, want)
