@@ -110,6 +110,7 @@ _PROTOS = {
     'case_set_pdl': [i32],
     'case_set_chain': [i32],
     'case_set_fork': [i32],
+    'case_set_additive_impl': [i32],
     'case_set_fused_tail': [i32],
     'case_decode_step': [C.POINTER(StepArgs), i32, vp],
     'gttp_decode_step': [C.POINTER(GttpStepArgs), i32, vp],

@@ -16,8 +16,11 @@
 
 namespace cb {
 
+int g_additive_impl = 3;      // 3 = warp-autonomous kernel, 2 = block-synchronous tiles (A/B)
+
 constexpr int A2T = 256;      // threads
 constexpr int A2K = 32;       // keys per tile
+constexpr int A2_SPLIT = 32;  // key splits are whole tiles of 32 (the fp32 kernels of attention.cu use AATTN_TILE)
 constexpr int A2ULD = H + 8;  // padded bf16 row of the U tile
 
 __device__ __forceinline__ void a2_cp16(uint32_t dst, const void* src, int nbytes) {
@@ -47,7 +50,7 @@ __global__ __launch_bounds__(A2T) void additive_attn_v2_kernel(
   pdl_trigger();
   pdl_wait();
   const int b = blockIdx.x, sp = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int chunk = split_chunk(S, nsplit, AATTN_TILE);
+  const int chunk = split_chunk(S, nsplit, A2_SPLIT);
   const int s_begin = sp * chunk, s_end = min(S, s_begin + chunk);
   const int ntiles = s_end > s_begin ? (s_end - s_begin + A2K - 1) / A2K : 0;
   const int r0 = b * W;
@@ -231,15 +234,286 @@ __global__ __launch_bounds__(A2T) void additive_attn_v2_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------ v3
+// Warp-autonomous form: no block barrier inside the key loop.  A tile is 8 warps x KPT keys; warp w owns
+// keys 4w..4w+3 of every tile and streams exactly those rows (Uk.mem row + value row) into a private
+// double buffer with cp.async - padding keys are neither loaded nor evaluated, at key granularity.
+// Lane l owns hidden units 8l..8l+7 (scores) and value columns 8l..8l+7 (context): per key a lane
+// evaluates 8 x W tanh terms, the 4 x W partial sums of a tile are reduced across the warp with a
+// 16-shuffle multi-value butterfly (lane l ends up with sum number l >> SH), and every warp keeps its
+// own online softmax (max, sum, prior-weighted sum) and context accumulators - merged across the 8
+// warps once, at the end.  The MUFU pipe (one tanh per (row, key, hidden unit)) is the only shared
+// resource the warps contend for.
+template <int WMAX, int DV, bool FAST>
+__global__ __launch_bounds__(A2T) void additive_attn_v3_kernel(
+    const float* __restrict__ qa, const bf16* __restrict__ U, const bf16* __restrict__ Mv,
+    const float* __restrict__ vvec, const uint8_t* __restrict__ mask, const float* __restrict__ prior,
+    const int32_t* __restrict__ tok, int tok_ld, int t, int W, int S, int nsplit, float* __restrict__ scores,
+    float* __restrict__ stats, float* __restrict__ ctx_part) {
+  constexpr int CG = DV / 256;
+  constexpr int KPT = WMAX == 8 ? 2 : 4;               // keys per warp per tile
+  constexpr int NV = KPT * WMAX;                       // partial sums per warp per tile (4, 8, 16)
+  constexpr int LW = WMAX == 1 ? 0 : (WMAX == 2 ? 1 : (WMAX == 4 ? 2 : 3));
+  constexpr int LNV = (KPT == 4 ? 2 : 1) + LW;         // log2(NV)
+  constexpr int SH = 5 - LNV;                          // lane l holds sum number l >> SH
+  constexpr int TILEK = 8 * KPT;
+  constexpr int ROWB = (H + DV) * 2;                   // staged bytes per key: U row, then value row
+  constexpr int WSTAGE = KPT * ROWB;
+  extern __shared__ __align__(128) unsigned char sm[];
+  __shared__ float wst[8][WMAX][3];
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.x, sp = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = split_chunk(S, nsplit, A2_SPLIT);
+  const int s_begin = sp * chunk, s_end = min(S, s_begin + chunk);
+  const int ntiles = s_end > s_begin ? (s_end - s_begin + TILEK - 1) / TILEK : 0;
+  const int r0 = b * W;
+  const uint8_t* mb = mask + (size_t)b * S;
+  const bf16* Ub = U + (size_t)b * S * H;
+  const bf16* Mb = Mv + (size_t)b * S * DV;
+  const float* pb = prior ? prior + (size_t)b * S : nullptr;
+  unsigned char* wbuf = sm + (size_t)warp * 2 * WSTAGE;
+  const uint32_t wbuf_s = smem_u32(wbuf);
+
+  // this lane's slice of the queries and of v
+  float qv[WMAX][8], vv[8];
+#pragma unroll
+  for (int w = 0; w < WMAX; ++w) {
+    const float* q = qa + (size_t)(r0 + min(w, W - 1)) * H + lane * 8;
+    const float4 a0 = *reinterpret_cast<const float4*>(q), a1 = *reinterpret_cast<const float4*>(q + 4);
+    qv[w][0] = a0.x; qv[w][1] = a0.y; qv[w][2] = a0.z; qv[w][3] = a0.w;
+    qv[w][4] = a1.x; qv[w][5] = a1.y; qv[w][6] = a1.z; qv[w][7] = a1.w;
+  }
+  {
+    const float4 a0 = *reinterpret_cast<const float4*>(vvec + lane * 8), a1 = *reinterpret_cast<const float4*>(vvec + lane * 8 + 4);
+    vv[0] = a0.x; vv[1] = a0.y; vv[2] = a0.z; vv[3] = a0.w; vv[4] = a1.x; vv[5] = a1.y; vv[6] = a1.z; vv[7] = a1.w;
+  }
+  // the (key, row) this lane represents after the butterfly
+  const int myj = lane >> SH, myk = myj >> LW, myw = myj & (WMAX - 1);
+  bool rowvalid = myw < W;
+  if (rowvalid && tok) rowvalid = tok[(size_t)(r0 + myw) * tok_ld + t] != 0;
+
+  auto key_of = [&](int ti, int k) { return s_begin + ti * TILEK + warp * KPT + k; };
+  auto valid_bits = [&](int ti) -> unsigned {          // bit k: key k of this warp's group is a real key
+    bool ok = false;
+    if (lane < KPT && ti < ntiles) {
+      const int s = key_of(ti, lane);
+      ok = s < s_end && mb[s] != 0;
+    }
+    return __ballot_sync(0xffffffffu, ok);
+  };
+  auto issue = [&](int ti, int stage, unsigned vb) {
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+      if ((vb >> k) & 1u) {
+        const int s = key_of(ti, k);
+        const uint32_t dst = wbuf_s + stage * WSTAGE + k * ROWB;
+        a2_cp16(dst + lane * 16, Ub + (size_t)s * H + lane * 8, 16);
+#pragma unroll
+        for (int c = 0; c < CG; ++c)
+          a2_cp16(dst + H * 2 + (c * 32 + lane) * 16, Mb + (size_t)s * DV + (c * 32 + lane) * 8, 16);
+      }
+    }
+  };
+
+  float m_run = -INFINITY, l_run = 0.f, lw_run = 0.f;  // statistics of row myw (replicated over its lanes)
+  float acc[WMAX][CG][8];
+#pragma unroll
+  for (int w = 0; w < WMAX; ++w)
+#pragma unroll
+    for (int c = 0; c < CG; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[w][c][i] = 0.f;
+
+  unsigned vb = valid_bits(0);
+  issue(0, 0, vb);
+  a2_commit();
+  for (int ti = 0; ti < ntiles; ++ti) {
+    const int stage = ti & 1;
+    const unsigned vb_next = valid_bits(ti + 1);
+    if (ti + 1 < ntiles) issue(ti + 1, stage ^ 1, vb_next);
+    a2_commit();
+    a2_wait<1>();
+    __syncwarp();
+    const unsigned char* st = wbuf + stage * WSTAGE;
+    // ---- partial scores of this lane's 8 hidden units
+    float part[NV];
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+#pragma unroll
+      for (int w = 0; w < WMAX; ++w) part[k * WMAX + w] = 0.f;
+      if ((vb >> k) & 1u) {
+        float u[8];
+        ld8c(reinterpret_cast<const bf16*>(st + k * ROWB) + lane * 8, u);
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w) {
+          if (w < W) {
+            float e = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float x = qv[w][i] + u[i];
+              e = fmaf(vv[i], FAST ? tanh_fast(x) : tanh_acc(x), e);
+            }
+            part[k * WMAX + w] = e;
+          }
+        }
+      }
+    }
+    // ---- multi-value butterfly: NV sums over 32 lanes in NV - 1 + SH shuffles
+    {
+      int n = NV;
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        if (n > 1) {
+          n >>= 1;
+          const bool hi = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < NV / 2; ++i) {
+            if (i < n) {
+              const float keep = hi ? part[i + n] : part[i];
+              const float send = hi ? part[i] : part[i + n];
+              part[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+        } else {
+          part[0] += __shfl_xor_sync(0xffffffffu, part[0], off);
+        }
+      }
+    }
+    const int skey = key_of(ti, myk);
+    const bool ok = rowvalid && ((vb >> myk) & 1u);
+    const float e = ok ? part[0] : -INFINITY;
+    if ((lane & ((1 << SH) - 1)) == 0 && myw < W && skey < s_end) scores[(size_t)(r0 + myw) * S + skey] = e;
+    // ---- online softmax of row myw over the group's keys (the key index sits in the upper bits of myj)
+    float tmax = e;
+#pragma unroll
+    for (int o = (1 << (SH + LW)); o < 32; o <<= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    const float mn = fmaxf(m_run, tmax);
+    const float sc = (m_run == -INFINITY) ? 0.f : fexp(m_run - mn);
+    const float p = (e == -INFINITY) ? 0.f : fexp(e - mn);
+    float psum = p, pwsum = (pb && ok) ? pb[skey] * p : p;
+#pragma unroll
+    for (int o = (1 << (SH + LW)); o < 32; o <<= 1) {
+      psum += __shfl_xor_sync(0xffffffffu, psum, o);
+      pwsum += __shfl_xor_sync(0xffffffffu, pwsum, o);
+    }
+    l_run = fmaf(l_run, sc, psum);
+    lw_run = fmaf(lw_run, sc, pwsum);
+    m_run = mn;
+    // ---- context: every lane needs all p[k][w] and the rescale factors
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w) {
+      if (w < W) {
+        const float scw = __shfl_sync(0xffffffffu, sc, w << SH);
+#pragma unroll
+        for (int c = 0; c < CG; ++c)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[w][c][i] *= scw;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+      float pk[WMAX];
+#pragma unroll
+      for (int w = 0; w < WMAX; ++w) pk[w] = __shfl_sync(0xffffffffu, p, (k * WMAX + w) << SH);
+      if ((vb >> k) & 1u) {
+#pragma unroll
+        for (int c = 0; c < CG; ++c) {
+          float mv[8];
+          ld8c(reinterpret_cast<const bf16*>(st + k * ROWB + H * 2) + c * 256 + lane * 8, mv);
+#pragma unroll
+          for (int w = 0; w < WMAX; ++w) {
+            if (w < W) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[w][c][i] = fmaf(pk[w], mv[i], acc[w][c][i]);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();                                         // this stage is refilled two iterations from now
+    vb = vb_next;
+  }
+  a2_wait<0>();
+  // ---- merge the 8 warps: statistics, then the contexts through the (now idle) staging memory
+  if ((lane & ((1 << SH) - 1)) == 0 && myk == 0 && myw < W) {
+    wst[warp][myw][0] = m_run; wst[warp][myw][1] = l_run; wst[warp][myw][2] = lw_run;
+  }
+  __syncthreads();
+  float fw[WMAX];                                         // this warp's rescale factor per row
+#pragma unroll
+  for (int w = 0; w < WMAX; ++w) {
+    fw[w] = 0.f;
+    if (w < W) {
+      float Mx = -INFINITY;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) Mx = fmaxf(Mx, wst[g][w][0]);
+      const float mw = wst[warp][w][0];
+      fw[w] = (mw == -INFINITY) ? 0.f : fexp(mw - Mx);
+    }
+  }
+  float* cred = reinterpret_cast<float*>(sm);
+  constexpr int CRED_ROWS = (8 * 2 * WSTAGE) / (8 * DV * 4) < WMAX ? (8 * 2 * WSTAGE) / (8 * DV * 4) : WMAX;
+  for (int w0 = 0; w0 < W; w0 += CRED_ROWS) {
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w) {
+      if (w >= w0 && w < w0 + CRED_ROWS && w < W) {
+#pragma unroll
+        for (int c = 0; c < CG; ++c) {
+          float* d = cred + ((size_t)(warp * CRED_ROWS + (w - w0)) * DV) + c * 256 + lane * 8;
+          *reinterpret_cast<float4*>(d) = make_float4(acc[w][c][0] * fw[w], acc[w][c][1] * fw[w], acc[w][c][2] * fw[w], acc[w][c][3] * fw[w]);
+          *reinterpret_cast<float4*>(d + 4) = make_float4(acc[w][c][4] * fw[w], acc[w][c][5] * fw[w], acc[w][c][6] * fw[w], acc[w][c][7] * fw[w]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < min(CRED_ROWS, W - w0) * DV; i += A2T) {
+      const int wl = i / DV, col = i % DV;
+      float s2 = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) s2 += cred[(size_t)(g * CRED_ROWS + wl) * DV + col];
+      ctx_part[((size_t)(r0 + w0 + wl) * nsplit + sp) * DV + col] = s2;
+    }
+    __syncthreads();
+  }
+  if (tid < W) {
+    float Mx = -INFINITY;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) Mx = fmaxf(Mx, wst[g][tid][0]);
+    float l = 0.f, lw = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float f = (wst[g][tid][0] == -INFINITY) ? 0.f : fexp(wst[g][tid][0] - Mx);
+      l = fmaf(wst[g][tid][1], f, l);
+      lw = fmaf(wst[g][tid][2], f, lw);
+    }
+    float* so = stats + ((size_t)(r0 + tid) * nsplit + sp) * 4;
+    so[0] = Mx; so[1] = l; so[2] = lw; so[3] = 0.f;
+  }
+}
+
 template <int WMAX, int DV, bool FAST>
 static int launch_v2(const float* qa, const void* U, const void* Mv, const float* v, const uint8_t* mask,
                      const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S, int nsplit,
                      float* scores, float* stats, float* ctx_part, cudaStream_t st) {
-  const int chunk = split_chunk(S, nsplit, AATTN_TILE);
-  const size_t smem = (size_t)2 * A2K * A2ULD * 2 + (size_t)2 * A2K * DV * 2 +
-                      sizeof(float) * ((size_t)WMAX * H + H + 8 * WMAX * A2K + WMAX * A2K + 8) +
-                      sizeof(uint32_t) * (size_t)(chunk / A2K + 1);
-  auto kern = additive_attn_v2_kernel<WMAX, DV, FAST>;
+  if (g_additive_impl == 2) {
+    const int chunk = split_chunk(S, nsplit, A2_SPLIT);
+    const size_t smem = (size_t)2 * A2K * A2ULD * 2 + (size_t)2 * A2K * DV * 2 +
+                        sizeof(float) * ((size_t)WMAX * H + H + 8 * WMAX * A2K + WMAX * A2K + 8) +
+                        sizeof(uint32_t) * (size_t)(chunk / A2K + 1);
+    auto kern = additive_attn_v2_kernel<WMAX, DV, FAST>;
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      attr = true;
+    }
+    launch_k(kern, dim3(B, nsplit), A2T, smem, st, qa, (const bf16*)U, (const bf16*)Mv, v, mask, prior, tok, tok_ld, t, W, S,
+                                             nsplit, scores, stats, ctx_part);
+    return check_launch("case_additive_attn(v2)");
+  }
+  constexpr int KPT = WMAX == 8 ? 2 : 4;
+  const size_t smem = (size_t)8 * 2 * KPT * (H + DV) * 2;
+  auto kern = additive_attn_v3_kernel<WMAX, DV, FAST>;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -247,7 +521,7 @@ static int launch_v2(const float* qa, const void* U, const void* Mv, const float
   }
   launch_k(kern, dim3(B, nsplit), A2T, smem, st, qa, (const bf16*)U, (const bf16*)Mv, v, mask, prior, tok, tok_ld, t, W, S,
                                            nsplit, scores, stats, ctx_part);
-  return check_launch("case_additive_attn(v2)");
+  return check_launch("case_additive_attn(v3)");
 }
 
 template <int DV, bool FAST>
@@ -272,4 +546,10 @@ int case_additive_attn_v2(const float* qa, const void* U, const void* Mv, const 
   }
   if (fast_tanh) return dispatch_v2<512, true>(W, qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, S, nsplit, scores, stats, ctx_part, st);
   return dispatch_v2<512, false>(W, qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, S, nsplit, scores, stats, ctx_part, st);
+}
+
+extern "C" int case_set_additive_impl(int impl) {
+  const int old = cb::g_additive_impl;
+  cb::g_additive_impl = impl == 2 ? 2 : 3;
+  return old;
 }

@@ -42,6 +42,25 @@ def _nsplit(units_per_split_group: int, S: int, tile: int, target_ctas: int) -> 
     return int(max(1, min(n, L.MAX_SPLIT, -(-S // tile))))
 
 
+def _nsplit_additive(B: int, S: int, bf16: bool, target_ctas: int = 296) -> int:
+    """Key splits of the additive attention (CTAs = B * nsplit).  bf16 kernel: splits are whole 32-key
+    tiles and 2 CTAs are resident per SM, so pick the split count that minimises
+    (rounds of 296 resident CTAs) x (tiles per split) - at B = 64, S = 2560 that is 9 splits (576 CTAs,
+    two full rounds of 9 tiles) instead of 10 (640 CTAs: a third, mostly empty round).  fp32 kernel:
+    the older rule on 128-key tiles."""
+    if not bf16:
+        return _nsplit(B, S, L.AATTN_TILE, 2 * target_ctas)
+    best, best_cost = 1, None
+    for ns in range(1, L.MAX_SPLIT + 1):
+        chunk = -(-(-(-S // ns)) // 32) * 32
+        if (ns - 1) * chunk >= S:          # the last split would be empty
+            continue
+        cost = -(-(B * ns) // target_ctas) * (chunk // 32)
+        if best_cost is None or cost < best_cost or (cost == best_cost and ns < best):
+            best, best_cost = ns, cost
+    return best
+
+
 def pack_tiled(w: torch.Tensor, dtype) -> torch.Tensor:
     """nn.Linear weight [N, K] -> the kernels' streaming layout (one contiguous run of 16 KB tiles per
     256 output columns).  fp32: [N/256][K][256] for the CUDA-core kernels.  bf16: [N/256][K/32] slabs
@@ -289,7 +308,7 @@ class CaseDecodeEngine(_EngineBase):
             self.nsx = [_nsplit(B, s, 2 * 64, 128) for s in self.S]
         else:                          # SIMT kernel: CTA = (query, head, split)
             self.nsx = [_nsplit(B * L.NH, s, L.XATTN_TILE, 6 * 148) for s in self.S]
-        self.nsa = [_nsplit(B, s, L.AATTN_TILE, 2 * target_ctas) for s in self.S]
+        self.nsa = [_nsplit_additive(B, s, weights.cdtype == L.BF16, target_ctas) for s in self.S]
         # per-batch tensors
         self.feat = z(B, H)
         if weights.cdtype == L.BF16:      # interleaved, swizzled K|V tiles for the tensor-core kernel
@@ -548,7 +567,7 @@ class GttpDecodeEngine(_EngineBase):
                                     device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
         z = lambda *s: torch.zeros(*s, **f32)
-        self.ns = [_nsplit(B, s, L.AATTN_TILE, 2 * target_ctas) for s in (Lc, Lb)]
+        self.ns = [_nsplit_additive(B, s, weights.cdtype == L.BF16, target_ctas) for s in (Lc, Lb)]
         self.U = [torch.zeros(B, s, H, dtype=td, device=dev) for s in (Lc, Lb)]
         self.Mv = [torch.zeros(B, s, 2 * H, dtype=td, device=dev) for s in (Lc, Lb)]
         self.mask = [torch.zeros(B, s, dtype=torch.uint8, device=dev) for s in (Lc, Lb)]

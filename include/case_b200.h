@@ -199,6 +199,10 @@ int case_additive_attn(const float* qa, const void* U, const void* Mv, const flo
                        int nsplit, float* attn_un, float* stats, float* ctx_part, int fast_tanh, int dtype,
                        case_stream_t stream);
 
+/* bf16 additive attention kernel: 3 (default) = warp-autonomous (no block barrier in the key loop, padding
+ * skipped per key), 2 = block-synchronous 32-key tiles; returns the old setting (A/B aid). */
+int case_set_additive_impl(int impl);
+
 /* CaSE row finaliser (Model.py:110-113, 39): hN = LN(h); merges both attentions' partials into
  * ctx0/ctx1, computes the mixture gates softmax(Wm.[hN;ctx0;ctx1]+bm) and, per memory i, the pair
  * (F_i, M_i) = fac[r][i][0..1] such that copy weight(r,i,s) = F_i * prior_i[b,s] * exp(e_i[r,s] - M_i)
