@@ -91,6 +91,9 @@ _PROTOS = {
     'case_layer_chain': [C.POINTER(LayerWeights), C.POINTER(LayerWeights), vp, vp, vp, C.c_float, vp, vp, vp, vp, i32,
                          vp, vp, vp, vp, i32, vp, i32, vp, i32, i32, vp, vp, i32, i32, vp],
     'case_layer_chain_max_tmax': [],
+    'case_layer_stack': [C.POINTER(LayerWeights), i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, C.c_float, vp, vp, vp, i32, vp,
+                         i32, vp, i32, i32, vp, vp, i32, i32, vp],
+    'case_layer_chain_max_s0': [],
     'case_additive_attn': [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp],
     'case_finalize_rows': [vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp],
     'case_vocab_gemm': [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp],
@@ -109,6 +112,7 @@ _PROTOS = {
     'case_gttp_gates': [vp, vp, vp, vp, vp, i32, i32, i32, vp],
     'case_set_pdl': [i32],
     'case_set_chain': [i32],
+    'case_set_stack_fusion': [i32],
     'case_set_fork': [i32],
     'case_set_additive_impl': [i32],
     'case_set_fused_tail': [i32],

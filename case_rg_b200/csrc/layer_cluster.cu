@@ -43,6 +43,9 @@ constexpr int CSCLD = CTMAX + 1;   // score row stride
 constexpr uint32_t CMASKED = 0x40000000u;
 constexpr uint32_t XA_BYTES = CROWS * H * 2, XF_BYTES = CROWS * H * 4;   // payload of one exchange
 
+constexpr int CS0MAX = 64;         // largest first-memory length the in-kernel cross-attention handles (one tile)
+constexpr int CSCLD2 = CS0MAX + 1; // score row stride (covers both the self- and the small cross-attention)
+
 constexpr int OFF_W = 0;
 constexpr int OFF_XA = OFF_W + CNS * CWB;
 constexpr int OFF_LA = OFF_XA + CROWS * CALD * 2;
@@ -50,29 +53,36 @@ constexpr int OFF_XF = OFF_LA + CROWS * CALD * 2;
 constexpr int OFF_OWN = OFF_XF + CROWS * CFLD * 4;
 constexpr int OFF_Q = OFF_OWN + CROWS * CCOL * 4;
 constexpr int OFF_SC = OFF_Q + CROWS * CCOL * 4;
-constexpr int OFF_PAR = OFF_SC + 2 * CROWS * CSCLD * 4;
-constexpr int OFF_PROW = OFF_PAR + (8 * CCOL + 6 * H) * 4;
+constexpr int OFF_PROW = OFF_SC + 2 * CROWS * CSCLD2 * 4;
 constexpr int OFF_BAR = OFF_PROW + CROWS * CTMAX * 4;
 constexpr int OFF_KV = OFF_BAR + 64;           // K history [8 rows][2 heads][Tmax][32] bf16, then V history
+constexpr int CMAXF = 5;           // front halves per launch: up to 4 fused layers + the front that feeds a big cross-attention
+
+struct ChainLayer {                // device pointers of one layer
+  const char* wc;                  // cluster-packed matrices
+  const float *bqkv, *bo, *bq2, *bo2, *b1, *b2, *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
+  bf16* kc; bf16* vc;              // self-attention cache of the layer
+  const bf16* kx;                  // cross-attention K|V tiles of the layer (fused small cross-attention only)
+};
 
 struct ChainArgs {
-  int R, t, Tmax, nsplit, has_back, has_front, first;
-  // back half (layer Lb)
+  int R, t, Tmax, nsplit, has_back, nfront, first, W, S0;
+  // initial back half: merges the partials of the preceding (big) cross-attention
+  ChainLayer back;
   const float* b_in; const float* part_ml; const float* part_acc;
-  const char* wb;
-  const float *bo2, *b1, *b2, *ln3_g, *ln3_b;
-  float* h_out;
-  // front half (layer Lf)
-  const float* h_in;                                   // front-only launch without embedding
-  const float* E; const float* pe; float emb_scale; float* x_out;   // front-only launch with embedding
-  const char* wf;
-  const float *bqkv, *bo, *bq2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
-  bf16* kc; bf16* vc;
+  float* h_out;                    // output rows of the initial back half
+  // front halves layers[0 .. nfront-1]; the first nfront-1 are followed in-kernel by the cross-attention over
+  // the S0 keys of the first memory and by their own back half
+  ChainLayer layers[CMAXF];
+  const uint8_t* mask0;            // [B][S0]
+  float* h_fused_out;              // output rows of the LAST fused layer (the stack output), may be NULL
+  const float* h_in;               // input rows of a launch without back half and without embedding
+  const float* E; const float* pe; float emb_scale; float* x_out;
   const int32_t* anc; int anc_ld;
   const int32_t* tok; int tok_ld;
-  int32_t* prow_g;                                     // [R][Tmax] history row table of this step (may be NULL)
-  float* b_out; float* q2_out;
-  long long* dbg;      // optional stage clock stamps of CTA 0 (case_debug_chain_timing)
+  int32_t* prow_g;                 // [R][Tmax] history row table of this step (may be NULL)
+  float* b_out; float* q2_out;     // outputs of the last front half
+  long long* dbg;                  // optional stage clock stamps of CTA 0 (case_debug_chain_timing)
 };
 
 static long long* g_chain_dbg = nullptr;
@@ -102,6 +112,10 @@ __device__ __forceinline__ void c_bulk(uint32_t dst, const void* src, uint32_t b
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+__device__ __forceinline__ void c_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void c_bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void c_cpasync16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -216,18 +230,26 @@ __device__ __forceinline__ void bcast_bf16(uint32_t xa_local, uint32_t bar_local
   c_st_async16(c_mapa(la, rk), c_mapa(bar_local, rk), x, y, z, w);
 }
 
+// LayerNorm parameters of a lane's 8 columns, requested from global memory BEFORE the exchange they
+// follow is waited for (their latency hides behind the DSMEM hop)
+struct LnPar { float g[8], b[8]; };
+__device__ __forceinline__ LnPar ln_load(const float* __restrict__ g, const float* __restrict__ b) {
+  const int lane = threadIdx.x & 31;
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + lane * 8)), g1 = __ldg(reinterpret_cast<const float4*>(g + lane * 8 + 4));
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + lane * 8)), b1 = __ldg(reinterpret_cast<const float4*>(b + lane * 8 + 4));
+  LnPar p;
+  p.g[0] = g0.x; p.g[1] = g0.y; p.g[2] = g0.z; p.g[3] = g0.w; p.g[4] = g1.x; p.g[5] = g1.y; p.g[6] = g1.z; p.g[7] = g1.w;
+  p.b[0] = b0.x; p.b[1] = b0.y; p.b[2] = b0.z; p.b[3] = b0.w; p.b[4] = b1.x; p.b[5] = b1.y; p.b[6] = b1.z; p.b[7] = b1.w;
+  return p;
+}
 // LayerNorm of the 8 full fp32 rows in xf (warp w: row w) -> bf16 A tile `la`; the CTA's own 64 columns
 // are kept in fp32 (`own`, the residual of the next linear) and optionally stored to gout.
-__device__ __forceinline__ void ln_rows(const float* xf, const float* g, const float* b, bf16* la, float* own, int c,
-                                        float* gout, int r0, int R) {
+__device__ __forceinline__ void ln_rows(const float* xf, const LnPar& lp, bf16* la, float* own, int c, float* gout,
+                                        int r0, int R) {
   const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4 x0 = *reinterpret_cast<const float4*>(xf + i * CFLD + lane * 8);
   const float4 x1 = *reinterpret_cast<const float4*>(xf + i * CFLD + lane * 8 + 4);
-  const float4 g0 = *reinterpret_cast<const float4*>(g + lane * 8), g1 = *reinterpret_cast<const float4*>(g + lane * 8 + 4);
-  const float4 b0 = *reinterpret_cast<const float4*>(b + lane * 8), b1 = *reinterpret_cast<const float4*>(b + lane * 8 + 4);
   const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) s += v[k];
@@ -238,7 +260,7 @@ __device__ __forceinline__ void ln_rows(const float* xf, const float* g, const f
   const float rstd = rsqrtf(warp_sum(q) * (1.f / H) + LN_EPS);
   float y[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) y[k] = (v[k] - mean) * rstd * gg[k] + bb[k];
+  for (int k = 0; k < 8; ++k) y[k] = (v[k] - mean) * rstd * lp.g[k] + lp.b[k];
   *reinterpret_cast<uint4*>(la + i * CALD + lane * 8) =
       make_uint4(c_pack(y[0], y[1]), c_pack(y[2], y[3]), c_pack(y[4], y[5]), c_pack(y[6], y[7]));
   if ((lane >> 3) == c) {
@@ -264,14 +286,15 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
   // MMA / epilogue role: warp = 8-column subtile, lane = (row g, column pair tq)
   const int g = lane >> 2, tq = lane & 3;
   const int er = r0 + g, erl = min(er, a.R - 1);     // rows past R replay row R-1 and store nothing
-  const int ecol = CCOL * c + 8 * warp + 2 * tq;     // global column of the lane's pair
+  const int lcol = 8 * warp + 2 * tq;                // the lane's column pair inside the CTA slice
+  const int ecol = CCOL * c + lcol;                  // ... and in the full row
   // attention role: 16 lanes per (row, local head)
   const int ai = tid >> 5, ahl = (tid >> 4) & 1, acp = tid & 15;
   const int arl = min(r0 + ai, a.R - 1);
 
   int dbg_n = 0;
   auto stamp = [&]() {
-    if (a.dbg != nullptr && blockIdx.x == 0 && tid == 0) a.dbg[dbg_n++] = clock64();
+    if (a.dbg != nullptr && blockIdx.x == 0 && tid == 0 && dbg_n < 60) a.dbg[dbg_n++] = clock64();
   };
   stamp();
   const uint32_t s_base = smem_u32(sm);
@@ -283,16 +306,18 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
   float* own = reinterpret_cast<float*>(sm + OFF_OWN);
   float* q_s = reinterpret_cast<float*>(sm + OFF_Q);
   float* sc = reinterpret_cast<float*>(sm + OFF_SC);
-  float* par = reinterpret_cast<float*>(sm + OFF_PAR);   // 8 bias slices of 64, then 6 LN vectors of 256
   uint32_t* prow = reinterpret_cast<uint32_t*>(sm + OFF_PROW);
   bf16* kh_s = reinterpret_cast<bf16*>(sm + OFF_KV);
   bf16* vh_s = kh_s + (size_t)CROWS * 2 * Tmax * 32;
 
-  // ---- weight sequence of this launch: [Wo2 W1 W2] then [Wq Wk Wv Wo Wq2]
+  // ---- weight sequence of this launch: [Wo2 W1 W2 of the initial back half], then the matrices of the
+  // fused layers in natural order (Wq Wk Wv Wo Wq2 | Wo2 W1 W2), then Wq Wk Wv Wo Wq2 of the last front
   const int nback = a.has_back ? 3 : 0;
-  const int nseq = nback + (a.has_front ? 5 : 0);
+  const int nseq = nback + (a.nfront > 0 ? 8 * (a.nfront - 1) + 5 : 0);
   auto seq_ptr = [&](int k) -> const char* {
-    return k < nback ? a.wb + (size_t)(c * 8 + 5 + k) * CWB : a.wf + (size_t)(c * 8 + (k - nback)) * CWB;
+    if (k < nback) return a.back.wc + (size_t)(c * 8 + 5 + k) * CWB;
+    const int kk = k - nback;
+    return a.layers[kk >> 3].wc + (size_t)(c * 8 + (kk & 7)) * CWB;
   };
   int issued = 0;                                    // thread 0 only
   auto refill = [&](int consumed) {
@@ -321,6 +346,9 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
     ++ph_xf;
     if (tid == 0) c_mb_expect(s_bxf, XF_BYTES);
   };
+  auto bias2 = [&](const float* bvec) -> float2 {    // the lane's two bias entries (requested early, used late)
+    return __ldg(reinterpret_cast<const float2*>(bvec + ecol));
+  };
 
   if (tid == 0) {
     for (int s = 0; s < 5; ++s) c_mb_init(s_bar + 8 * s, 1);
@@ -331,28 +359,10 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
   __syncthreads();
   refill(0);
 
-  // ---- constants: bias slices and LayerNorm vectors
-  {
-    const float* bsrc[8] = {a.bqkv, a.bqkv ? a.bqkv + H : nullptr, a.bqkv ? a.bqkv + 2 * H : nullptr, a.bo, a.bq2,
-                            a.bo2, a.b1, a.b2};
-#pragma unroll
-    for (int m2 = 0; m2 < 2; ++m2) {
-      const int idx = tid + m2 * CT, m = idx >> 6, k = idx & 63;
-      par[idx] = bsrc[m] ? __ldg(bsrc[m] + CCOL * c + k) : 0.f;
-    }
-    const float* lsrc[6] = {a.ln1_g, a.ln1_b, a.ln2_g, a.ln2_b, a.ln3_g, a.ln3_b};
-#pragma unroll
-    for (int m2 = 0; m2 < 6; ++m2) par[8 * CCOL + m2 * H + tid] = lsrc[m2] ? __ldg(lsrc[m2] + tid) : 0.f;
-  }
-  const float* b_q = par, *b_k = par + 64, *b_v = par + 128, *b_o = par + 192, *b_q2 = par + 256, *b_o2 = par + 320;
-  const float* b_1 = par + 384, *b_2 = par + 448;
-  const float* ln1g = par + 512, *ln1b = ln1g + H, *ln2g = ln1b + H, *ln2b = ln2g + H, *ln3g = ln2b + H, *ln3b = ln3g + H;
-  const int lcol = 8 * warp + 2 * tq;                // the lane's column pair inside the CTA slice
-
   // ---- KV-cache history of heads 2c, 2c+1 for the 8 rows -> shared memory (positions 0..t-1), and the
   // table prow[row][j] = physical row | masked bit for j = 0..t.  The first launch of a step derives it
   // from anc/tok (written by the launch right before it, hence after the wait) and publishes it.
-  auto load_history = [&](bool derive) {
+  auto load_prow = [&](bool derive) {
     for (int idx = tid; idx < CROWS * (t + 1); idx += CT) {
       const int ii = idx / (t + 1), j = idx - ii * (t + 1);
       const int rr = min(r0 + ii, a.R - 1);
@@ -365,19 +375,25 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
         pv = (uint32_t)a.prow_g[(size_t)rr * Tmax + j];
       }
       prow[ii * CTMAX + j] = pv;
+    }
+  };
+  auto load_history = [&](const bf16* kc, const bf16* vc) {   // needs prow (same thread wrote the entries it reads)
+    for (int idx = tid; idx < CROWS * (t + 1); idx += CT) {
+      const int ii = idx / (t + 1), j = idx - ii * (t + 1);
       if (j < t) {
+        const uint32_t pv = prow[ii * CTMAX + j];
         const size_t goff = ((size_t)(pv & ~CMASKED) * Tmax + j) * H + CCOL * c;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {   // chunks 0..3: head 2c, 4..7: head 2c+1
           const uint32_t soff = (uint32_t)((((ii * 2 + (q >> 2)) * Tmax + j) * 32 + (q & 3) * 8) * 2);
-          c_cpasync16(smem_u32(kh_s) + soff, a.kc + goff + q * 8);
-          c_cpasync16(smem_u32(vh_s) + soff, a.vc + goff + q * 8);
+          c_cpasync16(smem_u32(kh_s) + soff, kc + goff + q * 8);
+          c_cpasync16(smem_u32(vh_s) + soff, vc + goff + q * 8);
         }
       }
     }
   };
-  const bool early_hist = a.has_front && !a.first && a.prow_g != nullptr;
-  if (early_hist) load_history(false);
+  const bool early_hist = a.nfront > 0 && !a.first && a.prow_g != nullptr;
+  if (early_hist) { load_prow(false); load_history(a.layers[0].kc, a.layers[0].vc); }
 
   float2 bres = make_float2(0.f, 0.f);               // residual b of the cross-attention block (own columns)
   if (a.has_back) bres = *reinterpret_cast<const float2*>(a.b_in + (size_t)erl * H + ecol);
@@ -388,8 +404,48 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
   stamp();
 
   int consumed = 0;
+  // ---- back half of a layer after its cross-attention context has been exchanged into XA:
+  // h2 = b + ctx.Wo2 + bo2; c = LN3(h2); h3 = c + W2.gelu(W1.c + b1) + b2 (TransformerDecoder.py:82-89)
+  auto back_half = [&](const ChainLayer& Lb, float2 b_res, float* hdst, bool feed_front) {
+    const float2 bo2 = bias2(Lb.bo2), b1v = bias2(Lb.b1), b2v = bias2(Lb.b2);
+    const LnPar ln3 = ln_load(Lb.ln3_g, Lb.ln3_b);
+    wait_xa();
+    stamp();
+    {
+      const float2 d = mma_cols8(s_xa, wait_w(consumed), warp);
+      bcast_f32(s_xf, s_bxf, c, b_res.x + d.x + bo2.x, b_res.y + d.y + bo2.y);
+      __syncthreads();
+      ++consumed;
+      refill(consumed);
+    }
+    wait_xf();
+    stamp();
+    ln_rows(xf, ln3, la, own, c, nullptr, r0, a.R);
+    __syncthreads();
+    stamp();
+    {
+      const float2 d = mma_cols8(s_la, wait_w(consumed), warp);
+      bcast_bf16(s_xa, s_bxa, g, CCOL * c + 8 * warp, c_pack(gelu_erf(d.x + b1v.x), gelu_erf(d.y + b1v.y)));
+      __syncthreads();
+      ++consumed;
+      refill(consumed);
+    }
+    wait_xa();
+    stamp();
+    {
+      const float2 d = mma_cols8(s_xa, wait_w(consumed), warp);
+      const float2 cres = *reinterpret_cast<const float2*>(own + g * CCOL + lcol);
+      const float h0 = cres.x + d.x + b2v.x, h1 = cres.y + d.y + b2v.y;
+      if (hdst != nullptr && er < a.R) *reinterpret_cast<float2*>(hdst + (size_t)er * H + ecol) = make_float2(h0, h1);
+      if (feed_front) bcast_f32(s_xf, s_bxf, c, h0, h1);
+      __syncthreads();
+      ++consumed;
+      refill(consumed);
+    }
+  };
+
   if (a.has_back) {
-    // ---- B0: merge the cross-attention partials of heads 2c, 2c+1, broadcast ctx (bf16)
+    // ---- merge the (big) cross-attention partials of heads 2c, 2c+1, broadcast ctx (bf16)
     {
       const int ns = a.nsplit;
       const size_t pb = ((size_t)arl * NH + 2 * c + ahl) * ns;
@@ -420,45 +476,8 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
       const float inv = Z > 0.f ? 1.f / Z : 0.f;
       bcast_bf16(s_xa, s_bxa, ai, CCOL * c + 32 * ahl + 8 * (acp >> 2), c_pack(c0 * inv, c1 * inv));
     }
-    wait_xa();
-    stamp();
-    // ---- B1: h2 = b + ctx.Wo2 + bo2 -> fp32 broadcast
-    {
-      const float2 d = mma_cols8(s_xa, wait_w(consumed), warp);
-      bcast_f32(s_xf, s_bxf, c, bres.x + d.x + b_o2[lcol], bres.y + d.y + b_o2[lcol + 1]);
-      __syncthreads();
-      ++consumed;
-      refill(consumed);
-    }
-    wait_xf();
-    stamp();
-    // ---- B2: c = LN3(h2)
-    ln_rows(xf, ln3g, ln3b, la, own, c, nullptr, r0, a.R);
-    __syncthreads();
-    stamp();
-    // ---- B3: gelu(c.W1 + b1) -> bf16 broadcast
-    {
-      const float2 d = mma_cols8(s_la, wait_w(consumed), warp);
-      bcast_bf16(s_xa, s_bxa, g, CCOL * c + 8 * warp, c_pack(gelu_erf(d.x + b_1[lcol]), gelu_erf(d.y + b_1[lcol + 1])));
-      __syncthreads();
-      ++consumed;
-      refill(consumed);
-    }
-    wait_xa();
-    stamp();
-    // ---- B4: h3 = c + f.W2 + b2 -> global (own columns) and fp32 broadcast
-    {
-      const float2 d = mma_cols8(s_xa, wait_w(consumed), warp);
-      const float2 cres = *reinterpret_cast<const float2*>(own + g * CCOL + lcol);
-      const float h0 = cres.x + d.x + b_2[lcol], h1 = cres.y + d.y + b_2[lcol + 1];
-      if (er < a.R) *reinterpret_cast<float2*>(a.h_out + (size_t)er * H + ecol) = make_float2(h0, h1);
-      if (a.has_front) bcast_f32(s_xf, s_bxf, c, h0, h1);
-      __syncthreads();
-      ++consumed;
-      refill(consumed);
-    }
-    if (!a.has_front) return;          // uniform over the cluster; nothing is in flight towards this CTA
-    wait_xf();
+    back_half(a.back, bres, a.h_out, a.nfront > 0);
+    if (a.nfront == 0) return;         // uniform over the cluster; nothing is in flight towards this CTA
   } else {
     // first layer of the step: every CTA builds all 8 input rows locally (no exchange)
     for (int idx = tid; idx < CROWS * (H / 4); idx += CT) {
@@ -478,126 +497,261 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
       }
       *reinterpret_cast<float4*>(xf + ii * CFLD + k4 * 4) = x;
     }
-    __syncthreads();
   }
-  if (!early_hist) load_history(a.first || a.prow_g == nullptr);
+  if (!early_hist) { load_prow(a.first || a.prow_g == nullptr); load_history(a.layers[0].kc, a.layers[0].vc); }
 
-  stamp();
-  // ---- F0: a = LN1(h)
-  ln_rows(xf, ln1g, ln1b, la, own, c, nullptr, r0, a.R);
-  __syncthreads();
-  stamp();
-  // ---- F1: q | k | v of heads 2c, 2c+1 (warp w: the same 8 columns of all three)
-  {
-    const uint32_t wqkv[3] = {wait_w(consumed), wait_w(consumed + 1), wait_w(consumed + 2)};
-    float2 qkv[3];
-    mma_cols8x3(s_la, wqkv, warp, qkv);
-    const float2 dq = qkv[0], dk = qkv[1], dv = qkv[2];
-    *reinterpret_cast<float2*>(q_s + g * CCOL + lcol) = make_float2(dq.x + b_q[lcol], dq.y + b_q[lcol + 1]);
-    const uint32_t kp = c_pack(dk.x + b_k[lcol], dk.y + b_k[lcol + 1]);
-    const uint32_t vp = c_pack(dv.x + b_v[lcol], dv.y + b_v[lcol + 1]);
-    const int hl = warp >> 2, dcol = lcol & 31;
-    *reinterpret_cast<uint32_t*>(kh_s + (size_t)((g * 2 + hl) * Tmax + t) * 32 + dcol) = kp;
-    *reinterpret_cast<uint32_t*>(vh_s + (size_t)((g * 2 + hl) * Tmax + t) * 32 + dcol) = vp;
-    if (er < a.R) {
-      const size_t goff = ((size_t)er * Tmax + t) * H + ecol;
-      *reinterpret_cast<uint32_t*>(a.kc + goff) = kp;
-      *reinterpret_cast<uint32_t*>(a.vc + goff) = vp;
+  for (int f = 0; f < a.nfront; ++f) {
+    const ChainLayer& Lf = a.layers[f];
+    const bool fused = f + 1 < a.nfront;             // followed in-kernel by the small cross-attention + back half
+    if (fused) {
+      // this (row, head)'s K|V tile of the fused cross-attention -> L2, long before it is read
+      const char* tile = reinterpret_cast<const char*>(Lf.kx) + ((size_t)(arl / a.W) * NH + 2 * c + ahl) * 8192;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c_prefetch_l2(tile + (acp * 4 + q) * 128);
+      // the next layer's matrices -> L2 (one cluster asks, every cluster hits)
+      if (blockIdx.x < CL && tid < 8) c_bulk_prefetch_l2(a.layers[f + 1].wc + (size_t)(c * 8 + tid) * CWB, CWB);
     }
-    c_cpasync_wait_all();
+    // ================= front half (TransformerDecoder.py:76-80)
+    const LnPar ln1 = ln_load(Lf.ln1_g, Lf.ln1_b);
+    const float2 bq = bias2(Lf.bqkv), bk = bias2(Lf.bqkv + H), bv = bias2(Lf.bqkv + 2 * H);
+    if (f > 0 || a.has_back) wait_xf(); else __syncthreads();
+    stamp();
+    // ---- F0: a = LN1(h)
+    ln_rows(xf, ln1, la, own, c, nullptr, r0, a.R);
     __syncthreads();
-    consumed += 3;
-    refill(consumed);
-  }
-  stamp();
-  // ---- F2: self-attention of (row ai, head 2c + ahl) over positions 0..t (16 lanes), ctx -> bf16 broadcast
-  {
-    const float* qr = q_s + ai * CCOL + 32 * ahl;
-    float qv[32];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float4 x = *reinterpret_cast<const float4*>(qr + k * 4);
-      qv[4 * k] = x.x; qv[4 * k + 1] = x.y; qv[4 * k + 2] = x.z; qv[4 * k + 3] = x.w;
-    }
-    const bf16* kb = kh_s + (size_t)(ai * 2 + ahl) * Tmax * 32;
-    const bf16* vb = vh_s + (size_t)(ai * 2 + ahl) * Tmax * 32;
-    float* scr = sc + (ai * 2 + ahl) * CSCLD;
-    float sv[3];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      const int j = acp + 16 * u;
-      sv[u] = -INFINITY;
-      if (j <= t) {
-        const uint4* kr = reinterpret_cast<const uint4*>(kb + (size_t)j * 32);
-        float d = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 x = kr[q];
-          const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            d = fmaf(qv[q * 8 + 2 * e], __uint_as_float(w4[e] << 16), d);
-            d = fmaf(qv[q * 8 + 2 * e + 1], __uint_as_float(w4[e] & 0xffff0000u), d);
-          }
-        }
-        sv[u] = (prow[ai * CTMAX + j] & CMASKED) ? -INFINITY : d;
+    stamp();
+    // ---- F1: q | k | v of heads 2c, 2c+1 (warp w: the same 8 columns of all three)
+    {
+      const uint32_t wqkv[3] = {wait_w(consumed), wait_w(consumed + 1), wait_w(consumed + 2)};
+      float2 qkv[3];
+      mma_cols8x3(s_la, wqkv, warp, qkv);
+      *reinterpret_cast<float2*>(q_s + g * CCOL + lcol) = make_float2(qkv[0].x + bq.x, qkv[0].y + bq.y);
+      const uint32_t kp = c_pack(qkv[1].x + bk.x, qkv[1].y + bk.y);
+      const uint32_t vp = c_pack(qkv[2].x + bv.x, qkv[2].y + bv.y);
+      const int hl = warp >> 2, dcol = lcol & 31;
+      *reinterpret_cast<uint32_t*>(kh_s + (size_t)((g * 2 + hl) * Tmax + t) * 32 + dcol) = kp;
+      *reinterpret_cast<uint32_t*>(vh_s + (size_t)((g * 2 + hl) * Tmax + t) * 32 + dcol) = vp;
+      if (er < a.R) {
+        const size_t goff = ((size_t)er * Tmax + t) * H + ecol;
+        *reinterpret_cast<uint32_t*>(Lf.kc + goff) = kp;
+        *reinterpret_cast<uint32_t*>(Lf.vc + goff) = vp;
       }
-      mx = fmaxf(mx, sv[u]);
+      c_cpasync_wait_all();
+      __syncthreads();
+      consumed += 3;
+      refill(consumed);
     }
+    stamp();
+    const float2 bo = bias2(Lf.bo), bq2 = bias2(Lf.bq2);
+    const LnPar ln2 = ln_load(Lf.ln2_g, Lf.ln2_b);
+    // ---- F2: self-attention of (row ai, head 2c + ahl) over positions 0..t (16 lanes), ctx -> bf16 broadcast
+    {
+      const float* qr = q_s + ai * CCOL + 32 * ahl;
+      float qv[32];
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
+      for (int k = 0; k < 8; ++k) {
+        const float4 x = *reinterpret_cast<const float4*>(qr + k * 4);
+        qv[4 * k] = x.x; qv[4 * k + 1] = x.y; qv[4 * k + 2] = x.z; qv[4 * k + 3] = x.w;
+      }
+      const bf16* kb = kh_s + (size_t)(ai * 2 + ahl) * Tmax * 32;
+      const bf16* vb = vh_s + (size_t)(ai * 2 + ahl) * Tmax * 32;
+      float* scr = sc + (ai * 2 + ahl) * CSCLD2;
+      float sv[3];
+      float mx = -INFINITY;
 #pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      const int j = acp + 16 * u;
-      const float p = (sv[u] == -INFINITY) ? 0.f : fexp(sv[u] - mx);
-      sum += p;
-      if (j <= t) scr[j] = p;
-    }
+      for (int u = 0; u < 3; ++u) {
+        const int j = acp + 16 * u;
+        sv[u] = -INFINITY;
+        if (j <= t) {
+          const uint4* kr = reinterpret_cast<const uint4*>(kb + (size_t)j * 32);
+          float d = 0.f;
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    __syncwarp();
-    float c0 = 0.f, c1 = 0.f, d0 = 0.f, d1 = 0.f;
-    int j = 0;
-    for (; j + 1 <= t; j += 2) {
-      const float p0 = scr[j], p1 = scr[j + 1];
-      const uint32_t x0 = *reinterpret_cast<const uint32_t*>(vb + (size_t)j * 32 + 2 * acp);
-      const uint32_t x1 = *reinterpret_cast<const uint32_t*>(vb + (size_t)(j + 1) * 32 + 2 * acp);
-      c0 = fmaf(p0, __uint_as_float(x0 << 16), c0);
-      c1 = fmaf(p0, __uint_as_float(x0 & 0xffff0000u), c1);
-      d0 = fmaf(p1, __uint_as_float(x1 << 16), d0);
-      d1 = fmaf(p1, __uint_as_float(x1 & 0xffff0000u), d1);
+          for (int q = 0; q < 4; ++q) {
+            const uint4 x = kr[q];
+            const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              d = fmaf(qv[q * 8 + 2 * e], __uint_as_float(w4[e] << 16), d);
+              d = fmaf(qv[q * 8 + 2 * e + 1], __uint_as_float(w4[e] & 0xffff0000u), d);
+            }
+          }
+          sv[u] = (prow[ai * CTMAX + j] & CMASKED) ? -INFINITY : d;
+        }
+        mx = fmaxf(mx, sv[u]);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f;
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int j = acp + 16 * u;
+        const float p = (sv[u] == -INFINITY) ? 0.f : fexp(sv[u] - mx);
+        sum += p;
+        if (j <= t) scr[j] = p;
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      __syncwarp();
+      float c0 = 0.f, c1 = 0.f, d0 = 0.f, d1 = 0.f;
+      int j = 0;
+      for (; j + 1 <= t; j += 2) {
+        const float p0 = scr[j], p1 = scr[j + 1];
+        const uint32_t x0 = *reinterpret_cast<const uint32_t*>(vb + (size_t)j * 32 + 2 * acp);
+        const uint32_t x1 = *reinterpret_cast<const uint32_t*>(vb + (size_t)(j + 1) * 32 + 2 * acp);
+        c0 = fmaf(p0, __uint_as_float(x0 << 16), c0);
+        c1 = fmaf(p0, __uint_as_float(x0 & 0xffff0000u), c1);
+        d0 = fmaf(p1, __uint_as_float(x1 << 16), d0);
+        d1 = fmaf(p1, __uint_as_float(x1 & 0xffff0000u), d1);
+      }
+      if (j <= t) {
+        const float p0 = scr[j];
+        const uint32_t x0 = *reinterpret_cast<const uint32_t*>(vb + (size_t)j * 32 + 2 * acp);
+        c0 = fmaf(p0, __uint_as_float(x0 << 16), c0);
+        c1 = fmaf(p0, __uint_as_float(x0 & 0xffff0000u), c1);
+      }
+      const float inv = sum > 0.f ? 1.f / sum : 0.f;
+      bcast_bf16(s_xa, s_bxa, ai, CCOL * c + 32 * ahl + 8 * (acp >> 2), c_pack((c0 + d0) * inv, (c1 + d1) * inv));
     }
-    if (j <= t) {
-      const float p0 = scr[j];
-      const uint32_t x0 = *reinterpret_cast<const uint32_t*>(vb + (size_t)j * 32 + 2 * acp);
-      c0 = fmaf(p0, __uint_as_float(x0 << 16), c0);
-      c1 = fmaf(p0, __uint_as_float(x0 & 0xffff0000u), c1);
+    wait_xa();
+    stamp();
+    // ---- F3: h1 = a + ctx.Wo + bo -> fp32 broadcast
+    {
+      const float2 d = mma_cols8(s_xa, wait_w(consumed), warp);
+      const float2 ares = *reinterpret_cast<const float2*>(own + g * CCOL + lcol);
+      bcast_f32(s_xf, s_bxf, c, ares.x + d.x + bo.x, ares.y + d.y + bo.y);
+      __syncthreads();                 // every warp is past the self-attention: the history buffers are free
+      ++consumed;
+      refill(consumed);
+      if (fused) load_history(a.layers[f + 1].kc, a.layers[f + 1].vc);   // next layer's history, far ahead of its use
     }
-    const float inv = sum > 0.f ? 1.f / sum : 0.f;
-    bcast_bf16(s_xa, s_bxa, ai, CCOL * c + 32 * ahl + 8 * (acp >> 2), c_pack((c0 + d0) * inv, (c1 + d1) * inv));
-  }
-  wait_xa();
-  stamp();
-  // ---- F3: h1 = a + ctx.Wo + bo -> fp32 broadcast
-  {
-    const float2 d = mma_cols8(s_xa, wait_w(consumed), warp);
-    const float2 ares = *reinterpret_cast<const float2*>(own + g * CCOL + lcol);
-    bcast_f32(s_xf, s_bxf, c, ares.x + d.x + b_o[lcol], ares.y + d.y + b_o[lcol + 1]);
-    ++consumed;
-  }
-  wait_xf();
-  stamp();
-  // ---- F4: b = LN2(h1) (own columns -> global: the residual of the next launch's back half)
-  ln_rows(xf, ln2g, ln2b, la, own, c, a.b_out, r0, a.R);
-  __syncthreads();
-  stamp();
-  // ---- F5: q2 = b.Wq2 + bq2 (pre-scaled) -> global, consumed by the cross-attention
-  {
-    const float2 d = mma_cols8(s_la, wait_w(consumed), warp);
-    if (er < a.R)
-      *reinterpret_cast<float2*>(a.q2_out + (size_t)er * H + ecol) = make_float2(d.x + b_q2[lcol], d.y + b_q2[lcol + 1]);
+    wait_xf();
+    stamp();
+    // ---- F4: b = LN2(h1) (own columns: the residual of this layer's back half)
+    ln_rows(xf, ln2, la, own, c, fused ? nullptr : a.b_out, r0, a.R);
+    __syncthreads();
+    stamp();
+    // ---- F5: q2 = b.Wq2 + bq2 (pre-scaled): to global for a big cross-attention, or kept for the fused one
+    {
+      const float2 d = mma_cols8(s_la, wait_w(consumed), warp);
+      const float2 q2v = make_float2(d.x + bq2.x, d.y + bq2.y);
+      if (!fused) {
+        if (er < a.R) *reinterpret_cast<float2*>(a.q2_out + (size_t)er * H + ecol) = q2v;
+        break;
+      }
+      *reinterpret_cast<float2*>(q_s + g * CCOL + lcol) = q2v;
+      __syncthreads();
+      ++consumed;
+      refill(consumed);
+    }
+    stamp();
+    // ================= fused cross-attention over the S0 keys of the first memory (TransformerDecoder.py:81)
+    // K|V tiles of (query, head): bf16 [2][64 keys][32], 16-byte chunks at chunk ^ ((key >> 1) & 3); read
+    // straight from L2 (3.75 KB each), 16 lanes per (row, head) as in the self-attention
+    {
+      const int S0 = a.S0, bq_ = arl / a.W;
+      const char* kt = reinterpret_cast<const char*>(Lf.kx) + ((size_t)bq_ * NH + 2 * c + ahl) * 8192;
+      const char* vt = kt + 4096;
+      const uint8_t* mk = a.mask0 + (size_t)bq_ * S0;
+      const float* qr = q_s + ai * CCOL + 32 * ahl;
+      float qv[32];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 x = *reinterpret_cast<const float4*>(qr + k * 4);
+        qv[4 * k] = x.x; qv[4 * k + 1] = x.y; qv[4 * k + 2] = x.z; qv[4 * k + 3] = x.w;
+      }
+      float* scr = sc + (ai * 2 + ahl) * CSCLD2;
+      float sv[4];
+      float mx = -INFINITY;
+      {
+        uint4 kk[4][4];                              // every K chunk of the lane's (up to) 4 keys in flight at once
+        bool okk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = acp + 16 * u, jj = min(j, S0 - 1);
+          okk[u] = j < S0 && mk[jj] != 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            kk[u][q] = __ldg(reinterpret_cast<const uint4*>(kt + jj * 64 + ((q ^ ((jj >> 1) & 3)) << 4)));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float d = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t w4[4] = {kk[u][q].x, kk[u][q].y, kk[u][q].z, kk[u][q].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              d = fmaf(qv[q * 8 + 2 * e], __uint_as_float(w4[e] << 16), d);
+              d = fmaf(qv[q * 8 + 2 * e + 1], __uint_as_float(w4[e] & 0xffff0000u), d);
+            }
+          }
+          sv[u] = okk[u] ? d : -INFINITY;
+          mx = fmaxf(mx, sv[u]);
+        }
+      }
+      // V: lane (chunk cg = acp & 3, key group kg = acp >> 2) loads the 16-byte chunk cg of keys kg, kg+4, ..
+      // (all in flight at once); issued before the softmax so their latency overlaps it
+      const int cg = acp & 3, kg = acp >> 2;
+      uint4 vv[CS0MAX / 4];
+#pragma unroll
+      for (int u = 0; u < CS0MAX / 4; ++u) {
+        const int j = min(kg + 4 * u, S0 - 1);
+        vv[u] = __ldg(reinterpret_cast<const uint4*>(vt + j * 64 + ((cg ^ ((j >> 1) & 3)) << 4)));
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = acp + 16 * u;
+        const float p = (sv[u] == -INFINITY) ? 0.f : fexp(sv[u] - mx);
+        sum += p;
+        if (j < S0) scr[j] = p;
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      __syncwarp();
+      float cacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dims 8 cg .. 8 cg + 7 over this lane's keys
+#pragma unroll
+      for (int u = 0; u < CS0MAX / 4; ++u) {
+        const int j = kg + 4 * u;
+        const float p = j < S0 ? scr[j] : 0.f;
+        const uint32_t w4[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          cacc[2 * e] = fmaf(p, __uint_as_float(w4[e] << 16), cacc[2 * e]);
+          cacc[2 * e + 1] = fmaf(p, __uint_as_float(w4[e] & 0xffff0000u), cacc[2 * e + 1]);
+        }
+      }
+      // sum the four key groups (lanes acp ^ 4, acp ^ 8), then lane (cg, kg) keeps dims 8 cg + 2 kg, +1,
+      // which is exactly its column pair 2 acp' of the broadcast layout with acp' = 4 cg + kg
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        cacc[e] += __shfl_xor_sync(0xffffffffu, cacc[e], 4);
+        cacc[e] += __shfl_xor_sync(0xffffffffu, cacc[e], 8);
+      }
+      const float c0 = kg == 0 ? cacc[0] : (kg == 1 ? cacc[2] : (kg == 2 ? cacc[4] : cacc[6]));
+      const float c1 = kg == 0 ? cacc[1] : (kg == 1 ? cacc[3] : (kg == 2 ? cacc[5] : cacc[7]));
+      const float inv = sum > 0.f ? 1.f / sum : 0.f;
+      // this lane now holds columns 32 ahl + 8 cg + 2 kg: the quad (same cg... no: same acp' >> 2 = cg) covers 8 columns
+      {
+        const int acpp = 4 * cg + kg;                // position of the lane's pair in the head's 16 pairs
+        // gather the quad's four pairs in pair order: lanes with the same cg and kg = 0..3 are acp = cg, cg+4, cg+8, cg+12
+        const uint32_t packed = c_pack(c0 * inv, c1 * inv);
+        const int base16 = lane & 16;
+        const uint32_t x = __shfl_sync(0xffffffffu, packed, base16 + cg), y = __shfl_sync(0xffffffffu, packed, base16 + cg + 4);
+        const uint32_t z = __shfl_sync(0xffffffffu, packed, base16 + cg + 8), w = __shfl_sync(0xffffffffu, packed, base16 + cg + 12);
+        const uint32_t la_ = s_xa + (uint32_t)(ai * CALD + CCOL * c + 32 * ahl + 8 * cg) * 2;
+        const uint32_t rk = (uint32_t)kg;           // lane (cg, kg) feeds rank kg with the quad's 16 bytes
+        c_st_async16(c_mapa(la_, rk), c_mapa(s_bxa, rk), x, y, z, w);
+        (void)acpp;
+      }
+    }
+    // ================= back half of the same layer; its residual b is the own-column LN2 output
+    {
+      const float2 b_own = *reinterpret_cast<const float2*>(own + g * CCOL + lcol);
+      back_half(Lf, b_own, f + 2 == a.nfront ? a.h_fused_out : nullptr, true);
+    }
   }
   stamp();
 }
@@ -607,7 +761,8 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
 using namespace cb;
 
 extern "C" int case_layer_chain_max_tmax(void) { return CTMAX; }
-/* debugging aid (not part of the stable ABI): device buffer of >= 32 int64 that receives the clock64()
+extern "C" int case_layer_chain_max_s0(void) { return CS0MAX; }
+/* debugging aid (not part of the stable ABI): device buffer of >= 64 int64 that receives the clock64()
  * stamps of CTA 0 at every stage boundary of the next case_layer_chain launches; NULL switches it off */
 extern "C" int case_debug_chain_timing(void* buf) { g_chain_dbg = (long long*)buf; return 0; }
 
@@ -626,6 +781,35 @@ extern "C" int case_debug_chain_max_clusters(int smem, int cluster) {
   return e == cudaSuccess ? n : -(int)e;
 }
 
+static void fill_layer(ChainLayer& L, const case_layer_weights_t* w, void* kc, void* vc, const void* kx) {
+  L.wc = reinterpret_cast<const char*>(w->Wc);
+  L.bqkv = w->bqkv; L.bo = w->bo; L.bq2 = w->bq2; L.bo2 = w->bo2; L.b1 = w->b1; L.b2 = w->b2;
+  L.ln1_g = w->ln1_g; L.ln1_b = w->ln1_b; L.ln2_g = w->ln2_g; L.ln2_b = w->ln2_b; L.ln3_g = w->ln3_g; L.ln3_b = w->ln3_b;
+  L.kc = (bf16*)kc; L.vc = (bf16*)vc; L.kx = (const bf16*)kx;
+}
+
+static int launch_chain(ChainArgs& a, cudaStream_t stream) {
+  a.dbg = g_chain_dbg;
+  const size_t smem = (size_t)OFF_KV + (a.nfront > 0 ? (size_t)4 * CROWS * a.Tmax * 64 : 0);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(layer_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OFF_KV + 4 * CROWS * CTMAX * 64);
+    attr = true;
+  }
+  const int nclusters = (a.R + CROWS - 1) / CROWS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nclusters * CL); cfg.blockDim = dim3(CT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 2 : 1;
+  void* pa[] = {(void*)&a};
+  g_launch_err = cudaLaunchKernelExC(&cfg, (const void*)layer_chain_kernel, pa);
+  return check_launch("case_layer_chain");
+}
+
 extern "C" int case_layer_chain(const case_layer_weights_t* wb, const case_layer_weights_t* wf, const float* h_in,
                                 const float* E, const float* pe, float emb_scale, float* x_out, const float* b_in,
                                 const float* part_ml, const float* part_acc, int nsplit, float* h_out, void* kcache,
@@ -639,37 +823,39 @@ extern "C" int case_layer_chain(const case_layer_weights_t* wb, const case_layer
   CB_REQUIRE(wb || h_in || (E && x_out), "case_layer_chain: a front-only launch needs h_in or (E, x_out)");
   ChainArgs a;
   memset(&a, 0, sizeof(a));
-  a.R = R; a.t = t; a.Tmax = Tmax; a.nsplit = nsplit; a.has_back = wb != nullptr; a.has_front = wf != nullptr;
-  a.first = first;
-  a.dbg = g_chain_dbg;
+  a.R = R; a.t = t; a.Tmax = Tmax; a.nsplit = nsplit; a.has_back = wb != nullptr; a.nfront = wf != nullptr ? 1 : 0;
+  a.first = first; a.W = 1; a.S0 = 1;
   if (wb) {
-    a.b_in = b_in; a.part_ml = part_ml; a.part_acc = part_acc; a.wb = reinterpret_cast<const char*>(wb->Wc);
-    a.bo2 = wb->bo2; a.b1 = wb->b1; a.b2 = wb->b2; a.ln3_g = wb->ln3_g; a.ln3_b = wb->ln3_b; a.h_out = h_out;
+    fill_layer(a.back, wb, nullptr, nullptr, nullptr);
+    a.b_in = b_in; a.part_ml = part_ml; a.part_acc = part_acc; a.h_out = h_out;
   }
   if (wf) {
+    fill_layer(a.layers[0], wf, kcache, vcache, nullptr);
     a.h_in = h_in; a.E = E; a.pe = pe; a.emb_scale = emb_scale; a.x_out = x_out;
-    a.wf = reinterpret_cast<const char*>(wf->Wc);
-    a.bqkv = wf->bqkv; a.bo = wf->bo; a.bq2 = wf->bq2; a.ln1_g = wf->ln1_g; a.ln1_b = wf->ln1_b;
-    a.ln2_g = wf->ln2_g; a.ln2_b = wf->ln2_b;
-    a.kc = (bf16*)kcache; a.vc = (bf16*)vcache; a.anc = anc; a.anc_ld = anc_ld; a.tok = tok; a.tok_ld = tok_ld;
-    a.prow_g = prow; a.b_out = b_out; a.q2_out = q2_out;
+    a.anc = anc; a.anc_ld = anc_ld; a.tok = tok; a.tok_ld = tok_ld; a.prow_g = prow; a.b_out = b_out; a.q2_out = q2_out;
   }
-  const size_t smem = (size_t)OFF_KV + (wf ? (size_t)4 * CROWS * Tmax * 64 : 0);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(layer_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OFF_KV + 4 * CROWS * CTMAX * 64);
-    attr = true;
+  return launch_chain(a, (cudaStream_t)stream);
+}
+
+extern "C" int case_layer_stack(const case_layer_weights_t* layers, int nfused, void* const* kcache, void* const* vcache,
+                                const void* const* kx, const uint8_t* mask0, int W, int S0, const float* h_in,
+                                const float* E, const float* pe, float emb_scale, float* x_out, float* h_fused_out,
+                                const int32_t* anc, int anc_ld, const int32_t* tok, int tok_ld, int32_t* prow, int t,
+                                int Tmax, float* b_out, float* q2_out, int R, int first, case_stream_t stream) {
+  CB_REQUIRE(layers && kcache && vcache && nfused >= 1 && nfused < CMAXF, "case_layer_stack: 1..4 fused layers");
+  CB_REQUIRE(R > 0 && Tmax >= 1 && Tmax <= CTMAX && t >= 0 && t < Tmax, "case_layer_stack: bad R / t / Tmax (Tmax <= 48)");
+  CB_REQUIRE(kx && mask0 && W >= 1 && S0 >= 1 && S0 <= CS0MAX, "case_layer_stack: the fused cross-attention handles S0 <= 64 keys");
+  CB_REQUIRE(h_in || (E && x_out), "case_layer_stack: needs h_in or (E, x_out)");
+  CB_REQUIRE(anc && tok && b_out && q2_out, "case_layer_stack: null pointer");
+  ChainArgs a;
+  memset(&a, 0, sizeof(a));
+  a.R = R; a.t = t; a.Tmax = Tmax; a.nsplit = 1; a.has_back = 0; a.nfront = nfused + 1; a.first = first; a.W = W; a.S0 = S0;
+  for (int f = 0; f <= nfused; ++f) {
+    CB_REQUIRE(layers[f].Wc && kcache[f] && vcache[f] && (f == nfused || kx[f]), "case_layer_stack: layer pointers missing");
+    fill_layer(a.layers[f], &layers[f], kcache[f], vcache[f], f < nfused ? kx[f] : nullptr);
   }
-  const int nclusters = (R + CROWS - 1) / CROWS;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(nclusters * CL); cfg.blockDim = dim3(CT); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute at[2];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 2 : 1;
-  void* pa[] = {(void*)&a};
-  g_launch_err = cudaLaunchKernelExC(&cfg, (const void*)layer_chain_kernel, pa);
-  return check_launch("case_layer_chain");
+  a.mask0 = mask0; a.h_fused_out = h_fused_out;
+  a.h_in = h_in; a.E = E; a.pe = pe; a.emb_scale = emb_scale; a.x_out = x_out;
+  a.anc = anc; a.anc_ld = anc_ld; a.tok = tok; a.tok_ld = tok_ld; a.prow_g = prow; a.b_out = b_out; a.q2_out = q2_out;
+  return launch_chain(a, (cudaStream_t)stream);
 }

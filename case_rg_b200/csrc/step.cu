@@ -12,6 +12,7 @@ static thread_local char g_err[512] = "ok";
 int g_use_pdl = 1;
 int g_use_chain = 1;
 int g_use_fork = 1;
+int g_use_stack = 1;
 int g_use_tail = 2;
 // side stream + events for the fork/join inside a step (created on first use, outside any capture: the
 // engines run one uncaptured warm-up step before they capture)
@@ -62,6 +63,11 @@ extern "C" int case_set_chain(int on) {
 extern "C" int case_set_fused_tail(int on) {
   const int old = g_use_tail;
   g_use_tail = on < 0 ? 0 : (on > 2 ? 2 : on);
+  return old;
+}
+extern "C" int case_set_stack_fusion(int on) {
+  const int old = g_use_stack;
+  g_use_stack = on ? 1 : 0;
   return old;
 }
 extern "C" int case_set_fork(int on) {
@@ -152,7 +158,30 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
     // so they run on a side stream: attns[0] beside the whole second stack, attns[1] beside norm1 ->
     // gen.0 -> vocabulary GEMM (fork/join by events, captured into the graph like any other edge).
     const bool fork = g_use_fork && a->h0 != nullptr && a->qa1 != nullptr && aux_ready();
-    for (int L = 0; L <= 8; ++L) {
+    // the whole first stack (4 layers over the S0 <= 64 keys of the query memory, cross-attention included)
+    // plus the first half-layer of the second stack is ONE launch; otherwise one launch per half-layer pair
+    const bool stack0 = g_use_stack && a->S[0] <= case_layer_chain_max_s0();
+    int Lstart = 0;
+    if (stack0) {
+      float* hdst0 = fork ? a->h0 : a->h;
+      void* kcs[5]; void* vcs[5]; const void* kxs[4];
+      for (int l = 0; l < 5; ++l) { kcs[l] = a->kcache[l]; vcs[l] = a->vcache[l]; }
+      for (int l = 0; l < 4; ++l) kxs[l] = a->Kx[l];
+      TRY(case_layer_stack(a->layers, 4, kcs, vcs, kxs, a->mask[0], W, a->S[0], nullptr, a->E, a->pe, 16.0f, a->x_in, hdst0,
+                           anc, TL, a->tok, TL, a->prow, t, a->Tmax, a->bbuf, a->q2, R, 1, st));
+      if (fork) {
+        CUTRY(cudaEventRecord(g_ev_fork[0], st));
+        CUTRY(cudaStreamWaitEvent(g_aux, g_ev_fork[0], 0));
+        TRY(stack_attention(0, hdst0, a->qa, g_aux));
+        CUTRY(cudaEventRecord(g_ev_join[0], g_aux));
+      } else {
+        TRY(stack_attention(0, hdst0, a->qa, st));
+      }
+      TRY(case_cross_attn_partial_tc(a->q2, a->Kx[4], a->mask[1], B, W, a->S[1], a->nsplit_x[1], a->part_ml, a->part_acc,
+                                     st));
+      Lstart = 5;
+    }
+    for (int L = Lstart; L <= 8; ++L) {
       const case_layer_weights_t* wb = L > 0 ? &a->layers[L - 1] : nullptr;
       const case_layer_weights_t* wf = L < 8 ? &a->layers[L] : nullptr;
       float* hdst = (L == 4 && fork) ? a->h0 : a->h;

@@ -462,11 +462,17 @@ class CaseDecodeEngine(_EngineBase):
 
     def kernel_launches_per_step(self) -> int:
         # (+1 in bench.py: the activation re-pack inside the vocabulary GEMM call)
-        if self.w.cdtype == L.BF16 and self.Tmax <= L.load().case_layer_chain_max_tmax():
-            # 9 x layer_chain + 8 x cross + 2 x (row_linear, additive) + norm1 + gen.0 + vocab + row_tail + select
-            return 9 + 8 + 4 + 1 + 1 + 1 + 1 + 1
-        # embed + 8 x (front, cross, back) + 2 x (row_linear, additive) + norm1 + gen.0 + vocab + row_tail + select
-        return 1 + 24 + 4 + 1 + 1 + 1 + 1 + 1
+        lib = L.load()
+        tail = 3                       # vocab_base + sparse_tail + select
+        if self.w.cdtype == L.BF16 and self.Tmax <= lib.case_layer_chain_max_tmax():
+            if self.S[0] <= lib.case_layer_chain_max_s0():
+                # layer_stack (first stack + front 4) + 4 x cross + 4 x layer_chain + 2 x (row_linear, additive)
+                # + norm1 + gen.0 + vocab + tail
+                return 1 + 4 + 4 + 4 + 1 + 1 + 1 + tail
+            # 9 x layer_chain + 8 x cross + 2 x (row_linear, additive) + norm1 + gen.0 + vocab + tail
+            return 9 + 8 + 4 + 1 + 1 + 1 + tail
+        # embed + 8 x (front, cross, back) + 2 x (row_linear, additive) + norm1 + gen.0 + vocab + tail
+        return 1 + 24 + 4 + 1 + 1 + 1 + tail
 
 
 class CaseEngineGroup:

@@ -57,6 +57,8 @@ int case_set_pdl(int on);
 /* Cluster layer kernels (case_layer_chain) in case_decode_step for bf16 storage (default on; 0 = the
  * row-block kernels case_layer_front / case_layer_back); returns the old setting. */
 int case_set_chain(int on);
+/* Fuse the first stack (short memory, S0 <= 64) into one case_layer_stack launch (default on). */
+int case_set_stack_fusion(int on);
 /* Fork/join of the additive attentions onto a library-owned side stream inside case_decode_step
  * (cluster path only; default on); returns the old setting. */
 int case_set_fork(int on);
@@ -183,6 +185,22 @@ int case_layer_chain(const case_layer_weights_t* wb, const case_layer_weights_t*
                      void* vcache, const int32_t* anc, int anc_ld, const int32_t* tok, int tok_ld, int32_t* prow,
                      int t, int Tmax, float* b_out, float* q2_out, int R, int first, case_stream_t stream);
 int case_layer_chain_max_tmax(void);
+
+/* A whole decoder stack over a SHORT memory in one cluster launch: for f = 0 .. nfused-1 the first half
+ * of layers[f], the cross-attention over the S0 <= case_layer_chain_max_s0() keys of that memory (K|V
+ * tiles kx[f] in the case_cross_attn_partial_tc layout, mask0 uint8 [B][S0], W rows per query) and the
+ * second half of layers[f] - then the first half of layers[nfused], whose b_out / q2_out feed the next
+ * (big) cross-attention launch.  Replaces 2 * nfused + 1 launches (CaSE: the whole query-memory stack,
+ * TransformerDecoder.py:191-218 with num_layers = 4, plus the first half-layer of the passage stack).
+ * Input rows as in case_layer_chain (h_in, or the embedding when E != NULL); h_fused_out (may be NULL)
+ * receives the output rows of layer nfused-1, i.e. the stack output.  kcache / vcache: nfused + 1
+ * pointers, kx: nfused pointers; all layers need Wc. */
+int case_layer_stack(const case_layer_weights_t* layers, int nfused, void* const* kcache, void* const* vcache,
+                     const void* const* kx, const uint8_t* mask0, int W, int S0, const float* h_in, const float* E,
+                     const float* pe, float emb_scale, float* x_out, float* h_fused_out, const int32_t* anc,
+                     int anc_ld, const int32_t* tok, int tok_ld, int32_t* prow, int t, int Tmax, float* b_out,
+                     float* q2_out, int R, int first, case_stream_t stream);
+int case_layer_chain_max_s0(void);
 
 /* ---------------------------------------------------------------- additive ("bilinear") attention */
 
