@@ -505,6 +505,11 @@ class CaseEngineGroup:
     def decode(self, max_len: int, mode: int = L.MODE_MODULE_GREEDY, use_graph: bool = True) -> torch.Tensor:
         if mode != L.MODE_BEAM and self.W != 1:
             raise ValueError('greedy modes need an engine built with W == 1')
+        self.launch(max_len, mode, use_graph)
+        return self._finish_tokens(max_len, mode)
+
+    @torch.no_grad()
+    def launch(self, max_len: int, mode: int = L.MODE_MODULE_GREEDY, use_graph: bool = True) -> None:
         for sub in self.subs:                      # captures (host-synchronous) happen before anything runs
             sub.ensure_graph(max_len, mode, use_graph)
         main = torch.cuda.current_stream(self.device)
@@ -514,6 +519,8 @@ class CaseEngineGroup:
                 sub.launch(max_len, mode, use_graph)
         for st in self.streams:
             main.wait_stream(st)
+
+    def _finish_tokens(self, max_len: int, mode: int) -> torch.Tensor:
         out = torch.cat([sub.state.out_tokens[:, :max_len] for sub in self.subs]).to(torch.int64)
         if mode == L.MODE_BEAM:                    # merge1D (Utils.py:366-377): pad to the longest answer of the batch
             Lmax = int(torch.stack([sub.state.best_len.max() for sub in self.subs]).max().item())

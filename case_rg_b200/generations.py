@@ -43,6 +43,22 @@ def beam(model, data, vocab2id=None, max_len=20, width=5, encode_outputs=None, i
     return model.fast_search(data, max_len, width, L.MODE_BEAM, encode_outputs, init_decoder_states)
 
 
+def beam_batches(model, batches, vocab2id=None, max_len=20, width=5):
+    """``beam`` over an iterable of HOST batches, the way the predict loop feeds a model one batch after
+    another (common/CumulativeTrainer.py:141-156): yields the answers of every batch, in order, as host
+    LongTensors.  The host-to-device copy of batch i+1 runs on a copy stream while batch i is decoding
+    (double-buffered staging, pinned host tensors copy asynchronously), so the PCIe time of the encoder
+    outputs (175 MB per batch at the BASELINE shape) is hidden behind the decode."""
+    _check_vocab(vocab2id)
+    return model.search_batches(batches, max_len, width, L.MODE_BEAM)
+
+
+def greedy_batches(model, batches, vocab2id=None, max_len=20):
+    """``greedy`` over an iterable of host batches with the copy of the next batch overlapped (see beam_batches)."""
+    _check_vocab(vocab2id)
+    return model.search_batches(batches, max_len, 1, L.MODE_PROTO_GREEDY)
+
+
 class _FastModel:
     beam_width = 1
     max_dec_len = 40
@@ -102,6 +118,64 @@ class FastCaSE(_FastModel):
                     d['answer_rep'], d['source_map'])
         self.last_engine = eng
         return eng.decode(max_len, mode, use_graph=self.use_graph)
+
+    _KEYS = ('mem_q', 'mem_p', 'query', 'passage', 'prior_q', 'prior_p', 'answer_rep', 'source_map')
+
+    def search_batches(self, batches, max_len, width, mode):
+        """Generator behind beam_batches / greedy_batches."""
+        dev = self.weights.device
+        main = torch.cuda.current_stream(dev)
+        copy = torch.cuda.Stream(dev)
+        staging = [None, None]              # two sets of device buffers, reused while the shapes repeat
+        prefilled = [None, None]            # event: the prefill that last read staging set k has finished
+
+        def stage(k, host):
+            shapes = {n: (tuple(host[n].shape), host[n].dtype) for n in self._KEYS}
+            with torch.cuda.stream(copy):
+                if staging[k] is None or staging[k][0] != shapes:
+                    # allocated ON the copy stream: a block the allocator recycles from the main stream's pool
+                    # (e.g. a prefill temporary that was freed on the host but is still being read on the
+                    # device) must never be handed to a buffer the copy stream writes
+                    staging[k] = (shapes, {n: torch.empty(host[n].shape, dtype=host[n].dtype, device=dev)
+                                           for n in self._KEYS})
+                if prefilled[k] is not None:
+                    copy.wait_event(prefilled[k])
+                for n in self._KEYS:
+                    staging[k][1][n].copy_(host[n], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return ev
+
+        it = iter(batches)
+        nxt = next(it, None)
+        k = 0
+        ready = stage(0, nxt) if nxt is not None else None
+        pending = None                      # engine whose decode is in flight
+        while nxt is not None:
+            d = staging[k][1]
+            B = d['source_map'].size(0)
+            S0 = d['mem_q'].reshape(B, -1, L.H).size(1)
+            S1 = d['mem_p'].reshape(B, -1, L.H).size(1)
+            eng = self.engine_for(B, width, S0, S1, max_len, self.streams)
+            # stream order: decode(i-1) -> prefill(i); the host enqueues prefill(i) while decode(i-1) runs.
+            # (prefill never touches the search state the pending answers are read from)
+            main.wait_event(ready)
+            eng.prefill(d['mem_q'], d['mem_p'], d['query'].ne(0), d['passage'].ne(0), d['prior_q'], d['prior_p'],
+                        d['answer_rep'], d['source_map'])
+            prefilled[k] = torch.cuda.Event()
+            prefilled[k].record(main)
+            nxt = next(it, None)
+            if nxt is not None:             # the next batch starts crossing PCIe before this one decodes
+                ready = stage(k ^ 1, nxt)
+            if pending is not None:         # answers of the previous batch (host sync), then reuse its state
+                yield pending._finish_tokens(max_len, mode).cpu()
+            if mode != L.MODE_BEAM and eng.W != 1:
+                raise ValueError('greedy modes need an engine built with W == 1')
+            eng.launch(max_len, mode, use_graph=self.use_graph)
+            self.last_engine = pending = eng
+            k ^= 1
+        if pending is not None:
+            yield pending._finish_tokens(max_len, mode).cpu()
 
     def module_greedy(self, data, max_len):
         """The in-module loop of CaSETransformerSeqDecoder.forward (no EOS handling, Model.py:91-123)."""

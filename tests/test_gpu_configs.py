@@ -119,3 +119,21 @@ def test_stream_sliced_batch_gives_the_same_answers(B, W, streams, dtype):
         n = min(a.size(1), b.size(1))
         same = sum(int(torch.equal(a[i, :n], b[i, :n])) for i in range(B))
         assert same >= B - 1, (a, b)
+
+
+@pytest.mark.timeout(300)
+def test_streamed_batches_equal_single_calls():
+    """generations.beam_batches (next batch's H2D overlapped with the current decode, double-buffered
+    staging) returns, batch by batch, exactly what generations.beam returns for that batch alone."""
+    from case_rg_b200 import generations as FG
+    V, T, W, B = 3000, 8, 4, 6
+    sd = syn.make_case_decoder_state(71, V, 256, peaked=0.3, boost={syn.EOS: 8.0}, gen_gate_bias=2.0)
+    model = FG.FastCaSE(sd, device='cuda:0', dtype='bf16')
+    hosts = [syn.make_case_inputs(80 + i, B, 24, 3, 50, V, 256).pin() for i in range(4)]
+    keys = ('mem_q', 'mem_p', 'query', 'passage', 'prior_q', 'prior_p', 'answer_rep', 'source_map')
+    as_dict = lambda h: {k: getattr(h, k) for k in keys}
+    want = [FG.beam(model, _case_data(h), None, T, W).cpu() for h in hosts]
+    got = list(FG.beam_batches(model, (as_dict(h) for h in hosts), None, T, W))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.device.type == 'cpu' and torch.equal(g, w), (g, w)
