@@ -338,11 +338,19 @@ def roofline(model, eng, args, torch):
     eng = eng.subs[0] if hasattr(eng, 'subs') else eng    # the launch shape of one stream's slice
     B, W, S1 = eng.B, eng.W, eng.S[1]
     esz = 2 if eng.w.cdtype == L.BF16 else 4
-    alg = B * 2 * S1 * L.H * esz
+    compact = bool(getattr(eng, 'compact', False))
+    # algorithmic bytes: K and V of every key the attention needs, once per query;
+    # with the compacted memory that is the VALID keys only (padding is dropped at prefill)
+    nkeys = int(eng.xcount.sum().item()) if compact else B * S1
+    alg = nkeys * 2 * L.H * esz
     st = torch.cuda.current_stream()
     reps = 20
     def launch(l):
-        if eng.w.cdtype == L.BF16:
+        if compact:
+            L.call('case_cross_attn_part', eng.q2.data_ptr(), eng.Kx[l].data_ptr(), eng.xcount.data_ptr(),
+                   eng.xprefix.data_ptr(), B, W, S1, eng.xslots, eng.part_ml.data_ptr(), eng.part_acc.data_ptr(),
+                   st.cuda_stream)
+        elif eng.w.cdtype == L.BF16:
             L.call('case_cross_attn_partial_tc', eng.q2.data_ptr(), eng.Kx[l].data_ptr(), eng.mask[1].data_ptr(), B, W,
                    S1, eng.nsx[1], eng.part_ml.data_ptr(), eng.part_acc.data_ptr(), st.cuda_stream)
         else:
@@ -363,8 +371,9 @@ def roofline(model, eng, args, torch):
     ach = alg / (us * 1e-6) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed
     # `ncu --set full` capture (profiles/r1_top_kernels_ncu_summary.txt): 168.3 MB read + 5.4 MB written
-    traffic = 173.7e6 * B / 64 if (eng.w.cdtype == L.BF16 and (W, S1) == (4, 2560)) else None
-    return dict(kernel='cross_attn_mma_kernel (passage memory)' if eng.w.cdtype == L.BF16 else 'cross_attn_partial_kernel (passage memory)', bound='hbm', achieved=ach, peak=peak, unit='GB/s',
+    traffic = None      # filled from the committed `ncu --set full` capture of this kernel (profiles/)
+    kname = 'cross_attn_part_kernel (passage memory, valid keys)' if compact else ('cross_attn_mma_kernel (passage memory)' if eng.w.cdtype == L.BF16 else 'cross_attn_partial_kernel (passage memory)')
+    return dict(kernel=kname, bound='hbm', achieved=ach, peak=peak, unit='GB/s',
                 frac=ach / peak, traffic=traffic, peak_source=which, algorithmic_bytes_per_launch=alg,
                 us_per_launch=us, launches_per_decode_step=4)
 

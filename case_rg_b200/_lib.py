@@ -61,7 +61,7 @@ class StepArgs(C.Structure):
                 ('out_tokens', vp), ('n_live', vp),
                 ('x_in', vp), ('h', vp), ('bbuf', vp), ('q2', vp), ('part_ml', vp), ('part_acc', vp), ('qa', vp),
                 ('attn_un', vp * 2), ('stats', vp * 2), ('ctxp', vp * 2), ('hN', vp), ('ctx', vp * 2), ('gates', vp),
-                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp), ('prow', vp), ('h0', vp), ('qa1', vp), ('base_ms', vp), ('base_e', vp), ('base_i', vp)]
+                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp), ('prow', vp), ('h0', vp), ('qa1', vp), ('base_ms', vp), ('base_e', vp), ('base_i', vp), ('xcount', vp), ('xprefix', vp), ('xslots', i32)]
 
 
 class GttpStepArgs(C.Structure):
@@ -87,6 +87,9 @@ _PROTOS = {
     'case_cross_attn_partial': [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp],
     'case_cross_attn_partial_tc': [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp],
     'case_pack_kv_tiles': [vp, i32, i32, i32, i32, i32, vp, vp],
+    'case_pack_kv_tiles_gather': [vp, i32, i32, i32, vp, vp, i32, vp, vp],
+    'case_cross_attn_part': [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp],
+    'case_cross_attn_part_slots': [i32],
     'case_layer_back': [vp, vp, vp, i32, C.POINTER(LayerWeights), vp, i32, i32, vp],
     'case_layer_chain': [C.POINTER(LayerWeights), C.POINTER(LayerWeights), vp, vp, vp, C.c_float, vp, vp, vp, vp, i32,
                          vp, vp, vp, vp, i32, vp, i32, vp, i32, i32, vp, vp, i32, i32, vp],

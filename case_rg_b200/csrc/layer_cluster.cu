@@ -450,22 +450,22 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
       const int ns = a.nsplit;
       const size_t pb = ((size_t)arl * NH + 2 * c + ahl) * ns;
       float M = -INFINITY, Z = 0.f, c0 = 0.f, c1 = 0.f;
-      for (int jb = 0; jb < ns; jb += 4) {
-        float2 ml[4], pa[4];
+      for (int jb = 0; jb < ns; jb += 8) {        // 16 loads in flight per round
+        float2 ml[8], pa[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const int j = min(jb + u, ns - 1);
           ml[u] = *reinterpret_cast<const float2*>(a.part_ml + (pb + j) * 2);
           pa[u] = *reinterpret_cast<const float2*>(a.part_acc + (pb + j) * HD + 2 * acp);
         }
         float bm = -INFINITY;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) bm = fmaxf(bm, ml[u].x);
+        for (int u = 0; u < 8; ++u) bm = fmaxf(bm, ml[u].x);
         const float Mn = fmaxf(M, bm);
         const float rs = (M == -INFINITY) ? 0.f : fexp(M - Mn);
         Z *= rs; c0 *= rs; c1 *= rs;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const float e = (jb + u < ns && ml[u].x != -INFINITY) ? fexp(ml[u].x - Mn) : 0.f;
           Z = fmaf(ml[u].y, e, Z);
           c0 = fmaf(pa[u].x, e, c0);

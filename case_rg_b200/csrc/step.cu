@@ -151,6 +151,17 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
   const int k2 = 2 * W;
   const bool sparse = g_use_tail == 2 && !a->materialize_only && a->base_ms && a->base_e && a->base_i && a->V >= k2 &&
                       a->S[0] + a->S[1] <= case_sparse_tail_max_sources();
+  // cross-attention over memory i for layer L: compacted + balanced partition where the prefill provided it
+  const bool xpart = dt == CASE_BF16 && a->xcount != nullptr && a->xprefix != nullptr && a->xslots > 0;
+  auto big_xattn = [&](int L) -> int {
+    const int i = L / 4;
+    if (i == 1 && xpart)
+      return case_cross_attn_part(a->q2, a->Kx[L], a->xcount, a->xprefix, B, W, a->S[1], a->xslots, a->part_ml, a->part_acc,
+                                  st);
+    return case_cross_attn_partial_tc(a->q2, a->Kx[L], a->mask[i], B, W, a->S[i], a->nsplit_x[i], a->part_ml,
+                                      a->part_acc, st);
+  };
+  auto nparts_of = [&](int L) -> int { return (L / 4 == 1 && xpart) ? a->xslots : a->nsplit_x[L / 4]; };
   const bool chain = dt == CASE_BF16 && g_use_chain && a->layers[0].Wc != nullptr && a->Tmax <= case_layer_chain_max_tmax();
   if (chain) {
     // Cluster kernels: [embed + front 0] x [back 0 + front 1] x ... x [back 7], one launch between
@@ -177,8 +188,7 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       } else {
         TRY(stack_attention(0, hdst0, a->qa, st));
       }
-      TRY(case_cross_attn_partial_tc(a->q2, a->Kx[4], a->mask[1], B, W, a->S[1], a->nsplit_x[1], a->part_ml, a->part_acc,
-                                     st));
+      TRY(big_xattn(4));
       Lstart = 5;
     }
     for (int L = Lstart; L <= 8; ++L) {
@@ -186,7 +196,7 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       const case_layer_weights_t* wf = L < 8 ? &a->layers[L] : nullptr;
       float* hdst = (L == 4 && fork) ? a->h0 : a->h;
       TRY(case_layer_chain(wb, wf, nullptr, a->E, a->pe, 16.0f /* sqrt(256) */, a->x_in, a->bbuf, a->part_ml,
-                           a->part_acc, L > 0 ? a->nsplit_x[(L - 1) / 4] : 1, hdst, wf ? a->kcache[L] : nullptr,
+                           a->part_acc, L > 0 ? nparts_of(L - 1) : 1, hdst, wf ? a->kcache[L] : nullptr,
                            wf ? a->vcache[L] : nullptr, anc, TL, a->tok, TL, a->prow, t, a->Tmax, a->bbuf, a->q2, R,
                            L == 0, st));
       if (L == 4 || L == 8) {
@@ -201,9 +211,7 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
         }
       }
       if (L == 8) break;
-      const int i = L / 4;
-      TRY(case_cross_attn_partial_tc(a->q2, a->Kx[L], a->mask[i], B, W, a->S[i], a->nsplit_x[i], a->part_ml,
-                                     a->part_acc, st));
+      TRY(big_xattn(L));
     }
     TRY(case_layernorm_rows(a->h, a->lnN_g, a->lnN_b, a->hN, R, st));
     TRY(gen0());
@@ -221,10 +229,9 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       const int L = i * 4 + l;
       TRY(case_layer_front(hin, &a->layers[L], a->kcache[L], a->vcache[L], anc, TL, a->tok, TL, t, a->Tmax,
                            a->bbuf, a->q2, R, dt, st));
-      int nparts = a->nsplit_x[i];
-      if (dt == CASE_BF16) {   // tensor-core tiles
-        TRY(case_cross_attn_partial_tc(a->q2, a->Kx[L], a->mask[i], B, W, a->S[i], a->nsplit_x[i], a->part_ml,
-                                       a->part_acc, st));                 // Kx holds the interleaved K|V tiles
+      int nparts = nparts_of(L);
+      if (dt == CASE_BF16) {   // tensor-core tiles (Kx holds the interleaved K|V tiles)
+        TRY(big_xattn(L));
       } else {
         TRY(case_cross_attn_partial(a->q2, a->Kx[L], a->Vx[L], a->mask[i], B, W, a->S[i], a->nsplit_x[i],
                                     a->part_ml, a->part_acc, dt, st));

