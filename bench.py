@@ -57,7 +57,7 @@ def config_dict(args, extra=None):
              queries_per_gpu=args.batch, beam=args.beam, passages=WORKLOAD['NP'], passage_len=WORKLOAD['Lp'],
              query_len=WORKLOAD['Lq'], max_target_length=WORKLOAD['T'], vocab=WORKLOAD['V'],
              parallelism=f'queries sharded x{args.gpus}, no data-path collective',
-             l2='per-step K/V + Uk.mem streams (0.86 GB) exceed the 126 MB L2; no explicit flush')
+             l2='per-step K/V + Uk.mem streams (~0.6 GB of valid keys) exceed the 126 MB L2; no explicit flush')
     if extra:
         c.update(extra)
     return c
@@ -371,7 +371,9 @@ def roofline(model, eng, args, torch):
     ach = alg / (us * 1e-6) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed
     # `ncu --set full` capture (profiles/r1_top_kernels_ncu_summary.txt): 168.3 MB read + 5.4 MB written
-    traffic = None      # filled from the committed `ncu --set full` capture of this kernel (profiles/)
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at the BASELINE shape from the committed
+    # `ncu --set full` capture (profiles/r1_top_kernels_ncu_summary.txt): 114.3 MB read + 4.3 MB written
+    traffic = 118.6e6 if (compact and (B, W, S1) == (64, 4, 2560)) else None
     kname = 'cross_attn_part_kernel (passage memory, valid keys)' if compact else ('cross_attn_mma_kernel (passage memory)' if eng.w.cdtype == L.BF16 else 'cross_attn_partial_kernel (passage memory)')
     return dict(kernel=kname, bound='hbm', achieved=ach, peak=peak, unit='GB/s',
                 frac=ach / peak, traffic=traffic, peak_source=which, algorithmic_bytes_per_launch=alg,
