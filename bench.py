@@ -274,6 +274,17 @@ def main():
         clocks.start()
     ms, wall, out = timed(step_resident, args.steps)
     ms_e2e, wall_e2e, out_e = timed(lambda: run_e2e(args.steps), 1)
+    # the PCIe rate this box gives the pinned input buffers (explains e2e vs value when the link is slow/shared)
+    stage_dev = {k: torch.empty_like(v, device=dev) for k, v in host_data.items()}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for k, v in host_data.items():
+        stage_dev[k].copy_(v, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    h2d_ms = e0.elapsed_time(e1)
+    del stage_dev
     clk = clocks.stop() if rank == 0 else None
 
     # where the step goes: prefill (once per batch) vs the T decode steps, timed separately
@@ -316,7 +327,8 @@ def main():
                 ms_per_decode_step=decode_ms / T, prefill_ms=prefill_ms, decode_ms=decode_ms,
                 answer_tokens_per_step=tokens_per_step,
                 e2e=dict(value=e2e_value, unit='tokens/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                         ms_per_step=ms_e2e / args.steps),
+                         ms_per_step=ms_e2e / args.steps, h2d_ms_alone=h2d_ms, h2d_gbs_alone=h2d / (h2d_ms * 1e6),
+                         pinned=all(v.is_pinned() for v in host_data.values())),
                 gpu_launches=launches, clocks=clk, roofline=roof, cpu_baseline=cpu,
                 wall_s=dict(resident=wall, e2e=wall_e2e))
     print(json.dumps(line), flush=True)

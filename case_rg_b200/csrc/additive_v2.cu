@@ -17,6 +17,9 @@
 namespace cb {
 
 int g_additive_impl = 3;      // 3 = warp-autonomous kernel, 2 = block-synchronous tiles (A/B)
+static const int32_t* g_add_cidx = nullptr;     // compaction tables of the NEXT launch (case_additive_attn_compact)
+static const int32_t* g_add_ncount = nullptr;
+static const int32_t* g_add_qorder = nullptr;
 
 constexpr int A2T = 256;      // threads
 constexpr int A2K = 32;       // keys per tile
@@ -249,7 +252,8 @@ __global__ __launch_bounds__(A2T) void additive_attn_v3_kernel(
     const float* __restrict__ qa, const bf16* __restrict__ U, const bf16* __restrict__ Mv,
     const float* __restrict__ vvec, const uint8_t* __restrict__ mask, const float* __restrict__ prior,
     const int32_t* __restrict__ tok, int tok_ld, int t, int W, int S, int nsplit, float* __restrict__ scores,
-    float* __restrict__ stats, float* __restrict__ ctx_part) {
+    float* __restrict__ stats, float* __restrict__ ctx_part, const int32_t* __restrict__ cidx,
+    const int32_t* __restrict__ ncount, const int32_t* __restrict__ qorder) {
   constexpr int CG = DV / 256;
   constexpr int KPT = WMAX == 8 ? 2 : 4;               // keys per warp per tile
   constexpr int NV = KPT * WMAX;                       // partial sums per warp per tile (4, 8, 16)
@@ -263,12 +267,17 @@ __global__ __launch_bounds__(A2T) void additive_attn_v3_kernel(
   __shared__ float wst[8][WMAX][3];
   pdl_trigger();
   pdl_wait();
-  const int b = blockIdx.x, sp = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int chunk = split_chunk(S, nsplit, A2_SPLIT);
-  const int s_begin = sp * chunk, s_end = min(S, s_begin + chunk);
+  // compacted form (cidx != NULL): the split walks the VALID keys of the query, cidx[b][j] = position of the
+  // j-th one, every split of a query gets the same number of them, and heavy queries are launched first
+  const int b = qorder ? qorder[blockIdx.x] : blockIdx.x, sp = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Sv = cidx ? ncount[b] : S;                 // keys to walk
+  const int chunk = split_chunk(Sv, nsplit, A2_SPLIT);
+  const int s_begin = sp * chunk, s_end = min(Sv, s_begin + chunk);
   const int ntiles = s_end > s_begin ? (s_end - s_begin + TILEK - 1) / TILEK : 0;
   const int r0 = b * W;
   const uint8_t* mb = mask + (size_t)b * S;
+  const int32_t* cb = cidx ? cidx + (size_t)b * S : nullptr;
   const bf16* Ub = U + (size_t)b * S * H;
   const bf16* Mb = Mv + (size_t)b * S * DV;
   const float* pb = prior ? prior + (size_t)b * S : nullptr;
@@ -294,19 +303,23 @@ __global__ __launch_bounds__(A2T) void additive_attn_v3_kernel(
   if (rowvalid && tok) rowvalid = tok[(size_t)(r0 + myw) * tok_ld + t] != 0;
 
   auto key_of = [&](int ti, int k) { return s_begin + ti * TILEK + warp * KPT + k; };
-  auto valid_bits = [&](int ti) -> unsigned {          // bit k: key k of this warp's group is a real key
+  // valid bits (bit k) and, in the compacted form, the memory positions of the group's keys (lane k holds key k's)
+  int pos_next = 0;
+  auto valid_bits = [&](int ti) -> unsigned {
     bool ok = false;
+    pos_next = 0;
     if (lane < KPT && ti < ntiles) {
       const int s = key_of(ti, lane);
-      ok = s < s_end && mb[s] != 0;
+      if (cb) { ok = s < s_end; pos_next = ok ? cb[s] : 0; }
+      else { ok = s < s_end && mb[s] != 0; pos_next = s; }
     }
     return __ballot_sync(0xffffffffu, ok);
   };
-  auto issue = [&](int ti, int stage, unsigned vb) {
+  auto issue = [&](int stage, unsigned vbits, int pos_lane) {
 #pragma unroll
     for (int k = 0; k < KPT; ++k) {
-      if ((vb >> k) & 1u) {
-        const int s = key_of(ti, k);
+      const int s = __shfl_sync(0xffffffffu, pos_lane, k);
+      if ((vbits >> k) & 1u) {
         const uint32_t dst = wbuf_s + stage * WSTAGE + k * ROWB;
         a2_cp16(dst + lane * 16, Ub + (size_t)s * H + lane * 8, 16);
 #pragma unroll
@@ -326,12 +339,14 @@ __global__ __launch_bounds__(A2T) void additive_attn_v3_kernel(
       for (int i = 0; i < 8; ++i) acc[w][c][i] = 0.f;
 
   unsigned vb = valid_bits(0);
-  issue(0, 0, vb);
+  int pos = pos_next;                                  // lane k: memory position of key k of the current tile
+  issue(0, vb, pos);
   a2_commit();
   for (int ti = 0; ti < ntiles; ++ti) {
     const int stage = ti & 1;
     const unsigned vb_next = valid_bits(ti + 1);
-    if (ti + 1 < ntiles) issue(ti + 1, stage ^ 1, vb_next);
+    const int pos_n = pos_next;
+    if (ti + 1 < ntiles) issue(stage ^ 1, vb_next, pos_n);
     a2_commit();
     a2_wait<1>();
     __syncwarp();
@@ -380,10 +395,12 @@ __global__ __launch_bounds__(A2T) void additive_attn_v3_kernel(
         }
       }
     }
-    const int skey = key_of(ti, myk);
+    const int skey = __shfl_sync(0xffffffffu, pos, myk);        // memory position of this lane's key
+    const bool inrange = key_of(ti, myk) < s_end;
     const bool ok = rowvalid && ((vb >> myk) & 1u);
     const float e = ok ? part[0] : -INFINITY;
-    if ((lane & ((1 << SH) - 1)) == 0 && myw < W && skey < s_end) scores[(size_t)(r0 + myw) * S + skey] = e;
+    // (compacted form: padding positions are never visited; their scores were set to -inf at prefill)
+    if ((lane & ((1 << SH) - 1)) == 0 && myw < W && inrange) scores[(size_t)(r0 + myw) * S + skey] = e;
     // ---- online softmax of row myw over the group's keys (the key index sits in the upper bits of myj)
     float tmax = e;
 #pragma unroll
@@ -433,6 +450,7 @@ __global__ __launch_bounds__(A2T) void additive_attn_v3_kernel(
     }
     __syncwarp();                                         // this stage is refilled two iterations from now
     vb = vb_next;
+    pos = pos_n;
   }
   a2_wait<0>();
   // ---- merge the 8 warps: statistics, then the contexts through the (now idle) staging memory
@@ -496,6 +514,8 @@ template <int WMAX, int DV, bool FAST>
 static int launch_v2(const float* qa, const void* U, const void* Mv, const float* v, const uint8_t* mask,
                      const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S, int nsplit,
                      float* scores, float* stats, float* ctx_part, cudaStream_t st) {
+  const int32_t* cidx = g_add_cidx; const int32_t* ncount = g_add_ncount; const int32_t* qorder = g_add_qorder;
+  g_add_cidx = g_add_ncount = g_add_qorder = nullptr;          // one-shot: set by case_additive_attn_compact
   if (g_additive_impl == 2) {
     const int chunk = split_chunk(S, nsplit, A2_SPLIT);
     const size_t smem = (size_t)2 * A2K * A2ULD * 2 + (size_t)2 * A2K * DV * 2 +
@@ -520,7 +540,7 @@ static int launch_v2(const float* qa, const void* U, const void* Mv, const float
     attr = true;
   }
   launch_k(kern, dim3(B, nsplit), A2T, smem, st, qa, (const bf16*)U, (const bf16*)Mv, v, mask, prior, tok, tok_ld, t, W, S,
-                                           nsplit, scores, stats, ctx_part);
+                                           nsplit, scores, stats, ctx_part, cidx, ncount, qorder);
   return check_launch("case_additive_attn(v3)");
 }
 
@@ -552,4 +572,23 @@ extern "C" int case_set_additive_impl(int impl) {
   const int old = cb::g_additive_impl;
   cb::g_additive_impl = impl == 2 ? 2 : 3;
   return old;
+}
+
+/* case_additive_attn over the VALID keys only (bf16, warp-autonomous kernel): cidx int32 [B][S] positions
+ * of the valid keys (ascending), ncount int32 [B], qorder int32 [B] launch order of the queries (heaviest
+ * first; may be NULL).  scores[r][s] of padding positions are NOT written: fill them with -inf once. */
+extern "C" int case_additive_attn_compact(const float* qa, const void* U, const void* Mv, const float* v,
+                                          const uint8_t* mask, const float* prior, const int32_t* tok, int tok_ld, int t,
+                                          int B, int W, int S, int DV, int nsplit, float* attn_un, float* stats,
+                                          float* ctx_part, int fast_tanh, const int32_t* cidx, const int32_t* ncount,
+                                          const int32_t* qorder, case_stream_t stream) {
+  if (!cidx || !ncount) { cb::set_error("case_additive_attn_compact: cidx / ncount missing"); return CASE_EINVAL; }
+  cb::g_add_cidx = cidx; cb::g_add_ncount = ncount; cb::g_add_qorder = qorder;
+  const int old = cb::g_additive_impl;
+  cb::g_additive_impl = 3;
+  const int rc = case_additive_attn_v2(qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, W, S, DV, nsplit, attn_un, stats,
+                                       ctx_part, fast_tanh, (cudaStream_t)stream);
+  cb::g_additive_impl = old;
+  cb::g_add_cidx = cb::g_add_ncount = cb::g_add_qorder = nullptr;
+  return rc;
 }

@@ -121,6 +121,10 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
     q.nseg = 2; q.K = 2 * H; q.Wt = a->Wqa_t[i]; q.bias = a->bqa[i]; q.N = H; q.out = qa; q.ldo = H;
     q.R = R; q.dtype = dt;
     TRY(case_row_linear(&q, s2));
+    if (i == 1 && dt == CASE_BF16 && a->xidx != nullptr && a->xcount != nullptr)   // valid keys only, balanced splits
+      return case_additive_attn_compact(qa, a->U[i], a->Mv[i], a->va[i], a->mask[i], a->prior[i], a->tok, TL, t, B, W,
+                                        a->S[i], H, a->nsplit_a[i], a->attn_un[i], a->stats[i], a->ctxp[i],
+                                        a->fast_tanh, a->xidx, a->xcount, a->xorder, s2);
     return case_additive_attn(qa, a->U[i], a->Mv[i], a->va[i], a->mask[i], a->prior[i], a->tok, TL, t, B, W, a->S[i],
                               H, a->nsplit_a[i], a->attn_un[i], a->stats[i], a->ctxp[i], a->fast_tanh, dt, s2);
   };

@@ -336,6 +336,7 @@ class CaseDecodeEngine(_EngineBase):
         self.xcount = torch.zeros(B, dtype=torch.int32, device=dev)
         self.xprefix = torch.zeros(B + 1, dtype=torch.int32, device=dev)
         self.xidx = torch.zeros(B, S1, dtype=torch.int32, device=dev) if self.compact else None
+        self.xorder = torch.zeros(B, dtype=torch.int32, device=dev)
         self.x_in, self.h, self.bbuf, self.q2 = z(R, H), z(R, H), z(R, H), z(R, H)
         self.part_ml, self.part_acc = z(R, L.NH, nsx, 2), z(R, L.NH, nsx, L.HD)
         self.qa = z(R, H)
@@ -385,6 +386,7 @@ class CaseDecodeEngine(_EngineBase):
         a.map, a.map_ld = self.map.data_ptr(), self.map.size(1)
         if self.compact:
             a.xcount, a.xprefix, a.xslots = self.xcount.data_ptr(), self.xprefix.data_ptr(), self.xslots
+            a.xidx, a.xorder = self.xidx.data_ptr(), self.xorder.data_ptr()
         self.state.bind(a)
         for n in ('x_in', 'h', 'bbuf', 'q2', 'part_ml', 'part_acc', 'qa', 'hN', 'gates', 'fac', 'gfeat', 'logits',
                   'dist', 'top_vals', 'top_idx', 'prow', 'h0', 'qa1', 'base_ms', 'base_e', 'base_i'):
@@ -421,6 +423,9 @@ class CaseDecodeEngine(_EngineBase):
                     cnt = valid.sum(1)
                     self.xcount.copy_(cnt)
                     self.xprefix[1:].copy_(torch.cumsum((cnt + 63) // 64, 0))
+                    self.xorder.copy_(torch.argsort(cnt, descending=True, stable=True))
+                    # the additive attention visits valid keys only: padding scores are -inf once and for all
+                    self.attn_un[i].masked_fill_(~valid.repeat_interleave(self.W, 0), float('-inf'))
                     L.call('case_pack_kv_tiles_gather', kv.data_ptr(), kv.size(1), B, S, self.xidx.data_ptr(),
                            self.xcount.data_ptr(), 4, outs, stream)
                 else:

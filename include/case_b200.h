@@ -233,6 +233,16 @@ int case_additive_attn(const float* qa, const void* U, const void* Mv, const flo
                        int nsplit, float* attn_un, float* stats, float* ctx_part, int fast_tanh, int dtype,
                        case_stream_t stream);
 
+/* case_additive_attn over the VALID keys only (bf16): cidx int32 [B][S] = positions of the valid keys of
+ * every query (ascending), ncount int32 [B]; every key split of a query walks the same number of valid
+ * keys, and qorder int32 [B] (may be NULL) launches the heaviest queries first.  attn_un of padding
+ * positions is NOT written: the caller fills those entries with -inf once (they never change). */
+int case_additive_attn_compact(const float* qa, const void* U, const void* Mv, const float* v, const uint8_t* mask,
+                               const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S, int DV,
+                               int nsplit, float* attn_un, float* stats, float* ctx_part, int fast_tanh,
+                               const int32_t* cidx, const int32_t* ncount, const int32_t* qorder,
+                               case_stream_t stream);
+
 /* bf16 additive attention kernel: 3 (default) = warp-autonomous (no block barrier in the key loop, padding
  * skipped per key), 2 = block-synchronous 32-key tiles; returns the old setting (A/B aid). */
 int case_set_additive_impl(int impl);
@@ -386,6 +396,7 @@ typedef struct {
   /* compacted second memory (may be NULL -> masks + case_cross_attn_partial_tc): Kx[4..7] then hold the
    * gathered tiles, part_ml / part_acc have xslots slots per (row, head) */
   const int32_t* xcount; const int32_t* xprefix; int32_t xslots;
+  const int32_t* xidx; const int32_t* xorder;   /* [B][S1] valid positions, [B] queries by valid count (desc) */
 } case_step_args_t;
 
 /* Enqueue one full decode step t (embedding .. select) for all R rows: the body of the eval loop
