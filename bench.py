@@ -184,6 +184,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':   # would put a banner line on stdout next to the JSON line
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
     w = WORKLOAD
     B, W, T, V = args.batch, args.beam, w['T'], w['V']
