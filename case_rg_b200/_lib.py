@@ -61,7 +61,7 @@ class StepArgs(C.Structure):
                 ('out_tokens', vp), ('n_live', vp),
                 ('x_in', vp), ('h', vp), ('bbuf', vp), ('q2', vp), ('part_ml', vp), ('part_acc', vp), ('qa', vp),
                 ('attn_un', vp * 2), ('stats', vp * 2), ('ctxp', vp * 2), ('hN', vp), ('ctx', vp * 2), ('gates', vp),
-                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp), ('prow', vp), ('h0', vp), ('qa1', vp), ('base_ms', vp), ('base_e', vp), ('base_i', vp), ('xcount', vp), ('xprefix', vp), ('xslots', i32), ('xidx', vp), ('xorder', vp)]
+                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp), ('prow', vp), ('h0', vp), ('qa1', vp), ('base_ms', vp), ('base_e', vp), ('base_i', vp), ('xcount', vp), ('xprefix', vp), ('xslots', i32), ('xidx', vp), ('xorder', vp), ('qcount', vp)]
 
 
 class GttpStepArgs(C.Structure):
@@ -109,7 +109,7 @@ _PROTOS = {
     'case_row_tail': [C.POINTER(TailArgs), vp],
     'case_row_tail_max_vocab': [],
     'case_vocab_base': [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp],
-    'case_sparse_tail': [C.POINTER(TailArgs), vp, vp, vp, i32, vp],
+    'case_sparse_tail': [C.POINTER(TailArgs), vp, vp, vp, i32, C.POINTER(SelectArgs), vp, vp],
     'case_sparse_tail_max_sources': [],
     'case_beam_select': [C.POINTER(SelectArgs), vp],
     'case_gru_cell': [vp, vp, vp, vp, vp, i32, vp],
@@ -121,6 +121,7 @@ _PROTOS = {
     'case_set_fork': [i32],
     'case_set_additive_impl': [i32],
     'case_set_fused_tail': [i32],
+    'case_set_fused_select': [i32],
     'case_decode_step': [C.POINTER(StepArgs), i32, vp],
     'gttp_decode_step': [C.POINTER(GttpStepArgs), i32, vp],
 }

@@ -15,8 +15,11 @@
 //                      gets g0 * exp(logit - max) / sum + mass (one gather from the logits) -> top-k
 //                      over touched ids + base candidates.
 // Work after the attentions drops from three passes over the 31 MB tile to ~2.7 k entries per row.
+#include <string.h>
+
 #include "common.cuh"
 #include "topk.cuh"
+#include "select.cuh"
 
 namespace cb {
 
@@ -138,7 +141,8 @@ __device__ __forceinline__ uint32_t sp_step(int id) { return (((uint32_t)id * 40
 __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t a, const float* __restrict__ base_ms,
                                                          const float* __restrict__ base_e,
                                                          const int32_t* __restrict__ base_i, int k2, int nslots,
-                                                         long long* dbg) {
+                                                         long long* dbg, const case_select_args_t sel, int do_select,
+                                                         int32_t* __restrict__ qcount) {
   extern __shared__ __align__(16) int hkeys[];            // [nslots] ids (-1 = empty), then [nslots] float masses
   float* hvals = reinterpret_cast<float*>(hkeys + nslots);
   __shared__ float sh[TSW * 3];
@@ -350,6 +354,22 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
     a.top_idx[(size_t)r * K + lane] = oi;
   }
   stamp();
+  // ---- fused search bookkeeping: the last CTA of a query's W rows runs Generations.beam / greedy for it
+  if (do_select) {
+    __shared__ int s_last;
+    __threadfence();                                      // this row's top-k is visible device-wide
+    __syncthreads();
+    if (tid == 0) {
+      const int old = atomicAdd(qcount + b, 1);
+      s_last = old == a.W - 1;
+      if (s_last) qcount[b] = 0;                          // ready for the next step
+    }
+    __syncthreads();
+    if (s_last && warp == 0) {
+      __threadfence();
+      beam_select_query(sel, b, lane);
+    }
+  }
 }
 
 }  // namespace cb
@@ -374,7 +394,8 @@ extern "C" int case_debug_sparse_tail_timing(void* buf) { g_sp_dbg = (long long*
 extern "C" int case_sparse_tail_max_sources(void) { return 10900; }   // 16384 slots at load factor <= 2/3
 
 extern "C" int case_sparse_tail(const case_tail_args_t* a, const float* base_ms, const float* base_e,
-                                const int32_t* base_i, int k2, case_stream_t stream) {
+                                const int32_t* base_i, int k2, const case_select_args_t* sel, int32_t* qcount,
+                                case_stream_t stream) {
   CB_REQUIRE(a && a->logits && a->gates && a->fac && a->map && base_ms && base_e && base_i, "case_sparse_tail: null pointer");
   CB_REQUIRE(a->R > 0 && a->W >= 1 && a->V > 0 && a->top_vals && a->top_idx, "case_sparse_tail: bad sizes / outputs");
   CB_REQUIRE(a->K >= 1 && a->K <= CASE_MAX_W && k2 >= a->K && k2 <= 2 * CASE_MAX_W, "case_sparse_tail: need K <= k2 <= 16");
@@ -396,6 +417,12 @@ extern "C" int case_sparse_tail(const case_tail_args_t* a, const float* base_ms,
     cudaFuncSetAttribute(sparse_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
     attr = true;
   }
-  launch_k(sparse_tail_kernel, a->R, TS, smem, st, *a, base_ms, base_e, base_i, k2, nslots, g_sp_dbg);
+  CB_REQUIRE(sel == nullptr || (qcount != nullptr && sel->B * sel->W == a->R && sel->W == a->W && a->K == a->W),
+             "case_sparse_tail: fused select needs qcount and matching B / W (k = W)");
+  case_select_args_t sv;
+  memset(&sv, 0, sizeof(sv));
+  if (sel) sv = *sel;
+  launch_k(sparse_tail_kernel, a->R, TS, smem, st, *a, base_ms, base_e, base_i, k2, nslots, g_sp_dbg, sv, sel ? 1 : 0,
+           qcount);
   return check_launch("case_sparse_tail");
 }

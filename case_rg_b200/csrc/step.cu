@@ -14,6 +14,7 @@ int g_use_chain = 1;
 int g_use_fork = 1;
 int g_use_stack = 1;
 int g_use_tail = 2;
+int g_use_fused_select = 1;
 // side stream + events for the fork/join inside a step (created on first use, outside any capture: the
 // engines run one uncaptured warm-up step before they capture)
 static cudaStream_t g_aux = nullptr;
@@ -70,6 +71,11 @@ extern "C" int case_set_stack_fusion(int on) {
   g_use_stack = on ? 1 : 0;
   return old;
 }
+extern "C" int case_set_fused_select(int on) {
+  const int old = g_use_fused_select;
+  g_use_fused_select = on ? 1 : 0;
+  return old;
+}
 extern "C" int case_set_fork(int on) {
   const int old = g_use_fork;
   g_use_fork = on ? 1 : 0;
@@ -86,6 +92,21 @@ extern "C" const char* case_last_error(void) { return g_err; }
 static case_seg_t seg(const float* p, int ld, int width, int div, int gather = 0) {
   case_seg_t s;
   s.p = p; s.ld = ld; s.width = width; s.div = div; s.gather = gather;
+  return s;
+}
+
+static case_select_args_t select_args(int mode, int B, int W, int t, int max_len, int Tmax, int BOS, int EOS, int UNK,
+                                      int PAD, const float* top_vals, const int32_t* top_idx, int32_t* live, double* cum,
+                                      int32_t* length, int32_t* tok, int32_t* const anc[2], int32_t* parent,
+                                      int32_t* ended, double* best_key, int32_t* best_len, int32_t* out_tokens,
+                                      int32_t* n_live) {
+  case_select_args_t s;
+  memset(&s, 0, sizeof(s));
+  s.mode = mode; s.B = B; s.W = W; s.t = t; s.max_len = max_len; s.Tmax = Tmax;
+  s.BOS = BOS; s.EOS = EOS; s.UNK = UNK; s.PAD = PAD;
+  s.top_vals = top_vals; s.top_idx = top_idx; s.live = live; s.cum = cum; s.length = length; s.tok = tok;
+  s.anc_in = anc[t & 1]; s.anc_out = anc[(t + 1) & 1]; s.parent = parent; s.ended = ended;
+  s.best_key = best_key; s.best_len = best_len; s.out_tokens = out_tokens; s.n_live = n_live;
   return s;
 }
 
@@ -266,7 +287,12 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
     }
     if (a->materialize_only) { ta.dist = a->dist; } else { ta.top_vals = a->top_vals; ta.top_idx = a->top_idx; }
     if (sparse) {
-      TRY(case_sparse_tail(&ta, a->base_ms, a->base_e, a->base_i, k2, st));
+      const bool fuse_sel = a->qcount != nullptr && g_use_fused_select;
+      case_select_args_t sel = select_args(a->mode, B, W, t, a->max_len, a->Tmax, a->BOS, a->EOS, a->UNK, a->PAD,
+                                           a->top_vals, a->top_idx, a->live, a->cum, a->length, a->tok, a->anc, a->parent,
+                                           a->ended, a->best_key, a->best_len, a->out_tokens, a->n_live);
+      TRY(case_sparse_tail(&ta, a->base_ms, a->base_e, a->base_i, k2, fuse_sel ? &sel : nullptr, a->qcount, st));
+      if (fuse_sel) return 0;
     } else {
       TRY(case_row_tail(&ta, st));
     }

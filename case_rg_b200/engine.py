@@ -337,6 +337,7 @@ class CaseDecodeEngine(_EngineBase):
         self.xprefix = torch.zeros(B + 1, dtype=torch.int32, device=dev)
         self.xidx = torch.zeros(B, S1, dtype=torch.int32, device=dev) if self.compact else None
         self.xorder = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.qcount = torch.zeros(B, dtype=torch.int32, device=dev)
         self.x_in, self.h, self.bbuf, self.q2 = z(R, H), z(R, H), z(R, H), z(R, H)
         self.part_ml, self.part_acc = z(R, L.NH, nsx, 2), z(R, L.NH, nsx, L.HD)
         self.qa = z(R, H)
@@ -387,6 +388,7 @@ class CaseDecodeEngine(_EngineBase):
         if self.compact:
             a.xcount, a.xprefix, a.xslots = self.xcount.data_ptr(), self.xprefix.data_ptr(), self.xslots
             a.xidx, a.xorder = self.xidx.data_ptr(), self.xorder.data_ptr()
+        a.qcount = self.qcount.data_ptr()
         self.state.bind(a)
         for n in ('x_in', 'h', 'bbuf', 'q2', 'part_ml', 'part_acc', 'qa', 'hN', 'gates', 'fac', 'gfeat', 'logits',
                   'dist', 'top_vals', 'top_idx', 'prow', 'h0', 'qa1', 'base_ms', 'base_e', 'base_i'):
@@ -487,7 +489,7 @@ class CaseDecodeEngine(_EngineBase):
     def kernel_launches_per_step(self) -> int:
         # (+1 in bench.py: the activation re-pack inside the vocabulary GEMM call)
         lib = L.load()
-        tail = 3                       # vocab_base + sparse_tail + select
+        tail = 2                       # vocab_base + sparse_tail (search bookkeeping fused into it)
         if self.w.cdtype == L.BF16 and self.Tmax <= lib.case_layer_chain_max_tmax():
             if self.S[0] <= lib.case_layer_chain_max_s0():
                 # layer_stack (first stack + front 4) + 4 x cross + 4 x layer_chain + 2 x (row_linear, additive)

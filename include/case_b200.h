@@ -66,6 +66,8 @@ int case_set_fork(int on);
  * 2 (default) = case_vocab_base + case_sparse_tail where the scratch buffers are given, else 1; returns
  * the old setting. */
 int case_set_fused_tail(int on);
+/* Search bookkeeping inside the sparse tail launch instead of a case_beam_select launch (default on). */
+int case_set_fused_select(int on);
 
 /* ---------------------------------------------------------------- row-wise building blocks */
 
@@ -318,8 +320,6 @@ int case_row_tail_max_vocab(void);
  *   plus the base statistics; sum of S[i] <= case_sparse_tail_max_sources(). */
 int case_vocab_base(const float* logits, int ldl, int R, int V, int mask_col0, int k2, float* base_ms,
                     float* base_l, int32_t* base_i, case_stream_t stream);
-int case_sparse_tail(const case_tail_args_t* a, const float* base_ms, const float* base_l, const int32_t* base_i,
-                     int k2, case_stream_t stream);
 int case_sparse_tail_max_sources(void);
 
 /* ---------------------------------------------------------------- search bookkeeping */
@@ -344,6 +344,12 @@ typedef struct {
 } case_select_args_t;
 
 int case_beam_select(const case_select_args_t* a, case_stream_t stream);
+
+/* case_sparse_tail (see the vocabulary section): sel != NULL fuses case_beam_select into the launch - the
+ * last CTA of a query's W rows runs the bookkeeping of that query (k must equal W); qcount: int32 [B],
+ * zero before the first launch (the kernel leaves it zero). */
+int case_sparse_tail(const case_tail_args_t* a, const float* base_ms, const float* base_l, const int32_t* base_i,
+                     int k2, const case_select_args_t* sel, int32_t* qcount, case_stream_t stream);
 
 /* ---------------------------------------------------------------- GTTP step pieces */
 
@@ -397,6 +403,7 @@ typedef struct {
    * gathered tiles, part_ml / part_acc have xslots slots per (row, head) */
   const int32_t* xcount; const int32_t* xprefix; int32_t xslots;
   const int32_t* xidx; const int32_t* xorder;   /* [B][S1] valid positions, [B] queries by valid count (desc) */
+  int32_t* qcount;                      /* [B] zeros (may be NULL): lets the sparse tail run the search bookkeeping */
 } case_step_args_t;
 
 /* Enqueue one full decode step t (embedding .. select) for all R rows: the body of the eval loop

@@ -92,7 +92,7 @@ def sparse_stamps(R=256, W=4, V=30522, S=(60, 2560), K=4):
         L.call('case_vocab_base', keep['logits'].data_ptr(), ldv, R, V, 0, k2, bms.data_ptr(), bl.data_ptr(), bi.data_ptr(), st)
 
     def tail():
-        L.check(lib.case_sparse_tail(C.byref(a), bms.data_ptr(), bl.data_ptr(), bi.data_ptr(), k2, st), 'sparse')
+        L.check(lib.case_sparse_tail(C.byref(a), bms.data_ptr(), bl.data_ptr(), bi.data_ptr(), k2, None, None, st), 'sparse')
     base()
     for rep in range(2):
         dbg.zero_()

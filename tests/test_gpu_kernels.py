@@ -413,7 +413,7 @@ def test_sparse_tail_matches_dense_tail(R, W, V, S0, S1, K, finalize):
     L.call('case_vocab_base', logits.data_ptr(), ldv, R, V, 1 - finalize, k2, base_ms.data_ptr(), base_e.data_ptr(),
            base_i.data_ptr(), st)
     a2, sparse = args()
-    L.check(lib.case_sparse_tail(C.byref(a2), base_ms.data_ptr(), base_e.data_ptr(), base_i.data_ptr(), k2, st),
+    L.check(lib.case_sparse_tail(C.byref(a2), base_ms.data_ptr(), base_e.data_ptr(), base_i.data_ptr(), k2, None, None, st),
             'case_sparse_tail')
     torch.cuda.synchronize()
     # base statistics against torch
