@@ -42,6 +42,8 @@ def parse():
     ap.add_argument('--no-pdl', action='store_true', help='disable programmatic dependent launch (A/B)')
     ap.add_argument('--no-chain', action='store_true', help='row-block layer kernels instead of the cluster kernels (A/B)')
     ap.add_argument('--no-fork', action='store_true', help='no side stream for the additive attentions (A/B)')
+    ap.add_argument('--no-post', action='store_true', help='row_linear launches instead of post linears (A/B)')
+    ap.add_argument('--no-stack', action='store_true', help='no fused first stack (A/B)')
     ap.add_argument('--streams', type=int, default=1, help='batch slices decoded concurrently on their own streams')
     ap.add_argument('--batch', type=int, default=WORKLOAD['B'])
     ap.add_argument('--beam', type=int, default=WORKLOAD['W'])
@@ -195,6 +197,10 @@ def main():
         L.load().case_set_chain(0)
     if args.no_fork:
         L.load().case_set_fork(0)
+    if args.no_post:
+        L.load().case_set_post_linears(0)
+    if args.no_stack:
+        L.load().case_set_stack_fusion(0)
     if args.profile:
         args.streams = 1
 

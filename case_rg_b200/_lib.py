@@ -39,6 +39,15 @@ class SelectArgs(C.Structure):
                                   'parent', 'ended', 'best_key', 'best_len', 'out_tokens', 'n_live')]
 
 
+class PostLinear(C.Structure):
+    _fields_ = [('Wc', vp), ('bias', vp), ('out', vp), ('nchunk', i32), ('seg', i32 * 3)]
+
+
+class ChainPost(C.Structure):
+    _fields_ = [('npost', i32), ('W', i32), ('lin', PostLinear * 2), ('feat', vp), ('x_in', vp), ('ln_g', vp),
+                ('ln_b', vp), ('ln_out', vp)]
+
+
 class TailArgs(C.Structure):
     _fields_ = [(n, i32) for n in ('R', 'V', 'W', 'K', 'ldl', 'ldd', 'mask_col0', 'nmem', 'do_finalize', 'fac_ld',
                                    'map_ld')] + \
@@ -61,7 +70,7 @@ class StepArgs(C.Structure):
                 ('out_tokens', vp), ('n_live', vp),
                 ('x_in', vp), ('h', vp), ('bbuf', vp), ('q2', vp), ('part_ml', vp), ('part_acc', vp), ('qa', vp),
                 ('attn_un', vp * 2), ('stats', vp * 2), ('ctxp', vp * 2), ('hN', vp), ('ctx', vp * 2), ('gates', vp),
-                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp), ('prow', vp), ('h0', vp), ('qa1', vp), ('base_ms', vp), ('base_e', vp), ('base_i', vp), ('xcount', vp), ('xprefix', vp), ('xslots', i32), ('xidx', vp), ('xorder', vp), ('qcount', vp)]
+                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp), ('prow', vp), ('h0', vp), ('qa1', vp), ('base_ms', vp), ('base_e', vp), ('base_i', vp), ('xcount', vp), ('xprefix', vp), ('xslots', i32), ('xidx', vp), ('xorder', vp), ('qcount', vp), ('Wqa_c', vp * 2), ('Wg_c', vp)]
 
 
 class GttpStepArgs(C.Structure):
@@ -92,10 +101,10 @@ _PROTOS = {
     'case_cross_attn_part_slots': [i32],
     'case_layer_back': [vp, vp, vp, i32, C.POINTER(LayerWeights), vp, i32, i32, vp],
     'case_layer_chain': [C.POINTER(LayerWeights), C.POINTER(LayerWeights), vp, vp, vp, C.c_float, vp, vp, vp, vp, i32,
-                         vp, vp, vp, vp, i32, vp, i32, vp, i32, i32, vp, vp, i32, i32, vp],
+                         vp, vp, vp, vp, i32, vp, i32, vp, i32, i32, vp, vp, i32, i32, C.POINTER(ChainPost), vp],
     'case_layer_chain_max_tmax': [],
     'case_layer_stack': [C.POINTER(LayerWeights), i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, C.c_float, vp, vp, vp, i32, vp,
-                         i32, vp, i32, i32, vp, vp, i32, i32, vp],
+                         i32, vp, i32, i32, vp, vp, i32, i32, C.POINTER(ChainPost), vp],
     'case_layer_chain_max_s0': [],
     'case_additive_attn': [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp],
     'case_additive_attn_compact': [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp,
@@ -122,12 +131,13 @@ _PROTOS = {
     'case_set_additive_impl': [i32],
     'case_set_fused_tail': [i32],
     'case_set_fused_select': [i32],
+    'case_set_post_linears': [i32],
     'case_decode_step': [C.POINTER(StepArgs), i32, vp],
     'gttp_decode_step': [C.POINTER(GttpStepArgs), i32, vp],
 }
 _SIZE_FNS = ['case_vocab_tc_workspace_bytes', 'case_vocab_tc_packed_weight_bytes']
 EXPORTS = sorted(list(_PROTOS) + ['case_abi_version', 'case_last_error', 'case_struct_size'] + _SIZE_FNS)
-_STRUCTS = [Seg, RowLinArgs, LayerWeights, SelectArgs, StepArgs, GttpStepArgs, TailArgs]
+_STRUCTS = [Seg, RowLinArgs, LayerWeights, SelectArgs, StepArgs, GttpStepArgs, TailArgs, ChainPost]
 
 _lib = None
 

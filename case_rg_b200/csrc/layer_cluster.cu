@@ -55,7 +55,9 @@ constexpr int OFF_Q = OFF_OWN + CROWS * CCOL * 4;
 constexpr int OFF_SC = OFF_Q + CROWS * CCOL * 4;
 constexpr int OFF_PROW = OFF_SC + 2 * CROWS * CSCLD2 * 4;
 constexpr int OFF_BAR = OFF_PROW + CROWS * CTMAX * 4;
-constexpr int OFF_KV = OFF_BAR + 64;           // K history [8 rows][2 heads][Tmax][32] bf16, then V history
+constexpr int OFF_PT = OFF_BAR + 64;           // two bf16 A tiles kept for the post linears (raw rows, per-query feature)
+constexpr int OFF_KV = OFF_PT + 2 * CROWS * CALD * 2;   // K history [8 rows][2 heads][Tmax][32] bf16, then V history
+                                               // (a launch without front halves keeps a third post tile here)
 constexpr int CMAXF = 5;           // front halves per launch: up to 4 fused layers + the front that feeds a big cross-attention
 
 struct ChainLayer {                // device pointers of one layer
@@ -82,8 +84,14 @@ struct ChainArgs {
   const int32_t* tok; int tok_ld;
   int32_t* prow_g;                 // [R][Tmax] history row table of this step (may be NULL)
   float* b_out; float* q2_out;     // outputs of the last front half
+  // post linears: y = [segments] . W^T + bias on the rows that leave the LAST back half of the launch
+  // (attention query = [h ; feat], gen.0 = [x_in ; norm1(h) ; feat]; Model.py:108, 115)
+  int npost;
+  struct { const char* w; const float* bias; float* out; int nchunk; int seg[3]; } post[2];
+  const float* feat; const float* xin; const float* lnN_g; const float* lnN_b; float* hN_out;
   long long* dbg;                  // optional stage clock stamps of CTA 0 (case_debug_chain_timing)
 };
+constexpr int SEG_H = 1, SEG_HLN = 2, SEG_FEAT = 3, SEG_XIN = 4;
 
 static long long* g_chain_dbg = nullptr;
 
@@ -299,8 +307,14 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
   stamp();
   const uint32_t s_base = smem_u32(sm);
   const uint32_t s_w = s_base + OFF_W, s_xa = s_base + OFF_XA, s_la = s_base + OFF_LA, s_xf = s_base + OFF_XF;
-  const uint32_t s_bar = s_base + OFF_BAR;           // [0..2] weight slots, [3] XA exchange, [4] XF exchange
-  const uint32_t s_bxa = s_bar + 24, s_bxf = s_bar + 32;
+  const uint32_t s_bar = s_base + OFF_BAR;           // [0..4] weight slots, [6] XA exchange, [7] XF exchange
+  const uint32_t s_bxa = s_bar + 48, s_bxf = s_bar + 56;
+  // a launch without front half has no KV history: two more weight slots live there, so all three matrices of
+  // the back half and the first post-linear chunks are requested at launch
+  const int nslots = a.nfront == 0 ? CNS + 2 : CNS;
+  auto slot_addr = [&](int sl) -> uint32_t {
+    return sl < CNS ? s_w + sl * CWB : s_base + OFF_KV + CROWS * CALD * 2 + (sl - CNS) * CWB;
+  };
   bf16* la = reinterpret_cast<bf16*>(sm + OFF_LA);
   float* xf = reinterpret_cast<float*>(sm + OFF_XF);
   float* own = reinterpret_cast<float*>(sm + OFF_OWN);
@@ -313,26 +327,33 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
   // ---- weight sequence of this launch: [Wo2 W1 W2 of the initial back half], then the matrices of the
   // fused layers in natural order (Wq Wk Wv Wo Wq2 | Wo2 W1 W2), then Wq Wk Wv Wo Wq2 of the last front
   const int nback = a.has_back ? 3 : 0;
-  const int nseq = nback + (a.nfront > 0 ? 8 * (a.nfront - 1) + 5 : 0);
+  const int nlayer_seq = nback + (a.nfront > 0 ? 8 * (a.nfront - 1) + 5 : 0);
+  const int npost0 = a.npost > 0 ? a.post[0].nchunk : 0, npost1 = a.npost > 1 ? a.post[1].nchunk : 0;
+  const int nseq = nlayer_seq + npost0 + npost1;       // the post-linear chunks come last
   auto seq_ptr = [&](int k) -> const char* {
     if (k < nback) return a.back.wc + (size_t)(c * 8 + 5 + k) * CWB;
-    const int kk = k - nback;
-    return a.layers[kk >> 3].wc + (size_t)(c * 8 + (kk & 7)) * CWB;
+    if (k < nlayer_seq) {
+      const int kk = k - nback;
+      return a.layers[kk >> 3].wc + (size_t)(c * 8 + (kk & 7)) * CWB;
+    }
+    const int kp = k - nlayer_seq;
+    if (kp < npost0) return a.post[0].w + (size_t)(c * npost0 + kp) * CWB;
+    return a.post[1].w + (size_t)(c * npost1 + (kp - npost0)) * CWB;
   };
   int issued = 0;                                    // thread 0 only
   auto refill = [&](int consumed) {
     if (tid == 0) {
-      while (issued < nseq && issued < consumed + CNS) {
-        const int slot = issued % CNS;
+      while (issued < nseq && issued < consumed + nslots) {
+        const int slot = issued % nslots;
         c_mb_expect(s_bar + 8 * slot, CWB);
-        c_bulk(s_w + slot * CWB, seq_ptr(issued), CWB, s_bar + 8 * slot);
+        c_bulk(slot_addr(slot), seq_ptr(issued), CWB, s_bar + 8 * slot);
         ++issued;
       }
     }
   };
   auto wait_w = [&](int k) -> uint32_t {             // returns the shared address of matrix k of the sequence
-    c_mb_wait(s_bar + 8 * (k % CNS), (uint32_t)(k / CNS) & 1u);
-    return s_w + (k % CNS) * CWB;
+    c_mb_wait(s_bar + 8 * (k % nslots), (uint32_t)(k / nslots) & 1u);
+    return slot_addr(k % nslots);
   };
   // exchange barriers: thread 0 arms the next phase as soon as the current one has completed
   uint32_t ph_xa = 0, ph_xf = 0;
@@ -351,7 +372,7 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
   };
 
   if (tid == 0) {
-    for (int s = 0; s < 5; ++s) c_mb_init(s_bar + 8 * s, 1);
+    for (int s = 0; s < 8; ++s) c_mb_init(s_bar + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     c_mb_expect(s_bxa, XA_BYTES);
     c_mb_expect(s_bxf, XF_BYTES);
@@ -404,6 +425,52 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
   stamp();
 
   int consumed = 0;
+  // ---- post linears.  capture_post: called when XF holds the rows that leave the last back half; keeps
+  // bf16 copies of what the linears need (the raw rows, the per-query feature, x_in) in tiles nobody else
+  // touches.  run_post: at the very end of the launch, so the front half that may follow is not delayed.
+  bf16* pt0 = reinterpret_cast<bf16*>(sm + OFF_PT);
+  bf16* pt1 = pt0 + CROWS * CALD;
+  bf16* pt2 = reinterpret_cast<bf16*>(sm + OFF_KV);    // only without front halves
+  bool need_ln = false, need_xin = false;
+  for (int p = 0; p < a.npost; ++p)
+    for (int j = 0; j < a.post[p].nchunk; ++j) {
+      need_ln |= a.post[p].seg[j] == SEG_HLN;
+      need_xin |= a.post[p].seg[j] == SEG_XIN;
+    }
+  auto capture_post = [&]() {
+    const int i = warp, rr = min(r0 + i, a.R - 1);     // warp = row, lane = 8 columns
+    const float4 x0 = *reinterpret_cast<const float4*>(xf + i * CFLD + lane * 8);
+    const float4 x1 = *reinterpret_cast<const float4*>(xf + i * CFLD + lane * 8 + 4);
+    *reinterpret_cast<uint4*>(pt0 + i * CALD + lane * 8) =
+        make_uint4(c_pack(x0.x, x0.y), c_pack(x0.z, x0.w), c_pack(x1.x, x1.y), c_pack(x1.z, x1.w));
+    const float* fp = a.feat + (size_t)(rr / a.W) * H + lane * 8;
+    const float4 f0 = __ldg(reinterpret_cast<const float4*>(fp)), f1 = __ldg(reinterpret_cast<const float4*>(fp + 4));
+    *reinterpret_cast<uint4*>(pt1 + i * CALD + lane * 8) =
+        make_uint4(c_pack(f0.x, f0.y), c_pack(f0.z, f0.w), c_pack(f1.x, f1.y), c_pack(f1.z, f1.w));
+    if (need_xin) {
+      const float* xp = a.xin + (size_t)rr * H + lane * 8;
+      const float4 g0 = *reinterpret_cast<const float4*>(xp), g1 = *reinterpret_cast<const float4*>(xp + 4);
+      *reinterpret_cast<uint4*>(pt2 + i * CALD + lane * 8) =
+          make_uint4(c_pack(g0.x, g0.y), c_pack(g0.z, g0.w), c_pack(g1.x, g1.y), c_pack(g1.z, g1.w));
+    }
+  };
+  auto run_post = [&]() {
+    __syncthreads();                                   // the tiles (and LA when norm1 is a segment) are complete
+    for (int p = 0; p < a.npost; ++p) {
+      const float2 bias = bias2(a.post[p].bias);
+      float2 acc = make_float2(0.f, 0.f);
+      for (int j = 0; j < a.post[p].nchunk; ++j) {
+        const int kind = a.post[p].seg[j];
+        const uint32_t tile = kind == SEG_H ? smem_u32(pt0) : (kind == SEG_FEAT ? smem_u32(pt1) : (kind == SEG_XIN ? smem_u32(pt2) : s_la));
+        const float2 d = mma_cols8(tile, wait_w(consumed), warp);
+        acc.x += d.x; acc.y += d.y;
+        __syncthreads();
+        ++consumed;
+        refill(consumed);
+      }
+      if (er < a.R) *reinterpret_cast<float2*>(a.post[p].out + (size_t)er * H + ecol) = make_float2(acc.x + bias.x, acc.y + bias.y);
+    }
+  };
   // ---- back half of a layer after its cross-attention context has been exchanged into XA:
   // h2 = b + ctx.Wo2 + bo2; c = LN3(h2); h3 = c + W2.gelu(W1.c + b1) + b2 (TransformerDecoder.py:82-89)
   auto back_half = [&](const ChainLayer& Lb, float2 b_res, float* hdst, bool feed_front) {
@@ -476,8 +543,18 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
       const float inv = Z > 0.f ? 1.f / Z : 0.f;
       bcast_bf16(s_xa, s_bxa, ai, CCOL * c + 32 * ahl + 8 * (acp >> 2), c_pack(c0 * inv, c1 * inv));
     }
-    back_half(a.back, bres, a.h_out, a.nfront > 0);
-    if (a.nfront == 0) return;         // uniform over the cluster; nothing is in flight towards this CTA
+    back_half(a.back, bres, a.h_out, a.nfront > 0 || a.npost > 0);
+    if (a.nfront == 0) {               // uniform over the cluster
+      if (a.npost > 0) {
+        LnPar lnN;
+        if (need_ln) lnN = ln_load(a.lnN_g, a.lnN_b);
+        wait_xf();
+        capture_post();
+        if (need_ln) ln_rows(xf, lnN, la, own, c, a.hN_out, r0, a.R);   // norm1(h): A tile + own columns to global
+        run_post();
+      }
+      return;                          // nothing is in flight towards this CTA
+    }
   } else {
     // first layer of the step: every CTA builds all 8 input rows locally (no exchange)
     for (int idx = tid; idx < CROWS * (H / 4); idx += CT) {
@@ -515,6 +592,7 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
     const LnPar ln1 = ln_load(Lf.ln1_g, Lf.ln1_b);
     const float2 bq = bias2(Lf.bqkv), bk = bias2(Lf.bqkv + H), bv = bias2(Lf.bqkv + 2 * H);
     if (f > 0 || a.has_back) wait_xf(); else __syncthreads();
+    if (a.npost > 0 && f + 1 == a.nfront && (f > 0 || a.has_back)) capture_post();   // rows leaving the last back half
     stamp();
     // ---- F0: a = LN1(h)
     ln_rows(xf, ln1, la, own, c, nullptr, r0, a.R);
@@ -636,6 +714,9 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
       const float2 q2v = make_float2(d.x + bq2.x, d.y + bq2.y);
       if (!fused) {
         if (er < a.R) *reinterpret_cast<float2*>(a.q2_out + (size_t)er * H + ecol) = q2v;
+        __syncthreads();
+        ++consumed;
+        refill(consumed);
         break;
       }
       *reinterpret_cast<float2*>(q_s + g * CCOL + lcol) = q2v;
@@ -753,6 +834,7 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
       back_half(Lf, b_own, f + 2 == a.nfront ? a.h_fused_out : nullptr, true);
     }
   }
+  if (a.npost > 0) run_post();
   stamp();
 }
 
@@ -788,9 +870,33 @@ static void fill_layer(ChainLayer& L, const case_layer_weights_t* w, void* kc, v
   L.kc = (bf16*)kc; L.vc = (bf16*)vc; L.kx = (const bf16*)kx;
 }
 
+static int fill_post(ChainArgs& a, const case_chain_post_t* post) {
+  if (post == nullptr || post->npost == 0) return 0;
+  CB_REQUIRE(post->npost >= 1 && post->npost <= 2 && post->W >= 1 && post->feat, "case_layer_chain: bad post linears");
+  a.npost = post->npost; a.W = post->W; a.feat = post->feat; a.xin = post->x_in;
+  a.lnN_g = post->ln_g; a.lnN_b = post->ln_b; a.hN_out = post->ln_out;
+  for (int p = 0; p < post->npost; ++p) {
+    const case_post_linear_t& l = post->lin[p];
+    CB_REQUIRE(l.Wc && l.bias && l.out && l.nchunk >= 1 && l.nchunk <= 3, "case_layer_chain: post linear needs Wc, bias, out, 1..3 chunks");
+    a.post[p].w = reinterpret_cast<const char*>(l.Wc); a.post[p].bias = l.bias; a.post[p].out = l.out; a.post[p].nchunk = l.nchunk;
+    for (int j = 0; j < 3; ++j) {
+      a.post[p].seg[j] = j < l.nchunk ? l.seg[j] : 0;
+      if (j < l.nchunk) {
+        CB_REQUIRE(l.seg[j] >= CASE_SEG_H && l.seg[j] <= CASE_SEG_XIN, "case_layer_chain: unknown post segment");
+        CB_REQUIRE(l.seg[j] != CASE_SEG_HLN || (post->ln_g && post->ln_b && post->ln_out), "case_layer_chain: CASE_SEG_HLN needs ln_g, ln_b, ln_out");
+        CB_REQUIRE(l.seg[j] != CASE_SEG_XIN || (post->x_in && a.nfront == 0), "case_layer_chain: CASE_SEG_XIN needs x_in and a launch without front half");
+        CB_REQUIRE(l.seg[j] != CASE_SEG_HLN || a.nfront == 0, "case_layer_chain: CASE_SEG_HLN only in a launch without front half");
+      }
+    }
+  }
+  CB_REQUIRE(a.has_back || a.nfront >= 2, "case_layer_chain: post linears need a back half in the launch");
+  return 0;
+}
+
 static int launch_chain(ChainArgs& a, cudaStream_t stream) {
   a.dbg = g_chain_dbg;
-  const size_t smem = (size_t)OFF_KV + (a.nfront > 0 ? (size_t)4 * CROWS * a.Tmax * 64 : 0);
+  // KV history of the front halves, or (launch without front half) the third post tile
+  const size_t smem = (size_t)OFF_KV + (a.nfront > 0 ? (size_t)4 * CROWS * a.Tmax * 64 : (size_t)CROWS * CALD * 2 + 2 * CWB);
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(layer_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OFF_KV + 4 * CROWS * CTMAX * 64);
@@ -815,7 +921,7 @@ extern "C" int case_layer_chain(const case_layer_weights_t* wb, const case_layer
                                 const float* part_ml, const float* part_acc, int nsplit, float* h_out, void* kcache,
                                 void* vcache, const int32_t* anc, int anc_ld, const int32_t* tok, int tok_ld,
                                 int32_t* prow, int t, int Tmax, float* b_out, float* q2_out, int R, int first,
-                                case_stream_t stream) {
+                                const case_chain_post_t* post, case_stream_t stream) {
   CB_REQUIRE(wb || wf, "case_layer_chain: neither a back nor a front layer given");
   CB_REQUIRE(R > 0 && Tmax >= 1 && Tmax <= CTMAX && t >= 0 && t < Tmax, "case_layer_chain: bad R / t / Tmax (Tmax <= 48)");
   CB_REQUIRE(!wb || (wb->Wc && b_in && part_ml && part_acc && h_out && nsplit >= 1), "case_layer_chain: back half needs Wc, b_in, partials, h_out");
@@ -834,6 +940,7 @@ extern "C" int case_layer_chain(const case_layer_weights_t* wb, const case_layer
     a.h_in = h_in; a.E = E; a.pe = pe; a.emb_scale = emb_scale; a.x_out = x_out;
     a.anc = anc; a.anc_ld = anc_ld; a.tok = tok; a.tok_ld = tok_ld; a.prow_g = prow; a.b_out = b_out; a.q2_out = q2_out;
   }
+  { const int e = fill_post(a, post); if (e) return e; }
   return launch_chain(a, (cudaStream_t)stream);
 }
 
@@ -841,7 +948,8 @@ extern "C" int case_layer_stack(const case_layer_weights_t* layers, int nfused, 
                                 const void* const* kx, const uint8_t* mask0, int W, int S0, const float* h_in,
                                 const float* E, const float* pe, float emb_scale, float* x_out, float* h_fused_out,
                                 const int32_t* anc, int anc_ld, const int32_t* tok, int tok_ld, int32_t* prow, int t,
-                                int Tmax, float* b_out, float* q2_out, int R, int first, case_stream_t stream) {
+                                int Tmax, float* b_out, float* q2_out, int R, int first, const case_chain_post_t* post,
+                                case_stream_t stream) {
   CB_REQUIRE(layers && kcache && vcache && nfused >= 1 && nfused < CMAXF, "case_layer_stack: 1..4 fused layers");
   CB_REQUIRE(R > 0 && Tmax >= 1 && Tmax <= CTMAX && t >= 0 && t < Tmax, "case_layer_stack: bad R / t / Tmax (Tmax <= 48)");
   CB_REQUIRE(kx && mask0 && W >= 1 && S0 >= 1 && S0 <= CS0MAX, "case_layer_stack: the fused cross-attention handles S0 <= 64 keys");
@@ -857,5 +965,7 @@ extern "C" int case_layer_stack(const case_layer_weights_t* layers, int nfused, 
   a.mask0 = mask0; a.h_fused_out = h_fused_out;
   a.h_in = h_in; a.E = E; a.pe = pe; a.emb_scale = emb_scale; a.x_out = x_out;
   a.anc = anc; a.anc_ld = anc_ld; a.tok = tok; a.tok_ld = tok_ld; a.prow_g = prow; a.b_out = b_out; a.q2_out = q2_out;
+  { const int e = fill_post(a, post); if (e) return e; }
+  a.W = W;
   return launch_chain(a, (cudaStream_t)stream);
 }

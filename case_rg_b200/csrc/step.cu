@@ -15,6 +15,7 @@ int g_use_fork = 1;
 int g_use_stack = 1;
 int g_use_tail = 2;
 int g_use_fused_select = 1;
+int g_use_post = 1;
 // side stream + events for the fork/join inside a step (created on first use, outside any capture: the
 // engines run one uncaptured warm-up step before they capture)
 static cudaStream_t g_aux = nullptr;
@@ -76,6 +77,11 @@ extern "C" int case_set_fused_select(int on) {
   g_use_fused_select = on ? 1 : 0;
   return old;
 }
+extern "C" int case_set_post_linears(int on) {
+  const int old = g_use_post;
+  g_use_post = on ? 1 : 0;
+  return old;
+}
 extern "C" int case_set_fork(int on) {
   const int old = g_use_fork;
   g_use_fork = on ? 1 : 0;
@@ -134,7 +140,9 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
   const int32_t* anc = a->anc[t & 1];
 
   // attns[i]: query = [dec_out ; norm2(answer_rep)]   (Model.py:108), then the fused additive attention
-  auto stack_attention = [&](int i, const float* hsrc, float* qa, cudaStream_t s2) -> int {
+  auto stack_attention = [&](int i, const float* hsrc, float* qa, cudaStream_t s2, bool have_qa = false) -> int {
+    if (have_qa) goto additive;          // the query was produced by a post linear of the preceding cluster launch
+    {
     case_rowlin_args_t q;
     memset(&q, 0, sizeof(q));
     q.seg[0] = seg(hsrc, H, H, 1);
@@ -142,6 +150,8 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
     q.nseg = 2; q.K = 2 * H; q.Wt = a->Wqa_t[i]; q.bias = a->bqa[i]; q.N = H; q.out = qa; q.ldo = H;
     q.R = R; q.dtype = dt;
     TRY(case_row_linear(&q, s2));
+    }
+  additive:
     if (i == 1 && dt == CASE_BF16 && a->xidx != nullptr && a->xcount != nullptr)   // valid keys only, balanced splits
       return case_additive_attn_compact(qa, a->U[i], a->Mv[i], a->va[i], a->mask[i], a->prior[i], a->tok, TL, t, B, W,
                                         a->S[i], H, a->nsplit_a[i], a->attn_un[i], a->stats[i], a->ctxp[i],
@@ -197,21 +207,32 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
     // the whole first stack (4 layers over the S0 <= 64 keys of the query memory, cross-attention included)
     // plus the first half-layer of the second stack is ONE launch; otherwise one launch per half-layer pair
     const bool stack0 = g_use_stack && a->S[0] <= case_layer_chain_max_s0();
+    // attention queries, norm1 and gen.0 ride on the cluster launches as post linears (no row_linear launches)
+    const bool post = g_use_post && a->Wqa_c[0] != nullptr && a->Wqa_c[1] != nullptr && a->Wg_c != nullptr;
+    auto qa_post = [&](int i, float* out) {
+      case_chain_post_t p;
+      memset(&p, 0, sizeof(p));
+      p.npost = 1; p.W = W; p.feat = a->feat;
+      p.lin[0].Wc = a->Wqa_c[i]; p.lin[0].bias = a->bqa[i]; p.lin[0].out = out; p.lin[0].nchunk = 2;
+      p.lin[0].seg[0] = CASE_SEG_H; p.lin[0].seg[1] = CASE_SEG_FEAT;
+      return p;
+    };
     int Lstart = 0;
     if (stack0) {
       float* hdst0 = fork ? a->h0 : a->h;
       void* kcs[5]; void* vcs[5]; const void* kxs[4];
       for (int l = 0; l < 5; ++l) { kcs[l] = a->kcache[l]; vcs[l] = a->vcache[l]; }
       for (int l = 0; l < 4; ++l) kxs[l] = a->Kx[l];
+      case_chain_post_t p0 = qa_post(0, a->qa);
       TRY(case_layer_stack(a->layers, 4, kcs, vcs, kxs, a->mask[0], W, a->S[0], nullptr, a->E, a->pe, 16.0f, a->x_in, hdst0,
-                           anc, TL, a->tok, TL, a->prow, t, a->Tmax, a->bbuf, a->q2, R, 1, st));
+                           anc, TL, a->tok, TL, a->prow, t, a->Tmax, a->bbuf, a->q2, R, 1, post ? &p0 : nullptr, st));
       if (fork) {
         CUTRY(cudaEventRecord(g_ev_fork[0], st));
         CUTRY(cudaStreamWaitEvent(g_aux, g_ev_fork[0], 0));
-        TRY(stack_attention(0, hdst0, a->qa, g_aux));
+        TRY(stack_attention(0, hdst0, a->qa, g_aux, post));
         CUTRY(cudaEventRecord(g_ev_join[0], g_aux));
       } else {
-        TRY(stack_attention(0, hdst0, a->qa, st));
+        TRY(stack_attention(0, hdst0, a->qa, st, post));
       }
       TRY(big_xattn(4));
       Lstart = 5;
@@ -220,26 +241,37 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       const case_layer_weights_t* wb = L > 0 ? &a->layers[L - 1] : nullptr;
       const case_layer_weights_t* wf = L < 8 ? &a->layers[L] : nullptr;
       float* hdst = (L == 4 && fork) ? a->h0 : a->h;
+      case_chain_post_t pl;
+      memset(&pl, 0, sizeof(pl));
+      if (post && L == 4) pl = qa_post(0, a->qa);
+      if (post && L == 8) {
+        pl = qa_post(1, fork ? a->qa1 : a->qa);
+        pl.npost = 2; pl.x_in = a->x_in; pl.ln_g = a->lnN_g; pl.ln_b = a->lnN_b; pl.ln_out = a->hN;
+        pl.lin[1].Wc = a->Wg_c; pl.lin[1].bias = a->bg; pl.lin[1].out = a->gfeat; pl.lin[1].nchunk = 3;
+        pl.lin[1].seg[0] = CASE_SEG_XIN; pl.lin[1].seg[1] = CASE_SEG_HLN; pl.lin[1].seg[2] = CASE_SEG_FEAT;
+      }
       TRY(case_layer_chain(wb, wf, nullptr, a->E, a->pe, 16.0f /* sqrt(256) */, a->x_in, a->bbuf, a->part_ml,
                            a->part_acc, L > 0 ? nparts_of(L - 1) : 1, hdst, wf ? a->kcache[L] : nullptr,
                            wf ? a->vcache[L] : nullptr, anc, TL, a->tok, TL, a->prow, t, a->Tmax, a->bbuf, a->q2, R,
-                           L == 0, st));
+                           L == 0, pl.npost ? &pl : nullptr, st));
       if (L == 4 || L == 8) {
         const int i = L / 4 - 1;
         if (fork) {
           CUTRY(cudaEventRecord(g_ev_fork[i], st));
           CUTRY(cudaStreamWaitEvent(g_aux, g_ev_fork[i], 0));
-          TRY(stack_attention(i, hdst, i == 0 ? a->qa : a->qa1, g_aux));
+          TRY(stack_attention(i, hdst, i == 0 ? a->qa : a->qa1, g_aux, post));
           CUTRY(cudaEventRecord(g_ev_join[i], g_aux));
         } else {
-          TRY(stack_attention(i, hdst, a->qa, st));
+          TRY(stack_attention(i, hdst, a->qa, st, post));
         }
       }
       if (L == 8) break;
       TRY(big_xattn(L));
     }
-    TRY(case_layernorm_rows(a->h, a->lnN_g, a->lnN_b, a->hN, R, st));
-    TRY(gen0());
+    if (!post) {
+      TRY(case_layernorm_rows(a->h, a->lnN_g, a->lnN_b, a->hN, R, st));
+      TRY(gen0());
+    }
     TRY(case_vocab_gemm(a->gfeat, a->Wv, nullptr, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, a->vocab_ws, st));
     if (sparse && !getenv("CASE_SKIP_BASE")) TRY(case_vocab_base(a->logits, a->ldv, R, a->V, 0, k2, a->base_ms, a->base_e, a->base_i, st));
     if (fork) {
@@ -406,6 +438,7 @@ extern "C" size_t case_struct_size(int which) {
     case 4: return sizeof(case_step_args_t);
     case 5: return sizeof(gttp_step_args_t);
     case 6: return sizeof(case_tail_args_t);
+    case 7: return sizeof(case_chain_post_t);
     default: return 0;
   }
 }

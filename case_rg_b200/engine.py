@@ -101,6 +101,18 @@ def pack_cluster(mats) -> torch.Tensor:
     return w[:, :, n[:, None], src].permute(1, 0, 2, 3, 4).contiguous()
 
 
+def pack_post(w: torch.Tensor) -> torch.Tensor:
+    """nn.Linear weight [256 out][256 * nchunk in] -> the post-linear layout of the cluster kernels: bf16
+    [4 ranks][nchunk][64 n][256 k], chunk kc of row n stored at kc ^ (n & 7) (csrc/layer_cluster.cu)."""
+    N, K = w.shape
+    if N != 256 or K % 256:
+        raise ValueError(f'pack_post needs a [256, 256*n] weight, got {tuple(w.shape)}')
+    t = w.to(torch.bfloat16).view(4, 64, K // 256, 32, 8)               # [rank][n][chunk][kc][8]
+    n = torch.arange(64, device=w.device)
+    src = torch.arange(32, device=w.device)[None, :] ^ (n & 7)[:, None]
+    return t.permute(0, 2, 1, 3, 4)[:, :, n[:, None], src].contiguous()  # [rank][chunk][n][p][8]: position p holds chunk p ^ (n & 7)
+
+
 def pack_vocab_tc(w: torch.Tensor) -> torch.Tensor:
     """[V, 256] output-projection weight -> bf16 tiles of 128 rows in the UMMA K-major no-swizzle
     canonical layout the tcgen05 kernel bulk-copies straight into shared memory (case_b200.h)."""
@@ -207,6 +219,9 @@ class CaseWeights:
         self.va = [g(f'attns.{i}.v.weight').reshape(-1).contiguous() for i in range(2)]
         self.Uk_t = [g(f'attns.{i}.linear_key.weight').t().contiguous().to(self.tdtype) for i in range(2)]   # [H][H]
         self.Wg_t, self.bg = mat(g('gen.0.weight')), vec(g('gen.0.bias'))
+        bf = self.cdtype == L.BF16
+        self.Wqa_c = [pack_post(g(f'attns.{i}.linear_query.weight')) if bf else None for i in range(2)]
+        self.Wg_c = pack_post(g('gen.0.weight')) if bf else None
         self.Wv = g('gen.2.weight').contiguous().to(self.tdtype)                               # [V][H]
         self.Wv_tc = pack_vocab_tc(g('gen.2.weight')) if self.cdtype == L.BF16 else None
         self.Wm, self.bm = g('mix.weight').contiguous(), vec(g('mix.bias'))
@@ -389,6 +404,8 @@ class CaseDecodeEngine(_EngineBase):
             a.xcount, a.xprefix, a.xslots = self.xcount.data_ptr(), self.xprefix.data_ptr(), self.xslots
             a.xidx, a.xorder = self.xidx.data_ptr(), self.xorder.data_ptr()
         a.qcount = self.qcount.data_ptr()
+        if w.Wg_c is not None:
+            a.Wqa_c[0], a.Wqa_c[1], a.Wg_c = w.Wqa_c[0].data_ptr(), w.Wqa_c[1].data_ptr(), w.Wg_c.data_ptr()
         self.state.bind(a)
         for n in ('x_in', 'h', 'bbuf', 'q2', 'part_ml', 'part_acc', 'qa', 'hN', 'gates', 'fac', 'gfeat', 'logits',
                   'dist', 'top_vals', 'top_idx', 'prow', 'h0', 'qa1', 'base_ms', 'base_e', 'base_i'):
@@ -491,12 +508,12 @@ class CaseDecodeEngine(_EngineBase):
         lib = L.load()
         tail = 2                       # vocab_base + sparse_tail (search bookkeeping fused into it)
         if self.w.cdtype == L.BF16 and self.Tmax <= lib.case_layer_chain_max_tmax():
+            # attention queries, norm1 and gen.0 ride on the cluster launches (post linears): no row_linear launches
             if self.S[0] <= lib.case_layer_chain_max_s0():
-                # layer_stack (first stack + front 4) + 4 x cross + 4 x layer_chain + 2 x (row_linear, additive)
-                # + norm1 + gen.0 + vocab + tail
-                return 1 + 4 + 4 + 4 + 1 + 1 + 1 + tail
-            # 9 x layer_chain + 8 x cross + 2 x (row_linear, additive) + norm1 + gen.0 + vocab + tail
-            return 9 + 8 + 4 + 1 + 1 + 1 + tail
+                # layer_stack (first stack + front 4) + 4 x cross + 4 x layer_chain + 2 x additive + vocab + tail
+                return 1 + 4 + 4 + 2 + 1 + tail
+            # 9 x layer_chain + 8 x cross + 2 x additive + vocab + tail
+            return 9 + 8 + 2 + 1 + tail
         # embed + 8 x (front, cross, back) + 2 x (row_linear, additive) + norm1 + gen.0 + vocab + tail
         return 1 + 24 + 4 + 1 + 1 + 1 + tail
 

@@ -50,7 +50,8 @@ typedef void* case_stream_t; /* cudaStream_t */
 int case_abi_version(void);
 const char* case_last_error(void);
 /* sizeof() of the argument structs below, for binding self-checks: 0 case_seg_t, 1 case_rowlin_args_t,
- * 2 case_layer_weights_t, 3 case_select_args_t, 4 case_step_args_t, 5 gttp_step_args_t, 6 case_tail_args_t */
+ * 2 case_layer_weights_t, 3 case_select_args_t, 4 case_step_args_t, 5 gttp_step_args_t, 6 case_tail_args_t,
+ * 7 case_chain_post_t */
 size_t case_struct_size(int which);
 /* Programmatic dependent launch for every kernel of a step (default on); returns the old setting. */
 int case_set_pdl(int on);
@@ -68,6 +69,9 @@ int case_set_fork(int on);
 int case_set_fused_tail(int on);
 /* Search bookkeeping inside the sparse tail launch instead of a case_beam_select launch (default on). */
 int case_set_fused_select(int on);
+/* Attention-query linears, norm1 and gen.0 as post linears of the cluster launches instead of
+ * case_row_linear / case_layernorm_rows launches (default on; needs Wqa_c / Wg_c in the step arguments). */
+int case_set_post_linears(int on);
 
 /* ---------------------------------------------------------------- row-wise building blocks */
 
@@ -183,6 +187,24 @@ int case_pack_kv_tiles(const void* kv, int src_dtype, int ldkv, int B, int S, in
 int case_layer_back(const float* b_in, const float* part_ml, const float* part_acc, int nsplit,
                     const case_layer_weights_t* w, float* h_out, int R, int dtype, case_stream_t stream);
 
+/* Post linears of a cluster launch: y = [segments] . W^T + bias evaluated on the rows that leave the LAST
+ * back half of the launch, at the end of the launch (CaSE: the attention query [h ; norm2(answer_rep)],
+ * Model.py:108, and gen.0 on [x_in ; norm1(h) ; norm2(answer_rep)], Model.py:115).  Wc: the nn.Linear
+ * weight [256][256 * nchunk] cluster-packed per 256-column chunk: bf16 [4 ranks][nchunk][64 n][256 k], chunk
+ * kc of row n at kc ^ (n & 7).  seg[j] names the input of chunk j. */
+#define CASE_SEG_H 1     /* the rows themselves            */
+#define CASE_SEG_HLN 2   /* LayerNorm(rows; ln_g, ln_b), also written to ln_out */
+#define CASE_SEG_FEAT 3  /* feat[row / W]   ([B][H] fp32)  */
+#define CASE_SEG_XIN 4   /* x_in[row]       ([R][H] fp32; only in launches without a front half) */
+typedef struct {
+  const void* Wc; const float* bias; float* out; int32_t nchunk; int32_t seg[3];
+} case_post_linear_t;
+typedef struct {
+  int32_t npost, W;
+  case_post_linear_t lin[2];
+  const float* feat; const float* x_in; const float* ln_g; const float* ln_b; float* ln_out;
+} case_chain_post_t;
+
 /* Cluster form of the two calls above for bf16 storage: ONE launch runs the second half of layer Lb
  * (wb, may be NULL) followed by the first half of layer Lf (wf, may be NULL) for all rows, i.e. all row
  * work between two cross-attention launches (TransformerDecoder.py:82-89 of layer Lb, then :76-80 of
@@ -196,12 +218,14 @@ int case_layer_back(const float* b_in, const float* part_ml, const float* part_a
  * prow (int32 [R][Tmax], may be NULL): per-step table "physical row | masked bit" of every history
  * position; the launch with first = 1 (the first of a step: anc/tok were written by the launch right
  * before it) derives it from anc/tok and publishes it, later launches of the step read it early.
- * Tmax <= case_layer_chain_max_tmax() (the KV history of the 8 rows lives in shared memory). */
+ * Tmax <= case_layer_chain_max_tmax() (the KV history of the 8 rows lives in shared memory).
+ * post (may be NULL): post linears on the rows leaving the back half (see case_chain_post_t). */
 int case_layer_chain(const case_layer_weights_t* wb, const case_layer_weights_t* wf, const float* h_in,
                      const float* E, const float* pe, float emb_scale, float* x_out, const float* b_in,
                      const float* part_ml, const float* part_acc, int nsplit, float* h_out, void* kcache,
                      void* vcache, const int32_t* anc, int anc_ld, const int32_t* tok, int tok_ld, int32_t* prow,
-                     int t, int Tmax, float* b_out, float* q2_out, int R, int first, case_stream_t stream);
+                     int t, int Tmax, float* b_out, float* q2_out, int R, int first, const case_chain_post_t* post,
+                     case_stream_t stream);
 int case_layer_chain_max_tmax(void);
 
 /* A whole decoder stack over a SHORT memory in one cluster launch: for f = 0 .. nfused-1 the first half
@@ -217,7 +241,7 @@ int case_layer_stack(const case_layer_weights_t* layers, int nfused, void* const
                      const void* const* kx, const uint8_t* mask0, int W, int S0, const float* h_in, const float* E,
                      const float* pe, float emb_scale, float* x_out, float* h_fused_out, const int32_t* anc,
                      int anc_ld, const int32_t* tok, int tok_ld, int32_t* prow, int t, int Tmax, float* b_out,
-                     float* q2_out, int R, int first, case_stream_t stream);
+                     float* q2_out, int R, int first, const case_chain_post_t* post, case_stream_t stream);
 int case_layer_chain_max_s0(void);
 
 /* ---------------------------------------------------------------- additive ("bilinear") attention */
@@ -404,6 +428,7 @@ typedef struct {
   const int32_t* xcount; const int32_t* xprefix; int32_t xslots;
   const int32_t* xidx; const int32_t* xorder;   /* [B][S1] valid positions, [B] queries by valid count (desc) */
   int32_t* qcount;                      /* [B] zeros (may be NULL): lets the sparse tail run the search bookkeeping */
+  const void* Wqa_c[2]; const void* Wg_c;   /* attention-query / gen.0 weights as post linears of the cluster launches (may be NULL) */
 } case_step_args_t;
 
 /* Enqueue one full decode step t (embedding .. select) for all R rows: the body of the eval loop
