@@ -44,6 +44,7 @@ def parse():
     ap.add_argument('--no-fork', action='store_true', help='no side stream for the additive attentions (A/B)')
     ap.add_argument('--no-post', action='store_true', help='row_linear launches instead of post linears (A/B)')
     ap.add_argument('--no-stack', action='store_true', help='no fused first stack (A/B)')
+    ap.add_argument('--kv-prefetch', type=int, default=None, help='percent of the next K|V stream prefetched into L2 by the cluster launches (A/B)')
     ap.add_argument('--streams', type=int, default=1, help='batch slices decoded concurrently on their own streams')
     ap.add_argument('--batch', type=int, default=WORKLOAD['B'])
     ap.add_argument('--beam', type=int, default=WORKLOAD['W'])
@@ -201,6 +202,8 @@ def main():
         L.load().case_set_post_linears(0)
     if args.no_stack:
         L.load().case_set_stack_fusion(0)
+    if args.kv_prefetch is not None:
+        L.load().case_set_kv_prefetch(args.kv_prefetch)
     if args.profile:
         args.streams = 1
 

@@ -106,6 +106,7 @@ _PROTOS = {
     'case_layer_stack': [C.POINTER(LayerWeights), i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, C.c_float, vp, vp, vp, i32, vp,
                          i32, vp, i32, i32, vp, vp, i32, i32, C.POINTER(ChainPost), vp],
     'case_layer_chain_max_s0': [],
+    'case_layer_chain_prefetch': [vp, vp, i32, i32, i32],
     'case_additive_attn': [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp],
     'case_additive_attn_compact': [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp,
                                    vp, vp],
@@ -132,6 +133,7 @@ _PROTOS = {
     'case_set_fused_tail': [i32],
     'case_set_fused_select': [i32],
     'case_set_post_linears': [i32],
+    'case_set_kv_prefetch': [i32],
     'case_decode_step': [C.POINTER(StepArgs), i32, vp],
     'gttp_decode_step': [C.POINTER(GttpStepArgs), i32, vp],
 }

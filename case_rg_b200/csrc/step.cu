@@ -16,6 +16,8 @@ int g_use_stack = 1;
 int g_use_tail = 2;
 int g_use_fused_select = 1;
 int g_use_post = 1;
+int g_prefetch_pct = 0;        // measured: no gain at C2 (the prefetch traffic slows the latency-bound launch more than it helps)
+int g_prefetch_mask = 3;       // bit 0: from the stack launch (layer 4), bit 1: from the chain launches (layers 5..7)
 // side stream + events for the fork/join inside a step (created on first use, outside any capture: the
 // engines run one uncaptured warm-up step before they capture)
 static cudaStream_t g_aux = nullptr;
@@ -80,6 +82,12 @@ extern "C" int case_set_fused_select(int on) {
 extern "C" int case_set_post_linears(int on) {
   const int old = g_use_post;
   g_use_post = on ? 1 : 0;
+  return old;
+}
+extern "C" int case_set_kv_prefetch(int pct) {
+  const int old = g_prefetch_pct;
+  g_prefetch_pct = pct < 0 ? 0 : (pct > 100 ? 100 : pct);
+  if (getenv("CASE_PF_MASK")) g_prefetch_mask = atoi(getenv("CASE_PF_MASK"));
   return old;
 }
 extern "C" int case_set_fork(int on) {
@@ -224,6 +232,7 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       for (int l = 0; l < 5; ++l) { kcs[l] = a->kcache[l]; vcs[l] = a->vcache[l]; }
       for (int l = 0; l < 4; ++l) kxs[l] = a->Kx[l];
       case_chain_post_t p0 = qa_post(0, a->qa);
+      if (xpart && g_prefetch_pct > 0 && (g_prefetch_mask & 1)) case_layer_chain_prefetch(a->Kx[4], a->xprefix, B, a->S[1], g_prefetch_pct);
       TRY(case_layer_stack(a->layers, 4, kcs, vcs, kxs, a->mask[0], W, a->S[0], nullptr, a->E, a->pe, 16.0f, a->x_in, hdst0,
                            anc, TL, a->tok, TL, a->prow, t, a->Tmax, a->bbuf, a->q2, R, 1, post ? &p0 : nullptr, st));
       if (fork) {
@@ -250,6 +259,7 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
         pl.lin[1].Wc = a->Wg_c; pl.lin[1].bias = a->bg; pl.lin[1].out = a->gfeat; pl.lin[1].nchunk = 3;
         pl.lin[1].seg[0] = CASE_SEG_XIN; pl.lin[1].seg[1] = CASE_SEG_HLN; pl.lin[1].seg[2] = CASE_SEG_FEAT;
       }
+      if (xpart && g_prefetch_pct > 0 && (g_prefetch_mask & 2) && L >= 4 && L < 8) case_layer_chain_prefetch(a->Kx[L], a->xprefix, B, a->S[1], g_prefetch_pct);
       TRY(case_layer_chain(wb, wf, nullptr, a->E, a->pe, 16.0f /* sqrt(256) */, a->x_in, a->bbuf, a->part_ml,
                            a->part_acc, L > 0 ? nparts_of(L - 1) : 1, hdst, wf ? a->kcache[L] : nullptr,
                            wf ? a->vcache[L] : nullptr, anc, TL, a->tok, TL, a->prow, t, a->Tmax, a->bbuf, a->q2, R,

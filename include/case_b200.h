@@ -72,6 +72,9 @@ int case_set_fused_select(int on);
 /* Attention-query linears, norm1 and gen.0 as post linears of the cluster launches instead of
  * case_row_linear / case_layernorm_rows launches (default on; needs Wqa_c / Wg_c in the step arguments). */
 int case_set_post_linears(int on);
+/* Percentage of the next cross-attention's K|V stream that the preceding cluster launch prefetches into L2
+ * (default 0 = off: measured neutral-to-negative at the BASELINE shape, kept as an experiment switch). */
+int case_set_kv_prefetch(int pct);
 
 /* ---------------------------------------------------------------- row-wise building blocks */
 
@@ -243,6 +246,10 @@ int case_layer_stack(const case_layer_weights_t* layers, int nfused, void* const
                      int anc_ld, const int32_t* tok, int tok_ld, int32_t* prow, int t, int Tmax, float* b_out,
                      float* q2_out, int R, int first, const case_chain_post_t* post, case_stream_t stream);
 int case_layer_chain_max_s0(void);
+/* The NEXT case_layer_chain / case_layer_stack launch also prefetches into L2 `pct` percent of every
+ * (query, head) run of the compacted K|V stream KV (tile_prefix as in case_cross_attn_part) that the
+ * cross-attention launched after it will read: HBM is idle while the cluster kernels run.  One-shot. */
+int case_layer_chain_prefetch(const void* KV, const int32_t* tile_prefix, int B, int S, int pct);
 
 /* ---------------------------------------------------------------- additive ("bilinear") attention */
 
