@@ -44,6 +44,8 @@ def parse():
     ap.add_argument('--no-fork', action='store_true', help='no side stream for the additive attentions (A/B)')
     ap.add_argument('--no-post', action='store_true', help='row_linear launches instead of post linears (A/B)')
     ap.add_argument('--no-stack', action='store_true', help='no fused first stack (A/B)')
+    ap.add_argument('--no-gate', action='store_true', help='context form of the additive attentions (A/B)')
+    ap.add_argument('--xattn-ctas', type=int, default=None, help='grid of the passage cross-attention (default: one CTA per SM)')
     ap.add_argument('--kv-prefetch', type=int, default=None, help='percent of the next K|V stream prefetched into L2 by the cluster launches (A/B)')
     ap.add_argument('--streams', type=int, default=1, help='batch slices decoded concurrently on their own streams')
     ap.add_argument('--batch', type=int, default=WORKLOAD['B'])
@@ -202,6 +204,10 @@ def main():
         L.load().case_set_post_linears(0)
     if args.no_stack:
         L.load().case_set_stack_fusion(0)
+    if args.no_gate:
+        L.load().case_set_gate_form(0)
+    if args.xattn_ctas is not None:
+        L.load().case_set_xattn_ctas(args.xattn_ctas)
     if args.kv_prefetch is not None:
         L.load().case_set_kv_prefetch(args.kv_prefetch)
     if args.profile:

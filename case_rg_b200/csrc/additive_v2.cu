@@ -510,6 +510,246 @@ __global__ __launch_bounds__(A2T) void additive_attn_v3_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------ gate form
+// CaSE reads the contexts m_i = sum_s a_i[s] mem_i[s] ONLY inside the 3-way mixture gate
+// softmax(W_m [h; m_0; m_1] + b_m) (Model.py:39,117: c_m goes nowhere else), and the gate logits are linear
+// in m_i:  W_m,i . m_i = sum_s a_i[s] (W_m,i . mem_i[s]).  The prefill therefore projects every key once to
+// G[b][s][0..2] = W_m[:, H(1+i):H(2+i)] . mem_i[b][s] (fp32), and the step accumulates 3 numbers per
+// (row, key) instead of H: the value rows - half of the HBM stream and 32 FFMA per key per lane of the
+// kernel above - disappear, what is left is the tanh count.  Same warp-autonomous walk as v3 (per-warp
+// cp.async ring over the Uk.mem rows of the warp's keys, padding skipped per key, multi-value butterfly);
+// lane (key k, row w) keeps the three gate sums of its own (key, row) pairs and they are reduced once.
+// Outputs: scores, stats as above, gate_part [R][nsplit][4] = sum exp(e - m) * G (relative to stats' m).
+constexpr int AG_NST = 3;     // ring stages per warp
+template <int WMAX, bool FAST>
+__global__ __launch_bounds__(A2T, WMAX <= 4 ? 3 : 2) void additive_attn_gate_kernel(
+    const float* __restrict__ qa, const bf16* __restrict__ U, const float4* __restrict__ G,
+    const float* __restrict__ vvec, const uint8_t* __restrict__ mask, const float* __restrict__ prior,
+    const int32_t* __restrict__ tok, int tok_ld, int t, int W, int S, int nsplit, float* __restrict__ scores,
+    float* __restrict__ stats, float* __restrict__ gate_part, const int32_t* __restrict__ cidx,
+    const int32_t* __restrict__ ncount, const int32_t* __restrict__ qorder) {
+  constexpr int KPT = WMAX == 8 ? 2 : 4;               // keys per warp per tile
+  constexpr int NV = KPT * WMAX;                       // partial sums per warp per tile (4, 8, 16)
+  constexpr int LW = WMAX == 1 ? 0 : (WMAX == 2 ? 1 : (WMAX == 4 ? 2 : 3));
+  constexpr int LNV = (KPT == 4 ? 2 : 1) + LW;         // log2(NV)
+  constexpr int SH = 5 - LNV;                          // lane l holds sum number l >> SH
+  constexpr int TILEK = 8 * KPT;
+  constexpr int ROWB = H * 2;                          // staged bytes per key: the U row
+  constexpr int WSTAGE = KPT * ROWB;
+  extern __shared__ __align__(128) unsigned char sm[];
+  __shared__ float wst[8][WMAX][6];
+  pdl_trigger();
+  pdl_wait();
+  const int b = qorder ? qorder[blockIdx.x] : blockIdx.x, sp = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Sv = cidx ? ncount[b] : S;                 // keys to walk
+  const int chunk = split_chunk(Sv, nsplit, A2_SPLIT);
+  const int s_begin = sp * chunk, s_end = min(Sv, s_begin + chunk);
+  const int ntiles = s_end > s_begin ? (s_end - s_begin + TILEK - 1) / TILEK : 0;
+  const int r0 = b * W;
+  const uint8_t* mb = mask + (size_t)b * S;
+  const int32_t* cb = cidx ? cidx + (size_t)b * S : nullptr;
+  const bf16* Ub = U + (size_t)b * S * H;
+  const float4* Gb = G + (size_t)b * S;
+  const float* pb = prior ? prior + (size_t)b * S : nullptr;
+  unsigned char* wbuf = sm + (size_t)warp * AG_NST * WSTAGE;
+  const uint32_t wbuf_s = smem_u32(wbuf);
+
+  float qv[WMAX][8], vv[8];
+#pragma unroll
+  for (int w = 0; w < WMAX; ++w) {
+    const float* q = qa + (size_t)(r0 + min(w, W - 1)) * H + lane * 8;
+    const float4 a0 = *reinterpret_cast<const float4*>(q), a1 = *reinterpret_cast<const float4*>(q + 4);
+    qv[w][0] = a0.x; qv[w][1] = a0.y; qv[w][2] = a0.z; qv[w][3] = a0.w;
+    qv[w][4] = a1.x; qv[w][5] = a1.y; qv[w][6] = a1.z; qv[w][7] = a1.w;
+  }
+  {
+    const float4 a0 = *reinterpret_cast<const float4*>(vvec + lane * 8), a1 = *reinterpret_cast<const float4*>(vvec + lane * 8 + 4);
+    vv[0] = a0.x; vv[1] = a0.y; vv[2] = a0.z; vv[3] = a0.w; vv[4] = a1.x; vv[5] = a1.y; vv[6] = a1.z; vv[7] = a1.w;
+  }
+  const int myj = lane >> SH, myk = myj >> LW, myw = myj & (WMAX - 1);
+  bool rowvalid = myw < W;
+  if (rowvalid && tok) rowvalid = tok[(size_t)(r0 + myw) * tok_ld + t] != 0;
+
+  auto key_of = [&](int ti, int k) { return s_begin + ti * TILEK + warp * KPT + k; };
+  int pos_next = 0;
+  auto valid_bits = [&](int ti) -> unsigned {
+    bool ok = false;
+    pos_next = 0;
+    if (lane < KPT && ti < ntiles) {
+      const int s = key_of(ti, lane);
+      if (cb) { ok = s < s_end; pos_next = ok ? cb[s] : 0; }
+      else { ok = s < s_end && mb[s] != 0; pos_next = s; }
+    }
+    return __ballot_sync(0xffffffffu, ok);
+  };
+  auto issue = [&](int stage, unsigned vbits, int pos_lane) {
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+      const int s = __shfl_sync(0xffffffffu, pos_lane, k);
+      if ((vbits >> k) & 1u) a2_cp16(wbuf_s + stage * WSTAGE + k * ROWB + lane * 16, Ub + (size_t)s * H + lane * 8, 16);
+    }
+  };
+
+  float m_run = -INFINITY, l_run = 0.f, lw_run = 0.f;  // statistics of row myw (replicated over its lanes)
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f;                  // gate sums of this lane's (key slot, row) pairs
+
+  // tiles ti .. ti + AG_NST - 2 are in flight at the top of iteration ti
+  unsigned vbq[AG_NST - 1];
+  int posq[AG_NST - 1];
+#pragma unroll
+  for (int j = 0; j < AG_NST - 1; ++j) {
+    vbq[j] = valid_bits(j);
+    posq[j] = pos_next;
+    if (j < ntiles) issue(j, vbq[j], posq[j]);
+    a2_commit();
+  }
+  int stage = 0, fstage = AG_NST - 1;
+  for (int ti = 0; ti < ntiles; ++ti) {
+    const unsigned vb_new = valid_bits(ti + AG_NST - 1);
+    const int pos_new = pos_next;
+    if (ti + AG_NST - 1 < ntiles) issue(fstage, vb_new, pos_new);
+    a2_commit();
+    const unsigned vb = vbq[0];
+    const int pos = posq[0];
+    // gate projections and prior of this lane's key: in flight during the tanh block
+    const int skey = __shfl_sync(0xffffffffu, pos, myk);
+    const bool ok = rowvalid && ((vb >> myk) & 1u);
+    float4 gk = make_float4(0.f, 0.f, 0.f, 0.f);
+    float pr = 1.f;
+    if (ok) {
+      gk = __ldg(Gb + skey);
+      if (pb) pr = __ldg(pb + skey);
+    }
+    a2_wait<AG_NST - 1>();
+    __syncwarp();
+    const unsigned char* st = wbuf + stage * WSTAGE;
+    float part[NV];
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+#pragma unroll
+      for (int w = 0; w < WMAX; ++w) part[k * WMAX + w] = 0.f;
+      if ((vb >> k) & 1u) {
+        float u[8];
+        ld8c(reinterpret_cast<const bf16*>(st + k * ROWB) + lane * 8, u);
+#pragma unroll
+        for (int w = 0; w < WMAX; ++w) {
+          if (w < W) {
+            float e = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float x = qv[w][i] + u[i];
+              e = fmaf(vv[i], FAST ? tanh_fast(x) : tanh_acc(x), e);
+            }
+            part[k * WMAX + w] = e;
+          }
+        }
+      }
+    }
+    {
+      int n = NV;
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        if (n > 1) {
+          n >>= 1;
+          const bool hi = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < NV / 2; ++i) {
+            if (i < n) {
+              const float keep = hi ? part[i + n] : part[i];
+              const float send = hi ? part[i] : part[i + n];
+              part[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+        } else {
+          part[0] += __shfl_xor_sync(0xffffffffu, part[0], off);
+        }
+      }
+    }
+    const bool inrange = key_of(ti, myk) < s_end;
+    const float e = ok ? part[0] : -INFINITY;
+    if ((lane & ((1 << SH) - 1)) == 0 && myw < W && inrange) scores[(size_t)(r0 + myw) * S + skey] = e;
+    float tmax = e;
+#pragma unroll
+    for (int o = (1 << (SH + LW)); o < 32; o <<= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    const float mn = fmaxf(m_run, tmax);
+    const float sc = (m_run == -INFINITY) ? 0.f : fexp(m_run - mn);
+    const float p = (e == -INFINITY) ? 0.f : fexp(e - mn);
+    float psum = p, pwsum = pr * p;
+#pragma unroll
+    for (int o = (1 << (SH + LW)); o < 32; o <<= 1) {
+      psum += __shfl_xor_sync(0xffffffffu, psum, o);
+      pwsum += __shfl_xor_sync(0xffffffffu, pwsum, o);
+    }
+    l_run = fmaf(l_run, sc, psum);
+    lw_run = fmaf(lw_run, sc, pwsum);
+    m_run = mn;
+    g0 = fmaf(g0, sc, p * gk.x);
+    g1 = fmaf(g1, sc, p * gk.y);
+    g2 = fmaf(g2, sc, p * gk.z);
+    __syncwarp();                                         // this stage is refilled next iteration
+#pragma unroll
+    for (int j = 0; j + 1 < AG_NST - 1; ++j) { vbq[j] = vbq[j + 1]; posq[j] = posq[j + 1]; }
+    vbq[AG_NST - 2] = vb_new;
+    posq[AG_NST - 2] = pos_new;
+    fstage = stage;
+    stage = stage + 1 == AG_NST ? 0 : stage + 1;
+  }
+  a2_wait<0>();
+  // the key slots of a row sit in the upper lane bits: one reduction for the whole walk
+#pragma unroll
+  for (int o = (1 << (SH + LW)); o < 32; o <<= 1) {
+    g0 += __shfl_xor_sync(0xffffffffu, g0, o);
+    g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+    g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+  }
+  if ((lane & ((1 << SH) - 1)) == 0 && myk == 0 && myw < W) {
+    float* d = wst[warp][myw];
+    d[0] = m_run; d[1] = l_run; d[2] = lw_run; d[3] = g0; d[4] = g1; d[5] = g2;
+  }
+  __syncthreads();
+  if (tid < W) {
+    float Mx = -INFINITY;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) Mx = fmaxf(Mx, wst[g][tid][0]);
+    float l = 0.f, lw = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float f = (wst[g][tid][0] == -INFINITY) ? 0.f : fexp(wst[g][tid][0] - Mx);
+      l = fmaf(wst[g][tid][1], f, l);
+      lw = fmaf(wst[g][tid][2], f, lw);
+      a0 = fmaf(wst[g][tid][3], f, a0);
+      a1 = fmaf(wst[g][tid][4], f, a1);
+      a2 = fmaf(wst[g][tid][5], f, a2);
+    }
+    const size_t o = (size_t)(r0 + tid) * nsplit + sp;
+    reinterpret_cast<float4*>(stats)[o] = make_float4(Mx, l, lw, 0.f);
+    reinterpret_cast<float4*>(gate_part)[o] = make_float4(a0, a1, a2, 0.f);
+  }
+}
+
+template <int WMAX>
+static int launch_gate(int fast, const float* qa, const void* U, const float* G, const float* v, const uint8_t* mask,
+                       const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S, int nsplit,
+                       float* scores, float* stats, float* gate_part, const int32_t* cidx, const int32_t* ncount,
+                       const int32_t* qorder, cudaStream_t st) {
+  constexpr int KPT = WMAX == 8 ? 2 : 4;
+  const size_t smem = (size_t)8 * AG_NST * KPT * H * 2;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(additive_attn_gate_kernel<WMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(additive_attn_gate_kernel<WMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr = true;
+  }
+  if (fast)
+    launch_k(additive_attn_gate_kernel<WMAX, true>, dim3(B, nsplit), A2T, smem, st, qa, (const bf16*)U, (const float4*)G, v,
+             mask, prior, tok, tok_ld, t, W, S, nsplit, scores, stats, gate_part, cidx, ncount, qorder);
+  else
+    launch_k(additive_attn_gate_kernel<WMAX, false>, dim3(B, nsplit), A2T, smem, st, qa, (const bf16*)U, (const float4*)G, v,
+             mask, prior, tok, tok_ld, t, W, S, nsplit, scores, stats, gate_part, cidx, ncount, qorder);
+  return check_launch("case_additive_attn_gate");
+}
+
 template <int WMAX, int DV, bool FAST>
 static int launch_v2(const float* qa, const void* U, const void* Mv, const float* v, const uint8_t* mask,
                      const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S, int nsplit,
@@ -591,4 +831,26 @@ extern "C" int case_additive_attn_compact(const float* qa, const void* U, const 
   cb::g_additive_impl = old;
   cb::g_add_cidx = cb::g_add_ncount = cb::g_add_qorder = nullptr;
   return rc;
+}
+
+/* Gate form of the additive attention (bf16 keys): G fp32 [B][S][4] = (W_m slice of memory i) . mem[b][s]
+ * (3 gate logits' worth per key, 4th unused) replaces the value rows; gate_part [R][nsplit][4] =
+ * sum exp(e - m) * G relative to the split's m in stats.  cidx / ncount / qorder as in
+ * case_additive_attn_compact, or all NULL to walk every position under the mask. */
+extern "C" int case_additive_attn_gate(const float* qa, const void* U, const float* G, const float* v, const uint8_t* mask,
+                                       const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S,
+                                       int nsplit, float* attn_un, float* stats, float* gate_part, int fast_tanh,
+                                       const int32_t* cidx, const int32_t* ncount, const int32_t* qorder,
+                                       case_stream_t stream) {
+  using namespace cb;
+  CB_REQUIRE(qa && U && G && v && mask && attn_un && stats && gate_part, "case_additive_attn_gate: null pointer");
+  CB_REQUIRE(B > 0 && W >= 1 && W <= CASE_MAX_W && S > 0 && nsplit >= 1 && nsplit <= CASE_MAX_SPLIT, "case_additive_attn_gate: bad sizes");
+  CB_REQUIRE((cidx == nullptr) == (ncount == nullptr), "case_additive_attn_gate: cidx and ncount go together");
+  CB_REQUIRE((uintptr_t)G % 16 == 0 && (uintptr_t)U % 16 == 0 && (uintptr_t)stats % 16 == 0 && (uintptr_t)gate_part % 16 == 0,
+             "case_additive_attn_gate: U, G, stats, gate_part must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (W <= 1) return launch_gate<1>(fast_tanh, qa, U, G, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, attn_un, stats, gate_part, cidx, ncount, qorder, st);
+  if (W <= 2) return launch_gate<2>(fast_tanh, qa, U, G, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, attn_un, stats, gate_part, cidx, ncount, qorder, st);
+  if (W <= 4) return launch_gate<4>(fast_tanh, qa, U, G, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, attn_un, stats, gate_part, cidx, ncount, qorder, st);
+  return launch_gate<8>(fast_tanh, qa, U, G, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, attn_un, stats, gate_part, cidx, ncount, qorder, st);
 }

@@ -165,28 +165,45 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
     wstamp();
     const int col = tid < H ? tid : 0;                     // threads past H repeat column 0 and contribute nothing
     const float y = a.hN[(size_t)r * H + col];
-    float Z[2], Q[2], cx[2];
+    float Z[2], Q[2], cx[2] = {0.f, 0.f};
+    float gsum[3] = {0.f, 0.f, 0.f};                       // gate form: W_m,i . m_i summed over both memories
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int ns = a.ns[i];
       const float4* st = reinterpret_cast<const float4*>(a.stats[i]) + (size_t)r * ns;
-      const float* cp = a.ctxp[i] + (size_t)r * ns * H + col;
       float Mx = -INFINITY;
 #pragma unroll 4
       for (int j = 0; j < ns; ++j) Mx = fmaxf(Mx, __ldg(st + j).x);
-      float z = 0.f, q = 0.f, acc = 0.f;
+      float z = 0.f, q = 0.f;
+      if (a.gate_ctx) {
+        const float4* gp = reinterpret_cast<const float4*>(a.ctxp[i]) + (size_t)r * ns;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll 4
-      for (int j = 0; j < ns; ++j) {
-        const float4 sj = __ldg(st + j);
-        const float cj = cp[(size_t)j * H];
-        const float e = (sj.x == -INFINITY) ? 0.f : fexp(sj.x - Mx);
-        z = fmaf(sj.y, e, z);
-        q = fmaf(sj.z, e, q);
-        acc = fmaf(cj, e, acc);
+        for (int j = 0; j < ns; ++j) {
+          const float4 sj = __ldg(st + j);
+          const float4 gj = gp[j];
+          const float e = (sj.x == -INFINITY) ? 0.f : fexp(sj.x - Mx);
+          z = fmaf(sj.y, e, z);
+          q = fmaf(sj.z, e, q);
+          a0 = fmaf(gj.x, e, a0); a1 = fmaf(gj.y, e, a1); a2 = fmaf(gj.z, e, a2);
+        }
+        if (z > 0.f) { gsum[0] += a0 / z; gsum[1] += a1 / z; gsum[2] += a2 / z; }
+      } else {
+        const float* cp = a.ctxp[i] + (size_t)r * ns * H + col;
+        float acc = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < ns; ++j) {
+          const float4 sj = __ldg(st + j);
+          const float cj = cp[(size_t)j * H];
+          const float e = (sj.x == -INFINITY) ? 0.f : fexp(sj.x - Mx);
+          z = fmaf(sj.y, e, z);
+          q = fmaf(sj.z, e, q);
+          acc = fmaf(cj, e, acc);
+        }
+        cx[i] = z > 0.f ? acc / z : 0.f;
+        if (tid < H) a.ctx[i][(size_t)r * H + tid] = cx[i];
       }
       M[i] = Mx; Z[i] = z; Q[i] = q;
-      cx[i] = z > 0.f ? acc / z : 0.f;
-      if (tid < H) a.ctx[i][(size_t)r * H + tid] = cx[i];
       wstamp();
     }
     float part[3];
@@ -200,7 +217,7 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
     wstamp();
     __syncthreads();
     wstamp();
-    float lg[3] = {__ldg(a.bm), __ldg(a.bm + 1), __ldg(a.bm + 2)};
+    float lg[3] = {__ldg(a.bm) + gsum[0], __ldg(a.bm + 1) + gsum[1], __ldg(a.bm + 2) + gsum[2]};
 #pragma unroll
     for (int w = 0; w < TSW; ++w) { lg[0] += sh[w * 3]; lg[1] += sh[w * 3 + 1]; lg[2] += sh[w * 3 + 2]; }
     const float mx = fmaxf(lg[0], fmaxf(lg[1], lg[2]));
@@ -400,7 +417,7 @@ extern "C" int case_sparse_tail(const case_tail_args_t* a, const float* base_ms,
   CB_REQUIRE(a->R > 0 && a->W >= 1 && a->V > 0 && a->top_vals && a->top_idx, "case_sparse_tail: bad sizes / outputs");
   CB_REQUIRE(a->K >= 1 && a->K <= CASE_MAX_W && k2 >= a->K && k2 <= 2 * CASE_MAX_W, "case_sparse_tail: need K <= k2 <= 16");
   CB_REQUIRE(a->nmem >= 1 && a->nmem <= 2, "case_sparse_tail: nmem must be 1 or 2");
-  CB_REQUIRE(!a->do_finalize || (a->nmem == 2 && a->hN && a->stats[0] && a->stats[1] && a->ctxp[0] && a->ctxp[1] && a->Wm && a->bm && a->ctx[0] && a->ctx[1] && a->ns[0] >= 1 && a->ns[1] >= 1 && a->ns[0] <= CASE_MAX_SPLIT && a->ns[1] <= CASE_MAX_SPLIT),
+  CB_REQUIRE(!a->do_finalize || (a->nmem == 2 && a->hN && a->stats[0] && a->stats[1] && a->ctxp[0] && a->ctxp[1] && a->Wm && a->bm && (a->gate_ctx || (a->ctx[0] && a->ctx[1])) && a->ns[0] >= 1 && a->ns[1] >= 1 && a->ns[0] <= CASE_MAX_SPLIT && a->ns[1] <= CASE_MAX_SPLIT),
              "case_sparse_tail: the CaSE finaliser needs hN, stats, ctxp, Wm, bm, ctx for both memories");
   int total = 0;
   for (int i = 0; i < a->nmem; ++i) {

@@ -16,6 +16,7 @@ int g_use_stack = 1;
 int g_use_tail = 2;
 int g_use_fused_select = 1;
 int g_use_post = 1;
+int g_use_gate = 1;
 int g_prefetch_pct = 0;        // measured: no gain at C2 (the prefetch traffic slows the latency-bound launch more than it helps)
 int g_prefetch_mask = 3;       // bit 0: from the stack launch (layer 4), bit 1: from the chain launches (layers 5..7)
 // side stream + events for the fork/join inside a step (created on first use, outside any capture: the
@@ -84,6 +85,11 @@ extern "C" int case_set_post_linears(int on) {
   g_use_post = on ? 1 : 0;
   return old;
 }
+extern "C" int case_set_gate_form(int on) {
+  const int old = g_use_gate;
+  g_use_gate = on ? 1 : 0;
+  return old;
+}
 extern "C" int case_set_kv_prefetch(int pct) {
   const int old = g_prefetch_pct;
   g_prefetch_pct = pct < 0 ? 0 : (pct > 100 ? 100 : pct);
@@ -147,6 +153,13 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
   const int R = a->R, B = a->B, W = a->W, TL = a->Tmax + 1, dt = a->dtype;
   const int32_t* anc = a->anc[t & 1];
 
+  // search path: the sparse tail (touched ids + base candidates); `generate` face: the dense fused tail
+  const int k2 = 2 * W;
+  const bool sparse = g_use_tail == 2 && !a->materialize_only && a->base_ms && a->base_e && a->base_i && a->V >= k2 &&
+                      a->S[0] + a->S[1] <= case_sparse_tail_max_sources();
+  // gate form of the additive attentions: the contexts only feed the mixture gate, so 3 gate-projected numbers
+  // per key replace the value rows (needs the sparse tail, which merges gate partials instead of contexts)
+  const bool gate = g_use_gate && sparse && dt == CASE_BF16 && a->Gv[0] != nullptr && a->Gv[1] != nullptr;
   // attns[i]: query = [dec_out ; norm2(answer_rep)]   (Model.py:108), then the fused additive attention
   auto stack_attention = [&](int i, const float* hsrc, float* qa, cudaStream_t s2, bool have_qa = false) -> int {
     if (have_qa) goto additive;          // the query was produced by a post linear of the preceding cluster launch
@@ -160,6 +173,12 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
     TRY(case_row_linear(&q, s2));
     }
   additive:
+    if (gate) {
+      const bool cmp = i == 1 && a->xidx != nullptr && a->xcount != nullptr;
+      return case_additive_attn_gate(qa, a->U[i], a->Gv[i], a->va[i], a->mask[i], a->prior[i], a->tok, TL, t, B, W, a->S[i],
+                                     a->nsplit_a[i], a->attn_un[i], a->stats[i], a->ctxp[i], a->fast_tanh,
+                                     cmp ? a->xidx : nullptr, cmp ? a->xcount : nullptr, cmp ? a->xorder : nullptr, s2);
+    }
     if (i == 1 && dt == CASE_BF16 && a->xidx != nullptr && a->xcount != nullptr)   // valid keys only, balanced splits
       return case_additive_attn_compact(qa, a->U[i], a->Mv[i], a->va[i], a->mask[i], a->prior[i], a->tok, TL, t, B, W,
                                         a->S[i], H, a->nsplit_a[i], a->attn_un[i], a->stats[i], a->ctxp[i],
@@ -190,10 +209,6 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       return (int)_ce;                                                   \
     }                                                                    \
   } while (0)
-  // search path: the sparse tail (touched ids + base candidates); `generate` face: the dense fused tail
-  const int k2 = 2 * W;
-  const bool sparse = g_use_tail == 2 && !a->materialize_only && a->base_ms && a->base_e && a->base_i && a->V >= k2 &&
-                      a->S[0] + a->S[1] <= case_sparse_tail_max_sources();
   // cross-attention over memory i for layer L: compacted + balanced partition where the prefill provided it
   const bool xpart = dt == CASE_BF16 && a->xcount != nullptr && a->xprefix != nullptr && a->xslots > 0;
   auto big_xattn = [&](int L) -> int {
@@ -328,6 +343,7 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       ta.attn_un[i] = a->attn_un[i];
     }
     if (a->materialize_only) { ta.dist = a->dist; } else { ta.top_vals = a->top_vals; ta.top_idx = a->top_idx; }
+    ta.gate_ctx = gate ? 1 : 0;
     if (sparse) {
       const bool fuse_sel = a->qcount != nullptr && g_use_fused_select;
       case_select_args_t sel = select_args(a->mode, B, W, t, a->max_len, a->Tmax, a->BOS, a->EOS, a->UNK, a->PAD,

@@ -290,6 +290,16 @@ __global__ __launch_bounds__(256) void pack_kv_gather_kernel(const bf16* __restr
 
 using namespace cb;
 
+static int g_xp_ctas = 0;   // 0 = one CTA per SM
+/* Grid of case_cross_attn_part: n CTAs (0 = one per SM, the default).  A smaller grid leaves SMs to kernels of
+ * another stream (batch slices decoded concurrently: one slice streams K|V while the other is in its
+ * latency-bound cluster launches); returns the old setting. */
+extern "C" int case_set_xattn_ctas(int n) {
+  const int old = g_xp_ctas;
+  g_xp_ctas = n < 0 ? 0 : n;
+  return old;
+}
+
 extern "C" int case_cross_attn_part_slots(int S) { return ((S + 63) / 64 + XP_MIN_TILES - 1) / XP_MIN_TILES + 2; }
 
 extern "C" int case_cross_attn_part(const float* q2, const void* KV, const int32_t* ncount, const int32_t* tile_prefix,
@@ -314,7 +324,8 @@ extern "C" int case_cross_attn_part(const float* q2, const void* KV, const int32
     if (nsm <= 0) nsm = 148;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  launch_k(cross_attn_part_kernel, nsm, XP_WARPS * 32, smem, st, q2, (const bf16*)KV, ncount, tile_prefix, B, W,
+  const int grid = g_xp_ctas > 0 && g_xp_ctas < nsm ? g_xp_ctas : nsm;
+  launch_k(cross_attn_part_kernel, grid, XP_WARPS * 32, smem, st, q2, (const bf16*)KV, ncount, tile_prefix, B, W,
            (S + 63) / 64, nslot, part_ml, part_acc);
   return check_launch("case_cross_attn_part");
 }

@@ -225,6 +225,9 @@ class CaseWeights:
         self.Wv = g('gen.2.weight').contiguous().to(self.tdtype)                               # [V][H]
         self.Wv_tc = pack_vocab_tc(g('gen.2.weight')) if self.cdtype == L.BF16 else None
         self.Wm, self.bm = g('mix.weight').contiguous(), vec(g('mix.bias'))
+        # gate form (CaSE/Model.py:39,117): W_m's slice for context i as a [H][4] projection of the memory keys
+        self.Wm_g = [torch.cat([self.Wm[:, H * (1 + i):H * (2 + i)].t(), torch.zeros(H, 1, device=dev)], 1).contiguous()
+                     for i in range(2)]
 
 
 class _SearchState:
@@ -324,6 +327,7 @@ class CaseDecodeEngine(_EngineBase):
             self.nsx = [_nsplit(B, s, 2 * 64, 128) for s in self.S]
         else:                          # SIMT kernel: CTA = (query, head, split)
             self.nsx = [_nsplit(B * L.NH, s, L.XATTN_TILE, 6 * 148) for s in self.S]
+        target_ctas = int(os.environ.get('CASE_ADD_CTAS', target_ctas))
         self.nsa = [_nsplit_additive(B, s, weights.cdtype == L.BF16, target_ctas) for s in self.S]
         # per-batch tensors
         self.feat = z(B, H)
@@ -336,6 +340,8 @@ class CaseDecodeEngine(_EngineBase):
             self.Vx = [torch.zeros(B, L.NH, self.S[l // 4], L.HD, dtype=td, device=dev) for l in range(8)]
         self.U = [torch.zeros(B, s, H, dtype=td, device=dev) for s in self.S]
         self.Mv = [torch.zeros(B, s, H, dtype=td, device=dev) for s in self.S]
+        # gate-projected keys for the search path (case_additive_attn_gate): 3 gate logits' worth per key
+        self.Gv = [z(B, s, 4) for s in self.S] if weights.cdtype == L.BF16 else None
         self.mask = [torch.zeros(B, s, dtype=torch.uint8, device=dev) for s in self.S]
         self.prior = [z(B, s) for s in self.S]
         self.map = torch.zeros(B, S0 + S1, dtype=torch.int32, device=dev)
@@ -386,6 +392,8 @@ class CaseDecodeEngine(_EngineBase):
             a.attn_un[i], a.stats[i], a.ctxp[i] = (self.attn_un[i].data_ptr(), self.stats[i].data_ptr(),
                                                    self.ctxp[i].data_ptr())
             a.ctx[i] = self.ctx[i].data_ptr()
+            if self.Gv is not None:
+                a.Gv[i] = self.Gv[i].data_ptr()
         a.map_off[0], a.map_off[1] = 0, self.S[0]
         a.max_len, a.BOS, a.EOS, a.UNK, a.PAD, a.materialize_only = self.Tmax, BOS, EOS, UNK, PAD, 0
         a.E, a.pe = w.E.data_ptr(), w.pe.data_ptr()
@@ -456,6 +464,8 @@ class CaseDecodeEngine(_EngineBase):
                     self.Vx[i * 4 + l].copy_(kv[l, 1])
             torch.mm(flat, w.Uk_t[i], out=self.U[i].view(B * S, H))
             self.Mv[i].copy_(m)
+            if self.Gv is not None:
+                torch.mm(mems[i].to(dev, torch.float32).reshape(B * S, H), w.Wm_g[i], out=self.Gv[i].view(B * S, 4))
             self.mask[i].copy_(masks[i].to(dev).to(torch.uint8))
             self.prior[i].copy_(priors[i].to(dev, torch.float32))
         self.map.copy_(source_map.to(dev).to(torch.int32))

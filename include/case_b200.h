@@ -72,6 +72,12 @@ int case_set_fused_select(int on);
 /* Attention-query linears, norm1 and gen.0 as post linears of the cluster launches instead of
  * case_row_linear / case_layernorm_rows launches (default on; needs Wqa_c / Wg_c in the step arguments). */
 int case_set_post_linears(int on);
+/* Gate form of the additive attentions on the search path (default on; needs Gv in the step arguments, bf16
+ * and the sparse tail): case_additive_attn_gate instead of case_additive_attn[_compact]. */
+int case_set_gate_form(int on);
+/* Grid of case_cross_attn_part: n CTAs instead of one per SM (0 = default).  For batch slices decoded
+ * concurrently on several streams: a smaller grid leaves SMs to the other slice's cluster launches. */
+int case_set_xattn_ctas(int n);
 /* Percentage of the next cross-attention's K|V stream that the preceding cluster launch prefetches into L2
  * (default 0 = off: measured neutral-to-negative at the BASELINE shape, kept as an experiment switch). */
 int case_set_kv_prefetch(int pct);
@@ -276,6 +282,16 @@ int case_additive_attn_compact(const float* qa, const void* U, const void* Mv, c
                                const int32_t* cidx, const int32_t* ncount, const int32_t* qorder,
                                case_stream_t stream);
 
+/* Gate form (bf16 keys) for CaSE's search path: the contexts m_i are read only by the 3-way mixture gate
+ * softmax(W_m [h; m_0; m_1] + b_m) (CaSE/Model.py:39,117), which is linear in m_i, so the prefill projects
+ * every key once to G fp32 [B][S][4] = (W_m[:, H(1+i):H(2+i)] . mem_i[b][s], 0) and the step accumulates
+ * gate_part [R][nsplit][4] = sum exp(e-m) * G instead of ctx_part (no value rows are read).  attn_un and
+ * stats as in case_additive_attn; cidx / ncount / qorder as in case_additive_attn_compact or all NULL. */
+int case_additive_attn_gate(const float* qa, const void* U, const float* G, const float* v, const uint8_t* mask,
+                            const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S,
+                            int nsplit, float* attn_un, float* stats, float* gate_part, int fast_tanh,
+                            const int32_t* cidx, const int32_t* ncount, const int32_t* qorder, case_stream_t stream);
+
 /* bf16 additive attention kernel: 3 (default) = warp-autonomous (no block barrier in the key loop, padding
  * skipped per key), 2 = block-synchronous 32-key tiles; returns the old setting (A/B aid). */
 int case_set_additive_impl(int impl);
@@ -337,6 +353,7 @@ typedef struct {
   float* ctx[2]; float* gates; float* fac;
   const int32_t* map; const float* prior[2]; const float* attn_un[2];
   float* top_vals; int32_t* top_idx; float* dist;
+  int32_t gate_ctx;   /* case_sparse_tail only: ctxp[i] hold gate_part [R][ns][4] of case_additive_attn_gate (ctx[i] unused) */
 } case_tail_args_t;
 int case_row_tail(const case_tail_args_t* a, case_stream_t stream);
 int case_row_tail_max_vocab(void);
@@ -436,6 +453,8 @@ typedef struct {
   const int32_t* xidx; const int32_t* xorder;   /* [B][S1] valid positions, [B] queries by valid count (desc) */
   int32_t* qcount;                      /* [B] zeros (may be NULL): lets the sparse tail run the search bookkeeping */
   const void* Wqa_c[2]; const void* Wg_c;   /* attention-query / gen.0 weights as post linears of the cluster launches (may be NULL) */
+  const float* Gv[2];                   /* [B][S_i][4] fp32 gate-projected memories (may be NULL): the search path then runs
+                                           case_additive_attn_gate and never reads Mv */
 } case_step_args_t;
 
 /* Enqueue one full decode step t (embedding .. select) for all R rows: the body of the eval loop

@@ -36,7 +36,7 @@ def main():
 
     def launch():
         return lib.case_layer_stack(a.layers, 4, kcs, vcs, kxs, a.mask[0], W, 60, None, a.E, a.pe, 16.0, a.x_in, a.h0,
-                                    a.anc[t & 1], T + 1, a.tok, T + 1, a.prow, t, T, a.bbuf, a.q2, eng.R, 1, st)
+                                    a.anc[t & 1], T + 1, a.tok, T + 1, a.prow, t, T, a.bbuf, a.q2, eng.R, 1, None, st)
     names = ['start->resident', 'pdl_wait']
     for f in range(5):
         names += [f'L{f} {n}' for n in FRONT]

@@ -139,6 +139,65 @@ def test_additive_attention_vs_torch(W, S, DV, nsplit, use_prior, dtype):
     assert rel_err((Q / Z.clamp_min(1e-30))[live], (pr * a).sum(1)[live]) < 2e-4
 
 
+@pytest.mark.parametrize('compact', [False, True])
+@pytest.mark.parametrize('W,S,nsplit,use_prior', [(1, 60, 1, True), (4, 2560, 9, True), (4, 1000, 3, False), (8, 333, 2, True),
+                                                  (2, 130, 2, False), (3, 77, 1, True)])
+def test_additive_attention_gate_form_vs_torch(W, S, nsplit, use_prior, compact):
+    """case_additive_attn_gate: scores, softmax partials and the gate partials sum_s exp(e-m) G[s] against torch
+    (masked walk and the compacted valid-key walk), incl. all-padding tiles, an empty query and a PAD-input row."""
+    from case_rg_b200 import _lib as L
+    B, H = 4, 256
+    g = torch.Generator().manual_seed(W * 100 + S + 7)
+    qa = torch.randn(B * W, H, generator=g).to(DEV)
+    U = torch.randn(B, S, H, generator=g).to(DEV).to(torch.bfloat16)
+    G = torch.randn(B, S, 4, generator=g).to(DEV)
+    v = (torch.randn(H, generator=g) * 0.3).to(DEV)
+    mask = torch.rand(B, S, generator=g) > 0.25
+    mask[:, 0] = True
+    if S > 200:
+        mask[1, 64:192] = False            # whole tiles of padding
+    mask[3] = False                        # a query without any valid key
+    mask = mask.to(DEV)
+    prior = torch.rand(B, S, generator=g).to(DEV) if use_prior else None
+    tok = torch.ones(B * W, 4, dtype=torch.int32, device=DEV)
+    tok[0, 2] = 0                          # row 0 consumes a PAD token at t = 2 -> fully masked row
+    scores = torch.full((B * W, S), float('nan'), device=DEV)
+    stats = torch.zeros(B * W, nsplit, 4, device=DEV)
+    gpart = torch.zeros(B * W, nsplit, 4, device=DEV)
+    cidx = ncount = qorder = None
+    if compact:
+        cidx = torch.argsort(~mask, dim=1, stable=True).to(torch.int32)
+        ncount = mask.sum(1).to(torch.int32)
+        qorder = torch.argsort(ncount, descending=True, stable=True).to(torch.int32)
+        scores.masked_fill_(~mask.repeat_interleave(W, 0), float('-inf'))      # the caller's job in this form
+    L.call('case_additive_attn_gate', qa.data_ptr(), U.data_ptr(), G.data_ptr(), v.data_ptr(),
+           mask.to(torch.uint8).data_ptr(), L.ptr(prior), tok.data_ptr(), 4, 2, B, W, S, nsplit, scores.data_ptr(),
+           stats.data_ptr(), gpart.data_ptr(), 0, L.ptr(cidx), L.ptr(ncount), L.ptr(qorder),
+           torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    e = (torch.tanh(qa.view(B, W, 1, H) + U.float().view(B, 1, S, H)) @ v).view(B * W, S)
+    ok = mask.repeat_interleave(W, 0).clone()
+    ok[0] = False
+    e = e.masked_fill(~ok, float('-inf'))
+    assert torch.equal(torch.isinf(scores), torch.isinf(e))
+    fin = ~torch.isinf(e)
+    assert float((scores[fin] - e[fin]).abs().max()) < 1e-4 * max(1.0, float(e[fin].abs().max()))
+    m = stats[..., 0]
+    M = m.max(1, keepdim=True).values
+    w = torch.where(torch.isinf(m), torch.zeros_like(m), torch.exp(m - M))
+    Z = (stats[..., 1] * w).sum(1)
+    Q = (stats[..., 2] * w).sum(1)
+    gs = (gpart * w.unsqueeze(-1)).sum(1) / Z.clamp_min(1e-30).unsqueeze(-1)
+    a = torch.softmax(e, 1)
+    a = torch.where(torch.isnan(a), torch.zeros_like(a), a)
+    want = torch.bmm(a.view(B, W, S), G).view(B * W, 4)
+    live = Z > 0
+    assert bool((~live)[0]) and bool(live[1:3 * W].all()) and not bool(live[3 * W:].any())
+    assert rel_err(gs[live][:, :3], want[live][:, :3]) < 2e-4
+    pr = prior.repeat_interleave(W, 0) if use_prior else torch.ones_like(a)
+    assert rel_err((Q / Z.clamp_min(1e-30))[live], (pr * a).sum(1)[live]) < 2e-4
+
+
 # --------------------------------------------------------------------------- cluster layer kernels
 def _chain_case(B, W, T, V=3000, seeds=(51, 52)):
     from case_rg_b200 import synthetic as syn
@@ -436,3 +495,23 @@ def test_sparse_tail_matches_dense_tail(R, W, V, S0, S1, K, finalize):
     if not bool(same.all()):   # only allowed where summation order flipped two values that agree to 2 ulp
         wv = torch.gather(dense['dist'][:, :V].cpu(), 1, want)
         assert torch.allclose(wv[~same], ref_v[~same], rtol=1e-5, atol=0), (got_i, want)
+    if finalize:
+        # gate form: ctxp replaced by the gate partials sum exp(e-m) (W_m,i . mem) - the same gates, factors and top-k
+        a3, gform = args()
+        gp = [torch.einsum('rnh,kh->rnk', ctxp[i], Wm[:, H * (1 + i):H * (2 + i)]) for i in range(2)]
+        gp = [torch.cat([x, torch.zeros(R, x.size(1), 1, **f32)], 2).contiguous() for x in gp]
+        for i in range(2):
+            a3.ctxp[i], a3.ctx[i] = gp[i].data_ptr(), None
+        a3.gate_ctx = 1
+        L.check(lib.case_sparse_tail(C.byref(a3), base_ms.data_ptr(), base_e.data_ptr(), base_i.data_ptr(), k2, None, None, st),
+                'case_sparse_tail(gate)')
+        torch.cuda.synchronize()
+        assert torch.allclose(gform['gates'], dense['gates'], rtol=1e-4, atol=1e-6)
+        assert torch.allclose(gform['fac'], dense['fac'], rtol=1e-4, atol=1e-7)
+        gi = gform['ti'].cpu().long()
+        rv = torch.gather(dense['dist'][:, :V].cpu(), 1, gi)
+        assert torch.allclose(gform['tv'].cpu(), rv, rtol=2e-4, atol=0)
+        sm = gi == want
+        if not bool(sm.all()):
+            wv = torch.gather(dense['dist'][:, :V].cpu(), 1, want)
+            assert torch.allclose(wv[~sm], rv[~sm], rtol=2e-4, atol=0), (gi, want)

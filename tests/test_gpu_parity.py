@@ -246,6 +246,37 @@ def test_beam_vs_oracle_midsize(dtype):
         assert same >= B - 2, (got, want)
 
 
+def test_gate_form_equals_context_form():
+    """Search path, bf16: the gate form of the additive attentions (3 gate-projected numbers per key, no value rows)
+    gives the gates and the answers of the context form (Model.py:39: W_m [h; m_0; m_1] is linear in m_i)."""
+    from case_rg_b200 import generations as FG
+    from case_rg_b200 import _lib as L
+    V, B, T, W = 5000, 6, 8, 4
+    sd = syn.make_case_decoder_state(32, V, H, peaked=0.3, boost={syn.EOS: 12.0}, gen_gate_bias=2.0)
+    inp = syn.make_case_inputs(42, B, 24, 4, 40, V, H)
+    lib = L.load()
+    res = {}
+    try:
+        for on in (0, 1):
+            lib.case_set_gate_form(on)
+            model = FG.FastCaSE(sd, device=DEV, dtype='bf16', use_graph=False)
+            toks = FG.beam(model, _case_data(inp), None, T, W).cpu()
+            eng = model.last_engine
+            eng.state.reset()
+            eng.args.mode, eng.args.max_len = L.MODE_BEAM, T
+            eng._run_steps(1)                       # gates / top-k of the first step, same inputs in both forms
+            torch.cuda.synchronize()
+            res[on] = (toks, eng.gates[::W, :3].clone(), eng.top_vals[::W].clone(), eng.top_idx[::W].clone())
+    finally:
+        lib.case_set_gate_form(1)
+    assert torch.allclose(res[0][1], res[1][1], atol=3e-3), (res[0][1], res[1][1])
+    assert torch.allclose(res[0][2], res[1][2], rtol=2e-2, atol=1e-6)
+    assert (res[0][3] == res[1][3]).float().mean() > 0.9
+    Lc = min(res[0][0].size(1), res[1][0].size(1))
+    same = sum(int(torch.equal(res[0][0][i, :Lc], res[1][0][i, :Lc])) for i in range(B))
+    assert same >= B - 1, (res[0][0], res[1][0])
+
+
 # --------------------------------------------------------------------------- properties at BASELINE size
 def test_c2_properties_full_size():
     """Config 2 (B=64, W=4, 10x256 passages, V=30522): size-independent properties."""
