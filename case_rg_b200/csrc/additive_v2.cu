@@ -519,7 +519,12 @@ __global__ __launch_bounds__(A2T) void additive_attn_v3_kernel(
 // kernel above - disappear, what is left is the tanh count.  Same warp-autonomous walk as v3 (per-warp
 // cp.async ring over the Uk.mem rows of the warp's keys, padding skipped per key, multi-value butterfly);
 // lane (key k, row w) keeps the three gate sums of its own (key, row) pairs and they are reduced once.
+// Splits are work-proportional (nsq[b] of the nsplit slots per query) so that the launch is ONE resident wave
+// of equally long CTAs (3 per SM).
 // Outputs: scores, stats as above, gate_part [R][nsplit][4] = sum exp(e - m) * G (relative to stats' m).
+// (A lane = (key, hidden quarter) mapping with q in shared memory - two shuffles per key instead of the
+//  butterfly - executes as many instructions (its per-warp prologue and the LDS traffic eat the gain) and was
+//  slower at every split policy: 52-62 us against 48 us at the BASELINE shape.)
 constexpr int AG_NST = 3;     // ring stages per warp
 template <int WMAX, bool FAST>
 __global__ __launch_bounds__(A2T, WMAX <= 4 ? 3 : 2) void additive_attn_gate_kernel(
@@ -527,7 +532,7 @@ __global__ __launch_bounds__(A2T, WMAX <= 4 ? 3 : 2) void additive_attn_gate_ker
     const float* __restrict__ vvec, const uint8_t* __restrict__ mask, const float* __restrict__ prior,
     const int32_t* __restrict__ tok, int tok_ld, int t, int W, int S, int nsplit, float* __restrict__ scores,
     float* __restrict__ stats, float* __restrict__ gate_part, const int32_t* __restrict__ cidx,
-    const int32_t* __restrict__ ncount, const int32_t* __restrict__ qorder) {
+    const int32_t* __restrict__ ncount, const int32_t* __restrict__ qorder, const int32_t* __restrict__ nsq) {
   constexpr int KPT = WMAX == 8 ? 2 : 4;               // keys per warp per tile
   constexpr int NV = KPT * WMAX;                       // partial sums per warp per tile (4, 8, 16)
   constexpr int LW = WMAX == 1 ? 0 : (WMAX == 2 ? 1 : (WMAX == 4 ? 2 : 3));
@@ -543,7 +548,16 @@ __global__ __launch_bounds__(A2T, WMAX <= 4 ? 3 : 2) void additive_attn_gate_ker
   const int b = qorder ? qorder[blockIdx.x] : blockIdx.x, sp = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Sv = cidx ? ncount[b] : S;                 // keys to walk
-  const int chunk = split_chunk(Sv, nsplit, A2_SPLIT);
+  const int nsb = nsq ? max(1, min(nsq[b], nsplit)) : nsplit;
+  if (sp >= nsb) {
+    if (tid < W) {
+      const size_t o = (size_t)(b * W + tid) * nsplit + sp;
+      reinterpret_cast<float4*>(stats)[o] = make_float4(-INFINITY, 0.f, 0.f, 0.f);
+      reinterpret_cast<float4*>(gate_part)[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
+  const int chunk = split_chunk(Sv, nsb, A2_SPLIT);
   const int s_begin = sp * chunk, s_end = min(Sv, s_begin + chunk);
   const int ntiles = s_end > s_begin ? (s_end - s_begin + TILEK - 1) / TILEK : 0;
   const int r0 = b * W;
@@ -728,11 +742,64 @@ __global__ __launch_bounds__(A2T, WMAX <= 4 ? 3 : 2) void additive_attn_gate_ker
   }
 }
 
+// ---- prefill side of the gate form
+// G[n][0..2] = Wg[0..2][:] . mem[n][:] for N key rows (bf16 storage, fp32 accumulate): one warp per row, HBM-bound
+__global__ __launch_bounds__(256) void gate_project_kernel(const bf16* __restrict__ mem, const float* __restrict__ Wg,
+                                                           float4* __restrict__ G, long long N) {
+  const int lane = threadIdx.x & 31;
+  float wg[3][8];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(Wg + j * H + lane * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(Wg + j * H + lane * 8 + 4));
+    wg[j][0] = a.x; wg[j][1] = a.y; wg[j][2] = a.z; wg[j][3] = a.w; wg[j][4] = b.x; wg[j][5] = b.y; wg[j][6] = b.z; wg[j][7] = b.w;
+  }
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long n = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); n < N; n += nw) {
+    float m[8];
+    ld8(mem + n * H + lane * 8, m);
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { d0 = fmaf(wg[0][i], m[i], d0); d1 = fmaf(wg[1][i], m[i], d1); d2 = fmaf(wg[2][i], m[i], d2); }
+    d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2);
+    if (lane == 0) G[n] = make_float4(d0, d1, d2, 0.f);
+  }
+}
+
+// work-proportional split plan: keys per CTA = max(ceil(sum / slots), ceil(max / max_split)) rounded up to 32,
+// nsq[b] = clamp(ceil(count[b] / that), 1, max_split).  One CTA (B is at most a few hundred).
+__global__ __launch_bounds__(256) void split_plan_kernel(const int32_t* __restrict__ count, int B, int slots, int max_split,
+                                                         int32_t* __restrict__ nsq) {
+  __shared__ long long ssum[8];
+  __shared__ int smax[8];
+  long long sum = 0;
+  int mx = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) { const int c = count[b]; sum += c; mx = max(mx, c); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = sum; smax[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  sum = 0; mx = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { sum += ssum[w]; mx = max(mx, smax[w]); }
+  long long chunk = (sum + slots - 1) / slots;
+  const long long cmin = (mx + max_split - 1) / max_split;
+  if (cmin > chunk) chunk = cmin;
+  chunk = (chunk + 31) / 32 * 32;
+  if (chunk < 32) chunk = 32;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const int n = (int)((count[b] + chunk - 1) / chunk);
+    nsq[b] = n < 1 ? 1 : (n > max_split ? max_split : n);
+  }
+}
+
 template <int WMAX>
 static int launch_gate(int fast, const float* qa, const void* U, const float* G, const float* v, const uint8_t* mask,
                        const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S, int nsplit,
                        float* scores, float* stats, float* gate_part, const int32_t* cidx, const int32_t* ncount,
-                       const int32_t* qorder, cudaStream_t st) {
+                       const int32_t* qorder, const int32_t* nsq, cudaStream_t st) {
   constexpr int KPT = WMAX == 8 ? 2 : 4;
   const size_t smem = (size_t)8 * AG_NST * KPT * H * 2;
   static bool attr = false;
@@ -743,10 +810,10 @@ static int launch_gate(int fast, const float* qa, const void* U, const float* G,
   }
   if (fast)
     launch_k(additive_attn_gate_kernel<WMAX, true>, dim3(B, nsplit), A2T, smem, st, qa, (const bf16*)U, (const float4*)G, v,
-             mask, prior, tok, tok_ld, t, W, S, nsplit, scores, stats, gate_part, cidx, ncount, qorder);
+             mask, prior, tok, tok_ld, t, W, S, nsplit, scores, stats, gate_part, cidx, ncount, qorder, nsq);
   else
     launch_k(additive_attn_gate_kernel<WMAX, false>, dim3(B, nsplit), A2T, smem, st, qa, (const bf16*)U, (const float4*)G, v,
-             mask, prior, tok, tok_ld, t, W, S, nsplit, scores, stats, gate_part, cidx, ncount, qorder);
+             mask, prior, tok, tok_ld, t, W, S, nsplit, scores, stats, gate_part, cidx, ncount, qorder, nsq);
   return check_launch("case_additive_attn_gate");
 }
 
@@ -836,12 +903,14 @@ extern "C" int case_additive_attn_compact(const float* qa, const void* U, const 
 /* Gate form of the additive attention (bf16 keys): G fp32 [B][S][4] = (W_m slice of memory i) . mem[b][s]
  * (3 gate logits' worth per key, 4th unused) replaces the value rows; gate_part [R][nsplit][4] =
  * sum exp(e - m) * G relative to the split's m in stats.  cidx / ncount / qorder as in
- * case_additive_attn_compact, or all NULL to walk every position under the mask. */
+ * case_additive_attn_compact, or all NULL to walk every position under the mask.  nsq int32 [B] (may be NULL):
+ * query b uses only its first nsq[b] <= nsplit splits (work-proportional splitting), the other slots are
+ * written as empty partials (m = -inf). */
 extern "C" int case_additive_attn_gate(const float* qa, const void* U, const float* G, const float* v, const uint8_t* mask,
                                        const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S,
                                        int nsplit, float* attn_un, float* stats, float* gate_part, int fast_tanh,
                                        const int32_t* cidx, const int32_t* ncount, const int32_t* qorder,
-                                       case_stream_t stream) {
+                                       const int32_t* nsq, case_stream_t stream) {
   using namespace cb;
   CB_REQUIRE(qa && U && G && v && mask && attn_un && stats && gate_part, "case_additive_attn_gate: null pointer");
   CB_REQUIRE(B > 0 && W >= 1 && W <= CASE_MAX_W && S > 0 && nsplit >= 1 && nsplit <= CASE_MAX_SPLIT, "case_additive_attn_gate: bad sizes");
@@ -849,8 +918,30 @@ extern "C" int case_additive_attn_gate(const float* qa, const void* U, const flo
   CB_REQUIRE((uintptr_t)G % 16 == 0 && (uintptr_t)U % 16 == 0 && (uintptr_t)stats % 16 == 0 && (uintptr_t)gate_part % 16 == 0,
              "case_additive_attn_gate: U, G, stats, gate_part must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (W <= 1) return launch_gate<1>(fast_tanh, qa, U, G, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, attn_un, stats, gate_part, cidx, ncount, qorder, st);
-  if (W <= 2) return launch_gate<2>(fast_tanh, qa, U, G, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, attn_un, stats, gate_part, cidx, ncount, qorder, st);
-  if (W <= 4) return launch_gate<4>(fast_tanh, qa, U, G, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, attn_un, stats, gate_part, cidx, ncount, qorder, st);
-  return launch_gate<8>(fast_tanh, qa, U, G, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, attn_un, stats, gate_part, cidx, ncount, qorder, st);
+  if (W <= 1) return launch_gate<1>(fast_tanh, qa, U, G, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, attn_un, stats, gate_part, cidx, ncount, qorder, nsq, st);
+  if (W <= 2) return launch_gate<2>(fast_tanh, qa, U, G, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, attn_un, stats, gate_part, cidx, ncount, qorder, nsq, st);
+  if (W <= 4) return launch_gate<4>(fast_tanh, qa, U, G, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, attn_un, stats, gate_part, cidx, ncount, qorder, nsq, st);
+  return launch_gate<8>(fast_tanh, qa, U, G, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, attn_un, stats, gate_part, cidx, ncount, qorder, nsq, st);
+}
+
+/* Prefill of the gate form: G fp32 [N][4] = (Wg[0] . mem[n], Wg[1] . mem[n], Wg[2] . mem[n], 0) for N key rows of
+ * bf16 [N][H]; Wg fp32 [3][H] = W_m[:, H(1+i):H(2+i)] (CaSE/Model.py:36,39). */
+extern "C" int case_gate_project(const void* mem, const float* Wg, float* G, long long N, case_stream_t stream) {
+  using namespace cb;
+  CB_REQUIRE(mem && Wg && G && N > 0, "case_gate_project: bad arguments");
+  CB_REQUIRE((uintptr_t)mem % 16 == 0 && (uintptr_t)Wg % 16 == 0 && (uintptr_t)G % 16 == 0, "case_gate_project: 16-byte alignment required");
+  const long long want = (N + 7) / 8;
+  const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+  launch_k(gate_project_kernel, grid, 256, 0, (cudaStream_t)stream, (const bf16*)mem, Wg, (float4*)G, N);
+  return check_launch("case_gate_project");
+}
+
+/* Work-proportional split plan for case_additive_attn_gate: nsq[b] = clamp(ceil(count[b] / c), 1, max_split) with
+ * c = max(ceil(sum(count) / slots), ceil(max(count) / max_split)) rounded up to a multiple of 32 keys, so the
+ * launch has about `slots` equally long CTAs (+ at most one short CTA per query). */
+extern "C" int case_split_plan(const int32_t* count, int B, int slots, int max_split, int32_t* nsq, case_stream_t stream) {
+  using namespace cb;
+  CB_REQUIRE(count && nsq && B > 0 && slots > 0 && max_split >= 1 && max_split <= CASE_MAX_SPLIT, "case_split_plan: bad arguments");
+  launch_k(split_plan_kernel, 1, 256, 0, (cudaStream_t)stream, count, B, slots, max_split, nsq);
+  return check_launch("case_split_plan");
 }

@@ -28,6 +28,7 @@ constexpr int TC_KCH = 4;                       // K chunks (pipeline stages)
 constexpr int TC_W_BYTES = TC_M * TC_K * 2;     // 64 KB
 constexpr int TC_A_BYTES = TC_NB * TC_K * 2;    // 128 KB
 constexpr int TC_SMEM = TC_W_BYTES + TC_A_BYTES + 128;
+constexpr int TC_THREADS = 256;                 // warps 0..3 feed the pipeline; all 8 drain TMEM (two per lane quarter)
 
 __device__ __forceinline__ void tc_mbar_init(uint32_t bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -125,7 +126,7 @@ __global__ void pack_activations_kernel(const float* __restrict__ f, bf16* __res
   *reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + off) = v;
 }
 
-__global__ __launch_bounds__(128, 1) void vocab_gemm_tc_kernel(const bf16* __restrict__ Wp, const bf16* __restrict__ Ap,
+__global__ __launch_bounds__(TC_THREADS, 1) void vocab_gemm_tc_kernel(const bf16* __restrict__ Wp, const bf16* __restrict__ Ap,
                                                                const float* __restrict__ bias,
                                                                float* __restrict__ logits, int R, int V, int ldl) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -153,7 +154,7 @@ __global__ __launch_bounds__(128, 1) void vocab_gemm_tc_kernel(const bf16* __res
   // one issuing lane per K chunk, in four different warps: a warp keeps only one bulk copy in
   // flight at a time (profiles/micro/bulk_bench.cu), so spreading the issue overlaps the chunks.
   // The weight tile is a constant: it is requested before the dependency wait.
-  if (lane == 0) {
+  if (lane == 0 && warp < TC_KCH) {
     const char* wsrc = reinterpret_cast<const char*>(Wp) + (size_t)tile * TC_W_BYTES;
     tc_expect_tx_only(s_bar + 8 * warp, W_CH);
     tc_bulk_g2s(s_w + warp * W_CH, wsrc + (size_t)warp * W_CH, W_CH, s_bar + 8 * warp);
@@ -164,8 +165,8 @@ __global__ __launch_bounds__(128, 1) void vocab_gemm_tc_kernel(const bf16* __res
     const int rows = min(TC_NB, R - blk * TC_NB);
     const int N = (rows + 15) & ~15;
     const uint32_t par = blk & 1;
-    if (lane == 0) {
-      const int c = warp;                                    // TC_KCH == number of warps
+    if (lane == 0 && warp < TC_KCH) {
+      const int c = warp;                                    // one issuing warp per K chunk
       const char* asrc = reinterpret_cast<const char*>(Ap) + (size_t)blk * TC_A_BYTES;
       const uint32_t a_ch = (uint32_t)N * (TC_K / TC_KCH) * 2;     // N rows x 64 k of bf16, contiguous
       const uint32_t bar = s_bar + 8 * c;
@@ -187,15 +188,17 @@ __global__ __launch_bounds__(128, 1) void vocab_gemm_tc_kernel(const bf16* __res
       }
       umma_commit(s_bar + 8 * TC_KCH);
     }
-    // ---- epilogue: every warp drains its 32 TMEM lanes (= 32 vocabulary rows)
+    // ---- epilogue: a warp reads the TMEM lanes of its quarter (warp % 4 = 32 vocabulary rows); the two warps
+    // of a quarter take alternate 32-column groups, so twice as many stores are in flight
     tc_wait(s_bar + 8 * TC_KCH, par);
     __syncwarp();         // lane 0 of warp 0 arrives here from the issue path; tcgen05.ld is .aligned
     tc_fence_after();
-    const int v = tile * TC_M + warp * 32 + lane;
+    const int lq = warp & 3;
+    const int v = tile * TC_M + lq * 32 + lane;
     const float bv = (bias && v < V) ? __ldg(bias + v) : 0.f;
-    for (int c0 = 0; c0 < N; c0 += 32) {
+    for (int c0 = (warp >> 2) * 32; c0 < N; c0 += 64) {
       uint32_t acc[32];
-      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, acc);
+      tmem_ld32(tmem + ((uint32_t)(lq * 32) << 16) + c0, acc);
       tmem_ld_wait();
       if (v < V) {
 #pragma unroll
@@ -237,7 +240,7 @@ extern "C" int case_vocab_gemm_tc(const float* f, const void* Wp, const float* b
   launch_k(pack_activations_kernel, (n + 255) / 256, 256, 0, st, f, (bf16*)workspace, R);
   int rc = check_launch("case_vocab_gemm_tc(pack)");
   if (rc) return rc;
-  launch_k(vocab_gemm_tc_kernel, (V + TC_M - 1) / TC_M, 128, TC_SMEM, st, (const bf16*)Wp, (const bf16*)workspace, bias,
+  launch_k(vocab_gemm_tc_kernel, (V + TC_M - 1) / TC_M, TC_THREADS, TC_SMEM, st, (const bf16*)Wp, (const bf16*)workspace, bias,
                                                                      logits, R, V, ldl);
   return check_launch("case_vocab_gemm_tc");
 }

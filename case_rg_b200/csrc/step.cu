@@ -87,7 +87,7 @@ extern "C" int case_set_post_linears(int on) {
 }
 extern "C" int case_set_gate_form(int on) {
   const int old = g_use_gate;
-  g_use_gate = on ? 1 : 0;
+  if (on >= 0) g_use_gate = on ? 1 : 0;      // negative: query only
   return old;
 }
 extern "C" int case_set_kv_prefetch(int pct) {
@@ -177,7 +177,8 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       const bool cmp = i == 1 && a->xidx != nullptr && a->xcount != nullptr;
       return case_additive_attn_gate(qa, a->U[i], a->Gv[i], a->va[i], a->mask[i], a->prior[i], a->tok, TL, t, B, W, a->S[i],
                                      a->nsplit_a[i], a->attn_un[i], a->stats[i], a->ctxp[i], a->fast_tanh,
-                                     cmp ? a->xidx : nullptr, cmp ? a->xcount : nullptr, cmp ? a->xorder : nullptr, s2);
+                                     cmp ? a->xidx : nullptr, cmp ? a->xcount : nullptr, cmp ? a->xorder : nullptr,
+                                     cmp ? a->xns : nullptr, s2);
     }
     if (i == 1 && dt == CASE_BF16 && a->xidx != nullptr && a->xcount != nullptr)   // valid keys only, balanced splits
       return case_additive_attn_compact(qa, a->U[i], a->Mv[i], a->va[i], a->mask[i], a->prior[i], a->tok, TL, t, B, W,

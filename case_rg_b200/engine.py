@@ -226,8 +226,7 @@ class CaseWeights:
         self.Wv_tc = pack_vocab_tc(g('gen.2.weight')) if self.cdtype == L.BF16 else None
         self.Wm, self.bm = g('mix.weight').contiguous(), vec(g('mix.bias'))
         # gate form (CaSE/Model.py:39,117): W_m's slice for context i as a [H][4] projection of the memory keys
-        self.Wm_g = [torch.cat([self.Wm[:, H * (1 + i):H * (2 + i)].t(), torch.zeros(H, 1, device=dev)], 1).contiguous()
-                     for i in range(2)]
+        self.Wm_g = [self.Wm[:, H * (1 + i):H * (2 + i)].contiguous() for i in range(2)]          # [3][H] each
 
 
 class _SearchState:
@@ -359,6 +358,15 @@ class CaseDecodeEngine(_EngineBase):
         self.xidx = torch.zeros(B, S1, dtype=torch.int32, device=dev) if self.compact else None
         self.xorder = torch.zeros(B, dtype=torch.int32, device=dev)
         self.qcount = torch.zeros(B, dtype=torch.int32, device=dev)
+        # work-proportional key splits of the second memory's additive attention (gate form): query b uses
+        # xns[b] of the MAX_SPLIT slots so that every CTA walks about the same number of valid keys and the
+        # whole launch is one resident wave (add_slots CTAs)
+        self.prop_split = self.compact and self.Gv is not None and os.environ.get('CASE_PROP_SPLIT', '1') != '0'
+        self.add_slots = int(os.environ.get('CASE_ADD_SLOTS', 3 * 148))
+        self.xns = torch.zeros(B, dtype=torch.int32, device=dev)
+        self._mv_src = [None, None]
+        if self.prop_split:
+            self.nsa[1] = L.MAX_SPLIT
         self.x_in, self.h, self.bbuf, self.q2 = z(R, H), z(R, H), z(R, H), z(R, H)
         self.part_ml, self.part_acc = z(R, L.NH, nsx, 2), z(R, L.NH, nsx, L.HD)
         self.qa = z(R, H)
@@ -411,6 +419,8 @@ class CaseDecodeEngine(_EngineBase):
         if self.compact:
             a.xcount, a.xprefix, a.xslots = self.xcount.data_ptr(), self.xprefix.data_ptr(), self.xslots
             a.xidx, a.xorder = self.xidx.data_ptr(), self.xorder.data_ptr()
+            if self.prop_split:
+                a.xns = self.xns.data_ptr()
         a.qcount = self.qcount.data_ptr()
         if w.Wg_c is not None:
             a.Wqa_c[0], a.Wqa_c[1], a.Wg_c = w.Wqa_c[0].data_ptr(), w.Wqa_c[1].data_ptr(), w.Wg_c.data_ptr()
@@ -439,7 +449,7 @@ class CaseDecodeEngine(_EngineBase):
             m = mems[i].to(dev, w.tdtype)         # bf16 storage: the prefill GEMMs run on bf16 tensor cores
             if m.size(1) != S:
                 raise ValueError(f'memory {i} has {m.size(1)} positions, engine was built for {S}')
-            flat = m.reshape(B * S, H)
+            flat = m.reshape(B * S, H).contiguous()
             kv = torch.addmm(w.kv_b[i], flat, w.kv_w[i])                       # [B*S, 4*2*H]
             if w.cdtype == L.BF16:        # one pass: GEMM rows -> swizzled bf16 K|V tiles of all 4 layers
                 outs = (C.c_void_p * 4)(*[self.Kx[i * 4 + l].data_ptr() for l in range(4)])
@@ -451,6 +461,9 @@ class CaseDecodeEngine(_EngineBase):
                     self.xcount.copy_(cnt)
                     self.xprefix[1:].copy_(torch.cumsum((cnt + 63) // 64, 0))
                     self.xorder.copy_(torch.argsort(cnt, descending=True, stable=True))
+                    if self.prop_split:     # keys per CTA: the launch fits add_slots CTAs, no query needs > MAX_SPLIT
+                        L.call('case_split_plan', self.xcount.data_ptr(), B, max(self.add_slots - B // 2, 1), L.MAX_SPLIT,
+                               self.xns.data_ptr(), stream)
                     # the additive attention visits valid keys only: padding scores are -inf once and for all
                     self.attn_un[i].masked_fill_(~valid.repeat_interleave(self.W, 0), float('-inf'))
                     L.call('case_pack_kv_tiles_gather', kv.data_ptr(), kv.size(1), B, S, self.xidx.data_ptr(),
@@ -463,9 +476,12 @@ class CaseDecodeEngine(_EngineBase):
                     self.Kx[i * 4 + l].copy_(kv[l, 0])
                     self.Vx[i * 4 + l].copy_(kv[l, 1])
             torch.mm(flat, w.Uk_t[i], out=self.U[i].view(B * S, H))
-            self.Mv[i].copy_(m)
-            if self.Gv is not None:
-                torch.mm(mems[i].to(dev, torch.float32).reshape(B * S, H), w.Wm_g[i], out=self.Gv[i].view(B * S, 4))
+            if self.Gv is None or not L.load().case_set_gate_form(-1):
+                self.Mv[i].copy_(m)
+                self._mv_src[i] = None
+            else:                   # the search path reads G instead; the value rows are filled when the `generate` face asks
+                self._mv_src[i] = m
+                L.call('case_gate_project', flat.data_ptr(), w.Wm_g[i].data_ptr(), self.Gv[i].data_ptr(), B * S, stream)
             self.mask[i].copy_(masks[i].to(dev).to(torch.uint8))
             self.prior[i].copy_(priors[i].to(dev, torch.float32))
         self.map.copy_(source_map.to(dev).to(torch.int32))
@@ -504,6 +520,10 @@ class CaseDecodeEngine(_EngineBase):
     def step_distribution(self, t: int) -> torch.Tensor:
         """Protocol ``generate`` face: run step t up to the finished distribution and return a view
         [R, V] of it (no top-k / select); the caller drives tok/anc through ``state``."""
+        for i in range(2):
+            if self._mv_src[i] is not None:
+                self.Mv[i].copy_(self._mv_src[i].view_as(self.Mv[i]))
+                self._mv_src[i] = None
         self.args.materialize_only = 1
         stream = torch.cuda.current_stream(self.device)
         L.check(self._step_fn(C.byref(self.args), t, stream.cuda_stream), self._step_name)

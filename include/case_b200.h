@@ -73,7 +73,8 @@ int case_set_fused_select(int on);
  * case_row_linear / case_layernorm_rows launches (default on; needs Wqa_c / Wg_c in the step arguments). */
 int case_set_post_linears(int on);
 /* Gate form of the additive attentions on the search path (default on; needs Gv in the step arguments, bf16
- * and the sparse tail): case_additive_attn_gate instead of case_additive_attn[_compact]. */
+ * and the sparse tail): case_additive_attn_gate instead of case_additive_attn[_compact].  Returns the old
+ * setting; a negative argument only queries. */
 int case_set_gate_form(int on);
 /* Grid of case_cross_attn_part: n CTAs instead of one per SM (0 = default).  For batch slices decoded
  * concurrently on several streams: a smaller grid leaves SMs to the other slice's cluster launches. */
@@ -286,11 +287,21 @@ int case_additive_attn_compact(const float* qa, const void* U, const void* Mv, c
  * softmax(W_m [h; m_0; m_1] + b_m) (CaSE/Model.py:39,117), which is linear in m_i, so the prefill projects
  * every key once to G fp32 [B][S][4] = (W_m[:, H(1+i):H(2+i)] . mem_i[b][s], 0) and the step accumulates
  * gate_part [R][nsplit][4] = sum exp(e-m) * G instead of ctx_part (no value rows are read).  attn_un and
- * stats as in case_additive_attn; cidx / ncount / qorder as in case_additive_attn_compact or all NULL. */
+ * stats as in case_additive_attn; cidx / ncount / qorder as in case_additive_attn_compact or all NULL.
+ * nsq int32 [B] (may be NULL): query b uses only its first nsq[b] <= nsplit splits, so that every CTA of the
+ * launch walks about the same number of keys; unused slots are written as empty partials (m = -inf). */
 int case_additive_attn_gate(const float* qa, const void* U, const float* G, const float* v, const uint8_t* mask,
                             const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S,
                             int nsplit, float* attn_un, float* stats, float* gate_part, int fast_tanh,
-                            const int32_t* cidx, const int32_t* ncount, const int32_t* qorder, case_stream_t stream);
+                            const int32_t* cidx, const int32_t* ncount, const int32_t* qorder, const int32_t* nsq,
+                            case_stream_t stream);
+
+/* Prefill of the gate form: G fp32 [N][4] = (Wg[0..2] . mem[n], 0) for N key rows mem bf16 [N][H];
+ * Wg fp32 [3][H] = W_m[:, H(1+i):H(2+i)] of memory i (CaSE/Model.py:36,39). */
+int case_gate_project(const void* mem, const float* Wg, float* G, long long N, case_stream_t stream);
+/* Split plan for case_additive_attn_gate: nsq[b] = clamp(ceil(count[b] / c), 1, max_split), c = max(ceil(sum(count)
+ * / slots), ceil(max(count) / max_split)) rounded up to 32 keys: about `slots` equally long CTAs per launch. */
+int case_split_plan(const int32_t* count, int B, int slots, int max_split, int32_t* nsq, case_stream_t stream);
 
 /* bf16 additive attention kernel: 3 (default) = warp-autonomous (no block barrier in the key loop, padding
  * skipped per key), 2 = block-synchronous 32-key tiles; returns the old setting (A/B aid). */
@@ -453,6 +464,7 @@ typedef struct {
   const int32_t* xidx; const int32_t* xorder;   /* [B][S1] valid positions, [B] queries by valid count (desc) */
   int32_t* qcount;                      /* [B] zeros (may be NULL): lets the sparse tail run the search bookkeeping */
   const void* Wqa_c[2]; const void* Wg_c;   /* attention-query / gen.0 weights as post linears of the cluster launches (may be NULL) */
+  const int32_t* xns;                   /* [B] splits of the second memory's additive attention per query (may be NULL) */
   const float* Gv[2];                   /* [B][S_i][4] fp32 gate-projected memories (may be NULL): the search path then runs
                                            case_additive_attn_gate and never reads Mv */
 } case_step_args_t;

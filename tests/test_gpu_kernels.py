@@ -164,15 +164,19 @@ def test_additive_attention_gate_form_vs_torch(W, S, nsplit, use_prior, compact)
     scores = torch.full((B * W, S), float('nan'), device=DEV)
     stats = torch.zeros(B * W, nsplit, 4, device=DEV)
     gpart = torch.zeros(B * W, nsplit, 4, device=DEV)
-    cidx = ncount = qorder = None
+    cidx = ncount = qorder = nsq = None
     if compact:
         cidx = torch.argsort(~mask, dim=1, stable=True).to(torch.int32)
         ncount = mask.sum(1).to(torch.int32)
         qorder = torch.argsort(ncount, descending=True, stable=True).to(torch.int32)
         scores.masked_fill_(~mask.repeat_interleave(W, 0), float('-inf'))      # the caller's job in this form
+        # work-proportional splits: queries use between 1 and nsplit of the slots
+        nsq = (ncount.float() / max(1.0, float(ncount.max())) * nsplit).ceil().clamp(1, nsplit).to(torch.int32)
+        stats.fill_(float('nan'))
+        gpart.fill_(float('nan'))
     L.call('case_additive_attn_gate', qa.data_ptr(), U.data_ptr(), G.data_ptr(), v.data_ptr(),
            mask.to(torch.uint8).data_ptr(), L.ptr(prior), tok.data_ptr(), 4, 2, B, W, S, nsplit, scores.data_ptr(),
-           stats.data_ptr(), gpart.data_ptr(), 0, L.ptr(cidx), L.ptr(ncount), L.ptr(qorder),
+           stats.data_ptr(), gpart.data_ptr(), 0, L.ptr(cidx), L.ptr(ncount), L.ptr(qorder), L.ptr(nsq),
            torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     e = (torch.tanh(qa.view(B, W, 1, H) + U.float().view(B, 1, S, H)) @ v).view(B * W, S)
