@@ -76,6 +76,14 @@ class _FastModel:
 
     __call__ = forward
 
+    id2vocab = None
+
+    def to_sentence(self, data, batch_indices):    # CaSE.to_sentence (CaSE/Model.py:270-271); needs self.id2vocab
+        from .results import to_sentence
+        if self.id2vocab is None:
+            raise ValueError('set model.id2vocab before calling to_sentence')
+        return to_sentence(batch_indices, self.id2vocab)
+
 
 class FastCaSE(_FastModel):
     """EncDecModel-protocol driver for the CaSE decoder.
