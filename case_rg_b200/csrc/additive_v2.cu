@@ -544,12 +544,14 @@ __global__ __launch_bounds__(A2T, WMAX <= 4 ? 3 : 2) void additive_attn_gate_ker
   extern __shared__ __align__(128) unsigned char sm[];
   __shared__ float wst[8][WMAX][6];
   pdl_trigger();
-  pdl_wait();
+  // everything up to the first key rows in flight reads prefill data only (split plan, key positions, Uk.mem);
+  // the wait for the producer of qa / tok comes after it
   const int b = qorder ? qorder[blockIdx.x] : blockIdx.x, sp = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Sv = cidx ? ncount[b] : S;                 // keys to walk
   const int nsb = nsq ? max(1, min(nsq[b], nsplit)) : nsplit;
   if (sp >= nsb) {
+    pdl_wait();
     if (tid < W) {
       const size_t o = (size_t)(b * W + tid) * nsplit + sp;
       reinterpret_cast<float4*>(stats)[o] = make_float4(-INFINITY, 0.f, 0.f, 0.f);
@@ -569,21 +571,7 @@ __global__ __launch_bounds__(A2T, WMAX <= 4 ? 3 : 2) void additive_attn_gate_ker
   unsigned char* wbuf = sm + (size_t)warp * AG_NST * WSTAGE;
   const uint32_t wbuf_s = smem_u32(wbuf);
 
-  float qv[WMAX][8], vv[8];
-#pragma unroll
-  for (int w = 0; w < WMAX; ++w) {
-    const float* q = qa + (size_t)(r0 + min(w, W - 1)) * H + lane * 8;
-    const float4 a0 = *reinterpret_cast<const float4*>(q), a1 = *reinterpret_cast<const float4*>(q + 4);
-    qv[w][0] = a0.x; qv[w][1] = a0.y; qv[w][2] = a0.z; qv[w][3] = a0.w;
-    qv[w][4] = a1.x; qv[w][5] = a1.y; qv[w][6] = a1.z; qv[w][7] = a1.w;
-  }
-  {
-    const float4 a0 = *reinterpret_cast<const float4*>(vvec + lane * 8), a1 = *reinterpret_cast<const float4*>(vvec + lane * 8 + 4);
-    vv[0] = a0.x; vv[1] = a0.y; vv[2] = a0.z; vv[3] = a0.w; vv[4] = a1.x; vv[5] = a1.y; vv[6] = a1.z; vv[7] = a1.w;
-  }
   const int myj = lane >> SH, myk = myj >> LW, myw = myj & (WMAX - 1);
-  bool rowvalid = myw < W;
-  if (rowvalid && tok) rowvalid = tok[(size_t)(r0 + myw) * tok_ld + t] != 0;
 
   auto key_of = [&](int ti, int k) { return s_begin + ti * TILEK + warp * KPT + k; };
   int pos_next = 0;
@@ -618,6 +606,21 @@ __global__ __launch_bounds__(A2T, WMAX <= 4 ? 3 : 2) void additive_attn_gate_ker
     if (j < ntiles) issue(j, vbq[j], posq[j]);
     a2_commit();
   }
+  pdl_wait();
+  float qv[WMAX][8], vv[8];
+#pragma unroll
+  for (int w = 0; w < WMAX; ++w) {
+    const float* q = qa + (size_t)(r0 + min(w, W - 1)) * H + lane * 8;
+    const float4 a0 = *reinterpret_cast<const float4*>(q), a1 = *reinterpret_cast<const float4*>(q + 4);
+    qv[w][0] = a0.x; qv[w][1] = a0.y; qv[w][2] = a0.z; qv[w][3] = a0.w;
+    qv[w][4] = a1.x; qv[w][5] = a1.y; qv[w][6] = a1.z; qv[w][7] = a1.w;
+  }
+  {
+    const float4 a0 = *reinterpret_cast<const float4*>(vvec + lane * 8), a1 = *reinterpret_cast<const float4*>(vvec + lane * 8 + 4);
+    vv[0] = a0.x; vv[1] = a0.y; vv[2] = a0.z; vv[3] = a0.w; vv[4] = a1.x; vv[5] = a1.y; vv[6] = a1.z; vv[7] = a1.w;
+  }
+  bool rowvalid = myw < W;
+  if (rowvalid && tok) rowvalid = tok[(size_t)(r0 + myw) * tok_ld + t] != 0;
   int stage = 0, fstage = AG_NST - 1;
   for (int ti = 0; ti < ntiles; ++ti) {
     const unsigned vb_new = valid_bits(ti + AG_NST - 1);
