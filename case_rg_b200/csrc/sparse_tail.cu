@@ -155,6 +155,13 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
   auto stamp = [&]() { if (dbg != nullptr && blockIdx.x == 0 && tid == 0) dbg[dbg_n++] = clock64(); };
   stamp();
   for (int i = tid; i < nslots; i += TS) { hkeys[i] = -1; hvals[i] = 0.f; }
+  // weights of the mixture gate (the h part) are requested before the dependency wait
+  float wmh[3] = {0.f, 0.f, 0.f}, bmv[3] = {0.f, 0.f, 0.f};
+  if (a.do_finalize) {
+    const int colw = tid < H ? tid : 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { wmh[k] = __ldg(a.Wm + (size_t)k * 3 * H + colw); bmv[k] = __ldg(a.bm + k); }
+  }
   pdl_wait();
   stamp();
   float g0, F[2] = {0.f, 0.f}, M[2] = {0.f, 0.f};
@@ -209,15 +216,18 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
     float part[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const float* wr = a.Wm + (size_t)k * 3 * H;
-      const float pk = fmaf(__ldg(wr + col), y, fmaf(__ldg(wr + H + col), cx[0], __ldg(wr + 2 * H + col) * cx[1]));
+      float pk = wmh[k] * y;
+      if (!a.gate_ctx) {
+        const float* wr = a.Wm + (size_t)k * 3 * H;
+        pk = fmaf(__ldg(wr + H + col), cx[0], fmaf(__ldg(wr + 2 * H + col), cx[1], pk));
+      }
       part[k] = warp_sum(tid < H ? pk : 0.f);
     }
     if (lane == 0) { sh[warp * 3] = part[0]; sh[warp * 3 + 1] = part[1]; sh[warp * 3 + 2] = part[2]; }
     wstamp();
     __syncthreads();
     wstamp();
-    float lg[3] = {__ldg(a.bm) + gsum[0], __ldg(a.bm + 1) + gsum[1], __ldg(a.bm + 2) + gsum[2]};
+    float lg[3] = {bmv[0] + gsum[0], bmv[1] + gsum[1], bmv[2] + gsum[2]};
 #pragma unroll
     for (int w = 0; w < TSW; ++w) { lg[0] += sh[w * 3]; lg[1] += sh[w * 3 + 1]; lg[2] += sh[w * 3 + 2]; }
     const float mx = fmaxf(lg[0], fmaxf(lg[1], lg[2]));
@@ -262,11 +272,12 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
     const float* at = a.attn_un[i] + (size_t)r * S;
     const float* pr = a.prior[i] ? a.prior[i] + (size_t)b * S : nullptr;
     const int32_t* mp = a.map + (size_t)b * a.map_ld + a.map_off[i];
-    for (int s0 = tid; s0 < S; s0 += 4 * TS) {
-      int id[4];
-      float ev[4], pv[4];
+    constexpr int HU = 8;                                  // positions per thread per round: all their loads in flight together
+    for (int s0 = tid; s0 < S; s0 += HU * TS) {
+      int id[HU];
+      float ev[HU], pv[HU];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < HU; ++u) {
         const int sidx = s0 + u * TS;
         const bool in = sidx < S;
         id[u] = in ? __ldg(mp + sidx) : -1;
@@ -274,7 +285,7 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
         pv[u] = (in && pr) ? __ldg(pr + sidx) : 1.f;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < HU; ++u) {
         if (ev[u] == -INFINITY || (unsigned)id[u] >= (unsigned)V) continue;   // masked source position
         const float cw = Fi * pv[u] * fexp(ev[u] - Mi);
         if (cw == 0.f) continue;
