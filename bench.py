@@ -46,6 +46,7 @@ def parse():
     ap.add_argument('--no-stack', action='store_true', help='no fused first stack (A/B)')
     ap.add_argument('--no-gate', action='store_true', help='context form of the additive attentions (A/B)')
     ap.add_argument('--xattn-ctas', type=int, default=None, help='grid of the passage cross-attention (default: one CTA per SM)')
+    ap.add_argument('--xattn-next', type=int, default=None, help='tiles per warp the passage cross-attention prefetches into L2 for the next layer (A/B)')
     ap.add_argument('--kv-prefetch', type=int, default=None, help='percent of the next K|V stream prefetched into L2 by the cluster launches (A/B)')
     ap.add_argument('--streams', type=int, default=1, help='batch slices decoded concurrently on their own streams')
     ap.add_argument('--batch', type=int, default=WORKLOAD['B'])
@@ -208,6 +209,8 @@ def main():
         L.load().case_set_gate_form(0)
     if args.xattn_ctas is not None:
         L.load().case_set_xattn_ctas(args.xattn_ctas)
+    if args.xattn_next is not None:
+        L.load().case_set_xattn_next_prefetch(args.xattn_next)
     if args.kv_prefetch is not None:
         L.load().case_set_kv_prefetch(args.kv_prefetch)
     if args.profile:

@@ -139,6 +139,8 @@ _PROTOS = {
     'case_set_kv_prefetch': [i32],
     'case_set_gate_form': [i32],
     'case_set_xattn_ctas': [i32],
+    'case_set_xattn_next_prefetch': [i32],
+    'case_cross_attn_part_next': [vp, i32],
     'case_decode_step': [C.POINTER(StepArgs), i32, vp],
     'gttp_decode_step': [C.POINTER(GttpStepArgs), i32, vp],
 }

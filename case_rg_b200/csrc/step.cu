@@ -17,6 +17,7 @@ int g_use_tail = 2;
 int g_use_fused_select = 1;
 int g_use_post = 1;
 int g_use_gate = 1;
+int g_xnext = 0;               // tiles per warp the passage cross-attention prefetches for the next layer's launch
 int g_prefetch_pct = 0;        // measured: no gain at C2 (the prefetch traffic slows the latency-bound launch more than it helps)
 int g_prefetch_mask = 3;       // bit 0: from the stack launch (layer 4), bit 1: from the chain launches (layers 5..7)
 // side stream + events for the fork/join inside a step (created on first use, outside any capture: the
@@ -88,6 +89,11 @@ extern "C" int case_set_post_linears(int on) {
 extern "C" int case_set_gate_form(int on) {
   const int old = g_use_gate;
   if (on >= 0) g_use_gate = on ? 1 : 0;      // negative: query only
+  return old;
+}
+extern "C" int case_set_xattn_next_prefetch(int ntiles) {
+  const int old = g_xnext;
+  g_xnext = ntiles < 0 ? 0 : ntiles;
   return old;
 }
 extern "C" int case_set_kv_prefetch(int pct) {
@@ -214,6 +220,7 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
   const bool xpart = dt == CASE_BF16 && a->xcount != nullptr && a->xprefix != nullptr && a->xslots > 0;
   auto big_xattn = [&](int L) -> int {
     const int i = L / 4;
+    if (i == 1 && xpart && g_xnext > 0 && L < 7) case_cross_attn_part_next(a->Kx[L + 1], g_xnext);
     if (i == 1 && xpart)
       return case_cross_attn_part(a->q2, a->Kx[L], a->xcount, a->xprefix, B, W, a->S[1], a->xslots, a->part_ml, a->part_acc,
                                   st);

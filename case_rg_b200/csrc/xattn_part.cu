@@ -95,7 +95,7 @@ __device__ __forceinline__ void xp_advance(XpPos& p, const int* tp, int B) {   /
 __global__ __launch_bounds__(XP_WARPS * 32) void cross_attn_part_kernel(
     const float* __restrict__ q2, const bf16* __restrict__ KV, const int32_t* __restrict__ ncount,
     const int32_t* __restrict__ tile_prefix, int B, int W, int ntile_all, int nslot, float* __restrict__ part_ml,
-    float* __restrict__ part_acc) {
+    float* __restrict__ part_acc, const bf16* __restrict__ KVnext, int npf) {
   extern __shared__ __align__(128) unsigned char xp_smem[];   // [warp][XP_NS stages of K|V][barriers], then tp[B+1]
   int* tp = reinterpret_cast<int*>(xp_smem + (size_t)XP_WARPS * XP_WARP_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g4 = lane >> 2, t4 = lane & 3;
@@ -255,6 +255,17 @@ __global__ __launch_bounds__(XP_WARPS * 32) void cross_attn_part_kernel(
     done += seg_n;
     for (int i = 0; i < seg_n; ++i) xp_advance(cp, tp, B);
   }
+  // The NEXT layer's launch walks the same partition over its own K|V stream: pull the tiles that fill this
+  // warp's ring there into L2 now, while HBM goes idle for the cluster launch in between
+  if (KVnext != nullptr && lane == 0) {
+    XpPos pp = xp_locate(tp, B, g_begin);
+    const int n = min(npf, my_tiles);
+    for (int i = 0; i < n; ++i) {
+      const char* src = reinterpret_cast<const char*>(KVnext) + ((size_t)(pp.b * NH + pp.head) * ntile_all + pp.tile) * XP_STAGE;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)XP_STAGE) : "memory");
+      xp_advance(pp, tp, B);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ prefill packing
@@ -291,6 +302,16 @@ __global__ __launch_bounds__(256) void pack_kv_gather_kernel(const bf16* __restr
 using namespace cb;
 
 static int g_xp_ctas = 0;   // 0 = one CTA per SM
+static const void* g_xp_next = nullptr;   // one-shot: K|V stream of the next layer's launch (case_cross_attn_part_next)
+static int g_xp_npf = 3;                  // tiles per warp to prefetch there (the ring depth)
+/* The NEXT case_cross_attn_part launch also prefetches into L2, as its warps finish, the first `ntiles` tiles of
+ * every warp's range of the stream KVnext (same B, S, counts: the K|V of the next layer), so that the next
+ * launch fills its rings from L2.  One-shot; ntiles <= 0 keeps the previous depth. */
+extern "C" int case_cross_attn_part_next(const void* KVnext, int ntiles) {
+  g_xp_next = KVnext;
+  if (ntiles > 0) g_xp_npf = ntiles;
+  return 0;
+}
 /* Grid of case_cross_attn_part: n CTAs (0 = one per SM, the default).  A smaller grid leaves SMs to kernels of
  * another stream (batch slices decoded concurrently: one slice streams K|V while the other is in its
  * latency-bound cluster launches); returns the old setting. */
@@ -326,7 +347,8 @@ extern "C" int case_cross_attn_part(const float* q2, const void* KV, const int32
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = g_xp_ctas > 0 && g_xp_ctas < nsm ? g_xp_ctas : nsm;
   launch_k(cross_attn_part_kernel, grid, XP_WARPS * 32, smem, st, q2, (const bf16*)KV, ncount, tile_prefix, B, W,
-           (S + 63) / 64, nslot, part_ml, part_acc);
+           (S + 63) / 64, nslot, part_ml, part_acc, (const bf16*)g_xp_next, g_xp_npf);
+  g_xp_next = nullptr;
   return check_launch("case_cross_attn_part");
 }
 

@@ -76,6 +76,13 @@ int case_set_post_linears(int on);
  * and the sparse tail): case_additive_attn_gate instead of case_additive_attn[_compact].  Returns the old
  * setting; a negative argument only queries. */
 int case_set_gate_form(int on);
+/* The NEXT case_cross_attn_part launch also prefetches into L2, as its warps finish, the first `ntiles` tiles
+ * of every warp's range of the stream KVnext (the next layer's K|V: same B, S, counts), so that launch fills its
+ * rings from L2 while HBM was idle anyway.  One-shot; ntiles <= 0 keeps the previous depth (default 3). */
+int case_cross_attn_part_next(const void* KVnext, int ntiles);
+/* Tiles per warp that case_decode_step asks the passage cross-attention of layer L to prefetch for layer L+1
+ * (default 0 = off: measured neutral at the BASELINE shape, the launch is bound by its fixed cost); returns the old setting. */
+int case_set_xattn_next_prefetch(int ntiles);
 /* Grid of case_cross_attn_part: n CTAs instead of one per SM (0 = default).  For batch slices decoded
  * concurrently on several streams: a smaller grid leaves SMs to the other slice's cluster launches. */
 int case_set_xattn_ctas(int n);
