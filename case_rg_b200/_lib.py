@@ -70,7 +70,7 @@ class StepArgs(C.Structure):
                 ('out_tokens', vp), ('n_live', vp),
                 ('x_in', vp), ('h', vp), ('bbuf', vp), ('q2', vp), ('part_ml', vp), ('part_acc', vp), ('qa', vp),
                 ('attn_un', vp * 2), ('stats', vp * 2), ('ctxp', vp * 2), ('hN', vp), ('ctx', vp * 2), ('gates', vp),
-                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp), ('prow', vp), ('h0', vp), ('qa1', vp), ('base_ms', vp), ('base_e', vp), ('base_i', vp), ('xcount', vp), ('xprefix', vp), ('xslots', i32), ('xidx', vp), ('xorder', vp), ('qcount', vp), ('Wqa_c', vp * 2), ('Wg_c', vp), ('xns', vp), ('Gv', vp * 2)]
+                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp), ('prow', vp), ('h0', vp), ('qa1', vp), ('base_ms', vp), ('base_e', vp), ('base_i', vp), ('xcount', vp), ('xprefix', vp), ('xslots', i32), ('xidx', vp), ('xorder', vp), ('qcount', vp), ('Wqa_c', vp * 2), ('Wg_c', vp), ('xns', vp), ('U16', vp * 2), ('Gv', vp * 2)]
 
 
 class GttpStepArgs(C.Structure):
@@ -132,12 +132,14 @@ _PROTOS = {
     'case_additive_attn_gate': [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp],
     'case_gate_project': [vp, vp, vp, C.c_longlong, vp],
     'case_split_plan': [vp, i32, i32, i32, vp, vp],
+    'case_additive_attn_gate_h': [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp],
     'case_set_additive_impl': [i32],
     'case_set_fused_tail': [i32],
     'case_set_fused_select': [i32],
     'case_set_post_linears': [i32],
     'case_set_kv_prefetch': [i32],
     'case_set_gate_form': [i32],
+    'case_set_gate_f16': [i32],
     'case_set_xattn_ctas': [i32],
     'case_set_xattn_next_prefetch': [i32],
     'case_cross_attn_part_next': [vp, i32],

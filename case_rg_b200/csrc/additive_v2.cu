@@ -12,6 +12,8 @@
 // Outputs: raw masked scores e [R][S], per split (max, sum, prior-weighted sum) and the context
 // partial relative to that max.  The tanh count (R*S*H per launch, one MUFU op each at 16/clk/SM)
 // is the floor of this kernel; its HBM stream is B*2*S*H*2 bytes.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace cb {
@@ -526,7 +528,7 @@ __global__ __launch_bounds__(A2T) void additive_attn_v3_kernel(
 //  butterfly - executes as many instructions (its per-warp prologue and the LDS traffic eat the gain) and was
 //  slower at every split policy: 52-62 us against 48 us at the BASELINE shape.)
 constexpr int AG_NST = 3;     // ring stages per warp
-template <int WMAX, bool FAST>
+template <int WMAX, bool FAST, bool FULLW>    // FULLW: W == WMAX, the row checks of the tanh block fold away
 __global__ __launch_bounds__(A2T, WMAX <= 4 ? 3 : 2) void additive_attn_gate_kernel(
     const float* __restrict__ qa, const bf16* __restrict__ U, const float4* __restrict__ G,
     const float* __restrict__ vvec, const uint8_t* __restrict__ mask, const float* __restrict__ prior,
@@ -651,7 +653,7 @@ __global__ __launch_bounds__(A2T, WMAX <= 4 ? 3 : 2) void additive_attn_gate_ker
         ld8c(reinterpret_cast<const bf16*>(st + k * ROWB) + lane * 8, u);
 #pragma unroll
         for (int w = 0; w < WMAX; ++w) {
-          if (w < W) {
+          if (FULLW || w < W) {
             float e = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -745,6 +747,256 @@ __global__ __launch_bounds__(A2T, WMAX <= 4 ? 3 : 2) void additive_attn_gate_ker
   }
 }
 
+// ------------------------------------------------------------------------------------------ gate form, f16 / tensor-core
+// The kernel above is issue-bound, not MUFU-bound: 6.2 warp instructions per tanh (FADD + MUFU + FFMA, bf16
+// unpacks, the butterfly's SHFL + FSEL).  Here the additions and the tanh are packed (HADD2, tanh.approx.f16x2:
+// one instruction per two elements at the same element rate) and the weighted sum over the hidden units - the
+// v . tanh(...) reduction - is done by the tensor core: the tanh values of 16 (key, row) pairs x 16 hidden units
+// are exactly the A fragment of mma.m16n8k16 as the lanes produce them, B = v in every column, so D[row][*] is
+// the score and the cross-lane reduction costs nothing.  Uk.mem is stored in f16 for this kernel (prefill: 10
+// mantissa bits instead of bf16's 7, the dominant error of the bf16 form), q and v are rounded to f16,
+// accumulation is fp32.
+// MEASURED (B200, BASELINE shape): ptxas turns tanh.approx.f16x2 into TWO MUFU.TANH.F16 plus a PRMT, so the MUFU
+// count is unchanged (3.5 M); instructions drop from 21.7 M to 17.1 M but the launch takes 56 us against 47 us
+// for the fp32-math kernel above (each HMMA waits for eight MUFU results and chains on one accumulator).  Off
+// by default (case_set_gate_f16), kept with its tests as the record of that experiment.
+//   tile      = KPT = 16 / WMAX keys x WMAX rows = the 16 rows of the MMA, row = key * WMAX + w
+//   lane      = (g = lane / 4, tq = lane % 4): rows g and g + 8 (same w, two keys), hidden units 64 tq .. 64 tq + 63
+//   k order   = hidden unit 64 tq + 4 c + j is column (j < 2 ? 2 tq + j : 2 tq + 6 + j) of k-step c (any fixed
+//               permutation of the hidden units is fine: q, U and v use the same one)
+//   smem row  = the 512-byte U row as four 128-byte quarters at a 144-byte stride (conflict-free LDS.128)
+constexpr int AH_QS = 144;                // quarter stride (bytes)
+constexpr int AH_ROWB = 4 * AH_QS;        // staged bytes per key
+__device__ __forceinline__ uint32_t ah_tanh2(uint32_t x) {
+  uint32_t y;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t ah_add2(uint32_t a, uint32_t b) {
+  uint32_t y;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b));
+  return y;
+}
+__device__ __forceinline__ uint32_t ah_pack(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void ah_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int WMAX>
+__global__ __launch_bounds__(A2T, WMAX == 4 ? 3 : 2) void additive_attn_gate_h_kernel(
+    const float* __restrict__ qa, const __half* __restrict__ U, const float4* __restrict__ G,
+    const float* __restrict__ vvec, const uint8_t* __restrict__ mask, const float* __restrict__ prior,
+    const int32_t* __restrict__ tok, int tok_ld, int t, int W, int S, int nsplit, float* __restrict__ scores,
+    float* __restrict__ stats, float* __restrict__ gate_part, const int32_t* __restrict__ cidx,
+    const int32_t* __restrict__ ncount, const int32_t* __restrict__ qorder, const int32_t* __restrict__ nsq) {
+  static_assert(WMAX == 2 || WMAX == 4 || WMAX == 8, "one MMA tile is 16 / WMAX keys");
+  constexpr int KPT = 16 / WMAX;                       // keys per warp per tile
+  constexpr int TILEK = 8 * KPT;
+  constexpr int WSTAGE = KPT * AH_ROWB;
+  extern __shared__ __align__(128) unsigned char sm[];
+  __half* v_s = reinterpret_cast<__half*>(sm + 8 * AG_NST * WSTAGE);      // v in f16, quarters at the 144-byte stride
+  __shared__ float wst[8][WMAX][6];
+  pdl_trigger();
+  const int b = qorder ? qorder[blockIdx.x] : blockIdx.x, sp = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Sv = cidx ? ncount[b] : S;                 // keys to walk
+  const int nsb = nsq ? max(1, min(nsq[b], nsplit)) : nsplit;
+  if (sp >= nsb) {
+    pdl_wait();
+    if (tid < W) {
+      const size_t o = (size_t)(b * W + tid) * nsplit + sp;
+      reinterpret_cast<float4*>(stats)[o] = make_float4(-INFINITY, 0.f, 0.f, 0.f);
+      reinterpret_cast<float4*>(gate_part)[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
+  const int chunk = split_chunk(Sv, nsb, A2_SPLIT);
+  const int s_begin = sp * chunk, s_end = min(Sv, s_begin + chunk);
+  const int ntiles = s_end > s_begin ? (s_end - s_begin + TILEK - 1) / TILEK : 0;
+  const int r0 = b * W;
+  const uint8_t* mb = mask + (size_t)b * S;
+  const int32_t* cb = cidx ? cidx + (size_t)b * S : nullptr;
+  const __half* Ub = U + (size_t)b * S * H;
+  const float4* Gb = G + (size_t)b * S;
+  const float* pb = prior ? prior + (size_t)b * S : nullptr;
+  unsigned char* wbuf = sm + (size_t)warp * AG_NST * WSTAGE;
+  const uint32_t wbuf_s = smem_u32(wbuf);
+  const int g = lane >> 2, tq = lane & 3;
+  const int keyA = g / WMAX, keyB = (g + 8) / WMAX, myw = g % WMAX;
+
+  auto key_of = [&](int ti, int k) { return s_begin + ti * TILEK + warp * KPT + k; };
+  // lane k < KPT owns the bookkeeping of key k of a tile: memory position (or, masked form, ~position) and validity
+  int pos_next = 0;
+  auto valid_bits = [&](int ti) -> unsigned {
+    bool ok = false;
+    pos_next = 0;
+    if (lane < KPT && ti < ntiles) {
+      const int s = key_of(ti, lane);
+      if (cb) { ok = s < s_end; pos_next = ok ? cb[s] : 0; }
+      else { ok = s < s_end && mb[s] != 0; pos_next = s; }
+    }
+    return __ballot_sync(0xffffffffu, ok);
+  };
+  auto issue = [&](int stage, unsigned vbits, int pos_lane) {
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+      const int s = __shfl_sync(0xffffffffu, pos_lane, k);
+      if ((vbits >> k) & 1u)
+        a2_cp16(wbuf_s + stage * WSTAGE + k * AH_ROWB + (lane >> 3) * AH_QS + (lane & 7) * 16, Ub + (size_t)s * H + lane * 8, 16);
+    }
+  };
+  unsigned vbq[AG_NST - 1];
+  int posq[AG_NST - 1];
+#pragma unroll
+  for (int j = 0; j < AG_NST - 1; ++j) {
+    vbq[j] = valid_bits(j);
+    posq[j] = pos_next;
+    if (j < ntiles) issue(j, vbq[j], posq[j]);
+    a2_commit();
+  }
+  // v (a weight) in f16 -> shared memory
+  for (int i = tid; i < H; i += A2T) v_s[(i >> 6) * (AH_QS / 2) + (i & 63)] = __float2half_rn(vvec[i]);
+  pdl_wait();
+  // this lane's 64 hidden units of q[row myw] as 32 f16 pairs: qh[2 c + j2] = units 64 tq + 4 c + 2 j2, + 1
+  uint32_t qh[32];
+  {
+    const float* q = qa + (size_t)(r0 + min(myw, W - 1)) * H + tq * 64;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float4 x = *reinterpret_cast<const float4*>(q + c * 4);
+      qh[2 * c] = ah_pack(x.x, x.y);
+      qh[2 * c + 1] = ah_pack(x.z, x.w);
+    }
+  }
+  bool rowvalid = myw < W;
+  if (rowvalid && tok) rowvalid = tok[(size_t)(r0 + myw) * tok_ld + t] != 0;
+  __syncthreads();                                      // v_s
+  const uint32_t v_q = smem_u32(v_s) + tq * AH_QS;
+
+  float m_run = -INFINITY, l_run = 0.f, lw_run = 0.f;  // row myw over the keys this lane group sees (merged per tile)
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f;                  // gate sums of this lane's two (key slot, row) pairs
+  int stage = 0, fstage = AG_NST - 1;
+  for (int ti = 0; ti < ntiles; ++ti) {
+    const unsigned vb_new = valid_bits(ti + AG_NST - 1);
+    const int pos_new = pos_next;
+    if (ti + AG_NST - 1 < ntiles) issue(fstage, vb_new, pos_new);
+    a2_commit();
+    const unsigned vb = vbq[0];
+    const int pos = posq[0];
+    const int posA = __shfl_sync(0xffffffffu, pos, keyA), posB = __shfl_sync(0xffffffffu, pos, keyB);
+    const bool okA = rowvalid && ((vb >> keyA) & 1u), okB = rowvalid && ((vb >> keyB) & 1u);
+    float4 gA = make_float4(0.f, 0.f, 0.f, 0.f), gB = gA;
+    float prA = 1.f, prB = 1.f;
+    if (okA) { gA = __ldg(Gb + posA); if (pb) prA = __ldg(pb + posA); }
+    if (okB) { gB = __ldg(Gb + posB); if (pb) prB = __ldg(pb + posB); }
+    a2_wait<AG_NST - 1>();
+    __syncwarp();
+    const uint32_t ua_s = wbuf_s + stage * WSTAGE + keyA * AH_ROWB + tq * AH_QS;
+    const uint32_t ub_s = wbuf_s + stage * WSTAGE + keyB * AH_ROWB + tq * AH_QS;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vb != 0u) {
+#pragma unroll
+      for (int c2 = 0; c2 < 8; ++c2) {                    // two k-steps of the MMA per 16-byte load
+        uint32_t ua[4], ub[4], vv[4];
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(ua[0]), "=r"(ua[1]), "=r"(ua[2]), "=r"(ua[3]) : "r"(ua_s + c2 * 16));
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(ub[0]), "=r"(ub[1]), "=r"(ub[2]), "=r"(ub[3]) : "r"(ub_s + c2 * 16));
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(vv[0]), "=r"(vv[1]), "=r"(vv[2]), "=r"(vv[3]) : "r"(v_q + c2 * 16));
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const uint32_t q0 = qh[4 * c2 + 2 * h2], q1 = qh[4 * c2 + 2 * h2 + 1];
+          const uint32_t a0 = ah_tanh2(ah_add2(q0, ua[2 * h2])), a1 = ah_tanh2(ah_add2(q0, ub[2 * h2]));
+          const uint32_t a2 = ah_tanh2(ah_add2(q1, ua[2 * h2 + 1])), a3 = ah_tanh2(ah_add2(q1, ub[2 * h2 + 1]));
+          ah_mma(acc, a0, a1, a2, a3, vv[2 * h2], vv[2 * h2 + 1]);
+        }
+      }
+    }
+    // every column of D holds the score of its row: rows g (key A) and g + 8 (key B)
+    const float eA = okA ? acc[0] : -INFINITY, eB = okB ? acc[2] : -INFINITY;
+    if (myw < W) {
+      if (tq == 0 && ((vb >> keyA) & 1u || (!cb && key_of(ti, keyA) < s_end))) scores[(size_t)(r0 + myw) * S + posA] = eA;
+      if (tq == 1 && ((vb >> keyB) & 1u || (!cb && key_of(ti, keyB) < s_end))) scores[(size_t)(r0 + myw) * S + posB] = eB;
+    }
+    // online softmax of row myw over the tile's keys: two here, the others WMAX * 4 .. 16 lanes away
+    float tmax = fmaxf(eA, eB);
+#pragma unroll
+    for (int o = WMAX * 4; o < 32; o <<= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    const float mn = fmaxf(m_run, tmax);
+    const float sc = (m_run == -INFINITY) ? 0.f : fexp(m_run - mn);
+    const float pA = (eA == -INFINITY) ? 0.f : fexp(eA - mn), pB = (eB == -INFINITY) ? 0.f : fexp(eB - mn);
+    float psum = pA + pB, pwsum = fmaf(prA, pA, prB * pB);
+#pragma unroll
+    for (int o = WMAX * 4; o < 32; o <<= 1) {
+      psum += __shfl_xor_sync(0xffffffffu, psum, o);
+      pwsum += __shfl_xor_sync(0xffffffffu, pwsum, o);
+    }
+    l_run = fmaf(l_run, sc, psum);
+    lw_run = fmaf(lw_run, sc, pwsum);
+    m_run = mn;
+    g0 = fmaf(g0, sc, fmaf(pA, gA.x, pB * gB.x));
+    g1 = fmaf(g1, sc, fmaf(pA, gA.y, pB * gB.y));
+    g2 = fmaf(g2, sc, fmaf(pA, gA.z, pB * gB.z));
+    __syncwarp();                                         // this stage is refilled next iteration
+#pragma unroll
+    for (int j = 0; j + 1 < AG_NST - 1; ++j) { vbq[j] = vbq[j + 1]; posq[j] = posq[j + 1]; }
+    vbq[AG_NST - 2] = vb_new;
+    posq[AG_NST - 2] = pos_new;
+    fstage = stage;
+    stage = stage + 1 == AG_NST ? 0 : stage + 1;
+  }
+  a2_wait<0>();
+#pragma unroll
+  for (int o = WMAX * 4; o < 32; o <<= 1) {
+    g0 += __shfl_xor_sync(0xffffffffu, g0, o);
+    g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+    g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+  }
+  if (tq == 0 && g < WMAX && myw < W) {
+    float* d = wst[warp][myw];
+    d[0] = m_run; d[1] = l_run; d[2] = lw_run; d[3] = g0; d[4] = g1; d[5] = g2;
+  }
+  __syncthreads();
+  if (tid < W) {
+    float Mx = -INFINITY;
+#pragma unroll
+    for (int gg = 0; gg < 8; ++gg) Mx = fmaxf(Mx, wst[gg][tid][0]);
+    float l = 0.f, lw = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int gg = 0; gg < 8; ++gg) {
+      const float f = (wst[gg][tid][0] == -INFINITY) ? 0.f : fexp(wst[gg][tid][0] - Mx);
+      l = fmaf(wst[gg][tid][1], f, l);
+      lw = fmaf(wst[gg][tid][2], f, lw);
+      a0 = fmaf(wst[gg][tid][3], f, a0);
+      a1 = fmaf(wst[gg][tid][4], f, a1);
+      a2 = fmaf(wst[gg][tid][5], f, a2);
+    }
+    const size_t o = (size_t)(r0 + tid) * nsplit + sp;
+    reinterpret_cast<float4*>(stats)[o] = make_float4(Mx, l, lw, 0.f);
+    reinterpret_cast<float4*>(gate_part)[o] = make_float4(a0, a1, a2, 0.f);
+  }
+}
+
+template <int WMAX>
+static int launch_gate_h(const float* qa, const void* U, const float* G, const float* v, const uint8_t* mask,
+                         const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S, int nsplit,
+                         float* scores, float* stats, float* gate_part, const int32_t* cidx, const int32_t* ncount,
+                         const int32_t* qorder, const int32_t* nsq, cudaStream_t st) {
+  constexpr int KPT = 16 / WMAX;
+  const size_t smem = (size_t)8 * AG_NST * KPT * AH_ROWB + 4 * AH_QS;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(additive_attn_gate_h_kernel<WMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    attr = true;
+  }
+  launch_k(additive_attn_gate_h_kernel<WMAX>, dim3(B, nsplit), A2T, smem, st, qa, (const __half*)U, (const float4*)G, v, mask,
+           prior, tok, tok_ld, t, W, S, nsplit, scores, stats, gate_part, cidx, ncount, qorder, nsq);
+  return check_launch("case_additive_attn_gate_h");
+}
+
 // ---- prefill side of the gate form
 // G[n][0..2] = Wg[0..2][:] . mem[n][:] for N key rows (bf16 storage, fp32 accumulate): one warp per row, HBM-bound
 __global__ __launch_bounds__(256) void gate_project_kernel(const bf16* __restrict__ mem, const float* __restrict__ Wg,
@@ -805,18 +1057,20 @@ static int launch_gate(int fast, const float* qa, const void* U, const float* G,
                        const int32_t* qorder, const int32_t* nsq, cudaStream_t st) {
   constexpr int KPT = WMAX == 8 ? 2 : 4;
   const size_t smem = (size_t)8 * AG_NST * KPT * H * 2;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(additive_attn_gate_kernel<WMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(additive_attn_gate_kernel<WMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr = true;
-  }
-  if (fast)
-    launch_k(additive_attn_gate_kernel<WMAX, true>, dim3(B, nsplit), A2T, smem, st, qa, (const bf16*)U, (const float4*)G, v,
-             mask, prior, tok, tok_ld, t, W, S, nsplit, scores, stats, gate_part, cidx, ncount, qorder, nsq);
-  else
-    launch_k(additive_attn_gate_kernel<WMAX, false>, dim3(B, nsplit), A2T, smem, st, qa, (const bf16*)U, (const float4*)G, v,
-             mask, prior, tok, tok_ld, t, W, S, nsplit, scores, stats, gate_part, cidx, ncount, qorder, nsq);
+  const bool full = W == WMAX;
+#define AG_LAUNCH(FAST_, FULL_)                                                                                           \
+  do {                                                                                                                    \
+    static bool attr = false;                                                                                             \
+    if (!attr) {                                                                                                          \
+      cudaFuncSetAttribute(additive_attn_gate_kernel<WMAX, FAST_, FULL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); \
+      attr = true;                                                                                                        \
+    }                                                                                                                     \
+    launch_k(additive_attn_gate_kernel<WMAX, FAST_, FULL_>, dim3(B, nsplit), A2T, smem, st, qa, (const bf16*)U,            \
+             (const float4*)G, v, mask, prior, tok, tok_ld, t, W, S, nsplit, scores, stats, gate_part, cidx, ncount, qorder, nsq); \
+  } while (0)
+  if (fast) { if (full) AG_LAUNCH(true, true); else AG_LAUNCH(true, false); }
+  else { if (full) AG_LAUNCH(false, true); else AG_LAUNCH(false, false); }
+#undef AG_LAUNCH
   return check_launch("case_additive_attn_gate");
 }
 
@@ -947,4 +1201,24 @@ extern "C" int case_split_plan(const int32_t* count, int B, int slots, int max_s
   CB_REQUIRE(count && nsq && B > 0 && slots > 0 && max_split >= 1 && max_split <= CASE_MAX_SPLIT, "case_split_plan: bad arguments");
   launch_k(split_plan_kernel, 1, 256, 0, (cudaStream_t)stream, count, B, slots, max_split, nsq);
   return check_launch("case_split_plan");
+}
+
+/* case_additive_attn_gate with Uk.mem stored in f16 (U f16 [B][S][H]) for 2 <= W <= 8: packed f16 additions and
+ * tanh.approx.f16x2, the v-weighted sum over the hidden units on the tensor core (mma.m16n8k16, fp32
+ * accumulation).  Always the approximate tanh.  Everything else as case_additive_attn_gate. */
+extern "C" int case_additive_attn_gate_h(const float* qa, const void* U, const float* G, const float* v, const uint8_t* mask,
+                                         const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S,
+                                         int nsplit, float* attn_un, float* stats, float* gate_part, const int32_t* cidx,
+                                         const int32_t* ncount, const int32_t* qorder, const int32_t* nsq,
+                                         case_stream_t stream) {
+  using namespace cb;
+  CB_REQUIRE(qa && U && G && v && mask && attn_un && stats && gate_part, "case_additive_attn_gate_h: null pointer");
+  CB_REQUIRE(B > 0 && W >= 2 && W <= CASE_MAX_W && S > 0 && nsplit >= 1 && nsplit <= CASE_MAX_SPLIT, "case_additive_attn_gate_h: bad sizes (2 <= W <= 8)");
+  CB_REQUIRE((cidx == nullptr) == (ncount == nullptr), "case_additive_attn_gate_h: cidx and ncount go together");
+  CB_REQUIRE((uintptr_t)G % 16 == 0 && (uintptr_t)U % 16 == 0 && (uintptr_t)stats % 16 == 0 && (uintptr_t)gate_part % 16 == 0 && (uintptr_t)qa % 16 == 0,
+             "case_additive_attn_gate_h: qa, U, G, stats, gate_part must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (W <= 2) return launch_gate_h<2>(qa, U, G, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, attn_un, stats, gate_part, cidx, ncount, qorder, nsq, st);
+  if (W <= 4) return launch_gate_h<4>(qa, U, G, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, attn_un, stats, gate_part, cidx, ncount, qorder, nsq, st);
+  return launch_gate_h<8>(qa, U, G, v, mask, prior, tok, tok_ld, t, B, W, S, nsplit, attn_un, stats, gate_part, cidx, ncount, qorder, nsq, st);
 }

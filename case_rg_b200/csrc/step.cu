@@ -17,6 +17,7 @@ int g_use_tail = 2;
 int g_use_fused_select = 1;
 int g_use_post = 1;
 int g_use_gate = 1;
+int g_use_gate_h = 0;          // f16 / tensor-core form of the gate kernel when the step arguments carry U16 (measured slower: off)
 int g_xnext = 0;               // tiles per warp the passage cross-attention prefetches for the next layer's launch
 int g_prefetch_pct = 0;        // measured: no gain at C2 (the prefetch traffic slows the latency-bound launch more than it helps)
 int g_prefetch_mask = 3;       // bit 0: from the stack launch (layer 4), bit 1: from the chain launches (layers 5..7)
@@ -89,6 +90,11 @@ extern "C" int case_set_post_linears(int on) {
 extern "C" int case_set_gate_form(int on) {
   const int old = g_use_gate;
   if (on >= 0) g_use_gate = on ? 1 : 0;      // negative: query only
+  return old;
+}
+extern "C" int case_set_gate_f16(int on) {
+  const int old = g_use_gate_h;
+  if (on >= 0) g_use_gate_h = on ? 1 : 0;
   return old;
 }
 extern "C" int case_set_xattn_next_prefetch(int ntiles) {
@@ -181,6 +187,11 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
   additive:
     if (gate) {
       const bool cmp = i == 1 && a->xidx != nullptr && a->xcount != nullptr;
+      if (g_use_gate_h && a->U16[i] != nullptr && W >= 2 && a->fast_tanh)
+        return case_additive_attn_gate_h(qa, a->U16[i], a->Gv[i], a->va[i], a->mask[i], a->prior[i], a->tok, TL, t, B, W,
+                                         a->S[i], a->nsplit_a[i], a->attn_un[i], a->stats[i], a->ctxp[i],
+                                         cmp ? a->xidx : nullptr, cmp ? a->xcount : nullptr, cmp ? a->xorder : nullptr,
+                                         cmp ? a->xns : nullptr, s2);
       return case_additive_attn_gate(qa, a->U[i], a->Gv[i], a->va[i], a->mask[i], a->prior[i], a->tok, TL, t, B, W, a->S[i],
                                      a->nsplit_a[i], a->attn_un[i], a->stats[i], a->ctxp[i], a->fast_tanh,
                                      cmp ? a->xidx : nullptr, cmp ? a->xcount : nullptr, cmp ? a->xorder : nullptr,

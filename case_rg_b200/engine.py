@@ -225,6 +225,7 @@ class CaseWeights:
         self.Wv = g('gen.2.weight').contiguous().to(self.tdtype)                               # [V][H]
         self.Wv_tc = pack_vocab_tc(g('gen.2.weight')) if self.cdtype == L.BF16 else None
         self.Wm, self.bm = g('mix.weight').contiguous(), vec(g('mix.bias'))
+        self.Uk_t16 = [g(f'attns.{i}.linear_key.weight').t().contiguous().to(torch.float16) for i in range(2)]
         # gate form (CaSE/Model.py:39,117): W_m's slice for context i as a [H][4] projection of the memory keys
         self.Wm_g = [self.Wm[:, H * (1 + i):H * (2 + i)].contiguous() for i in range(2)]          # [3][H] each
 
@@ -341,6 +342,9 @@ class CaseDecodeEngine(_EngineBase):
         self.Mv = [torch.zeros(B, s, H, dtype=td, device=dev) for s in self.S]
         # gate-projected keys for the search path (case_additive_attn_gate): 3 gate logits' worth per key
         self.Gv = [z(B, s, 4) for s in self.S] if weights.cdtype == L.BF16 else None
+        # f16 copies of Uk.mem for the tensor-core form of the gate kernel (W >= 2, approximate tanh)
+        self.U16 = ([torch.zeros(B, s, H, dtype=torch.float16, device=dev) for s in self.S]
+                    if self.Gv is not None and W >= 2 and self.fast_tanh and L.load().case_set_gate_f16(-1) else None)
         self.mask = [torch.zeros(B, s, dtype=torch.uint8, device=dev) for s in self.S]
         self.prior = [z(B, s) for s in self.S]
         self.map = torch.zeros(B, S0 + S1, dtype=torch.int32, device=dev)
@@ -402,6 +406,8 @@ class CaseDecodeEngine(_EngineBase):
             a.ctx[i] = self.ctx[i].data_ptr()
             if self.Gv is not None:
                 a.Gv[i] = self.Gv[i].data_ptr()
+            if self.U16 is not None:
+                a.U16[i] = self.U16[i].data_ptr()
         a.map_off[0], a.map_off[1] = 0, self.S[0]
         a.max_len, a.BOS, a.EOS, a.UNK, a.PAD, a.materialize_only = self.Tmax, BOS, EOS, UNK, PAD, 0
         a.E, a.pe = w.E.data_ptr(), w.pe.data_ptr()
@@ -475,12 +481,18 @@ class CaseDecodeEngine(_EngineBase):
                 for l in range(4):
                     self.Kx[i * 4 + l].copy_(kv[l, 0])
                     self.Vx[i * 4 + l].copy_(kv[l, 1])
-            torch.mm(flat, w.Uk_t[i], out=self.U[i].view(B * S, H))
-            if self.Gv is None or not L.load().case_set_gate_form(-1):
+            lib = L.load()
+            lazy = self.Gv is not None and bool(lib.case_set_gate_form(-1))      # the search path reads G (and U16) only
+            use16 = lazy and self.U16 is not None and bool(lib.case_set_gate_f16(-1))
+            if use16:
+                torch.mm(mems[i].to(dev, torch.float16).reshape(B * S, H), w.Uk_t16[i], out=self.U16[i].view(B * S, H))
+            else:
+                torch.mm(flat, w.Uk_t[i], out=self.U[i].view(B * S, H))
+            if not lazy:
                 self.Mv[i].copy_(m)
                 self._mv_src[i] = None
             else:                   # the search path reads G instead; the value rows are filled when the `generate` face asks
-                self._mv_src[i] = m
+                self._mv_src[i] = (m, use16)
                 L.call('case_gate_project', flat.data_ptr(), w.Wm_g[i].data_ptr(), self.Gv[i].data_ptr(), B * S, stream)
             self.mask[i].copy_(masks[i].to(dev).to(torch.uint8))
             self.prior[i].copy_(priors[i].to(dev, torch.float32))
@@ -522,7 +534,10 @@ class CaseDecodeEngine(_EngineBase):
         [R, V] of it (no top-k / select); the caller drives tok/anc through ``state``."""
         for i in range(2):
             if self._mv_src[i] is not None:
-                self.Mv[i].copy_(self._mv_src[i].view_as(self.Mv[i]))
+                m, need_u = self._mv_src[i]
+                self.Mv[i].copy_(m.view_as(self.Mv[i]))
+                if need_u:          # the bf16 Uk.mem of the context-form kernels was skipped at prefill
+                    torch.mm(m.reshape(-1, L.H), self.w.Uk_t[i], out=self.U[i].view(-1, L.H))
                 self._mv_src[i] = None
         self.args.materialize_only = 1
         stream = torch.cuda.current_stream(self.device)

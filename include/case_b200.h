@@ -80,6 +80,11 @@ int case_set_gate_form(int on);
  * of every warp's range of the stream KVnext (the next layer's K|V: same B, S, counts), so that launch fills its
  * rings from L2 while HBM was idle anyway.  One-shot; ntiles <= 0 keeps the previous depth (default 3). */
 int case_cross_attn_part_next(const void* KVnext, int ntiles);
+/* f16 / tensor-core form of the gate kernel (case_additive_attn_gate_h) when the step arguments carry U16, W >= 2
+ * and fast_tanh.  Default OFF: on sm_100a tanh.approx.f16x2 is two MUFU.TANH.F16 plus a PRMT, so the MUFU count
+ * does not drop and the kernel measures 56 us against 47 us at the BASELINE shape (kept as an experiment; its
+ * f16 Uk.mem is the more accurate storage).  Returns the old setting, a negative argument only queries. */
+int case_set_gate_f16(int on);
 /* Tiles per warp that case_decode_step asks the passage cross-attention of layer L to prefetch for layer L+1
  * (default 0 = off: measured neutral at the BASELINE shape, the launch is bound by its fixed cost); returns the old setting. */
 int case_set_xattn_next_prefetch(int ntiles);
@@ -303,6 +308,15 @@ int case_additive_attn_gate(const float* qa, const void* U, const float* G, cons
                             const int32_t* cidx, const int32_t* ncount, const int32_t* qorder, const int32_t* nsq,
                             case_stream_t stream);
 
+/* case_additive_attn_gate with Uk.mem stored in f16 (U f16 [B][S][H]), for 2 <= W <= 8: packed f16 additions and
+ * tanh.approx.f16x2 (always the approximate tanh), and the v-weighted sum over the hidden units on the tensor
+ * core (mma.m16n8k16, the tanh values as produced are the A fragment, B = v; fp32 accumulation): no butterfly,
+ * no FFMA, 4.9 instead of 6.2 instructions per tanh (experiment, see case_set_gate_f16). */
+int case_additive_attn_gate_h(const float* qa, const void* U, const float* G, const float* v, const uint8_t* mask,
+                              const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S,
+                              int nsplit, float* attn_un, float* stats, float* gate_part, const int32_t* cidx,
+                              const int32_t* ncount, const int32_t* qorder, const int32_t* nsq, case_stream_t stream);
+
 /* Prefill of the gate form: G fp32 [N][4] = (Wg[0..2] . mem[n], 0) for N key rows mem bf16 [N][H];
  * Wg fp32 [3][H] = W_m[:, H(1+i):H(2+i)] of memory i (CaSE/Model.py:36,39). */
 int case_gate_project(const void* mem, const float* Wg, float* G, long long N, case_stream_t stream);
@@ -472,6 +486,7 @@ typedef struct {
   int32_t* qcount;                      /* [B] zeros (may be NULL): lets the sparse tail run the search bookkeeping */
   const void* Wqa_c[2]; const void* Wg_c;   /* attention-query / gen.0 weights as post linears of the cluster launches (may be NULL) */
   const int32_t* xns;                   /* [B] splits of the second memory's additive attention per query (may be NULL) */
+  const void* U16[2];                   /* [B][S_i][H] f16 copies of U (may be NULL): case_additive_attn_gate_h when W >= 2 and fast_tanh */
   const float* Gv[2];                   /* [B][S_i][4] fp32 gate-projected memories (may be NULL): the search path then runs
                                            case_additive_attn_gate and never reads Mv */
 } case_step_args_t;

@@ -202,6 +202,71 @@ def test_additive_attention_gate_form_vs_torch(W, S, nsplit, use_prior, compact)
     assert rel_err((Q / Z.clamp_min(1e-30))[live], (pr * a).sum(1)[live]) < 2e-4
 
 
+@pytest.mark.parametrize('compact', [False, True])
+@pytest.mark.parametrize('W,S,nsplit,use_prior', [(4, 2560, 9, True), (4, 1000, 3, False), (8, 333, 2, True), (2, 130, 2, False),
+                                                  (3, 77, 1, True), (2, 60, 1, True)])
+def test_additive_attention_gate_f16_tensor_core_form_vs_torch(W, S, nsplit, use_prior, compact):
+    """case_additive_attn_gate_h (Uk.mem in f16, packed tanh, v-weighted sum on the tensor core) against torch on
+    the same f16-rounded U: scores, softmax partials, gate partials; masked and compacted walks, per-query split
+    counts, an empty query, a PAD-input row."""
+    from case_rg_b200 import _lib as L
+    B, H = 4, 256
+    g = torch.Generator().manual_seed(W * 100 + S + 11)
+    qa = torch.randn(B * W, H, generator=g).to(DEV)
+    U = torch.randn(B, S, H, generator=g).to(DEV).to(torch.float16)
+    G = torch.randn(B, S, 4, generator=g).to(DEV)
+    v = (torch.randn(H, generator=g) * 0.3).to(DEV)
+    mask = torch.rand(B, S, generator=g) > 0.25
+    mask[:, 0] = True
+    if S > 200:
+        mask[1, 64:192] = False
+    mask[3] = False
+    mask = mask.to(DEV)
+    prior = torch.rand(B, S, generator=g).to(DEV) if use_prior else None
+    tok = torch.ones(B * W, 4, dtype=torch.int32, device=DEV)
+    tok[0, 2] = 0
+    scores = torch.full((B * W, S), float('nan'), device=DEV)
+    stats = torch.full((B * W, nsplit, 4), float('nan'), device=DEV)
+    gpart = torch.full((B * W, nsplit, 4), float('nan'), device=DEV)
+    cidx = ncount = qorder = nsq = None
+    if compact:
+        cidx = torch.argsort(~mask, dim=1, stable=True).to(torch.int32)
+        ncount = mask.sum(1).to(torch.int32)
+        qorder = torch.argsort(ncount, descending=True, stable=True).to(torch.int32)
+        scores.masked_fill_(~mask.repeat_interleave(W, 0), float('-inf'))
+        nsq = (ncount.float() / max(1.0, float(ncount.max())) * nsplit).ceil().clamp(1, nsplit).to(torch.int32)
+    L.call('case_additive_attn_gate_h', qa.data_ptr(), U.data_ptr(), G.data_ptr(), v.data_ptr(),
+           mask.to(torch.uint8).data_ptr(), L.ptr(prior), tok.data_ptr(), 4, 2, B, W, S, nsplit, scores.data_ptr(),
+           stats.data_ptr(), gpart.data_ptr(), L.ptr(cidx), L.ptr(ncount), L.ptr(qorder), L.ptr(nsq),
+           torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    e = (torch.tanh(qa.view(B, W, 1, H) + U.float().view(B, 1, S, H)) @ v).view(B * W, S)
+    ok = mask.repeat_interleave(W, 0).clone()
+    ok[0] = False
+    e = e.masked_fill(~ok, float('-inf'))
+    assert torch.equal(torch.isinf(scores), torch.isinf(e))
+    fin = ~torch.isinf(e)
+    # f16 rounding of q + u (2^-11 relative) and tanh.approx.f16x2 (~5e-4 absolute), 256 terms weighted by |v| ~ 0.3
+    assert float((scores[fin] - e[fin]).abs().max()) < 2.5e-2, float((scores[fin] - e[fin]).abs().max())
+    assert float((scores[fin] - e[fin]).abs().mean()) < 4e-3
+    # the partials are exact functions of the kernel's OWN scores: compare them with torch on those
+    m = stats[..., 0]
+    assert not bool(torch.isnan(stats).any()) and not bool(torch.isnan(gpart).any())
+    M = m.max(1, keepdim=True).values
+    w = torch.where(torch.isinf(m), torch.zeros_like(m), torch.exp(m - M))
+    Z = (stats[..., 1] * w).sum(1)
+    Q = (stats[..., 2] * w).sum(1)
+    gs = (gpart * w.unsqueeze(-1)).sum(1) / Z.clamp_min(1e-30).unsqueeze(-1)
+    a = torch.softmax(scores, 1)
+    a = torch.where(torch.isnan(a), torch.zeros_like(a), a)
+    want = torch.bmm(a.view(B, W, S), G).view(B * W, 4)
+    live = Z > 0
+    assert bool((~live)[0]) and bool(live[1:3 * W].all()) and not bool(live[3 * W:].any())
+    assert rel_err(gs[live][:, :3], want[live][:, :3]) < 2e-4
+    pr = prior.repeat_interleave(W, 0) if use_prior else torch.ones_like(a)
+    assert rel_err((Q / Z.clamp_min(1e-30))[live], (pr * a).sum(1)[live]) < 2e-4
+
+
 # --------------------------------------------------------------------------- cluster layer kernels
 def _chain_case(B, W, T, V=3000, seeds=(51, 52)):
     from case_rg_b200 import synthetic as syn

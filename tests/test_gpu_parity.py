@@ -257,8 +257,9 @@ def test_gate_form_equals_context_form():
     lib = L.load()
     res = {}
     try:
-        for on in (0, 1):
-            lib.case_set_gate_form(on)
+        for on in (0, 1, 2):                        # context form, gate form, gate form in f16 on the tensor core
+            lib.case_set_gate_form(1 if on else 0)
+            lib.case_set_gate_f16(1 if on == 2 else 0)
             model = FG.FastCaSE(sd, device=DEV, dtype='bf16', use_graph=False)
             toks = FG.beam(model, _case_data(inp), None, T, W).cpu()
             eng = model.last_engine
@@ -269,12 +270,14 @@ def test_gate_form_equals_context_form():
             res[on] = (toks, eng.gates[::W, :3].clone(), eng.top_vals[::W].clone(), eng.top_idx[::W].clone())
     finally:
         lib.case_set_gate_form(1)
-    assert torch.allclose(res[0][1], res[1][1], atol=3e-3), (res[0][1], res[1][1])
-    assert torch.allclose(res[0][2], res[1][2], rtol=2e-2, atol=1e-6)
-    assert (res[0][3] == res[1][3]).float().mean() > 0.9
-    Lc = min(res[0][0].size(1), res[1][0].size(1))
-    same = sum(int(torch.equal(res[0][0][i, :Lc], res[1][0][i, :Lc])) for i in range(B))
-    assert same >= B - 1, (res[0][0], res[1][0])
+        lib.case_set_gate_f16(0)
+    for k in (1, 2):
+        assert torch.allclose(res[0][1], res[k][1], atol=3e-3), (k, res[0][1], res[k][1])
+        assert torch.allclose(res[0][2], res[k][2], rtol=2e-2, atol=1e-6)
+        assert (res[0][3] == res[k][3]).float().mean() > 0.9
+        Lc = min(res[0][0].size(1), res[k][0].size(1))
+        same = sum(int(torch.equal(res[0][0][i, :Lc], res[k][0][i, :Lc])) for i in range(B))
+        assert same >= B - 1, (k, res[0][0], res[k][0])
 
 
 # --------------------------------------------------------------------------- properties at BASELINE size
