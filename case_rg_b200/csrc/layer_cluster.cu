@@ -132,9 +132,10 @@ __device__ __forceinline__ void c_cpasync16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void c_cpasync_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
+// all CTAs of the cluster have initialised their mbarriers (made visible by fence.mbarrier_init.release.cluster):
+// a RELAXED arrive is enough - the release form costs ~1 us (MEMBAR.ALL.GPU + CCTL.IVALL)
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t c_mapa(uint32_t addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
@@ -393,6 +394,7 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
     c_mb_expect(s_bxf, XF_BYTES);
   }
   __syncthreads();
+  cluster_arrive_relaxed();  // "my barriers exist": the matching wait comes after the prologue loads below
   refill(0);
 
   // ---- KV-cache history of heads 2c, 2c+1 for the 8 rows -> shared memory (positions 0..t-1), and the
@@ -434,7 +436,7 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
   float2 bres = make_float2(0.f, 0.f);               // residual b of the cross-attention block (own columns)
   if (a.has_back) bres = *reinterpret_cast<const float2*>(a.b_in + (size_t)erl * H + ecol);
 
-  cluster_sync_all();      // every CTA of the cluster is resident (barriers initialised) before any remote store
+  cluster_wait();          // every CTA of the cluster is resident (barriers initialised) before any remote store
   stamp();
   pdl_wait();              // partials / tokens come from the kernel launched just before this one
   stamp();
@@ -532,22 +534,23 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
       const int ns = a.nsplit;
       const size_t pb = ((size_t)arl * NH + 2 * c + ahl) * ns;
       float M = -INFINITY, Z = 0.f, c0 = 0.f, c1 = 0.f;
-      for (int jb = 0; jb < ns; jb += 8) {        // 16 loads in flight per round
-        float2 ml[8], pa[8];
+      constexpr int MB = 12;                       // slots per round: 24 loads in flight (10 slots at S1 = 2560: one round)
+      for (int jb = 0; jb < ns; jb += MB) {
+        float2 ml[MB], pa[MB];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < MB; ++u) {
           const int j = min(jb + u, ns - 1);
           ml[u] = *reinterpret_cast<const float2*>(a.part_ml + (pb + j) * 2);
           pa[u] = *reinterpret_cast<const float2*>(a.part_acc + (pb + j) * HD + 2 * acp);
         }
         float bm = -INFINITY;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) bm = fmaxf(bm, ml[u].x);
+        for (int u = 0; u < MB; ++u) bm = fmaxf(bm, ml[u].x);
         const float Mn = fmaxf(M, bm);
         const float rs = (M == -INFINITY) ? 0.f : fexp(M - Mn);
         Z *= rs; c0 *= rs; c1 *= rs;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < MB; ++u) {
           const float e = (jb + u < ns && ml[u].x != -INFINITY) ? fexp(ml[u].x - Mn) : 0.f;
           Z = fmaf(ml[u].y, e, Z);
           c0 = fmaf(pa[u].x, e, c0);

@@ -34,8 +34,8 @@ def timing():
         dbg.zero_()
         lib.case_debug_chain_timing(dbg.data_ptr())
         L.check(lib.case_layer_chain(C.byref(a.layers[4]), C.byref(a.layers[5]), None, None, None, 16.0, None, a.bbuf,
-                                     a.part_ml, a.part_acc, a.nsplit_x[1], a.h, a.kcache[5], a.vcache[5], a.anc[t & 1],
-                                     T + 1, a.tok, T + 1, a.prow, t, T, a.bbuf, a.q2, eng.R, 0, st), 'chain')
+                                     a.part_ml, a.part_acc, (eng.xslots or a.nsplit_x[1]), a.h, a.kcache[5], a.vcache[5], a.anc[t & 1],
+                                     T + 1, a.tok, T + 1, a.prow, t, T, a.bbuf, a.q2, eng.R, 0, None, st), 'chain')
         torch.cuda.synchronize()
         lib.case_debug_chain_timing(None)
         s = dbg.cpu().tolist()
@@ -47,8 +47,8 @@ def timing():
     e0.record()
     for _ in range(50):
         lib.case_layer_chain(C.byref(a.layers[4]), C.byref(a.layers[5]), None, None, None, 16.0, None, a.bbuf,
-                             a.part_ml, a.part_acc, a.nsplit_x[1], a.h, a.kcache[5], a.vcache[5], a.anc[t & 1],
-                             T + 1, a.tok, T + 1, a.prow, t, T, a.bbuf, a.q2, eng.R, 0, st)
+                             a.part_ml, a.part_acc, (eng.xslots or a.nsplit_x[1]), a.h, a.kcache[5], a.vcache[5], a.anc[t & 1],
+                             T + 1, a.tok, T + 1, a.prow, t, T, a.bbuf, a.q2, eng.R, 0, None, st)
     e1.record()
     torch.cuda.synchronize()
     print(f'back-to-back launches: {e0.elapsed_time(e1) / 50 * 1e3:.1f} us each')
