@@ -385,18 +385,17 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
   // ---- fused search bookkeeping: the last CTA of a query's W rows runs Generations.beam / greedy for it
   if (do_select) {
     __shared__ int s_last;
-    __threadfence();                                      // this row's top-k is visible device-wide
-    __syncthreads();
+    __syncthreads();                                      // this row's top-k is written (CTA scope) ...
     if (tid == 0) {
-      const int old = atomicAdd(qcount + b, 1);
+      // ... and published by ONE release at device scope (cumulative over the barrier) instead of a
+      // sequentially-consistent fence by all 512 threads; the same operation acquires the other rows' top-k
+      int old;
+      asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(qcount + b) : "memory");
       s_last = old == a.W - 1;
       if (s_last) qcount[b] = 0;                          // ready for the next step
     }
     __syncthreads();
-    if (s_last && warp == 0) {
-      __threadfence();
-      beam_select_query(sel, b, lane);
-    }
+    if (s_last && warp == 0) beam_select_query(sel, b, lane);
   }
 }
 
