@@ -414,19 +414,21 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
       }
       prow[ii * CTMAX + j] = pv;
     }
+    __syncthreads();                 // load_history reads entries other threads wrote
   };
-  auto load_history = [&](const bf16* kc, const bf16* vc) {   // needs prow (same thread wrote the entries it reads)
-    for (int idx = tid; idx < CROWS * (t + 1); idx += CT) {
-      const int ii = idx / (t + 1), j = idx - ii * (t + 1);
-      if (j < t) {
+  // K and V of (row ii, position j < t) are one 128-byte line each (heads 2c, 2c+1): eight consecutive lanes copy
+  // its eight 16-byte chunks, so a warp instruction touches 4 lines (one lane per (row, position) pair touched 32:
+  // 4096 line requests per layer, ~2 us of LSU time in the middle of the stage chain)
+  auto load_history = [&](const bf16* kc, const bf16* vc) {   // needs load_prow
+    const uint32_t ks = smem_u32(kh_s), vs = smem_u32(vh_s);
+    for (int ii = 0; ii < CROWS; ++ii) {
+      for (int i = tid; i < t * 8; i += CT) {
+        const int j = i >> 3, q = i & 7;           // chunks 0..3: head 2c, 4..7: head 2c+1
         const uint32_t pv = prow[ii * CTMAX + j];
-        const size_t goff = ((size_t)(pv & ~CMASKED) * Tmax + j) * H + CCOL * c;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {   // chunks 0..3: head 2c, 4..7: head 2c+1
-          const uint32_t soff = (uint32_t)((((ii * 2 + (q >> 2)) * Tmax + j) * 32 + (q & 3) * 8) * 2);
-          c_cpasync16(smem_u32(kh_s) + soff, kc + goff + q * 8);
-          c_cpasync16(smem_u32(vh_s) + soff, vc + goff + q * 8);
-        }
+        const size_t goff = ((size_t)(pv & ~CMASKED) * Tmax + j) * H + CCOL * c + q * 8;
+        const uint32_t soff = (uint32_t)((((ii * 2 + (q >> 2)) * Tmax + j) * 32 + (q & 3) * 8) * 2);
+        c_cpasync16(ks + soff, kc + goff);
+        c_cpasync16(vs + soff, vc + goff);
       }
     }
   };
