@@ -262,14 +262,21 @@ __device__ __forceinline__ void ln_rows(const float* xf, const LnPar& lp, bf16* 
   const float4 x0 = *reinterpret_cast<const float4*>(xf + i * CFLD + lane * 8);
   const float4 x1 = *reinterpret_cast<const float4*>(xf + i * CFLD + lane * 8 + 4);
   const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-  float s = 0.f;
+  // one reduction round for both moments (the two shuffle chains interleave): the rows are residual-stream
+  // activations with |mean| of the order of the standard deviation, so E[x^2] - mean^2 loses nothing in fp32;
+  // shifting by the lane's first element keeps it that way for any input
+  const float sh = __shfl_sync(0xffffffffu, v[0], 0);
+  float s = 0.f, q = 0.f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) s += v[k];
-  const float mean = warp_sum(s) * (1.f / H);
-  float q = 0.f;
+  for (int k = 0; k < 8; ++k) { const float d = v[k] - sh; s += d; q = fmaf(d, d, q); }
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { const float d = v[k] - mean; q = fmaf(d, d, q); }
-  const float rstd = rsqrtf(warp_sum(q) * (1.f / H) + LN_EPS);
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const float md = s * (1.f / H);                  // mean - sh
+  const float mean = md + sh;
+  const float rstd = rsqrtf(fmaxf(q * (1.f / H) - md * md, 0.f) + LN_EPS);
   float y[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) y[k] = (v[k] - mean) * rstd * lp.g[k] + lp.b[k];

@@ -179,15 +179,41 @@ class FastCaSE(_FastModel):
             nxt = next(it, None)
             if nxt is not None:             # the next batch starts crossing PCIe before this one decodes
                 ready = stage(k ^ 1, nxt)
-            if pending is not None:         # answers of the previous batch (host sync), then reuse its state
-                yield pending._finish_tokens(max_len, mode).cpu()
             if mode != L.MODE_BEAM and eng.W != 1:
                 raise ValueError('greedy modes need an engine built with W == 1')
-            eng.launch(max_len, mode, use_graph=self.use_graph)
+            if pending is not None and not hasattr(pending, 'subs'):
+                # answers of the previous batch: snapshot them on the device (stream-ordered after its decode), put
+                # THIS batch's decode behind the snapshot right away, and only then wait for the snapshot on a side
+                # stream - the device never idles while the host reads answers
+                snap = (pending.state.out_tokens[:, :max_len].clone(), pending.state.best_len.clone())
+                ev = torch.cuda.Event()
+                ev.record(main)
+                eng.launch(max_len, mode, use_graph=self.use_graph)
+                yield self._read_snapshot(snap, ev, mode)
+            else:
+                if pending is not None:     # sliced engines: answers of the previous batch (host sync), then reuse the state
+                    yield pending._finish_tokens(max_len, mode).cpu()
+                eng.launch(max_len, mode, use_graph=self.use_graph)
             self.last_engine = pending = eng
             k ^= 1
         if pending is not None:
             yield pending._finish_tokens(max_len, mode).cpu()
+
+    def _read_snapshot(self, snap, ev, mode):
+        """Device snapshot (tokens [B, T] int32, best_len [B]) -> host int64 tokens, trimmed like _finish_tokens."""
+        dev = self.weights.device
+        if getattr(self, '_d2h_stream', None) is None:
+            self._d2h_stream = torch.cuda.Stream(dev)
+        d2h = self._d2h_stream
+        d2h.wait_event(ev)
+        with torch.cuda.stream(d2h):
+            toks = snap[0].to('cpu', non_blocking=True)
+            blen = snap[1].to('cpu', non_blocking=True)
+        d2h.synchronize()
+        out = toks.to(torch.int64)
+        if mode == L.MODE_BEAM:             # merge1D (Utils.py:366-377): pad to the longest answer of the batch
+            out = out[:, :max(int(blen.max()), 1)]
+        return out
 
     def module_greedy(self, data, max_len):
         """The in-module loop of CaSETransformerSeqDecoder.forward (no EOS handling, Model.py:91-123)."""
