@@ -174,6 +174,44 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
     const float y = a.hN[(size_t)r * H + col];
     float Z[2], Q[2], cx[2] = {0.f, 0.f};
     float gsum[3] = {0.f, 0.f, 0.f};                       // gate form: W_m,i . m_i summed over both memories
+    if (a.gate_ctx) {
+      // gate form: one load round for everything - lane (half = memory, slot) fetches the statistics and the gate
+      // partials of its slot, the merge is a segmented (16-lane) shuffle reduction (ns <= CASE_MAX_SPLIT = 16)
+      const int half = lane >> 4, sl = lane & 15;
+      const int nsh = half ? a.ns[1] : a.ns[0];
+      const float4* stp = reinterpret_cast<const float4*>(half ? a.stats[1] : a.stats[0]);
+      const float4* gpp = reinterpret_cast<const float4*>(half ? a.ctxp[1] : a.ctxp[0]);
+      float4 sj = make_float4(-INFINITY, 0.f, 0.f, 0.f), gj = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (sl < nsh) {
+        sj = __ldg(stp + (size_t)r * nsh + sl);
+        gj = gpp[(size_t)r * nsh + sl];
+      }
+      float Mx = sj.x;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) Mx = fmaxf(Mx, __shfl_xor_sync(0xffffffffu, Mx, o));
+      const float e = (sj.x == -INFINITY) ? 0.f : fexp(sj.x - Mx);
+      float z = sj.y * e, q = sj.z * e, a0 = gj.x * e, a1 = gj.y * e, a2 = gj.z * e;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        z += __shfl_xor_sync(0xffffffffu, z, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      }
+      const float g0h = z > 0.f ? a0 / z : 0.f, g1h = z > 0.f ? a1 / z : 0.f, g2h = z > 0.f ? a2 / z : 0.f;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        M[i] = __shfl_sync(0xffffffffu, Mx, 16 * i);
+        Z[i] = __shfl_sync(0xffffffffu, z, 16 * i);
+        Q[i] = __shfl_sync(0xffffffffu, q, 16 * i);
+        gsum[0] += __shfl_sync(0xffffffffu, g0h, 16 * i);
+        gsum[1] += __shfl_sync(0xffffffffu, g1h, 16 * i);
+        gsum[2] += __shfl_sync(0xffffffffu, g2h, 16 * i);
+      }
+      wstamp();
+      wstamp();
+    } else {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int ns = a.ns[i];
@@ -182,20 +220,7 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
 #pragma unroll 4
       for (int j = 0; j < ns; ++j) Mx = fmaxf(Mx, __ldg(st + j).x);
       float z = 0.f, q = 0.f;
-      if (a.gate_ctx) {
-        const float4* gp = reinterpret_cast<const float4*>(a.ctxp[i]) + (size_t)r * ns;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-#pragma unroll 4
-        for (int j = 0; j < ns; ++j) {
-          const float4 sj = __ldg(st + j);
-          const float4 gj = gp[j];
-          const float e = (sj.x == -INFINITY) ? 0.f : fexp(sj.x - Mx);
-          z = fmaf(sj.y, e, z);
-          q = fmaf(sj.z, e, q);
-          a0 = fmaf(gj.x, e, a0); a1 = fmaf(gj.y, e, a1); a2 = fmaf(gj.z, e, a2);
-        }
-        if (z > 0.f) { gsum[0] += a0 / z; gsum[1] += a1 / z; gsum[2] += a2 / z; }
-      } else {
+      {
         const float* cp = a.ctxp[i] + (size_t)r * ns * H + col;
         float acc = 0.f;
 #pragma unroll 4
@@ -212,6 +237,7 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
       }
       M[i] = Mx; Z[i] = z; Q[i] = q;
       wstamp();
+    }
     }
     float part[3];
 #pragma unroll
@@ -262,32 +288,36 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
     __syncthreads();       // the table is initialised
   }
   stamp();
-  // ---- copy mass of both memories into the hash table (linear probing, ids are exact)
-#pragma unroll 1
-  for (int i = 0; i < 2; ++i) {
-    if (i >= a.nmem) break;
-    const float Fi = i == 0 ? F[0] : F[1], Mi = i == 0 ? M[0] : M[1];
-    if (Fi == 0.f) continue;
-    const int S = a.S[i];
-    const float* at = a.attn_un[i] + (size_t)r * S;
-    const float* pr = a.prior[i] ? a.prior[i] + (size_t)b * S : nullptr;
-    const int32_t* mp = a.map + (size_t)b * a.map_ld + a.map_off[i];
-    constexpr int HU = 8;                                  // positions per thread per round: all their loads in flight together
-    for (int s0 = tid; s0 < S; s0 += HU * TS) {
+  // ---- copy mass of both memories into the hash table (double hashing, ids are exact).  The source positions of
+  // both memories are one index space, so all loads of a thread (ids, scores, priors: <= 6 positions at S = 2620)
+  // are in flight in ONE round
+  {
+    const int S0n = a.S[0], S1n = a.nmem > 1 ? a.S[1] : 0, Stot = S0n + S1n;
+    const float* at0 = a.attn_un[0] + (size_t)r * S0n;
+    const float* at1 = a.nmem > 1 ? a.attn_un[1] + (size_t)r * S1n : nullptr;
+    const float* pr0 = a.prior[0] ? a.prior[0] + (size_t)b * S0n : nullptr;
+    const float* pr1 = (a.nmem > 1 && a.prior[1]) ? a.prior[1] + (size_t)b * S1n : nullptr;
+    const int32_t* mp0 = a.map + (size_t)b * a.map_ld + a.map_off[0];
+    const int32_t* mp1 = a.map + (size_t)b * a.map_ld + a.map_off[1];
+    constexpr int HU = 8;                                  // positions per thread per round
+    for (int s0 = tid; s0 < Stot; s0 += HU * TS) {
       int id[HU];
       float ev[HU], pv[HU];
 #pragma unroll
       for (int u = 0; u < HU; ++u) {
         const int sidx = s0 + u * TS;
-        const bool in = sidx < S;
-        id[u] = in ? __ldg(mp + sidx) : -1;
-        ev[u] = in ? at[sidx] : -INFINITY;
-        pv[u] = (in && pr) ? __ldg(pr + sidx) : 1.f;
+        const bool in = sidx < Stot, m1 = sidx >= S0n;
+        const int sl = m1 ? sidx - S0n : sidx;
+        const float* pr = m1 ? pr1 : pr0;
+        id[u] = in ? __ldg((m1 ? mp1 : mp0) + sl) : -1;
+        ev[u] = in ? (m1 ? at1 : at0)[sl] : -INFINITY;
+        pv[u] = (in && pr) ? __ldg(pr + sl) : 1.f;
       }
 #pragma unroll
       for (int u = 0; u < HU; ++u) {
         if (ev[u] == -INFINITY || (unsigned)id[u] >= (unsigned)V) continue;   // masked source position
-        const float cw = Fi * pv[u] * fexp(ev[u] - Mi);
+        const bool m1 = s0 + u * TS >= S0n;
+        const float cw = (m1 ? F[1] : F[0]) * pv[u] * fexp(ev[u] - (m1 ? M[1] : M[0]));
         if (cw == 0.f) continue;
         uint32_t slot = sp_hash(id[u], hshift);
         const uint32_t step = sp_step(id[u]);

@@ -75,8 +75,13 @@ def stamps(**kw):
             print(f'   {n:16s} {s[i + 1] - s[i]:7d} cyc')
 
 
-def sparse_stamps(R=256, W=4, V=30522, S=(60, 2560), K=4):
-    a, keep = build(R=R, W=W, V=V, S=S, K=K)
+def sparse_stamps(R=256, W=4, V=30522, S=(60, 2560), K=4, gate=True):
+    a, keep = build(R=R, W=W, V=V, S=S, K=K, ns=(2, 16) if gate else (1, 10))
+    if gate:                               # production form: gate partials [R][ns][4] instead of context partials
+        keep['gp'] = [torch.randn(R, n, 4, dtype=torch.float32, device='cuda') for n in (2, 16)]
+        for i in range(2):
+            a.ctxp[i] = keep['gp'][i].data_ptr()
+        a.gate_ctx = 1
     lib = L.load()
     lib.case_debug_sparse_tail_timing.argtypes = [C.c_void_p]
     f32 = dict(dtype=torch.float32, device='cuda')
