@@ -54,7 +54,8 @@ class TailArgs(C.Structure):
                [('ns', i32 * 2), ('fac_off', i32 * 2), ('map_off', i32 * 2), ('S', i32 * 2),
                 ('logits', vp), ('hN', vp), ('stats', vp * 2), ('ctxp', vp * 2), ('Wm', vp), ('bm', vp),
                 ('ctx', vp * 2), ('gates', vp), ('fac', vp), ('map', vp), ('prior', vp * 2), ('attn_un', vp * 2),
-                ('top_vals', vp), ('top_idx', vp), ('dist', vp), ('gate_ctx', i32)]
+                ('top_vals', vp), ('top_idx', vp), ('dist', vp), ('gate_ctx', i32), ('cp_ld', i32),
+                ('cp_n', vp), ('cp_uid', vp), ('cp_first', vp), ('cp_start', vp), ('cp_perm', vp)]
 
 
 class StepArgs(C.Structure):
@@ -70,7 +71,7 @@ class StepArgs(C.Structure):
                 ('out_tokens', vp), ('n_live', vp),
                 ('x_in', vp), ('h', vp), ('bbuf', vp), ('q2', vp), ('part_ml', vp), ('part_acc', vp), ('qa', vp),
                 ('attn_un', vp * 2), ('stats', vp * 2), ('ctxp', vp * 2), ('hN', vp), ('ctx', vp * 2), ('gates', vp),
-                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp), ('prow', vp), ('h0', vp), ('qa1', vp), ('base_ms', vp), ('base_e', vp), ('base_i', vp), ('xcount', vp), ('xprefix', vp), ('xslots', i32), ('xidx', vp), ('xorder', vp), ('qcount', vp), ('Wqa_c', vp * 2), ('Wg_c', vp), ('xns', vp), ('U16', vp * 2), ('Gv', vp * 2)]
+                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp), ('prow', vp), ('h0', vp), ('qa1', vp), ('base_ms', vp), ('base_e', vp), ('base_i', vp), ('xcount', vp), ('xprefix', vp), ('xslots', i32), ('xidx', vp), ('xorder', vp), ('qcount', vp), ('Wqa_c', vp * 2), ('Wg_c', vp), ('xns', vp), ('cp_n', vp), ('cp_uid', vp), ('cp_first', vp), ('cp_start', vp), ('cp_perm', vp), ('cp_ld', i32), ('U16', vp * 2), ('Gv', vp * 2)]
 
 
 class GttpStepArgs(C.Structure):
@@ -140,6 +141,7 @@ _PROTOS = {
     'case_set_kv_prefetch': [i32],
     'case_set_gate_form': [i32],
     'case_set_gate_f16': [i32],
+    'case_set_copy_plan': [i32],
     'case_set_xattn_ctas': [i32],
     'case_set_xattn_next_prefetch': [i32],
     'case_cross_attn_part_next': [vp, i32],

@@ -151,10 +151,17 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
   const int b = r / a.W, V = a.V;
   const uint32_t hmask = (uint32_t)nslots - 1;
   const int hshift = 32 - (31 - __clz(nslots));            // nslots is a power of two
+  // plan mode (a.cp_n != NULL): the prefill sorted the valid source positions of the query by vocabulary id, so
+  // the touched ids are a ready list (ascending, unique) with their positions - no hash table, no atomics, the
+  // mass of a repeated id is summed in a fixed order, the logit gathers of neighbouring threads share lines.
+  // hkeys / hvals then hold (id, final value) of the list entries, nent of them.
+  const bool plan = a.cp_n != nullptr;
+  const int nent = plan ? a.cp_n[b] : nslots;
   int dbg_n = 0;
   auto stamp = [&]() { if (dbg != nullptr && blockIdx.x == 0 && tid == 0) dbg[dbg_n++] = clock64(); };
   stamp();
-  for (int i = tid; i < nslots; i += TS) { hkeys[i] = -1; hvals[i] = 0.f; }
+  if (!plan)
+    for (int i = tid; i < nslots; i += TS) { hkeys[i] = -1; hvals[i] = 0.f; }
   // weights of the mixture gate (the h part) are requested before the dependency wait
   float wmh[3] = {0.f, 0.f, 0.f}, bmv[3] = {0.f, 0.f, 0.f};
   if (a.do_finalize) {
@@ -291,7 +298,7 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
   // ---- copy mass of both memories into the hash table (double hashing, ids are exact).  The source positions of
   // both memories are one index space, so all loads of a thread (ids, scores, priors: <= 6 positions at S = 2620)
   // are in flight in ONE round
-  {
+  if (!plan) {
     const int S0n = a.S[0], S1n = a.nmem > 1 ? a.S[1] : 0, Stot = S0n + S1n;
     const float* at0 = a.attn_un[0] + (size_t)r * S0n;
     const float* at1 = a.nmem > 1 ? a.attn_un[1] + (size_t)r * S1n : nullptr;
@@ -347,6 +354,64 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
   const int K = a.K;
   // pass A: the final value of every touched id replaces its mass in the table; thread maximum
   float tmax = -INFINITY;
+  if (plan) {
+    const int S0n = a.S[0], S1n = a.S[1];
+    const float* at0 = a.attn_un[0] + (size_t)r * S0n;
+    const float* at1 = a.attn_un[1] + (size_t)r * S1n;
+    const float* pr0 = a.prior[0] ? a.prior[0] + (size_t)b * S0n : nullptr;
+    const float* pr1 = a.prior[1] ? a.prior[1] + (size_t)b * S1n : nullptr;
+    const size_t pb = (size_t)b * a.cp_ld;
+    auto copy_w = [&](int pos) -> float {                // gate_i * p_i[pos] of the reference (Model.py:41-42, 110-111)
+      const bool m1 = pos >= S0n;
+      const int sl = m1 ? pos - S0n : pos;
+      const float ev = (m1 ? at1 : at0)[sl];
+      const float* pr = m1 ? pr1 : pr0;
+      const float pv = pr ? __ldg(pr + sl) : 1.f;
+      return ev == -INFINITY ? 0.f : (m1 ? F[1] : F[0]) * pv * fexp(ev - (m1 ? M[1] : M[0]));
+    };
+    constexpr int PU = 4;                                  // list entries per thread per round
+    for (int u0 = tid; u0 < nent; u0 += PU * TS) {
+      int id[PU], fp[PU];
+      float lv[PU], ev[PU], pv[PU];
+#pragma unroll
+      for (int j = 0; j < PU; ++j) {
+        const int u = u0 + j * TS;
+        id[j] = u < nent ? __ldg(a.cp_uid + pb + u) : -1;
+        fp[j] = u < nent ? __ldg(a.cp_first + pb + u) : 0;      // first position | (occurrences - 1) << 16
+      }
+#pragma unroll
+      for (int j = 0; j < PU; ++j) {
+        lv[j] = 0.f; ev[j] = -INFINITY; pv[j] = 1.f;
+        if (id[j] >= 0) {
+          const int pos = fp[j] & 0xffff;
+          const bool m1 = pos >= S0n;
+          const int sl = m1 ? pos - S0n : pos;
+          const float* pr = m1 ? pr1 : pr0;
+          lv[j] = x[id[j]];
+          ev[j] = (m1 ? at1 : at0)[sl];
+          if (pr) pv[j] = __ldg(pr + sl);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < PU; ++j) {
+        if (id[j] < 0) continue;
+        const int u = u0 + j * TS, pos = fp[j] & 0xffff;
+        const bool m1 = pos >= S0n;
+        float mass = ev[j] == -INFINITY ? 0.f : (m1 ? F[1] : F[0]) * pv[j] * fexp(ev[j] - (m1 ? M[1] : M[0]));
+        const int extra = (int)((uint32_t)fp[j] >> 16);
+        if (extra > 0) {                                   // repeated id: the other occurrences, in position order
+          const int k0 = __ldg(a.cp_start + pb + u);
+          for (int k = 1; k <= extra; ++k) mass += copy_w(__ldg(a.cp_perm + pb + k0 + k));
+        }
+        const float e = (a.mask_col0 && id[j] == 0) ? 0.f : sp_exp(lv[j] - mm);
+        const float f = fmaf(scl, e, mass);
+        hkeys[u] = id[j];
+        hvals[u] = f;
+        tmax = fmaxf(tmax, f);
+      }
+    }
+    __syncthreads();                                       // the list is read by other threads below
+  } else
   for (int s0 = tid; s0 < nslots; s0 += 4 * TS) {        // nslots is a multiple of 4 * TS
     int id[4];
     float lv[4];
@@ -372,13 +437,22 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
     const float l = base_e[(size_t)r * SP_PARTS * k2 + tid];
     if ((unsigned)id < (unsigned)V && l > -INFINITY) {
       bool found = false;
-      uint32_t slot = sp_hash(id, hshift);
-      const uint32_t step = sp_step(id);
-      while (true) {
-        const int key = hkeys[slot];
-        if (key == id) { found = true; break; }
-        if (key == -1) break;
-        slot = (slot + step) & hmask;
+      if (plan) {                                          // the list is sorted: binary search
+        int lo = 0, hi = nent;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (hkeys[mid] < id) lo = mid + 1; else hi = mid;
+        }
+        found = lo < nent && hkeys[lo] == id;
+      } else {
+        uint32_t slot = sp_hash(id, hshift);
+        const uint32_t step = sp_step(id);
+        while (true) {
+          const int key = hkeys[slot];
+          if (key == id) { found = true; break; }
+          if (key == -1) break;
+          slot = (slot + step) & hmask;
+        }
       }
       if (!found) { fb = scl * sp_exp(l - mm); idb = id; }
     }
@@ -386,7 +460,7 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
   tmax = fmaxf(tmax, fb);
   const float T = block_kth_max(sc, K, tmax);
   if (tmax >= T && tmax > -INFINITY) {
-    for (int sl = tid; sl < nslots; sl += TS) {
+    for (int sl = tid; sl < nent; sl += TS) {
       const int id = hkeys[sl];
       if (id >= 0 && hvals[sl] >= T) topk_append(sc, hvals[sl], id);
     }
@@ -399,8 +473,8 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
   if (!block_select(sc, K, ov, oi)) {                    // massive ties: offer every candidate
     WarpTopK wl;
     wl.init();
-    for (int s0 = 0; s0 < nslots; s0 += TS) {
-      const int id = hkeys[s0 + tid];
+    for (int s0 = 0; s0 < nent; s0 += TS) {
+      const int id = s0 + tid < nent ? hkeys[s0 + tid] : -1;
       wl.offer(K, id >= 0 ? hvals[s0 + tid] : -INFINITY, id >= 0 ? id : 0x7fffffff);
     }
     wl.offer(K, fb, idb);
@@ -467,7 +541,12 @@ extern "C" int case_sparse_tail(const case_tail_args_t* a, const float* base_ms,
   CB_REQUIRE(total <= case_sparse_tail_max_sources(), "case_sparse_tail: too many source positions for the shared-memory table");
   int nslots = 4 * TS;
   while (nslots < 3 * total && nslots < 16384) nslots *= 2;  // load factor ~1/3 (<= 2/3 at the size limit)
-  const size_t smem = (size_t)nslots * 8;
+  const bool plan = a->cp_n != nullptr;
+  CB_REQUIRE(!plan || (a->nmem == 2 && a->cp_uid && a->cp_first && a->cp_start && a->cp_perm && a->cp_ld >= total && total < 65536),
+             "case_sparse_tail: the copy plan needs cp_uid / cp_first / cp_start / cp_perm with cp_ld >= S0 + S1 (two memories, < 65536 positions)");
+  // plan mode: (id, value) per list entry, at most one per source position; the hash layout otherwise
+  const size_t smem = plan ? (size_t)((total + 3) / 4 * 4) * 8 : (size_t)nslots * 8;
+  if (plan) nslots = (total + 3) / 4 * 4;
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr = false;
   if (!attr) {

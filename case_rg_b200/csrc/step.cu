@@ -18,6 +18,7 @@ int g_use_fused_select = 1;
 int g_use_post = 1;
 int g_use_gate = 1;
 int g_use_gate_h = 0;          // f16 / tensor-core form of the gate kernel when the step arguments carry U16 (measured slower: off)
+int g_use_plan = 1;            // sparse tail from the prefill's copy plan (sorted unique ids) instead of the hash table
 int g_xnext = 0;               // tiles per warp the passage cross-attention prefetches for the next layer's launch
 int g_prefetch_pct = 0;        // measured: no gain at C2 (the prefetch traffic slows the latency-bound launch more than it helps)
 int g_prefetch_mask = 3;       // bit 0: from the stack launch (layer 4), bit 1: from the chain launches (layers 5..7)
@@ -90,6 +91,11 @@ extern "C" int case_set_post_linears(int on) {
 extern "C" int case_set_gate_form(int on) {
   const int old = g_use_gate;
   if (on >= 0) g_use_gate = on ? 1 : 0;      // negative: query only
+  return old;
+}
+extern "C" int case_set_copy_plan(int on) {
+  const int old = g_use_plan;
+  if (on >= 0) g_use_plan = on ? 1 : 0;
   return old;
 }
 extern "C" int case_set_gate_f16(int on) {
@@ -363,6 +369,10 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
     }
     if (a->materialize_only) { ta.dist = a->dist; } else { ta.top_vals = a->top_vals; ta.top_idx = a->top_idx; }
     ta.gate_ctx = gate ? 1 : 0;
+    if (sparse && g_use_plan && a->cp_n != nullptr) {
+      ta.cp_n = a->cp_n; ta.cp_uid = a->cp_uid; ta.cp_first = a->cp_first; ta.cp_start = a->cp_start; ta.cp_perm = a->cp_perm;
+      ta.cp_ld = a->cp_ld;
+    }
     if (sparse) {
       const bool fuse_sel = a->qcount != nullptr && g_use_fused_select;
       case_select_args_t sel = select_args(a->mode, B, W, t, a->max_len, a->Tmax, a->BOS, a->EOS, a->UNK, a->PAD,

@@ -80,6 +80,10 @@ int case_set_gate_form(int on);
  * of every warp's range of the stream KVnext (the next layer's K|V: same B, S, counts), so that launch fills its
  * rings from L2 while HBM was idle anyway.  One-shot; ntiles <= 0 keeps the previous depth (default 3). */
 int case_cross_attn_part_next(const void* KVnext, int ntiles);
+/* Sparse tail from the copy plan, when the step arguments carry one (default on; the engine builds a plan only
+ * with CASE_COPY_PLAN=1: measured neutral at the BASELINE shape), instead of the shared-memory hash table;
+ * returns the old setting, a negative argument only queries. */
+int case_set_copy_plan(int on);
 /* f16 / tensor-core form of the gate kernel (case_additive_attn_gate_h) when the step arguments carry U16, W >= 2
  * and fast_tanh.  Default OFF: on sm_100a tanh.approx.f16x2 is two MUFU.TANH.F16 plus a PRMT, so the MUFU count
  * does not drop and the kernel measures 56 us against 47 us at the BASELINE shape (kept as an experiment; its
@@ -386,6 +390,12 @@ typedef struct {
   const int32_t* map; const float* prior[2]; const float* attn_un[2];
   float* top_vals; int32_t* top_idx; float* dist;
   int32_t gate_ctx;   /* case_sparse_tail only: ctxp[i] hold gate_part [R][ns][4] of case_additive_attn_gate (ctx[i] unused) */
+  /* case_sparse_tail only, optional copy plan of case_copy_plan (cp_n == NULL: hash table + atomics): per query
+   * the unique vocabulary ids of its VALID source positions (ascending), cp_first = first position | (occurrences
+   * - 1) << 16, cp_start = offset of the id's run in cp_perm, cp_perm = the valid positions sorted by (id, position);
+   * positions index the concatenation [memory 0 ; memory 1]; rows of cp_ld ints */
+  int32_t cp_ld;
+  const int32_t* cp_n; const int32_t* cp_uid; const int32_t* cp_first; const int32_t* cp_start; const int32_t* cp_perm;
 } case_tail_args_t;
 int case_row_tail(const case_tail_args_t* a, case_stream_t stream);
 int case_row_tail_max_vocab(void);
@@ -486,6 +496,9 @@ typedef struct {
   int32_t* qcount;                      /* [B] zeros (may be NULL): lets the sparse tail run the search bookkeeping */
   const void* Wqa_c[2]; const void* Wg_c;   /* attention-query / gen.0 weights as post linears of the cluster launches (may be NULL) */
   const int32_t* xns;                   /* [B] splits of the second memory's additive attention per query (may be NULL) */
+  /* copy plan of the batch for the sparse tail (may be NULL -> hash table): see case_tail_args_t */
+  const int32_t* cp_n; const int32_t* cp_uid; const int32_t* cp_first; const int32_t* cp_start; const int32_t* cp_perm;
+  int32_t cp_ld;
   const void* U16[2];                   /* [B][S_i][H] f16 copies of U (may be NULL): case_additive_attn_gate_h when W >= 2 and fast_tanh */
   const float* Gv[2];                   /* [B][S_i][4] fp32 gate-projected memories (may be NULL): the search path then runs
                                            case_additive_attn_gate and never reads Mv */

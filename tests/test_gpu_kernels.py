@@ -565,6 +565,46 @@ def test_sparse_tail_matches_dense_tail(R, W, V, S0, S1, K, finalize):
         wv = torch.gather(dense['dist'][:, :V].cpu(), 1, want)
         assert torch.allclose(wv[~same], ref_v[~same], rtol=1e-5, atol=0), (got_i, want)
     if finalize:
+        # plan mode: the prefill's sorted unique-id list instead of the hash table - same gates, same top-k
+        from case_rg_b200.engine import build_copy_plan
+        St = S0 + S1
+        valid = torch.ones(B, St, dtype=torch.bool, device=dev)
+        valid[:, S0::5] = False                              # exactly the positions whose scores are -inf above
+        valid[:, S0 + 7] = False                             # and one valid-score position the plan leaves out ...
+        cp = dict(n=torch.zeros(B, dtype=torch.int32, device=dev),
+                  **{k: torch.zeros(B, St + 1, dtype=torch.int32, device=dev) for k in ('uid', 'first', 'start', 'perm')})
+        attn_p = [attn[0], attn[1].clone()]
+        attn_p[1][:, 7] = float('-inf')                      # ... whose score the dense reference then must not see either
+        build_copy_plan(smap, valid, V, cp['n'], cp['uid'], cp['first'], cp['start'], cp['perm'])
+        ad, dense_p = args()
+        ad.attn_un[1] = attn_p[1].data_ptr()
+        ad.dist = dense_p['dist'].data_ptr()
+        L.check(lib.case_row_tail(C.byref(ad), st), 'case_row_tail')
+        ap, planned = args()
+        ap.attn_un[1] = attn_p[1].data_ptr()
+        ap.cp_n, ap.cp_uid, ap.cp_first = cp['n'].data_ptr(), cp['uid'].data_ptr(), cp['first'].data_ptr()
+        ap.cp_start, ap.cp_perm, ap.cp_ld = cp['start'].data_ptr(), cp['perm'].data_ptr(), St + 1
+        L.check(lib.case_sparse_tail(C.byref(ap), base_ms.data_ptr(), base_e.data_ptr(), base_i.data_ptr(), k2, None, None, st),
+                'case_sparse_tail(plan)')
+        torch.cuda.synchronize()
+        dp = dense_p['dist'][:, :V].double().cpu()
+        want_p = torch.argsort(torch.argsort(torch.argsort(-dp, dim=1, stable=True), dim=1), dim=1)[:, :K]
+        pi = planned['ti'].cpu().long()
+        rvp = torch.gather(dense_p['dist'][:, :V].cpu(), 1, pi)
+        assert torch.allclose(planned['tv'].cpu(), rvp, rtol=1e-5, atol=0), (planned['tv'], rvp)
+        smp = pi == want_p
+        if not bool(smp.all()):
+            wv = torch.gather(dense_p['dist'][:, :V].cpu(), 1, want_p)
+            assert torch.allclose(wv[~smp], rvp[~smp], rtol=1e-5, atol=0), (pi, want_p)
+        # a second launch gives bit-identical values: no atomics, fixed summation order
+        ap2, planned2 = args()
+        ap2.attn_un[1] = attn_p[1].data_ptr()
+        ap2.cp_n, ap2.cp_uid, ap2.cp_first = cp['n'].data_ptr(), cp['uid'].data_ptr(), cp['first'].data_ptr()
+        ap2.cp_start, ap2.cp_perm, ap2.cp_ld = cp['start'].data_ptr(), cp['perm'].data_ptr(), St + 1
+        L.check(lib.case_sparse_tail(C.byref(ap2), base_ms.data_ptr(), base_e.data_ptr(), base_i.data_ptr(), k2, None, None, st),
+                'case_sparse_tail(plan, again)')
+        torch.cuda.synchronize()
+        assert torch.equal(planned2['tv'], planned['tv']) and torch.equal(planned2['ti'], planned['ti'])
         # gate form: ctxp replaced by the gate partials sum exp(e-m) (W_m,i . mem) - the same gates, factors and top-k
         a3, gform = args()
         gp = [torch.einsum('rnh,kh->rnk', ctxp[i], Wm[:, H * (1 + i):H * (2 + i)]) for i in range(2)]
