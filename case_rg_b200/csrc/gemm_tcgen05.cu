@@ -217,6 +217,191 @@ __global__ __launch_bounds__(TC_THREADS, 1) void vocab_gemm_tc_kernel(const bf16
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ prefill projections
+// Once per batch and memory: the cross-attention K|V of all layers of a stack (TransformerDecoder.py:81 recomputes
+// them every step) and Uk.mem of the additive attention (BilinearAttention.py:34) are ONE GEMM over the memory rows,
+//   Y[key][n] = sum_k mem[key][k] * W[n][k] (+ bias[n]),   n = (layer, K|V, head, dim) ++ (Uk column)
+// whose epilogue writes the consumers' layouts directly: the swizzled bf16 K|V tiles of case_cross_attn_part /
+// case_layer_stack (valid keys first when cidx / ncount are given - the compaction happens on the LOAD side, the
+// A tiles are gathered) and U row-major at the keys' original positions.  No [B*S][2048] intermediate (687 MB at the
+// BASELINE shape) is written or re-read.
+//   CTA = PF_KEYS keys of one query (UMMA M = 128 tiles, TMEM lanes = keys) x a sequence of PF_N-column weight
+//   blocks.  The A tile(s) stay in shared memory; weight blocks (canonical layout, L2-resident) stream through two
+//   buffers; the accumulators are double buffered in TMEM: the MMAs of block j+1 run under the epilogue of block j.
+//   Measured at the BASELINE shape (B = 64, S = 2560 + 60, ~1750 valid keys per query): 0.31-0.33 ms for both
+//   memories against 0.20 (cuBLAS) + 0.28 (packing pass) before.  What bounds it (A/B with the MMAs and / or the
+//   epilogue switched off: 121 us with neither, 210 us MMAs only, 257 us epilogue only): every CTA re-streams all
+//   1.15 MB of weight blocks from L2 for its 128 keys, 148 of them together ask ~9 TB/s of L2 - the weight stream
+//   alone is the 121 us - and the SS-mode MMAs (128 B/clk of shared-memory operand reads at M = N = 128) share the
+//   shared-memory port with the landing copies.  256 keys x 64-column blocks (half the L2 stream) measured 380 us:
+//   N = 64 MMAs need 192 B/clk.  Next step: a 4-CTA cluster whose CTAs each fetch a quarter of a weight block and
+//   multicast it (quarter of the L2 stream), or the A tile in TMEM.
+constexpr int PF_M = 128, PF_TILES = 1, PF_N = 128;
+constexpr int PF_KEYS = PF_M * PF_TILES;             // keys per CTA
+constexpr int PF_A_BYTES = PF_M * TC_K * 2;          // 64 KB per A tile
+constexpr int PF_W_BYTES = PF_N * TC_K * 2;          // bytes per weight block
+constexpr int PF_CG = PF_N / 32;                     // 32-column groups (= heads) per block
+constexpr int PF_MAX_BIAS = 4 * 2 * TC_K;            // 4 layers x (K, V) x 256
+constexpr int PF_THREADS = 512;                      // 16 warps: one (tile, head) pair of a lane quarter each
+constexpr int PF_SMEM = PF_TILES * PF_A_BYTES + 2 * PF_W_BYTES + PF_MAX_BIAS * 4 + PF_KEYS * 4 + 128;
+static_assert(PF_TILES * PF_CG == 4, "the epilogue gives every warp one (tile, head) pair of its lane quarter");
+struct PfOut { bf16* p[4]; };
+
+__global__ __launch_bounds__(PF_THREADS, 1) void prefill_project_tc_kernel(
+    const bf16* __restrict__ mem, const bf16* __restrict__ Wp, const float* __restrict__ bias, int S,
+    const int32_t* __restrict__ cidx, const int32_t* __restrict__ ncount, int nl, PfOut out, bf16* __restrict__ U) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t s_a = smem_u32(smem), s_w = s_a + PF_TILES * PF_A_BYTES;
+  float* s_bias = reinterpret_cast<float*>(smem + PF_TILES * PF_A_BYTES + 2 * PF_W_BYTES);
+  int* s_src = reinterpret_cast<int*>(s_bias + PF_MAX_BIAS);
+  const uint32_t s_bar = smem_u32(s_src + PF_KEYS);        // [0,1] weights landed, [2,3] MMAs done
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_src + PF_KEYS) + 16;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mt = blockIdx.x, b = blockIdx.y;
+  const int ntile = (S + 63) / 64;
+  pdl_wait();
+  const int nv = ncount ? ncount[b] : S;
+  const int nkv = nl * 2 * TC_K / PF_N, nu = U ? TC_K / PF_N : 0;
+  const bool kv_live = mt * PF_KEYS < nv || mt == 0;      // tiles past the query's last one are never read
+  const int jb0 = kv_live ? 0 : nkv, nblk = nkv + nu - jb0;
+  if (nblk <= 0) return;
+  const int ntl = min(PF_TILES, (S - mt * PF_KEYS + PF_M - 1) / PF_M);   // A tiles wholly past the memory are skipped
+
+  if (tid == 0) {
+    tc_mbar_init(s_bar, 4); tc_mbar_init(s_bar + 8, 4);
+    tc_mbar_init(s_bar + 16, 1); tc_mbar_init(s_bar + 24, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid < PF_KEYS) {
+    const int sc = mt * PF_KEYS + tid;
+    s_src[tid] = sc < S ? (cidx ? cidx[(size_t)b * S + sc] : sc) : -1;
+  }
+  for (int i = tid; i < nl * 2 * TC_K; i += PF_THREADS) s_bias[i] = __ldg(bias + i);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  // weight block jj (local index) -> buffer jj & 1: four bulk copies issued from four warps
+  auto issue_w = [&](int jj) {
+    const uint32_t bar = s_bar + 8 * (jj & 1);
+    const char* src = reinterpret_cast<const char*>(Wp) + (size_t)(jb0 + jj) * PF_W_BYTES + (size_t)warp * (PF_W_BYTES / 4);
+    tc_expect_tx(bar, PF_W_BYTES / 4);
+    tc_bulk_g2s(s_w + (jj & 1) * PF_W_BYTES + warp * (PF_W_BYTES / 4), src, PF_W_BYTES / 4, bar);
+  };
+  if (lane == 0 && warp < 4) {
+    issue_w(0);
+    if (nblk > 1) issue_w(1);
+  }
+  // A tiles: 128 gathered memory rows each -> canonical layout.  lane = (k-chunk & 1, row & 15): 32-byte runs of a
+  // source row per 2 lanes, 2-way bank conflicts on the store side
+  for (int tl = 0; tl < ntl; ++tl) {
+    const int r16 = lane & 15, kc = warp * 2 + (lane >> 4);
+    uint4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {                        // warp: rows 16 i .. 16 i + 15, k-chunks 2*warp, 2*warp + 1
+      const int s = s_src[tl * PF_M + i * 16 + r16];
+      v[i] = make_uint4(0, 0, 0, 0);
+      if (s >= 0) v[i] = __ldg(reinterpret_cast<const uint4*>(mem + ((size_t)b * S + s) * TC_K + kc * 8));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<uint4*>(smem + tl * PF_A_BYTES + kc * (PF_M / 8) * 128 + (i * 16 + r16) * 16) = v[i];
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+  __syncthreads();
+
+  constexpr uint32_t idesc = umma_idesc(PF_M, PF_N);
+  auto issue_mma = [&](int jj) {
+    const int buf = jj & 1;
+    tc_wait(s_bar + 8 * buf, (jj >> 1) & 1);
+    tc_fence_after();
+    for (int tl = 0; tl < ntl; ++tl) {
+#pragma unroll
+      for (int ks = 0; ks < TC_K / 16; ++ks) {
+        const int kc = ks * 2;
+        const uint64_t ad = umma_desc(s_a + tl * PF_A_BYTES + kc * (PF_M / 8) * 128, (PF_M / 8) * 128, 128);
+        const uint64_t bd = umma_desc(s_w + buf * PF_W_BYTES + kc * (PF_N / 8) * 128, (PF_N / 8) * 128, 128);
+        umma_bf16(tmem + buf * (PF_TILES * PF_N) + tl * PF_N, ad, bd, idesc, ks != 0);
+      }
+    }
+    umma_commit(s_bar + 16 + 8 * buf);
+  };
+  if (tid == 0) issue_mma(0);
+
+  // epilogue roles: warp & 3 = TMEM lane quarter (32 keys), warp >> 2 = one of the quarter's four (tile, head) pairs.
+  // A thread drains the 32 columns of ITS key (tcgen05.ld: lane = key) = one head's K or V row = 64 contiguous bytes
+  // of the tile stream (a transposition through shared memory to 512-byte store runs measured no faster).
+  const int q = warp & 3, combo = warp >> 2, tl = combo / PF_CG, c0 = (combo % PF_CG) * 32;
+  const int km = tl * PF_M + q * 32 + lane, sc = mt * PF_KEYS + km;
+  const int tile = sc >> 6, key = sc & 63;
+  const int s_orig = s_src[km];
+  const bool kv_write = tile < ntile && (tile * 64 < nv || tile == 0);
+  const bool kv_valid = sc < nv;
+
+  for (int jj = 0; jj < nblk; ++jj) {
+    const int buf = jj & 1, j = jb0 + jj;
+    tc_wait(s_bar + 16 + 8 * buf, (jj >> 1) & 1);
+    tc_fence_after();
+    if (tid == 0 && jj + 1 < nblk) issue_mma(jj + 1);      // accumulators buf ^ 1 were drained in iteration jj - 1
+    if (lane == 0 && warp < 4 && jj + 2 < nblk) issue_w(jj + 2);   // MMAs of block jj are done: its buffer is free
+    __syncwarp();
+    if (tl < ntl) {
+      const int n0 = j * PF_N + c0;                         // first of the 32 output columns
+      uint32_t acc[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * (PF_TILES * PF_N) + tl * PF_N + c0, acc);
+      tmem_ld_wait();
+      uint4 o[4];
+      if (j < nkv) {
+        const float4* bp = reinterpret_cast<const float4*>(s_bias + n0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 b0 = bp[2 * c], b1 = bp[2 * c + 1];
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(acc[8 * c]) + b0.x, __uint_as_float(acc[8 * c + 1]) + b0.y);
+          __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(acc[8 * c + 2]) + b0.z, __uint_as_float(acc[8 * c + 3]) + b0.w);
+          __nv_bfloat162 p2 = __floats2bfloat162_rn(__uint_as_float(acc[8 * c + 4]) + b1.x, __uint_as_float(acc[8 * c + 5]) + b1.y);
+          __nv_bfloat162 p3 = __floats2bfloat162_rn(__uint_as_float(acc[8 * c + 6]) + b1.z, __uint_as_float(acc[8 * c + 7]) + b1.w);
+          o[c].x = *reinterpret_cast<uint32_t*>(&p0); o[c].y = *reinterpret_cast<uint32_t*>(&p1);
+          o[c].z = *reinterpret_cast<uint32_t*>(&p2); o[c].w = *reinterpret_cast<uint32_t*>(&p3);
+          if (!kv_valid) o[c] = make_uint4(0, 0, 0, 0);    // keys past the count are zero rows (pack_kv_gather_kernel)
+        }
+        if (kv_write) {
+          const int l = n0 / (2 * TC_K), kvj = (n0 / TC_K) & 1, hh = (n0 >> 5) & 7;
+          char* dst = reinterpret_cast<char*>(out.p[l]) + ((((size_t)(b * NH + hh) * ntile + tile) * 2 + kvj) * 64 + key) * 64;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + ((c ^ ((key >> 1) & 3)) << 4)) = o[c];
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(acc[8 * c]), __uint_as_float(acc[8 * c + 1]));
+          __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(acc[8 * c + 2]), __uint_as_float(acc[8 * c + 3]));
+          __nv_bfloat162 p2 = __floats2bfloat162_rn(__uint_as_float(acc[8 * c + 4]), __uint_as_float(acc[8 * c + 5]));
+          __nv_bfloat162 p3 = __floats2bfloat162_rn(__uint_as_float(acc[8 * c + 6]), __uint_as_float(acc[8 * c + 7]));
+          o[c].x = *reinterpret_cast<uint32_t*>(&p0); o[c].y = *reinterpret_cast<uint32_t*>(&p1);
+          o[c].z = *reinterpret_cast<uint32_t*>(&p2); o[c].w = *reinterpret_cast<uint32_t*>(&p3);
+        }
+        if (s_orig >= 0) {
+          uint4* dst = reinterpret_cast<uint4*>(U + ((size_t)b * S + s_orig) * TC_K + (n0 - nkv * PF_N));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) dst[c] = o[c];
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+  }
+}
+
 }  // namespace cb
 
 using namespace cb;
@@ -243,4 +428,26 @@ extern "C" int case_vocab_gemm_tc(const float* f, const void* Wp, const float* b
   launch_k(vocab_gemm_tc_kernel, (V + TC_M - 1) / TC_M, TC_THREADS, TC_SMEM, st, (const bf16*)Wp, (const bf16*)workspace, bias,
                                                                      logits, R, V, ldl);
   return check_launch("case_vocab_gemm_tc");
+}
+
+extern "C" int case_prefill_project_tc(const void* mem, const void* Wp, const float* bias, int B, int S, const int32_t* cidx,
+                                       const int32_t* ncount, int nl, void* const* out, void* U, case_stream_t stream) {
+  CB_REQUIRE(mem && Wp && bias && out && B > 0 && S > 0 && nl >= 1 && nl <= 4, "case_prefill_project_tc: bad arguments");
+  CB_REQUIRE(((uintptr_t)mem % 16 == 0) && ((uintptr_t)Wp % 16 == 0) && ((uintptr_t)U % 16 == 0),
+             "case_prefill_project_tc: 16-byte alignment required");
+  CB_REQUIRE((cidx == nullptr) == (ncount == nullptr), "case_prefill_project_tc: cidx and ncount go together");
+  CB_REQUIRE(B <= 65535, "case_prefill_project_tc: too many queries for one launch");
+  PfOut o;
+  for (int l = 0; l < 4; ++l) {
+    o.p[l] = l < nl ? (bf16*)out[l] : nullptr;
+    CB_REQUIRE(l >= nl || (out[l] && (uintptr_t)out[l] % 16 == 0), "case_prefill_project_tc: K|V outputs must be 16-byte aligned");
+  }
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(prefill_project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM);
+    attr = true;
+  }
+  launch_k(prefill_project_tc_kernel, dim3((S + PF_KEYS - 1) / PF_KEYS, B), PF_THREADS, PF_SMEM, (cudaStream_t)stream,
+           (const bf16*)mem, (const bf16*)Wp, bias, S, cidx, ncount, nl, o, (bf16*)U);
+  return check_launch("case_prefill_project_tc");
 }

@@ -141,14 +141,14 @@ def pack_post(w: torch.Tensor) -> torch.Tensor:
     return t.permute(0, 2, 1, 3, 4)[:, :, n[:, None], src].contiguous()  # [rank][chunk][n][p][8]: position p holds chunk p ^ (n & 7)
 
 
-def pack_vocab_tc(w: torch.Tensor) -> torch.Tensor:
-    """[V, 256] output-projection weight -> bf16 tiles of 128 rows in the UMMA K-major no-swizzle
-    canonical layout the tcgen05 kernel bulk-copies straight into shared memory (case_b200.h)."""
+def pack_vocab_tc(w: torch.Tensor, rows: int = 128) -> torch.Tensor:
+    """[V, 256] output-projection weight -> bf16 tiles of ``rows`` rows in the UMMA K-major no-swizzle
+    canonical layout the tcgen05 kernels bulk-copy straight into shared memory (case_b200.h)."""
     V, K = w.shape
-    VT = -(-V // 128)
-    wp = torch.zeros(VT * 128, K, dtype=torch.bfloat16, device=w.device)
+    VT = -(-V // rows)
+    wp = torch.zeros(VT * rows, K, dtype=torch.bfloat16, device=w.device)
     wp[:V] = w.to(torch.bfloat16)
-    return wp.view(VT, 16, 8, K // 8, 8).permute(0, 3, 1, 2, 4).contiguous()   # [tile][k/8][row/8][row%8][k%8]
+    return wp.view(VT, rows // 8, 8, K // 8, 8).permute(0, 3, 1, 2, 4).contiguous()   # [tile][k/8][row/8][row%8][k%8]
 
 
 _SWZ = {}
@@ -208,6 +208,7 @@ class CaseWeights:
         self.keep = []            # keeps every tensor alive
         self.layers = (L.LayerWeights * 8)()
         self.kv_w, self.kv_b = [], []                              # per stack: [H][Ln*2*H], [Ln*2*H]
+        self._kv_rows, self.pf_bias = [], []
         for i in range(2):
             kvw, kvb = [], []
             for l in range(4):
@@ -237,6 +238,8 @@ class CaseWeights:
                 kvw.append(Wx[H:].t())                            # [H][2H]: K cols then V cols
                 kvb.append(bx[H:])
             self.kv_w.append(torch.cat(kvw, dim=1).contiguous().to(self.tdtype))  # [H][Ln*2H]
+            self._kv_rows.append(torch.cat([k.t() for k in kvw], dim=0))             # [Ln*2H][H] fp32
+            self.pf_bias.append(torch.cat(kvb).float().contiguous())
             self.kv_b.append(torch.cat(kvb).contiguous().to(self.tdtype))
         self.E = g('embedding.0.weight').contiguous()
         self.pe = g('embedding.1.pe').contiguous()
@@ -248,6 +251,10 @@ class CaseWeights:
         self.Uk_t = [g(f'attns.{i}.linear_key.weight').t().contiguous().to(self.tdtype) for i in range(2)]   # [H][H]
         self.Wg_t, self.bg = mat(g('gen.0.weight')), vec(g('gen.0.bias'))
         bf = self.cdtype == L.BF16
+        # prefill GEMM of case_prefill_project_tc: rows (layer, K|V, head, dim) of the stack ++ the rows of Uk, 128-row blocks
+        self.Wpf = [pack_vocab_tc(torch.cat([self._kv_rows[i], g(f'attns.{i}.linear_key.weight')], 0)) if bf else None
+                    for i in range(2)]
+        del self._kv_rows
         self.Wqa_c = [pack_post(g(f'attns.{i}.linear_query.weight')) if bf else None for i in range(2)]
         self.Wg_c = pack_post(g('gen.0.weight')) if bf else None
         self.Wv = g('gen.2.weight').contiguous().to(self.tdtype)                               # [V][H]
@@ -383,6 +390,8 @@ class CaseDecodeEngine(_EngineBase):
         # scratch
         # second memory: only valid keys are packed (case_cross_attn_part); CASE_NO_COMPACT=1 keeps the masked form (A/B)
         self.compact = weights.cdtype == L.BF16 and os.environ.get('CASE_NO_COMPACT', '0') != '1'
+        # prefill projections on the own tcgen05 GEMM (K|V tiles + U written from its epilogue); CASE_PREFILL_TC=0: cuBLAS + pack (A/B)
+        self.prefill_tc = weights.cdtype == L.BF16 and os.environ.get('CASE_PREFILL_TC', '1') != '0'
         self.xslots = L.load().case_cross_attn_part_slots(S1) if self.compact else 0
         nsx = max(max(self.nsx), self.xslots)
         self.xcount = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -496,7 +505,9 @@ class CaseDecodeEngine(_EngineBase):
             if m.size(1) != S:
                 raise ValueError(f'memory {i} has {m.size(1)} positions, engine was built for {S}')
             flat = m.reshape(B * S, H).contiguous()
-            kv = torch.addmm(w.kv_b[i], flat, w.kv_w[i])                       # [B*S, 4*2*H]
+            fused = self.prefill_tc and w.cdtype == L.BF16      # own tcgen05 GEMM writes K|V tiles and U directly
+            kv = None if fused else torch.addmm(w.kv_b[i], flat, w.kv_w[i])    # [B*S, 4*2*H]
+            cidx = ncount = None
             if w.cdtype == L.BF16:        # one pass: GEMM rows -> swizzled bf16 K|V tiles of all 4 layers
                 outs = (C.c_void_p * 4)(*[self.Kx[i * 4 + l].data_ptr() for l in range(4)])
                 if i == 1 and self.compact:
@@ -512,9 +523,10 @@ class CaseDecodeEngine(_EngineBase):
                                self.xns.data_ptr(), stream)
                     # the additive attention visits valid keys only: padding scores are -inf once and for all
                     self.attn_un[i].masked_fill_(~valid.repeat_interleave(self.W, 0), float('-inf'))
-                    L.call('case_pack_kv_tiles_gather', kv.data_ptr(), kv.size(1), B, S, self.xidx.data_ptr(),
-                           self.xcount.data_ptr(), 4, outs, stream)
-                else:
+                    cidx, ncount = self.xidx.data_ptr(), self.xcount.data_ptr()
+                    if not fused:
+                        L.call('case_pack_kv_tiles_gather', kv.data_ptr(), kv.size(1), B, S, cidx, ncount, 4, outs, stream)
+                elif not fused:
                     L.call('case_pack_kv_tiles', kv.data_ptr(), L.BF16, kv.size(1), B, S, 4, outs, stream)
             else:
                 kv = kv.view(B, S, 4, 2, L.NH, L.HD).permute(2, 3, 0, 4, 1, 5)     # [l][k/v][B][NH][S][HD]
@@ -524,9 +536,12 @@ class CaseDecodeEngine(_EngineBase):
             lib = L.load()
             lazy = self.Gv is not None and bool(lib.case_set_gate_form(-1))      # the search path reads G (and U16) only
             use16 = lazy and self.U16 is not None and bool(lib.case_set_gate_f16(-1))
+            if fused:       # K|V tiles of the 4 layers (+ U unless the f16 experiment wants its own copy) in one launch
+                L.call('case_prefill_project_tc', flat.data_ptr(), w.Wpf[i].data_ptr(), w.pf_bias[i].data_ptr(), B, S,
+                       cidx, ncount, 4, outs, None if use16 else self.U[i].data_ptr(), stream)
             if use16:
                 torch.mm(mems[i].to(dev, torch.float16).reshape(B * S, H), w.Uk_t16[i], out=self.U16[i].view(B * S, H))
-            else:
+            elif not fused:
                 torch.mm(flat, w.Uk_t[i], out=self.U[i].view(B * S, H))
             if not lazy:
                 self.Mv[i].copy_(m)

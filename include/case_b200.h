@@ -196,6 +196,20 @@ int case_cross_attn_partial_tc(const float* q2, const void* KV, const uint8_t* m
 int case_cross_attn_part(const float* q2, const void* KV, const int32_t* ncount, const int32_t* tile_prefix, int B,
                          int W, int S, int nslot, float* part_ml, float* part_acc, case_stream_t stream);
 int case_cross_attn_part_slots(int S);
+/* Prefill projections of one memory as ONE tcgen05 GEMM whose epilogue writes the consumers' layouts (replaces
+ * projected-rows GEMM + case_pack_kv_tiles[_gather] + the Uk.mem GEMM; TransformerDecoder.py:81 and
+ * BilinearAttention.py:34 recompute both at every step):
+ *   out[l] (l < nl): the K|V tile stream of layer l, layout of case_cross_attn_partial_tc; with cidx / ncount (both
+ *     or neither) tile (b, j) holds the keys cidx[b][64 j ..] and keys >= ncount[b] are zero, tiles past a query's
+ *     last one are not written (as case_pack_kv_tiles_gather);
+ *   U (may be NULL): bf16 [B][S][H] = mem . Uk^T at the ORIGINAL positions of all S keys.
+ * mem: bf16 [B][S][H].  Wp: nl*4 (+2 with U) weight blocks of 128 output rows in the canonical layout of
+ * case_vocab_gemm_tc (64 KB each): rows (layer, K|V, head, dim) = multihead_attn.in_proj_weight[H:] of the nl
+ * layers, then the H rows of linear_key.weight.  bias: fp32 [nl*2*H] (in_proj_bias[H:]).  cidx must list ALL S
+ * positions of a query (valid ones first).  CTA = 128 keys of one query x all column blocks; accumulators double
+ * buffered in TMEM. */
+int case_prefill_project_tc(const void* mem, const void* Wp, const float* bias, int B, int S, const int32_t* cidx,
+                            const int32_t* ncount, int nl, void* const* out, void* U, case_stream_t stream);
 /* kv as in case_pack_kv_tiles (bf16 rows); cidx: int32 [B][S], cidx[b][j] = original position of the j-th
  * valid key of query b (ascending); key slots >= ncount[b] are zero. */
 int case_pack_kv_tiles_gather(const void* kv, int ldkv, int B, int S, const int32_t* cidx, const int32_t* ncount,

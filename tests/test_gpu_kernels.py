@@ -624,3 +624,56 @@ def test_sparse_tail_matches_dense_tail(R, W, V, S0, S1, K, finalize):
         if not bool(sm.all()):
             wv = torch.gather(dense['dist'][:, :V].cpu(), 1, want)
             assert torch.allclose(wv[~sm], rv[~sm], rtol=2e-4, atol=0), (gi, want)
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize('B,S,compact,with_u,nl', [(3, 60, False, True, 4), (5, 700, True, True, 4), (4, 2560, True, True, 4),
+                                                   (2, 130, True, False, 2), (2, 257, False, True, 1)])
+def test_prefill_project_tcgen05_vs_gemm_and_pack(B, S, compact, with_u, nl):
+    """case_prefill_project_tc (one tcgen05 GEMM, K|V tiles and U written from the epilogue, padding keys dropped on the
+    load side) against the projected-rows GEMM + case_pack_kv_tiles[_gather] + the Uk.mem GEMM it replaces."""
+    import ctypes as C
+    from case_rg_b200 import _lib as L
+    from case_rg_b200.engine import pack_vocab_tc
+    g = torch.Generator().manual_seed(B * 1000 + S)
+    H, NH = 256, 8
+    mem = torch.randn(B, S, H, generator=g).to(DEV).bfloat16()
+    Wkv = (torch.randn(nl * 2 * H, H, generator=g) / 16).to(DEV)
+    Wu = (torch.randn(H, H, generator=g) / 16).to(DEV)
+    bias = torch.randn(nl * 2 * H, generator=g).to(DEV)
+    valid = (torch.rand(B, S, generator=g) < 0.7).to(DEV)
+    valid[0] = False                                        # a query without any valid key
+    if B > 1:
+        valid[1] = True
+    lib = L.load()
+    st = torch.cuda.current_stream().cuda_stream
+    ntile = -(-S // 64)
+    mk = lambda: [torch.full((B, NH, ntile, 2, 64, 32), 7.0, dtype=torch.bfloat16, device=DEV) for _ in range(nl)]
+    ref, got = mk(), mk()
+    kv = (mem.float().reshape(B * S, H) @ Wkv.bfloat16().float().t() + bias).bfloat16().contiguous()
+    cidx = ncount = None
+    if compact:
+        xidx = torch.argsort(~valid, dim=1, stable=True).to(torch.int32).contiguous()
+        xcount = valid.sum(1).to(torch.int32).contiguous()
+        cidx, ncount = xidx.data_ptr(), xcount.data_ptr()
+        outs = (C.c_void_p * 4)(*[t.data_ptr() for t in ref], *[None] * (4 - nl))
+        L.call('case_pack_kv_tiles_gather', kv.data_ptr(), kv.size(1), B, S, cidx, ncount, nl, outs, st)
+    else:
+        outs = (C.c_void_p * 4)(*[t.data_ptr() for t in ref], *[None] * (4 - nl))
+        L.call('case_pack_kv_tiles', kv.data_ptr(), L.BF16, kv.size(1), B, S, nl, outs, st)
+    U = torch.full((B, S, H), float('nan'), dtype=torch.bfloat16, device=DEV)
+    Wp = pack_vocab_tc(torch.cat([Wkv, Wu], 0) if with_u else Wkv)
+    outs2 = (C.c_void_p * 4)(*[t.data_ptr() for t in got], *[None] * (4 - nl))
+    L.call('case_prefill_project_tc', mem.data_ptr(), Wp.data_ptr(), bias.data_ptr(), B, S, cidx, ncount, nl, outs2,
+           U.data_ptr() if with_u else None, st)
+    torch.cuda.synchronize()
+    for l in range(nl):
+        a, b = got[l].float(), ref[l].float()
+        assert torch.isfinite(a).all()
+        assert torch.equal(a == 0, b == 0) or float(((a == 0) != (b == 0)).float().mean()) < 1e-5   # the same zero rows
+        assert torch.allclose(a, b, rtol=1e-2, atol=1e-2), (l, float((a - b).abs().max()))
+        assert float((a != b).float().mean()) < 0.02, float((a != b).float().mean())       # 1-ulp roundings only
+    if with_u:
+        want = (mem.float().reshape(B * S, H) @ Wu.bfloat16().float().t()).view(B, S, H)
+        assert torch.isfinite(U.float()).all()                                            # every position written
+        assert torch.allclose(U.float(), want, rtol=1e-2, atol=1e-2), float((U.float() - want).abs().max())
