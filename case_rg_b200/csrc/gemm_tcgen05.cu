@@ -243,7 +243,8 @@ constexpr int PF_A_BYTES = PF_M * TC_K * 2;          // 64 KB per A tile
 constexpr int PF_W_BYTES = PF_N * TC_K * 2;          // bytes per weight block
 constexpr int PF_CG = PF_N / 32;                     // 32-column groups (= heads) per block
 constexpr int PF_MAX_BIAS = 4 * 2 * TC_K;            // 4 layers x (K, V) x 256
-constexpr int PF_THREADS = 512;                      // 16 warps: one (tile, head) pair of a lane quarter each
+constexpr int PF_EPI_WARPS = 16;                     // epilogue warps: one (tile, head) pair of a lane quarter each
+constexpr int PF_THREADS = (PF_EPI_WARPS + 1) * 32;  // + warp 16: its lane 0 issues the MMAs and nothing else
 constexpr int PF_SMEM = PF_TILES * PF_A_BYTES + 2 * PF_W_BYTES + PF_MAX_BIAS * 4 + PF_KEYS * 4 + 128;
 static_assert(PF_TILES * PF_CG == 4, "the epilogue gives every warp one (tile, head) pair of its lane quarter");
 struct PfOut { bf16* p[4]; };
@@ -269,8 +270,9 @@ __global__ __launch_bounds__(PF_THREADS, 1) void prefill_project_tc_kernel(
   const int ntl = min(PF_TILES, (S - mt * PF_KEYS + PF_M - 1) / PF_M);   // A tiles wholly past the memory are skipped
 
   if (tid == 0) {
-    tc_mbar_init(s_bar, 4); tc_mbar_init(s_bar + 8, 4);
-    tc_mbar_init(s_bar + 16, 1); tc_mbar_init(s_bar + 24, 1);
+    tc_mbar_init(s_bar, 4); tc_mbar_init(s_bar + 8, 4);              // weights landed
+    tc_mbar_init(s_bar + 16, 1); tc_mbar_init(s_bar + 24, 1);        // MMAs done (tcgen05.commit)
+    tc_mbar_init(s_bar + 32, PF_EPI_WARPS); tc_mbar_init(s_bar + 40, PF_EPI_WARPS);   // accumulator drained
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -300,7 +302,7 @@ __global__ __launch_bounds__(PF_THREADS, 1) void prefill_project_tc_kernel(
   }
   // A tiles: 128 gathered memory rows each -> canonical layout.  lane = (k-chunk & 1, row & 15): 32-byte runs of a
   // source row per 2 lanes, 2-way bank conflicts on the store side
-  for (int tl = 0; tl < ntl; ++tl) {
+  for (int tl = 0; tl < (warp < PF_EPI_WARPS ? ntl : 0); ++tl) {
     const int r16 = lane & 15, kc = warp * 2 + (lane >> 4);
     uint4 v[8];
 #pragma unroll
@@ -332,8 +334,17 @@ __global__ __launch_bounds__(PF_THREADS, 1) void prefill_project_tc_kernel(
     }
     umma_commit(s_bar + 16 + 8 * buf);
   };
-  if (tid == 0) issue_mma(0);
-
+  // warp 16: the MMA issuer.  tcgen05.mma issue blocks its thread for most of the MMAs' duration, so an issuer that
+  // is also an epilogue warp serialises weights -> MMAs -> epilogue (measured: 2.1 us per block = the sum of the
+  // three); a dedicated warp runs ahead, bounded only by landed weights and drained accumulators.
+  if (warp == PF_EPI_WARPS) {
+    if (lane == 0) {
+      for (int jj = 0; jj < nblk; ++jj) {
+        if (jj >= 2) tc_wait(s_bar + 32 + 8 * (jj & 1), ((jj >> 1) + 1) & 1);    // epilogue of block jj - 2 done
+        issue_mma(jj);
+      }
+    }
+  } else {
   // epilogue roles: warp & 3 = TMEM lane quarter (32 keys), warp >> 2 = one of the quarter's four (tile, head) pairs.
   // A thread drains the 32 columns of ITS key (tcgen05.ld: lane = key) = one head's K or V row = 64 contiguous bytes
   // of the tile stream (a transposition through shared memory to 512-byte store runs measured no faster).
@@ -348,7 +359,6 @@ __global__ __launch_bounds__(PF_THREADS, 1) void prefill_project_tc_kernel(
     const int buf = jj & 1, j = jb0 + jj;
     tc_wait(s_bar + 16 + 8 * buf, (jj >> 1) & 1);
     tc_fence_after();
-    if (tid == 0 && jj + 1 < nblk) issue_mma(jj + 1);      // accumulators buf ^ 1 were drained in iteration jj - 1
     if (lane == 0 && warp < 4 && jj + 2 < nblk) issue_w(jj + 2);   // MMAs of block jj are done: its buffer is free
     __syncwarp();
     if (tl < ntl) {
@@ -394,9 +404,13 @@ __global__ __launch_bounds__(PF_THREADS, 1) void prefill_project_tc_kernel(
       }
     }
     tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_bar + 32 + 8 * buf) : "memory");
   }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
   }
