@@ -45,6 +45,7 @@ def parse():
     ap.add_argument('--no-post', action='store_true', help='row_linear launches instead of post linears (A/B)')
     ap.add_argument('--no-stack', action='store_true', help='no fused first stack (A/B)')
     ap.add_argument('--no-gate', action='store_true', help='context form of the additive attentions (A/B)')
+    ap.add_argument('--no-evict-first', action='store_true', help='no L2 evict-first policy on the K|V / Uk.mem streams (A/B)')
     ap.add_argument('--gate-f16', action='store_true', help='f16 / tensor-core form of the gate kernel (A/B; slower)')
     ap.add_argument('--xattn-ctas', type=int, default=None, help='grid of the passage cross-attention (default: one CTA per SM)')
     ap.add_argument('--xattn-next', type=int, default=None, help='tiles per warp the passage cross-attention prefetches into L2 for the next layer (A/B)')
@@ -208,6 +209,8 @@ def main():
         L.load().case_set_stack_fusion(0)
     if args.no_gate:
         L.load().case_set_gate_form(0)
+    if args.no_evict_first:
+        L.load().case_set_stream_evict_first(0)
     if args.gate_f16:
         L.load().case_set_gate_f16(1)
     if args.xattn_ctas is not None:

@@ -31,6 +31,9 @@ constexpr int A2ULD = H + 8;  // padded bf16 row of the U tile
 __device__ __forceinline__ void a2_cp16(uint32_t dst, const void* src, int nbytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
 }
+__device__ __forceinline__ void a2_cp16_hint(uint32_t dst, const void* src, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void a2_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void a2_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -534,7 +537,8 @@ __global__ __launch_bounds__(A2T, WMAX <= 4 ? 3 : 2) void additive_attn_gate_ker
     const float* __restrict__ vvec, const uint8_t* __restrict__ mask, const float* __restrict__ prior,
     const int32_t* __restrict__ tok, int tok_ld, int t, int W, int S, int nsplit, float* __restrict__ scores,
     float* __restrict__ stats, float* __restrict__ gate_part, const int32_t* __restrict__ cidx,
-    const int32_t* __restrict__ ncount, const int32_t* __restrict__ qorder, const int32_t* __restrict__ nsq) {
+    const int32_t* __restrict__ ncount, const int32_t* __restrict__ qorder, const int32_t* __restrict__ nsq, int evict) {
+  const uint64_t pol = l2_stream_policy(evict);
   constexpr int KPT = WMAX == 8 ? 2 : 4;               // keys per warp per tile
   constexpr int NV = KPT * WMAX;                       // partial sums per warp per tile (4, 8, 16)
   constexpr int LW = WMAX == 1 ? 0 : (WMAX == 2 ? 1 : (WMAX == 4 ? 2 : 3));
@@ -591,7 +595,7 @@ __global__ __launch_bounds__(A2T, WMAX <= 4 ? 3 : 2) void additive_attn_gate_ker
 #pragma unroll
     for (int k = 0; k < KPT; ++k) {
       const int s = __shfl_sync(0xffffffffu, pos_lane, k);
-      if ((vbits >> k) & 1u) a2_cp16(wbuf_s + stage * WSTAGE + k * ROWB + lane * 16, Ub + (size_t)s * H + lane * 8, 16);
+      if ((vbits >> k) & 1u) a2_cp16_hint(wbuf_s + stage * WSTAGE + k * ROWB + lane * 16, Ub + (size_t)s * H + lane * 8, pol);
     }
   };
 
@@ -1066,7 +1070,7 @@ static int launch_gate(int fast, const float* qa, const void* U, const float* G,
       attr = true;                                                                                                        \
     }                                                                                                                     \
     launch_k(additive_attn_gate_kernel<WMAX, FAST_, FULL_>, dim3(B, nsplit), A2T, smem, st, qa, (const bf16*)U,            \
-             (const float4*)G, v, mask, prior, tok, tok_ld, t, W, S, nsplit, scores, stats, gate_part, cidx, ncount, qorder, nsq); \
+             (const float4*)G, v, mask, prior, tok, tok_ld, t, W, S, nsplit, scores, stats, gate_part, cidx, ncount, qorder, nsq, g_evict_first); \
   } while (0)
   if (fast) { if (full) AG_LAUNCH(true, true); else AG_LAUNCH(true, false); }
   else { if (full) AG_LAUNCH(false, true); else AG_LAUNCH(false, false); }

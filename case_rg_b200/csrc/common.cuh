@@ -17,6 +17,7 @@ constexpr float LN_EPS = 1e-5f;
 void set_error(const char* msg);
 int check_launch(const char* what);
 extern int g_use_pdl;          // programmatic dependent launch on every kernel of the step (step.cu)
+extern int g_evict_first;      // the once-per-step K|V / Uk.mem streams are loaded with an L2 evict-first policy (step.cu)
 extern cudaError_t g_launch_err;
 
 // Launch helper: same as kernel<<<grid, block, smem, stream>>>(args...) plus the programmatic
@@ -118,6 +119,15 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 #else
 __device__ __forceinline__ void pdl_trigger() {}
 #endif
+// L2 cache policy of a stream that is read once per step and is larger than L2 (cross-attention K|V, Uk.mem): with
+// evict-first its lines do not push out what the step re-reads (layer weights, the vocabulary weight, the logits tile,
+// the self-attention history)
+__device__ __forceinline__ uint64_t l2_stream_policy(int evict_first) {
+  uint64_t pol;
+  if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- reductions

@@ -18,6 +18,7 @@ int g_use_fused_select = 1;
 int g_use_post = 1;
 int g_use_gate = 1;
 int g_use_gate_h = 0;          // f16 / tensor-core form of the gate kernel when the step arguments carry U16 (measured slower: off)
+int g_evict_first = 1;         // L2 evict-first policy on the once-per-step K|V and Uk.mem streams
 int g_use_plan = 1;            // sparse tail from the prefill's copy plan (sorted unique ids) instead of the hash table
 int g_xnext = 0;               // tiles per warp the passage cross-attention prefetches for the next layer's launch
 int g_prefetch_pct = 0;        // measured: no gain at C2 (the prefetch traffic slows the latency-bound launch more than it helps)
@@ -91,6 +92,11 @@ extern "C" int case_set_post_linears(int on) {
 extern "C" int case_set_gate_form(int on) {
   const int old = g_use_gate;
   if (on >= 0) g_use_gate = on ? 1 : 0;      // negative: query only
+  return old;
+}
+extern "C" int case_set_stream_evict_first(int on) {
+  const int old = g_evict_first;
+  if (on >= 0) g_evict_first = on ? 1 : 0;   // negative: query only
   return old;
 }
 extern "C" int case_set_copy_plan(int on) {

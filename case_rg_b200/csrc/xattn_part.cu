@@ -43,9 +43,9 @@ __device__ __forceinline__ void xp_ldsm4_t(uint32_t (&r)[4], uint32_t addr) {
 __device__ __forceinline__ void xp_expect(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void xp_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
+__device__ __forceinline__ void xp_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "l"(pol)
                : "memory");
 }
 __device__ __forceinline__ bool xp_try_wait(uint32_t bar, uint32_t parity) {
@@ -95,7 +95,8 @@ __device__ __forceinline__ void xp_advance(XpPos& p, const int* tp, int B) {   /
 __global__ __launch_bounds__(XP_WARPS * 32) void cross_attn_part_kernel(
     const float* __restrict__ q2, const bf16* __restrict__ KV, const int32_t* __restrict__ ncount,
     const int32_t* __restrict__ tile_prefix, int B, int W, int ntile_all, int nslot, float* __restrict__ part_ml,
-    float* __restrict__ part_acc, const bf16* __restrict__ KVnext, int npf) {
+    float* __restrict__ part_acc, const bf16* __restrict__ KVnext, int npf, int evict) {
+  const uint64_t pol = l2_stream_policy(evict);
   extern __shared__ __align__(128) unsigned char xp_smem[];   // [warp][XP_NS stages of K|V][barriers], then tp[B+1]
   int* tp = reinterpret_cast<int*>(xp_smem + (size_t)XP_WARPS * XP_WARP_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g4 = lane >> 2, t4 = lane & 3;
@@ -136,7 +137,7 @@ __global__ __launch_bounds__(XP_WARPS * 32) void cross_attn_part_kernel(
     if (lane == 0) {
       for (; loaded < XP_NS && loaded < my_tiles; ++loaded) {
         xp_expect(bars + 8 * loaded, XP_STAGE);
-        xp_bulk(sbase + loaded * XP_STAGE, tile_src(lp), XP_STAGE, bars + 8 * loaded);
+        xp_bulk(sbase + loaded * XP_STAGE, tile_src(lp), XP_STAGE, bars + 8 * loaded, pol);
         xp_advance(lp, tp, B);
       }
     }
@@ -226,7 +227,7 @@ __global__ __launch_bounds__(XP_WARPS * 32) void cross_attn_part_kernel(
       __syncwarp();                              // every lane is done with this stage
       if (lane == 0 && loaded < my_tiles) {      // refill it with the tile XP_NS ahead (possibly of the next segment)
         xp_expect(bars + 8 * stage, XP_STAGE);
-        xp_bulk(sbase + stage * XP_STAGE, tile_src(lp), XP_STAGE, bars + 8 * stage);
+        xp_bulk(sbase + stage * XP_STAGE, tile_src(lp), XP_STAGE, bars + 8 * stage, pol);
         xp_advance(lp, tp, B);
       }
       if (loaded < my_tiles) ++loaded;
@@ -347,7 +348,7 @@ extern "C" int case_cross_attn_part(const float* q2, const void* KV, const int32
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = g_xp_ctas > 0 && g_xp_ctas < nsm ? g_xp_ctas : nsm;
   launch_k(cross_attn_part_kernel, grid, XP_WARPS * 32, smem, st, q2, (const bf16*)KV, ncount, tile_prefix, B, W,
-           (S + 63) / 64, nslot, part_ml, part_acc, (const bf16*)g_xp_next, g_xp_npf);
+           (S + 63) / 64, nslot, part_ml, part_acc, (const bf16*)g_xp_next, g_xp_npf, g_evict_first);
   g_xp_next = nullptr;
   return check_launch("case_cross_attn_part");
 }

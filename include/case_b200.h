@@ -80,6 +80,10 @@ int case_set_gate_form(int on);
  * of every warp's range of the stream KVnext (the next layer's K|V: same B, S, counts), so that launch fills its
  * rings from L2 while HBM was idle anyway.  One-shot; ntiles <= 0 keeps the previous depth (default 3). */
 int case_cross_attn_part_next(const void* KVnext, int ntiles);
+/* L2 evict-first policy on the streams a step reads once and that exceed L2 (cross-attention K|V of case_cross_attn_part,
+ * Uk.mem of case_additive_attn_gate), so they do not push the layer weights, the vocabulary weight and the logits tile
+ * out of L2 between steps (default on); returns the old setting, a negative argument only queries. */
+int case_set_stream_evict_first(int on);
 /* Sparse tail from the copy plan, when the step arguments carry one (default on; the engine builds a plan only
  * with CASE_COPY_PLAN=1: measured neutral at the BASELINE shape), instead of the shared-memory hash table;
  * returns the old setting, a negative argument only queries. */
