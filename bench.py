@@ -45,6 +45,7 @@ def parse():
     ap.add_argument('--no-post', action='store_true', help='row_linear launches instead of post linears (A/B)')
     ap.add_argument('--no-stack', action='store_true', help='no fused first stack (A/B)')
     ap.add_argument('--no-gate', action='store_true', help='context form of the additive attentions (A/B)')
+    ap.add_argument('--next-prefetch', type=int, default=None, help='L2 warm-up mask for the next step (A/B; 0 off, 1 weights + query K|V, 3 + history)')
     ap.add_argument('--no-evict-first', action='store_true', help='no L2 evict-first policy on the K|V / Uk.mem streams (A/B)')
     ap.add_argument('--gate-f16', action='store_true', help='f16 / tensor-core form of the gate kernel (A/B; slower)')
     ap.add_argument('--xattn-ctas', type=int, default=None, help='grid of the passage cross-attention (default: one CTA per SM)')
@@ -209,6 +210,8 @@ def main():
         L.load().case_set_stack_fusion(0)
     if args.no_gate:
         L.load().case_set_gate_form(0)
+    if args.next_prefetch is not None:
+        L.load().case_set_next_step_prefetch(args.next_prefetch)
     if args.no_evict_first:
         L.load().case_set_stream_evict_first(0)
     if args.gate_f16:

@@ -142,6 +142,7 @@ _PROTOS = {
     'case_set_gate_form': [i32],
     'case_set_gate_f16': [i32],
     'case_set_copy_plan': [i32],
+    'case_set_next_step_prefetch': [i32],
     'case_set_stream_evict_first': [i32],
     'case_prefill_project_tc': [vp, vp, vp, i32, i32, vp, vp, i32, vp, vp, vp],
     'case_set_xattn_ctas': [i32],

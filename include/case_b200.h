@@ -84,6 +84,11 @@ int case_cross_attn_part_next(const void* KVnext, int ntiles);
  * Uk.mem of case_additive_attn_gate), so they do not push the layer weights, the vocabulary weight and the logits tile
  * out of L2 between steps (default on); returns the old setting, a negative argument only queries. */
 int case_set_stream_evict_first(int on);
+/* L2 warm-up for the next step's fused-stack launch, issued on the side stream behind the passage additive attention
+ * (bit 0: layer weights + query-memory K|V tiles of layers 0..3, bit 1: their self-attention history).  Experiment,
+ * default 0: measured slower at the BASELINE shape;
+ * returns the old mask, a negative argument only queries. */
+int case_set_next_step_prefetch(int mask);
 /* Sparse tail from the copy plan, when the step arguments carry one (default on; the engine builds a plan only
  * with CASE_COPY_PLAN=1: measured neutral at the BASELINE shape), instead of the shared-memory hash table;
  * returns the old setting, a negative argument only queries. */
