@@ -8,9 +8,10 @@ Differences, all in test mode only (training stays on the reference module):
     CaSE/CaSEDataset.py:98-104,140).  The dense one-hot of ``build_map`` (Utils.py:344-355) is still
     accepted and converted back, but at BASELINE sizes it does not fit (20 GB at B=64, S=2620), so
     ``install_fast_decoder`` also stops ``CaSE.forward`` from building it.
-  * the first three returned tensors cover the last decoded position only ([B,1,.]); the reference
-    returns all T positions of its last step, and its only test-mode consumer reads element [3]
-    (CaSE/Model.py:331).
+  * the reference returns all T positions of its last step in elements [0..2]; its only test-mode consumer
+    reads element [3] (CaSE/Model.py:331).  Here [0] covers the last decoded position only ([B,1,H]), [1] is None
+    and [2] is None unless ``return_distribution`` is set (greedy only): the search path takes the top-k from the
+    mixture's parts and never builds the [R,V] tensor, so asking for it costs one extra step.
   * ``beam_width`` (default 1 = the reference's in-module greedy loop) selects Generations.beam
     semantics on the device.
 """
@@ -82,6 +83,7 @@ class FastCaSEDecoder(nn.Module):
                                  nn.Softmax(dim=-1))
         self.mix = nn.Linear(3 * H, num_memories + 1)
         self.beam_width, self.dtype, self.vocab_impl, self.use_graph = beam_width, dtype, vocab_impl, use_graph
+        self.return_distribution = False      # True: forward()[2] is the last step's extended distribution (one extra step)
         self._weights = None
         self._engines: Dict[tuple, CaseDecodeEngine] = {}
 
@@ -152,19 +154,83 @@ class FastCaSEDecoder(nn.Module):
         tokens = eng.decode(int(max_target_length), mode, use_graph=self.use_graph)
         sel = slice(0, None, W)
         dec_outputs = eng.hN[sel].unsqueeze(1)
-        ext = eng.dist[sel, :self.tgt_vocab_size].unsqueeze(1)
+        ext = None                  # the search path never builds the [R,V] mixture (top-k is taken from its parts)
+        if self.return_distribution and W == 1:
+            # on request: the last step again, up to the finished distribution (idempotent for the in-module greedy loop)
+            ext = eng.step_distribution(int(max_target_length) - 1)[:, :self.tgt_vocab_size].unsqueeze(1).clone()
         return dec_outputs, None, ext, tokens
 
 
+def masque_to_case_state(msd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """State dict of ``MasqueTransformerSeqDecoder`` (Masque/Model.py:13-36) -> the CaSE decoder layout the engine packs.
+
+    Masque's decoder is CaSE's without the additional decoder feature: one ``norm`` (= CaSE ``norm1``), attention
+    queries from the H-wide decoder state only (``linear_query`` [H,H], Masque/Model.py:31 against CaSE/Model.py:32),
+    ``gen`` = Linear(2H,H) -> Linear(H,V) (keys gen.0 / gen.1, no Dropout module in between).  The feature columns of
+    CaSE's ``linear_query`` [H,2H] and ``gen.0`` [H,3H] are filled with exact zeros and the engine is fed a zero
+    feature (norm2 = identity affine), so every product with them is exactly 0: same arithmetic, same kernels."""
+    H = msd['norm.weight'].numel()
+    sd = {}
+    for k, v in msd.items():
+        if k.startswith('norm.'):
+            sd['norm1.' + k[5:]] = v
+        elif k == 'gen.1.weight':
+            sd['gen.2.weight'] = v
+        elif k == 'gen.0.weight':
+            sd[k] = torch.cat([v, v.new_zeros(v.size(0), H)], 1)
+        elif k.endswith('linear_query.weight'):
+            sd[k] = torch.cat([v, v.new_zeros(v.size(0), H)], 1)
+        else:
+            sd[k] = v
+    sd['norm2.weight'] = msd['norm.weight'].new_ones(H)
+    sd['norm2.bias'] = msd['norm.weight'].new_zeros(H)
+    return sd
+
+
+class FastMasqueDecoder(FastCaSEDecoder):
+    """Module face for the Masque baseline: stands where the reference builds
+    ``MasqueTransformerSeqDecoder`` (Masque/Model.py:13), keeps ITS state_dict keys and ``forward`` signature
+    (Masque/Model.py:47: ``encode_masks`` / ``encode_weights`` before ``groundtruth_index``, no
+    ``additional_decoder_feature``) and runs the CaSE decode kernels through ``masque_to_case_state``."""
+
+    def __init__(self, num_memories, num_layers, nhead, tgt_vocab_size, hidden_size, emb_matrix=None, **kw):
+        super().__init__(num_memories, num_layers, nhead, tgt_vocab_size, hidden_size, emb_matrix=emb_matrix, **kw)
+        H = hidden_size
+        del self.norm1, self.norm2
+        self.norm = nn.LayerNorm(H)
+        self.attns = nn.ModuleList([_AdditiveParams(H, H, H) for _ in range(num_memories)])
+        self.gen = nn.Sequential(nn.Linear(2 * H, H), nn.Linear(H, tgt_vocab_size, bias=False), nn.Softmax(dim=-1))
+
+    def _packed(self, device) -> CaseWeights:
+        if self._weights is None or self._weights.device != device or self._weights.dtype_name != self.dtype:
+            self._weights = CaseWeights(masque_to_case_state(self.state_dict()), device=device, dtype=self.dtype)
+            self._engines = {}
+        return self._weights
+
+    def forward(self, encode_memories, BOS, UNK, source_map, encode_masks=None, encode_weights=None,
+                groundtruth_index=None, init_decoder_state=None, max_target_length=None):
+        B, dev = source_map.size(0), encode_memories[0].device
+        if encode_weights is None:        # Masque/Model.py:100-103: without weights p is the attention itself
+            encode_weights = [torch.ones(B, m.reshape(B, -1, self.hidden_size).size(1), device=dev) for m in encode_memories]
+        feat = torch.zeros(B, self.hidden_size, device=dev)
+        return super().forward(encode_memories, BOS, UNK, source_map, groundtruth_index=groundtruth_index,
+                               additional_decoder_feature=feat, encode_weights=encode_weights,
+                               encode_masks=encode_masks, init_decoder_state=init_decoder_state,
+                               max_target_length=max_target_length)
+
+
 def install_fast_decoder(model: nn.Module, beam_width: int = 1, dtype: str = 'bf16', **kw) -> nn.Module:
-    """Swap the decoder of a reference ``CaSE`` model (CaSE/Model.py:255-339) for the CUDA path, in place.
+    """Swap the decoder of a reference ``CaSE`` model (CaSE/Model.py:255-339) - or of the ``Masque`` baseline
+    (Masque/Model.py:202-285: same ``response_generation.decoder`` / ``do_test`` / ``build_map`` structure) - for the
+    CUDA path, in place.
 
     * ``model.response_generation.decoder`` becomes a ``FastCaSEDecoder`` holding the same weights;
     * ``model.forward`` keeps ``data['source_map']`` in index form instead of calling ``build_map``
       (Model.py:334-335) when ``method == 'test'``; training goes through the original forward.
     """
     ref_dec = model.response_generation.decoder
-    fast = FastCaSEDecoder.from_reference(ref_dec, beam_width=beam_width, dtype=dtype, **kw)
+    cls = FastMasqueDecoder if hasattr(ref_dec, 'norm') and not hasattr(ref_dec, 'norm1') else FastCaSEDecoder   # Masque/Model.py:29
+    fast = cls.from_reference(ref_dec, beam_width=beam_width, dtype=dtype, **kw)
     model.response_generation.decoder = fast
     orig_forward = model.forward
 

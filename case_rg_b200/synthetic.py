@@ -44,6 +44,28 @@ def sinusoid_table(max_len: int, H: int) -> torch.Tensor:
     return pe
 
 
+def make_masque_decoder_state(seed: int, V: int = BERT_VOCAB, H: int = 256, **kw) -> Dict[str, torch.Tensor]:
+    """Random-init state_dict with the keys of ``MasqueTransformerSeqDecoder`` (Masque/Model.py:14-36): the seeded CaSE
+    state with the feature columns dropped (``linear_query`` [H,H], ``gen.0`` [H,2H]), ``norm1`` as ``norm`` and the
+    vocabulary projection under ``gen.1``."""
+    sd = make_case_decoder_state(seed, V, H, **kw)
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in sd.items():
+        if k.startswith('norm2.'):
+            continue
+        if k.startswith('norm1.'):
+            out['norm.' + k[6:]] = v
+        elif k == 'gen.2.weight':
+            out['gen.1.weight'] = v
+        elif k == 'gen.0.weight':
+            out[k] = v[:, :2 * H].contiguous()
+        elif k.endswith('linear_query.weight'):
+            out[k] = v[:, :H].contiguous()
+        else:
+            out[k] = v
+    return out
+
+
 def make_case_decoder_state(seed: int, V: int = BERT_VOCAB, H: int = 256, num_memories: int = 2,
                             num_layers: int = 4, peaked: float = 0.0,
                             boost: Optional[Dict[int, float]] = None,

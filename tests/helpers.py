@@ -64,3 +64,14 @@ def pad_to(tokens, L):
     out = torch.zeros(tokens.size(0), L, dtype=torch.long)
     out[:, :tokens.size(1)] = tokens
     return out
+
+
+def build_masque(name='masque_module_greedy'):
+    """-> (npz, cfg, Masque state_dict, CaseInputs) for the Masque decoder fixture (tests/golden/make_masque_golden.py)."""
+    z, cfg = load_golden(name)
+    msd = syn.make_masque_decoder_state(int(cfg['wseed']), V_SMALL, H, peaked=cfg['peaked'], boost={0: cfg['pad_boost']},
+                                        gen_gate_bias=cfg['gate'])
+    assert abs(syn.state_checksum(msd) - float(z['wsum'])) < 1e-6 * max(1.0, abs(float(z['wsum'])))
+    inp = syn.make_case_inputs(int(cfg['iseed']), int(cfg['B']), int(cfg['Lq']), int(cfg['NP']), int(cfg['Lp']),
+                               V_SMALL, H)
+    return z, cfg, msd, inp

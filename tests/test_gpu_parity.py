@@ -479,3 +479,34 @@ def test_compacted_cross_attention_vs_torch(B, W, S):
     assert rel_err(got[live], want[live]) < 1.5e-2, rel_err(got[live], want[live])
     # a query without valid keys has only empty partials (l = 0): the layer kernels turn that into a zero context
     assert bool((ml[~live][..., 1] == 0).all())
+
+
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+@pytest.mark.parametrize('tag', ['w', 'now'])
+def test_masque_module_face_matches_reference_golden(tag, dtype):
+    """FastMasqueDecoder (Masque's state_dict keys and forward signature, CaSE decode kernels) against the golden
+    produced by the unmodified MasqueTransformerSeqDecoder: fp32 tokens identical and the last distribution within
+    1e-4; bf16 within 2e-2 on the distribution's large entries."""
+    from case_rg_b200.decoder import FastMasqueDecoder
+    from helpers import build_masque
+    z, cfg, msd, inp = build_masque()
+    inp = inp.to(DEV)
+    dec = FastMasqueDecoder(2, 4, 8, 1000, 256, dtype=dtype)
+    missing = dec.load_state_dict(msd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    dec = dec.to(DEV).eval()
+    dec.return_distribution = True
+    out = dec(inp.encode_memories, syn.BOS, syn.UNK, inp.source_map, encode_masks=inp.encode_masks,
+              encode_weights=inp.encode_weights if tag == 'w' else None, max_target_length=int(cfg['T']))
+    toks, dist = out[3].cpu().numpy(), out[2][:, 0].cpu()
+    gold = torch.from_numpy(z[f'dist_{tag}'][:, -1])
+    if dtype == 'fp32':
+        assert np.array_equal(toks, z[f'tokens_{tag}'])
+        assert rel_err(dist, gold) < 1e-4, rel_err(dist, gold)
+    else:
+        agree = float((toks == z[f'tokens_{tag}']).mean())
+        assert agree >= 0.9, agree
+    dec.return_distribution = False
+    out = dec(inp.encode_memories, syn.BOS, syn.UNK, inp.source_map, encode_masks=inp.encode_masks,
+              encode_weights=inp.encode_weights if tag == 'w' else None, max_target_length=int(cfg['T']))
+    assert out[2] is None and np.array_equal(out[3].cpu().numpy(), toks)

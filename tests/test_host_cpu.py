@@ -98,6 +98,25 @@ def test_signature_matches_reference_module():
            {k: tuple(v.shape) for k, v in fast.state_dict().items()}
 
 
+@pytest.mark.skipif(not os.path.isdir('/root/reference/Masque'), reason='reference tree only exists in the build box')
+def test_masque_face_matches_reference_module():
+    """FastMasqueDecoder keeps MasqueTransformerSeqDecoder's state_dict keys / shapes and forward signature
+    (Masque/Model.py:13-47); install_fast_decoder picks it for a Masque-shaped model."""
+    import inspect
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+    import make_golden  # noqa: F401  (import shim for the reference)
+    import Masque.Model as ref_masque
+    from case_rg_b200.decoder import FastMasqueDecoder, masque_to_case_state
+    ref = ref_masque.MasqueTransformerSeqDecoder(2, 4, 8, 300, 256)
+    fast = FastMasqueDecoder(2, 4, 8, 300, 256)
+    assert list(inspect.signature(ref.forward).parameters) == list(inspect.signature(fast.forward).parameters)
+    fast.load_state_dict(ref.state_dict(), strict=True)
+    assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == \
+           {k: tuple(v.shape) for k, v in fast.state_dict().items()}
+    assert set(masque_to_case_state(ref.state_dict())) == set(syn.make_case_decoder_state(3, 300, 256))
+    assert set(syn.make_masque_decoder_state(3, 300, 256)) == set(ref.state_dict())
+
+
 def test_shard_indices_match_distributed_sampler():
     from torch.utils.data.distributed import DistributedSampler
 
