@@ -410,11 +410,9 @@ def roofline(model, eng, args, torch):
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / (reps * 4)
     ach = alg / (us * 1e-6) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed
-    # `ncu --set full` capture (profiles/r1_top_kernels_ncu_summary.txt): 168.3 MB read + 5.4 MB written
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at the BASELINE shape from the committed
-    # `ncu --set full` capture (profiles/r1_top_kernels_ncu_summary.txt): 114.3 MB read + 4.3 MB written
-    traffic = 118.6e6 if (compact and (B, W, S1) == (64, 4, 2560)) else None
+    # `ncu --set full` capture (profiles/r1_top_kernels_ncu_summary.txt): 114.3 MB read + 3.1 MB written
+    traffic = 117.4e6 if (compact and (B, W, S1) == (64, 4, 2560)) else None
     kname = 'cross_attn_part_kernel (passage memory, valid keys)' if compact else ('cross_attn_mma_kernel (passage memory)' if eng.w.cdtype == L.BF16 else 'cross_attn_partial_kernel (passage memory)')
     return dict(kernel=kname, bound='hbm', achieved=ach, peak=peak, unit='GB/s',
                 frac=ach / peak, traffic=traffic, peak_source=which, algorithmic_bytes_per_launch=alg,
