@@ -401,9 +401,12 @@ class CaseDecodeEngine(_EngineBase):
         self.qcount = torch.zeros(B, dtype=torch.int32, device=dev)
         # work-proportional key splits of the second memory's additive attention (gate form): query b uses
         # xns[b] of the MAX_SPLIT slots so that every CTA walks about the same number of valid keys and the
-        # whole launch is one resident wave (add_slots CTAs)
+        # whole launch is one resident wave (add_slots CTAs).  Two CTAs per SM, not the three that fit: alone the
+        # launch is slower that way (64 against 47 us), but three CTAs fill the register file, and with two the
+        # vocabulary GEMM and vocab_base of the main stream get onto the SMs beside it - measured per step at C2:
+        # 0.3357 / 0.3317 / 0.3295 / 0.3294 / 0.3327 ms for 222 / 259 / 296 / 333 / 444 slots
         self.prop_split = self.compact and self.Gv is not None and os.environ.get('CASE_PROP_SPLIT', '1') != '0'
-        self.add_slots = int(os.environ.get('CASE_ADD_SLOTS', 3 * 148))
+        self.add_slots = int(os.environ.get('CASE_ADD_SLOTS', 2 * 148))
         self.xns = torch.zeros(B, dtype=torch.int32, device=dev)
         self._mv_src = [None, None]
         # copy plan of the batch (sparse tail from a sorted unique-id list instead of the hash table: no atomics, so
