@@ -193,8 +193,11 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':   # would put a banner line on stdout next to the JSON line
+        # NCCL's version banner (NCCL_DEBUG=VERSION, from the environment or /etc/nccl.conf) goes to stdout, next to the
+        # JSON line: the environment wins over the conf file, and any debug output is sent to stderr
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
             os.environ['NCCL_DEBUG'] = 'WARN'
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     w = WORKLOAD
     B, W, T, V = args.batch, args.beam, w['T'], w['V']
