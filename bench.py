@@ -341,9 +341,10 @@ def main():
     h2d = host.nbytes()
     d2h = int(out_e.numel() * out_e.element_size())
 
-    roof = cpu = None
+    roof = cpu = shares = None
     if rank == 0:
         roof = roofline(model, eng, args, torch)
+        shares = step_shares(step_resident, torch, dev)
         if not args.no_cpu_baseline and world == 1:
             cpu = cpu_baseline(args)
     if rank != 0:
@@ -361,11 +362,33 @@ def main():
                 e2e=dict(value=e2e_value, unit='tokens/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          ms_per_step=ms_e2e / args.steps, h2d_ms_alone=h2d_ms, h2d_gbs_alone=h2d / (h2d_ms * 1e6),
                          pinned=all(v.is_pinned() for v in host_data.values())),
-                gpu_launches=launches, clocks=clk, roofline=roof, cpu_baseline=cpu,
+                gpu_launches=launches, clocks=clk, roofline=roof, step_shares=shares, cpu_baseline=cpu,
                 wall_s=dict(resident=wall, e2e=wall_e2e))
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def step_shares(step_fn, torch, dev):
+    """Share of every kernel in the GPU time of one batch (prefill + decode graph), from the CUPTI activity records of
+    one extra, untimed batch: the figure the committed ncu launch list (profiles/) has to agree with.  The largest
+    share is the latency-bound row work of the cluster launches (layer_chain_kernel); the `roofline` object describes
+    the largest BANDWIDTH-bound kernel, the passage cross-attention."""
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step_fn()
+            torch.cuda.synchronize(dev)
+        tot = {}
+        for e in prof.events():
+            if e.device_type == torch.autograd.DeviceType.CUDA and 'Memcpy' not in e.name and 'Memset' not in e.name:
+                k = e.name.split('(')[0].split('<')[0].replace('void ', '').replace('cb::', '')
+                tot[k] = tot.get(k, 0.0) + (e.time_range.end - e.time_range.start)
+        s = sum(tot.values())
+        top = sorted(tot.items(), key=lambda kv: -kv[1])[:8]
+        return {k: round(v / s, 4) for k, v in top} if s > 0 else None
+    except Exception as ex:          # the profiler is evidence, not the product: never fail the bench line over it
+        return {'unavailable': str(ex)[:120]}
 
 
 def roofline(model, eng, args, torch):
