@@ -510,3 +510,32 @@ def test_masque_module_face_matches_reference_golden(tag, dtype):
     out = dec(inp.encode_memories, syn.BOS, syn.UNK, inp.source_map, encode_masks=inp.encode_masks,
               encode_weights=inp.encode_weights if tag == 'w' else None, max_target_length=int(cfg['T']))
     assert out[2] is None and np.array_equal(out[3].cpu().numpy(), toks)
+
+
+def test_cache_policy_and_prefill_switches_do_not_change_answers():
+    """Pure plumbing switches: the L2 evict-first hint on the K|V / Uk.mem streams (case_set_stream_evict_first) is a cache
+    policy only - identical tokens bit for bit; the own prefill GEMM against the cuBLAS + packing pass (CASE_PREFILL_TC=0)
+    differs by 1-ulp bf16 roundings of K|V at most - the same answers on peaked weights."""
+    import os
+    from case_rg_b200 import generations as FG
+    from case_rg_b200 import _lib as L
+    V, B, T, W = 5000, 6, 8, 4
+    sd = syn.make_case_decoder_state(32, V, H, peaked=0.3, boost={syn.EOS: 12.0}, gen_gate_bias=2.0)
+    inp = syn.make_case_inputs(42, B, 24, 4, 40, V, H)
+    lib = L.load()
+    res = {}
+    try:
+        for on in (0, 1):
+            lib.case_set_stream_evict_first(on)
+            res[on] = FG.beam(FG.FastCaSE(sd, device=DEV, dtype='bf16'), _case_data(inp), None, T, W).cpu()
+    finally:
+        lib.case_set_stream_evict_first(1)
+    assert torch.equal(res[0], res[1])
+    os.environ['CASE_PREFILL_TC'] = '0'
+    try:
+        lib_path = FG.beam(FG.FastCaSE(sd, device=DEV, dtype='bf16'), _case_data(inp), None, T, W).cpu()
+    finally:
+        del os.environ['CASE_PREFILL_TC']
+    Lc = min(lib_path.size(1), res[1].size(1))
+    same = sum(int(torch.equal(lib_path[i, :Lc], res[1][i, :Lc])) for i in range(B))
+    assert same >= B - 1, (lib_path, res[1])
