@@ -14,6 +14,9 @@ MAX_W, MAX_T, MAX_SPLIT = 8, 128, 16
 F32, BF16 = 0, 1
 MODE_MODULE_GREEDY, MODE_PROTO_GREEDY, MODE_BEAM = 0, 1, 2
 XATTN_TILE = AATTN_TILE = 128
+# option bits of StepArgs.opt / GttpStepArgs.opt (include/case_b200.h: a set bit switches one feature OFF)
+OPT_NO_PDL, OPT_NO_CHAIN, OPT_NO_STACK, OPT_NO_FORK, OPT_NO_POST, OPT_NO_GATE = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
+OPT_NO_EVICT_FIRST, OPT_DENSE_TAIL, OPT_UNFUSED_TAIL, OPT_NO_FUSED_SELECT, OPT_NO_COPY_PLAN = 0x40, 0x80, 0x100, 0x200, 0x400
 
 vp, i32, f32p = C.c_void_p, C.c_int32, C.c_void_p
 
@@ -71,7 +74,7 @@ class StepArgs(C.Structure):
                 ('out_tokens', vp), ('n_live', vp),
                 ('x_in', vp), ('h', vp), ('bbuf', vp), ('q2', vp), ('part_ml', vp), ('part_acc', vp), ('qa', vp),
                 ('attn_un', vp * 2), ('stats', vp * 2), ('ctxp', vp * 2), ('hN', vp), ('ctx', vp * 2), ('gates', vp),
-                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp), ('prow', vp), ('h0', vp), ('qa1', vp), ('base_ms', vp), ('base_e', vp), ('base_i', vp), ('xcount', vp), ('xprefix', vp), ('xslots', i32), ('xidx', vp), ('xorder', vp), ('qcount', vp), ('Wqa_c', vp * 2), ('Wg_c', vp), ('xns', vp), ('cp_n', vp), ('cp_uid', vp), ('cp_first', vp), ('cp_start', vp), ('cp_perm', vp), ('cp_ld', i32), ('U16', vp * 2), ('Gv', vp * 2)]
+                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp), ('prow', vp), ('h0', vp), ('qa1', vp), ('base_ms', vp), ('base_e', vp), ('base_i', vp), ('xcount', vp), ('xprefix', vp), ('xslots', i32), ('xidx', vp), ('xorder', vp), ('qcount', vp), ('Wqa_c', vp * 2), ('Wg_c', vp), ('xns', vp), ('cp_n', vp), ('cp_uid', vp), ('cp_first', vp), ('cp_start', vp), ('cp_perm', vp), ('cp_ld', i32), ('Gv', vp * 2), ('opt', i32), ('fork', vp)]
 
 
 class GttpStepArgs(C.Structure):
@@ -85,7 +88,8 @@ class GttpStepArgs(C.Structure):
                [(n, vp) for n in ('tok', 'live', 'cum', 'length', 'parent', 'ended', 'best_key', 'best_len',
                                   'out_tokens', 'n_live', 'emb', 'qa')] + \
                [('attn_un', vp * 2), ('stats', vp * 2), ('ctxp', vp * 2), ('ctx', vp * 2)] + \
-               [(n, vp) for n in ('gi', 'gh', 'feat', 'gates', 'fac', 'logits', 'dist', 'top_vals', 'top_idx', 'vocab_ws')]
+               [(n, vp) for n in ('gi', 'gh', 'feat', 'gates', 'fac', 'logits', 'dist', 'top_vals', 'top_idx', 'vocab_ws')] + \
+               [('opt', i32)]
 
 
 # name -> argtypes (return type is int for all but the three listed below)
@@ -107,7 +111,6 @@ _PROTOS = {
     'case_layer_stack': [C.POINTER(LayerWeights), i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, C.c_float, vp, vp, vp, i32, vp,
                          i32, vp, i32, i32, vp, vp, i32, i32, C.POINTER(ChainPost), vp],
     'case_layer_chain_max_s0': [],
-    'case_layer_chain_prefetch': [vp, vp, i32, i32, i32],
     'case_additive_attn': [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp],
     'case_additive_attn_compact': [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp,
                                    vp, vp],
@@ -126,28 +129,13 @@ _PROTOS = {
     'case_gru_cell': [vp, vp, vp, vp, vp, i32, vp],
     'case_attn_merge': [vp, vp, i32, i32, vp, vp, i32, i32, vp],
     'case_gttp_gates': [vp, vp, vp, vp, vp, i32, i32, i32, vp],
-    'case_set_pdl': [i32],
-    'case_set_chain': [i32],
-    'case_set_stack_fusion': [i32],
-    'case_set_fork': [i32],
     'case_additive_attn_gate': [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp],
     'case_gate_project': [vp, vp, vp, C.c_longlong, vp],
     'case_split_plan': [vp, i32, i32, i32, vp, vp],
-    'case_additive_attn_gate_h': [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp],
-    'case_set_additive_impl': [i32],
-    'case_set_fused_tail': [i32],
-    'case_set_fused_select': [i32],
-    'case_set_post_linears': [i32],
-    'case_set_kv_prefetch': [i32],
-    'case_set_gate_form': [i32],
-    'case_set_gate_f16': [i32],
-    'case_set_copy_plan': [i32],
-    'case_set_next_step_prefetch': [i32],
-    'case_set_stream_evict_first': [i32],
     'case_prefill_project_tc': [vp, vp, vp, i32, i32, vp, vp, i32, vp, vp, vp],
-    'case_set_xattn_ctas': [i32],
-    'case_set_xattn_next_prefetch': [i32],
-    'case_cross_attn_part_next': [vp, i32],
+    'case_thread_options': [i32],
+    'case_fork_create': [C.POINTER(vp)],
+    'case_fork_destroy': [vp],
     'case_decode_step': [C.POINTER(StepArgs), i32, vp],
     'gttp_decode_step': [C.POINTER(GttpStepArgs), i32, vp],
 }
@@ -171,7 +159,7 @@ def load():
     lib.case_last_error.restype = C.c_char_p
     lib.case_struct_size.restype = C.c_size_t
     lib.case_struct_size.argtypes = [C.c_int]
-    if lib.case_abi_version() != 1:
+    if lib.case_abi_version() != 2:
         raise RuntimeError('libcase_b200.so: unexpected ABI version')
     for i, st in enumerate(_STRUCTS):
         if lib.case_struct_size(i) != C.sizeof(st):

@@ -326,11 +326,7 @@ static int launch_additive(const float* qa, const void* U, const void* Mv, const
   const size_t fl = (size_t)WMAX * H + H + (size_t)NG * WMAX * TS + 8 + 128;
   const size_t smem = fl * sizeof(float) + (size_t)TS * LD * sizeof(T);
   auto kern = additive_attn_kernel<T, WMAX, FAST>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set = true;
-  }
+  ensure_smem<additive_attn_kernel<T, WMAX, FAST>>(96 * 1024);
   launch_k(kern, dim3(B, nsplit), AT, smem, st, qa, (const T*)U, (const T*)Mv, v, mask, prior, tok, tok_ld, t, W, S, DV,
                                           nsplit, attn_un, stats, ctx_part);
   return check_launch("case_additive_attn");
@@ -379,9 +375,10 @@ extern "C" int case_cross_attn_partial(const float* q2, const void* Kmem, const 
   return dispatch_cross_w<float>(q2, Kmem, Vmem, mask, B, W, S, nsplit, part_ml, part_acc, (cudaStream_t)stream);
 }
 
-int case_additive_attn_v2(const float* qa, const void* U, const void* Mv, const float* v, const uint8_t* mask,
-                          const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S, int DV,
-                          int nsplit, float* scores, float* stats, float* ctx_part, int fast_tanh, cudaStream_t st);
+int case_additive_attn_bf16(const float* qa, const void* U, const void* Mv, const float* v, const uint8_t* mask,
+                            const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S, int DV,
+                            int nsplit, float* scores, float* stats, float* ctx_part, int fast_tanh, const int32_t* cidx,
+                            const int32_t* ncount, const int32_t* qorder, cudaStream_t st);
 
 extern "C" int case_additive_attn(const float* qa, const void* U, const void* Mv, const float* v,
                                   const uint8_t* mask, const float* prior, const int32_t* tok, int tok_ld, int t,
@@ -392,13 +389,9 @@ extern "C" int case_additive_attn(const float* qa, const void* U, const void* Mv
   CB_REQUIRE(DV == 256 || DV == 512, "case_additive_attn: DV must be 256 or 512");
   CB_REQUIRE(nsplit >= 1 && nsplit <= CASE_MAX_SPLIT, "case_additive_attn: nsplit out of range");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == CASE_BF16)
-    return case_additive_attn_v2(qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, W, S, DV, nsplit, attn_un, stats,
-                                 ctx_part, fast_tanh, st);
-  if (dtype == CASE_BF16) {
-    if (fast_tanh) return dispatch_additive_w<bf16, true>(W, qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, S, DV, nsplit, attn_un, stats, ctx_part, st);
-    return dispatch_additive_w<bf16, false>(W, qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, S, DV, nsplit, attn_un, stats, ctx_part, st);
-  }
+  if (dtype == CASE_BF16)     // fused single-pass kernel of additive_v2.cu (the two-pass kernel here is the fp32 form)
+    return case_additive_attn_bf16(qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, W, S, DV, nsplit, attn_un, stats,
+                                   ctx_part, fast_tanh, nullptr, nullptr, nullptr, st);
   if (fast_tanh) return dispatch_additive_w<float, true>(W, qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, S, DV, nsplit, attn_un, stats, ctx_part, st);
   return dispatch_additive_w<float, false>(W, qa, U, Mv, v, mask, prior, tok, tok_ld, t, B, S, DV, nsplit, attn_un, stats, ctx_part, st);
 }
@@ -598,11 +591,7 @@ extern "C" int case_cross_attn_partial_tc(const float* q2, const void* KV, const
   CB_REQUIRE(B > 0 && W >= 1 && W <= CASE_MAX_W && S > 0, "case_cross_attn_partial_tc: bad sizes");
   CB_REQUIRE(nsplit >= 1 && nsplit <= CASE_MAX_XSPLIT, "case_cross_attn_partial_tc: nsplit out of range");
   CB_REQUIRE((uintptr_t)KV % 16 == 0, "case_cross_attn_partial_tc: KV must be 16-byte aligned");
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(cb::cross_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cb::XM_SMEM);
-    attr = true;
-  }
+  ensure_smem<cb::cross_attn_mma_kernel>(cb::XM_SMEM);
   launch_k(cb::cross_attn_mma_kernel, dim3(B, nsplit), cb::XM_WARPS * 32, cb::XM_SMEM, (cudaStream_t)stream,
            q2, (const cb::bf16*)KV, mask, W, S, nsplit, part_ml, part_acc);
   return cb::check_launch("case_cross_attn_partial_tc");

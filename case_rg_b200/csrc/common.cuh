@@ -16,9 +16,30 @@ constexpr float LN_EPS = 1e-5f;
 
 void set_error(const char* msg);
 int check_launch(const char* what);
-extern int g_use_pdl;          // programmatic dependent launch on every kernel of the step (step.cu)
-extern int g_evict_first;      // the once-per-step K|V / Uk.mem streams are loaded with an L2 evict-first policy (step.cu)
-extern cudaError_t g_launch_err;
+
+// Per-THREAD launch options (step.cu): nothing in this library is process-global.  The step orchestrators install the
+// options of their argument block (case_step_args_t.opt) for the duration of the call; direct launcher calls use the
+// calling thread's options (case_thread_options, default: everything on).
+struct LaunchOpts {
+  int pdl;           // programmatic dependent launch attribute on every kernel launch
+  int evict_first;   // the once-per-step K|V / Uk.mem streams are loaded with an L2 evict-first policy
+};
+LaunchOpts& launch_opts();
+cudaError_t& launch_err();
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: set it once per (kernel
+// instantiation, device) - not once per process, which would leave every device but the first at the 48 KB default.
+template <auto Kern>
+inline void ensure_smem(int bytes) {
+  static unsigned long long done = 0;          // one static per kernel; bit d = device d is set up
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(done & bit)) {
+    cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    done |= bit;                               // (a racing second thread repeats the same idempotent call)
+  }
+}
 
 // Launch helper: same as kernel<<<grid, block, smem, stream>>>(args...) plus the programmatic
 // stream-serialization attribute, so the next kernel's CTAs may be scheduled (and run their
@@ -34,8 +55,8 @@ inline void launch_k(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cu
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 1 : 0;
-  g_launch_err = cudaLaunchKernelExC(&cfg, (const void*)kern, pa);
+  cfg.attrs = at; cfg.numAttrs = launch_opts().pdl ? 1 : 0;
+  launch_err() = cudaLaunchKernelExC(&cfg, (const void*)kern, pa);
 }
 
 #define CB_REQUIRE(cond, msg)        \

@@ -429,11 +429,7 @@ extern "C" int case_vocab_gemm_tc(const float* f, const void* Wp, const float* b
   CB_REQUIRE(f && Wp && logits && workspace && R > 0 && V > 0 && ldl >= V, "case_vocab_gemm_tc: bad arguments");
   CB_REQUIRE(((uintptr_t)Wp % 16 == 0) && ((uintptr_t)workspace % 16 == 0), "case_vocab_gemm_tc: 16-byte alignment required");
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(vocab_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-    attr = true;
-  }
+  ensure_smem<vocab_gemm_tc_kernel>(TC_SMEM);
   const int nblk = (R + TC_NB - 1) / TC_NB;
   const int n = nblk * TC_NB * (TC_K / 8);
   launch_k(pack_activations_kernel, (n + 255) / 256, 256, 0, st, f, (bf16*)workspace, R);
@@ -456,11 +452,7 @@ extern "C" int case_prefill_project_tc(const void* mem, const void* Wp, const fl
     o.p[l] = l < nl ? (bf16*)out[l] : nullptr;
     CB_REQUIRE(l >= nl || (out[l] && (uintptr_t)out[l] % 16 == 0), "case_prefill_project_tc: K|V outputs must be 16-byte aligned");
   }
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(prefill_project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM);
-    attr = true;
-  }
+  ensure_smem<prefill_project_tc_kernel>(PF_SMEM);
   launch_k(prefill_project_tc_kernel, dim3((S + PF_KEYS - 1) / PF_KEYS, B), PF_THREADS, PF_SMEM, (cudaStream_t)stream,
            (const bf16*)mem, (const bf16*)Wp, bias, S, cidx, ncount, nl, o, (bf16*)U);
   return check_launch("case_prefill_project_tc");

@@ -89,14 +89,11 @@ struct ChainArgs {
   int npost;
   struct { const char* w; const float* bias; float* out; int nchunk; int seg[3]; } post[2];
   const float* feat; const float* xin; const float* lnN_g; const float* lnN_b; float* hN_out;
-  // L2 prefetch of the K|V stream the NEXT (big) cross-attention launch will read: HBM is idle while this
-  // launch runs, the compacted tiles of a (query, head) are one contiguous run
-  const char* pf_base; const int32_t* pf_tp; int pf_B, pf_ntile_all, pf_pct;
   long long* dbg;                  // optional stage clock stamps of CTA 0 (case_debug_chain_timing)
 };
 constexpr int SEG_H = 1, SEG_HLN = 2, SEG_FEAT = 3, SEG_XIN = 4;
 
-static long long* g_chain_dbg = nullptr;
+static thread_local long long* g_chain_dbg = nullptr;   // debugging aid of the calling thread
 
 // ---- PTX helpers
 __device__ __forceinline__ void c_mb_init(uint32_t bar, int count) {
@@ -382,18 +379,6 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
     return __ldg(reinterpret_cast<const float2*>(bvec + ecol));
   };
 
-  if (a.pf_base != nullptr && warp == 7) {
-    // (query, head) runs p = blockIdx.x, blockIdx.x + gridDim.x, ...; lanes take 64 KB pieces of a run
-    for (int p = blockIdx.x; p < a.pf_B * NH; p += gridDim.x) {
-      const int b = p / NH;
-      const long long bytes = (long long)(a.pf_tp[b + 1] - a.pf_tp[b]) * 8192 * a.pf_pct / 100;
-      const char* run = a.pf_base + (size_t)p * a.pf_ntile_all * 8192;
-      for (long long off = (long long)lane * 65536; off < bytes; off += 32 * 65536) {
-        const long long n = bytes - off < 65536 ? bytes - off : 65536;
-        c_bulk_prefetch_l2(run + off, (uint32_t)(n & ~15ll));
-      }
-    }
-  }
   if (tid == 0) {
     for (int s = 0; s < 8; ++s) c_mb_init(s_bar + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -920,20 +905,11 @@ static int fill_post(ChainArgs& a, const case_chain_post_t* post) {
   return 0;
 }
 
-static const void* g_pf_base = nullptr; static const int32_t* g_pf_tp = nullptr; static int g_pf_B = 0, g_pf_nt = 0, g_pf_pct = 100;
-
 static int launch_chain(ChainArgs& a, cudaStream_t stream) {
   a.dbg = g_chain_dbg;
-  a.pf_base = reinterpret_cast<const char*>(g_pf_base); a.pf_tp = g_pf_tp; a.pf_B = g_pf_B; a.pf_ntile_all = g_pf_nt;
-  a.pf_pct = g_pf_pct;
-  g_pf_base = nullptr; g_pf_tp = nullptr;                       // one-shot
   // KV history of the front halves, or (launch without front half) the third post tile
   const size_t smem = (size_t)OFF_KV + (a.nfront > 0 ? (size_t)4 * CROWS * a.Tmax * 64 : (size_t)CROWS * CALD * 2 + 2 * CWB);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(layer_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OFF_KV + 4 * CROWS * CTMAX * 64);
-    attr = true;
-  }
+  ensure_smem<layer_chain_kernel>(OFF_KV + 4 * CROWS * CTMAX * 64);
   const int nclusters = (a.R + CROWS - 1) / CROWS;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nclusters * CL); cfg.blockDim = dim3(CT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
@@ -942,9 +918,9 @@ static int launch_chain(ChainArgs& a, cudaStream_t stream) {
   at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 2 : 1;
+  cfg.attrs = at; cfg.numAttrs = launch_opts().pdl ? 2 : 1;
   void* pa[] = {(void*)&a};
-  g_launch_err = cudaLaunchKernelExC(&cfg, (const void*)layer_chain_kernel, pa);
+  launch_err() = cudaLaunchKernelExC(&cfg, (const void*)layer_chain_kernel, pa);
   return check_launch("case_layer_chain");
 }
 
@@ -1000,12 +976,4 @@ extern "C" int case_layer_stack(const case_layer_weights_t* layers, int nfused, 
   { const int e = fill_post(a, post); if (e) return e; }
   a.W = W;
   return launch_chain(a, (cudaStream_t)stream);
-}
-
-/* The NEXT case_layer_chain / case_layer_stack launch also prefetches into L2 the compacted K|V stream
- * (case_pack_kv_tiles_gather layout, tile_prefix as in case_cross_attn_part) that the cross-attention
- * launched after it will read: `pct` percent of every (query, head) run.  One-shot. */
-extern "C" int case_layer_chain_prefetch(const void* KV, const int32_t* tile_prefix, int B, int S, int pct) {
-  g_pf_base = KV; g_pf_tp = tile_prefix; g_pf_B = B; g_pf_nt = (S + 63) / 64; g_pf_pct = pct < 0 ? 0 : (pct > 100 ? 100 : pct);
-  return 0;
 }

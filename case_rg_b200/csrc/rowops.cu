@@ -636,12 +636,8 @@ extern "C" int case_row_linear(const case_rowlin_args_t* a, case_stream_t stream
   if (a->dtype == CASE_BF16) return case_row_linear_tc(a, (cudaStream_t)stream);
   const size_t smem = RING_BYTES + (size_t)(RB * a->K + 4 * RB * 256) * sizeof(float);
   dim3 grid((a->R + RB - 1) / RB, a->N / 256);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(row_linear_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(row_linear_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
-  }
+  ensure_smem<row_linear_kernel<bf16>>(200 * 1024);
+  ensure_smem<row_linear_kernel<float>>(200 * 1024);
   if (a->dtype == CASE_BF16) {
     launch_k(row_linear_kernel<bf16>, grid, NT, smem, (cudaStream_t)stream, *a);
   } else {
@@ -660,12 +656,8 @@ extern "C" int case_layer_front(const float* h, const case_layer_weights_t* w, v
                                (cudaStream_t)stream);
   const int grid = (R + RB - 1) / RB;
   const size_t smem = RING_BYTES + (size_t)FRONT_FLOATS * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(layer_front_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(layer_front_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
-  }
+  ensure_smem<layer_front_kernel<bf16>>(200 * 1024);
+  ensure_smem<layer_front_kernel<float>>(200 * 1024);
   if (dtype == CASE_BF16)
     launch_k(layer_front_kernel<bf16>, grid, NT, smem, (cudaStream_t)stream, h, *w, (bf16*)kcache, (bf16*)vcache, anc, anc_ld,
                                                                      tok, tok_ld, t, Tmax, b_out, q2_out, R);
@@ -683,12 +675,8 @@ extern "C" int case_layer_back(const float* b_in, const float* part_ml, const fl
   if (dtype == CASE_BF16) return case_layer_back_tc(b_in, part_ml, part_acc, nsplit, w, h_out, R, (cudaStream_t)stream);
   const int grid = (R + RB - 1) / RB;
   const size_t smem = RING_BYTES + (size_t)BACK_FLOATS * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(layer_back_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(layer_back_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
-  }
+  ensure_smem<layer_back_kernel<bf16>>(200 * 1024);
+  ensure_smem<layer_back_kernel<float>>(200 * 1024);
   if (dtype == CASE_BF16)
     launch_k(layer_back_kernel<bf16>, grid, NT, smem, (cudaStream_t)stream, b_in, part_ml, part_acc, nsplit, *w, h_out, R);
   else

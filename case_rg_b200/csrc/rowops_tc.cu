@@ -449,6 +449,25 @@ __global__ __launch_bounds__(TNT) void layer_back_tc_kernel(const float* __restr
         const float l = r < R ? part_ml[((size_t)r * NH + tid % NH) * 2 + 1] : 0.f;
         wgt[tid] = l > 0.f ? 1.f / l : 0.f;
       }
+    } else if (nsplit > 16) {
+      // many partials (compacted long memories: up to CASE_MAX_XSPLIT slots): the weights alone fill bs | ys
+      // (64 x 64 floats), so the (m, l) pairs are read straight from global memory instead of being staged
+      if (tid < TRB * NH) {
+        const int r = r0 + tid / NH;
+        const float2* mlp = reinterpret_cast<const float2*>(part_ml) + ((size_t)r * NH + tid % NH) * nsplit;
+        float M = -INFINITY, Z = 0.f;
+        if (r < R) {
+          for (int j = 0; j < nsplit; ++j) M = fmaxf(M, mlp[j].x);
+          for (int j = 0; j < nsplit; ++j) {
+            const float2 ml = mlp[j];
+            Z = fmaf(ml.y, (ml.x == -INFINITY) ? 0.f : fexp(ml.x - M), Z);
+          }
+        }
+        for (int j = 0; j < nsplit; ++j) {
+          const float mj = r < R ? mlp[j].x : -INFINITY;
+          wgt[tid * nsplit + j] = (Z > 0.f && mj != -INFINITY) ? fexp(mj - M) / Z : 0.f;
+        }
+      }
     } else {
       float* mls = wgt + TRB * NH * nsplit;            // staged (m, l) pairs
       for (int i = tid; i < TRB * NH * nsplit; i += TCT) {
@@ -535,11 +554,7 @@ using namespace cb;
 
 int case_row_linear_tc(const case_rowlin_args_t* a, cudaStream_t st) {
   const size_t smem = (size_t)TNS * TSLAB + 128 + (size_t)16 * (a->K + 8) * 2;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(row_linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
-  }
+  ensure_smem<row_linear_tc_kernel>(200 * 1024);
   dim3 grid((a->R + TRB - 1) / TRB, a->N / 256);
   launch_k(row_linear_tc_kernel, grid, TNT, smem, st, *a);
   return check_launch("case_row_linear(tc)");
@@ -548,11 +563,7 @@ int case_row_linear_tc(const case_rowlin_args_t* a, cudaStream_t st) {
 int case_layer_front_tc(const float* h, const case_layer_weights_t* w, void* kcache, void* vcache, const int32_t* anc,
                         int anc_ld, const int32_t* tok, int tok_ld, int t, int Tmax, float* b_out, float* q2_out, int R,
                         cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(layer_front_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_FRONT_SMEM);
-    attr = true;
-  }
+  ensure_smem<layer_front_tc_kernel>(T_FRONT_SMEM);
   launch_k(layer_front_tc_kernel, (R + TRB - 1) / TRB, TNT, T_FRONT_SMEM, st, h, *w, (bf16*)kcache, (bf16*)vcache, anc, anc_ld,
                                                                         tok, tok_ld, t, Tmax, b_out, q2_out, R);
   return check_launch("case_layer_front(tc)");
@@ -560,12 +571,9 @@ int case_layer_front_tc(const float* h, const case_layer_weights_t* w, void* kca
 
 int case_layer_back_tc(const float* b_in, const float* part_ml, const float* part_acc, int nsplit,
                        const case_layer_weights_t* w, float* h_out, int R, cudaStream_t st) {
-  CB_REQUIRE(nsplit <= 16, "case_layer_back: the tensor-core path merges at most 16 partials per (row, head)");
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(layer_back_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_BACK_SMEM);
-    attr = true;
-  }
+  CB_REQUIRE(nsplit <= CASE_MAX_XSPLIT, "case_layer_back: at most CASE_MAX_XSPLIT partials per (row, head)");
+  static_assert(TRB * NH * CASE_MAX_XSPLIT * 4 <= 2 * TRB * FLD * 4, "merge weights must fit the row buffers");
+  ensure_smem<layer_back_tc_kernel>(T_BACK_SMEM);
   launch_k(layer_back_tc_kernel, (R + TRB - 1) / TRB, TNT, T_BACK_SMEM, st, b_in, part_ml, part_acc, nsplit, *w, h_out, R);
   return check_launch("case_layer_back(tc)");
 }

@@ -143,8 +143,15 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
                                                          const int32_t* __restrict__ base_i, int k2, int nslots,
                                                          long long* dbg, const case_select_args_t sel, int do_select,
                                                          int32_t* __restrict__ qcount) {
-  extern __shared__ __align__(16) int hkeys[];            // [nslots] ids (-1 = empty), then [nslots] float masses
+  // [nslots] ids (-1 = empty), then [nslots] low words of the masses (later: the final float values), then - hash
+  // mode only - [nslots] high words.  The copy mass of an id is accumulated as a 64-bit FIXED-POINT integer (2^-62
+  // units, two native 32-bit shared-memory atomics with an explicit carry): integer addition is associative, so the
+  // mass - and with it every top-k value, cost and token - is bit-identical from run to run whatever order the
+  // threads arrive in, and it is the exactly rounded sum of the fp32 contributions.
+  extern __shared__ __align__(16) int hkeys[];
   float* hvals = reinterpret_cast<float*>(hkeys + nslots);
+  uint32_t* hlo = reinterpret_cast<uint32_t*>(hkeys + nslots);
+  uint32_t* hhi = reinterpret_cast<uint32_t*>(hkeys + 2 * nslots);
   __shared__ float sh[TSW * 3];
   __shared__ TopKScratch<TSW, 256> sc;
   const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -161,7 +168,7 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
   auto stamp = [&]() { if (dbg != nullptr && blockIdx.x == 0 && tid == 0) dbg[dbg_n++] = clock64(); };
   stamp();
   if (!plan)
-    for (int i = tid; i < nslots; i += TS) { hkeys[i] = -1; hvals[i] = 0.f; }
+    for (int i = tid; i < nslots; i += TS) { hkeys[i] = -1; hlo[i] = 0u; hhi[i] = 0u; }
   // weights of the mixture gate (the h part) are requested before the dependency wait
   float wmh[3] = {0.f, 0.f, 0.f}, bmv[3] = {0.f, 0.f, 0.f};
   if (a.do_finalize) {
@@ -330,7 +337,15 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
         const uint32_t step = sp_step(id[u]);
         while (true) {
           const int old = atomicCAS(hkeys + slot, -1, id[u]);
-          if (old == -1 || old == id[u]) { atomicAdd(hvals + slot, cw); break; }
+          if (old == -1 || old == id[u]) {
+            // cw <= gate_i <= 1 and the masses of a row sum to <= 1: 2^62 units leave two bits of headroom
+            const unsigned long long q = __float2ull_rn(cw * 4611686018427387904.f);
+            const uint32_t lo = (uint32_t)q;
+            const uint32_t prev = atomicAdd(hlo + slot, lo);
+            const uint32_t hi = (uint32_t)(q >> 32) + ((uint32_t)(prev + lo) < prev ? 1u : 0u);   // carry out of the low word
+            if (hi) atomicAdd(hhi + slot, hi);
+            break;
+          }
           slot = (slot + step) & hmask;
         }
       }
@@ -424,7 +439,8 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
     for (int u = 0; u < 4; ++u) {
       if (id[u] < 0) continue;
       const float e = (a.mask_col0 && id[u] == 0) ? 0.f : sp_exp(lv[u] - mm);
-      const float f = fmaf(scl, e, hvals[s0 + u * TS]);
+      const unsigned long long q = ((unsigned long long)hhi[s0 + u * TS] << 32) | hlo[s0 + u * TS];
+      const float f = fmaf(scl, e, __ull2float_rn(q) * 2.168404344971009e-19f);   // 2^-62
       hvals[s0 + u * TS] = f;
       tmax = fmaxf(tmax, f);
     }
@@ -519,7 +535,7 @@ extern "C" int case_vocab_base(const float* logits, int ldl, int R, int V, int m
   return check_launch("case_vocab_base");
 }
 
-static long long* g_sp_dbg = nullptr;
+static thread_local long long* g_sp_dbg = nullptr;   // debugging aid of the calling thread
 extern "C" int case_debug_sparse_tail_timing(void* buf) { g_sp_dbg = (long long*)buf; return 0; }
 
 extern "C" int case_sparse_tail_max_sources(void) { return 10900; }   // 16384 slots at load factor <= 2/3
@@ -545,14 +561,10 @@ extern "C" int case_sparse_tail(const case_tail_args_t* a, const float* base_ms,
   CB_REQUIRE(!plan || (a->nmem == 2 && a->cp_uid && a->cp_first && a->cp_start && a->cp_perm && a->cp_ld >= total && total < 65536),
              "case_sparse_tail: the copy plan needs cp_uid / cp_first / cp_start / cp_perm with cp_ld >= S0 + S1 (two memories, < 65536 positions)");
   // plan mode: (id, value) per list entry, at most one per source position; the hash layout otherwise
-  const size_t smem = plan ? (size_t)((total + 3) / 4 * 4) * 8 : (size_t)nslots * 8;
+  const size_t smem = plan ? (size_t)((total + 3) / 4 * 4) * 8 : (size_t)nslots * 12;
   if (plan) nslots = (total + 3) / 4 * 4;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(sparse_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
-    attr = true;
-  }
+  ensure_smem<sparse_tail_kernel>(16384 * 12);
   CB_REQUIRE(sel == nullptr || (qcount != nullptr && sel->B * sel->W == a->R && sel->W == a->W && a->K == a->W),
              "case_sparse_tail: fused select needs qcount and matching B / W (k = W)");
   case_select_args_t sv;

@@ -8,35 +8,14 @@
 
 namespace cb {
 
+// Nothing here is process-global: the error text, the pending launch error and the launch options belong to the
+// calling thread; the side stream and events of the fork/join live in a caller-owned case_fork_t.
 static thread_local char g_err[512] = "ok";
-int g_use_pdl = 1;
-int g_use_chain = 1;
-int g_use_fork = 1;
-int g_use_stack = 1;
-int g_use_tail = 2;
-int g_use_fused_select = 1;
-int g_use_post = 1;
-int g_use_gate = 1;
-int g_use_gate_h = 0;          // f16 / tensor-core form of the gate kernel when the step arguments carry U16 (measured slower: off)
-int g_evict_first = 1;         // L2 evict-first policy on the once-per-step K|V and Uk.mem streams
-int g_use_plan = 1;            // sparse tail from the prefill's copy plan (sorted unique ids) instead of the hash table
-int g_xnext = 0;               // tiles per warp the passage cross-attention prefetches for the next layer's launch
-int g_prefetch_pct = 0;        // measured: no gain at C2 (the prefetch traffic slows the latency-bound launch more than it helps)
-int g_prefetch_mask = 3;       // bit 0: from the stack launch (layer 4), bit 1: from the chain launches (layers 5..7)
-// side stream + events for the fork/join inside a step (created on first use, outside any capture: the
-// engines run one uncaptured warm-up step before they capture)
-static cudaStream_t g_aux = nullptr;
-static cudaEvent_t g_ev_fork[2] = {nullptr, nullptr}, g_ev_join[2] = {nullptr, nullptr};
-static bool aux_ready() {
-  if (g_aux) return true;
-  if (cudaStreamCreateWithFlags(&g_aux, cudaStreamNonBlocking) != cudaSuccess) { g_aux = nullptr; return false; }
-  for (int i = 0; i < 2; ++i) {
-    if (cudaEventCreateWithFlags(&g_ev_fork[i], cudaEventDisableTiming) != cudaSuccess) return false;
-    if (cudaEventCreateWithFlags(&g_ev_join[i], cudaEventDisableTiming) != cudaSuccess) return false;
-  }
-  return true;
-}
-cudaError_t g_launch_err = cudaSuccess;
+static thread_local cudaError_t g_launch_err = cudaSuccess;
+static thread_local LaunchOpts g_opts = {1, 1};
+
+LaunchOpts& launch_opts() { return g_opts; }
+cudaError_t& launch_err() { return g_launch_err; }
 
 void set_error(const char* msg) {
   strncpy(g_err, msg, sizeof(g_err) - 1);
@@ -54,104 +33,64 @@ int check_launch(const char* what) {
   return 0;
 }
 
+// the orchestrators run with the options of THEIR argument block and put the thread's own back on every exit path
+struct OptScope {
+  LaunchOpts saved;
+  explicit OptScope(int opt) : saved(g_opts) {
+    g_opts.pdl = (opt & CASE_OPT_NO_PDL) ? 0 : 1;
+    g_opts.evict_first = (opt & CASE_OPT_NO_EVICT_FIRST) ? 0 : 1;
+  }
+  ~OptScope() { g_opts = saved; }
+};
+
 }  // namespace cb
 
-namespace cb {
-// L2 warm-up for the NEXT step's first launch (the fused query-memory stack): what it reads - 4 MB of layer weights,
-// the query memory's K|V tiles, the self-attention history of its four layers - was pushed out of L2 by the step's
-// 0.6 GB of K|V streams (experiment, default off: measured no gain, the launch's 77 us in the graph against 54-60 us
-// stand-alone are not L2 misses on these regions).  Launched on the side stream behind the passage additive attention.
-struct PfRegions { const char* p[16]; unsigned long long bytes[16]; int n; };
-__global__ void l2_prefetch_kernel(PfRegions r) {
-  pdl_wait();
-  constexpr unsigned CH = 4096;
-  for (int i = 0; i < r.n; ++i) {
-    const unsigned long long nch = (r.bytes[i] + CH - 1) / CH;
-    for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < nch;
-         c += (unsigned long long)gridDim.x * blockDim.x) {
-      const unsigned long long off = c * CH;
-      const unsigned len = (unsigned)min((unsigned long long)CH, r.bytes[i] - off) & ~15u;
-      if (len) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(r.p[i] + off), "r"(len) : "memory");
-    }
-  }
-}
-}  // namespace cb
-int g_next_prefetch = 0;       // bit 0: weights + query-memory K|V, bit 1: self-attention history of layers 0..3.  Measured
-                               // at C2: the stack launch stays at 77 us and the step gets slower (0.333 -> 0.345 / 0.404 ms): off
+// side stream + events of the fork/join inside a step, owned by the caller (one per engine, on the engine's device)
+struct case_fork_s {
+  cudaStream_t aux;
+  cudaEvent_t ev_fork[2], ev_join[2];
+  int device;
+};
 
 using namespace cb;
 
-extern "C" int case_set_next_step_prefetch(int mask) {
-  const int old = g_next_prefetch;
-  if (mask >= 0) g_next_prefetch = mask;
-  return old;
+extern "C" int case_fork_create(case_fork_t** out) {
+  CB_REQUIRE(out, "case_fork_create: null pointer");
+  case_fork_s* f = (case_fork_s*)calloc(1, sizeof(case_fork_s));
+  CB_REQUIRE(f, "case_fork_create: out of host memory");
+  cudaError_t e = cudaGetDevice(&f->device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->aux, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&f->ev_fork[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_join[i], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) {
+    set_error(cudaGetErrorString(e));
+    case_fork_destroy(f);
+    return (int)e;
+  }
+  *out = f;
+  return 0;
 }
 
-extern "C" int case_abi_version(void) { return 1; }
-extern "C" int case_set_pdl(int on) {
-  const int old = g_use_pdl;
-  g_use_pdl = on ? 1 : 0;
-  return old;
+extern "C" int case_fork_destroy(case_fork_t* f) {
+  if (!f) return 0;
+  for (int i = 0; i < 2; ++i) {
+    if (f->ev_fork[i]) cudaEventDestroy(f->ev_fork[i]);
+    if (f->ev_join[i]) cudaEventDestroy(f->ev_join[i]);
+  }
+  if (f->aux) cudaStreamDestroy(f->aux);
+  free(f);
+  return 0;
 }
-extern "C" int case_set_chain(int on) {
-  const int old = g_use_chain;
-  g_use_chain = on ? 1 : 0;
-  return old;
-}
-extern "C" int case_set_fused_tail(int on) {
-  const int old = g_use_tail;
-  g_use_tail = on < 0 ? 0 : (on > 2 ? 2 : on);
-  return old;
-}
-extern "C" int case_set_stack_fusion(int on) {
-  const int old = g_use_stack;
-  g_use_stack = on ? 1 : 0;
-  return old;
-}
-extern "C" int case_set_fused_select(int on) {
-  const int old = g_use_fused_select;
-  g_use_fused_select = on ? 1 : 0;
-  return old;
-}
-extern "C" int case_set_post_linears(int on) {
-  const int old = g_use_post;
-  g_use_post = on ? 1 : 0;
-  return old;
-}
-extern "C" int case_set_gate_form(int on) {
-  const int old = g_use_gate;
-  if (on >= 0) g_use_gate = on ? 1 : 0;      // negative: query only
-  return old;
-}
-extern "C" int case_set_stream_evict_first(int on) {
-  const int old = g_evict_first;
-  if (on >= 0) g_evict_first = on ? 1 : 0;   // negative: query only
-  return old;
-}
-extern "C" int case_set_copy_plan(int on) {
-  const int old = g_use_plan;
-  if (on >= 0) g_use_plan = on ? 1 : 0;
-  return old;
-}
-extern "C" int case_set_gate_f16(int on) {
-  const int old = g_use_gate_h;
-  if (on >= 0) g_use_gate_h = on ? 1 : 0;
-  return old;
-}
-extern "C" int case_set_xattn_next_prefetch(int ntiles) {
-  const int old = g_xnext;
-  g_xnext = ntiles < 0 ? 0 : ntiles;
-  return old;
-}
-extern "C" int case_set_kv_prefetch(int pct) {
-  const int old = g_prefetch_pct;
-  g_prefetch_pct = pct < 0 ? 0 : (pct > 100 ? 100 : pct);
-  if (getenv("CASE_PF_MASK")) g_prefetch_mask = atoi(getenv("CASE_PF_MASK"));
-  return old;
-}
-extern "C" int case_set_fork(int on) {
-  const int old = g_use_fork;
-  g_use_fork = on ? 1 : 0;
+
+extern "C" int case_abi_version(void) { return 2; }
+extern "C" int case_thread_options(int opt) {
+  const int old = (g_opts.pdl ? 0 : CASE_OPT_NO_PDL) | (g_opts.evict_first ? 0 : CASE_OPT_NO_EVICT_FIRST);
+  if (opt >= 0) {
+    g_opts.pdl = (opt & CASE_OPT_NO_PDL) ? 0 : 1;
+    g_opts.evict_first = (opt & CASE_OPT_NO_EVICT_FIRST) ? 0 : 1;
+  }
   return old;
 }
 extern "C" const char* case_last_error(void) { return g_err; }
@@ -205,14 +144,22 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
   cudaStream_t st = (cudaStream_t)stream;
   const int R = a->R, B = a->B, W = a->W, TL = a->Tmax + 1, dt = a->dtype;
   const int32_t* anc = a->anc[t & 1];
+  const int opt = a->opt;
+  OptScope scope(opt);
+  const int use_tail = (opt & CASE_OPT_UNFUSED_TAIL) ? 0 : ((opt & CASE_OPT_DENSE_TAIL) ? 1 : 2);
+  if (a->fork != nullptr) {
+    int dev = -1;
+    cudaGetDevice(&dev);
+    CB_REQUIRE(dev == a->fork->device, "case_decode_step: the fork handle was created on another device");
+  }
 
   // search path: the sparse tail (touched ids + base candidates); `generate` face: the dense fused tail
   const int k2 = 2 * W;
-  const bool sparse = g_use_tail == 2 && !a->materialize_only && a->base_ms && a->base_e && a->base_i && a->V >= k2 &&
+  const bool sparse = use_tail == 2 && !a->materialize_only && a->base_ms && a->base_e && a->base_i && a->V >= k2 &&
                       a->S[0] + a->S[1] <= case_sparse_tail_max_sources();
   // gate form of the additive attentions: the contexts only feed the mixture gate, so 3 gate-projected numbers
   // per key replace the value rows (needs the sparse tail, which merges gate partials instead of contexts)
-  const bool gate = g_use_gate && sparse && dt == CASE_BF16 && a->Gv[0] != nullptr && a->Gv[1] != nullptr;
+  const bool gate = !(opt & CASE_OPT_NO_GATE) && sparse && dt == CASE_BF16 && a->Gv[0] != nullptr && a->Gv[1] != nullptr;
   // attns[i]: query = [dec_out ; norm2(answer_rep)]   (Model.py:108), then the fused additive attention
   auto stack_attention = [&](int i, const float* hsrc, float* qa, cudaStream_t s2, bool have_qa = false) -> int {
     if (have_qa) goto additive;          // the query was produced by a post linear of the preceding cluster launch
@@ -228,11 +175,6 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
   additive:
     if (gate) {
       const bool cmp = i == 1 && a->xidx != nullptr && a->xcount != nullptr;
-      if (g_use_gate_h && a->U16[i] != nullptr && W >= 2 && a->fast_tanh)
-        return case_additive_attn_gate_h(qa, a->U16[i], a->Gv[i], a->va[i], a->mask[i], a->prior[i], a->tok, TL, t, B, W,
-                                         a->S[i], a->nsplit_a[i], a->attn_un[i], a->stats[i], a->ctxp[i],
-                                         cmp ? a->xidx : nullptr, cmp ? a->xcount : nullptr, cmp ? a->xorder : nullptr,
-                                         cmp ? a->xns : nullptr, s2);
       return case_additive_attn_gate(qa, a->U[i], a->Gv[i], a->va[i], a->mask[i], a->prior[i], a->tok, TL, t, B, W, a->S[i],
                                      a->nsplit_a[i], a->attn_un[i], a->stats[i], a->ctxp[i], a->fast_tanh,
                                      cmp ? a->xidx : nullptr, cmp ? a->xcount : nullptr, cmp ? a->xorder : nullptr,
@@ -272,7 +214,6 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
   const bool xpart = dt == CASE_BF16 && a->xcount != nullptr && a->xprefix != nullptr && a->xslots > 0;
   auto big_xattn = [&](int L) -> int {
     const int i = L / 4;
-    if (i == 1 && xpart && g_xnext > 0 && L < 7) case_cross_attn_part_next(a->Kx[L + 1], g_xnext);
     if (i == 1 && xpart)
       return case_cross_attn_part(a->q2, a->Kx[L], a->xcount, a->xprefix, B, W, a->S[1], a->xslots, a->part_ml, a->part_acc,
                                   st);
@@ -280,18 +221,21 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
                                       a->part_acc, st);
   };
   auto nparts_of = [&](int L) -> int { return (L / 4 == 1 && xpart) ? a->xslots : a->nsplit_x[L / 4]; };
-  const bool chain = dt == CASE_BF16 && g_use_chain && a->layers[0].Wc != nullptr && a->Tmax <= case_layer_chain_max_tmax();
+  const bool chain = dt == CASE_BF16 && !(opt & CASE_OPT_NO_CHAIN) && a->layers[0].Wc != nullptr && a->Tmax <= case_layer_chain_max_tmax();
   if (chain) {
     // Cluster kernels: [embed + front 0] x [back 0 + front 1] x ... x [back 7], one launch between
     // cross-attentions.  The two additive attentions only feed the mixture gates and the copy scatter,
     // so they run on a side stream: attns[0] beside the whole second stack, attns[1] beside norm1 ->
     // gen.0 -> vocabulary GEMM (fork/join by events, captured into the graph like any other edge).
-    const bool fork = g_use_fork && a->h0 != nullptr && a->qa1 != nullptr && aux_ready();
+    const bool fork = !(opt & CASE_OPT_NO_FORK) && a->fork != nullptr && a->h0 != nullptr && a->qa1 != nullptr;
+    cudaStream_t aux = fork ? a->fork->aux : st;
+    cudaEvent_t* ev_fork = fork ? a->fork->ev_fork : nullptr;
+    cudaEvent_t* ev_join = fork ? a->fork->ev_join : nullptr;
     // the whole first stack (4 layers over the S0 <= 64 keys of the query memory, cross-attention included)
     // plus the first half-layer of the second stack is ONE launch; otherwise one launch per half-layer pair
-    const bool stack0 = g_use_stack && a->S[0] <= case_layer_chain_max_s0();
+    const bool stack0 = !(opt & CASE_OPT_NO_STACK) && a->S[0] <= case_layer_chain_max_s0();
     // attention queries, norm1 and gen.0 ride on the cluster launches as post linears (no row_linear launches)
-    const bool post = g_use_post && a->Wqa_c[0] != nullptr && a->Wqa_c[1] != nullptr && a->Wg_c != nullptr;
+    const bool post = !(opt & CASE_OPT_NO_POST) && a->Wqa_c[0] != nullptr && a->Wqa_c[1] != nullptr && a->Wg_c != nullptr;
     auto qa_post = [&](int i, float* out) {
       case_chain_post_t p;
       memset(&p, 0, sizeof(p));
@@ -307,14 +251,13 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       for (int l = 0; l < 5; ++l) { kcs[l] = a->kcache[l]; vcs[l] = a->vcache[l]; }
       for (int l = 0; l < 4; ++l) kxs[l] = a->Kx[l];
       case_chain_post_t p0 = qa_post(0, a->qa);
-      if (xpart && g_prefetch_pct > 0 && (g_prefetch_mask & 1)) case_layer_chain_prefetch(a->Kx[4], a->xprefix, B, a->S[1], g_prefetch_pct);
       TRY(case_layer_stack(a->layers, 4, kcs, vcs, kxs, a->mask[0], W, a->S[0], nullptr, a->E, a->pe, 16.0f, a->x_in, hdst0,
                            anc, TL, a->tok, TL, a->prow, t, a->Tmax, a->bbuf, a->q2, R, 1, post ? &p0 : nullptr, st));
       if (fork) {
-        CUTRY(cudaEventRecord(g_ev_fork[0], st));
-        CUTRY(cudaStreamWaitEvent(g_aux, g_ev_fork[0], 0));
-        TRY(stack_attention(0, hdst0, a->qa, g_aux, post));
-        CUTRY(cudaEventRecord(g_ev_join[0], g_aux));
+        CUTRY(cudaEventRecord(ev_fork[0], st));
+        CUTRY(cudaStreamWaitEvent(aux, ev_fork[0], 0));
+        TRY(stack_attention(0, hdst0, a->qa, aux, post));
+        CUTRY(cudaEventRecord(ev_join[0], aux));
       } else {
         TRY(stack_attention(0, hdst0, a->qa, st, post));
       }
@@ -334,7 +277,6 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
         pl.lin[1].Wc = a->Wg_c; pl.lin[1].bias = a->bg; pl.lin[1].out = a->gfeat; pl.lin[1].nchunk = 3;
         pl.lin[1].seg[0] = CASE_SEG_XIN; pl.lin[1].seg[1] = CASE_SEG_HLN; pl.lin[1].seg[2] = CASE_SEG_FEAT;
       }
-      if (xpart && g_prefetch_pct > 0 && (g_prefetch_mask & 2) && L >= 4 && L < 8) case_layer_chain_prefetch(a->Kx[L], a->xprefix, B, a->S[1], g_prefetch_pct);
       TRY(case_layer_chain(wb, wf, nullptr, a->E, a->pe, 16.0f /* sqrt(256) */, a->x_in, a->bbuf, a->part_ml,
                            a->part_acc, L > 0 ? nparts_of(L - 1) : 1, hdst, wf ? a->kcache[L] : nullptr,
                            wf ? a->vcache[L] : nullptr, anc, TL, a->tok, TL, a->prow, t, a->Tmax, a->bbuf, a->q2, R,
@@ -342,29 +284,10 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       if (L == 4 || L == 8) {
         const int i = L / 4 - 1;
         if (fork) {
-          CUTRY(cudaEventRecord(g_ev_fork[i], st));
-          CUTRY(cudaStreamWaitEvent(g_aux, g_ev_fork[i], 0));
-          TRY(stack_attention(i, hdst, i == 0 ? a->qa : a->qa1, g_aux, post));
-          if (i == 1 && g_next_prefetch && stack0) {
-            PfRegions pr;
-            pr.n = 0;
-            auto add = [&](const void* p, size_t bytes) {
-              if (p && bytes && pr.n < 16) { pr.p[pr.n] = (const char*)p; pr.bytes[pr.n] = bytes; ++pr.n; }
-            };
-            for (int l = 0; l < 4; ++l) {
-              if (g_next_prefetch & 1) {
-                add(a->layers[l].Wc, (size_t)4 * 8 * 64 * 256 * 2);
-                add(a->Kx[l], (size_t)B * NH * ((a->S[0] + 63) / 64) * 8192);
-              }
-              if (g_next_prefetch & 2) {
-                add(a->kcache[l], (size_t)R * a->Tmax * H * 2);
-                add(a->vcache[l], (size_t)R * a->Tmax * H * 2);
-              }
-            }
-            launch_k(l2_prefetch_kernel, 148, 128, 0, g_aux, pr);
-            TRY(check_launch("l2_prefetch"));
-          }
-          CUTRY(cudaEventRecord(g_ev_join[i], g_aux));
+          CUTRY(cudaEventRecord(ev_fork[i], st));
+          CUTRY(cudaStreamWaitEvent(aux, ev_fork[i], 0));
+          TRY(stack_attention(i, hdst, i == 0 ? a->qa : a->qa1, aux, post));
+          CUTRY(cudaEventRecord(ev_join[i], aux));
         } else {
           TRY(stack_attention(i, hdst, a->qa, st, post));
         }
@@ -377,10 +300,10 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       TRY(gen0());
     }
     TRY(case_vocab_gemm(a->gfeat, a->Wv, nullptr, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, a->vocab_ws, st));
-    if (sparse && !getenv("CASE_SKIP_BASE")) TRY(case_vocab_base(a->logits, a->ldv, R, a->V, 0, k2, a->base_ms, a->base_e, a->base_i, st));
+    if (sparse) TRY(case_vocab_base(a->logits, a->ldv, R, a->V, 0, k2, a->base_ms, a->base_e, a->base_i, st));
     if (fork) {
-      CUTRY(cudaStreamWaitEvent(st, g_ev_join[0], 0));
-      CUTRY(cudaStreamWaitEvent(st, g_ev_join[1], 0));
+      CUTRY(cudaStreamWaitEvent(st, ev_join[0], 0));
+      CUTRY(cudaStreamWaitEvent(st, ev_join[1], 0));
     }
   } else {
   TRY(case_embed_rows(a->E, a->pe, a->tok, TL, t, 16.0f /* sqrt(256) */, a->x_in, R, st));
@@ -407,7 +330,7 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
   TRY(case_vocab_gemm(a->gfeat, a->Wv, nullptr, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, a->vocab_ws, st));
   if (sparse) TRY(case_vocab_base(a->logits, a->ldv, R, a->V, 0, k2, a->base_ms, a->base_e, a->base_i, st));
   }
-  if (sparse || (g_use_tail && a->V <= case_row_tail_max_vocab())) {
+  if (sparse || (use_tail && a->V <= case_row_tail_max_vocab())) {
     // one launch: attention merge + gates, softmax x gate, both copy scatters, top-k; the [R, V]
     // distribution is written only for the `generate` face
     case_tail_args_t ta;
@@ -423,12 +346,12 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
     }
     if (a->materialize_only) { ta.dist = a->dist; } else { ta.top_vals = a->top_vals; ta.top_idx = a->top_idx; }
     ta.gate_ctx = gate ? 1 : 0;
-    if (sparse && g_use_plan && a->cp_n != nullptr) {
+    if (sparse && !(opt & CASE_OPT_NO_COPY_PLAN) && a->cp_n != nullptr) {
       ta.cp_n = a->cp_n; ta.cp_uid = a->cp_uid; ta.cp_first = a->cp_first; ta.cp_start = a->cp_start; ta.cp_perm = a->cp_perm;
       ta.cp_ld = a->cp_ld;
     }
     if (sparse) {
-      const bool fuse_sel = a->qcount != nullptr && g_use_fused_select;
+      const bool fuse_sel = a->qcount != nullptr && !(opt & CASE_OPT_NO_FUSED_SELECT);
       case_select_args_t sel = select_args(a->mode, B, W, t, a->max_len, a->Tmax, a->BOS, a->EOS, a->UNK, a->PAD,
                                            a->top_vals, a->top_idx, a->live, a->cum, a->length, a->tok, a->anc, a->parent,
                                            a->ended, a->best_key, a->best_len, a->out_tokens, a->n_live);
@@ -462,6 +385,9 @@ extern "C" int gttp_decode_step(const gttp_step_args_t* a, int t, case_stream_t 
   const int R = a->R, B = a->B, W = a->W, TL = a->Tmax + 1, dt = a->dtype;
   const float* s_in = a->state[t & 1];
   float* s_out = a->state[(t + 1) & 1];
+  const int opt = a->opt;
+  OptScope scope(opt);
+  const int use_tail = (opt & CASE_OPT_UNFUSED_TAIL) ? 0 : 1;
 
   TRY(case_embed_rows(a->E, nullptr, a->tok, TL, t, 1.0f, a->emb, R, st));
   // two additive attentions with the previous GRU state as query (GTTP/Model.py:117-122)
@@ -515,7 +441,7 @@ extern "C" int gttp_decode_step(const gttp_step_args_t* a, int t, case_stream_t 
   }
   TRY(case_vocab_gemm(a->feat, a->Wv, a->bv, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, a->vocab_ws, st));
   TRY(case_gttp_gates(a->feat, a->wc, a->bc, a->gates, a->fac, CASE_MAX_SPLIT, ns[1], R, st));
-  if (g_use_tail && a->V <= case_row_tail_max_vocab()) {
+  if (use_tail && a->V <= case_row_tail_max_vocab()) {
     case_tail_args_t ta;
     memset(&ta, 0, sizeof(ta));
     ta.R = R; ta.V = a->V; ta.W = W; ta.K = W; ta.ldl = a->ldv; ta.ldd = a->ldv; ta.mask_col0 = 1; ta.nmem = 1;

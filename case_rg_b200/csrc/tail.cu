@@ -337,7 +337,7 @@ __global__ __launch_bounds__(TT) void row_tail_kernel(const case_tail_args_t a, 
 
 using namespace cb;
 
-static long long* g_tail_dbg = nullptr;
+static thread_local long long* g_tail_dbg = nullptr;   // debugging aid of the calling thread
 /* debugging aid (not part of the stable ABI): clock64() stamps of CTA 0 at the phase boundaries */
 extern "C" int case_debug_tail_timing(void* buf) { g_tail_dbg = (long long*)buf; return 0; }
 
@@ -363,17 +363,13 @@ extern "C" int case_row_tail(const case_tail_args_t* a, case_stream_t stream) {
   at[0].val.clusterDim.x = TCL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 2 : 1;
+  cfg.attrs = at; cfg.numAttrs = launch_opts().pdl ? 2 : 1;
   long long* dbg = g_tail_dbg;
   void* pa[] = {(void*)a, (void*)&Vq, (void*)&dbg};
 #define TAIL_LAUNCH(KK)                                                                                        \
   do {                                                                                                          \
-    static bool attr = false;                                                                                   \
-    if (!attr) {                                                                                                \
-      cudaFuncSetAttribute(row_tail_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);      \
-      attr = true;                                                                                              \
-    }                                                                                                           \
-    g_launch_err = cudaLaunchKernelExC(&cfg, (const void*)row_tail_kernel<KK>, pa);                            \
+    ensure_smem<row_tail_kernel<KK>>(200 * 1024); \
+    launch_err() = cudaLaunchKernelExC(&cfg, (const void*)row_tail_kernel<KK>, pa);                            \
   } while (0)
   if (K == 1) TAIL_LAUNCH(1);
   else if (K == 2) TAIL_LAUNCH(2);

@@ -95,7 +95,7 @@ __device__ __forceinline__ void xp_advance(XpPos& p, const int* tp, int B) {   /
 __global__ __launch_bounds__(XP_WARPS * 32) void cross_attn_part_kernel(
     const float* __restrict__ q2, const bf16* __restrict__ KV, const int32_t* __restrict__ ncount,
     const int32_t* __restrict__ tile_prefix, int B, int W, int ntile_all, int nslot, float* __restrict__ part_ml,
-    float* __restrict__ part_acc, const bf16* __restrict__ KVnext, int npf, int evict) {
+    float* __restrict__ part_acc, int evict) {
   const uint64_t pol = l2_stream_policy(evict);
   extern __shared__ __align__(128) unsigned char xp_smem[];   // [warp][XP_NS stages of K|V][barriers], then tp[B+1]
   int* tp = reinterpret_cast<int*>(xp_smem + (size_t)XP_WARPS * XP_WARP_BYTES);
@@ -256,17 +256,6 @@ __global__ __launch_bounds__(XP_WARPS * 32) void cross_attn_part_kernel(
     done += seg_n;
     for (int i = 0; i < seg_n; ++i) xp_advance(cp, tp, B);
   }
-  // The NEXT layer's launch walks the same partition over its own K|V stream: pull the tiles that fill this
-  // warp's ring there into L2 now, while HBM goes idle for the cluster launch in between
-  if (KVnext != nullptr && lane == 0) {
-    XpPos pp = xp_locate(tp, B, g_begin);
-    const int n = min(npf, my_tiles);
-    for (int i = 0; i < n; ++i) {
-      const char* src = reinterpret_cast<const char*>(KVnext) + ((size_t)(pp.b * NH + pp.head) * ntile_all + pp.tile) * XP_STAGE;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)XP_STAGE) : "memory");
-      xp_advance(pp, tp, B);
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------ prefill packing
@@ -302,26 +291,6 @@ __global__ __launch_bounds__(256) void pack_kv_gather_kernel(const bf16* __restr
 
 using namespace cb;
 
-static int g_xp_ctas = 0;   // 0 = one CTA per SM
-static const void* g_xp_next = nullptr;   // one-shot: K|V stream of the next layer's launch (case_cross_attn_part_next)
-static int g_xp_npf = 3;                  // tiles per warp to prefetch there (the ring depth)
-/* The NEXT case_cross_attn_part launch also prefetches into L2, as its warps finish, the first `ntiles` tiles of
- * every warp's range of the stream KVnext (same B, S, counts: the K|V of the next layer), so that the next
- * launch fills its rings from L2.  One-shot; ntiles <= 0 keeps the previous depth. */
-extern "C" int case_cross_attn_part_next(const void* KVnext, int ntiles) {
-  g_xp_next = KVnext;
-  if (ntiles > 0) g_xp_npf = ntiles;
-  return 0;
-}
-/* Grid of case_cross_attn_part: n CTAs (0 = one per SM, the default).  A smaller grid leaves SMs to kernels of
- * another stream (batch slices decoded concurrently: one slice streams K|V while the other is in its
- * latency-bound cluster launches); returns the old setting. */
-extern "C" int case_set_xattn_ctas(int n) {
-  const int old = g_xp_ctas;
-  g_xp_ctas = n < 0 ? 0 : n;
-  return old;
-}
-
 extern "C" int case_cross_attn_part_slots(int S) { return ((S + 63) / 64 + XP_MIN_TILES - 1) / XP_MIN_TILES + 2; }
 
 extern "C" int case_cross_attn_part(const float* q2, const void* KV, const int32_t* ncount, const int32_t* tile_prefix,
@@ -333,23 +302,14 @@ extern "C" int case_cross_attn_part(const float* q2, const void* KV, const int32
   CB_REQUIRE((uintptr_t)KV % 16 == 0, "case_cross_attn_part: KV must be 16-byte aligned");
   const size_t smem = (size_t)XP_WARPS * XP_WARP_BYTES + (size_t)(B + 1) * 4;
   CB_REQUIRE(smem <= 227 * 1024, "case_cross_attn_part: too many queries for the shared-memory prefix table");
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(cross_attn_part_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr = true;
-  }
-  static int nsm = 0;
-  if (nsm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    if (nsm <= 0) nsm = 148;
-  }
+  ensure_smem<cross_attn_part_kernel>(227 * 1024);
+  int dev = 0, nsm = 0;                                  // persistent grid: one CTA per SM of the CURRENT device
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  if (nsm <= 0) nsm = 148;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = g_xp_ctas > 0 && g_xp_ctas < nsm ? g_xp_ctas : nsm;
-  launch_k(cross_attn_part_kernel, grid, XP_WARPS * 32, smem, st, q2, (const bf16*)KV, ncount, tile_prefix, B, W,
-           (S + 63) / 64, nslot, part_ml, part_acc, (const bf16*)g_xp_next, g_xp_npf, g_evict_first);
-  g_xp_next = nullptr;
+  launch_k(cross_attn_part_kernel, nsm, XP_WARPS * 32, smem, st, q2, (const bf16*)KV, ncount, tile_prefix, B, W,
+           (S + 63) / 64, nslot, part_ml, part_acc, launch_opts().evict_first);
   return check_launch("case_cross_attn_part");
 }
 

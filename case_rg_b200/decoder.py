@@ -66,8 +66,10 @@ class FastCaSEDecoder(nn.Module):
     """Parameter container with the reference's state_dict layout + the CUDA decode path."""
 
     def __init__(self, num_memories, num_layers, nhead, tgt_vocab_size, hidden_size, emb_matrix=None,
-                 beam_width: int = 1, dtype: str = 'bf16', vocab_impl: Optional[int] = None, use_graph: bool = True):
+                 beam_width: int = 1, dtype: str = 'bf16', vocab_impl: Optional[int] = None, use_graph: bool = True,
+                 opt: int = 0):
         super().__init__()
+        self.opt = int(opt)                   # CASE_OPT_* bits of the engines (0 = default fast path)
         if (num_memories, num_layers, nhead, hidden_size) != (2, 4, 8, L.H):
             raise ValueError('FastCaSEDecoder is built for the shipped configuration: num_memories=2, '
                              f'num_layers=4, nhead=8, hidden_size={L.H} (CaSE/Model.py:265, Run.py:71)')
@@ -119,12 +121,12 @@ class FastCaSEDecoder(nn.Module):
         return self._weights
 
     def engine_for(self, B, W, S0, S1, T, device) -> CaseDecodeEngine:
-        key = (B, W, S0, S1, T, str(device), self.dtype, self.vocab_impl)
+        key = (B, W, S0, S1, T, str(device), self.dtype, self.vocab_impl, self.opt)
         e = self._engines.get(key)
         if e is None:
             if len(self._engines) >= 4:       # shapes are few in practice (full batches + one tail batch)
                 self._engines.clear()
-            e = CaseDecodeEngine(self._packed(device), B, W, S0, S1, T, vocab_impl=self.vocab_impl)
+            e = CaseDecodeEngine(self._packed(device), B, W, S0, S1, T, vocab_impl=self.vocab_impl, opt=self.opt)
             self._engines[key] = e
         return e
 
@@ -241,4 +243,36 @@ def install_fast_decoder(model: nn.Module, beam_width: int = 1, dtype: str = 'bf
 
     model.forward = types.MethodType(forward, model)
     model._reference_decoder = [ref_dec]     # list: keeps it out of the module tree / state_dict
+    return model
+
+
+def install_fast_gttp(model: nn.Module, dtype: str = 'bf16', **kw) -> nn.Module:
+    """Swap the step side of a reference ``GTTP`` model (GTTP/Model.py:133-212) for the CUDA path, in place.
+
+    ``model.forward(data, 'test')`` keeps its contract (``{'answer': LongTensor}``, greedy for ``beam_width == 1``, else
+    beam; GTTP/Model.py:204-212) but
+      * ``data['background_map']`` stays in its int64 index form - ``build_map`` (Utils.py:344-355) is not called;
+      * the bi-GRU encoders and ``enc2dec`` (``encode`` / ``init_decoder_states``, Model.py:156-174) run as the reference
+        wrote them - they are outside the hot path - and their outputs feed the device search;
+      * ``decode`` / ``generate`` / ``to_word`` + ``Generations.greedy/beam`` (Model.py:176-193, Generations.py:66-190) are
+        replaced by ``FastGTTP.fast_search`` (gttp_decode_step x max_dec_len in one CUDA graph).
+    Training (``method='train'``) goes through the original forward."""
+    from .generations import FastGTTP
+    sd = {k: v for k, v in model.state_dict().items() if k.startswith('dec.') or k.startswith('gen.')}
+    dev = next(model.parameters()).device
+    fast = FastGTTP(sd, device=dev, dtype=dtype, max_dec_len=model.max_dec_len, beam_width=model.beam_width, **kw)
+    orig_forward = model.forward
+
+    def forward(self, data, method='train'):
+        if method != 'test':
+            return orig_forward(data, method=method)
+        enc = self.encode(data)                                   # (c_enc_output, c_state, b_enc_output, b_state)
+        init = self.init_decoder_states(data, enc)                # [B, 1, H]
+        d = dict(context=data['context'], background=data['background'], background_map=data['background_map'],
+                 src_output=enc[0], bg_output=enc[2], init_state=init)
+        mode = L.MODE_PROTO_GREEDY if self.beam_width == 1 else L.MODE_BEAM
+        return {'answer': fast.fast_search(d, self.max_dec_len, self.beam_width, mode)}
+
+    model.forward = types.MethodType(forward, model)
+    model._fast_gttp = [fast]            # list: keeps it out of the module tree / state_dict
     return model

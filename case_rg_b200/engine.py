@@ -26,7 +26,43 @@ PAD, BOS, EOS, UNK = 0, 1, 2, 100
 def _require_cuda(device):
     if not torch.cuda.is_available():
         raise RuntimeError('case_rg_b200 needs a CUDA device: the decode path has no CPU fallback')
-    return torch.device(device if device is not None else 'cuda')
+    dev = torch.device(device if device is not None else 'cuda')
+    if dev.type != 'cuda':
+        raise RuntimeError(f'case_rg_b200 needs a CUDA device, got {dev}: the decode path has no CPU fallback')
+    if dev.index is None:
+        dev = torch.device('cuda', torch.cuda.current_device())
+    return dev
+
+
+class _on_device:
+    """The C launchers work on the calling thread's CURRENT device (include/case_b200.h): every engine entry point
+    runs under its own device, so an engine built for cuda:1 is usable whatever the caller's current device is."""
+
+    def __init__(self, dev):
+        self.guard = torch.cuda.device(dev)
+
+    def __enter__(self):
+        return self.guard.__enter__()
+
+    def __exit__(self, *a):
+        return self.guard.__exit__(*a)
+
+
+class _Fork:
+    """Owner of a case_fork_t (side stream + events of the step's fork/join) on one device."""
+
+    def __init__(self, dev):
+        self.h = C.c_void_p()
+        with torch.cuda.device(dev):
+            L.check(L.load().case_fork_create(C.byref(self.h)), 'case_fork_create')
+
+    def __del__(self):
+        try:
+            if self.h:
+                L.load().case_fork_destroy(self.h)
+                self.h = C.c_void_p()
+        except Exception:
+            pass
 
 
 def _storage(dtype: str):
@@ -260,7 +296,6 @@ class CaseWeights:
         self.Wv = g('gen.2.weight').contiguous().to(self.tdtype)                               # [V][H]
         self.Wv_tc = pack_vocab_tc(g('gen.2.weight')) if self.cdtype == L.BF16 else None
         self.Wm, self.bm = g('mix.weight').contiguous(), vec(g('mix.bias'))
-        self.Uk_t16 = [g(f'attns.{i}.linear_key.weight').t().contiguous().to(torch.float16) for i in range(2)]
         # gate form (CaSE/Model.py:39,117): W_m's slice for context i as a [H][4] projection of the memory keys
         self.Wm_g = [self.Wm[:, H * (1 + i):H * (2 + i)].contiguous() for i in range(2)]          # [3][H] each
 
@@ -308,21 +343,29 @@ class _SearchState:
 
 
 class _EngineBase:
+    def set_options(self, opt: int):
+        """CASE_OPT_* bits of this engine's step calls (0 = the default fast path); drops captured graphs."""
+        if int(opt) != int(self.args.opt):
+            self.args.opt = int(opt)
+            self._graphs.clear()
+
     def _run_steps(self, max_len: int):
-        stream = torch.cuda.current_stream(self.device)
-        for t in range(max_len):
-            L.check(self._step_fn(C.byref(self.args), t, stream.cuda_stream), self._step_name)
+        with _on_device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            for t in range(max_len):
+                L.check(self._step_fn(C.byref(self.args), t, stream.cuda_stream), self._step_name)
 
     def _capture(self, max_len, mode):
         """Capture all ``max_len`` steps into one CUDA graph (t is a by-value kernel argument)."""
-        stream = torch.cuda.current_stream(self.device)
-        L.check(self._step_fn(C.byref(self.args), 0, stream.cuda_stream), self._step_name)   # warm-up, not captured
-        torch.cuda.synchronize(self.device)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            cs = torch.cuda.current_stream(self.device)
-            for t in range(max_len):
-                L.check(self._step_fn(C.byref(self.args), t, cs.cuda_stream), self._step_name)
+        with _on_device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            L.check(self._step_fn(C.byref(self.args), 0, stream.cuda_stream), self._step_name)   # warm-up, not captured
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                cs = torch.cuda.current_stream(self.device)
+                for t in range(max_len):
+                    L.check(self._step_fn(C.byref(self.args), t, cs.cuda_stream), self._step_name)
         self._graphs[(max_len, mode)] = g
 
     def _finish_tokens(self, max_len: int, mode: int) -> torch.Tensor:
@@ -339,7 +382,9 @@ class CaseDecodeEngine(_EngineBase):
     """All buffers + the step argument block for one CaSE problem shape."""
 
     def __init__(self, weights: CaseWeights, B: int, W: int, S0: int, S1: int, Tmax: int = 40,
-                 fast_tanh: Optional[bool] = None, vocab_impl: Optional[int] = None, target_ctas: int = 296):
+                 fast_tanh: Optional[bool] = None, vocab_impl: Optional[int] = None, target_ctas: int = 296,
+                 opt: int = 0):
+        self.opt = int(opt)
         if not (1 <= W <= L.MAX_W):
             raise ValueError(f'beam width must be 1..{L.MAX_W}')
         if not (1 <= Tmax <= L.MAX_T):
@@ -377,9 +422,6 @@ class CaseDecodeEngine(_EngineBase):
         self.Mv = [torch.zeros(B, s, H, dtype=td, device=dev) for s in self.S]
         # gate-projected keys for the search path (case_additive_attn_gate): 3 gate logits' worth per key
         self.Gv = [z(B, s, 4) for s in self.S] if weights.cdtype == L.BF16 else None
-        # f16 copies of Uk.mem for the tensor-core form of the gate kernel (W >= 2, approximate tanh)
-        self.U16 = ([torch.zeros(B, s, H, dtype=torch.float16, device=dev) for s in self.S]
-                    if self.Gv is not None and W >= 2 and self.fast_tanh and L.load().case_set_gate_f16(-1) else None)
         self.mask = [torch.zeros(B, s, dtype=torch.uint8, device=dev) for s in self.S]
         self.prior = [z(B, s) for s in self.S]
         self.map = torch.zeros(B, S0 + S1, dtype=torch.int32, device=dev)
@@ -438,11 +480,13 @@ class CaseDecodeEngine(_EngineBase):
         self._graphs = {}
         self._step_fn = L.load().case_decode_step
         self._step_name = 'case_decode_step'
+        self._fork = _Fork(dev)               # side stream + events of this engine's fork/join (per engine, per device)
         self._fill_args()
 
     def _fill_args(self):
         a = self.args = L.StepArgs()
         w = self.w
+        a.opt, a.fork = self.opt, self._fork.h
         a.B, a.W, a.R, a.V, a.ldv, a.Tmax = self.B, self.W, self.R, self.V, self.ldv, self.Tmax
         a.dtype, a.fast_tanh, a.vocab_impl, a.mode = w.cdtype, self.fast_tanh, self.vocab_impl, L.MODE_MODULE_GREEDY
         for i in range(2):
@@ -455,8 +499,6 @@ class CaseDecodeEngine(_EngineBase):
             a.ctx[i] = self.ctx[i].data_ptr()
             if self.Gv is not None:
                 a.Gv[i] = self.Gv[i].data_ptr()
-            if self.U16 is not None:
-                a.U16[i] = self.U16[i].data_ptr()
         a.map_off[0], a.map_off[1] = 0, self.S[0]
         a.max_len, a.BOS, a.EOS, a.UNK, a.PAD, a.materialize_only = self.Tmax, BOS, EOS, UNK, PAD, 0
         a.E, a.pe = w.E.data_ptr(), w.pe.data_ptr()
@@ -489,7 +531,11 @@ class CaseDecodeEngine(_EngineBase):
 
     # ------------------------------------------------------------------ per batch
     @torch.no_grad()
-    def prefill(self, mem_q, mem_p, mask_q, mask_p, prior_q, prior_p, answer_rep, source_map):
+    def prefill(self, *tensors):
+        with _on_device(self.device):
+            return self._prefill(*tensors)
+
+    def _prefill(self, mem_q, mem_p, mask_q, mask_p, prior_q, prior_p, answer_rep, source_map):
         """Once per batch: flatten (Model.py:56-58), norm2(answer_rep) (:98), and everything the
         reference recomputes every step although it never changes - the cross-attention K/V
         projections of both memories for all 8 layers (TransformerDecoder.py:81) and Uk.mem
@@ -536,21 +582,17 @@ class CaseDecodeEngine(_EngineBase):
                 for l in range(4):
                     self.Kx[i * 4 + l].copy_(kv[l, 0])
                     self.Vx[i * 4 + l].copy_(kv[l, 1])
-            lib = L.load()
-            lazy = self.Gv is not None and bool(lib.case_set_gate_form(-1))      # the search path reads G (and U16) only
-            use16 = lazy and self.U16 is not None and bool(lib.case_set_gate_f16(-1))
-            if fused:       # K|V tiles of the 4 layers (+ U unless the f16 experiment wants its own copy) in one launch
+            lazy = self.Gv is not None and not (self.args.opt & L.OPT_NO_GATE)   # the search path reads G only
+            if fused:       # K|V tiles of the 4 layers + U in one launch
                 L.call('case_prefill_project_tc', flat.data_ptr(), w.Wpf[i].data_ptr(), w.pf_bias[i].data_ptr(), B, S,
-                       cidx, ncount, 4, outs, None if use16 else self.U[i].data_ptr(), stream)
-            if use16:
-                torch.mm(mems[i].to(dev, torch.float16).reshape(B * S, H), w.Uk_t16[i], out=self.U16[i].view(B * S, H))
-            elif not fused:
+                       cidx, ncount, 4, outs, self.U[i].data_ptr(), stream)
+            else:
                 torch.mm(flat, w.Uk_t[i], out=self.U[i].view(B * S, H))
             if not lazy:
                 self.Mv[i].copy_(m)
                 self._mv_src[i] = None
             else:                   # the search path reads G instead; the value rows are filled when the `generate` face asks
-                self._mv_src[i] = (m, use16)
+                self._mv_src[i] = m
                 L.call('case_gate_project', flat.data_ptr(), w.Wm_g[i].data_ptr(), self.Gv[i].data_ptr(), B * S, stream)
             self.mask[i].copy_(masks[i].to(dev).to(torch.uint8))
             self.prior[i].copy_(priors[i].to(dev, torch.float32))
@@ -597,14 +639,12 @@ class CaseDecodeEngine(_EngineBase):
         [R, V] of it (no top-k / select); the caller drives tok/anc through ``state``."""
         for i in range(2):
             if self._mv_src[i] is not None:
-                m, need_u = self._mv_src[i]
-                self.Mv[i].copy_(m.view_as(self.Mv[i]))
-                if need_u:          # the bf16 Uk.mem of the context-form kernels was skipped at prefill
-                    torch.mm(m.reshape(-1, L.H), self.w.Uk_t[i], out=self.U[i].view(-1, L.H))
+                self.Mv[i].copy_(self._mv_src[i].view_as(self.Mv[i]))
                 self._mv_src[i] = None
         self.args.materialize_only = 1
-        stream = torch.cuda.current_stream(self.device)
-        L.check(self._step_fn(C.byref(self.args), t, stream.cuda_stream), self._step_name)
+        with _on_device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            L.check(self._step_fn(C.byref(self.args), t, stream.cuda_stream), self._step_name)
         self.args.materialize_only = 0
         return self.dist[:, :self.V]
 
@@ -615,7 +655,7 @@ class CaseDecodeEngine(_EngineBase):
         # (+1 in bench.py: the activation re-pack inside the vocabulary GEMM call)
         lib = L.load()
         tail = 2                       # vocab_base + sparse_tail (search bookkeeping fused into it)
-        if self.w.cdtype == L.BF16 and self.Tmax <= lib.case_layer_chain_max_tmax():
+        if self.w.cdtype == L.BF16 and self.Tmax <= lib.case_layer_chain_max_tmax() and not (self.args.opt & L.OPT_NO_CHAIN):
             # attention queries, norm1 and gen.0 ride on the cluster launches (post linears): no row_linear launches
             if self.S[0] <= lib.case_layer_chain_max_s0():
                 # layer_stack (first stack + front 4) + 4 x cross + 4 x layer_chain + 2 x additive + vocab + tail
@@ -624,65 +664,6 @@ class CaseDecodeEngine(_EngineBase):
             return 9 + 8 + 2 + 1 + tail
         # embed + 8 x (front, cross, back) + 2 x (row_linear, additive) + norm1 + gen.0 + vocab + tail
         return 1 + 24 + 4 + 1 + 1 + 1 + tail
-
-
-class CaseEngineGroup:
-    """Several CaSE engines over contiguous slices of one batch, decoded CONCURRENTLY on their own
-    streams.  Queries are independent (Generations.py:163-180 groups hypotheses by query), so a batch
-    can be cut anywhere; while one slice is in the latency-bound part of a step (the layer chain, the
-    vocabulary tail) the other streams K/V from HBM, which is what fills the machine at decode sizes.
-    Same prefill / decode interface as ``CaseDecodeEngine``."""
-
-    def __init__(self, weights: CaseWeights, B: int, W: int, S0: int, S1: int, Tmax: int = 40, parts: int = 2, **kw):
-        parts = max(1, min(parts, B))
-        sizes = [B // parts + (1 if i < B % parts else 0) for i in range(parts)]
-        self.bounds = [0]
-        for n in sizes:
-            self.bounds.append(self.bounds[-1] + n)
-        self.subs = [CaseDecodeEngine(weights, n, W, S0, S1, Tmax, **kw) for n in sizes]
-        self.device, self.w = weights.device, weights
-        self.B, self.W, self.R, self.S, self.Tmax, self.V = B, W, B * W, (S0, S1), Tmax, weights.V
-        self.streams = [torch.cuda.Stream(self.device) for _ in self.subs]
-
-    def _cut(self, x, i):
-        return x[self.bounds[i]:self.bounds[i + 1]]
-
-    @torch.no_grad()
-    def prefill(self, *tensors):
-        for i, sub in enumerate(self.subs):
-            sub.prefill(*[self._cut(x, i) for x in tensors])
-
-    @torch.no_grad()
-    def decode(self, max_len: int, mode: int = L.MODE_MODULE_GREEDY, use_graph: bool = True) -> torch.Tensor:
-        if mode != L.MODE_BEAM and self.W != 1:
-            raise ValueError('greedy modes need an engine built with W == 1')
-        self.launch(max_len, mode, use_graph)
-        return self._finish_tokens(max_len, mode)
-
-    @torch.no_grad()
-    def launch(self, max_len: int, mode: int = L.MODE_MODULE_GREEDY, use_graph: bool = True) -> None:
-        for sub in self.subs:                      # captures (host-synchronous) happen before anything runs
-            sub.ensure_graph(max_len, mode, use_graph)
-        main = torch.cuda.current_stream(self.device)
-        for sub, st in zip(self.subs, self.streams):
-            st.wait_stream(main)
-            with torch.cuda.stream(st):
-                sub.launch(max_len, mode, use_graph)
-        for st in self.streams:
-            main.wait_stream(st)
-
-    def _finish_tokens(self, max_len: int, mode: int) -> torch.Tensor:
-        out = torch.cat([sub.state.out_tokens[:, :max_len] for sub in self.subs]).to(torch.int64)
-        if mode == L.MODE_BEAM:                    # merge1D (Utils.py:366-377): pad to the longest answer of the batch
-            Lmax = int(torch.stack([sub.state.best_len.max() for sub in self.subs]).max().item())
-            out = out[:, :max(Lmax, 1)]
-        return out
-
-    def answer_tokens(self) -> int:
-        return int(sum(int(sub.state.best_len.sum().item()) for sub in self.subs))
-
-    def kernel_launches_per_step(self) -> int:
-        return sum(sub.kernel_launches_per_step() for sub in self.subs)
 
 
 class GttpWeights:
@@ -714,7 +695,8 @@ class GttpWeights:
 
 class GttpDecodeEngine(_EngineBase):
     def __init__(self, weights: GttpWeights, B: int, W: int, Lc: int, Lb: int, Tmax: int = 40,
-                 fast_tanh: Optional[bool] = None, vocab_impl: Optional[int] = None, target_ctas: int = 296):
+                 fast_tanh: Optional[bool] = None, vocab_impl: Optional[int] = None, target_ctas: int = 296,
+                 opt: int = 0):
         if not (1 <= W <= L.MAX_W):
             raise ValueError(f'beam width must be 1..{L.MAX_W}')
         self.w = weights
@@ -754,6 +736,7 @@ class GttpDecodeEngine(_EngineBase):
         a = self.args = L.GttpStepArgs()
         w = weights
         a.B, a.W, a.R, a.V, a.ldv, a.dtype = B, W, R, V, self.ldv, w.cdtype
+        a.opt = int(opt)
         a.fast_tanh, a.vocab_impl, a.mode = self.fast_tanh, self.vocab_impl, L.MODE_PROTO_GREEDY
         a.Lc, a.Lb, a.nsplit_c, a.nsplit_b = Lc, Lb, self.ns[0], self.ns[1]
         a.max_len, a.BOS, a.EOS, a.UNK, a.PAD, a.materialize_only, a.Tmax = Tmax, BOS, EOS, UNK, PAD, 0, Tmax

@@ -17,7 +17,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib as L
-from .engine import CaseDecodeEngine, CaseEngineGroup, CaseWeights, GttpDecodeEngine, GttpWeights
+from .engine import CaseDecodeEngine, CaseWeights, GttpDecodeEngine, GttpWeights
 
 PAD_WORD, BOS_WORD, UNK_WORD, EOS_WORD = '[PAD]', '[unused0]', '[UNK]', '[unused1]'
 
@@ -93,24 +93,20 @@ class FastCaSE(_FastModel):
     'prior_q', 'prior_p', 'answer_rep' [B,H], 'source_map' int64 [B,S]."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device=None, dtype='bf16', max_dec_len=40,
-                 beam_width=1, vocab_impl: Optional[int] = None, use_graph=True, prefix='', streams: int = 1):
-        """streams > 1: the batch is cut into that many slices decoded concurrently on their own CUDA
-        streams (CaseEngineGroup) - worthwhile from about 128 decode rows (B * W) up."""
+                 beam_width=1, vocab_impl: Optional[int] = None, use_graph=True, prefix='', opt: int = 0):
+        """opt: CASE_OPT_* bits for every engine of this model (0 = the default fast path; A/B and fallback tests)."""
         self.weights = CaseWeights(state_dict, device=device, dtype=dtype, prefix=prefix)
         self.max_dec_len, self.beam_width, self.vocab_impl, self.use_graph = max_dec_len, beam_width, vocab_impl, use_graph
-        self.streams = int(streams)
+        self.opt = int(opt)
         self._engines = {}
 
-    def engine_for(self, B, W, S0, S1, T, streams: int = 1):
-        key = (B, W, S0, S1, T, streams)
+    def engine_for(self, B, W, S0, S1, T):
+        key = (B, W, S0, S1, T, self.opt)
         if key not in self._engines:
             if len(self._engines) >= 4:
                 self._engines.clear()
-            if streams > 1 and B >= streams:
-                self._engines[key] = CaseEngineGroup(self.weights, B, W, S0, S1, T, parts=streams,
-                                                     vocab_impl=self.vocab_impl)
-            else:
-                self._engines[key] = CaseDecodeEngine(self.weights, B, W, S0, S1, T, vocab_impl=self.vocab_impl)
+            self._engines[key] = CaseDecodeEngine(self.weights, B, W, S0, S1, T, vocab_impl=self.vocab_impl,
+                                                  opt=self.opt)
         return self._engines[key]
 
     def encode(self, data):
@@ -121,7 +117,7 @@ class FastCaSE(_FastModel):
         B = d['source_map'].size(0)
         S0 = d['mem_q'].reshape(B, -1, L.H).size(1)
         S1 = d['mem_p'].reshape(B, -1, L.H).size(1)
-        eng = self.engine_for(B, width, S0, S1, max_len, self.streams)
+        eng = self.engine_for(B, width, S0, S1, max_len)
         eng.prefill(d['mem_q'], d['mem_p'], d['query'].ne(0), d['passage'].ne(0), d['prior_q'], d['prior_p'],
                     d['answer_rep'], d['source_map'])
         self.last_engine = eng
@@ -168,7 +164,7 @@ class FastCaSE(_FastModel):
             B = d['source_map'].size(0)
             S0 = d['mem_q'].reshape(B, -1, L.H).size(1)
             S1 = d['mem_p'].reshape(B, -1, L.H).size(1)
-            eng = self.engine_for(B, width, S0, S1, max_len, self.streams)
+            eng = self.engine_for(B, width, S0, S1, max_len)
             # stream order: decode(i-1) -> prefill(i); the host enqueues prefill(i) while decode(i-1) runs.
             # (prefill never touches the search state the pending answers are read from)
             main.wait_event(ready)
@@ -181,7 +177,7 @@ class FastCaSE(_FastModel):
                 ready = stage(k ^ 1, nxt)
             if mode != L.MODE_BEAM and eng.W != 1:
                 raise ValueError('greedy modes need an engine built with W == 1')
-            if pending is not None and not hasattr(pending, 'subs'):
+            if pending is not None:
                 # answers of the previous batch: snapshot them on the device (stream-ordered after its decode), put
                 # THIS batch's decode behind the snapshot right away, and only then wait for the snapshot on a side
                 # stream - the device never idles while the host reads answers
@@ -191,8 +187,6 @@ class FastCaSE(_FastModel):
                 eng.launch(max_len, mode, use_graph=self.use_graph)
                 yield self._read_snapshot(snap, ev, mode)
             else:
-                if pending is not None:     # sliced engines: answers of the previous batch (host sync), then reuse the state
-                    yield pending._finish_tokens(max_len, mode).cpu()
                 eng.launch(max_len, mode, use_graph=self.use_graph)
             self.last_engine = pending = eng
             k ^= 1
@@ -226,9 +220,10 @@ class FastGTTP(_FastModel):
     'src_output' [B,Lc,2H], 'bg_output' [B,Lb,2H], 'init_state' [B,1,H] (GTTP/Model.py:156-174)."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device=None, dtype='bf16', max_dec_len=40,
-                 beam_width=1, vocab_impl: Optional[int] = None, use_graph=True, prefix=''):
+                 beam_width=1, vocab_impl: Optional[int] = None, use_graph=True, prefix='', opt: int = 0):
         self.weights = GttpWeights(state_dict, device=device, dtype=dtype, prefix=prefix)
         self.max_dec_len, self.beam_width, self.vocab_impl, self.use_graph = max_dec_len, beam_width, vocab_impl, use_graph
+        self.opt = int(opt)
         self._engines = {}
 
     def engine_for(self, B, W, Lc, Lb, T):
@@ -236,7 +231,8 @@ class FastGTTP(_FastModel):
         if key not in self._engines:
             if len(self._engines) >= 4:
                 self._engines.clear()
-            self._engines[key] = GttpDecodeEngine(self.weights, B, W, Lc, Lb, T, vocab_impl=self.vocab_impl)
+            self._engines[key] = GttpDecodeEngine(self.weights, B, W, Lc, Lb, T, vocab_impl=self.vocab_impl,
+                                                  opt=self.opt)
         return self._engines[key]
 
     def fast_search(self, data, max_len, width, mode, encode_outputs=None, init_decoder_states=None):

@@ -13,6 +13,8 @@
  *  - launch-only: functions enqueue work on `stream` and return immediately (no sync);
  *  - return value: 0 on success, otherwise a cudaError_t (or CASE_EINVAL for bad arguments);
  *    case_last_error() gives a static message for the calling thread;
+ *  - no process-global state: launchers are re-entrant and work on the calling thread's CURRENT device; per-kernel
+ *    device attributes are set up per device on first use;
  *  - `dtype` selects the storage type of caches and weight matrices: CASE_F32 or CASE_BF16.
  *    Activations, softmax statistics and distributions are always fp32;
  *  - hidden size is fixed at 256 with 8 heads of 32 (CaSE/Model.py:261-265, Run.py:71);
@@ -53,60 +55,36 @@ const char* case_last_error(void);
  * 2 case_layer_weights_t, 3 case_select_args_t, 4 case_step_args_t, 5 gttp_step_args_t, 6 case_tail_args_t,
  * 7 case_chain_post_t */
 size_t case_struct_size(int which);
-/* Programmatic dependent launch for every kernel of a step (default on); returns the old setting. */
-int case_set_pdl(int on);
-/* Cluster layer kernels (case_layer_chain) in case_decode_step for bf16 storage (default on; 0 = the
- * row-block kernels case_layer_front / case_layer_back); returns the old setting. */
-int case_set_chain(int on);
-/* Fuse the first stack (short memory, S0 <= 64) into one case_layer_stack launch (default on). */
-int case_set_stack_fusion(int on);
-/* Fork/join of the additive attentions onto a library-owned side stream inside case_decode_step
- * (cluster path only; default on); returns the old setting. */
-int case_set_fork(int on);
-/* Tail of the step orchestrators: 0 = finalize + softmax_mix + copy_scatter + topk_rows, 1 = case_row_tail,
- * 2 (default) = case_vocab_base + case_sparse_tail where the scratch buffers are given, else 1; returns
- * the old setting. */
-int case_set_fused_tail(int on);
-/* Search bookkeeping inside the sparse tail launch instead of a case_beam_select launch (default on). */
-int case_set_fused_select(int on);
-/* Attention-query linears, norm1 and gen.0 as post linears of the cluster launches instead of
- * case_row_linear / case_layernorm_rows launches (default on; needs Wqa_c / Wg_c in the step arguments). */
-int case_set_post_linears(int on);
-/* Gate form of the additive attentions on the search path (default on; needs Gv in the step arguments, bf16
- * and the sparse tail): case_additive_attn_gate instead of case_additive_attn[_compact].  Returns the old
- * setting; a negative argument only queries. */
-int case_set_gate_form(int on);
-/* The NEXT case_cross_attn_part launch also prefetches into L2, as its warps finish, the first `ntiles` tiles
- * of every warp's range of the stream KVnext (the next layer's K|V: same B, S, counts), so that launch fills its
- * rings from L2 while HBM was idle anyway.  One-shot; ntiles <= 0 keeps the previous depth (default 3). */
-int case_cross_attn_part_next(const void* KVnext, int ntiles);
-/* L2 evict-first policy on the streams a step reads once and that exceed L2 (cross-attention K|V of case_cross_attn_part,
- * Uk.mem of case_additive_attn_gate), so they do not push the layer weights, the vocabulary weight and the logits tile
- * out of L2 between steps (default on); returns the old setting, a negative argument only queries. */
-int case_set_stream_evict_first(int on);
-/* L2 warm-up for the next step's fused-stack launch, issued on the side stream behind the passage additive attention
- * (bit 0: layer weights + query-memory K|V tiles of layers 0..3, bit 1: their self-attention history).  Experiment,
- * default 0: measured slower at the BASELINE shape;
- * returns the old mask, a negative argument only queries. */
-int case_set_next_step_prefetch(int mask);
-/* Sparse tail from the copy plan, when the step arguments carry one (default on; the engine builds a plan only
- * with CASE_COPY_PLAN=1: measured neutral at the BASELINE shape), instead of the shared-memory hash table;
- * returns the old setting, a negative argument only queries. */
-int case_set_copy_plan(int on);
-/* f16 / tensor-core form of the gate kernel (case_additive_attn_gate_h) when the step arguments carry U16, W >= 2
- * and fast_tanh.  Default OFF: on sm_100a tanh.approx.f16x2 is two MUFU.TANH.F16 plus a PRMT, so the MUFU count
- * does not drop and the kernel measures 56 us against 47 us at the BASELINE shape (kept as an experiment; its
- * f16 Uk.mem is the more accurate storage).  Returns the old setting, a negative argument only queries. */
-int case_set_gate_f16(int on);
-/* Tiles per warp that case_decode_step asks the passage cross-attention of layer L to prefetch for layer L+1
- * (default 0 = off: measured neutral at the BASELINE shape, the launch is bound by its fixed cost); returns the old setting. */
-int case_set_xattn_next_prefetch(int ntiles);
-/* Grid of case_cross_attn_part: n CTAs instead of one per SM (0 = default).  For batch slices decoded
- * concurrently on several streams: a smaller grid leaves SMs to the other slice's cluster launches. */
-int case_set_xattn_ctas(int n);
-/* Percentage of the next cross-attention's K|V stream that the preceding cluster launch prefetches into L2
- * (default 0 = off: measured neutral-to-negative at the BASELINE shape, kept as an experiment switch). */
-int case_set_kv_prefetch(int pct);
+
+/* ---------------------------------------------------------------- options and per-engine handles
+ * The library keeps NO process-global state: every launcher is re-entrant, two engines on two host threads (or two
+ * devices) never see each other.  What used to be library switches are bits of an option word carried by the step
+ * argument blocks (case_step_args_t.opt / gttp_step_args_t.opt); 0 = the default fast path, a set bit switches one
+ * feature OFF (A/B measurements, fallbacks under test). */
+#define CASE_OPT_NO_PDL 0x001          /* no programmatic dependent launch attribute on the kernels                 */
+#define CASE_OPT_NO_CHAIN 0x002        /* bf16: row-block layer kernels (case_layer_front / _back) instead of the
+                                          cluster kernels (case_layer_chain / case_layer_stack)                      */
+#define CASE_OPT_NO_STACK 0x004        /* no fusion of the first stack into one case_layer_stack launch              */
+#define CASE_OPT_NO_FORK 0x008         /* additive attentions on the main stream even when a fork handle is given    */
+#define CASE_OPT_NO_POST 0x010         /* attention queries / norm1 / gen.0 as own launches, not as post linears     */
+#define CASE_OPT_NO_GATE 0x020         /* context form of the additive attentions on the search path                 */
+#define CASE_OPT_NO_EVICT_FIRST 0x040  /* no L2 evict-first policy on the once-per-step K|V / Uk.mem streams         */
+#define CASE_OPT_DENSE_TAIL 0x080      /* case_row_tail instead of case_vocab_base + case_sparse_tail                */
+#define CASE_OPT_UNFUSED_TAIL 0x100    /* finalize + softmax_mix + copy_scatter + topk_rows launches                 */
+#define CASE_OPT_NO_FUSED_SELECT 0x200 /* case_beam_select as its own launch                                         */
+#define CASE_OPT_NO_COPY_PLAN 0x400    /* ignore a copy plan in the step arguments (hash-table sparse tail)          */
+
+/* Options of the CALLING THREAD for direct launcher calls (only CASE_OPT_NO_PDL and CASE_OPT_NO_EVICT_FIRST apply
+ * to single launchers); returns the previous word, a negative argument only queries.  The step orchestrators ignore
+ * this and use the option word of their argument block. */
+int case_thread_options(int opt);
+
+/* Side stream + events for the fork/join inside case_decode_step (the additive attentions run beside the layer
+ * stack / the vocabulary GEMM).  Created on the CURRENT device, owned by the caller - one per engine - and passed in
+ * case_step_args_t.fork (NULL = no fork).  The only host objects the library ever creates. */
+typedef struct case_fork_s case_fork_t;
+int case_fork_create(case_fork_t** out);
+int case_fork_destroy(case_fork_t* f);
 
 /* ---------------------------------------------------------------- row-wise building blocks */
 
@@ -292,10 +270,6 @@ int case_layer_stack(const case_layer_weights_t* layers, int nfused, void* const
                      int anc_ld, const int32_t* tok, int tok_ld, int32_t* prow, int t, int Tmax, float* b_out,
                      float* q2_out, int R, int first, const case_chain_post_t* post, case_stream_t stream);
 int case_layer_chain_max_s0(void);
-/* The NEXT case_layer_chain / case_layer_stack launch also prefetches into L2 `pct` percent of every
- * (query, head) run of the compacted K|V stream KV (tile_prefix as in case_cross_attn_part) that the
- * cross-attention launched after it will read: HBM is idle while the cluster kernels run.  One-shot. */
-int case_layer_chain_prefetch(const void* KV, const int32_t* tile_prefix, int B, int S, int pct);
 
 /* ---------------------------------------------------------------- additive ("bilinear") attention */
 
@@ -335,25 +309,12 @@ int case_additive_attn_gate(const float* qa, const void* U, const float* G, cons
                             const int32_t* cidx, const int32_t* ncount, const int32_t* qorder, const int32_t* nsq,
                             case_stream_t stream);
 
-/* case_additive_attn_gate with Uk.mem stored in f16 (U f16 [B][S][H]), for 2 <= W <= 8: packed f16 additions and
- * tanh.approx.f16x2 (always the approximate tanh), and the v-weighted sum over the hidden units on the tensor
- * core (mma.m16n8k16, the tanh values as produced are the A fragment, B = v; fp32 accumulation): no butterfly,
- * no FFMA, 4.9 instead of 6.2 instructions per tanh (experiment, see case_set_gate_f16). */
-int case_additive_attn_gate_h(const float* qa, const void* U, const float* G, const float* v, const uint8_t* mask,
-                              const float* prior, const int32_t* tok, int tok_ld, int t, int B, int W, int S,
-                              int nsplit, float* attn_un, float* stats, float* gate_part, const int32_t* cidx,
-                              const int32_t* ncount, const int32_t* qorder, const int32_t* nsq, case_stream_t stream);
-
 /* Prefill of the gate form: G fp32 [N][4] = (Wg[0..2] . mem[n], 0) for N key rows mem bf16 [N][H];
  * Wg fp32 [3][H] = W_m[:, H(1+i):H(2+i)] of memory i (CaSE/Model.py:36,39). */
 int case_gate_project(const void* mem, const float* Wg, float* G, long long N, case_stream_t stream);
 /* Split plan for case_additive_attn_gate: nsq[b] = clamp(ceil(count[b] / c), 1, max_split), c = max(ceil(sum(count)
  * / slots), ceil(max(count) / max_split)) rounded up to 32 keys: about `slots` equally long CTAs per launch. */
 int case_split_plan(const int32_t* count, int B, int slots, int max_split, int32_t* nsq, case_stream_t stream);
-
-/* bf16 additive attention kernel: 3 (default) = warp-autonomous (no block barrier in the key loop, padding
- * skipped per key), 2 = block-synchronous 32-key tiles; returns the old setting (A/B aid). */
-int case_set_additive_impl(int impl);
 
 /* CaSE row finaliser (Model.py:110-113, 39): hN = LN(h); merges both attentions' partials into
  * ctx0/ctx1, computes the mixture gates softmax(Wm.[hN;ctx0;ctx1]+bm) and, per memory i, the pair
@@ -522,9 +483,10 @@ typedef struct {
   /* copy plan of the batch for the sparse tail (may be NULL -> hash table): see case_tail_args_t */
   const int32_t* cp_n; const int32_t* cp_uid; const int32_t* cp_first; const int32_t* cp_start; const int32_t* cp_perm;
   int32_t cp_ld;
-  const void* U16[2];                   /* [B][S_i][H] f16 copies of U (may be NULL): case_additive_attn_gate_h when W >= 2 and fast_tanh */
   const float* Gv[2];                   /* [B][S_i][4] fp32 gate-projected memories (may be NULL): the search path then runs
                                            case_additive_attn_gate and never reads Mv */
+  int32_t opt;                          /* CASE_OPT_* bits (0 = default fast path) */
+  case_fork_t* fork;                    /* side stream + events of this engine (may be NULL: everything on `stream`) */
 } case_step_args_t;
 
 /* Enqueue one full decode step t (embedding .. select) for all R rows: the body of the eval loop
@@ -551,6 +513,7 @@ typedef struct {
   float* gi; float* gh; float* feat; float* gates; float* fac; float* logits; float* dist;
   float* top_vals; int32_t* top_idx;
   void* vocab_ws;
+  int32_t opt;                                           /* CASE_OPT_NO_PDL / CASE_OPT_UNFUSED_TAIL */
 } gttp_step_args_t;
 
 /* One GTTP decode step (GTTP/Model.py:176-193 -> BBCDecoder.forward :113-131 ->

@@ -12,8 +12,12 @@ Follows, function by function:
   build_map (one-hot) ................................... common/Utils.py:344-355
   topk (k=1 -> torch.max) ............................... common/Utils.py:156-168
 
-Everything is fp32 torch on CPU; weights come from a state_dict with the reference's key names
-(prefix-free: 'embedding.0.weight', 'decs.0.layers.0.self_attn.in_proj_weight', ...).
+Everything is fp32 torch, on the CPU by default; weights come from a state_dict with the reference's key
+names (prefix-free: 'embedding.0.weight', 'decs.0.layers.0.self_attn.in_proj_weight', ...).
+
+``CaseOracle(sd, device=...)``: the full-size parity tests (BASELINE configs 2/4/5: B=64 x beam 4 x 40 steps over
+2620 keys, V=30522) evaluate these same torch fp32 expressions on the GPU box's device so the checker finishes in
+seconds; TF32 is switched off for that (``strict_fp32``), so the arithmetic stays IEEE fp32 like the CPU's.
 """
 import math
 from typing import Dict, List, Optional
@@ -22,6 +26,13 @@ import torch
 import torch.nn.functional as F
 
 NEG_CAUSAL = -1e20   # neginf(float32), common/Utils.py:14-21
+
+
+def strict_fp32():
+    """fp32 matmuls stay fp32 when the oracle is evaluated on a CUDA device (no TF32)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.set_float32_matmul_precision('highest')
 
 
 def _ln(x, sd, name):
@@ -44,7 +55,7 @@ def _mha(sd, name, query, memory, nhead, attn_mask=None, key_padding_mask=None):
     v = v.reshape(Tk, R * nhead, hd).transpose(0, 1)
     mask = None
     if key_padding_mask is not None:
-        kp = torch.zeros(R, Tk).masked_fill(key_padding_mask, float('-inf'))
+        kp = torch.zeros(R, Tk, device=query.device).masked_fill(key_padding_mask, float('-inf'))
         mask = kp.view(R, 1, 1, Tk).expand(-1, nhead, -1, -1).reshape(R * nhead, 1, Tk)
     if attn_mask is not None:
         mask = attn_mask if mask is None else attn_mask + mask
@@ -80,15 +91,15 @@ def _additive_attention(sd, name, query, key, value, mask):
     return torch.bmm(a, value), a
 
 
-def causal_mask(n):
-    m = torch.tril(torch.ones(n, n, dtype=torch.bool))
-    return torch.zeros(n, n).masked_fill(~m, NEG_CAUSAL)
+def causal_mask(n, device=None):
+    m = torch.tril(torch.ones(n, n, dtype=torch.bool, device=device))
+    return torch.zeros(n, n, device=device).masked_fill(~m, NEG_CAUSAL)
 
 
 def onehot_map(source_map, V):
     """build_map (Utils.py:344-355): dense fp32 one-hot [B,S,V]."""
     B, S = source_map.shape
-    m = torch.zeros(B, S, V)
+    m = torch.zeros(B, S, V, device=source_map.device)
     m.scatter_(2, source_map.unsqueeze(2), 1.0)
     return m
 
@@ -96,8 +107,11 @@ def onehot_map(source_map, V):
 class CaseOracle:
     """Reference-order evaluation of the decoder over a whole token prefix."""
 
-    def __init__(self, sd: Dict[str, torch.Tensor], nhead: int = 8):
-        self.sd = {k: v.detach().float() for k, v in sd.items()}
+    def __init__(self, sd: Dict[str, torch.Tensor], nhead: int = 8, device=None):
+        self.dev = torch.device(device if device is not None else 'cpu')
+        if self.dev.type == 'cuda':
+            strict_fp32()
+        self.sd = {k: v.detach().float().to(self.dev) for k, v in sd.items()}
         self.H = sd['embedding.0.weight'].size(1)
         self.V = sd['gen.2.weight'].size(0)
         self.nhead = nhead
@@ -107,13 +121,14 @@ class CaseOracle:
     # ---- Model.py:56-58: flatten memories / masks / weights to [B, S_i(, H)]
     def prepare(self, inp):
         B = inp.source_map.size(0)
+        d = self.dev
         return dict(
             B=B,
-            mem=[m.reshape(B, -1, self.H).float() for m in inp.encode_memories],
-            mask=[m.reshape(B, -1) for m in inp.encode_masks],
-            w=[w.reshape(B, -1).float() for w in inp.encode_weights],
-            feat=inp.answer_rep.float(),
-            source_map=inp.source_map,
+            mem=[m.reshape(B, -1, self.H).float().to(d) for m in inp.encode_memories],
+            mask=[m.reshape(B, -1).to(d) for m in inp.encode_masks],
+            w=[w.reshape(B, -1).float().to(d) for w in inp.encode_weights],
+            feat=inp.answer_rep.float().to(d),
+            source_map=inp.source_map.to(d),
         )
 
     def embed(self, idx):
@@ -125,9 +140,10 @@ class CaseOracle:
         """Body of the eval loop for one prefix (Model.py:95-117).  idx int64 [R,n] (BOS first).
         Returns every intermediate the parity tests look at, for all n positions."""
         sd, H = self.sd, self.H
+        idx = idx.to(self.dev)
         R, n = idx.shape
         if row2q is None:
-            row2q = torch.arange(R)
+            row2q = torch.arange(R, device=self.dev)
         x_in = self.embed(idx)                                              # [R,n,H]
         feat = _ln(ctx['feat'][row2q], sd, 'norm2').unsqueeze(1).expand(-1, n, -1)
         h = x_in.transpose(0, 1)                                            # [n,R,H]
@@ -138,7 +154,7 @@ class CaseOracle:
             mmask = ctx['mask'][i][row2q]
             for l in range(self.L):
                 h = _decoder_layer(sd, f'decs.{i}.layers.{l}.', h, mem.transpose(0, 1), self.nhead,
-                                   causal_mask(n), ~tok_valid, ~mmask)
+                                   causal_mask(n, self.dev), ~tok_valid, ~mmask)
             # Model.py:108: mask = outer(idx != 0, mem_mask)
             m2 = tok_valid.unsqueeze(-1) & mmask.unsqueeze(1)
             c, a = _additive_attention(sd, f'attns.{i}', torch.cat([h.transpose(0, 1), feat], -1), mem, mem, m2)
@@ -155,7 +171,7 @@ class CaseOracle:
         if onehot is not None:
             copy = torch.bmm(copy_w, onehot[row2q])                         # Model.py:43
         else:
-            copy = torch.zeros(R, n, self.V).scatter_add_(2, smap.unsqueeze(1).expand(-1, n, -1), copy_w)
+            copy = torch.zeros(R, n, self.V, device=self.dev).scatter_add_(2, smap.unsqueeze(1).expand(-1, n, -1), copy_w)
         dist = gates[:, :, 0].unsqueeze(-1) * gen + copy                    # Model.py:41,48
         return dict(dist=dist, gen=gen, logits=logits, gates=gates, p=ps, attn=attn_raw, ctx=cm,
                     dec_out=hN, gen_feat=f, copy_w=copy_w)
@@ -166,8 +182,8 @@ class CaseOracle:
         step's outputs (which cover all T positions, as the reference returns them)."""
         ctx = self.prepare(inp)
         B = ctx['B']
-        oh = onehot_map(inp.source_map, self.V) if dense_onehot else None
-        idx = torch.full((B, 1), 1, dtype=torch.long)
+        oh = onehot_map(ctx['source_map'], self.V) if dense_onehot else None
+        idx = torch.full((B, 1), 1, dtype=torch.long, device=self.dev)
         outs = []
         last = None
         for _ in range(T):
@@ -190,13 +206,14 @@ class _PrefixStepper:
 
     def __init__(self, orc: CaseOracle, inp, dense_onehot):
         self.o, self.ctx = orc, orc.prepare(inp)
-        self.oh = onehot_map(inp.source_map, orc.V) if dense_onehot else None
+        self.oh = onehot_map(self.ctx['source_map'], orc.V) if dense_onehot else None
         self.B = self.ctx['B']
-        self.prefix = torch.zeros(self.B, 0, dtype=torch.long)
-        self.row2q = torch.arange(self.B)
+        self.prefix = torch.zeros(self.B, 0, dtype=torch.long, device=orc.dev)
+        self.row2q = torch.arange(self.B, device=orc.dev)
         self.last = None
 
     def advance(self, parents, tokens):
+        parents, tokens = parents.to(self.o.dev), tokens.to(self.o.dev)
         self.prefix = torch.cat([self.prefix[parents], tokens.view(-1, 1)], dim=1)
         self.row2q = self.row2q[parents]
         self.last = self.o.prefix_forward(self.ctx, self.prefix, self.row2q, self.oh)
@@ -224,16 +241,18 @@ class IncrementalStepper:
                 self.xk[i, l] = F.linear(ctx['mem'][i], W[H:2 * H], b[H:2 * H])
                 self.xv[i, l] = F.linear(ctx['mem'][i], W[2 * H:], b[2 * H:])
             self.uk.append(F.linear(ctx['mem'][i], sd[f'attns.{i}.linear_key.weight']))
-        self.row2q = torch.arange(self.B)
+        dev = orc.dev
+        self.row2q = torch.arange(self.B, device=dev)
         self.t = 0
-        self.tokens = torch.zeros(self.B, 0, dtype=torch.long)
-        self.kc = {(i, l): torch.zeros(self.B, 0, H) for i in range(orc.M) for l in range(orc.L)}
-        self.vc = {(i, l): torch.zeros(self.B, 0, H) for i in range(orc.M) for l in range(orc.L)}
+        self.tokens = torch.zeros(self.B, 0, dtype=torch.long, device=dev)
+        self.kc = {(i, l): torch.zeros(self.B, 0, H, device=dev) for i in range(orc.M) for l in range(orc.L)}
+        self.vc = {(i, l): torch.zeros(self.B, 0, H, device=dev) for i in range(orc.M) for l in range(orc.L)}
         self.last = None
 
     def advance(self, parents, tokens):
         o, sd, H, nh = self.o, self.o.sd, self.o.H, self.o.nhead
         hd = H // nh
+        parents, tokens = parents.to(o.dev), tokens.to(o.dev)
         self.row2q = self.row2q[parents]
         self.tokens = torch.cat([self.tokens[parents], tokens.view(-1, 1)], dim=1)
         for k in self.kc:

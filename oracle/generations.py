@@ -37,7 +37,7 @@ def greedy(stepper, max_len: int) -> torch.Tensor:
     for t in range(max_len):
         dist = stepper.advance(parents, inp)
         _, ids = topk(dist, 1)
-        tok = ids[:, 0].clone()
+        tok = ids[:, 0].clone().cpu()        # (the stepper may evaluate on another device)
         this_end = tok == EOS
         if t == 0:
             tok[this_end] = UNK
@@ -84,6 +84,7 @@ def beam(stepper, max_len: int, width: int, return_all: bool = False):
         toks = torch.tensor([h.tokens[-1] for h in fringe], dtype=torch.long)
         dist = stepper.advance(parents, toks)
         probs, ids = topk(dist, width)
+        probs, ids = probs.cpu(), ids.cpu()   # one transfer per step when the stepper evaluates on another device
         children = {q: [] for q in range(B)}
         for i, h in enumerate(fringe):
             for j in range(width):

@@ -19,8 +19,12 @@ from .case_decoder import _additive_attention, onehot_map
 
 
 class GttpOracle:
-    def __init__(self, sd: Dict[str, torch.Tensor]):
-        self.sd = {k: v.detach().float() for k, v in sd.items()}
+    def __init__(self, sd: Dict[str, torch.Tensor], device=None):
+        self.dev = torch.device(device if device is not None else 'cpu')
+        if self.dev.type == 'cuda':
+            from .case_decoder import strict_fp32
+            strict_fp32()
+        self.sd = {k: v.detach().float().to(self.dev) for k, v in sd.items()}
         self.H = sd['dec.gru.weight_hh_l0'].size(1)
         self.V = sd['gen.linear.weight'].size(0)
 
@@ -62,15 +66,17 @@ class GttpOracle:
 
 class _GttpStepper:
     def __init__(self, orc, inp, dense_onehot):
-        self.o, self.inp = orc, inp
+        self.o, self.inp = orc, inp.to(orc.dev)
+        inp = self.inp
         self.B = inp.context.size(0)
         self.state = inp.init_state.float()
-        self.row2q = torch.arange(self.B)
+        self.row2q = torch.arange(self.B, device=orc.dev)
         self.oh = onehot_map(inp.background_map, orc.V) if dense_onehot else None
         self.last = None
 
     def advance(self, parents, tokens):
         inp = self.inp
+        parents, tokens = parents.to(self.o.dev), tokens.to(self.o.dev)
         self.row2q = self.row2q[parents]
         q2 = self.row2q
         feat, st, bg_a = self.o.step(tokens, self.state[parents], inp.src_output[q2], inp.bg_output[q2],

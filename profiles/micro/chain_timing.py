@@ -60,17 +60,15 @@ def rowdiff():
     inp = syn.make_case_inputs(52, B, 20, 3, 40, V, 256).to('cuda')
     data = dict(mem_q=inp.mem_q, mem_p=inp.mem_p, query=inp.query, passage=inp.passage, prior_q=inp.prior_q,
                 prior_p=inp.prior_p, answer_rep=inp.answer_rep, source_map=inp.source_map)
-    model = FastCaSE(sd, device='cuda', dtype='bf16', use_graph=False)
-    lib = L.load()
+    models = {c: FastCaSE(sd, device='cuda', dtype='bf16', use_graph=False, opt=0 if c else L.OPT_NO_CHAIN) for c in (0, 1)}
     for T_ in (1, 2, 3, 9):
         res = {}
         for chain in (0, 1):
-            lib.case_set_chain(chain)
+            model = models[chain]
             model.fast_search(data, T_, W, L.MODE_BEAM)
             eng = model.last_engine
             torch.cuda.synchronize()
             res[chain] = (eng.h.clone(), eng.state.live.clone(), eng.state.tok.clone(), eng.q2.clone())
-        lib.case_set_chain(1)
         d = (res[0][0] - res[1][0]).abs().amax(1)
         dq = (res[0][3] - res[1][3]).abs().amax(1)
         print(f'T={T_} row max|dh|:', [f'{x:.3f}' for x in d.tolist()])
@@ -94,14 +92,12 @@ def vs_fp32():
     m32 = FastCaSE(sd, device='cuda', dtype='fp32', use_graph=False)
     m32.fast_search(data, T, W, L.MODE_BEAM)
     ref = m32.last_engine.h.clone()
-    model = FastCaSE(sd, device='cuda', dtype='bf16', use_graph=False)
     for chain in (0, 1):
-        lib.case_set_chain(chain)
+        model = FastCaSE(sd, device='cuda', dtype='bf16', use_graph=False, opt=0 if chain else L.OPT_NO_CHAIN)
         model.fast_search(data, T, W, L.MODE_BEAM)
         torch.cuda.synchronize()
         d = (model.last_engine.h - ref).abs().amax(1)
         print(f'chain={chain} row max|h - h_fp32|:', [f'{x:.3f}' for x in d.tolist()])
-    lib.case_set_chain(1)
 
 
 if __name__ == '__main__':

@@ -202,71 +202,6 @@ def test_additive_attention_gate_form_vs_torch(W, S, nsplit, use_prior, compact)
     assert rel_err((Q / Z.clamp_min(1e-30))[live], (pr * a).sum(1)[live]) < 2e-4
 
 
-@pytest.mark.parametrize('compact', [False, True])
-@pytest.mark.parametrize('W,S,nsplit,use_prior', [(4, 2560, 9, True), (4, 1000, 3, False), (8, 333, 2, True), (2, 130, 2, False),
-                                                  (3, 77, 1, True), (2, 60, 1, True)])
-def test_additive_attention_gate_f16_tensor_core_form_vs_torch(W, S, nsplit, use_prior, compact):
-    """case_additive_attn_gate_h (Uk.mem in f16, packed tanh, v-weighted sum on the tensor core) against torch on
-    the same f16-rounded U: scores, softmax partials, gate partials; masked and compacted walks, per-query split
-    counts, an empty query, a PAD-input row."""
-    from case_rg_b200 import _lib as L
-    B, H = 4, 256
-    g = torch.Generator().manual_seed(W * 100 + S + 11)
-    qa = torch.randn(B * W, H, generator=g).to(DEV)
-    U = torch.randn(B, S, H, generator=g).to(DEV).to(torch.float16)
-    G = torch.randn(B, S, 4, generator=g).to(DEV)
-    v = (torch.randn(H, generator=g) * 0.3).to(DEV)
-    mask = torch.rand(B, S, generator=g) > 0.25
-    mask[:, 0] = True
-    if S > 200:
-        mask[1, 64:192] = False
-    mask[3] = False
-    mask = mask.to(DEV)
-    prior = torch.rand(B, S, generator=g).to(DEV) if use_prior else None
-    tok = torch.ones(B * W, 4, dtype=torch.int32, device=DEV)
-    tok[0, 2] = 0
-    scores = torch.full((B * W, S), float('nan'), device=DEV)
-    stats = torch.full((B * W, nsplit, 4), float('nan'), device=DEV)
-    gpart = torch.full((B * W, nsplit, 4), float('nan'), device=DEV)
-    cidx = ncount = qorder = nsq = None
-    if compact:
-        cidx = torch.argsort(~mask, dim=1, stable=True).to(torch.int32)
-        ncount = mask.sum(1).to(torch.int32)
-        qorder = torch.argsort(ncount, descending=True, stable=True).to(torch.int32)
-        scores.masked_fill_(~mask.repeat_interleave(W, 0), float('-inf'))
-        nsq = (ncount.float() / max(1.0, float(ncount.max())) * nsplit).ceil().clamp(1, nsplit).to(torch.int32)
-    L.call('case_additive_attn_gate_h', qa.data_ptr(), U.data_ptr(), G.data_ptr(), v.data_ptr(),
-           mask.to(torch.uint8).data_ptr(), L.ptr(prior), tok.data_ptr(), 4, 2, B, W, S, nsplit, scores.data_ptr(),
-           stats.data_ptr(), gpart.data_ptr(), L.ptr(cidx), L.ptr(ncount), L.ptr(qorder), L.ptr(nsq),
-           torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
-    e = (torch.tanh(qa.view(B, W, 1, H) + U.float().view(B, 1, S, H)) @ v).view(B * W, S)
-    ok = mask.repeat_interleave(W, 0).clone()
-    ok[0] = False
-    e = e.masked_fill(~ok, float('-inf'))
-    assert torch.equal(torch.isinf(scores), torch.isinf(e))
-    fin = ~torch.isinf(e)
-    # f16 rounding of q + u (2^-11 relative) and tanh.approx.f16x2 (~5e-4 absolute), 256 terms weighted by |v| ~ 0.3
-    assert float((scores[fin] - e[fin]).abs().max()) < 2.5e-2, float((scores[fin] - e[fin]).abs().max())
-    assert float((scores[fin] - e[fin]).abs().mean()) < 4e-3
-    # the partials are exact functions of the kernel's OWN scores: compare them with torch on those
-    m = stats[..., 0]
-    assert not bool(torch.isnan(stats).any()) and not bool(torch.isnan(gpart).any())
-    M = m.max(1, keepdim=True).values
-    w = torch.where(torch.isinf(m), torch.zeros_like(m), torch.exp(m - M))
-    Z = (stats[..., 1] * w).sum(1)
-    Q = (stats[..., 2] * w).sum(1)
-    gs = (gpart * w.unsqueeze(-1)).sum(1) / Z.clamp_min(1e-30).unsqueeze(-1)
-    a = torch.softmax(scores, 1)
-    a = torch.where(torch.isnan(a), torch.zeros_like(a), a)
-    want = torch.bmm(a.view(B, W, S), G).view(B * W, 4)
-    live = Z > 0
-    assert bool((~live)[0]) and bool(live[1:3 * W].all()) and not bool(live[3 * W:].any())
-    assert rel_err(gs[live][:, :3], want[live][:, :3]) < 2e-4
-    pr = prior.repeat_interleave(W, 0) if use_prior else torch.ones_like(a)
-    assert rel_err((Q / Z.clamp_min(1e-30))[live], (pr * a).sum(1)[live]) < 2e-4
-
-
 # --------------------------------------------------------------------------- cluster layer kernels
 def _chain_case(B, W, T, V=3000, seeds=(51, 52)):
     from case_rg_b200 import synthetic as syn
@@ -312,14 +247,10 @@ def test_layer_chain_vs_fp32_and_row_block_kernels(B, T):
         prefix[::2, 2] = 0           # PAD inside the history of every other row
     lib = L.load()
     ref = _teacher_forced_states(FastCaSE(sd, device='cuda', dtype='fp32', use_graph=False), data, prefix)
-    model = FastCaSE(sd, device='cuda', dtype='bf16', use_graph=False)
     outs = {}
-    for chain in (0, 1):
-        old = lib.case_set_chain(chain)
-        try:
-            outs[chain] = _teacher_forced_states(model, data, prefix)
-        finally:
-            lib.case_set_chain(old)
+    for chain in (0, 1):          # per-engine option word: row-block kernels against the cluster kernels
+        model = FastCaSE(sd, device='cuda', dtype='bf16', use_graph=False, opt=0 if chain else L.OPT_NO_CHAIN)
+        outs[chain] = _teacher_forced_states(model, data, prefix)
     worst = {}
     for t in range(T):
         for k in ('h', 'q2', 'logits', 'dist'):
@@ -342,17 +273,13 @@ def test_layer_chain_first_step_beam_rows(B, W):
     m32 = FastCaSE(sd, device='cuda', dtype='fp32', use_graph=False)
     m32.fast_search(data, 1, W, L.MODE_BEAM)
     ref = dict(h=m32.last_engine.h.clone(), logits=m32.last_engine.logits[:, :3000].clone())
-    model = FastCaSE(sd, device='cuda', dtype='bf16', use_graph=False)
     err = {}
     for chain in (0, 1):
-        old = lib.case_set_chain(chain)
-        try:
-            model.fast_search(data, 1, W, L.MODE_BEAM)
-            torch.cuda.synchronize()
-            eng = model.last_engine
-            err[chain] = dict(h=rel_err(eng.h, ref['h']), logits=rel_err(eng.logits[:, :3000], ref['logits']))
-        finally:
-            lib.case_set_chain(old)
+        model = FastCaSE(sd, device='cuda', dtype='bf16', use_graph=False, opt=0 if chain else L.OPT_NO_CHAIN)
+        model.fast_search(data, 1, W, L.MODE_BEAM)
+        torch.cuda.synchronize()
+        eng = model.last_engine
+        err[chain] = dict(h=rel_err(eng.h, ref['h']), logits=rel_err(eng.logits[:, :3000], ref['logits']))
     for k in ('h', 'logits'):
         assert err[1][k] < 3e-2 and err[1][k] < 2.0 * err[0][k] + 3e-3, err
 
@@ -379,12 +306,8 @@ def test_layer_chain_full_search_agrees(B, W, T):
     ref = FastCaSE(sd, device='cuda', dtype='fp32', use_graph=True).fast_search(data, T, W, mode).cpu()
     pref = {}
     for chain in (0, 1):
-        old = lib.case_set_chain(chain)
-        try:
-            model = FastCaSE(sd, device='cuda', dtype='bf16', use_graph=True)
-            pref[chain], n = _common_prefix(model.fast_search(data, T, W, mode).cpu(), ref)
-        finally:
-            lib.case_set_chain(old)
+        model = FastCaSE(sd, device='cuda', dtype='bf16', use_graph=True, opt=0 if chain else L.OPT_NO_CHAIN)
+        pref[chain], n = _common_prefix(model.fast_search(data, T, W, mode).cpu(), ref)
     print(pref, n)
     assert pref[1] >= 0.7 * pref[0] - 1.0, (pref, n)
     if T > 48:

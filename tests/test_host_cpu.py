@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.case_abi_version() == 1
+    assert lib.case_abi_version() == 2
 
 
 def test_struct_layouts_match(lib):
