@@ -175,6 +175,25 @@ def load():
     return lib
 
 
+TORCH_LIB_PATH = os.path.join(HERE, 'libcase_b200_torch.so')
+_torch_ops = None
+
+
+def load_torch_ops():
+    """Register the torch custom-op layer (TORCH_LIBRARY(case_b200, ...), csrc/torch_ops.cpp) and return
+    ``torch.ops.case_b200``.  The ops validate their tensors at the dispatcher boundary and call the same C ABI; only
+    CUDA kernels are registered (a CPU tensor fails in the dispatcher: no CPU fallback)."""
+    global _torch_ops
+    if _torch_ops is None:
+        import torch
+        load()
+        if not os.path.exists(TORCH_LIB_PATH):
+            raise RuntimeError(f'{TORCH_LIB_PATH} not found: run `python -c "import __graft_entry__ as g; g.build()"`')
+        torch.ops.load_library(TORCH_LIB_PATH)
+        _torch_ops = torch.ops.case_b200
+    return _torch_ops
+
+
 def check(rc, what=''):
     if rc != 0:
         msg = load().case_last_error().decode()

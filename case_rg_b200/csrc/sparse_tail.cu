@@ -144,7 +144,7 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
                                                          long long* dbg, const case_select_args_t sel, int do_select,
                                                          int32_t* __restrict__ qcount) {
   // [nslots] ids (-1 = empty), then [nslots] low words of the masses (later: the final float values), then - hash
-  // mode only - [nslots] high words.  The copy mass of an id is accumulated as a 64-bit FIXED-POINT integer (2^-62
+  // mode only - [nslots] high words.  The copy mass of an id is accumulated as a 64-bit FIXED-POINT integer (2^-48
   // units, two native 32-bit shared-memory atomics with an explicit carry): integer addition is associative, so the
   // mass - and with it every top-k value, cost and token - is bit-identical from run to run whatever order the
   // threads arrive in, and it is the exactly rounded sum of the fp32 contributions.
@@ -338,8 +338,9 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
         while (true) {
           const int old = atomicCAS(hkeys + slot, -1, id[u]);
           if (old == -1 || old == id[u]) {
-            // cw <= gate_i <= 1 and the masses of a row sum to <= 1: 2^62 units leave two bits of headroom
-            const unsigned long long q = __float2ull_rn(cw * 4611686018427387904.f);
+            // units of 2^-48 (3.6e-15: below fp32 resolution for every mass >= 6e-8, exact conversion for cw >= 2^-24);
+            // probability masses are <= 1, the 16 integer bits are headroom for un-normalised callers (saturating)
+            const unsigned long long q = __float2ull_rn(fminf(cw, 32768.f) * 281474976710656.f);
             const uint32_t lo = (uint32_t)q;
             const uint32_t prev = atomicAdd(hlo + slot, lo);
             const uint32_t hi = (uint32_t)(q >> 32) + ((uint32_t)(prev + lo) < prev ? 1u : 0u);   // carry out of the low word
@@ -440,7 +441,7 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
       if (id[u] < 0) continue;
       const float e = (a.mask_col0 && id[u] == 0) ? 0.f : sp_exp(lv[u] - mm);
       const unsigned long long q = ((unsigned long long)hhi[s0 + u * TS] << 32) | hlo[s0 + u * TS];
-      const float f = fmaf(scl, e, __ull2float_rn(q) * 2.168404344971009e-19f);   // 2^-62
+      const float f = fmaf(scl, e, __ull2float_rn(q) * 3.552713678800501e-15f);   // 2^-48
       hvals[s0 + u * TS] = f;
       tmax = fmaxf(tmax, f);
     }

@@ -246,7 +246,7 @@ def install_fast_decoder(model: nn.Module, beam_width: int = 1, dtype: str = 'bf
     return model
 
 
-def install_fast_gttp(model: nn.Module, dtype: str = 'bf16', **kw) -> nn.Module:
+def install_fast_gttp(model: nn.Module, dtype: str = 'bf16', device=None, **kw) -> nn.Module:
     """Swap the step side of a reference ``GTTP`` model (GTTP/Model.py:133-212) for the CUDA path, in place.
 
     ``model.forward(data, 'test')`` keeps its contract (``{'answer': LongTensor}``, greedy for ``beam_width == 1``, else
@@ -256,10 +256,16 @@ def install_fast_gttp(model: nn.Module, dtype: str = 'bf16', **kw) -> nn.Module:
         wrote them - they are outside the hot path - and their outputs feed the device search;
       * ``decode`` / ``generate`` / ``to_word`` + ``Generations.greedy/beam`` (Model.py:176-193, Generations.py:66-190) are
         replaced by ``FastGTTP.fast_search`` (gttp_decode_step x max_dec_len in one CUDA graph).
-    Training (``method='train'``) goes through the original forward."""
+    Training (``method='train'``) goes through the original forward.
+
+    ``device``: where the step engine lives (default: the model's device).  The reference's encoders call
+    ``pack_padded_sequence`` with device-side lengths (common/Utils.py:313-336), which current torch only accepts on the
+    CPU - so the model may stay on the CPU while the search runs on ``device``: the encoder outputs (a few MB) are moved
+    there, the answers come back on the model's device."""
     from .generations import FastGTTP
     sd = {k: v for k, v in model.state_dict().items() if k.startswith('dec.') or k.startswith('gen.')}
-    dev = next(model.parameters()).device
+    mdev = next(model.parameters()).device
+    dev = torch.device(device) if device is not None else mdev
     fast = FastGTTP(sd, device=dev, dtype=dtype, max_dec_len=model.max_dec_len, beam_width=model.beam_width, **kw)
     orig_forward = model.forward
 
@@ -270,8 +276,9 @@ def install_fast_gttp(model: nn.Module, dtype: str = 'bf16', **kw) -> nn.Module:
         init = self.init_decoder_states(data, enc)                # [B, 1, H]
         d = dict(context=data['context'], background=data['background'], background_map=data['background_map'],
                  src_output=enc[0], bg_output=enc[2], init_state=init)
+        d = {k: v.to(dev) for k, v in d.items()}
         mode = L.MODE_PROTO_GREEDY if self.beam_width == 1 else L.MODE_BEAM
-        return {'answer': fast.fast_search(d, self.max_dec_len, self.beam_width, mode)}
+        return {'answer': fast.fast_search(d, self.max_dec_len, self.beam_width, mode).to(mdev)}
 
     model.forward = types.MethodType(forward, model)
     model._fast_gttp = [fast]            # list: keeps it out of the module tree / state_dict

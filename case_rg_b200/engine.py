@@ -349,23 +349,37 @@ class _EngineBase:
             self.args.opt = int(opt)
             self._graphs.clear()
 
+    # The step orchestrator is reached either through ctypes (default) or through the torch custom op
+    # case_b200::decode_step / gttp_step (use_torch_ops = True): the same C entry point, the same argument block - the op
+    # takes it as a uint8 view of the ctypes struct - and the stream is torch's current stream either way.
+    use_torch_ops = False
+
+    def _step(self, t: int, cuda_stream: int):
+        if self.use_torch_ops:
+            ops = L.load_torch_ops()
+            if getattr(self, '_args_blob', None) is None:
+                self._args_blob = torch.frombuffer(self.args, dtype=torch.uint8)
+            (ops.gttp_step if self._step_name == 'gttp_decode_step' else ops.decode_step)(self._args_blob, t)
+        else:
+            L.check(self._step_fn(C.byref(self.args), t, cuda_stream), self._step_name)
+
     def _run_steps(self, max_len: int):
         with _on_device(self.device):
             stream = torch.cuda.current_stream(self.device)
             for t in range(max_len):
-                L.check(self._step_fn(C.byref(self.args), t, stream.cuda_stream), self._step_name)
+                self._step(t, stream.cuda_stream)
 
     def _capture(self, max_len, mode):
         """Capture all ``max_len`` steps into one CUDA graph (t is a by-value kernel argument)."""
         with _on_device(self.device):
             stream = torch.cuda.current_stream(self.device)
-            L.check(self._step_fn(C.byref(self.args), 0, stream.cuda_stream), self._step_name)   # warm-up, not captured
+            self._step(0, stream.cuda_stream)                                                  # warm-up, not captured
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 cs = torch.cuda.current_stream(self.device)
                 for t in range(max_len):
-                    L.check(self._step_fn(C.byref(self.args), t, cs.cuda_stream), self._step_name)
+                    self._step(t, cs.cuda_stream)
         self._graphs[(max_len, mode)] = g
 
     def _finish_tokens(self, max_len: int, mode: int) -> torch.Tensor:
@@ -643,8 +657,7 @@ class CaseDecodeEngine(_EngineBase):
                 self._mv_src[i] = None
         self.args.materialize_only = 1
         with _on_device(self.device):
-            stream = torch.cuda.current_stream(self.device)
-            L.check(self._step_fn(C.byref(self.args), t, stream.cuda_stream), self._step_name)
+            self._step(t, torch.cuda.current_stream(self.device).cuda_stream)
         self.args.materialize_only = 0
         return self.dist[:, :self.V]
 

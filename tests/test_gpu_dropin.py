@@ -84,7 +84,8 @@ def test_install_fast_decoder_into_live_reference_masque(ns):
 def test_install_fast_gttp_into_live_reference_gttp(ns, width):
     """GTTP.forward(data, 'test'): the reference bi-GRU encoders feed first the reference decode/generate/to_word under
     Generations.greedy / beam (as shipped; beam through the dict-wrapping adapter of SURVEY.md §8c), then the installed
-    device search."""
+    device search.  The reference model stays on the CPU: its encoders pass device-side lengths to
+    pack_padded_sequence (common/Utils.py:313-336), which this torch rejects on CUDA - the step engine runs on cuda:0."""
     from baseline import refshim
     from case_rg_b200.decoder import install_fast_gttp
     V, T, B = 1500, 9, 4
@@ -94,28 +95,35 @@ def test_install_fast_gttp_into_live_reference_gttp(ns, width):
     sdg = syn.make_gttp_state(95, V, H, H, peaked=0.3, boost={syn.EOS: 5.0})
     missing = model.load_state_dict(sdg, strict=False)
     assert not missing.unexpected_keys
-    model = model.to(DEV).eval()
+    model = model.eval()
     ginp = syn.make_gttp_inputs(96, B, 12, 3, 16, V, H)
-    data = {'id': ginp.ids.to(DEV), 'context': ginp.context.to(DEV), 'background': ginp.background.to(DEV),
-            'background_map': ginp.background_map.to(DEV)}
+    data = {'id': ginp.ids, 'context': ginp.context, 'background': ginp.background, 'background_map': ginp.background_map}
+    # the reference helpers jump to CUDA whenever it is visible (Utils.new_tensor / build_map): pin them to the CPU for
+    # the reference half of this test, the way bench.py's reference arm does with CUDA_VISIBLE_DEVICES=""
+    real = torch.cuda.is_available
+    torch.cuda.is_available = lambda: False
+    try:
+        with torch.no_grad():
+            if width == 1:
+                want = model(copy.copy(data), method='test')['answer']      # the shipped path: Generations.greedy
+            else:
+                # Generations.beam slices encode outputs per node (Utils.get_data), which needs them in a dict: drive the
+                # reference's own decode / generate / to_word through the adapter subclass
+                ad = refshim.make_gttp_adapter(ns, H, H, vocab2id, id2vocab, max_dec_len=T, beam_width=width)
+                ad.load_state_dict(model.state_dict())
+                ad = ad.eval()
+                enc = model.encode(data)
+                fake = type('I', (), {})()
+                fake.src_output, fake.bg_output, fake.init_state = enc[0], enc[2], model.init_decoder_states(data, enc)
+                ad.attach(fake)
+                d2 = dict(data, background_map=ns.utils.build_map(data['background_map'], max=V))
+                want = ns.gen.beam(ad, d2, vocab2id, T, width)
+    finally:
+        torch.cuda.is_available = real
     with torch.no_grad():
-        if width == 1:
-            want = model(copy.copy(data), method='test')['answer']      # the shipped path: Generations.greedy
-        else:
-            # Generations.beam slices encode outputs per node (Utils.get_data), which needs them in a dict: drive the
-            # reference's own decode / generate / to_word through the adapter subclass
-            ad = refshim.make_gttp_adapter(ns, H, H, vocab2id, id2vocab, max_dec_len=T, beam_width=width)
-            ad.load_state_dict(model.state_dict())
-            ad = ad.to(DEV).eval()
-            enc = model.encode(data)
-            fake = type('I', (), {})()
-            fake.src_output, fake.bg_output, fake.init_state = enc[0], enc[2], model.init_decoder_states(data, enc)
-            ad.attach(fake)
-            d2 = dict(data, background_map=ns.utils.build_map(data['background_map'], max=V))
-            want = ns.gen.beam(ad, d2, vocab2id, T, width)
-        install_fast_gttp(model, dtype='fp32')
+        install_fast_gttp(model, dtype='fp32', device=DEV)
         got = model(copy.copy(data), method='test')['answer']
-    assert got.dtype == torch.int64
+    assert got.dtype == torch.int64 and got.device == want.device
     L = min(got.size(1), want.size(1))
-    assert torch.equal(got[:, :L].cpu(), want[:, :L].cpu()), (got, want)
+    assert torch.equal(got[:, :L], want[:, :L]), (got, want)
     assert got.size(1) == want.size(1) or width == 1

@@ -168,3 +168,21 @@ def test_synthetic_inputs_follow_dataset_layout():
     assert float((inp.mem_p * (~inp.passage.ne(0)).unsqueeze(-1)).abs().max()) == 0.0
     a, b = syn.make_case_inputs(5, 2, 12, 3, 16, 1000, 256), syn.make_case_inputs(5, 2, 12, 3, 16, 1000, 256)
     assert torch.equal(a.mem_q, b.mem_q) and torch.equal(a.passage, b.passage)
+
+
+def test_torch_custom_op_layer_registers_and_has_no_cpu_kernels():
+    """TORCH_LIBRARY(case_b200, ...): the op library loads next to the C ABI, every op named in csrc/torch_ops.cpp is
+    registered with the dispatcher, and the compute ops have CUDA kernels only - a CPU tensor is refused by the
+    dispatcher (no compute runs here: there is no GPU on this box)."""
+    ops = _lib.load_torch_ops()
+    for name in ('topk_rows', 'copy_scatter_', 'softmax_mix', 'vocab_gemm', 'cross_attn_part', 'additive_attn_gate',
+                 'decode_step', 'gttp_step'):
+        assert hasattr(ops, name), name
+    with pytest.raises(NotImplementedError):
+        ops.topk_rows(torch.zeros(2, 8), 8, 1)
+    with pytest.raises(NotImplementedError):
+        ops.softmax_mix(torch.zeros(2, 8), torch.zeros(2, 4), 8, False)
+    with pytest.raises(RuntimeError):          # the step ops check their argument blob before anything is launched
+        ops.decode_step(torch.zeros(16, dtype=torch.uint8), 0)
+    schema = torch.ops.case_b200.copy_scatter_.default._schema
+    assert schema.arguments[0].alias_info is not None and schema.arguments[0].alias_info.is_write
