@@ -39,7 +39,8 @@ class LayerWeights(C.Structure):
 class SelectArgs(C.Structure):
     _fields_ = [(n, i32) for n in ('mode', 'B', 'W', 't', 'max_len', 'Tmax', 'BOS', 'EOS', 'UNK', 'PAD')] + \
                [(n, vp) for n in ('top_vals', 'top_idx', 'live', 'cum', 'length', 'tok', 'anc_in', 'anc_out',
-                                  'parent', 'ended', 'best_key', 'best_len', 'out_tokens', 'n_live')]
+                                  'parent', 'ended', 'best_key', 'best_len', 'out_tokens', 'n_live')] + \
+               [('V_in', i32), ('tok_ext', vp)]
 
 
 class PostLinear(C.Structure):
@@ -58,7 +59,7 @@ class TailArgs(C.Structure):
                 ('logits', vp), ('hN', vp), ('stats', vp * 2), ('ctxp', vp * 2), ('Wm', vp), ('bm', vp),
                 ('ctx', vp * 2), ('gates', vp), ('fac', vp), ('map', vp), ('prior', vp * 2), ('attn_un', vp * 2),
                 ('top_vals', vp), ('top_idx', vp), ('dist', vp), ('gate_ctx', i32), ('cp_ld', i32),
-                ('cp_n', vp), ('cp_uid', vp), ('cp_first', vp), ('cp_start', vp), ('cp_perm', vp)]
+                ('cp_n', vp), ('cp_uid', vp), ('cp_first', vp), ('cp_start', vp), ('cp_perm', vp), ('Vext', i32)]
 
 
 class StepArgs(C.Structure):
@@ -74,7 +75,7 @@ class StepArgs(C.Structure):
                 ('out_tokens', vp), ('n_live', vp),
                 ('x_in', vp), ('h', vp), ('bbuf', vp), ('q2', vp), ('part_ml', vp), ('part_acc', vp), ('qa', vp),
                 ('attn_un', vp * 2), ('stats', vp * 2), ('ctxp', vp * 2), ('hN', vp), ('ctx', vp * 2), ('gates', vp),
-                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp), ('prow', vp), ('h0', vp), ('qa1', vp), ('base_ms', vp), ('base_e', vp), ('base_i', vp), ('xcount', vp), ('xprefix', vp), ('xslots', i32), ('xidx', vp), ('xorder', vp), ('qcount', vp), ('Wqa_c', vp * 2), ('Wg_c', vp), ('xns', vp), ('cp_n', vp), ('cp_uid', vp), ('cp_first', vp), ('cp_start', vp), ('cp_perm', vp), ('cp_ld', i32), ('Gv', vp * 2), ('opt', i32), ('fork', vp)]
+                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp), ('prow', vp), ('h0', vp), ('qa1', vp), ('base_ms', vp), ('base_e', vp), ('base_i', vp), ('xcount', vp), ('xprefix', vp), ('xslots', i32), ('xidx', vp), ('xorder', vp), ('qcount', vp), ('Wqa_c', vp * 2), ('Wg_c', vp), ('xns', vp), ('cp_n', vp), ('cp_uid', vp), ('cp_first', vp), ('cp_start', vp), ('cp_perm', vp), ('cp_ld', i32), ('Gv', vp * 2), ('opt', i32), ('fork', vp), ('n_oov', i32), ('tok_ext', vp)]
 
 
 class GttpStepArgs(C.Structure):
@@ -120,6 +121,7 @@ _PROTOS = {
     'case_softmax_mix': [vp, i32, vp, vp, i32, i32, i32, i32, vp],
     'case_copy_scatter': [vp, i32, i32, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp],
     'case_topk_rows': [vp, i32, i32, i32, i32, vp, vp, vp],
+    'case_oov_fold': [vp, i32, i32, i32, i32, vp, vp, i32, vp],
     'case_row_tail': [C.POINTER(TailArgs), vp],
     'case_row_tail_max_vocab': [],
     'case_vocab_base': [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp],

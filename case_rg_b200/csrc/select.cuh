@@ -12,6 +12,10 @@ namespace cb {
 __device__ __forceinline__ void beam_select_query(const case_select_args_t& a, int b, int lane) {
   const int W = a.W, t = a.t, TL = a.Tmax + 1;
   const int r0 = b * W;
+  // extended vocabulary: ids >= V_in are dynamic (OOV) entries - the decoder is fed UNK, tok_ext keeps the id
+  const bool ext = a.V_in > 0 && a.tok_ext != nullptr;
+  int32_t* tok_o = ext ? a.tok_ext : a.tok;
+  auto feed = [&](int id) { return (ext && id >= a.V_in) ? a.UNK : id; };
 
   if (a.mode != CASE_MODE_BEAM) {   // W == 1
     if (lane == 0) {
@@ -24,7 +28,8 @@ __device__ __forceinline__ void beam_select_query(const case_select_args_t& a, i
         a.ended[b] = was_ended | this_end;
       }
       a.out_tokens[(size_t)b * a.Tmax + t] = tk;
-      a.tok[(size_t)r0 * TL + t + 1] = tk;
+      a.tok[(size_t)r0 * TL + t + 1] = feed(tk);
+      if (ext) tok_o[(size_t)r0 * TL + t + 1] = tk;
       a.parent[r0] = r0;
       a.live[r0] = 1;
       a.n_live[b] = 1;
@@ -87,7 +92,8 @@ __device__ __forceinline__ void beam_select_query(const case_select_args_t& a, i
     for (int j = lane; j < t; j += 32) a.anc_out[(size_t)rn * TL + j] = a.anc_in[(size_t)pr * TL + j];
     if (lane == 0) {
       a.anc_out[(size_t)rn * TL + t] = pr;
-      a.tok[(size_t)rn * TL + t + 1] = ctok[c];
+      a.tok[(size_t)rn * TL + t + 1] = feed(ctok[c]);
+      if (ext) tok_o[(size_t)rn * TL + t + 1] = ctok[c];
       a.cum[rn] = ccum[c];
       a.length[rn] = clen[c];
       a.live[rn] = 1;
@@ -99,6 +105,7 @@ __device__ __forceinline__ void beam_select_query(const case_select_args_t& a, i
     a.live[rn] = 0;
     a.parent[rn] = rn;
     a.tok[(size_t)rn * TL + t + 1] = a.PAD;
+    if (ext) tok_o[(size_t)rn * TL + t + 1] = a.PAD;
     for (int j = 0; j <= t; ++j) a.anc_out[(size_t)rn * TL + j] = rn;
   }
   if (s_best >= 0) {   // record the new best finished sequence: BOS dropped, EOS kept (:188)
@@ -108,7 +115,7 @@ __device__ __forceinline__ void beam_select_query(const case_select_args_t& a, i
       int v = a.PAD;
       if (j < t) {
         const int src = (j + 1 == t) ? pr : a.anc_in[(size_t)pr * TL + j + 1];
-        v = a.tok[(size_t)src * TL + j + 1];
+        v = tok_o[(size_t)src * TL + j + 1];
       } else if (j == t) {
         v = ctok[c];
       }

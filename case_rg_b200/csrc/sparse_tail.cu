@@ -156,6 +156,7 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
   __shared__ TopKScratch<TSW, 256> sc;
   const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = r / a.W, V = a.V;
+  const int Vx = a.Vext > V ? a.Vext : V;                  // extended vocabulary: ids in [V, Vx) are dynamic entries without a logit
   const uint32_t hmask = (uint32_t)nslots - 1;
   const int hshift = 32 - (31 - __clz(nslots));            // nslots is a power of two
   // plan mode (a.cp_n != NULL): the prefill sorted the valid source positions of the query by vocabulary id, so
@@ -329,7 +330,7 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
       }
 #pragma unroll
       for (int u = 0; u < HU; ++u) {
-        if (ev[u] == -INFINITY || (unsigned)id[u] >= (unsigned)V) continue;   // masked source position
+        if (ev[u] == -INFINITY || (unsigned)id[u] >= (unsigned)Vx) continue;   // masked source position
         const bool m1 = s0 + u * TS >= S0n;
         const float cw = (m1 ? F[1] : F[0]) * pv[u] * fexp(ev[u] - (m1 ? M[1] : M[0]));
         if (cw == 0.f) continue;
@@ -434,12 +435,12 @@ __global__ __launch_bounds__(TS) void sparse_tail_kernel(const case_tail_args_t 
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       id[u] = hkeys[s0 + u * TS];
-      lv[u] = id[u] >= 0 ? x[id[u]] : 0.f;
+      lv[u] = (id[u] >= 0 && id[u] < V) ? x[id[u]] : -INFINITY;     // dynamic entries: no base term
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (id[u] < 0) continue;
-      const float e = (a.mask_col0 && id[u] == 0) ? 0.f : sp_exp(lv[u] - mm);
+      const float e = ((a.mask_col0 && id[u] == 0) || id[u] >= V) ? 0.f : sp_exp(lv[u] - mm);
       const unsigned long long q = ((unsigned long long)hhi[s0 + u * TS] << 32) | hlo[s0 + u * TS];
       const float f = fmaf(scl, e, __ull2float_rn(q) * 3.552713678800501e-15f);   // 2^-48
       hvals[s0 + u * TS] = f;
@@ -559,6 +560,7 @@ extern "C" int case_sparse_tail(const case_tail_args_t* a, const float* base_ms,
   int nslots = 4 * TS;
   while (nslots < 3 * total && nslots < 16384) nslots *= 2;  // load factor ~1/3 (<= 2/3 at the size limit)
   const bool plan = a->cp_n != nullptr;
+  CB_REQUIRE(a->Vext == 0 || (a->Vext >= a->V && !plan), "case_sparse_tail: Vext must be >= V (hash-table mode)");
   CB_REQUIRE(!plan || (a->nmem == 2 && a->cp_uid && a->cp_first && a->cp_start && a->cp_perm && a->cp_ld >= total && total < 65536),
              "case_sparse_tail: the copy plan needs cp_uid / cp_first / cp_start / cp_perm with cp_ld >= S0 + S1 (two memories, < 65536 positions)");
   // plan mode: (id, value) per list entry, at most one per source position; the hash layout otherwise

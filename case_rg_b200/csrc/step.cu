@@ -146,6 +146,10 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
   const int32_t* anc = a->anc[t & 1];
   const int opt = a->opt;
   OptScope scope(opt);
+  // extended vocabulary (n_oov dynamic ids behind the V fixed ones): the sparse tail handles it on the search path, the
+  // dense forms fall to the unfused kernels, which are generic in the row width
+  const int n_oov = a->n_oov > 0 ? a->n_oov : 0, Vx = a->V + n_oov;
+  CB_REQUIRE(n_oov == 0 || (a->tok_ext != nullptr && a->ldv >= Vx), "case_decode_step: n_oov needs tok_ext and ldv >= V + n_oov");
   const int use_tail = (opt & CASE_OPT_UNFUSED_TAIL) ? 0 : ((opt & CASE_OPT_DENSE_TAIL) ? 1 : 2);
   if (a->fork != nullptr) {
     int dev = -1;
@@ -330,7 +334,7 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
   TRY(case_vocab_gemm(a->gfeat, a->Wv, nullptr, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, a->vocab_ws, st));
   if (sparse) TRY(case_vocab_base(a->logits, a->ldv, R, a->V, 0, k2, a->base_ms, a->base_e, a->base_i, st));
   }
-  if (sparse || (use_tail && a->V <= case_row_tail_max_vocab())) {
+  if (sparse || (use_tail && n_oov == 0 && a->V <= case_row_tail_max_vocab())) {
     // one launch: attention merge + gates, softmax x gate, both copy scatters, top-k; the [R, V]
     // distribution is written only for the `generate` face
     case_tail_args_t ta;
@@ -346,6 +350,7 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
     }
     if (a->materialize_only) { ta.dist = a->dist; } else { ta.top_vals = a->top_vals; ta.top_idx = a->top_idx; }
     ta.gate_ctx = gate ? 1 : 0;
+    ta.Vext = n_oov ? Vx : 0;
     if (sparse && !(opt & CASE_OPT_NO_COPY_PLAN) && a->cp_n != nullptr) {
       ta.cp_n = a->cp_n; ta.cp_uid = a->cp_uid; ta.cp_first = a->cp_first; ta.cp_start = a->cp_start; ta.cp_perm = a->cp_perm;
       ta.cp_ld = a->cp_ld;
@@ -355,6 +360,7 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       case_select_args_t sel = select_args(a->mode, B, W, t, a->max_len, a->Tmax, a->BOS, a->EOS, a->UNK, a->PAD,
                                            a->top_vals, a->top_idx, a->live, a->cum, a->length, a->tok, a->anc, a->parent,
                                            a->ended, a->best_key, a->best_len, a->out_tokens, a->n_live);
+      if (n_oov) { sel.V_in = a->V; sel.tok_ext = a->tok_ext; }
       TRY(case_sparse_tail(&ta, a->base_ms, a->base_e, a->base_i, k2, fuse_sel ? &sel : nullptr, a->qcount, st));
       if (fuse_sel) return 0;
     } else {
@@ -364,17 +370,23 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
   } else {
     TRY(finalize());
     TRY(case_softmax_mix(a->logits, a->ldv, a->gates, a->dist, a->ldv, R, a->V, 0, st));
+    if (n_oov)      // the dynamic columns start from zero: they only ever receive copy mass
+      CUTRY(cudaMemset2DAsync(a->dist + a->V, (size_t)a->ldv * sizeof(float), 0, (size_t)n_oov * sizeof(float), R, st));
     for (int i = 0; i < 2; ++i) {
       TRY(case_copy_scatter(a->map, a->map_ld, a->map_off[i], a->prior[i], a->attn_un[i],
                             a->fac + (size_t)i * CASE_MAX_SPLIT, 2 * CASE_MAX_SPLIT, a->dist, a->ldv, B, W, a->S[i],
-                            a->V, st));
+                            Vx, st));
     }
     if (a->materialize_only) return 0;
-    TRY(case_topk_rows(a->dist, a->ldv, R, a->V, W, a->top_vals, a->top_idx, st));
+    TRY(case_topk_rows(a->dist, a->ldv, R, Vx, W, a->top_vals, a->top_idx, st));
   }
-  return select_step(a->mode, B, W, t, a->max_len, a->Tmax, a->BOS, a->EOS, a->UNK, a->PAD, a->top_vals, a->top_idx,
-                     a->live, a->cum, a->length, a->tok, a->anc, a->parent, a->ended, a->best_key, a->best_len,
-                     a->out_tokens, a->n_live, st);
+  {
+    case_select_args_t sel = select_args(a->mode, B, W, t, a->max_len, a->Tmax, a->BOS, a->EOS, a->UNK, a->PAD, a->top_vals,
+                                         a->top_idx, a->live, a->cum, a->length, a->tok, a->anc, a->parent, a->ended,
+                                         a->best_key, a->best_len, a->out_tokens, a->n_live);
+    if (n_oov) { sel.V_in = a->V; sel.tok_ext = a->tok_ext; }
+    return case_beam_select(&sel, st);
+  }
 }
 
 extern "C" int gttp_decode_step(const gttp_step_args_t* a, int t, case_stream_t stream) {

@@ -266,6 +266,31 @@ extern "C" int case_copy_scatter(const int32_t* map, int map_ld, int map_off, co
   return check_launch("case_copy_scatter");
 }
 
+namespace cb {
+// one CTA per row: thread d folds dynamic entry d into its vocabulary id and applies the overlap mask
+__global__ __launch_bounds__(256) void oov_fold_kernel(float* __restrict__ gen, int ldg, int V, int D,
+                                                       const int32_t* __restrict__ vmap, const float* __restrict__ overlap,
+                                                       int rows_per_map) {
+  pdl_wait();
+  const int r = blockIdx.x, q = r / rows_per_map;
+  float* row = gen + (size_t)r * ldg;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float w = row[V + d];
+    const int v = vmap[(size_t)q * D + d];
+    if (w != 0.f && (unsigned)v < (unsigned)V) atomicAdd(row + v, w);   // several OOV words fold onto UNK
+    row[V + d] = w * overlap[(size_t)q * D + d];
+  }
+}
+}  // namespace cb
+
+extern "C" int case_oov_fold(float* gen, int ldg, int R, int V, int D, const int32_t* vocab_map, const float* overlap,
+                             int rows_per_map, case_stream_t stream) {
+  CB_REQUIRE(gen && vocab_map && overlap && R > 0 && V > 0 && D > 0 && rows_per_map >= 1, "case_oov_fold: bad arguments");
+  CB_REQUIRE(ldg >= V + D, "case_oov_fold: rows must hold V + D entries");
+  launch_k(cb::oov_fold_kernel, R, 256, 0, (cudaStream_t)stream, gen, ldg, V, D, vocab_map, overlap, rows_per_map);
+  return check_launch("case_oov_fold");
+}
+
 extern "C" int case_topk_rows(const float* dist, int ldd, int R, int V, int k, float* vals, int32_t* idx,
                               case_stream_t stream) {
   CB_REQUIRE(dist && vals && idx && R > 0 && V > 0, "case_topk_rows: bad arguments");

@@ -303,10 +303,12 @@ class CaseWeights:
 class _SearchState:
     """Buffers shared by both engines for the on-device greedy / beam bookkeeping."""
 
-    def __init__(self, dev, B, W, Tmax):
+    def __init__(self, dev, B, W, Tmax, ext=False):
         R, TL = B * W, Tmax + 1
         i32 = dict(dtype=torch.int32, device=dev)
         self.tok = torch.zeros(R, TL, **i32)
+        # extended vocabulary: tok feeds the decoder (OOV ids become UNK), tok_ext keeps the ids of the returned sequences
+        self.tok_ext = torch.zeros(R, TL, **i32) if ext else None
         self.anc = [torch.zeros(R, TL, **i32), torch.zeros(R, TL, **i32)]
         self.live = torch.zeros(R, **i32)
         self.cum = torch.zeros(R, dtype=torch.float64, device=dev)
@@ -324,6 +326,8 @@ class _SearchState:
     def reset(self, bos=BOS):
         self.tok.zero_()
         self.tok[:, 0] = bos
+        if self.tok_ext is not None:
+            self.tok_ext.copy_(self.tok)
         self.anc[0].copy_(self._arange[:, None].expand_as(self.anc[0]))   # every row is its own history
         self.anc[1].copy_(self.anc[0])
         self.live.copy_(self._slot0)            # one root hypothesis per query (Generations.py:132-134)
@@ -397,8 +401,10 @@ class CaseDecodeEngine(_EngineBase):
 
     def __init__(self, weights: CaseWeights, B: int, W: int, S0: int, S1: int, Tmax: int = 40,
                  fast_tanh: Optional[bool] = None, vocab_impl: Optional[int] = None, target_ctas: int = 296,
-                 opt: int = 0):
-        self.opt = int(opt)
+                 opt: int = 0, n_oov: int = 0):
+        """n_oov > 0: extended vocabulary - ``source_map`` entries in [V, V + n_oov) are per-query dynamic (OOV) words,
+        the mixture and its top-k range over V + n_oov ids (pointer-generator extension; an OOV id is fed back as UNK)."""
+        self.opt, self.n_oov = int(opt), int(n_oov)
         if not (1 <= W <= L.MAX_W):
             raise ValueError(f'beam width must be 1..{L.MAX_W}')
         if not (1 <= Tmax <= L.MAX_T):
@@ -407,7 +413,7 @@ class CaseDecodeEngine(_EngineBase):
         self.device = dev = weights.device
         self.B, self.W, self.R, self.S, self.Tmax, self.V = B, W, B * W, (S0, S1), Tmax, weights.V
         R, V, H = self.R, self.V, L.H
-        self.ldv = -(-V // 8) * 8
+        self.ldv = -(-(V + self.n_oov) // 8) * 8
         td = weights.tdtype
         self.fast_tanh = int(weights.cdtype == L.BF16 if fast_tanh is None else fast_tanh)
         self.vocab_impl = int((1 if weights.cdtype == L.BF16 else 0) if vocab_impl is None else vocab_impl)
@@ -442,7 +448,7 @@ class CaseDecodeEngine(_EngineBase):
         # state
         self.kcache = [torch.zeros(R, Tmax, H, dtype=td, device=dev) for _ in range(8)]
         self.vcache = [torch.zeros(R, Tmax, H, dtype=td, device=dev) for _ in range(8)]
-        self.state = _SearchState(dev, B, W, Tmax)
+        self.state = _SearchState(dev, B, W, Tmax, ext=self.n_oov > 0)
         # scratch
         # second memory: only valid keys are packed (case_cross_attn_part); CASE_NO_COMPACT=1 keeps the masked form (A/B)
         self.compact = weights.cdtype == L.BF16 and os.environ.get('CASE_NO_COMPACT', '0') != '1'
@@ -501,6 +507,8 @@ class CaseDecodeEngine(_EngineBase):
         a = self.args = L.StepArgs()
         w = self.w
         a.opt, a.fork = self.opt, self._fork.h
+        if self.n_oov:
+            a.n_oov, a.tok_ext = self.n_oov, self.state.tok_ext.data_ptr()
         a.B, a.W, a.R, a.V, a.ldv, a.Tmax = self.B, self.W, self.R, self.V, self.ldv, self.Tmax
         a.dtype, a.fast_tanh, a.vocab_impl, a.mode = w.cdtype, self.fast_tanh, self.vocab_impl, L.MODE_MODULE_GREEDY
         for i in range(2):
@@ -659,7 +667,7 @@ class CaseDecodeEngine(_EngineBase):
         with _on_device(self.device):
             self._step(t, torch.cuda.current_stream(self.device).cuda_stream)
         self.args.materialize_only = 0
-        return self.dist[:, :self.V]
+        return self.dist[:, :self.V + self.n_oov]
 
     def answer_tokens(self) -> int:
         return int(self.state.best_len.sum().item())

@@ -93,20 +93,23 @@ class FastCaSE(_FastModel):
     'prior_q', 'prior_p', 'answer_rep' [B,H], 'source_map' int64 [B,S]."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device=None, dtype='bf16', max_dec_len=40,
-                 beam_width=1, vocab_impl: Optional[int] = None, use_graph=True, prefix='', opt: int = 0):
-        """opt: CASE_OPT_* bits for every engine of this model (0 = the default fast path; A/B and fallback tests)."""
+                 beam_width=1, vocab_impl: Optional[int] = None, use_graph=True, prefix='', opt: int = 0,
+                 n_oov: int = 0):
+        """opt: CASE_OPT_* bits for every engine of this model (0 = the default fast path; A/B and fallback tests).
+        n_oov: size of the per-query dynamic vocabulary behind the V fixed ids (``source_map`` may point into
+        [V, V + n_oov); returned ids then range over the extended vocabulary)."""
         self.weights = CaseWeights(state_dict, device=device, dtype=dtype, prefix=prefix)
         self.max_dec_len, self.beam_width, self.vocab_impl, self.use_graph = max_dec_len, beam_width, vocab_impl, use_graph
-        self.opt = int(opt)
+        self.opt, self.n_oov = int(opt), int(n_oov)
         self._engines = {}
 
     def engine_for(self, B, W, S0, S1, T):
-        key = (B, W, S0, S1, T, self.opt)
+        key = (B, W, S0, S1, T, self.opt, self.n_oov)
         if key not in self._engines:
             if len(self._engines) >= 4:
                 self._engines.clear()
             self._engines[key] = CaseDecodeEngine(self.weights, B, W, S0, S1, T, vocab_impl=self.vocab_impl,
-                                                  opt=self.opt)
+                                                  opt=self.opt, n_oov=self.n_oov)
         return self._engines[key]
 
     def encode(self, data):

@@ -354,6 +354,14 @@ int case_copy_scatter(const int32_t* map, int map_ld, int map_off, const float* 
                       const float* fac, int fac_ld, float* dist, int ldd, int B, int W, int S, int V,
                       case_stream_t stream);
 
+/* copy_topk's folding step (common/Utils.py:170-178) on an extended row gen [R][ldg] = [V vocabulary entries | D dynamic
+ * entries]: vocab[v] += sum over d with vocab_map[q][d] == v of dyn[d]; dyn[d] *= overlap[q][d]  (q = r / rows_per_map:
+ * the maps are per query, the rows per hypothesis).  vocab_map int32 [Q][D] is the index form of the reference's one-hot
+ * [Q][D][V]; overlap fp32 [Q][D] (1 = the dynamic word is NOT in the vocabulary).  In place; follow with
+ * case_topk_rows over V + D columns. */
+int case_oov_fold(float* gen, int ldg, int R, int V, int D, const int32_t* vocab_map, const float* overlap,
+                  int rows_per_map, case_stream_t stream);
+
 /* Per-row top-k, values descending, ties -> lower index first (Utils.topk, Utils.py:156-168). */
 int case_topk_rows(const float* dist, int ldd, int R, int V, int k, float* vals, int32_t* idx,
                    case_stream_t stream);
@@ -380,6 +388,10 @@ typedef struct {
    * positions index the concatenation [memory 0 ; memory 1]; rows of cp_ld ints */
   int32_t cp_ld;
   const int32_t* cp_n; const int32_t* cp_uid; const int32_t* cp_first; const int32_t* cp_start; const int32_t* cp_perm;
+  /* case_sparse_tail only: extended vocabulary (pointer-generator OOV extension).  Vext > V: copy targets map[b][s] may
+   * lie in [V, Vext) - per-query dynamic entries that have no logit, so their mixture value is the copy mass alone -
+   * and the top-k indices range over [0, Vext).  0 = V (no extension). */
+  int32_t Vext;
 } case_tail_args_t;
 int case_row_tail(const case_tail_args_t* a, case_stream_t stream);
 int case_row_tail_max_vocab(void);
@@ -415,6 +427,11 @@ typedef struct {
   int32_t* best_len;       /* [B] tokens in best_seq                                     */
   int32_t* out_tokens;     /* [B][Tmax] greedy: per-step token; beam: best sequence      */
   int32_t* n_live;         /* [B] live hypotheses per query after this step (early-exit hint) */
+  /* extended vocabulary: a selected id >= V_in (> 0) is a per-query dynamic (OOV) entry; it is fed back to the decoder as
+   * UNK (it has no embedding row) while tok_ext [R][Tmax+1] keeps the extended id for the returned sequences.
+   * V_in = 0 / tok_ext = NULL: no extension (tok holds both). */
+  int32_t V_in;
+  int32_t* tok_ext;
 } case_select_args_t;
 
 int case_beam_select(const case_select_args_t* a, case_stream_t stream);
@@ -487,6 +504,11 @@ typedef struct {
                                            case_additive_attn_gate and never reads Mv */
   int32_t opt;                          /* CASE_OPT_* bits (0 = default fast path) */
   case_fork_t* fork;                    /* side stream + events of this engine (may be NULL: everything on `stream`) */
+  /* extended vocabulary (pointer-generator OOV extension, the "extended (vocab + OOV) distribution"): map entries in
+   * [V, V + n_oov) are per-query dynamic words; dist / top-k range over V + n_oov ids (ldv >= V + n_oov), an OOV id is
+   * fed back as UNK and kept in tok_ext [R][Tmax+1] for the output.  n_oov = 0: off. */
+  int32_t n_oov;
+  int32_t* tok_ext;
 } case_step_args_t;
 
 /* Enqueue one full decode step t (embedding .. select) for all R rows: the body of the eval loop

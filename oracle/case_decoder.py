@@ -197,8 +197,8 @@ class CaseOracle:
     def stepper(self, inp, dense_onehot: bool = False):
         return _PrefixStepper(self, inp, dense_onehot)
 
-    def incremental(self, inp):
-        return IncrementalStepper(self, inp)
+    def incremental(self, inp, n_oov: int = 0):
+        return IncrementalStepper(self, inp, n_oov)
 
 
 class _PrefixStepper:
@@ -227,8 +227,13 @@ class IncrementalStepper:
     once.  This is the executable spec of the CUDA path's data flow; it is validated against
     ``prefix_forward`` in tests/test_oracle_golden.py."""
 
-    def __init__(self, orc: CaseOracle, inp):
+    def __init__(self, orc: CaseOracle, inp, n_oov: int = 0):
+        """n_oov > 0: pointer-generator OOV extension of CaSE/Model.py:38-48 - ``source_map`` ids in [V, V + n_oov) are
+        per-query dynamic words: the distribution has V + n_oov columns (the one-hot of build_map simply gets that many,
+        Utils.py:344-355 with max = V + n_oov; the generation part is zero there) and a dynamic id is fed back as UNK,
+        having no embedding row."""
         self.o = orc
+        self.n_oov = int(n_oov)
         sd, H = orc.sd, orc.H
         self.ctx = ctx = orc.prepare(inp)
         self.B = ctx['B']
@@ -260,6 +265,7 @@ class IncrementalStepper:
             self.vc[k] = self.vc[k][parents]
         R, t = tokens.numel(), self.t
         q2 = self.row2q
+        tokens = torch.where(tokens >= o.V, torch.full_like(tokens, 100), tokens) if self.n_oov else tokens   # OOV -> UNK
         x_in = F.embedding(tokens, sd['embedding.0.weight']) * math.sqrt(H) + sd['embedding.1.pe'][t]
         feat = self.feat[q2]
         valid = tokens.ne(0)
@@ -309,6 +315,8 @@ class IncrementalStepper:
         gates = torch.softmax(F.linear(torch.cat([hN] + cm, -1), sd['mix.weight'], sd['mix.bias']), -1)
         copy_w = torch.cat([gates[:, i + 1:i + 2] * ps[i] for i in range(o.M)], -1)
         dist = gates[:, :1] * gen
+        if self.n_oov:
+            dist = torch.cat([dist, dist.new_zeros(R, self.n_oov)], 1)
         dist = dist.scatter_add(1, self.ctx['source_map'][q2], copy_w)
         self.t += 1
         self.last = dict(dist=dist, gen=gen, logits=logits, gates=gates, p=ps, ctx=cm, dec_out=hN,

@@ -26,6 +26,17 @@ def topk(dist, k):
     return torch.max(dist, dim=1, keepdim=True)
 
 
+def copy_topk(gen_output, vocab_map, vocab_overlap, k):
+    """Utils.copy_topk (Utils.py:170-178): ``gen_output`` [R, V + D] = vocabulary entries then D dynamic entries;
+    ``vocab_map`` one-hot [R, D, V] folds every dynamic entry onto its vocabulary id, ``vocab_overlap`` [R, D] keeps only
+    the dynamic entries that are NOT vocabulary words; top-k over the V + D columns."""
+    V = vocab_map.size(-1)
+    vocab, dyn = gen_output[:, :V], gen_output[:, V:]
+    vocab = vocab + torch.bmm(dyn.unsqueeze(1), vocab_map).squeeze(1)
+    dyn = dyn * vocab_overlap
+    return topk(torch.cat([vocab, dyn], dim=-1), k)
+
+
 def greedy(stepper, max_len: int) -> torch.Tensor:
     """Generations.greedy (Generations.py:66-110): EOS at t==0 is rewritten to UNK but still ends
     the row; ended rows emit PAD (and PAD is what is fed back)."""

@@ -75,3 +75,23 @@ def build_masque(name='masque_module_greedy'):
     inp = syn.make_case_inputs(int(cfg['iseed']), int(cfg['B']), int(cfg['Lq']), int(cfg['NP']), int(cfg['Lp']),
                                V_SMALL, H)
     return z, cfg, msd, inp
+
+
+def glks_inputs(seed=31, R=6, V=700, Lb=90, H=256, D=40):
+    """Seeded inputs of the GLKS Mixturer / copy_topk fixture (tests/golden/make_glks_golden.py reads them from here)."""
+    g = torch.Generator().manual_seed(seed)
+    state = torch.randn(R, 1, H, generator=g)
+    p_v = torch.softmax(torch.randn(R, V, generator=g) * 2, 1)
+    p_k = torch.softmax(torch.randn(R, Lb, generator=g) * 2, 1)
+    p_k[:, ::9] = 0.0                                             # masked background positions carry no mass
+    bmap = torch.randint(0, V, (R, Lb), generator=g)
+    bmap[:, 5] = bmap[:, 6] = bmap[:, 7]                          # repeated copy targets
+    w = torch.randn(1, H, generator=g) * 0.2
+    b = torch.randn(1, generator=g)
+    # copy_topk: extended rows [V + D], D dynamic words, some of them vocabulary words (overlap 0)
+    gen_ext = torch.softmax(torch.randn(R, V + D, generator=g) * 2, 1)
+    vmap = torch.randint(0, V, (R, D), generator=g)
+    vmap[:, 3] = vmap[:, 4] = 100                                 # two OOV words fold onto UNK
+    overlap = (torch.rand(R, D, generator=g) > 0.5).float()
+    overlap[:, 3] = overlap[:, 4] = 1.0
+    return dict(state=state, p_v=p_v, p_k=p_k, bmap=bmap, w=w, b=b, gen_ext=gen_ext, vmap=vmap, overlap=overlap)
