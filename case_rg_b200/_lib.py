@@ -34,7 +34,7 @@ class RowLinArgs(C.Structure):
 
 class LayerWeights(C.Structure):
     _fields_ = [(n, vp) for n in ('Wqkv_t', 'bqkv', 'Wo_t', 'bo', 'Wq2_t', 'bq2', 'Wo2_t', 'bo2', 'W1_t', 'b1',
-                                  'W2_t', 'b2', 'ln1_g', 'ln1_b', 'ln2_g', 'ln2_b', 'ln3_g', 'ln3_b', 'Wc', 'Wr')]
+                                  'W2_t', 'b2', 'ln1_g', 'ln1_b', 'ln2_g', 'ln2_b', 'ln3_g', 'ln3_b', 'Wc')]
 
 
 class SelectArgs(C.Structure):
@@ -45,7 +45,7 @@ class SelectArgs(C.Structure):
 
 
 class PostLinear(C.Structure):
-    _fields_ = [('Wc', vp), ('bias', vp), ('out', vp), ('nchunk', i32), ('seg', i32 * 3), ('Wr', vp)]
+    _fields_ = [('Wc', vp), ('bias', vp), ('out', vp), ('nchunk', i32), ('seg', i32 * 3)]
 
 
 class ChainPost(C.Structure):
@@ -76,7 +76,7 @@ class StepArgs(C.Structure):
                 ('out_tokens', vp), ('n_live', vp),
                 ('x_in', vp), ('h', vp), ('bbuf', vp), ('q2', vp), ('part_ml', vp), ('part_acc', vp), ('qa', vp),
                 ('attn_un', vp * 2), ('stats', vp * 2), ('ctxp', vp * 2), ('hN', vp), ('ctx', vp * 2), ('gates', vp),
-                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp), ('prow', vp), ('h0', vp), ('qa1', vp), ('base_ms', vp), ('base_e', vp), ('base_i', vp), ('xcount', vp), ('xprefix', vp), ('xslots', i32), ('xidx', vp), ('xorder', vp), ('qcount', vp), ('Wqa_c', vp * 2), ('Wg_c', vp), ('xns', vp), ('cp_n', vp), ('cp_uid', vp), ('cp_first', vp), ('cp_start', vp), ('cp_perm', vp), ('cp_ld', i32), ('Gv', vp * 2), ('opt', i32), ('fork', vp), ('n_oov', i32), ('tok_ext', vp), ('Wqa_r', vp * 2), ('Wg_r', vp)]
+                ('fac', vp), ('gfeat', vp), ('logits', vp), ('dist', vp), ('top_vals', vp), ('top_idx', vp), ('vocab_ws', vp), ('prow', vp), ('h0', vp), ('qa1', vp), ('base_ms', vp), ('base_e', vp), ('base_i', vp), ('xcount', vp), ('xprefix', vp), ('xslots', i32), ('xidx', vp), ('xorder', vp), ('qcount', vp), ('Wqa_c', vp * 2), ('Wg_c', vp), ('xns', vp), ('cp_n', vp), ('cp_uid', vp), ('cp_first', vp), ('cp_start', vp), ('cp_perm', vp), ('cp_ld', i32), ('Gv', vp * 2), ('opt', i32), ('fork', vp), ('n_oov', i32), ('tok_ext', vp)]
 
 
 class GttpStepArgs(C.Structure):

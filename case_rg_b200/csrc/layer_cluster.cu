@@ -62,7 +62,6 @@ constexpr int CMAXF = 5;           // front halves per launch: up to 4 fused lay
 
 struct ChainLayer {                // device pointers of one layer
   const char* wc;                  // cluster-packed matrices
-  const char* wr;                  // row-split packing of the same matrices (layer_rows_kernel), may be NULL
   const float *bqkv, *bo, *bq2, *bo2, *b1, *b2, *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
   bf16* kc; bf16* vc;              // self-attention cache of the layer
   const bf16* kx;                  // cross-attention K|V tiles of the layer (fused small cross-attention only)
@@ -88,7 +87,7 @@ struct ChainArgs {
   // post linears: y = [segments] . W^T + bias on the rows that leave the LAST back half of the launch
   // (attention query = [h ; feat], gen.0 = [x_in ; norm1(h) ; feat]; Model.py:108, 115)
   int npost;
-  struct { const char* w; const char* wr; const float* bias; float* out; int nchunk; int seg[3]; } post[2];
+  struct { const char* w; const float* bias; float* out; int nchunk; int seg[3]; } post[2];
   const float* feat; const float* xin; const float* lnN_g; const float* lnN_b; float* hN_out;
   long long* dbg;                  // optional stage clock stamps of CTA 0 (case_debug_chain_timing)
 };
@@ -856,19 +855,16 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
 // Row-split form of the same row work (the default): no cluster, no exchange.
 //
 // The column-split cluster above pays one DSMEM exchange (~0.45 us with its wait) after every dependent linear - six
-// per layer - because a CTA only ever holds 64 of the 256 columns of a row; and its MMA stage is latency-bound (one warp
-// = one 8-column subtile = two dependent chains of eight HMMAs).  Here a CTA owns RB = 4 decode rows END TO END and a
-// warp owns 32 output columns of every linear: four n-tiles x two k-parities = eight INDEPENDENT accumulator chains per
-// warp, so the tensor pipe is fed at issue rate.  A matrix streams through a 4-slot ring as four K-chunks [256 n][64 k]
-// (32 KB, "row-split packing": chunk position p of row n holds k-chunk p ^ (n & 7)) fed by four producer warps (one
-// bulk copy in flight per warp); the stage is bound by that stream (128 KB per matrix into the SM).  Results go straight
-// into local shared-memory tiles - dependent linears are separated by one 256-thread named barrier.  64 CTAs at
-// R = 256 read 64 x 1 MB per layer from L2 (the matrices are L2 resident, requests of neighbouring SMs for the same
-// lines are merged there).  The self-attention history is not staged in shared memory (4 rows x 8 heads x 2 x t x 64 B
-// does not fit beside the ring): 16 lanes per (row, head) read K / V rows from L2, which the launch prefetches there as
-// soon as the row table is known.
+// per layer - because a CTA only ever holds 64 of the 256 columns of a row.  Here a CTA owns RB = 4 decode rows END TO
+// END: it streams EVERY [64 n][256 k] weight slice of a matrix (the same cluster-packed blob, rank after rank) through
+// a 4-slot ring fed by four producer warps (one bulk copy in flight per warp: ~200 GB/s into the SM), eight consumer
+// warps compute 8 columns each per slice, and the results go straight into local shared-memory tiles - dependent
+// linears are separated by one 256-thread named barrier.  64 CTAs at R = 256 read 64 x 1 MB per layer from L2 (the
+// matrices are L2 resident and requests of neighbouring SMs for the same lines are merged there).  The self-attention
+// history is not staged in shared memory (4 rows x 8 heads x 2 x t x 64 B does not fit beside the ring): 16 lanes per
+// (row, head) read K / V rows from L2, which the launch prefetches there as soon as the row table is known.
 constexpr int RB = 4;                    // decode rows per CTA
-constexpr int RCW = 8;                   // consumer warps: warp w = output columns 32w .. 32w+31 of every linear
+constexpr int RCW = 8;                   // consumer warps: warp w = columns 8w .. 8w+7 of the current 64-column slice
 constexpr int RCT = RCW * 32;
 constexpr int RPW = 4;                   // producer warps = weight slots
 constexpr int RNT = RCT + RPW * 32;
@@ -934,9 +930,9 @@ __global__ __launch_bounds__(RNT, 1) void layer_rows_kernel(const ChainArgs a) {
   const uint32_t s_base = smem_u32(sm);
   const uint32_t s_bar = s_base + R_OFF_BAR;           // full[p] at +8p, empty[p] at +8(RPW + p)
 
-  // ---- weight sequence of this launch, in K-chunks [256 n][64 k] (chunk kc of matrix k = slice 4k + kc):
+  // ---- weight sequence of this launch, in slices of [64 n][256 k] (rank c of matrix k = slice 4k + c):
   // [Wo2 W1 W2 of the initial back half], the matrices of the fused layers in natural order (Wq Wk Wv Wo Wq2 | Wo2 W1
-  // W2), Wq Wk Wv Wo Wq2 of the last front, then the 256-column input chunks of the post linears
+  // W2), Wq Wk Wv Wo Wq2 of the last front, then the post linears (rank-major: all chunks of rank c, then rank c+1)
   const int nback = a.has_back ? 3 : 0;
   const int nlayer_seq = nback + (a.nfront > 0 ? 8 * (a.nfront - 1) + 5 : 0);
   const int npost0 = a.npost > 0 ? a.post[0].nchunk : 0, npost1 = a.npost > 1 ? a.post[1].nchunk : 0;
@@ -958,15 +954,16 @@ __global__ __launch_bounds__(RNT, 1) void layer_rows_kernel(const ChainArgs a) {
       const int p = warp - RCW;
       const uint32_t full = s_bar + 8 * p, empty = s_bar + 8 * (RPW + p), dst = s_base + R_OFF_W + p * CWB;
       for (int s = p; s < nslices; s += RPW) {
-        const int k = s / CL, kc = s % CL;             // matrix k of the sequence, K-chunk kc
+        const int k = s / CL, c = s % CL;
         const char* src;
-        if (k < nback) src = a.back.wr + (size_t)((5 + k) * CL + kc) * CWB;
+        if (k < nback) src = a.back.wc + (size_t)(c * 8 + 5 + k) * CWB;
         else if (k < nlayer_seq) {
           const int kk = k - nback;
-          src = a.layers[kk >> 3].wr + (size_t)((kk & 7) * CL + kc) * CWB;
+          src = a.layers[kk >> 3].wc + (size_t)(c * 8 + (kk & 7)) * CWB;
         } else {
-          const int kp = k - nlayer_seq;               // input chunk kp of the post linears, in order
-          src = kp < npost0 ? a.post[0].wr + (size_t)(kp * CL + kc) * CWB : a.post[1].wr + (size_t)((kp - npost0) * CL + kc) * CWB;
+          int sp = s - CL * nlayer_seq;                // slice index inside the post region
+          if (sp < CL * npost0) src = a.post[0].w + (size_t)sp * CWB;            // [rank][chunk] is the blob's own order
+          else src = a.post[1].w + (size_t)(sp - CL * npost0) * CWB;
         }
         const int use = s / RPW;
         if (use > 0) c_mb_wait(empty, (uint32_t)(use - 1) & 1u);
@@ -981,7 +978,7 @@ __global__ __launch_bounds__(RNT, 1) void layer_rows_kernel(const ChainArgs a) {
   const int g = lane >> 2, tq = lane & 3;              // MMA / epilogue role: row g (valid below RB), column pair tq
   const bool erow = g < RB;
   const int er = r0 + g, erl = min(er, a.R - 1);
-  const int wcol = 32 * warp + 2 * tq;                 // the lane's first column pair (n-tile j adds 8 j)
+  const int wcol = 8 * warp + 2 * tq;                  // the lane's column pair inside a 64-column slice
   // attention role: 16 lanes per (row, head); a pass covers 16 of the RB * NH pairs
   const int acp = tid & 15;
 
@@ -1013,53 +1010,21 @@ __global__ __launch_bounds__(RNT, 1) void layer_rows_kernel(const ChainArgs a) {
     reinterpret_cast<uint32_t*>(pt2 + RB * CALD)[i] = 0u;
   }
 
-  int slice = 0;                                       // K-chunks consumed so far (uniform over the consumers)
-  // acc += A[8 x 256] . W[32w .. 32w+31][256]^T for one matrix = four K-chunks of the ring.  Per 16-wide k-step: one
-  // ldmatrix.x2 of A, two ldmatrix.x4 of W (n-tiles 2p, 2p+1: low / high k halves), four HMMAs on independent chains.
-  auto mma_matrix = [&](uint32_t a_tile, float (&acc)[4][2][4]) {
-    const uint32_t a_base = a_tile + (uint32_t)((lane & 7) * CALD + ((lane >> 3) & 1) * 8) * 2;
-    const int mtx = lane >> 3;                         // ldmatrix.x4: matrix (n-tile 2p + (mtx >> 1), k half mtx & 1)
+  int slice = 0;                                       // slices consumed so far (uniform over the consumers)
+  // y[:, 64c + 8w .. +7] of one matrix: D = A . W^T for the four slices; epi(ecol, d) gets the lane's column pair
+  auto linear = [&](uint32_t a_tile, auto&& epi) {
 #pragma unroll 1
-    for (int kc = 0; kc < CL; ++kc) {
+    for (int c = 0; c < CL; ++c) {
       const int p = slice % RPW;
       c_mb_wait(s_bar + 8 * p, (uint32_t)(slice / RPW) & 1u);
-      const uint32_t slot = s_base + R_OFF_W + p * CWB;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint32_t af[2];
-        c_ldsm2(af, a_base + (uint32_t)(4 * kc + q) * 32);
-#pragma unroll
-        for (int pp = 0; pp < 2; ++pp) {
-          const int n = 32 * warp + 8 * (2 * pp + (mtx >> 1)) + (lane & 7);
-          uint32_t b[4];
-          c_ldsm4(b, slot + (uint32_t)n * 128 + (uint32_t)(((2 * q + (mtx & 1)) ^ (n & 7)) << 4));
-          c_mma8(acc[2 * pp][q & 1], af, b[0], b[1]);
-          c_mma8(acc[2 * pp + 1][q & 1], af, b[2], b[3]);
-        }
-      }
+      const float2 d = mma_cols8(a_tile, s_base + R_OFF_W + p * CWB, warp);
       __syncwarp();
       if (lane == 0) c_mb_arrive(s_bar + 8 * (RPW + p));   // this warp is done with the slot
+      epi(CCOL * c + wcol, d);
       ++slice;
     }
   };
-  auto acc_zero = [&](float (&acc)[4][2][4]) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) { acc[j][h2][0] = acc[j][h2][1] = acc[j][h2][2] = acc[j][h2][3] = 0.f; }
-  };
-  // one linear: epi(ecol, d) for the lane's four column pairs (row g)
-  auto linear = [&](uint32_t a_tile, const float* bvec, auto&& epi) {
-    float2 bias[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) bias[j] = __ldg(reinterpret_cast<const float2*>(bvec + wcol + 8 * j));   // in flight during the MMAs
-    float acc[4][2][4];
-    acc_zero(acc);
-    mma_matrix(a_tile, acc);
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      epi(wcol + 8 * j, make_float2(acc[j][0][0] + acc[j][1][0] + bias[j].x, acc[j][0][1] + acc[j][1][1] + bias[j].y));
-  };
+  auto bias2 = [&](const float* bvec, int ecol) -> float2 { return __ldg(reinterpret_cast<const float2*>(bvec + ecol)); };
 
   // ---- prow[row][j] = physical row | masked bit for j = 0..t (the first launch of a step derives and publishes it)
   auto load_prow = [&](bool derive) {
@@ -1122,20 +1087,24 @@ __global__ __launch_bounds__(RNT, 1) void layer_rows_kernel(const ChainArgs a) {
   auto run_post = [&]() {
     rows_sync();                                       // the tiles (and LA when norm1 is a segment) are complete
     for (int p = 0; p < a.npost; ++p) {
-      float2 bias[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bias[j] = __ldg(reinterpret_cast<const float2*>(a.post[p].bias + wcol + 8 * j));
-      float acc[4][2][4];
-      acc_zero(acc);
-      for (int j = 0; j < a.post[p].nchunk; ++j) {
-        const int kind = a.post[p].seg[j];
-        mma_matrix(kind == SEG_H ? smem_u32(pt0) : (kind == SEG_FEAT ? smem_u32(pt1) : (kind == SEG_XIN ? smem_u32(pt2) : s_la)), acc);
-      }
-      if (erow && er < a.R) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<float2*>(a.post[p].out + (size_t)er * H + wcol + 8 * j) =
-              make_float2(acc[j][0][0] + acc[j][1][0] + bias[j].x, acc[j][0][1] + acc[j][1][1] + bias[j].y);
+      const int nch = a.post[p].nchunk;
+#pragma unroll 1
+      for (int c = 0; c < CL; ++c) {
+        const int ecol = CCOL * c + wcol;
+        const float2 bias = bias2(a.post[p].bias, ecol);
+        float2 acc = make_float2(0.f, 0.f);
+        for (int j = 0; j < nch; ++j) {
+          const int kind = a.post[p].seg[j];
+          const uint32_t tile = kind == SEG_H ? smem_u32(pt0) : (kind == SEG_FEAT ? smem_u32(pt1) : (kind == SEG_XIN ? smem_u32(pt2) : s_la));
+          const int sl = slice % RPW;
+          c_mb_wait(s_bar + 8 * sl, (uint32_t)(slice / RPW) & 1u);
+          const float2 d = mma_cols8(tile, s_base + R_OFF_W + sl * CWB, warp);
+          __syncwarp();
+          if (lane == 0) c_mb_arrive(s_bar + 8 * (RPW + sl));
+          acc.x += d.x; acc.y += d.y;
+          ++slice;
+        }
+        if (erow && er < a.R) *reinterpret_cast<float2*>(a.post[p].out + (size_t)er * H + ecol) = make_float2(acc.x + bias.x, acc.y + bias.y);
       }
     }
   };
@@ -1144,25 +1113,28 @@ __global__ __launch_bounds__(RNT, 1) void layer_rows_kernel(const ChainArgs a) {
   // h2 = b + ctx.Wo2 + bo2; c = LN3(h2); h3 = c + W2.gelu(W1.c + b1) + b2 (TransformerDecoder.py:82-89)
   auto back_half = [&](const ChainLayer& Lb, float* hdst) {
     const LnPar ln3 = ln_load(Lb.ln3_g, Lb.ln3_b);
-    linear(s_xa, Lb.bo2, [&](int ecol, float2 d) {
+    linear(s_xa, [&](int ecol, float2 d) {
+      const float2 b = bias2(Lb.bo2, ecol);
       if (erow) {
         const float2 r = *reinterpret_cast<const float2*>(res + g * CFLD + ecol);
-        *reinterpret_cast<float2*>(xf + g * CFLD + ecol) = make_float2(r.x + d.x, r.y + d.y);
+        *reinterpret_cast<float2*>(xf + g * CFLD + ecol) = make_float2(r.x + d.x + b.x, r.y + d.y + b.y);
       }
     });
     rows_sync();
     stamp();
     ln_rows_full(xf, ln3, la, res, nullptr, r0, a.R);
     rows_sync();
-    linear(s_la, Lb.b1, [&](int ecol, float2 d) {
-      if (erow) *reinterpret_cast<uint32_t*>(xa + g * CALD + ecol) = c_pack(gelu_erf(d.x), gelu_erf(d.y));
+    linear(s_la, [&](int ecol, float2 d) {
+      const float2 b = bias2(Lb.b1, ecol);
+      if (erow) *reinterpret_cast<uint32_t*>(xa + g * CALD + ecol) = c_pack(gelu_erf(d.x + b.x), gelu_erf(d.y + b.y));
     });
     rows_sync();
     stamp();
-    linear(s_xa, Lb.b2, [&](int ecol, float2 d) {
+    linear(s_xa, [&](int ecol, float2 d) {
+      const float2 b = bias2(Lb.b2, ecol);
       if (erow) {
         const float2 r = *reinterpret_cast<const float2*>(res + g * CFLD + ecol);
-        const float2 h = make_float2(r.x + d.x, r.y + d.y);
+        const float2 h = make_float2(r.x + d.x + b.x, r.y + d.y + b.y);
         *reinterpret_cast<float2*>(xf + g * CFLD + ecol) = h;
         if (hdst != nullptr && er < a.R) *reinterpret_cast<float2*>(hdst + (size_t)er * H + ecol) = h;
       }
@@ -1260,19 +1232,22 @@ __global__ __launch_bounds__(RNT, 1) void layer_rows_kernel(const ChainArgs a) {
     ln_rows_full(xf, ln1, la, res, nullptr, r0, a.R);
     rows_sync();
     // ---- F1: q, k, v (k / v of the newest position: bf16 to the cache and to KCUR / VCUR)
-    linear(s_la, Lf.bqkv, [&](int ecol, float2 d) {
-      if (erow) *reinterpret_cast<float2*>(q_s + g * H + ecol) = d;
+    linear(s_la, [&](int ecol, float2 d) {
+      const float2 b = bias2(Lf.bqkv, ecol);
+      if (erow) *reinterpret_cast<float2*>(q_s + g * H + ecol) = make_float2(d.x + b.x, d.y + b.y);
     });
-    linear(s_la, Lf.bqkv + H, [&](int ecol, float2 d) {
+    linear(s_la, [&](int ecol, float2 d) {
+      const float2 b = bias2(Lf.bqkv + H, ecol);
       if (erow) {
-        const uint32_t kp = c_pack(d.x, d.y);
+        const uint32_t kp = c_pack(d.x + b.x, d.y + b.y);
         *reinterpret_cast<uint32_t*>(kcur + g * CALD + ecol) = kp;
         if (er < a.R) *reinterpret_cast<uint32_t*>(Lf.kc + ((size_t)er * Tmax + t) * H + ecol) = kp;
       }
     });
-    linear(s_la, Lf.bqkv + 2 * H, [&](int ecol, float2 d) {
+    linear(s_la, [&](int ecol, float2 d) {
+      const float2 b = bias2(Lf.bqkv + 2 * H, ecol);
       if (erow) {
-        const uint32_t vp = c_pack(d.x, d.y);
+        const uint32_t vp = c_pack(d.x + b.x, d.y + b.y);
         *reinterpret_cast<uint32_t*>(vcur + g * CALD + ecol) = vp;
         if (er < a.R) *reinterpret_cast<uint32_t*>(Lf.vc + ((size_t)er * Tmax + t) * H + ecol) = vp;
       }
@@ -1369,10 +1344,11 @@ __global__ __launch_bounds__(RNT, 1) void layer_rows_kernel(const ChainArgs a) {
     rows_sync();
     stamp();
     // ---- F3: h1 = a + ctx.Wo + bo
-    linear(s_xa, Lf.bo, [&](int ecol, float2 d) {
+    linear(s_xa, [&](int ecol, float2 d) {
+      const float2 b = bias2(Lf.bo, ecol);
       if (erow) {
         const float2 r = *reinterpret_cast<const float2*>(res + g * CFLD + ecol);
-        *reinterpret_cast<float2*>(xf + g * CFLD + ecol) = make_float2(r.x + d.x, r.y + d.y);
+        *reinterpret_cast<float2*>(xf + g * CFLD + ecol) = make_float2(r.x + d.x + b.x, r.y + d.y + b.y);
       }
     });
     rows_sync();
@@ -1381,9 +1357,10 @@ __global__ __launch_bounds__(RNT, 1) void layer_rows_kernel(const ChainArgs a) {
     rows_sync();
     stamp();
     // ---- F5: q2 = b.Wq2 + bq2 (pre-scaled): to global for a big cross-attention, or kept for the fused one
-    linear(s_la, Lf.bq2, [&](int ecol, float2 d) {
+    linear(s_la, [&](int ecol, float2 d) {
+      const float2 b = bias2(Lf.bq2, ecol);
       if (erow) {
-        const float2 q2v = d;
+        const float2 q2v = make_float2(d.x + b.x, d.y + b.y);
         if (!fused) { if (er < a.R) *reinterpret_cast<float2*>(a.q2_out + (size_t)er * H + ecol) = q2v; }
         else *reinterpret_cast<float2*>(q_s + g * H + ecol) = q2v;
       }
@@ -1516,7 +1493,6 @@ extern "C" int case_debug_chain_max_clusters(int smem, int cluster) {
 
 static void fill_layer(ChainLayer& L, const case_layer_weights_t* w, void* kc, void* vc, const void* kx) {
   L.wc = reinterpret_cast<const char*>(w->Wc);
-  L.wr = reinterpret_cast<const char*>(w->Wr);
   L.bqkv = w->bqkv; L.bo = w->bo; L.bq2 = w->bq2; L.bo2 = w->bo2; L.b1 = w->b1; L.b2 = w->b2;
   L.ln1_g = w->ln1_g; L.ln1_b = w->ln1_b; L.ln2_g = w->ln2_g; L.ln2_b = w->ln2_b; L.ln3_g = w->ln3_g; L.ln3_b = w->ln3_b;
   L.kc = (bf16*)kc; L.vc = (bf16*)vc; L.kx = (const bf16*)kx;
@@ -1529,8 +1505,8 @@ static int fill_post(ChainArgs& a, const case_chain_post_t* post) {
   a.lnN_g = post->ln_g; a.lnN_b = post->ln_b; a.hN_out = post->ln_out;
   for (int p = 0; p < post->npost; ++p) {
     const case_post_linear_t& l = post->lin[p];
-    CB_REQUIRE((l.Wc || l.Wr) && l.bias && l.out && l.nchunk >= 1 && l.nchunk <= 3, "case_layer_chain: post linear needs Wc or Wr, bias, out, 1..3 chunks");
-    a.post[p].w = reinterpret_cast<const char*>(l.Wc); a.post[p].wr = reinterpret_cast<const char*>(l.Wr); a.post[p].bias = l.bias; a.post[p].out = l.out; a.post[p].nchunk = l.nchunk;
+    CB_REQUIRE(l.Wc && l.bias && l.out && l.nchunk >= 1 && l.nchunk <= 3, "case_layer_chain: post linear needs Wc, bias, out, 1..3 chunks");
+    a.post[p].w = reinterpret_cast<const char*>(l.Wc); a.post[p].bias = l.bias; a.post[p].out = l.out; a.post[p].nchunk = l.nchunk;
     for (int j = 0; j < 3; ++j) {
       a.post[p].seg[j] = j < l.nchunk ? l.seg[j] : 0;
       if (j < l.nchunk) {
@@ -1552,21 +1528,8 @@ static int launch_rows(ChainArgs& a, cudaStream_t stream) {
   return check_launch("case_layer_chain(rows)");
 }
 
-static bool rows_ready(const ChainArgs& a) {    // every matrix of the launch has its row-split packing
-  if (a.has_back && !a.back.wr) return false;
-  for (int f = 0; f < a.nfront; ++f) if (!a.layers[f].wr) return false;
-  for (int p = 0; p < a.npost; ++p) if (!a.post[p].wr) return false;
-  return true;
-}
-
 static int launch_chain(ChainArgs& a, cudaStream_t stream) {
-  if (!launch_opts().cluster_layers && rows_ready(a)) return launch_rows(a, stream);
-  {
-    bool ok = !a.has_back || a.back.wc;
-    for (int f = 0; f < a.nfront; ++f) ok = ok && a.layers[f].wc;
-    for (int p = 0; p < a.npost; ++p) ok = ok && a.post[p].w;
-    CB_REQUIRE(ok, "case_layer_chain: the cluster kernel needs the cluster-packed weights (Wc)");
-  }
+  if (!launch_opts().cluster_layers) return launch_rows(a, stream);
   a.dbg = g_chain_dbg;
   // KV history of the front halves, or (launch without front half) the third post tile
   const size_t smem = (size_t)OFF_KV + (a.nfront > 0 ? (size_t)4 * CROWS * a.Tmax * 64 : (size_t)CROWS * CALD * 2 + 2 * CWB);
@@ -1593,8 +1556,8 @@ extern "C" int case_layer_chain(const case_layer_weights_t* wb, const case_layer
                                 const case_chain_post_t* post, case_stream_t stream) {
   CB_REQUIRE(wb || wf, "case_layer_chain: neither a back nor a front layer given");
   CB_REQUIRE(R > 0 && Tmax >= 1 && Tmax <= CTMAX && t >= 0 && t < Tmax, "case_layer_chain: bad R / t / Tmax (Tmax <= 48)");
-  CB_REQUIRE(!wb || ((wb->Wc || wb->Wr) && b_in && part_ml && part_acc && h_out && nsplit >= 1), "case_layer_chain: back half needs Wc / Wr, b_in, partials, h_out");
-  CB_REQUIRE(!wf || ((wf->Wc || wf->Wr) && kcache && vcache && anc && tok && b_out && q2_out), "case_layer_chain: front half needs Wc / Wr, caches, anc, tok, b_out, q2_out");
+  CB_REQUIRE(!wb || (wb->Wc && b_in && part_ml && part_acc && h_out && nsplit >= 1), "case_layer_chain: back half needs Wc, b_in, partials, h_out");
+  CB_REQUIRE(!wf || (wf->Wc && kcache && vcache && anc && tok && b_out && q2_out), "case_layer_chain: front half needs Wc, caches, anc, tok, b_out, q2_out");
   CB_REQUIRE(wb || h_in || (E && x_out), "case_layer_chain: a front-only launch needs h_in or (E, x_out)");
   ChainArgs a;
   memset(&a, 0, sizeof(a));
@@ -1628,7 +1591,7 @@ extern "C" int case_layer_stack(const case_layer_weights_t* layers, int nfused, 
   memset(&a, 0, sizeof(a));
   a.R = R; a.t = t; a.Tmax = Tmax; a.nsplit = 1; a.has_back = 0; a.nfront = nfused + 1; a.first = first; a.W = W; a.S0 = S0;
   for (int f = 0; f <= nfused; ++f) {
-    CB_REQUIRE((layers[f].Wc || layers[f].Wr) && kcache[f] && vcache[f] && (f == nfused || kx[f]), "case_layer_stack: layer pointers missing");
+    CB_REQUIRE(layers[f].Wc && kcache[f] && vcache[f] && (f == nfused || kx[f]), "case_layer_stack: layer pointers missing");
     fill_layer(a.layers[f], &layers[f], kcache[f], vcache[f], f < nfused ? kx[f] : nullptr);
   }
   a.mask0 = mask0; a.h_fused_out = h_fused_out;

@@ -228,8 +228,7 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
                                       a->part_acc, st);
   };
   auto nparts_of = [&](int L) -> int { return (L / 4 == 1 && xpart) ? a->xslots : a->nsplit_x[L / 4]; };
-  const bool chain = dt == CASE_BF16 && !(opt & CASE_OPT_NO_CHAIN) && (a->layers[0].Wc != nullptr || a->layers[0].Wr != nullptr) &&
-                     a->Tmax <= case_layer_chain_max_tmax();
+  const bool chain = dt == CASE_BF16 && !(opt & CASE_OPT_NO_CHAIN) && a->layers[0].Wc != nullptr && a->Tmax <= case_layer_chain_max_tmax();
   if (chain) {
     // Cluster kernels: [embed + front 0] x [back 0 + front 1] x ... x [back 7], one launch between
     // cross-attentions.  The two additive attentions only feed the mixture gates and the copy scatter,
@@ -243,13 +242,12 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
     // plus the first half-layer of the second stack is ONE launch; otherwise one launch per half-layer pair
     const bool stack0 = !(opt & CASE_OPT_NO_STACK) && a->S[0] <= case_layer_chain_max_s0();
     // attention queries, norm1 and gen.0 ride on the cluster launches as post linears (no row_linear launches)
-    const bool post = !(opt & CASE_OPT_NO_POST) && ((a->Wqa_c[0] != nullptr && a->Wqa_c[1] != nullptr && a->Wg_c != nullptr) ||
-                                                    (a->Wqa_r[0] != nullptr && a->Wqa_r[1] != nullptr && a->Wg_r != nullptr));
+    const bool post = !(opt & CASE_OPT_NO_POST) && a->Wqa_c[0] != nullptr && a->Wqa_c[1] != nullptr && a->Wg_c != nullptr;
     auto qa_post = [&](int i, float* out) {
       case_chain_post_t p;
       memset(&p, 0, sizeof(p));
       p.npost = 1; p.W = W; p.feat = a->feat;
-      p.lin[0].Wc = a->Wqa_c[i]; p.lin[0].Wr = a->Wqa_r[i]; p.lin[0].bias = a->bqa[i]; p.lin[0].out = out; p.lin[0].nchunk = 2;
+      p.lin[0].Wc = a->Wqa_c[i]; p.lin[0].bias = a->bqa[i]; p.lin[0].out = out; p.lin[0].nchunk = 2;
       p.lin[0].seg[0] = CASE_SEG_H; p.lin[0].seg[1] = CASE_SEG_FEAT;
       return p;
     };
@@ -283,7 +281,7 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
       if (post && L == 8) {
         pl = qa_post(1, fork ? a->qa1 : a->qa);
         pl.npost = 2; pl.x_in = a->x_in; pl.ln_g = a->lnN_g; pl.ln_b = a->lnN_b; pl.ln_out = a->hN;
-        pl.lin[1].Wc = a->Wg_c; pl.lin[1].Wr = a->Wg_r; pl.lin[1].bias = a->bg; pl.lin[1].out = a->gfeat; pl.lin[1].nchunk = 3;
+        pl.lin[1].Wc = a->Wg_c; pl.lin[1].bias = a->bg; pl.lin[1].out = a->gfeat; pl.lin[1].nchunk = 3;
         pl.lin[1].seg[0] = CASE_SEG_XIN; pl.lin[1].seg[1] = CASE_SEG_HLN; pl.lin[1].seg[2] = CASE_SEG_FEAT;
       }
       TRY(case_layer_chain(wb, wf, nullptr, a->E, a->pe, 16.0f /* sqrt(256) */, a->x_in, a->bbuf, a->part_ml,

@@ -165,28 +165,6 @@ def pack_cluster(mats) -> torch.Tensor:
     return w[:, :, n[:, None], src].permute(1, 0, 2, 3, 4).contiguous()
 
 
-def pack_rows(mats) -> torch.Tensor:
-    """nn.Linear weights [256 out][256 in] -> the row-split packing of the default layer kernel (csrc/layer_cluster.cu,
-    layer_rows_kernel): bf16 [len(mats)][4 k-chunks][256 n][64 k]; inside the 128-byte row n of a k-chunk the 16-byte
-    chunk kc is stored at position kc ^ (n & 7) (conflict-free ldmatrix)."""
-    w = torch.stack([m.to(torch.bfloat16) for m in mats])              # [m][256 n][256 k]
-    if tuple(w.shape[1:]) != (256, 256):
-        raise ValueError(f'pack_rows needs 256x256 matrices, got {tuple(w.shape)}')
-    M = w.size(0)
-    w = w.view(M, 256, 4, 8, 8).permute(0, 2, 1, 3, 4)                   # [m][kc][n][chunk][8]
-    n = torch.arange(256, device=w.device)
-    src = torch.arange(8, device=w.device)[None, :] ^ (n & 7)[:, None]   # stored position p holds chunk p ^ (n & 7)
-    return w[:, :, n[:, None], src].contiguous()
-
-
-def pack_rows_post(w: torch.Tensor) -> torch.Tensor:
-    """nn.Linear weight [256 out][256 * nchunk in] -> pack_rows of its 256-column input chunks."""
-    N, K = w.shape
-    if N != 256 or K % 256:
-        raise ValueError(f'pack_rows_post needs a [256, 256*n] weight, got {tuple(w.shape)}')
-    return pack_rows([w[:, 256 * j:256 * (j + 1)] for j in range(K // 256)])
-
-
 def pack_post(w: torch.Tensor) -> torch.Tensor:
     """nn.Linear weight [256 out][256 * nchunk in] -> the post-linear layout of the cluster kernels: bf16
     [4 ranks][nchunk][64 n][256 k], chunk kc of row n stored at kc ^ (n & 7) (csrc/layer_cluster.cu)."""
@@ -286,11 +264,9 @@ class CaseWeights:
                          ln2_g=vec(g(p + 'norm2.weight')), ln2_b=vec(g(p + 'norm2.bias')),
                          ln3_g=vec(g(p + 'norm3.weight')), ln3_b=vec(g(p + 'norm3.bias')))
                 if self.cdtype == L.BF16:
-                    eight = [Wi[:H], Wi[H:2 * H], Wi[2 * H:], g(p + 'self_attn.out_proj.weight'),
-                             Wx[:H] * scale, g(p + 'multihead_attn.out_proj.weight'),
-                             g(p + 'linear1.weight'), g(p + 'linear2.weight')]
-                    t['Wc'] = pack_cluster(eight)       # column-split cluster kernel (CASE_OPT_CLUSTER_LAYERS)
-                    t['Wr'] = pack_rows(eight)          # row-split kernel (default)
+                    t['Wc'] = pack_cluster([Wi[:H], Wi[H:2 * H], Wi[2 * H:], g(p + 'self_attn.out_proj.weight'),
+                                            Wx[:H] * scale, g(p + 'multihead_attn.out_proj.weight'),
+                                            g(p + 'linear1.weight'), g(p + 'linear2.weight')])
                 self.keep.append(t)
                 lw = self.layers[i * 4 + l]
                 for k, v in t.items():
@@ -317,8 +293,6 @@ class CaseWeights:
         del self._kv_rows
         self.Wqa_c = [pack_post(g(f'attns.{i}.linear_query.weight')) if bf else None for i in range(2)]
         self.Wg_c = pack_post(g('gen.0.weight')) if bf else None
-        self.Wqa_r = [pack_rows_post(g(f'attns.{i}.linear_query.weight')) if bf else None for i in range(2)]
-        self.Wg_r = pack_rows_post(g('gen.0.weight')) if bf else None
         self.Wv = g('gen.2.weight').contiguous().to(self.tdtype)                               # [V][H]
         self.Wv_tc = pack_vocab_tc(g('gen.2.weight')) if self.cdtype == L.BF16 else None
         self.Wm, self.bm = g('mix.weight').contiguous(), vec(g('mix.bias'))
@@ -572,7 +546,6 @@ class CaseDecodeEngine(_EngineBase):
             a.cp_start, a.cp_perm, a.cp_ld = self.cp_start.data_ptr(), self.cp_perm.data_ptr(), self.cp_uid.size(1)
         if w.Wg_c is not None:
             a.Wqa_c[0], a.Wqa_c[1], a.Wg_c = w.Wqa_c[0].data_ptr(), w.Wqa_c[1].data_ptr(), w.Wg_c.data_ptr()
-            a.Wqa_r[0], a.Wqa_r[1], a.Wg_r = w.Wqa_r[0].data_ptr(), w.Wqa_r[1].data_ptr(), w.Wg_r.data_ptr()
         self.state.bind(a)
         for n in ('x_in', 'h', 'bbuf', 'q2', 'part_ml', 'part_acc', 'qa', 'hN', 'gates', 'fac', 'gfeat', 'logits',
                   'dist', 'top_vals', 'top_idx', 'prow', 'h0', 'qa1', 'base_ms', 'base_e', 'base_i'):

@@ -146,11 +146,7 @@ typedef struct {
   const float* ln1_g; const float* ln1_b;
   const float* ln2_g; const float* ln2_b;
   const float* ln3_g; const float* ln3_b;
-  const void* Wc;     /* bf16 only, may be NULL: the eight matrices "cluster-packed" for the column-split cluster kernel */
-  const void* Wr;     /* bf16 only, may be NULL: the same eight matrices in the row-split packing of the default
-                         case_layer_chain / case_layer_stack kernel: [8 matrices Wq,Wk,Wv,Wo,Wq2,Wo2,W1,W2][4 k-chunks]
-                         [256 n][64 k], the 16-byte chunk kc of a 128-byte row n stored at position kc ^ (n & 7)
-                         (Wq / Wq2 pre-scaled like Wqkv_t / Wq2_t) */
+  const void* Wc;     /* bf16 only, may be NULL: the eight matrices "cluster-packed" for case_layer_chain */
 } case_layer_weights_t;
 
 /* First half of a layer for the newest position t of every row (TransformerDecoder.py:76-80):
@@ -232,7 +228,6 @@ int case_layer_back(const float* b_in, const float* part_ml, const float* part_a
 #define CASE_SEG_XIN 4   /* x_in[row]       ([R][H] fp32; only in launches without a front half) */
 typedef struct {
   const void* Wc; const float* bias; float* out; int32_t nchunk; int32_t seg[3];
-  const void* Wr;   /* row-split packing: bf16 [nchunk][4 k-chunks][256 n][64 k], swizzled as case_layer_weights_t.Wr */
 } case_post_linear_t;
 typedef struct {
   int32_t npost, W;
@@ -517,7 +512,6 @@ typedef struct {
    * fed back as UNK and kept in tok_ext [R][Tmax+1] for the output.  n_oov = 0: off. */
   int32_t n_oov;
   int32_t* tok_ext;
-  const void* Wqa_r[2]; const void* Wg_r;   /* row-split packing of the post-linear weights (case_post_linear_t.Wr; may be NULL) */
 } case_step_args_t;
 
 /* Enqueue one full decode step t (embedding .. select) for all R rows: the body of the eval loop
