@@ -673,7 +673,7 @@ def roofline(wl, eng, ms_per_decode_step, torch, dev):
             ach = work / (per * 1e-6) / 1e9
             kernels.append(dict(kernel=name, bound=bound, achieved=ach, peak=hbm, unit='GB/s', frac=ach / hbm,
                                 us_per_launch_in_graph=per, launches=n, work_per_launch=work, model=what))
-    for name in ('layer_rows_kernel', 'layer_chain_kernel', 'sparse_tail_kernel'):
+    for name in ('layer_chain_kernel', 'sparse_tail_kernel'):
         if name in kt:
             us, n, _ = kt[name]
             kernels.append(dict(kernel=name, bound='latency', us_per_launch_in_graph=us / n, launches=n,

@@ -17,7 +17,6 @@ XATTN_TILE = AATTN_TILE = 128
 # option bits of StepArgs.opt / GttpStepArgs.opt (include/case_b200.h: a set bit switches one feature OFF)
 OPT_NO_PDL, OPT_NO_CHAIN, OPT_NO_STACK, OPT_NO_FORK, OPT_NO_POST, OPT_NO_GATE = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 OPT_NO_EVICT_FIRST, OPT_DENSE_TAIL, OPT_UNFUSED_TAIL, OPT_NO_FUSED_SELECT, OPT_NO_COPY_PLAN = 0x40, 0x80, 0x100, 0x200, 0x400
-OPT_CLUSTER_LAYERS = 0x800
 
 vp, i32, f32p = C.c_void_p, C.c_int32, C.c_void_p
 

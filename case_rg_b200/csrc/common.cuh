@@ -23,7 +23,6 @@ int check_launch(const char* what);
 struct LaunchOpts {
   int pdl;           // programmatic dependent launch attribute on every kernel launch
   int evict_first;   // the once-per-step K|V / Uk.mem streams are loaded with an L2 evict-first policy
-  int cluster_layers;  // case_layer_chain / case_layer_stack: the column-split cluster kernel instead of the row-split one
 };
 LaunchOpts& launch_opts();
 cudaError_t& launch_err();

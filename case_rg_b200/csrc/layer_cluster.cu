@@ -850,622 +850,6 @@ __global__ __launch_bounds__(CT, 1) void layer_chain_kernel(const ChainArgs a) {
   stamp();
 }
 
-
-// =====================================================================================================================
-// Row-split form of the same row work (the default): no cluster, no exchange.
-//
-// The column-split cluster above pays one DSMEM exchange (~0.45 us with its wait) after every dependent linear - six
-// per layer - because a CTA only ever holds 64 of the 256 columns of a row.  Here a CTA owns RB = 4 decode rows END TO
-// END: it streams EVERY [64 n][256 k] weight slice of a matrix (the same cluster-packed blob, rank after rank) through
-// a 4-slot ring fed by four producer warps (one bulk copy in flight per warp: ~200 GB/s into the SM), eight consumer
-// warps compute 8 columns each per slice, and the results go straight into local shared-memory tiles - dependent
-// linears are separated by one 256-thread named barrier.  64 CTAs at R = 256 read 64 x 1 MB per layer from L2 (the
-// matrices are L2 resident and requests of neighbouring SMs for the same lines are merged there).  The self-attention
-// history is not staged in shared memory (4 rows x 8 heads x 2 x t x 64 B does not fit beside the ring): 16 lanes per
-// (row, head) read K / V rows from L2, which the launch prefetches there as soon as the row table is known.
-constexpr int RB = 4;                    // decode rows per CTA
-constexpr int RCW = 8;                   // consumer warps: warp w = columns 8w .. 8w+7 of the current 64-column slice
-constexpr int RCT = RCW * 32;
-constexpr int RPW = 4;                   // producer warps = weight slots
-constexpr int RNT = RCT + RPW * 32;
-constexpr int R_OFF_W = 0;
-constexpr int R_OFF_XF = R_OFF_W + RPW * CWB;              // fp32 [8][CFLD]  residual stream rows (LayerNorm input)
-constexpr int R_OFF_RES = R_OFF_XF + 8 * CFLD * 4;         // fp32 [8][CFLD]  LayerNorm output = residual of the next add
-constexpr int R_OFF_LA = R_OFF_RES + 8 * CFLD * 4;         // bf16 [8][CALD]  A tile (LayerNorm output)
-constexpr int R_OFF_XA = R_OFF_LA + 8 * CALD * 2;          // bf16 [8][CALD]  A tile (attention context / gelu output)
-constexpr int R_OFF_KCUR = R_OFF_XA + 8 * CALD * 2;        // bf16 [8][CALD]  k of the newest position, then v
-constexpr int R_OFF_VCUR = R_OFF_KCUR + 8 * CALD * 2;
-constexpr int R_OFF_Q = R_OFF_VCUR + 8 * CALD * 2;         // fp32 [RB][H]    q (self-attention) / q2 (fused cross-attention)
-constexpr int R_OFF_SC = R_OFF_Q + RB * H * 4;             // fp32 [RB * NH][CSCLD2]  softmax numerators
-constexpr int R_OFF_PROW = R_OFF_SC + RB * NH * CSCLD2 * 4;
-constexpr int R_OFF_PT = R_OFF_PROW + RB * CTMAX * 4;      // three bf16 A tiles of the post linears
-constexpr int R_OFF_BAR = R_OFF_PT + 3 * 8 * CALD * 2;     // full[RPW], empty[RPW]
-constexpr int R_SMEM = R_OFF_BAR + 2 * RPW * 8;
-
-__device__ __forceinline__ void rows_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RCT) : "memory"); }
-__device__ __forceinline__ void c_mb_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
-// LayerNorm of full rows (warp i < RB: row i) from xf -> bf16 A tile + fp32 residual tile (+ global rows)
-__device__ __forceinline__ void ln_rows_full(const float* xf, const LnPar& lp, bf16* la, float* res, float* gout, int r0,
-                                             int R) {
-  const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (i >= RB) return;
-  const float4 x0 = *reinterpret_cast<const float4*>(xf + i * CFLD + lane * 8);
-  const float4 x1 = *reinterpret_cast<const float4*>(xf + i * CFLD + lane * 8 + 4);
-  const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-  const float sh = __shfl_sync(0xffffffffu, v[0], 0);
-  float s = 0.f, q = 0.f;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { const float d = v[k] - sh; s += d; q = fmaf(d, d, q); }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    q += __shfl_xor_sync(0xffffffffu, q, o);
-  }
-  const float md = s * (1.f / H);
-  const float mean = md + sh;
-  const float rstd = rsqrtf(fmaxf(q * (1.f / H) - md * md, 0.f) + LN_EPS);
-  float y[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) y[k] = (v[k] - mean) * rstd * lp.g[k] + lp.b[k];
-  *reinterpret_cast<uint4*>(la + i * CALD + lane * 8) =
-      make_uint4(c_pack(y[0], y[1]), c_pack(y[2], y[3]), c_pack(y[4], y[5]), c_pack(y[6], y[7]));
-  float* o = res + i * CFLD + lane * 8;
-  *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
-  *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
-  if (gout != nullptr && r0 + i < R) {
-    float* go = gout + (size_t)(r0 + i) * H + lane * 8;
-    *reinterpret_cast<float4*>(go) = make_float4(y[0], y[1], y[2], y[3]);
-    *reinterpret_cast<float4*>(go + 4) = make_float4(y[4], y[5], y[6], y[7]);
-  }
-}
-
-__global__ __launch_bounds__(RNT, 1) void layer_rows_kernel(const ChainArgs a) {
-  extern __shared__ __align__(128) unsigned char sm[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int r0 = blockIdx.x * RB;
-  const int t = a.t, Tmax = a.Tmax;
-  const uint32_t s_base = smem_u32(sm);
-  const uint32_t s_bar = s_base + R_OFF_BAR;           // full[p] at +8p, empty[p] at +8(RPW + p)
-
-  // ---- weight sequence of this launch, in slices of [64 n][256 k] (rank c of matrix k = slice 4k + c):
-  // [Wo2 W1 W2 of the initial back half], the matrices of the fused layers in natural order (Wq Wk Wv Wo Wq2 | Wo2 W1
-  // W2), Wq Wk Wv Wo Wq2 of the last front, then the post linears (rank-major: all chunks of rank c, then rank c+1)
-  const int nback = a.has_back ? 3 : 0;
-  const int nlayer_seq = nback + (a.nfront > 0 ? 8 * (a.nfront - 1) + 5 : 0);
-  const int npost0 = a.npost > 0 ? a.post[0].nchunk : 0, npost1 = a.npost > 1 ? a.post[1].nchunk : 0;
-  const int nslices = CL * (nlayer_seq + npost0 + npost1);
-
-  if (tid == 0) {
-    for (int p = 0; p < RPW; ++p) {
-      c_mb_init(s_bar + 8 * p, 1);
-      c_mb_init(s_bar + 8 * (RPW + p), RCW);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (warp >= RCW) {
-    // ================= producers: warp p owns slot p and the slices p, p + RPW, ...  (weights do not depend on the
-    // preceding kernel: the stream starts before the programmatic-dependency wait of the consumers)
-    if (lane == 0) {
-      const int p = warp - RCW;
-      const uint32_t full = s_bar + 8 * p, empty = s_bar + 8 * (RPW + p), dst = s_base + R_OFF_W + p * CWB;
-      for (int s = p; s < nslices; s += RPW) {
-        const int k = s / CL, c = s % CL;
-        const char* src;
-        if (k < nback) src = a.back.wc + (size_t)(c * 8 + 5 + k) * CWB;
-        else if (k < nlayer_seq) {
-          const int kk = k - nback;
-          src = a.layers[kk >> 3].wc + (size_t)(c * 8 + (kk & 7)) * CWB;
-        } else {
-          int sp = s - CL * nlayer_seq;                // slice index inside the post region
-          if (sp < CL * npost0) src = a.post[0].w + (size_t)sp * CWB;            // [rank][chunk] is the blob's own order
-          else src = a.post[1].w + (size_t)(sp - CL * npost0) * CWB;
-        }
-        const int use = s / RPW;
-        if (use > 0) c_mb_wait(empty, (uint32_t)(use - 1) & 1u);
-        c_mb_expect(full, CWB);
-        c_bulk(dst, src, CWB, full);
-      }
-    }
-    return;
-  }
-
-  // ================= consumers
-  const int g = lane >> 2, tq = lane & 3;              // MMA / epilogue role: row g (valid below RB), column pair tq
-  const bool erow = g < RB;
-  const int er = r0 + g, erl = min(er, a.R - 1);
-  const int wcol = 8 * warp + 2 * tq;                  // the lane's column pair inside a 64-column slice
-  // attention role: 16 lanes per (row, head); a pass covers 16 of the RB * NH pairs
-  const int acp = tid & 15;
-
-  int dbg_n = 0;
-  auto stamp = [&]() {
-    if (a.dbg != nullptr && blockIdx.x == 0 && tid == 0 && dbg_n < 60) a.dbg[dbg_n++] = clock64();
-  };
-  stamp();
-  float* xf = reinterpret_cast<float*>(sm + R_OFF_XF);
-  float* res = reinterpret_cast<float*>(sm + R_OFF_RES);
-  bf16* la = reinterpret_cast<bf16*>(sm + R_OFF_LA);
-  bf16* xa = reinterpret_cast<bf16*>(sm + R_OFF_XA);
-  bf16* kcur = reinterpret_cast<bf16*>(sm + R_OFF_KCUR);
-  bf16* vcur = reinterpret_cast<bf16*>(sm + R_OFF_VCUR);
-  float* q_s = reinterpret_cast<float*>(sm + R_OFF_Q);
-  float* sc = reinterpret_cast<float*>(sm + R_OFF_SC);
-  uint32_t* prow = reinterpret_cast<uint32_t*>(sm + R_OFF_PROW);
-  bf16* pt0 = reinterpret_cast<bf16*>(sm + R_OFF_PT);
-  bf16* pt1 = pt0 + 8 * CALD;
-  bf16* pt2 = pt1 + 8 * CALD;
-  const uint32_t s_la = s_base + R_OFF_LA, s_xa = s_base + R_OFF_XA;
-
-  // rows RB..7 of the A tiles only feed accumulator rows nobody reads; keep them finite
-  for (int i = tid; i < (8 - RB) * CALD / 2; i += RCT) {
-    reinterpret_cast<uint32_t*>(la + RB * CALD)[i] = 0u;
-    reinterpret_cast<uint32_t*>(xa + RB * CALD)[i] = 0u;
-    reinterpret_cast<uint32_t*>(pt0 + RB * CALD)[i] = 0u;
-    reinterpret_cast<uint32_t*>(pt1 + RB * CALD)[i] = 0u;
-    reinterpret_cast<uint32_t*>(pt2 + RB * CALD)[i] = 0u;
-  }
-
-  int slice = 0;                                       // slices consumed so far (uniform over the consumers)
-  // y[:, 64c + 8w .. +7] of one matrix: D = A . W^T for the four slices; epi(ecol, d) gets the lane's column pair
-  auto linear = [&](uint32_t a_tile, auto&& epi) {
-#pragma unroll 1
-    for (int c = 0; c < CL; ++c) {
-      const int p = slice % RPW;
-      c_mb_wait(s_bar + 8 * p, (uint32_t)(slice / RPW) & 1u);
-      const float2 d = mma_cols8(a_tile, s_base + R_OFF_W + p * CWB, warp);
-      __syncwarp();
-      if (lane == 0) c_mb_arrive(s_bar + 8 * (RPW + p));   // this warp is done with the slot
-      epi(CCOL * c + wcol, d);
-      ++slice;
-    }
-  };
-  auto bias2 = [&](const float* bvec, int ecol) -> float2 { return __ldg(reinterpret_cast<const float2*>(bvec + ecol)); };
-
-  // ---- prow[row][j] = physical row | masked bit for j = 0..t (the first launch of a step derives and publishes it)
-  auto load_prow = [&](bool derive) {
-    for (int idx = tid; idx < RB * (t + 1); idx += RCT) {
-      const int ii = idx / (t + 1), j = idx - ii * (t + 1);
-      const int rr = min(r0 + ii, a.R - 1);
-      uint32_t pv;
-      if (derive) {
-        const int pr = j < t ? a.anc[(size_t)rr * a.anc_ld + j] : rr;
-        pv = (uint32_t)pr | (a.tok[(size_t)pr * a.tok_ld + j] != 0 ? 0u : CMASKED);
-        if (a.prow_g != nullptr && r0 + ii < a.R) a.prow_g[(size_t)rr * Tmax + j] = (int32_t)pv;
-      } else {
-        pv = (uint32_t)a.prow_g[(size_t)rr * Tmax + j];
-      }
-      prow[ii * CTMAX + j] = pv;
-    }
-    rows_sync();
-  };
-  // the K and V history rows of the CTA's hypotheses (512 bytes each) -> L2, long before the attention reads them
-  auto prefetch_history = [&](const bf16* kc, const bf16* vc) {
-    for (int i = tid; i < RB * t * 8; i += RCT) {
-      const int ii = i / (t * 8), rem = i - ii * (t * 8), j = rem >> 3, q = rem & 7;
-      const size_t goff = ((size_t)(prow[ii * CTMAX + j] & ~CMASKED) * Tmax + j) * H + (q & 3) * 64;
-      c_prefetch_l2((q < 4 ? kc : vc) + goff);
-    }
-  };
-  const bool early_hist = a.nfront > 0 && !a.first && a.prow_g != nullptr;
-  if (early_hist) { load_prow(false); prefetch_history(a.layers[0].kc, a.layers[0].vc); }
-
-  pdl_wait();              // partials / tokens / b come from the kernel launched just before this one
-  stamp();
-
-  // ---- post linears (see the cluster kernel): capture when XF holds the rows leaving the last back half, run last
-  bool need_ln = false, need_xin = false;
-  for (int p = 0; p < a.npost; ++p)
-    for (int j = 0; j < a.post[p].nchunk; ++j) {
-      need_ln |= a.post[p].seg[j] == SEG_HLN;
-      need_xin |= a.post[p].seg[j] == SEG_XIN;
-    }
-  auto capture_post = [&]() {
-    const int i = warp;
-    if (i < RB) {
-      const int rr = min(r0 + i, a.R - 1);
-      const float4 x0 = *reinterpret_cast<const float4*>(xf + i * CFLD + lane * 8);
-      const float4 x1 = *reinterpret_cast<const float4*>(xf + i * CFLD + lane * 8 + 4);
-      *reinterpret_cast<uint4*>(pt0 + i * CALD + lane * 8) =
-          make_uint4(c_pack(x0.x, x0.y), c_pack(x0.z, x0.w), c_pack(x1.x, x1.y), c_pack(x1.z, x1.w));
-      const float* fp = a.feat + (size_t)(rr / a.W) * H + lane * 8;
-      const float4 f0 = __ldg(reinterpret_cast<const float4*>(fp)), f1 = __ldg(reinterpret_cast<const float4*>(fp + 4));
-      *reinterpret_cast<uint4*>(pt1 + i * CALD + lane * 8) =
-          make_uint4(c_pack(f0.x, f0.y), c_pack(f0.z, f0.w), c_pack(f1.x, f1.y), c_pack(f1.z, f1.w));
-      if (need_xin) {
-        const float* xp = a.xin + (size_t)rr * H + lane * 8;
-        const float4 g0 = *reinterpret_cast<const float4*>(xp), g1 = *reinterpret_cast<const float4*>(xp + 4);
-        *reinterpret_cast<uint4*>(pt2 + i * CALD + lane * 8) =
-            make_uint4(c_pack(g0.x, g0.y), c_pack(g0.z, g0.w), c_pack(g1.x, g1.y), c_pack(g1.z, g1.w));
-      }
-    }
-  };
-  auto run_post = [&]() {
-    rows_sync();                                       // the tiles (and LA when norm1 is a segment) are complete
-    for (int p = 0; p < a.npost; ++p) {
-      const int nch = a.post[p].nchunk;
-#pragma unroll 1
-      for (int c = 0; c < CL; ++c) {
-        const int ecol = CCOL * c + wcol;
-        const float2 bias = bias2(a.post[p].bias, ecol);
-        float2 acc = make_float2(0.f, 0.f);
-        for (int j = 0; j < nch; ++j) {
-          const int kind = a.post[p].seg[j];
-          const uint32_t tile = kind == SEG_H ? smem_u32(pt0) : (kind == SEG_FEAT ? smem_u32(pt1) : (kind == SEG_XIN ? smem_u32(pt2) : s_la));
-          const int sl = slice % RPW;
-          c_mb_wait(s_bar + 8 * sl, (uint32_t)(slice / RPW) & 1u);
-          const float2 d = mma_cols8(tile, s_base + R_OFF_W + sl * CWB, warp);
-          __syncwarp();
-          if (lane == 0) c_mb_arrive(s_bar + 8 * (RPW + sl));
-          acc.x += d.x; acc.y += d.y;
-          ++slice;
-        }
-        if (erow && er < a.R) *reinterpret_cast<float2*>(a.post[p].out + (size_t)er * H + ecol) = make_float2(acc.x + bias.x, acc.y + bias.y);
-      }
-    }
-  };
-
-  // ---- back half of a layer once its cross-attention context is in XA and its residual b in RES:
-  // h2 = b + ctx.Wo2 + bo2; c = LN3(h2); h3 = c + W2.gelu(W1.c + b1) + b2 (TransformerDecoder.py:82-89)
-  auto back_half = [&](const ChainLayer& Lb, float* hdst) {
-    const LnPar ln3 = ln_load(Lb.ln3_g, Lb.ln3_b);
-    linear(s_xa, [&](int ecol, float2 d) {
-      const float2 b = bias2(Lb.bo2, ecol);
-      if (erow) {
-        const float2 r = *reinterpret_cast<const float2*>(res + g * CFLD + ecol);
-        *reinterpret_cast<float2*>(xf + g * CFLD + ecol) = make_float2(r.x + d.x + b.x, r.y + d.y + b.y);
-      }
-    });
-    rows_sync();
-    stamp();
-    ln_rows_full(xf, ln3, la, res, nullptr, r0, a.R);
-    rows_sync();
-    linear(s_la, [&](int ecol, float2 d) {
-      const float2 b = bias2(Lb.b1, ecol);
-      if (erow) *reinterpret_cast<uint32_t*>(xa + g * CALD + ecol) = c_pack(gelu_erf(d.x + b.x), gelu_erf(d.y + b.y));
-    });
-    rows_sync();
-    stamp();
-    linear(s_xa, [&](int ecol, float2 d) {
-      const float2 b = bias2(Lb.b2, ecol);
-      if (erow) {
-        const float2 r = *reinterpret_cast<const float2*>(res + g * CFLD + ecol);
-        const float2 h = make_float2(r.x + d.x + b.x, r.y + d.y + b.y);
-        *reinterpret_cast<float2*>(xf + g * CFLD + ecol) = h;
-        if (hdst != nullptr && er < a.R) *reinterpret_cast<float2*>(hdst + (size_t)er * H + ecol) = h;
-      }
-    });
-    rows_sync();
-    stamp();
-  };
-
-  if (a.has_back) {
-    // residual b of the cross-attention block -> RES; merge of the (big) cross-attention partials -> XA
-    for (int idx = tid; idx < RB * (H / 4); idx += RCT) {
-      const int ii = idx / (H / 4), k4 = idx - ii * (H / 4);
-      const int rr = min(r0 + ii, a.R - 1);
-      *reinterpret_cast<float4*>(res + ii * CFLD + k4 * 4) = *reinterpret_cast<const float4*>(a.b_in + (size_t)rr * H + k4 * 4);
-    }
-#pragma unroll 1
-    for (int pass = 0; pass < RB * NH / 16; ++pass) {
-      const int pair = pass * 16 + (tid >> 4), ai = pair / NH, hd = pair % NH;
-      const int arl = min(r0 + ai, a.R - 1);
-      const int ns = a.nsplit;
-      const size_t pb = ((size_t)arl * NH + hd) * ns;
-      float M = -INFINITY, Z = 0.f, c0 = 0.f, c1 = 0.f;
-      constexpr int MB = 12;
-      for (int jb = 0; jb < ns; jb += MB) {
-        float2 ml[MB], pa[MB];
-#pragma unroll
-        for (int u = 0; u < MB; ++u) {
-          const int j = min(jb + u, ns - 1);
-          ml[u] = *reinterpret_cast<const float2*>(a.part_ml + (pb + j) * 2);
-          pa[u] = *reinterpret_cast<const float2*>(a.part_acc + (pb + j) * HD + 2 * acp);
-        }
-        float bm = -INFINITY;
-#pragma unroll
-        for (int u = 0; u < MB; ++u) bm = fmaxf(bm, ml[u].x);
-        const float Mn = fmaxf(M, bm);
-        const float rs = (M == -INFINITY) ? 0.f : fexp(M - Mn);
-        Z *= rs; c0 *= rs; c1 *= rs;
-#pragma unroll
-        for (int u = 0; u < MB; ++u) {
-          const float e = (jb + u < ns && ml[u].x != -INFINITY) ? fexp(ml[u].x - Mn) : 0.f;
-          Z = fmaf(ml[u].y, e, Z);
-          c0 = fmaf(pa[u].x, e, c0);
-          c1 = fmaf(pa[u].y, e, c1);
-        }
-        M = Mn;
-      }
-      const float inv = Z > 0.f ? 1.f / Z : 0.f;
-      *reinterpret_cast<uint32_t*>(xa + ai * CALD + HD * hd + 2 * acp) = c_pack(c0 * inv, c1 * inv);
-    }
-    rows_sync();
-    stamp();
-    back_half(a.back, a.h_out);
-    if (a.nfront == 0) {
-      if (a.npost > 0) {
-        LnPar lnN;
-        if (need_ln) lnN = ln_load(a.lnN_g, a.lnN_b);
-        capture_post();
-        if (need_ln) ln_rows_full(xf, lnN, la, res, a.hN_out, r0, a.R);   // norm1(h): A tile + rows to global
-        run_post();
-      }
-      return;
-    }
-  } else {
-    // first layer of the step: build the input rows (embedding or given rows)
-    for (int idx = tid; idx < RB * (H / 4); idx += RCT) {
-      const int ii = idx / (H / 4), k4 = idx - ii * (H / 4);
-      const int rr = min(r0 + ii, a.R - 1);
-      float4 x;
-      if (a.E != nullptr) {            // x = E[tok] * sqrt(H) + pe[t]   (Model.py:96, PositionalEmbedding.py:44-48)
-        const int tk = a.tok[(size_t)rr * a.tok_ld + t];
-        x = *reinterpret_cast<const float4*>(a.E + (size_t)tk * H + k4 * 4);
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.pe != nullptr) p = *reinterpret_cast<const float4*>(a.pe + (size_t)t * H + k4 * 4);
-        x = make_float4(fmaf(x.x, a.emb_scale, p.x), fmaf(x.y, a.emb_scale, p.y), fmaf(x.z, a.emb_scale, p.z),
-                        fmaf(x.w, a.emb_scale, p.w));
-        if (r0 + ii < a.R) *reinterpret_cast<float4*>(a.x_out + (size_t)rr * H + k4 * 4) = x;
-      } else {
-        x = *reinterpret_cast<const float4*>(a.h_in + (size_t)rr * H + k4 * 4);
-      }
-      *reinterpret_cast<float4*>(xf + ii * CFLD + k4 * 4) = x;
-    }
-  }
-  if (!early_hist) { load_prow(a.first || a.prow_g == nullptr); prefetch_history(a.layers[0].kc, a.layers[0].vc); }
-  rows_sync();
-
-  for (int f = 0; f < a.nfront; ++f) {
-    const ChainLayer& Lf = a.layers[f];
-    const bool fused = f + 1 < a.nfront;             // followed in-kernel by the small cross-attention + back half
-    if (fused) prefetch_history(a.layers[f + 1].kc, a.layers[f + 1].vc);
-    // ================= front half (TransformerDecoder.py:76-80)
-    const LnPar ln1 = ln_load(Lf.ln1_g, Lf.ln1_b);
-    if (a.npost > 0 && f + 1 == a.nfront && (f > 0 || a.has_back)) capture_post();   // rows leaving the last back half
-    stamp();
-    // ---- F0: a = LN1(h)
-    ln_rows_full(xf, ln1, la, res, nullptr, r0, a.R);
-    rows_sync();
-    // ---- F1: q, k, v (k / v of the newest position: bf16 to the cache and to KCUR / VCUR)
-    linear(s_la, [&](int ecol, float2 d) {
-      const float2 b = bias2(Lf.bqkv, ecol);
-      if (erow) *reinterpret_cast<float2*>(q_s + g * H + ecol) = make_float2(d.x + b.x, d.y + b.y);
-    });
-    linear(s_la, [&](int ecol, float2 d) {
-      const float2 b = bias2(Lf.bqkv + H, ecol);
-      if (erow) {
-        const uint32_t kp = c_pack(d.x + b.x, d.y + b.y);
-        *reinterpret_cast<uint32_t*>(kcur + g * CALD + ecol) = kp;
-        if (er < a.R) *reinterpret_cast<uint32_t*>(Lf.kc + ((size_t)er * Tmax + t) * H + ecol) = kp;
-      }
-    });
-    linear(s_la, [&](int ecol, float2 d) {
-      const float2 b = bias2(Lf.bqkv + 2 * H, ecol);
-      if (erow) {
-        const uint32_t vp = c_pack(d.x + b.x, d.y + b.y);
-        *reinterpret_cast<uint32_t*>(vcur + g * CALD + ecol) = vp;
-        if (er < a.R) *reinterpret_cast<uint32_t*>(Lf.vc + ((size_t)er * Tmax + t) * H + ecol) = vp;
-      }
-    });
-    rows_sync();
-    stamp();
-    const LnPar ln2 = ln_load(Lf.ln2_g, Lf.ln2_b);
-    // ---- F2: self-attention of (row ai, head hd) over positions 0..t, 16 lanes per pair; ctx -> XA (bf16)
-#pragma unroll 1
-    for (int pass = 0; pass < RB * NH / 16; ++pass) {
-      const int pair = pass * 16 + (tid >> 4), ai = pair / NH, hd = pair % NH;
-      const float* qr = q_s + ai * H + HD * hd;
-      float qv[32];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float4 x = *reinterpret_cast<const float4*>(qr + k * 4);
-        qv[4 * k] = x.x; qv[4 * k + 1] = x.y; qv[4 * k + 2] = x.z; qv[4 * k + 3] = x.w;
-      }
-      float* scr = sc + pair * CSCLD2;
-      uint4 kk[3][4];
-#pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        const int j = acp + 16 * u;
-        if (j < t) {
-          const uint4* kr = reinterpret_cast<const uint4*>(Lf.kc + ((size_t)(prow[ai * CTMAX + j] & ~CMASKED) * Tmax + j) * H + HD * hd);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) kk[u][q] = __ldg(kr + q);
-        } else if (j == t) {
-          const uint4* kr = reinterpret_cast<const uint4*>(kcur + ai * CALD + HD * hd);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) kk[u][q] = kr[q];
-        }
-      }
-      float sv[3];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        const int j = acp + 16 * u;
-        sv[u] = -INFINITY;
-        if (j <= t) {
-          float d = 0.f;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t w4[4] = {kk[u][q].x, kk[u][q].y, kk[u][q].z, kk[u][q].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              d = fmaf(qv[q * 8 + 2 * e], __uint_as_float(w4[e] << 16), d);
-              d = fmaf(qv[q * 8 + 2 * e + 1], __uint_as_float(w4[e] & 0xffff0000u), d);
-            }
-          }
-          sv[u] = (prow[ai * CTMAX + j] & CMASKED) ? -INFINITY : d;
-        }
-        mx = fmaxf(mx, sv[u]);
-      }
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      float sum = 0.f;
-#pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        const int j = acp + 16 * u;
-        const float p = (sv[u] == -INFINITY) ? 0.f : fexp(sv[u] - mx);
-        sum += p;
-        if (j <= t) scr[j] = p;
-      }
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      __syncwarp();
-      // V: the lane owns dims 2 acp, 2 acp + 1 of the head over all positions (4-byte loads, 64 bytes per position
-      // across the 16 lanes), eight positions in flight
-      float c0 = 0.f, c1 = 0.f;
-      for (int j0 = 0; j0 < t; j0 += 8) {
-        uint32_t x[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int j = min(j0 + u, t - 1);
-          x[u] = __ldg(reinterpret_cast<const uint32_t*>(Lf.vc + ((size_t)(prow[ai * CTMAX + j] & ~CMASKED) * Tmax + j) * H + HD * hd + 2 * acp));
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float p = j0 + u < t ? scr[j0 + u] : 0.f;
-          c0 = fmaf(p, __uint_as_float(x[u] << 16), c0);
-          c1 = fmaf(p, __uint_as_float(x[u] & 0xffff0000u), c1);
-        }
-      }
-      {
-        const float p = scr[t];
-        const uint32_t x = *reinterpret_cast<const uint32_t*>(vcur + ai * CALD + HD * hd + 2 * acp);
-        c0 = fmaf(p, __uint_as_float(x << 16), c0);
-        c1 = fmaf(p, __uint_as_float(x & 0xffff0000u), c1);
-      }
-      const float inv = sum > 0.f ? 1.f / sum : 0.f;
-      *reinterpret_cast<uint32_t*>(xa + ai * CALD + HD * hd + 2 * acp) = c_pack(c0 * inv, c1 * inv);
-    }
-    rows_sync();
-    stamp();
-    // ---- F3: h1 = a + ctx.Wo + bo
-    linear(s_xa, [&](int ecol, float2 d) {
-      const float2 b = bias2(Lf.bo, ecol);
-      if (erow) {
-        const float2 r = *reinterpret_cast<const float2*>(res + g * CFLD + ecol);
-        *reinterpret_cast<float2*>(xf + g * CFLD + ecol) = make_float2(r.x + d.x + b.x, r.y + d.y + b.y);
-      }
-    });
-    rows_sync();
-    // ---- F4: b = LN2(h1) (RES: the residual of this layer's back half)
-    ln_rows_full(xf, ln2, la, res, fused ? nullptr : a.b_out, r0, a.R);
-    rows_sync();
-    stamp();
-    // ---- F5: q2 = b.Wq2 + bq2 (pre-scaled): to global for a big cross-attention, or kept for the fused one
-    linear(s_la, [&](int ecol, float2 d) {
-      const float2 b = bias2(Lf.bq2, ecol);
-      if (erow) {
-        const float2 q2v = make_float2(d.x + b.x, d.y + b.y);
-        if (!fused) { if (er < a.R) *reinterpret_cast<float2*>(a.q2_out + (size_t)er * H + ecol) = q2v; }
-        else *reinterpret_cast<float2*>(q_s + g * H + ecol) = q2v;
-      }
-    });
-    if (!fused) break;
-    rows_sync();
-    stamp();
-    // ================= fused cross-attention over the S0 keys of the first memory (TransformerDecoder.py:81)
-#pragma unroll 1
-    for (int pass = 0; pass < RB * NH / 16; ++pass) {
-      const int pair = pass * 16 + (tid >> 4), ai = pair / NH, hd = pair % NH;
-      const int arl = min(r0 + ai, a.R - 1);
-      const int S0 = a.S0, bq_ = arl / a.W;
-      const char* kt = reinterpret_cast<const char*>(Lf.kx) + ((size_t)bq_ * NH + hd) * 8192;
-      const char* vt = kt + 4096;
-      const uint8_t* mk = a.mask0 + (size_t)bq_ * S0;
-      const float* qr = q_s + ai * H + HD * hd;
-      float qv[32];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float4 x = *reinterpret_cast<const float4*>(qr + k * 4);
-        qv[4 * k] = x.x; qv[4 * k + 1] = x.y; qv[4 * k + 2] = x.z; qv[4 * k + 3] = x.w;
-      }
-      float* scr = sc + pair * CSCLD2;
-      float sv[4];
-      float mx = -INFINITY;
-      {
-        uint4 kk[4][4];
-        bool okk[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = acp + 16 * u, jj = min(j, S0 - 1);
-          okk[u] = j < S0 && mk[jj] != 0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            kk[u][q] = __ldg(reinterpret_cast<const uint4*>(kt + jj * 64 + ((q ^ ((jj >> 1) & 3)) << 4)));
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float d = 0.f;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t w4[4] = {kk[u][q].x, kk[u][q].y, kk[u][q].z, kk[u][q].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              d = fmaf(qv[q * 8 + 2 * e], __uint_as_float(w4[e] << 16), d);
-              d = fmaf(qv[q * 8 + 2 * e + 1], __uint_as_float(w4[e] & 0xffff0000u), d);
-            }
-          }
-          sv[u] = okk[u] ? d : -INFINITY;
-          mx = fmaxf(mx, sv[u]);
-        }
-      }
-      const int cg = acp & 3, kg = acp >> 2;
-      uint4 vv[CS0MAX / 4];
-#pragma unroll
-      for (int u = 0; u < CS0MAX / 4; ++u) {
-        const int j = min(kg + 4 * u, S0 - 1);
-        vv[u] = __ldg(reinterpret_cast<const uint4*>(vt + j * 64 + ((cg ^ ((j >> 1) & 3)) << 4)));
-      }
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      float sum = 0.f;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = acp + 16 * u;
-        const float p = (sv[u] == -INFINITY) ? 0.f : fexp(sv[u] - mx);
-        sum += p;
-        if (j < S0) scr[j] = p;
-      }
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      __syncwarp();
-      float cacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dims 8 cg .. 8 cg + 7 over this lane's keys
-#pragma unroll
-      for (int u = 0; u < CS0MAX / 4; ++u) {
-        const int j = kg + 4 * u;
-        const float p = j < S0 ? scr[j] : 0.f;
-        const uint32_t w4[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          cacc[2 * e] = fmaf(p, __uint_as_float(w4[e] << 16), cacc[2 * e]);
-          cacc[2 * e + 1] = fmaf(p, __uint_as_float(w4[e] & 0xffff0000u), cacc[2 * e + 1]);
-        }
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        cacc[e] += __shfl_xor_sync(0xffffffffu, cacc[e], 4);
-        cacc[e] += __shfl_xor_sync(0xffffffffu, cacc[e], 8);
-      }
-      const float c0 = kg == 0 ? cacc[0] : (kg == 1 ? cacc[2] : (kg == 2 ? cacc[4] : cacc[6]));
-      const float c1 = kg == 0 ? cacc[1] : (kg == 1 ? cacc[3] : (kg == 2 ? cacc[5] : cacc[7]));
-      const float inv = sum > 0.f ? 1.f / sum : 0.f;
-      // lane (cg, kg) holds dims 8 cg + 2 kg, +1 of the head
-      *reinterpret_cast<uint32_t*>(xa + ai * CALD + HD * hd + 8 * cg + 2 * kg) = c_pack(c0 * inv, c1 * inv);
-    }
-    rows_sync();
-    stamp();
-    // ================= back half of the same layer (its residual b is in RES)
-    back_half(Lf, f + 2 == a.nfront ? a.h_fused_out : nullptr);
-  }
-  if (a.npost > 0) run_post();
-  stamp();
-}
-
 }  // namespace cb
 
 using namespace cb;
@@ -1521,15 +905,7 @@ static int fill_post(ChainArgs& a, const case_chain_post_t* post) {
   return 0;
 }
 
-static int launch_rows(ChainArgs& a, cudaStream_t stream) {
-  a.dbg = g_chain_dbg;
-  ensure_smem<layer_rows_kernel>(R_SMEM);
-  launch_k(layer_rows_kernel, (a.R + RB - 1) / RB, RNT, R_SMEM, stream, a);
-  return check_launch("case_layer_chain(rows)");
-}
-
 static int launch_chain(ChainArgs& a, cudaStream_t stream) {
-  if (!launch_opts().cluster_layers) return launch_rows(a, stream);
   a.dbg = g_chain_dbg;
   // KV history of the front halves, or (launch without front half) the third post tile
   const size_t smem = (size_t)OFF_KV + (a.nfront > 0 ? (size_t)4 * CROWS * a.Tmax * 64 : (size_t)CROWS * CALD * 2 + 2 * CWB);

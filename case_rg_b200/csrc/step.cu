@@ -12,7 +12,7 @@ namespace cb {
 // calling thread; the side stream and events of the fork/join live in a caller-owned case_fork_t.
 static thread_local char g_err[512] = "ok";
 static thread_local cudaError_t g_launch_err = cudaSuccess;
-static thread_local LaunchOpts g_opts = {1, 1, 0};
+static thread_local LaunchOpts g_opts = {1, 1};
 
 LaunchOpts& launch_opts() { return g_opts; }
 cudaError_t& launch_err() { return g_launch_err; }
@@ -39,7 +39,6 @@ struct OptScope {
   explicit OptScope(int opt) : saved(g_opts) {
     g_opts.pdl = (opt & CASE_OPT_NO_PDL) ? 0 : 1;
     g_opts.evict_first = (opt & CASE_OPT_NO_EVICT_FIRST) ? 0 : 1;
-    g_opts.cluster_layers = (opt & CASE_OPT_CLUSTER_LAYERS) ? 1 : 0;
   }
   ~OptScope() { g_opts = saved; }
 };
@@ -87,12 +86,10 @@ extern "C" int case_fork_destroy(case_fork_t* f) {
 
 extern "C" int case_abi_version(void) { return 2; }
 extern "C" int case_thread_options(int opt) {
-  const int old = (g_opts.pdl ? 0 : CASE_OPT_NO_PDL) | (g_opts.evict_first ? 0 : CASE_OPT_NO_EVICT_FIRST) |
-                  (g_opts.cluster_layers ? CASE_OPT_CLUSTER_LAYERS : 0);
+  const int old = (g_opts.pdl ? 0 : CASE_OPT_NO_PDL) | (g_opts.evict_first ? 0 : CASE_OPT_NO_EVICT_FIRST);
   if (opt >= 0) {
     g_opts.pdl = (opt & CASE_OPT_NO_PDL) ? 0 : 1;
     g_opts.evict_first = (opt & CASE_OPT_NO_EVICT_FIRST) ? 0 : 1;
-    g_opts.cluster_layers = (opt & CASE_OPT_CLUSTER_LAYERS) ? 1 : 0;
   }
   return old;
 }

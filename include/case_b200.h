@@ -73,11 +73,8 @@ size_t case_struct_size(int which);
 #define CASE_OPT_UNFUSED_TAIL 0x100    /* finalize + softmax_mix + copy_scatter + topk_rows launches                 */
 #define CASE_OPT_NO_FUSED_SELECT 0x200 /* case_beam_select as its own launch                                         */
 #define CASE_OPT_NO_COPY_PLAN 0x400    /* ignore a copy plan in the step arguments (hash-table sparse tail)          */
-#define CASE_OPT_CLUSTER_LAYERS 0x800  /* case_layer_chain / case_layer_stack on the column-split 4-CTA cluster kernel
-                                          (DSMEM exchanges) instead of the default row-split kernel                  */
 
-/* Options of the CALLING THREAD for direct launcher calls (only CASE_OPT_NO_PDL, CASE_OPT_NO_EVICT_FIRST and
- * CASE_OPT_CLUSTER_LAYERS apply
+/* Options of the CALLING THREAD for direct launcher calls (only CASE_OPT_NO_PDL and CASE_OPT_NO_EVICT_FIRST apply
  * to single launchers); returns the previous word, a negative argument only queries.  The step orchestrators ignore
  * this and use the option word of their argument block. */
 int case_thread_options(int opt);
