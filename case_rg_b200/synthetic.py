@@ -125,6 +125,61 @@ def make_case_decoder_state(seed: int, V: int = BERT_VOCAB, H: int = 256, num_me
     return sd
 
 
+def make_case_producer_state(seed: int, V: int = BERT_VOCAB, H: int = 256) -> Dict[str, torch.Tensor]:
+    """Random-init state of CaSE's pre-decode producers under the reference's canonical key names (CaSE/Model.py:255-268):
+    the shared ``query_encoder`` (TransformerSeqEncoder: 3 layers, 8 heads), ``passage_selection`` (Interaction, query
+    blocks 5H->H + 2 x H->H, passage blocks 5H->H + 4 x H->H, scorer) and ``span_extraction`` (Interaction, query blocks
+    5H->H + 1, passage blocks 5H->H + 2, norm1 / norm2, scorer).  xavier-uniform on matrices as ``init_params``
+    (common/CumulativeTrainer.py:13-24); LayerNorm parameters and biases get small perturbations so that every term of
+    the computation is exercised."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def mha(p, C):
+        sd[p + 'in_proj_weight'] = _xavier(g, 3 * C, C)
+        sd[p + 'in_proj_bias'] = _uni(g, 3 * C, 0.05)
+        sd[p + 'out_proj.weight'] = _xavier(g, C, C)
+        sd[p + 'out_proj.bias'] = _uni(g, C, 0.05)
+
+    def norm(p, C):
+        sd[p + 'weight'] = 1.0 + _uni(g, C, 0.1)
+        sd[p + 'bias'] = _uni(g, C, 0.1)
+
+    def linear(p, n, k):
+        sd[p + 'weight'] = _xavier(g, n, k)
+        sd[p + 'bias'] = _uni(g, n, 1.0 / math.sqrt(k))
+
+    sd['query_encoder.embedding.0.weight'] = _xavier(g, V, H)
+    sd['query_encoder.embedding.0.weight'][0] = 0.0                      # padding_idx = 0
+    sd['query_encoder.embedding.1.pe'] = sinusoid_table(1000, H)
+    for l in range(3):
+        p = f'query_encoder.enc.layers.{l}.'
+        mha(p + 'self_attn.', H)
+        linear(p + 'linear1.', H, H)
+        linear(p + 'linear2.', H, H)
+        norm(p + 'norm1.', H)
+        norm(p + 'norm2.', H)
+
+    def blocks(prefix, n_extra):
+        for i in range(1 + n_extra):
+            C = 5 * H if i == 0 else H
+            p = f'{prefix}{i}.'
+            mha(p + 'self_attn.', C)
+            norm(p + 'norm1.', C)
+            norm(p + 'norm2.', C)
+            linear(p + 'linear1.', H, C)
+            linear(p + 'linear2.', H, H)
+
+    for mod, nq, npb in (('passage_selection.', 2, 4), ('span_extraction.', 1, 2)):
+        sd[mod + 'interaction.dual_att_linear.weight'] = _xavier(g, 1, 3 * H)
+        blocks(mod + 'query_blocks.', nq)
+        blocks(mod + 'passage_blocks.', npb)
+        linear(mod + 'scorer.', 1, H)
+    norm('span_extraction.norm1.', H)
+    norm('span_extraction.norm2.', H)
+    return sd
+
+
 def make_gttp_state(seed: int, V: int = 50000, H: int = 256, E: int = 256, peaked: float = 0.0,
                     boost: Optional[Dict[int, float]] = None) -> Dict[str, torch.Tensor]:
     """Random-init step-side keys of GTTP (``dec.*`` and ``gen.*``; GTTP/Model.py:5-12,96-111)."""

@@ -95,3 +95,23 @@ def glks_inputs(seed=31, R=6, V=700, Lb=90, H=256, D=40):
     overlap = (torch.rand(R, D, generator=g) > 0.5).float()
     overlap[:, 3] = overlap[:, 4] = 1.0
     return dict(state=state, p_v=p_v, p_k=p_k, bmap=bmap, w=w, b=b, gen_ext=gen_ext, vmap=vmap, overlap=overlap)
+
+
+def producers_case(ns=None, V=600, T=5, B=2, Lq=12, NP=3, Lp=20, seed=77):
+    """Seeded full-model fixture of the pre-decode producers: (cfg, producer state_dict, decoder state_dict, data, model).
+    The weights come from ``synthetic`` (no reference needed at test time); with ``ns`` (the loaded reference) the
+    unmodified ``CaSE`` model is also built and loaded with exactly these weights (tests/golden/make_producers_golden.py,
+    live drop-in tests)."""
+    cfg = dict(V=V, T=T, B=B, Lq=Lq, NP=NP, Lp=Lp, seed=seed)
+    inp = syn.make_case_inputs(seed + 1, B, Lq, NP, Lp, V, H)
+    data = {'id': inp.ids, 'query': inp.query, 'passage': inp.passage, 'source_map': inp.source_map}
+    sd_prod = syn.make_case_producer_state(seed, V, H)
+    sd_dec = syn.make_case_decoder_state(seed + 2, V, H, peaked=0.3, gen_gate_bias=2.0)
+    model = None
+    if ns is not None:
+        from baseline import refshim
+        model = refshim.reference_case_model(ns, V, T, decoder_sd=sd_dec, seed=seed)
+        missing = model.load_state_dict(sd_prod, strict=False)
+        assert not missing.unexpected_keys, missing.unexpected_keys
+        model.eval()
+    return cfg, sd_prod, sd_dec, data, model
