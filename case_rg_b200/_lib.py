@@ -135,6 +135,13 @@ _PROTOS = {
     'case_gate_project': [vp, vp, vp, C.c_longlong, vp],
     'case_split_plan': [vp, i32, i32, i32, vp, vp],
     'case_prefill_project_tc': [vp, vp, vp, i32, i32, vp, vp, i32, vp, vp, vp],
+    'case_enc_embed': [vp, vp, vp, C.c_longlong, i32, C.c_float, vp, vp],
+    'case_ln_rows_wide': [vp, vp, i32, vp, vp, vp, vp, C.c_longlong, i32, vp],
+    'case_enc_attention': [vp, vp, i32, i32, i32, i32, vp, vp],
+    'case_interaction': [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp],
+    'case_rows_dot': [vp, vp, vp, C.c_longlong, C.c_longlong, vp, vp],
+    'case_prior_answer': [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp],
+    'case_gemm_rows_tc': [vp, vp, vp, C.c_longlong, i32, i32, i32, vp, i32, vp, vp, i32, vp],
     'case_thread_options': [i32],
     'case_fork_create': [C.POINTER(vp)],
     'case_fork_destroy': [vp],
@@ -142,7 +149,8 @@ _PROTOS = {
     'gttp_decode_step': [C.POINTER(GttpStepArgs), i32, vp],
 }
 _SIZE_FNS = ['case_vocab_tc_workspace_bytes', 'case_vocab_tc_packed_weight_bytes']
-EXPORTS = sorted(list(_PROTOS) + ['case_abi_version', 'case_last_error', 'case_struct_size'] + _SIZE_FNS)
+_SIZE_FNS2 = ['case_interaction_smem_bytes', 'case_gemm_rows_packed_weight_bytes']      # (int, int) -> size_t
+EXPORTS = sorted(list(_PROTOS) + ['case_abi_version', 'case_last_error', 'case_struct_size'] + _SIZE_FNS + _SIZE_FNS2)
 _STRUCTS = [Seg, RowLinArgs, LayerWeights, SelectArgs, StepArgs, GttpStepArgs, TailArgs, ChainPost]
 
 _lib = None
@@ -169,6 +177,9 @@ def load():
     for name in _SIZE_FNS:
         getattr(lib, name).restype = C.c_size_t
         getattr(lib, name).argtypes = [C.c_int]
+    for name in _SIZE_FNS2:
+        getattr(lib, name).restype = C.c_size_t
+        getattr(lib, name).argtypes = [C.c_int, C.c_int]
     for name, argtypes in _PROTOS.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libcase_b200.so')
 TORCH_LIB = os.path.join(HERE, 'libcase_b200_torch.so')
-SOURCES = ['rowops.cu', 'rowops_tc.cu', 'layer_cluster.cu', 'attention.cu', 'xattn_part.cu', 'additive_v2.cu', 'vocab.cu', 'tail.cu', 'sparse_tail.cu', 'select.cu', 'step.cu', 'gemm_tcgen05.cu']
+SOURCES = ['rowops.cu', 'rowops_tc.cu', 'layer_cluster.cu', 'attention.cu', 'xattn_part.cu', 'additive_v2.cu', 'vocab.cu', 'tail.cu', 'sparse_tail.cu', 'select.cu', 'step.cu', 'gemm_tcgen05.cu', 'producers.cu', 'gemm_rows.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 

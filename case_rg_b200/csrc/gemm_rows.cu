@@ -1,0 +1,309 @@
+// Row GEMM on tcgen05 / TMEM for the Linear layers of the pre-decode producers:
+//
+//   Y[M][N] = mask_rows( act( X[M][K] . W[N][K]^T + bias[N] ) + residual[M][N] )
+//
+// X: bf16 row-major (the LayerNorm / attention / previous GEMM output), K = 256 * KB; W: the nn.Linear weight packed
+// per 256-wide K block into 128-row tiles of the UMMA K-major no-swizzle canonical layout (as case_vocab_gemm_tc:
+// [KB][ceil(N/128)][64 KB]); Y: bf16 or fp32 row-major.  One CTA owns 128 rows (UMMA M = 128 = the TMEM lanes) and walks N
+// in chunks of two 128-column blocks; a chunk's accumulator D[128 x 256] (fp32) lives in one half of tensor memory while
+// the epilogue drains the other half:
+//   warps 0-3   producers: gather the A tile of K block kb (128 rows x 256 k, 16-byte chunks into the canonical layout)
+//               and stream the weight blocks (four bulk copies per block, one per warp) through two 64 KB buffers
+//   warp 4      MMA issuer (one thread): 16 tcgen05.mma (M = 128, N = 128, K = 16) per (A tile, weight block);
+//               tcgen05.commit signals "weight buffer free", "A tile free", "accumulator complete"
+//   warps 8-15  epilogue: tcgen05.ld (lane = row, 32 columns at a time), bias / gelu / relu / residual / row mask,
+//               64-byte (bf16) or 128-byte (fp32) stores per thread
+// The A tile is single-buffered (64 KB A + 2 x 64 KB W = 192 KB of shared memory), so the gather of K block kb+1 waits
+// for the MMAs of kb; with K = 256 (most layers) the tile is gathered once per chunk.
+#include "common.cuh"
+
+namespace cb {
+
+constexpr int GR_M = 128, GR_NB = 128, GR_KB = 256;
+constexpr int GR_A_BYTES = GR_M * GR_KB * 2;         // 64 KB
+constexpr int GR_W_BYTES = GR_NB * GR_KB * 2;        // 64 KB
+constexpr int GR_THREADS = 512;
+constexpr int GR_SMEM = GR_A_BYTES + 2 * GR_W_BYTES + 256;
+
+__device__ __forceinline__ void gr_mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void gr_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gr_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void gr_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void gr_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ uint64_t gr_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__host__ __device__ constexpr uint32_t gr_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void gr_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void gr_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void gr_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void gr_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void gr_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void gr_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t gr_pk2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+struct GemmRowsArgs {
+  const bf16* X; const bf16* Wp; const float* bias;
+  long long M; int N, K;
+  int act;                       // 0 none, 1 gelu (erf), 2 relu
+  const void* res; int res_bf16; // residual [M][N] fp32 or bf16, may be NULL
+  const uint8_t* row_mask;       // [M] (1 = keep), may be NULL: masked rows are written as zeros
+  void* Y; int y_bf16;
+};
+
+__global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmRowsArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t s_a = smem_u32(smem), s_w = s_a + GR_A_BYTES;
+  const uint32_t s_bar = s_w + 2 * GR_W_BYTES;
+  // barriers: [0] a_full (128 producer threads), [1] a_free, [2,3] w_full, [4,5] w_free, [6,7] acc_full, [8,9] acc_free
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + GR_A_BYTES + 2 * GR_W_BYTES + 128);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long m0 = (long long)blockIdx.x * GR_M;
+  const int KB = a.K / GR_KB, NBT = a.N / GR_NB;        // K blocks, N blocks (N % 128 == 0)
+  const int nchunk = (NBT + 1) / 2;
+
+  if (tid == 0) {
+    gr_mbar_init(s_bar, 128); gr_mbar_init(s_bar + 8, 1);
+    gr_mbar_init(s_bar + 16, 4); gr_mbar_init(s_bar + 24, 4);
+    gr_mbar_init(s_bar + 32, 1); gr_mbar_init(s_bar + 40, 1);
+    gr_mbar_init(s_bar + 48, 1); gr_mbar_init(s_bar + 56, 1);
+    gr_mbar_init(s_bar + 64, 8); gr_mbar_init(s_bar + 72, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  gr_fence_before();
+  __syncthreads();
+  gr_fence_after();
+  const uint32_t tmem = *s_tmem;
+  pdl_wait();
+
+  if (warp < 4) {
+    // ================= producers
+    int ai = 0, wi = 0;
+    for (int c = 0; c < nchunk; ++c) {
+      const int nbc = min(2, NBT - 2 * c);
+      for (int kb = 0; kb < KB; ++kb) {
+        // weight blocks of this (chunk, K block) first: they only wait for their buffer
+        for (int jj = 0; jj < nbc; ++jj, ++wi) {
+          if (lane == 0) {
+            const int buf = wi & 1;
+            if (wi >= 2) gr_wait(s_bar + 32 + 8 * buf, (uint32_t)((wi >> 1) - 1) & 1u);
+            const char* src = reinterpret_cast<const char*>(a.Wp) + ((size_t)kb * NBT + (2 * c + jj)) * GR_W_BYTES +
+                              (size_t)warp * (GR_W_BYTES / 4);
+            gr_expect_tx(s_bar + 16 + 8 * buf, GR_W_BYTES / 4);
+            gr_bulk(s_w + buf * GR_W_BYTES + warp * (GR_W_BYTES / 4), src, GR_W_BYTES / 4, s_bar + 16 + 8 * buf);
+          }
+        }
+        // A tile of K block kb (re-gathered per chunk when KB > 1; once per CTA when KB == 1)
+        if (KB > 1 || c == 0) {
+          if (ai >= 1) gr_wait(s_bar + 8, (uint32_t)(ai - 1) & 1u);
+          const int r16 = lane & 15;
+#pragma unroll 1
+          for (int p = 0; p < 4; ++p) {
+            const int kc = warp * 8 + 2 * p + (lane >> 4);
+            uint4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const long long m = m0 + i * 16 + r16;
+              v[i] = make_uint4(0, 0, 0, 0);
+              if (m < a.M) v[i] = __ldg(reinterpret_cast<const uint4*>(a.X + (size_t)m * a.K + kb * GR_KB + kc * 8));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<uint4*>(smem + kc * (GR_M / 8) * 128 + (i * 16 + r16) * 16) = v[i];
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+          gr_arrive(s_bar);
+          ++ai;
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ================= MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = gr_idesc(GR_M, GR_NB);
+      int ai = 0, wi = 0;
+      for (int c = 0; c < nchunk; ++c) {
+        const int nbc = min(2, NBT - 2 * c), tb = c & 1;
+        if (c >= 2) gr_wait(s_bar + 64 + 8 * tb, (uint32_t)((c >> 1) - 1) & 1u);      // epilogue of chunk c - 2 done
+        for (int kb = 0; kb < KB; ++kb) {
+          if (KB > 1 || c == 0) { gr_wait(s_bar, (uint32_t)ai & 1u); ++ai; }
+          gr_fence_after();
+          for (int jj = 0; jj < nbc; ++jj, ++wi) {
+            const int buf = wi & 1;
+            gr_wait(s_bar + 16 + 8 * buf, (uint32_t)(wi >> 1) & 1u);
+            gr_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < GR_KB / 16; ++ks) {
+              const int kc = ks * 2;
+              const uint64_t ad = gr_desc(s_a + kc * (GR_M / 8) * 128, (GR_M / 8) * 128, 128);
+              const uint64_t bd = gr_desc(s_w + buf * GR_W_BYTES + kc * (GR_NB / 8) * 128, (GR_NB / 8) * 128, 128);
+              gr_umma(tmem + tb * 256 + jj * GR_NB, ad, bd, idesc, (kb | ks) != 0);
+            }
+            gr_commit(s_bar + 32 + 8 * buf);             // weight buffer free once these MMAs have read it
+          }
+          if (KB > 1) gr_commit(s_bar + 8);              // A tile free
+        }
+        gr_commit(s_bar + 48 + 8 * tb);                  // accumulator of the chunk complete
+      }
+    }
+  } else if (warp >= 8) {
+    // ================= epilogue: warp & 3 = TMEM lane quarter, (warp - 8) >> 2 = which 32-column groups
+    const int q = warp & 3, hh = (warp - 8) >> 2;
+    const long long m = m0 + q * 32 + lane;
+    const bool rowok = m < a.M;
+    const bool keep = rowok && (a.row_mask == nullptr || a.row_mask[m] != 0);
+    for (int c = 0; c < nchunk; ++c) {
+      const int nbc = min(2, NBT - 2 * c), tb = c & 1;
+      gr_wait(s_bar + 48 + 8 * tb, (uint32_t)(c >> 1) & 1u);
+      gr_fence_after();
+      for (int cg = hh; cg < nbc * 4; cg += 2) {
+        const int n0 = c * 256 + cg * 32;
+        uint32_t acc[32];
+        gr_tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + tb * 256 + cg * 32, acc);
+        gr_tmem_ld_wait();
+        if (rowok) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + j));
+            v[j] = __uint_as_float(acc[j]) + b4.x; v[j + 1] = __uint_as_float(acc[j + 1]) + b4.y;
+            v[j + 2] = __uint_as_float(acc[j + 2]) + b4.z; v[j + 3] = __uint_as_float(acc[j + 3]) + b4.w;
+          }
+          if (a.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (a.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (a.res != nullptr) {
+            if (a.res_bf16) {
+              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.res) + (size_t)m * a.N + n0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 w = rp[j];
+                v[8 * j] += __uint_as_float(w.x << 16); v[8 * j + 1] += __uint_as_float(w.x & 0xffff0000u);
+                v[8 * j + 2] += __uint_as_float(w.y << 16); v[8 * j + 3] += __uint_as_float(w.y & 0xffff0000u);
+                v[8 * j + 4] += __uint_as_float(w.z << 16); v[8 * j + 5] += __uint_as_float(w.z & 0xffff0000u);
+                v[8 * j + 6] += __uint_as_float(w.w << 16); v[8 * j + 7] += __uint_as_float(w.w & 0xffff0000u);
+              }
+            } else {
+              const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.res) + (size_t)m * a.N + n0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 w = rp[j];
+                v[4 * j] += w.x; v[4 * j + 1] += w.y; v[4 * j + 2] += w.z; v[4 * j + 3] += w.w;
+              }
+            }
+          }
+          if (!keep) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          if (a.y_bf16) {
+            uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(a.Y) + (size_t)m * a.N + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              yp[j] = make_uint4(gr_pk2(v[8 * j], v[8 * j + 1]), gr_pk2(v[8 * j + 2], v[8 * j + 3]), gr_pk2(v[8 * j + 4], v[8 * j + 5]),
+                                 gr_pk2(v[8 * j + 6], v[8 * j + 7]));
+          } else {
+            float4* yp = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.Y) + (size_t)m * a.N + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
+      }
+      gr_fence_before();
+      __syncwarp();
+      if (lane == 0) gr_arrive(s_bar + 64 + 8 * tb);
+    }
+  }
+  gr_fence_before();
+  __syncthreads();
+  gr_fence_after();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+/* packed weight bytes for an [N][K] Linear: K / 256 blocks x ceil(N / 128) tiles of 64 KB */
+extern "C" size_t case_gemm_rows_packed_weight_bytes(int N, int K) {
+  return (size_t)(K / GR_KB) * ((N + GR_NB - 1) / GR_NB) * GR_W_BYTES;
+}
+
+extern "C" int case_gemm_rows_tc(const void* X, const void* Wp, const float* bias, long long M, int N, int K, int act,
+                                 const void* residual, int residual_dtype, const uint8_t* row_mask, void* Y, int y_dtype,
+                                 case_stream_t stream) {
+  CB_REQUIRE(X && Wp && bias && Y && M > 0, "case_gemm_rows_tc: null pointer");
+  CB_REQUIRE(N > 0 && N % GR_NB == 0 && K > 0 && K % GR_KB == 0, "case_gemm_rows_tc: N must be a multiple of 128 and K of 256");
+  CB_REQUIRE(act >= 0 && act <= 2, "case_gemm_rows_tc: act is 0 (none), 1 (gelu) or 2 (relu)");
+  CB_REQUIRE(((uintptr_t)X % 16 == 0) && ((uintptr_t)Wp % 16 == 0) && ((uintptr_t)Y % 16 == 0) && ((uintptr_t)bias % 16 == 0) &&
+                 ((uintptr_t)residual % 16 == 0),
+             "case_gemm_rows_tc: 16-byte alignment required");
+  CB_REQUIRE((y_dtype == CASE_F32 || y_dtype == CASE_BF16) && (!residual || residual_dtype == CASE_F32 || residual_dtype == CASE_BF16),
+             "case_gemm_rows_tc: dtypes are CASE_F32 / CASE_BF16");
+  CB_REQUIRE((M + GR_M - 1) / GR_M <= 0x7fffffffLL, "case_gemm_rows_tc: too many rows");
+  GemmRowsArgs a;
+  a.X = (const bf16*)X; a.Wp = (const bf16*)Wp; a.bias = bias; a.M = M; a.N = N; a.K = K; a.act = act;
+  a.res = residual; a.res_bf16 = residual_dtype == CASE_BF16; a.row_mask = row_mask; a.Y = Y; a.y_bf16 = y_dtype == CASE_BF16;
+  ensure_smem<gemm_rows_tc_kernel>(GR_SMEM);
+  launch_k(gemm_rows_tc_kernel, (unsigned)((M + GR_M - 1) / GR_M), GR_THREADS, GR_SMEM, (cudaStream_t)stream, a);
+  return check_launch("case_gemm_rows_tc");
+}

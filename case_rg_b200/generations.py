@@ -94,7 +94,7 @@ class FastCaSE(_FastModel):
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device=None, dtype='bf16', max_dec_len=40,
                  beam_width=1, vocab_impl: Optional[int] = None, use_graph=True, prefix='', opt: int = 0,
-                 n_oov: int = 0):
+                 n_oov: int = 0, producers: Optional[Dict[str, torch.Tensor]] = None):
         """opt: CASE_OPT_* bits for every engine of this model (0 = the default fast path; A/B and fallback tests).
         n_oov: size of the per-query dynamic vocabulary behind the V fixed ids (``source_map`` may point into
         [V, V + n_oov); returned ids then range over the extended vocabulary)."""
@@ -102,6 +102,26 @@ class FastCaSE(_FastModel):
         self.max_dec_len, self.beam_width, self.vocab_impl, self.use_graph = max_dec_len, beam_width, vocab_impl, use_graph
         self.opt, self.n_oov = int(opt), int(n_oov)
         self._engines = {}
+        # producers: state_dict of the pre-decode modules (reference key names 'query_encoder.*', 'passage_selection.*',
+        # 'span_extraction.*') -> search_ids decodes from token ids, the encoder outputs never leave the device
+        self.producers = None
+        if producers is not None:
+            from .producers import CaseProducers
+            self.producers = CaseProducers(producers, device=self.weights.device)
+
+    def search_ids(self, data, max_len=None, width=None, mode='beam'):
+        """CaSE.do_test from token ids (CaSE/Model.py:313-331): ``data`` = {'query' int [B,1,Lq], 'passage' int [B,NP,Lp],
+        'source_map' int [B,S]} -> {'answer': LongTensor, 'rank': [B,NP]} like the reference's forward(data, 'test')."""
+        if self.producers is None:
+            raise RuntimeError('FastCaSE was built without producers=...')
+        max_len = self.max_dec_len if max_len is None else max_len
+        width = self.beam_width if width is None else width
+        p = self.producers(data['query'], data['passage'])
+        d = dict(mem_q=p['mem_q'], mem_p=p['mem_p'], query=data['query'].to(self.weights.device),
+                 passage=data['passage'].to(self.weights.device), prior_q=p['prior_q'], prior_p=p['prior_p'],
+                 answer_rep=p['answer_rep'], source_map=data['source_map'].to(self.weights.device))
+        m = {'beam': L.MODE_BEAM, 'greedy': L.MODE_PROTO_GREEDY, 'module_greedy': L.MODE_MODULE_GREEDY}[mode]
+        return {'answer': self.fast_search(d, max_len, width, m), 'rank': p['rank']}
 
     def engine_for(self, B, W, S0, S1, T):
         key = (B, W, S0, S1, T, self.opt, self.n_oov)

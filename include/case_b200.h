@@ -458,6 +458,58 @@ int case_attn_merge(const float* stats, const float* ctx_part, int nsplit, int D
 int case_gttp_gates(const float* f, const float* wc, const float* bc, float* gates, float* fac, int fac_ld,
                     int nsplit, int R, case_stream_t stream);
 
+/* ---------------------------------------------------------------- pre-decode producers
+ * What CaSE.do_test runs before the decoder (CaSE/Model.py:313-331): the shared TransformerSeqEncoder
+ * (common/TransformerSeqEncoderDecoder.py:14-45), Interaction (common/Interaction.py:15-76), the TransformerBlock stacks
+ * of passage selection / supporting-token identification (common/TransformerBlock.py:22-33, CaSE/Model.py:127-215) and the
+ * prior / answer representation of ResponseGeneration.action (CaSE/Model.py:230-245).  Rows = tokens, row-major; GEMM
+ * operands bf16, accumulation / statistics / residual streams fp32. */
+
+/* x[m] = E[tok[m]] * scale + pe[m % L]   (nn.Embedding + PositionalEmbedding over [N][L] token ids); x fp32 [M][256]. */
+int case_enc_embed(const float* E, const float* pe, const int32_t* tok, long long M, int L, float scale, float* x,
+                   case_stream_t stream);
+
+/* LayerNorm (eps 1e-5) of (x + add) over rows of width C = 256 or 1280; x / add fp32 or bf16 (in_dtype), add may be
+ * NULL; outputs: y16 bf16 and / or y32 fp32 (either may be NULL). */
+int case_ln_rows_wide(const void* x, const void* add, int in_dtype, const float* g, const float* b, void* y16, float* y32,
+                      long long M, int C, case_stream_t stream);
+
+/* nn.MultiheadAttention self-attention with a key padding mask over nseq sequences of L tokens (TransformerEncoder.py:66,
+ * TransformerBlock.py:27): qkv bf16 [nseq * L][3C] = in_proj output (Q | K | V column blocks), kmask uint8 [nseq * L]
+ * (1 = valid key), out bf16 [nseq * L][C] (before out_proj).  C = 256 (heads of 32) or 1280 (heads of 160), 8 heads;
+ * the 1/sqrt(head dim) scale is applied here.  FlashAttention-2 style on mma.sync, 64-query x 64-key tiles. */
+int case_enc_attention(const void* qkv, const uint8_t* kmask, int nseq, int L, int C, int nhead, void* out,
+                       case_stream_t stream);
+
+/* Interaction.forward (common/Interaction.py:15-76) for B queries x NP passages without its [B*NP][Lp][Lq][3H] tensor:
+ * Eq fp32 [B][Lq][256] (one query sequence per query), Ep fp32 [B*NP][Lp][256], masks uint8, w fp32 [768] =
+ * dual_att_linear.weight.  Outputs: Gp bf16 [B*NP*Lp][1280] (G_q_p, PAD rows zero) and Gq bf16 [B*Lq][1280] (G_p_q after
+ * the max over the passages).  Scratch: A1 fp32 [B*NP*Lp][256], Gq_scratch fp32 [B*NP*Lq][1280].  Lq <= 64; the score
+ * matrix [Lp][Lq] of a pair lives in shared memory (case_interaction_smem_bytes <= 227 KB). */
+int case_interaction(const float* Eq, const float* Ep, const uint8_t* qmask, const uint8_t* pmask, const float* w, int B,
+                     int NP, int Lq, int Lp, float* A1_scratch, float* Gq_scratch, void* Gq_out, void* Gp_out,
+                     case_stream_t stream);
+size_t case_interaction_smem_bytes(int Lq, int Lp);
+
+/* y[r] = w . x[r * row_stride] + b over fp32 rows of width 256 (the scorer Linear(H, 1): CaSE/Model.py:164, 203). */
+int case_rows_dot(const float* x, const float* w, const float* b, long long nrows, long long row_stride, float* y,
+                  case_stream_t stream);
+
+/* prior[b][s] = sigmoid(pscore[b][s / Lp]) * sigmoid(tscore[b][s]) (0 at PAD: token scores are masked to -1e6 first),
+ * normalised by 1e-8 + its sum; answer[b] = sum_s prior[b][s] * memp[b][s]   (CaSE/Model.py:205-206, 239-243). */
+int case_prior_answer(const float* pscore, const float* tscore, const uint8_t* pmask, const float* memp, int B, int NP,
+                      int Lp, float* prior, float* answer, case_stream_t stream);
+
+/* Y[M][N] = mask_rows( act( X[M][K] . W[N][K]^T + bias ) + residual ) on tcgen05 / TMEM.  X bf16 row-major; Wp = the
+ * nn.Linear weight packed per 256-wide K block into 128-row tiles of the canonical layout of case_vocab_gemm_tc
+ * ([K/256][N/128][64 KB], case_gemm_rows_packed_weight_bytes); N % 128 == 0, K % 256 == 0; act: 0 none, 1 gelu (erf),
+ * 2 relu; residual [M][N] fp32 / bf16 or NULL; row_mask uint8 [M] or NULL (masked rows are written as zeros); Y bf16 or
+ * fp32 (y_dtype). */
+int case_gemm_rows_tc(const void* X, const void* Wp, const float* bias, long long M, int N, int K, int act,
+                      const void* residual, int residual_dtype, const uint8_t* row_mask, void* Y, int y_dtype,
+                      case_stream_t stream);
+size_t case_gemm_rows_packed_weight_bytes(int N, int K);
+
 /* ---------------------------------------------------------------- whole-step orchestrators */
 
 typedef struct {

@@ -1,0 +1,176 @@
+"""SURVEY.md §8f N1 on the device: the pre-decode producers (shared encoder, Interaction, TransformerBlock stacks, prior /
+answer representation) - every kernel against plain torch on the same inputs, the whole pipeline against the oracle
+(oracle/producers.py, pinned on the unmodified reference) and against the golden made by the unmodified CaSE.forward, and
+the answers decoded FROM TOKEN IDS (producers + decoder) against the reference's.
+
+bf16 GEMM operands with fp32 accumulation / statistics / residual streams: north_star's bf16 band (2e-2 relative) is the
+tolerance of everything that went through a GEMM; the kernels themselves are checked tighter on exact operands."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from case_rg_b200 import synthetic as syn
+from helpers import GOLDEN, H, producers_case
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize('C,dt', [(256, torch.float32), (1280, torch.bfloat16), (256, torch.bfloat16), (1280, torch.float32)])
+def test_ln_rows_wide_vs_torch(C, dt):
+    from case_rg_b200 import _lib as L
+    M = 1037
+    g = torch.Generator().manual_seed(C)
+    x = (torch.randn(M, C, generator=g) * 2 + 0.5).to(DEV).to(dt)
+    add = torch.randn(M, C, generator=g).to(DEV).to(dt)
+    w, b = (1 + 0.1 * torch.randn(C, generator=g)).to(DEV), (0.1 * torch.randn(C, generator=g)).to(DEV)
+    for use_add in (False, True):
+        y16 = torch.empty(M, C, dtype=torch.bfloat16, device=DEV)
+        y32 = torch.empty(M, C, device=DEV)
+        L.call('case_ln_rows_wide', x.data_ptr(), add.data_ptr() if use_add else None, L.BF16 if dt == torch.bfloat16 else L.F32,
+               w.data_ptr(), b.data_ptr(), y16.data_ptr(), y32.data_ptr(), M, C, _st())
+        want = F.layer_norm(x.float() + (add.float() if use_add else 0), (C,), w, b, 1e-5)
+        assert rel(y32, want) < 2e-6
+        assert rel(y16, want) < 5e-3
+
+
+@pytest.mark.parametrize('C,L_,nseq', [(256, 100, 7), (1280, 256, 5), (256, 60, 3), (1280, 77, 4), (256, 512, 2)])
+def test_enc_attention_vs_torch(C, L_, nseq):
+    """Self-attention with the key padding mask against torch on the same bf16 q / k / v (fp32 math): ragged valid
+    lengths, partial last key tile, sequences shorter than one tile."""
+    from case_rg_b200 import _lib as L
+    nh, hd = 8, C // 8
+    g = torch.Generator().manual_seed(C + L_)
+    qkv = (torch.randn(nseq * L_, 3 * C, generator=g) * 0.7).to(DEV).bfloat16()
+    lens = torch.randint(2, L_ + 1, (nseq,), generator=g)
+    lens[0] = L_
+    mask = (torch.arange(L_)[None, :] < lens[:, None])
+    km = mask.reshape(-1).to(torch.uint8).to(DEV)
+    out = torch.full((nseq * L_, C), float('nan'), dtype=torch.bfloat16, device=DEV)
+    L.call('case_enc_attention', qkv.data_ptr(), km.data_ptr(), nseq, L_, C, nh, out.data_ptr(), _st())
+    torch.cuda.synchronize()
+    q, k, v = [t.float().view(nseq, L_, nh, hd).transpose(1, 2) for t in qkv.float().split(C, dim=1)]
+    s = (q @ k.transpose(-1, -2)) / (hd ** 0.5)
+    s = s.masked_fill(~mask.to(DEV)[:, None, None, :], float('-inf'))
+    want = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(nseq * L_, C)
+    assert torch.isfinite(out.float()).all()
+    # p is rounded to bf16 for the P.V MMA and the output to bf16
+    assert rel(out, want) < 1.2e-2, rel(out, want)
+
+
+@pytest.mark.parametrize('M,N,K,act,res,mask,out32', [(300, 256, 256, 0, None, False, False), (1000, 768, 256, 0, None, False, False),
+                                                      (515, 256, 256, 1, 'f32', False, True), (260, 3840, 1280, 0, None, False, False),
+                                                      (129, 1280, 1280, 0, 'bf16', False, False), (700, 256, 1280, 2, None, True, True),
+                                                      (128, 256, 256, 2, 'f32', True, True)])
+def test_gemm_rows_tc_vs_torch(M, N, K, act, res, mask, out32):
+    """case_gemm_rows_tc (tcgen05 / TMEM, bias + activation + residual + row mask epilogue) against torch fp32 on the same
+    bf16-rounded operands: partial last row tile, 1 and 5 K blocks, 2 .. 30 column blocks."""
+    from case_rg_b200 import _lib as L
+    from case_rg_b200.producers import _Linear
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).to(DEV).bfloat16()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5)
+    b = torch.randn(N, generator=g) * 0.1
+    lin = _Linear(w, b, torch.device(DEV))
+    r = None
+    if res:
+        r = torch.randn(M, N, generator=g).to(DEV)
+        r = r.bfloat16() if res == 'bf16' else r
+    rm = (torch.rand(M, generator=g) > 0.3).to(torch.uint8).to(DEV) if mask else None
+    y = torch.full((M, N), float('nan'), dtype=torch.float32 if out32 else torch.bfloat16, device=DEV)
+    L.call('case_gemm_rows_tc', x.data_ptr(), lin.wp.data_ptr(), lin.b.data_ptr(), M, N, K, act, L.ptr(r),
+           (L.BF16 if res == 'bf16' else L.F32) if res else 0, L.ptr(rm), y.data_ptr(), L.F32 if out32 else L.BF16, _st())
+    torch.cuda.synchronize()
+    want = x.float() @ lin.w16.float().t() + lin.b
+    want = F.gelu(want) if act == 1 else (torch.relu(want) if act == 2 else want)
+    if r is not None:
+        want = want + r.float()
+    if rm is not None:
+        want = want * rm.view(-1, 1).float()
+    assert torch.isfinite(y.float()).all()
+    assert rel(y, want) < (2e-5 if out32 else 5e-3), rel(y, want)
+    if rm is not None:
+        assert float(y[rm == 0].abs().max()) == 0.0
+
+
+def _pipeline_inputs(B=3, Lq=20, NP=4, Lp=50, V=900, seed=5):
+    sd = syn.make_case_producer_state(seed, V, H)
+    inp = syn.make_case_inputs(seed + 1, B, Lq, NP, Lp, V, H)
+    return sd, inp
+
+
+def test_interaction_vs_oracle():
+    """The Interaction kernel on fp32 encoder-like inputs against the oracle's Interaction (Interaction.py:15-76): both
+    5H-wide outputs, PAD rows / columns zero, the max over the passages; an all-PAD-but-two passage included."""
+    from case_rg_b200 import _lib as L
+    from oracle.producers import interaction
+    B, NP, Lq, Lp = 3, 4, 20, 50
+    g = torch.Generator().manual_seed(9)
+    Eq, Ep = torch.randn(B, 1, Lq, H, generator=g), torch.randn(B, NP, Lp, H, generator=g)
+    w = torch.randn(1, 3 * H, generator=g) * 0.05
+    qm = torch.arange(Lq)[None, None, :] < torch.tensor([20, 13, 7])[:, None, None]
+    pl = torch.randint(5, Lp + 1, (B, NP), generator=g)
+    pl[1, 2] = 2
+    pm = torch.arange(Lp)[None, None, :] < pl[:, :, None]
+    want_q, want_p = interaction({'x.dual_att_linear.weight': w}, 'x.', Eq, Ep, qm, pm)
+    d = lambda t: t.to(DEV).contiguous()
+    A1 = torch.empty(B * NP * Lp, H, device=DEV)
+    Gqt = torch.empty(B * NP * Lq, 5 * H, device=DEV)
+    Gq = torch.empty(B * Lq, 5 * H, dtype=torch.bfloat16, device=DEV)
+    Gp = torch.full((B * NP * Lp, 5 * H), float('nan'), dtype=torch.bfloat16, device=DEV)
+    L.call('case_interaction', d(Eq).data_ptr(), d(Ep).data_ptr(), d(qm.reshape(-1).to(torch.uint8)).data_ptr(),
+           d(pm.reshape(-1).to(torch.uint8)).data_ptr(), d(w.reshape(-1)).data_ptr(), B, NP, Lq, Lp, A1.data_ptr(), Gqt.data_ptr(),
+           Gq.data_ptr(), Gp.data_ptr(), _st())
+    torch.cuda.synchronize()
+    assert torch.isfinite(Gp.float()).all() and torch.isfinite(Gq.float()).all()
+    # E_q / B1 are held in bf16 in shared memory and the outputs are bf16
+    assert rel(Gp.view(B, NP, Lp, -1), want_p) < 1.5e-2, rel(Gp.view(B, NP, Lp, -1), want_p)
+    assert rel(Gq.view(B, 1, Lq, -1), want_q) < 1.5e-2, rel(Gq.view(B, 1, Lq, -1), want_q)
+    assert float(Gp.view(B, NP, Lp, -1)[~pm.to(DEV)].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('gemm', ['tc', 'cublas'])
+def test_producers_vs_oracle(gemm):
+    """The whole pre-decode pipeline from token ids against oracle.producers (fp32): encoder output, passage-selection
+    representations and scores, the decoder's memories, prior and answer representation - within the bf16 band; the own
+    tcgen05 GEMM and cuBLAS on the same operands give the same numbers."""
+    from case_rg_b200.producers import CaseProducers
+    from oracle.producers import producers
+    sd, inp = _pipeline_inputs()
+    want = producers(sd, inp.query, inp.passage)
+    got = CaseProducers(sd, device=DEV, gemm=gemm)(inp.query, inp.passage)
+    torch.cuda.synchronize()
+    for k, tol in (('enc_p', 2e-2), ('enc_q', 2e-2), ('ps_p', 3e-2), ('mem_q', 3e-2), ('mem_p', 3e-2), ('answer_rep', 3e-2),
+                   ('prior_p', 5e-2)):
+        assert torch.isfinite(got[k]).all(), k
+        assert rel(got[k], want[k]) < tol, (gemm, k, rel(got[k], want[k]))
+    assert rel(got['rank'], want['passage_score']) < 5e-2
+    assert torch.allclose(got['prior_p'].reshape(3, -1).sum(1), torch.ones(3, device=DEV), atol=1e-4)
+    assert float(got['prior_p'][~inp.passage.ne(0).to(DEV)].abs().max()) == 0.0
+
+
+def test_decode_from_token_ids_matches_reference_golden():
+    """Producers + decoder from token ids (FastCaSE.search_ids) against what the unmodified CaSE.forward(data, 'test')
+    returned for the fixture of tests/golden/make_producers_golden.py: rank within the bf16 band, answers through the
+    oracle-scored tie criterion of parity_tools (the fixture's decoder weights are peaked)."""
+    from case_rg_b200 import generations as FG
+    cfg, sd_prod, sd_dec, data, _ = producers_case()
+    z = np.load(os.path.join(GOLDEN, 'case_producers.npz'))
+    model = FG.FastCaSE(sd_dec, device=DEV, dtype='bf16', producers=sd_prod)
+    out = model.search_ids({k: v.to(DEV) for k, v in data.items()}, cfg['T'], 1, mode='module_greedy')
+    assert out['answer'].shape == z['answer'].shape
+    assert rel(out['rank'], torch.from_numpy(z['rank'])) < 5e-2
+    agree = float((out['answer'].cpu().numpy() == z['answer']).mean())
+    assert agree >= 0.8, (out['answer'], z['answer'])
