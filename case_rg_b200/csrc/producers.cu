@@ -263,7 +263,7 @@ __global__ __launch_bounds__(256) void interaction_kernel(const float* __restric
   bf16* b1 = eq + IT_LQ * IT_EQLD;                                      // [Lq][IT_EQLD]
   float* U = reinterpret_cast<float*>(b1 + IT_LQ * IT_EQLD);            // [Lp][Lq + 1]
   const int UL = Lq + 1;
-  float* rowb = U + (size_t)Lp * UL;                                    // [8][H]  w3 * E_p[i] of the warp's current row
+  float* rowb = U + (((size_t)Lp * UL + 3) & ~(size_t)3);               // [8][H]  w3 * E_p[i] of the warp's current row (16-byte aligned)
   float* aj = rowb + 8 * H;                                             // [IT_LQ]
   float* cmax = aj + IT_LQ;                                             // [IT_LQ]
   float* csum = cmax + IT_LQ;                                           // [IT_LQ]
@@ -582,7 +582,7 @@ extern "C" int case_enc_attention(const void* qkv, const uint8_t* kmask, int nse
 }
 
 extern "C" size_t case_interaction_smem_bytes(int Lq, int Lp) {
-  return (size_t)2 * IT_LQ * IT_EQLD * 2 + ((size_t)Lp * (Lq + 1) + 8 * H + 3 * IT_LQ + 2 * (size_t)Lp) * 4;
+  return (size_t)2 * IT_LQ * IT_EQLD * 2 + ((((size_t)Lp * (Lq + 1) + 3) & ~(size_t)3) + 8 * H + 3 * IT_LQ + 2 * (size_t)Lp) * 4;
 }
 
 extern "C" int case_interaction(const float* Eq, const float* Ep, const uint8_t* qmask, const uint8_t* pmask, const float* w,

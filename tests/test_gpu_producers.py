@@ -125,7 +125,11 @@ def test_interaction_vs_oracle():
     pl[1, 2] = 2
     pm = torch.arange(Lp)[None, None, :] < pl[:, :, None]
     want_q, want_p = interaction({'x.dual_att_linear.weight': w}, 'x.', Eq, Ep, qm, pm)
-    d = lambda t: t.to(DEV).contiguous()
+    keep = []                                   # device copies must outlive the launch (no temporaries behind data_ptr())
+
+    def d(t):
+        keep.append(t.to(DEV).contiguous())
+        return keep[-1]
     A1 = torch.empty(B * NP * Lp, H, device=DEV)
     Gqt = torch.empty(B * NP * Lq, 5 * H, device=DEV)
     Gq = torch.empty(B * Lq, 5 * H, dtype=torch.bfloat16, device=DEV)
@@ -172,5 +176,16 @@ def test_decode_from_token_ids_matches_reference_golden():
     out = model.search_ids({k: v.to(DEV) for k, v in data.items()}, cfg['T'], 1, mode='module_greedy')
     assert out['answer'].shape == z['answer'].shape
     assert rel(out['rank'], torch.from_numpy(z['rank'])) < 5e-2
-    agree = float((out['answer'].cpu().numpy() == z['answer']).mean())
-    assert agree >= 0.8, (out['answer'], z['answer'])
+    # answers: identical, or - where a row leaves the reference's sequence - the oracle (fp32 producers + decoder, which
+    # reproduces the golden answers exactly on the CPU) rates the two tokens within the band of TWO bf16 stages
+    import parity_tools as PT
+    from oracle.case_decoder import CaseOracle
+    from oracle.producers import producers
+    o = producers(sd_prod, data['query'], data['passage'])
+    inp = syn.CaseInputs(data['query'], data['passage'], data['source_map'], o['mem_q'], o['mem_p'], o['prior_q'], o['prior_p'],
+                         o['answer_rep'], data['id'], cfg['V'])
+    orc = CaseOracle(sd_dec)
+    want, dists, scale = PT.oracle_greedy(lambda: orc.incremental(inp), cfg['B'], cfg['T'])
+    assert np.array_equal(want.numpy(), z['answer'])
+    res = PT.compare_greedy(out['answer'].cpu(), want, dists, 2 * 2e-2 * scale)
+    assert res['miss'] == 0, res
