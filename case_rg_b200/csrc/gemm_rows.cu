@@ -2,28 +2,29 @@
 //
 //   Y[M][N] = mask_rows( act( X[M][K] . W[N][K]^T + bias[N] ) + residual[M][N] )
 //
-// X: bf16 row-major (the LayerNorm / attention / previous GEMM output), K = 256 * KB; W: the nn.Linear weight packed
-// per 256-wide K block into 128-row tiles of the UMMA K-major no-swizzle canonical layout (as case_vocab_gemm_tc:
-// [KB][ceil(N/128)][64 KB]); Y: bf16 or fp32 row-major.  One CTA owns 128 rows (UMMA M = 128 = the TMEM lanes) and walks N
-// in chunks of two 128-column blocks; a chunk's accumulator D[128 x 256] (fp32) lives in one half of tensor memory while
-// the epilogue drains the other half:
-//   warps 0-3   producers: gather the A tile of K block kb (128 rows x 256 k, 16-byte chunks into the canonical layout)
-//               and stream the weight blocks (four bulk copies per block, one per warp) through two 64 KB buffers
-//   warp 4      MMA issuer (one thread): 16 tcgen05.mma (M = 128, N = 128, K = 16) per (A tile, weight block);
-//               tcgen05.commit signals "weight buffer free", "A tile free", "accumulator complete"
-//   warps 8-15  epilogue: tcgen05.ld (lane = row, 32 columns at a time), bias / gelu / relu / residual / row mask,
-//               64-byte (bf16) or 128-byte (fp32) stores per thread
-// The A tile is single-buffered (64 KB A + 2 x 64 KB W = 192 KB of shared memory), so the gather of K block kb+1 waits
-// for the MMAs of kb; with K = 256 (most layers) the tile is gathered once per chunk.
+// X: bf16 row-major (the LayerNorm / attention / previous GEMM output), K % 128 == 0; W: the nn.Linear weight packed per
+// 128-wide K block into 256-row tiles of the UMMA K-major no-swizzle canonical layout ([K/128][N/256][64 KB]); Y: bf16 or
+// fp32 row-major.  One CTA owns 128 rows (UMMA M = 128 = the TMEM lanes) and walks N in chunks of 256 columns (UMMA
+// N = 256: 96 B/clk of shared-memory operand reads, against 128 B/clk at N = 128); a chunk's accumulator D[128 x 256]
+// (fp32) lives in one half of tensor memory while the epilogue drains the other half.  The K loop runs over a two-stage
+// ring of (A tile 128 x 128, W tile 256 x 128) = 96 KB per stage:
+//   warps 0-3 / 4-7  producers of the even / odd stages: the A tile is gathered with 16-byte cp.async (16 per thread, all
+//                    in flight; rows past M are zero-filled) into the canonical layout, the W tile arrives as four bulk
+//                    copies; two stages are in flight at any time, so the gather latency of one hides behind the other
+//   warp 16          MMA issuer (one thread): 8 tcgen05.mma (M = 128, N = 256, K = 16) per stage; tcgen05.commit signals
+//                    "stage free" and "accumulator complete"
+//   warps 8-15       epilogue: tcgen05.ld (lane = row, 32 columns at a time), bias / gelu / relu / residual / row mask,
+//                    64-byte (bf16) or 128-byte (fp32) stores per thread
 #include "common.cuh"
 
 namespace cb {
 
-constexpr int GR_M = 128, GR_NB = 128, GR_KB = 256;
-constexpr int GR_A_BYTES = GR_M * GR_KB * 2;         // 64 KB
-constexpr int GR_W_BYTES = GR_NB * GR_KB * 2;        // 64 KB
-constexpr int GR_THREADS = 512;
-constexpr int GR_SMEM = GR_A_BYTES + 2 * GR_W_BYTES + 256;
+constexpr int GR_M = 128, GR_NC = 256, GR_KB = 128;
+constexpr int GR_A_BYTES = GR_M * GR_KB * 2;         // 32 KB
+constexpr int GR_W_BYTES = GR_NC * GR_KB * 2;        // 64 KB
+constexpr int GR_STAGE = GR_A_BYTES + GR_W_BYTES;    // 96 KB
+constexpr int GR_THREADS = 17 * 32;
+constexpr int GR_SMEM = 2 * GR_STAGE + 256;
 
 __device__ __forceinline__ void gr_mbar_init(uint32_t bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -104,17 +105,18 @@ struct GemmRowsArgs {
 
 __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmRowsArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const uint32_t s_a = smem_u32(smem), s_w = s_a + GR_A_BYTES;
-  const uint32_t s_bar = s_w + 2 * GR_W_BYTES;
-  // barriers: [0] a_full (128 producer threads), [1] a_free, [2,3] w_full, [4,5] w_free, [6,7] acc_full, [8,9] acc_free
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + GR_A_BYTES + 2 * GR_W_BYTES + 128);
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t s_bar = s_base + 2 * GR_STAGE;
+  // barriers: [0,1] a_full (128 gather threads), [2,3] w_full (4 issuing lanes + bytes), [4,5] stage free (MMAs done),
+  //           [6,7] acc_full, [8,9] acc_free (8 epilogue warps)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + 2 * GR_STAGE + 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long m0 = (long long)blockIdx.x * GR_M;
-  const int KB = a.K / GR_KB, NBT = a.N / GR_NB;        // K blocks, N blocks (N % 128 == 0)
-  const int nchunk = (NBT + 1) / 2;
+  const int KB = a.K / GR_KB, nchunk = a.N / GR_NC;
+  const int nit = nchunk * KB;                          // ring iterations
 
   if (tid == 0) {
-    gr_mbar_init(s_bar, 128); gr_mbar_init(s_bar + 8, 1);
+    gr_mbar_init(s_bar, 128); gr_mbar_init(s_bar + 8, 128);
     gr_mbar_init(s_bar + 16, 4); gr_mbar_init(s_bar + 24, 4);
     gr_mbar_init(s_bar + 32, 1); gr_mbar_init(s_bar + 40, 1);
     gr_mbar_init(s_bar + 48, 1); gr_mbar_init(s_bar + 56, 1);
@@ -131,90 +133,81 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
   const uint32_t tmem = *s_tmem;
   pdl_wait();
 
-  if (warp < 4) {
-    // ================= producers
-    int ai = 0, wi = 0;
-    for (int c = 0; c < nchunk; ++c) {
-      const int nbc = min(2, NBT - 2 * c);
-      for (int kb = 0; kb < KB; ++kb) {
-        // weight blocks of this (chunk, K block) first: they only wait for their buffer
-        for (int jj = 0; jj < nbc; ++jj, ++wi) {
-          if (lane == 0) {
-            const int buf = wi & 1;
-            if (wi >= 2) gr_wait(s_bar + 32 + 8 * buf, (uint32_t)((wi >> 1) - 1) & 1u);
-            const char* src = reinterpret_cast<const char*>(a.Wp) + ((size_t)kb * NBT + (2 * c + jj)) * GR_W_BYTES +
-                              (size_t)warp * (GR_W_BYTES / 4);
-            gr_expect_tx(s_bar + 16 + 8 * buf, GR_W_BYTES / 4);
-            gr_bulk(s_w + buf * GR_W_BYTES + warp * (GR_W_BYTES / 4), src, GR_W_BYTES / 4, s_bar + 16 + 8 * buf);
-          }
-        }
-        // A tile of K block kb (re-gathered per chunk when KB > 1; once per CTA when KB == 1)
-        if (KB > 1 || c == 0) {
-          if (ai >= 1) gr_wait(s_bar + 8, (uint32_t)(ai - 1) & 1u);
-          const int r16 = lane & 15;
-#pragma unroll 1
-          for (int p = 0; p < 4; ++p) {
-            const int kc = warp * 8 + 2 * p + (lane >> 4);
-            uint4 v[8];
+  if (warp < 8) {
+    // ================= producers: group g = warp / 4 feeds the stages it with (it & 1) == g
+    const int g = warp >> 2, w4 = warp & 3, t128 = tid & 127;
+    const uint32_t s_a = s_base + g * GR_STAGE, s_w = s_a + GR_A_BYTES;
+    // gather role: thread = (row & 15 + 16 i, k-chunk pair): lane = (kc & 1, row & 15) -> 32-byte runs of a source row per
+    // lane pair, 2-way bank conflicts on the shared-memory side
+    const int r16 = lane & 15;
+    for (int it = g; it < nit; it += 2) {
+      const int c = it / KB, kb = it - c * KB, use = it >> 1;
+      if (use >= 1) gr_wait(s_bar + 32 + 8 * g, (uint32_t)(use - 1) & 1u);      // the MMAs of this stage's previous use are done
+      if (lane == 0) {
+        const char* src = reinterpret_cast<const char*>(a.Wp) + ((size_t)kb * nchunk + c) * GR_W_BYTES + (size_t)w4 * (GR_W_BYTES / 4);
+        gr_expect_tx(s_bar + 16 + 8 * g, GR_W_BYTES / 4);
+        gr_bulk(s_w + w4 * (GR_W_BYTES / 4), src, GR_W_BYTES / 4, s_bar + 16 + 8 * g);
+      }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const long long m = m0 + i * 16 + r16;
-              v[i] = make_uint4(0, 0, 0, 0);
-              if (m < a.M) v[i] = __ldg(reinterpret_cast<const uint4*>(a.X + (size_t)m * a.K + kb * GR_KB + kc * 8));
-            }
+      for (int p = 0; p < 2; ++p) {
+        const int kc = w4 * 4 + 2 * p + (lane >> 4);     // 16 k-chunks of 8 per stage, 4 per warp
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<uint4*>(smem + kc * (GR_M / 8) * 128 + (i * 16 + r16) * 16) = v[i];
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-          gr_arrive(s_bar);
-          ++ai;
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 16 + r16;
+          const long long m = m0 + row;
+          const bf16* src = a.X + (size_t)(m < a.M ? m : 0) * a.K + kb * GR_KB + kc * 8;
+          const uint32_t dst = s_a + kc * (GR_M / 8) * 128 + row * 16;
+          const int nbytes = m < a.M ? 16 : 0;           // rows past M are zero-filled
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
         }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      gr_arrive(s_bar + 8 * g);
+      (void)t128;
     }
-  } else if (warp == 4) {
+  } else if (warp == 16) {
     // ================= MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = gr_idesc(GR_M, GR_NB);
-      int ai = 0, wi = 0;
+      constexpr uint32_t idesc = gr_idesc(GR_M, GR_NC);
+      int it = 0;
       for (int c = 0; c < nchunk; ++c) {
-        const int nbc = min(2, NBT - 2 * c), tb = c & 1;
+        const int tb = c & 1;
         if (c >= 2) gr_wait(s_bar + 64 + 8 * tb, (uint32_t)((c >> 1) - 1) & 1u);      // epilogue of chunk c - 2 done
-        for (int kb = 0; kb < KB; ++kb) {
-          if (KB > 1 || c == 0) { gr_wait(s_bar, (uint32_t)ai & 1u); ++ai; }
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int g = it & 1;
+          const uint32_t par = (uint32_t)(it >> 1) & 1u;
+          gr_wait(s_bar + 8 * g, par);
+          gr_wait(s_bar + 16 + 8 * g, par);
           gr_fence_after();
-          for (int jj = 0; jj < nbc; ++jj, ++wi) {
-            const int buf = wi & 1;
-            gr_wait(s_bar + 16 + 8 * buf, (uint32_t)(wi >> 1) & 1u);
-            gr_fence_after();
+          const uint32_t s_a = s_base + g * GR_STAGE, s_w = s_a + GR_A_BYTES;
 #pragma unroll
-            for (int ks = 0; ks < GR_KB / 16; ++ks) {
-              const int kc = ks * 2;
-              const uint64_t ad = gr_desc(s_a + kc * (GR_M / 8) * 128, (GR_M / 8) * 128, 128);
-              const uint64_t bd = gr_desc(s_w + buf * GR_W_BYTES + kc * (GR_NB / 8) * 128, (GR_NB / 8) * 128, 128);
-              gr_umma(tmem + tb * 256 + jj * GR_NB, ad, bd, idesc, (kb | ks) != 0);
-            }
-            gr_commit(s_bar + 32 + 8 * buf);             // weight buffer free once these MMAs have read it
+          for (int ks = 0; ks < GR_KB / 16; ++ks) {
+            const int kc = ks * 2;
+            const uint64_t ad = gr_desc(s_a + kc * (GR_M / 8) * 128, (GR_M / 8) * 128, 128);
+            const uint64_t bd = gr_desc(s_w + kc * (GR_NC / 8) * 128, (GR_NC / 8) * 128, 128);
+            gr_umma(tmem + tb * GR_NC, ad, bd, idesc, (kb | ks) != 0);
           }
-          if (KB > 1) gr_commit(s_bar + 8);              // A tile free
+          gr_commit(s_bar + 32 + 8 * g);                 // stage free once these MMAs have read it
         }
         gr_commit(s_bar + 48 + 8 * tb);                  // accumulator of the chunk complete
       }
     }
-  } else if (warp >= 8) {
-    // ================= epilogue: warp & 3 = TMEM lane quarter, (warp - 8) >> 2 = which 32-column groups
+  } else {
+    // ================= epilogue (warps 8-15): warp & 3 = TMEM lane quarter, (warp - 8) >> 2 = which 32-column groups
     const int q = warp & 3, hh = (warp - 8) >> 2;
     const long long m = m0 + q * 32 + lane;
     const bool rowok = m < a.M;
     const bool keep = rowok && (a.row_mask == nullptr || a.row_mask[m] != 0);
     for (int c = 0; c < nchunk; ++c) {
-      const int nbc = min(2, NBT - 2 * c), tb = c & 1;
+      const int tb = c & 1;
       gr_wait(s_bar + 48 + 8 * tb, (uint32_t)(c >> 1) & 1u);
       gr_fence_after();
-      for (int cg = hh; cg < nbc * 4; cg += 2) {
-        const int n0 = c * 256 + cg * 32;
+      for (int cg = hh; cg < GR_NC / 32; cg += 2) {
+        const int n0 = c * GR_NC + cg * 32;
         uint32_t acc[32];
-        gr_tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + tb * 256 + cg * 32, acc);
+        gr_tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + tb * GR_NC + cg * 32, acc);
         gr_tmem_ld_wait();
         if (rowok) {
           float v[32];
@@ -258,13 +251,13 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
           if (a.y_bf16) {
             uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(a.Y) + (size_t)m * a.N + n0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              yp[j] = make_uint4(gr_pk2(v[8 * j], v[8 * j + 1]), gr_pk2(v[8 * j + 2], v[8 * j + 3]), gr_pk2(v[8 * j + 4], v[8 * j + 5]),
-                                 gr_pk2(v[8 * j + 6], v[8 * j + 7]));
+            for (int j = 0; j < 4; ++j)     // streaming stores: Y passes through L2 once, X and W tiles are re-read from it
+              __stcs(yp + j, make_uint4(gr_pk2(v[8 * j], v[8 * j + 1]), gr_pk2(v[8 * j + 2], v[8 * j + 3]),
+                                        gr_pk2(v[8 * j + 4], v[8 * j + 5]), gr_pk2(v[8 * j + 6], v[8 * j + 7])));
           } else {
             float4* yp = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.Y) + (size_t)m * a.N + n0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) yp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 8; ++j) __stcs(yp + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
           }
         }
       }
@@ -283,16 +276,16 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
 
 using namespace cb;
 
-/* packed weight bytes for an [N][K] Linear: K / 256 blocks x ceil(N / 128) tiles of 64 KB */
+/* packed weight bytes for an [N][K] Linear: K / 128 blocks x N / 256 tiles of 64 KB */
 extern "C" size_t case_gemm_rows_packed_weight_bytes(int N, int K) {
-  return (size_t)(K / GR_KB) * ((N + GR_NB - 1) / GR_NB) * GR_W_BYTES;
+  return (size_t)(K / GR_KB) * ((N + GR_NC - 1) / GR_NC) * GR_W_BYTES;
 }
 
 extern "C" int case_gemm_rows_tc(const void* X, const void* Wp, const float* bias, long long M, int N, int K, int act,
                                  const void* residual, int residual_dtype, const uint8_t* row_mask, void* Y, int y_dtype,
                                  case_stream_t stream) {
   CB_REQUIRE(X && Wp && bias && Y && M > 0, "case_gemm_rows_tc: null pointer");
-  CB_REQUIRE(N > 0 && N % GR_NB == 0 && K > 0 && K % GR_KB == 0, "case_gemm_rows_tc: N must be a multiple of 128 and K of 256");
+  CB_REQUIRE(N > 0 && N % GR_NC == 0 && K > 0 && K % GR_KB == 0, "case_gemm_rows_tc: N must be a multiple of 256 and K of 128");
   CB_REQUIRE(act >= 0 && act <= 2, "case_gemm_rows_tc: act is 0 (none), 1 (gelu) or 2 (relu)");
   CB_REQUIRE(((uintptr_t)X % 16 == 0) && ((uintptr_t)Wp % 16 == 0) && ((uintptr_t)Y % 16 == 0) && ((uintptr_t)bias % 16 == 0) &&
                  ((uintptr_t)residual % 16 == 0),

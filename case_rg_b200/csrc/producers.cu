@@ -269,6 +269,8 @@ __global__ __launch_bounds__(256) void interaction_kernel(const float* __restric
   float* csum = cmax + IT_LQ;                                           // [IT_LQ]
   float* rmax = csum + IT_LQ;                                           // [Lp]
   float* rsum = rmax + Lp;                                              // [Lp]
+  int* vidx = reinterpret_cast<int*>(rsum + Lp);                        // [Lp] indices of the valid passage rows
+  int* nvalid = vidx + Lp;
   pdl_wait();
   const int s = blockIdx.x, b = s / NP;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -338,7 +340,18 @@ __global__ __launch_bounds__(256) void interaction_kernel(const float* __restric
     __syncwarp();
   }
   __syncthreads();
-  // ---- P2: column statistics
+  // ---- P2: column statistics; list of the valid rows (warp 7: ballot compaction, order kept)
+  if (warp == 7) {
+    int n = 0;
+    for (int i0 = 0; i0 < Lp; i0 += 32) {
+      const int i = i0 + lane;
+      const bool ok = i < Lp && pm[i] != 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (ok) vidx[n + __popc(bal & ((1u << lane) - 1u))] = i;
+      n += __popc(bal);
+    }
+    if (lane == 0) *nvalid = n;
+  }
   if (tid < Lq) {
     float mx = -INFINITY;
     for (int i = 0; i < Lp; ++i) mx = fmaxf(mx, U[i * UL + tid]);
@@ -364,26 +377,43 @@ __global__ __launch_bounds__(256) void interaction_kernel(const float* __restric
       acc[6] = fmaf(a, bf_lo(x.w), acc[6]); acc[7] = fmaf(a, bf_hi(x.w), acc[7]);
     }
   };
-  // reduction over the rows for the warp's columns: acc[c][8 dims] = sum_i B[i][j_c] * X[i]  (X fp32 rows in global memory)
+  // reduction over the rows for the warp's columns: acc[c][8 dims] = sum_i B[i][j_c] * X[i]  (X fp32 rows in global memory).
+  // Only the valid rows are walked (vidx: their indices, built once), four at a time with all eight 16-byte loads of the
+  // batch in flight together - the loop is bound by the latency of these loads otherwise.
   auto col_prod = [&](const float* X, float (&acc)[8][8]) {
+    float cm[8], ci[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
+    for (int c = 0; c < 8; ++c) {
+      const int j = warp + 8 * c;
+      cm[c] = j < Lq ? cmax[j] : 0.f;
+      ci[c] = (j < Lq && csum[j] > 0.f) ? 1.f / csum[j] : 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[c][k] = 0.f;
-    for (int i = 0; i < Lp; ++i) {
-      if (pm[i] == 0) continue;
-      const float4 x0 = *reinterpret_cast<const float4*>(X + (size_t)i * H + lane * 8);
-      const float4 x1 = *reinterpret_cast<const float4*>(X + (size_t)i * H + lane * 8 + 4);
+    }
+    const int nv = *nvalid;
+    for (int i0 = 0; i0 < nv; i0 += 4) {
+      int ii[4];
+      float4 x0[4], x1[4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int j = warp + 8 * c;
-        if (j >= Lq) break;
-        const float u = U[i * UL + j];
-        const float bw = (u == -INFINITY || csum[j] <= 0.f) ? 0.f : __expf(u - cmax[j]) / csum[j];
-        acc[c][0] = fmaf(bw, x0.x, acc[c][0]); acc[c][1] = fmaf(bw, x0.y, acc[c][1]);
-        acc[c][2] = fmaf(bw, x0.z, acc[c][2]); acc[c][3] = fmaf(bw, x0.w, acc[c][3]);
-        acc[c][4] = fmaf(bw, x1.x, acc[c][4]); acc[c][5] = fmaf(bw, x1.y, acc[c][5]);
-        acc[c][6] = fmaf(bw, x1.z, acc[c][6]); acc[c][7] = fmaf(bw, x1.w, acc[c][7]);
+      for (int u = 0; u < 4; ++u) {
+        ii[u] = vidx[min(i0 + u, nv - 1)];
+        x0[u] = *reinterpret_cast<const float4*>(X + (size_t)ii[u] * H + lane * 8);
+        x1[u] = *reinterpret_cast<const float4*>(X + (size_t)ii[u] * H + lane * 8 + 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (i0 + u >= nv) break;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int j = warp + 8 * c;
+          if (j >= Lq) break;
+          const float uu = U[ii[u] * UL + j];
+          const float bw = (uu == -INFINITY) ? 0.f : __expf(uu - cm[c]) * ci[c];
+          acc[c][0] = fmaf(bw, x0[u].x, acc[c][0]); acc[c][1] = fmaf(bw, x0[u].y, acc[c][1]);
+          acc[c][2] = fmaf(bw, x0[u].z, acc[c][2]); acc[c][3] = fmaf(bw, x0[u].w, acc[c][3]);
+          acc[c][4] = fmaf(bw, x1[u].x, acc[c][4]); acc[c][5] = fmaf(bw, x1[u].y, acc[c][5]);
+          acc[c][6] = fmaf(bw, x1[u].z, acc[c][6]); acc[c][7] = fmaf(bw, x1[u].w, acc[c][7]);
+        }
       }
     }
   };
@@ -582,7 +612,7 @@ extern "C" int case_enc_attention(const void* qkv, const uint8_t* kmask, int nse
 }
 
 extern "C" size_t case_interaction_smem_bytes(int Lq, int Lp) {
-  return (size_t)2 * IT_LQ * IT_EQLD * 2 + ((((size_t)Lp * (Lq + 1) + 3) & ~(size_t)3) + 8 * H + 3 * IT_LQ + 2 * (size_t)Lp) * 4;
+  return (size_t)2 * IT_LQ * IT_EQLD * 2 + ((((size_t)Lp * (Lq + 1) + 3) & ~(size_t)3) + 8 * H + 3 * IT_LQ + 3 * (size_t)Lp + 4) * 4;
 }
 
 extern "C" int case_interaction(const float* Eq, const float* Ep, const uint8_t* qmask, const uint8_t* pmask, const float* w,

@@ -246,6 +246,29 @@ def install_fast_decoder(model: nn.Module, beam_width: int = 1, dtype: str = 'bf
     return model
 
 
+def install_fast_model(model: nn.Module, beam_width: int = 1, dtype: str = 'bf16', **kw) -> nn.Module:
+    """The whole of ``CaSE.do_test`` on the device (CaSE/Model.py:313-331): ``install_fast_decoder`` plus the pre-decode
+    producers - shared encoder, passage selection, supporting-token identification, prior / answer
+    representation - through ``producers.CaseProducers`` built from the model's own state_dict.  ``model.forward(data,
+    'test')`` keeps its contract ({'answer', 'rank'}); training goes through the original modules."""
+    from .producers import CaseProducers
+    install_fast_decoder(model, beam_width=beam_width, dtype=dtype, **kw)
+    dev = next(model.parameters()).device
+    prod = CaseProducers(model.state_dict(), device=dev)
+    dec = model.response_generation.decoder
+
+    def do_test(self, data):
+        p = prod(data['query'], data['passage'])
+        out = dec([p['mem_q'], p['mem_p']], self.response_generation.BOS, self.response_generation.UNK, data['source_map'],
+                  additional_decoder_feature=p['answer_rep'], groundtruth_index=None, max_target_length=self.max_target_length,
+                  encode_masks=[data['query'].ne(0), data['passage'].ne(0)], encode_weights=[p['prior_q'], p['prior_p']])
+        return {'answer': out[3], 'rank': p['rank']}
+
+    model.do_test = types.MethodType(do_test, model)
+    model._fast_producers = [prod]
+    return model
+
+
 def install_fast_gttp(model: nn.Module, dtype: str = 'bf16', device=None, **kw) -> nn.Module:
     """Swap the step side of a reference ``GTTP`` model (GTTP/Model.py:133-212) for the CUDA path, in place.
 

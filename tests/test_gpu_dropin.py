@@ -59,6 +59,33 @@ def test_install_fast_decoder_into_live_reference_case(ns, dtype):
     assert set(model.state_dict().keys()) == ref_keys
 
 
+def test_install_fast_model_into_live_reference_case(ns):
+    """install_fast_model: producers AND decoder of the live reference CaSE replaced - forward(data, 'test') from token
+    ids.  rank within the bf16 band of the unmodified model's; answers identical or oracle-rated ties (two bf16 stages)."""
+    import parity_tools as PT
+    from helpers import producers_case
+    from case_rg_b200.decoder import install_fast_model
+    from oracle.case_decoder import CaseOracle
+    from oracle.producers import producers
+    cfg, sd_prod, sd_dec, data, model = producers_case(ns)
+    model = model.to(DEV).eval()
+    d = {k: v.to(DEV) for k, v in data.items()}
+    with torch.no_grad():
+        want = model(copy.copy(d), method='test')
+        install_fast_model(model, dtype='bf16')
+        got = model(copy.copy(d), method='test')
+    assert got['answer'].shape == want['answer'].shape and got['rank'].shape == want['rank'].shape
+    assert float((got['rank'] - want['rank']).abs().max() / want['rank'].abs().max()) < 5e-2
+    o = producers(sd_prod, data['query'], data['passage'])
+    inp = syn.CaseInputs(data['query'], data['passage'], data['source_map'], o['mem_q'], o['mem_p'], o['prior_q'], o['prior_p'],
+                         o['answer_rep'], data['id'], cfg['V'])
+    orc = CaseOracle(sd_dec)
+    ref, dists, scale = PT.oracle_greedy(lambda: orc.incremental(inp), cfg['B'], cfg['T'])
+    assert torch.equal(ref, want['answer'].cpu())                  # oracle == the unmodified model on the device
+    res = PT.compare_greedy(got['answer'].cpu(), ref, dists, 2 * 2e-2 * scale)
+    assert res['miss'] == 0, res
+
+
 def test_install_fast_decoder_into_live_reference_masque(ns):
     from case_rg_b200.decoder import install_fast_decoder, FastMasqueDecoder
     V, T, B = 2000, 8, 3
