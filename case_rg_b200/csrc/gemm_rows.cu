@@ -9,7 +9,8 @@
 // (fp32) lives in one half of tensor memory while the epilogue drains the other half.  The K loop runs over a two-stage
 // ring of (A tile 128 x 128, W tile 256 x 128) = 96 KB per stage:
 //   warps 0-3 / 4-7  producers of the even / odd stages: the A tile is gathered with 16-byte cp.async (16 per thread, all
-//                    in flight; rows past M are zero-filled) into the canonical layout, the W tile arrives as four bulk
+//                    in flight, a full 128-byte line per quarter warp; rows past M are zero-filled) into the 128-byte-swizzle
+//                    K-major layout (conflict-free on the shared-memory side), the pre-packed W tile arrives as four bulk
 //                    copies; two stages are in flight at any time, so the gather latency of one hides behind the other
 //   warp 16          MMA issuer (one thread): 8 tcgen05.mma (M = 128, N = 256, K = 16) per stage; tcgen05.commit signals
 //                    "stage free" and "accumulator complete"
@@ -58,6 +59,11 @@ __device__ __forceinline__ uint64_t gr_desc(uint32_t smem_addr, uint32_t lbo_byt
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
+// K-major operand in the 128-byte-swizzle layout: rows of 64 bf16 (128 B), 8-row groups 1024 B apart, the 16-byte chunk c of
+// row r stored at chunk position c ^ (r & 7).  The leading-dimension offset is not used by this layout.
+__device__ __forceinline__ uint64_t gr_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
 __host__ __device__ constexpr uint32_t gr_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -104,16 +110,20 @@ struct GemmRowsArgs {
 };
 
 __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmRowsArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t s_base = smem_u32(smem);
   const uint32_t s_bar = s_base + 2 * GR_STAGE;
   // barriers: [0,1] a_full (128 gather threads), [2,3] w_full (4 issuing lanes + bytes), [4,5] stage free (MMAs done),
   //           [6,7] acc_full, [8,9] acc_free (8 epilogue warps)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + 2 * GR_STAGE + 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long m0 = (long long)blockIdx.x * GR_M;
+  // persistent: this CTA owns the row tiles blockIdx.x, blockIdx.x + gridDim.x, ...; a work unit is (row tile, 256-column
+  // chunk), the stage ring and the two accumulators run on across units so the epilogue of one overlaps the next one's MMAs
   const int KB = a.K / GR_KB, nchunk = a.N / GR_NC;
-  const int nit = nchunk * KB;                          // ring iterations
+  const int ntile = (int)((a.M + GR_M - 1) / GR_M);
+  const int mine = ((int)blockIdx.x < ntile) ? (ntile - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int nunit = mine * nchunk;
+  const int nit = nunit * KB;                           // ring iterations
 
   if (tid == 0) {
     gr_mbar_init(s_bar, 128); gr_mbar_init(s_bar + 8, 128);
@@ -135,13 +145,15 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
 
   if (warp < 8) {
     // ================= producers: group g = warp / 4 feeds the stages it with (it & 1) == g
-    const int g = warp >> 2, w4 = warp & 3, t128 = tid & 127;
+    const int g = warp >> 2, w4 = warp & 3;
     const uint32_t s_a = s_base + g * GR_STAGE, s_w = s_a + GR_A_BYTES;
-    // gather role: thread = (row & 15 + 16 i, k-chunk pair): lane = (kc & 1, row & 15) -> 32-byte runs of a source row per
-    // lane pair, 2-way bank conflicts on the shared-memory side
-    const int r16 = lane & 15;
+    // gather role: a quarter warp (8 lanes) copies one 128-byte run of a source row - one full cache line per request - into
+    // the 128-byte-swizzle layout, where its eight 16-byte chunks land in eight different bank groups
+    const int rq = w4 * 4 + (lane >> 3), ch = lane & 7;
     for (int it = g; it < nit; it += 2) {
-      const int c = it / KB, kb = it - c * KB, use = it >> 1;
+      const int u = it / KB, kb = it - u * KB, use = it >> 1;
+      const int mt = u / nchunk, c = u - mt * nchunk;
+      const long long m0 = ((long long)blockIdx.x + (long long)mt * gridDim.x) * GR_M;
       if (use >= 1) gr_wait(s_bar + 32 + 8 * g, (uint32_t)(use - 1) & 1u);      // the MMAs of this stage's previous use are done
       if (lane == 0) {
         const char* src = reinterpret_cast<const char*>(a.Wp) + ((size_t)kb * nchunk + c) * GR_W_BYTES + (size_t)w4 * (GR_W_BYTES / 4);
@@ -149,14 +161,13 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
         gr_bulk(s_w + w4 * (GR_W_BYTES / 4), src, GR_W_BYTES / 4, s_bar + 16 + 8 * g);
       }
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        const int kc = w4 * 4 + 2 * p + (lane >> 4);     // 16 k-chunks of 8 per stage, 4 per warp
+      for (int h = 0; h < 2; ++h) {                      // the two 64-wide K atoms of the stage
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int row = i * 16 + r16;
+          const int row = i * 16 + rq;
           const long long m = m0 + row;
-          const bf16* src = a.X + (size_t)(m < a.M ? m : 0) * a.K + kb * GR_KB + kc * 8;
-          const uint32_t dst = s_a + kc * (GR_M / 8) * 128 + row * 16;
+          const bf16* src = a.X + (size_t)(m < a.M ? m : 0) * a.K + kb * GR_KB + h * 64 + ch * 8;
+          const uint32_t dst = s_a + h * (GR_A_BYTES / 2) + (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4);
           const int nbytes = m < a.M ? 16 : 0;           // rows past M are zero-filled
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
         }
@@ -165,16 +176,15 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       gr_arrive(s_bar + 8 * g);
-      (void)t128;
     }
   } else if (warp == 16) {
     // ================= MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = gr_idesc(GR_M, GR_NC);
       int it = 0;
-      for (int c = 0; c < nchunk; ++c) {
+      for (int c = 0; c < nunit; ++c) {
         const int tb = c & 1;
-        if (c >= 2) gr_wait(s_bar + 64 + 8 * tb, (uint32_t)((c >> 1) - 1) & 1u);      // epilogue of chunk c - 2 done
+        if (c >= 2) gr_wait(s_bar + 64 + 8 * tb, (uint32_t)((c >> 1) - 1) & 1u);      // epilogue of unit c - 2 done
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int g = it & 1;
           const uint32_t par = (uint32_t)(it >> 1) & 1u;
@@ -185,7 +195,7 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
 #pragma unroll
           for (int ks = 0; ks < GR_KB / 16; ++ks) {
             const int kc = ks * 2;
-            const uint64_t ad = gr_desc(s_a + kc * (GR_M / 8) * 128, (GR_M / 8) * 128, 128);
+            const uint64_t ad = gr_desc_sw128(s_a + (ks >> 2) * (GR_A_BYTES / 2) + (ks & 3) * 32);
             const uint64_t bd = gr_desc(s_w + kc * (GR_NC / 8) * 128, (GR_NC / 8) * 128, 128);
             gr_umma(tmem + tb * GR_NC, ad, bd, idesc, (kb | ks) != 0);
           }
@@ -197,12 +207,13 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
   } else {
     // ================= epilogue (warps 8-15): warp & 3 = TMEM lane quarter, (warp - 8) >> 2 = which 32-column groups
     const int q = warp & 3, hh = (warp - 8) >> 2;
-    const long long m = m0 + q * 32 + lane;
-    const bool rowok = m < a.M;
-    const bool keep = rowok && (a.row_mask == nullptr || a.row_mask[m] != 0);
-    for (int c = 0; c < nchunk; ++c) {
-      const int tb = c & 1;
-      gr_wait(s_bar + 48 + 8 * tb, (uint32_t)(c >> 1) & 1u);
+    for (int u = 0; u < nunit; ++u) {
+      const int mt = u / nchunk, c = u - mt * nchunk;
+      const long long m = ((long long)blockIdx.x + (long long)mt * gridDim.x) * GR_M + q * 32 + lane;
+      const bool rowok = m < a.M;
+      const bool keep = rowok && (a.row_mask == nullptr || a.row_mask[m] != 0);
+      const int tb = u & 1;
+      gr_wait(s_bar + 48 + 8 * tb, (uint32_t)(u >> 1) & 1u);
       gr_fence_after();
       for (int cg = hh; cg < GR_NC / 32; cg += 2) {
         const int n0 = c * GR_NC + cg * 32;
@@ -297,6 +308,11 @@ extern "C" int case_gemm_rows_tc(const void* X, const void* Wp, const float* bia
   a.X = (const bf16*)X; a.Wp = (const bf16*)Wp; a.bias = bias; a.M = M; a.N = N; a.K = K; a.act = act;
   a.res = residual; a.res_bf16 = residual_dtype == CASE_BF16; a.row_mask = row_mask; a.Y = Y; a.y_bf16 = y_dtype == CASE_BF16;
   ensure_smem<gemm_rows_tc_kernel>(GR_SMEM);
-  launch_k(gemm_rows_tc_kernel, (unsigned)((M + GR_M - 1) / GR_M), GR_THREADS, GR_SMEM, (cudaStream_t)stream, a);
+  const long long ntile = (M + GR_M - 1) / GR_M;
+  int dev = 0, nsm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  if (nsm <= 0) nsm = 148;
+  launch_k(gemm_rows_tc_kernel, (unsigned)(ntile < nsm ? ntile : nsm), GR_THREADS, GR_SMEM, (cudaStream_t)stream, a);
   return check_launch("case_gemm_rows_tc");
 }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """case_gemm_rows_tc against cuBLAS (torch.mm, bf16 in / fp32 out) on the Linear shapes of the pre-decode producers at the
-BASELINE shape (M = 64 x 10 x 256 passage tokens).  usage: python profiles/micro/gemm_rows_bench.py"""
+BASELINE shape (M = 64 x 10 x 256 passage tokens).  usage: python profiles/micro/gemm_rows_bench.py [N K]"""
 import os
 import sys
 
@@ -32,6 +32,8 @@ def main():
     for N, K, act, res, out32 in ((768, 256, 0, None, False), (256, 256, 0, 'f32', True), (256, 256, 1, None, False),
                                   (3840, 1280, 0, None, False), (1280, 1280, 0, 'bf16', False), (256, 1280, 2, None, False),
                                   (256, 256, 0, None, True)):
+        if len(sys.argv) > 2 and (N, K) != (int(sys.argv[1]), int(sys.argv[2])):
+            continue
         x = torch.randn(M, K, device=dev).bfloat16()
         lin = _Linear(torch.randn(N, K) / K ** 0.5, torch.randn(N) * 0.1, dev)
         r = None if res is None else (torch.randn(M, N, device=dev) if res == 'f32' else torch.randn(M, N, device=dev).bfloat16())
