@@ -44,31 +44,35 @@ __global__ __launch_bounds__(256) void enc_embed_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------ LayerNorm
-// one warp per row; C / 32 elements per lane held in registers.  x (and the optional addend) fp32 or bf16.
+// one warp per row; C / 32 elements per lane held in registers, in 16-byte chunks interleaved over the lanes (chunk i of
+// lane l = chunk 32 i + l of the row), so that every load / store instruction of the warp covers one contiguous run.
+// x (and the optional addend) fp32 or bf16.
 template <int C, bool XBF>
 __global__ __launch_bounds__(256) void ln_rows_wide_kernel(const void* __restrict__ x_, const void* __restrict__ add_,
                                                            const float* __restrict__ g, const float* __restrict__ b,
                                                            bf16* __restrict__ y16, float* __restrict__ y32, long long M) {
   pdl_wait();
-  constexpr int PER = C / 32;                      // 8 or 40, contiguous per lane
+  constexpr int PER = C / 32;                      // 8 or 40 per lane
+  constexpr int VEC = XBF ? 8 : 4;                 // elements per 16-byte chunk of the input
+  constexpr int NCH = PER / VEC;
   const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (m >= M) return;
   const int lane = threadIdx.x & 31;
   float v[PER];
   auto load = [&](const void* p, float (&o)[PER]) {
     if (XBF) {
-      const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p) + (size_t)m * C + lane * PER);
+      const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p) + (size_t)m * C) + lane;
 #pragma unroll
-      for (int i = 0; i < PER / 8; ++i) {
-        const uint4 w = r[i];
+      for (int i = 0; i < NCH; ++i) {
+        const uint4 w = r[32 * i];
         o[8 * i] = bf_lo(w.x); o[8 * i + 1] = bf_hi(w.x); o[8 * i + 2] = bf_lo(w.y); o[8 * i + 3] = bf_hi(w.y);
         o[8 * i + 4] = bf_lo(w.z); o[8 * i + 5] = bf_hi(w.z); o[8 * i + 6] = bf_lo(w.w); o[8 * i + 7] = bf_hi(w.w);
       }
     } else {
-      const float4* r = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + (size_t)m * C + lane * PER);
+      const float4* r = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + (size_t)m * C) + lane;
 #pragma unroll
-      for (int i = 0; i < PER / 4; ++i) {
-        const float4 w = r[i];
+      for (int i = 0; i < NCH; ++i) {
+        const float4 w = r[32 * i];
         o[4 * i] = w.x; o[4 * i + 1] = w.y; o[4 * i + 2] = w.z; o[4 * i + 3] = w.w;
       }
     }
@@ -91,18 +95,30 @@ __global__ __launch_bounds__(256) void ln_rows_wide_kernel(const void* __restric
   q = warp_sum(q);
   const float rstd = rsqrtf(q * (1.f / C) + LN_EPS);
 #pragma unroll
-  for (int i = 0; i < PER; ++i) v[i] = (v[i] - mean) * rstd * __ldg(g + lane * PER + i) + __ldg(b + lane * PER + i);
-  if (y16 != nullptr) {
-    uint4* o = reinterpret_cast<uint4*>(y16 + (size_t)m * C + lane * PER);
+  for (int i = 0; i < NCH; ++i) {
+    const int c0 = (32 * i + lane) * VEC;          // first column of the chunk
 #pragma unroll
-    for (int i = 0; i < PER / 8; ++i)
-      o[i] = make_uint4(pk2(v[8 * i], v[8 * i + 1]), pk2(v[8 * i + 2], v[8 * i + 3]), pk2(v[8 * i + 4], v[8 * i + 5]),
-                        pk2(v[8 * i + 6], v[8 * i + 7]));
-  }
-  if (y32 != nullptr) {
-    float4* o = reinterpret_cast<float4*>(y32 + (size_t)m * C + lane * PER);
+    for (int e = 0; e < VEC; e += 4) {
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c0 + e)), bb = __ldg(reinterpret_cast<const float4*>(b + c0 + e));
+      float* t = v + VEC * i + e;
+      t[0] = (t[0] - mean) * rstd * gg.x + bb.x; t[1] = (t[1] - mean) * rstd * gg.y + bb.y;
+      t[2] = (t[2] - mean) * rstd * gg.z + bb.z; t[3] = (t[3] - mean) * rstd * gg.w + bb.w;
+    }
+    if (y16 != nullptr) {
+      bf16* o = y16 + (size_t)m * C + c0;
+      if (VEC == 8) {
+        *reinterpret_cast<uint4*>(o) = make_uint4(pk2(v[8 * i], v[8 * i + 1]), pk2(v[8 * i + 2], v[8 * i + 3]),
+                                                  pk2(v[8 * i + 4], v[8 * i + 5]), pk2(v[8 * i + 6], v[8 * i + 7]));
+      } else {
+        *reinterpret_cast<uint2*>(o) = make_uint2(pk2(v[4 * i], v[4 * i + 1]), pk2(v[4 * i + 2], v[4 * i + 3]));
+      }
+    }
+    if (y32 != nullptr) {
+      float* o = y32 + (size_t)m * C + c0;
 #pragma unroll
-    for (int i = 0; i < PER / 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      for (int e = 0; e < VEC; e += 4)
+        *reinterpret_cast<float4*>(o + e) = make_float4(v[VEC * i + e], v[VEC * i + e + 1], v[VEC * i + e + 2], v[VEC * i + e + 3]);
+    }
   }
 }
 
@@ -124,7 +140,7 @@ __device__ __forceinline__ void pa_ldsm4t(uint32_t (&r)[4], uint32_t addr) {
 
 // softmax(Q K^T / sqrt(HD) + key padding mask) V for one (64-query tile, head, sequence).  qkv: bf16 [M][3C] rows =
 // tokens (Q | K | V column blocks, head h = columns h * HD ..), kmask uint8 [M] (1 = valid key), out bf16 [M][C].
-// Warp w owns query rows 16 w .. 16 w + 15 of the tile; keys stream through shared memory in tiles of 64.
+// Warp w owns query rows 16 w .. 16 w + 15 of the tile; keys stream through a two-stage cp.async ring of 64-key tiles.
 template <int HD_>
 __global__ __launch_bounds__(128) void enc_attention_kernel(const bf16* __restrict__ qkv, const uint8_t* __restrict__ kmask,
                                                             int L, int C, float scale, bf16* __restrict__ out) {
@@ -134,21 +150,39 @@ __global__ __launch_bounds__(128) void enc_attention_kernel(const bf16* __restri
   constexpr int CH = HD_ / 8;                       // 16-byte chunks per row
   extern __shared__ __align__(128) unsigned char sm[];
   bf16* Qs = reinterpret_cast<bf16*>(sm);
-  bf16* Ks = Qs + 64 * LD;
-  bf16* Vs = Ks + 64 * LD;
-  uint8_t* ms = reinterpret_cast<uint8_t*>(Vs + 64 * LD);
+  bf16* KV = Qs + 64 * LD;                          // two stages of (K tile, V tile), 64 x LD each
+  uint8_t* msk = reinterpret_cast<uint8_t*>(KV + 4 * 64 * LD);     // [2][64]
   pdl_wait();
   const int qt = blockIdx.x, h = blockIdx.y, seq = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
   const size_t row0 = (size_t)seq * L;
   const int ld = 3 * C;
-  // Q tile
+  // 16-byte cp.async with zero fill for the positions past the sequence
+  auto cp16 = [](const bf16* dst, const bf16* src, bool ok) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+  };
+  auto fetch_kv = [&](int kt) {                     // key tile kt -> stage kt & 1
+    bf16* Kd = KV + (kt & 1) * 2 * 64 * LD;
+    bf16* Vd = Kd + 64 * LD;
+    for (int i = tid; i < 64 * CH; i += 128) {
+      const int r = i / CH, c = i - r * CH, pos = kt * 64 + r;
+      const bool ok = pos < L;
+      const bf16* src = qkv + (row0 + (ok ? pos : 0)) * ld + C + h * HD_ + c * 8;
+      cp16(Kd + r * LD + c * 8, src, ok);
+      cp16(Vd + r * LD + c * 8, src + C, ok);
+    }
+    if (tid < 64) { const int pos = kt * 64 + tid; msk[(kt & 1) * 64 + tid] = pos < L ? kmask[row0 + pos] : 0; }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // Q tile, then the first key tile; the loop keeps one tile in flight behind the one it computes on
   for (int i = tid; i < 64 * CH; i += 128) {
     const int r = i / CH, c = i - r * CH, pos = qt * 64 + r;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (pos < L) v = *reinterpret_cast<const uint4*>(qkv + (row0 + pos) * ld + h * HD_ + c * 8);
-    *reinterpret_cast<uint4*>(Qs + r * LD + c * 8) = v;
+    const bool ok = pos < L;
+    cp16(Qs + r * LD + c * 8, qkv + (row0 + (ok ? pos : 0)) * ld + h * HD_ + c * 8, ok);
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  fetch_kv(0);
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
   __syncthreads();
   uint32_t qf[KS][4];
 #pragma unroll
@@ -160,19 +194,17 @@ __global__ __launch_bounds__(128) void enc_attention_kernel(const bf16* __restri
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   const int nkt = (L + 63) / 64;
   for (int kt = 0; kt < nkt; ++kt) {
-    __syncthreads();                                // the previous tile is consumed
-    for (int i = tid; i < 64 * CH; i += 128) {
-      const int r = i / CH, c = i - r * CH, pos = kt * 64 + r;
-      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-      if (pos < L) {
-        kv = *reinterpret_cast<const uint4*>(qkv + (row0 + pos) * ld + C + h * HD_ + c * 8);
-        vv = *reinterpret_cast<const uint4*>(qkv + (row0 + pos) * ld + 2 * C + h * HD_ + c * 8);
-      }
-      *reinterpret_cast<uint4*>(Ks + r * LD + c * 8) = kv;
-      *reinterpret_cast<uint4*>(Vs + r * LD + c * 8) = vv;
+    __syncthreads();                                // the stage the next fetch overwrites is consumed
+    if (kt + 1 < nkt) {
+      fetch_kv(kt + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    if (tid < 64) { const int pos = kt * 64 + tid; ms[tid] = pos < L ? kmask[row0 + pos] : 0; }
     __syncthreads();
+    const bf16* Ks = KV + (kt & 1) * 2 * 64 * LD;
+    const bf16* Vs = Ks + 64 * LD;
+    const uint8_t* ms = msk + (kt & 1) * 64;
     // ---- S = Q K^T for the 64 keys of the tile (8 n-tiles)
     float s[8][4];
 #pragma unroll
@@ -601,7 +633,7 @@ extern "C" int case_enc_attention(const void* qkv, const uint8_t* kmask, int nse
   const float scale = 1.f / sqrtf((float)hd);
   dim3 grid((L + 63) / 64, nhead, nseq);
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = (size_t)3 * 64 * (hd + 8) * 2 + 64;
+  const size_t smem = (size_t)5 * 64 * (hd + 8) * 2 + 128;
   if (hd == 32) {
     launch_k(enc_attention_kernel<32>, grid, 128, smem, st, (const bf16*)qkv, kmask, L, C, scale, (bf16*)out);
   } else {
