@@ -596,10 +596,56 @@ def extra_lines(args, dev, torch):
         except Exception as ex:      # evidence beside the headline: never fail the bench line over it
             return dict(unavailable=repr(ex)[:200])
     out['fp32'] = quick('c2', CONFIGS['c2'], 'fp32')
+    out['from_token_ids'] = from_token_ids(args, CONFIGS['c2'], dev, torch)
     share = dict(CONFIGS['c5'], rows=32, label='per-GPU share of c5 at 8 GPUs: 32 queries, beam 8, 20 x 512-token passages')
     out['other_configs'] = dict(c1=quick('c1', CONFIGS['c1'], 'bf16'), c4=quick('c4', CONFIGS['c4'], 'bf16'),
                                 c5_per_gpu_share=quick('c5', share, 'bf16'))
     return out
+
+
+def from_token_ids(args, cfg, dev, torch, steps=3):
+    """the whole of ``CaSE.do_test`` on the device.  Each pass copies only the token ids (query, passage,
+    source_map) from pinned host memory, runs the pre-decode producers (encoder, two Interactions, transformer blocks,
+    scorers, prior / answer_rep - case_rg_b200/producers.py), the prefill and the beam decode, and reads the answers back.
+    Random-init producer weights of the reference's architecture; value in answer tokens / s like the headline."""
+    try:
+        from case_rg_b200 import synthetic as syn, generations as FG, _lib as L
+        T, W, V, B = cfg['T'], cfg['W'], cfg['V'], cfg['B']
+        model = FG.FastCaSE(syn.make_case_decoder_state(WSEED, V, H), device=dev, dtype='bf16', max_dec_len=T, beam_width=W,
+                            vocab_impl=1, use_graph=not args.no_graph,
+                            producers=syn.make_case_producer_state(WSEED + 1, V, H))
+        prod = model.producers
+        inp = syn.make_case_inputs(ISEED, B, cfg['Lq'], cfg['NP'], cfg['Lp'], V, H)
+        host = {k: getattr(inp, k).pin_memory() for k in ('query', 'passage', 'source_map')}
+
+        def one():
+            d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            return model.search_ids(d, T, W, 'beam')['answer'].cpu()
+
+        def ev(fn, n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(n):
+                r = fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / n, r
+        for _ in range(2):
+            ans = one()
+        toks = _answer_tokens(ans, False)
+        ms, ans = ev(one, steps)
+        q, p = host['query'].to(dev), host['passage'].to(dev)
+        ms_prod, _ = ev(lambda: prod(q, p), steps)
+        res = dict(value=toks / (ms * 1e-3), unit='tokens/s', ms_per_batch=ms, producers_ms=ms_prod,
+                   h2d_bytes_per_batch=sum(v.numel() * v.element_size() for v in host.values()),
+                   d2h_bytes_per_batch=int(ans.numel() * ans.element_size()), answer_tokens_per_batch=toks, steps=steps,
+                   workload='c2 from token ids: producers + prefill + beam-4 decode, host ids in, answers out')
+        del model, prod
+        torch.cuda.empty_cache()
+        return res
+    except Exception as ex:          # evidence beside the headline: never fail the bench line over it
+        return dict(unavailable=repr(ex)[:300])
 
 
 # ----------------------------------------------------------------------------- roofline
@@ -624,7 +670,9 @@ def roofline(wl, eng, ms_per_decode_step, torch, dev):
     """`roofline` object of the JSON line.  Top level = the dominant BANDWIDTH-bound kernel (the passage-memory cross-
     attention, 4 launches per decode step), timed IN the decode graph (CUPTI records of one batch); `kernels` = the same
     for every kernel with a byte or flop model; `step` = the whole decode step against the HBM peak (algorithmic bytes of
-    an incremental decoder over the VALID keys; DESIGN.md §4 states every term)."""
+    an incremental decoder over the VALID keys; DESIGN.md §4 states every term).  In-graph durations are
+    CUPTI's start-to-end of each launch: with programmatic dependent launch a kernel's record starts when its first CTA is
+    resident, i.e. it includes the wait for the predecessor's tail - the per-kernel fractions are lower bounds."""
     L = wl.L
     peaks = {}
     try:
@@ -656,8 +704,9 @@ def roofline(wl, eng, ms_per_decode_step, torch, dev):
                                       'Uk.mem rows + gate-projected keys of the valid keys (mean of the two launches)'),
         'vocab_gemm_tc_kernel': ('tensor', 2.0 * R * H * V, '2 R H V flops'),
         'vocab_base_kernel': ('l2', R * V * 4, 'one read of the fp32 logits tile (L2-resident)'),
-        'prefill_project_tc_kernel': ('tensor', 2.0 * (B * (S0 + S1) / 2.0) * H * (8 * H + H),
-                                      '2 keys H (8H K|V columns + H Uk columns) flops (mean of the two launches)'),
+        'prefill_project_tc_kernel': ('tensor', 2.0 * ((valid0 + valid1) / 2.0) * H * (8 * H + H),
+                                      '2 valid_keys H (8H K|V columns + H Uk columns) flops (mean of the two launches; '
+                                      'padded keys are neither gathered nor multiplied)'),
     }
     kernels = []
     for name, (bound, work, what) in models.items():
