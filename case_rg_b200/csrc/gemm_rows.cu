@@ -2,30 +2,34 @@
 //
 //   Y[M][N] = mask_rows( act( X[M][K] . W[N][K]^T + bias[N] ) + residual[M][N] )
 //
-// X: bf16 row-major (the LayerNorm / attention / previous GEMM output), K % 128 == 0; W: the nn.Linear weight packed per
-// 128-wide K block into 256-row tiles of the UMMA K-major no-swizzle canonical layout ([K/128][N/256][64 KB]); Y: bf16 or
-// fp32 row-major.  One CTA owns 128 rows (UMMA M = 128 = the TMEM lanes) and walks N in chunks of 256 columns (UMMA
-// N = 256: 96 B/clk of shared-memory operand reads, against 128 B/clk at N = 128); a chunk's accumulator D[128 x 256]
-// (fp32) lives in one half of tensor memory while the epilogue drains the other half.  The K loop runs over a two-stage
-// ring of (A tile 128 x 128, W tile 256 x 128) = 96 KB per stage:
-//   warps 0-3 / 4-7  producers of the even / odd stages: the A tile is gathered with 16-byte cp.async (16 per thread, all
-//                    in flight, a full 128-byte line per quarter warp; rows past M are zero-filled) into the 128-byte-swizzle
-//                    K-major layout (conflict-free on the shared-memory side), the pre-packed W tile arrives as four bulk
-//                    copies; two stages are in flight at any time, so the gather latency of one hides behind the other
-//   warp 16          MMA issuer (one thread): 8 tcgen05.mma (M = 128, N = 256, K = 16) per stage; tcgen05.commit signals
+// X: bf16 row-major (the LayerNorm / attention / previous GEMM output), K % 64 == 0; W: the nn.Linear weight packed per
+// 64-wide K block into 256-row tiles of the UMMA K-major no-swizzle canonical layout ([K/64][N/256][32 KB]); Y: bf16 or
+// fp32 row-major.  Persistent grid (one CTA per SM): a CTA takes row tiles of 128 (UMMA M = 128 = the TMEM lanes) and walks
+// N in chunks of 256 columns (UMMA N = 256: 96 B/clk of shared-memory operand reads, against 128 B/clk at N = 128); the
+// accumulator D[128 x 256] (fp32) of a (row tile, chunk) unit lives in one half of tensor memory while the epilogue drains
+// the other half.  The K loop runs over a four-stage ring of (A tile 128 x 64, W tile 256 x 64) = 48 KB per stage that
+// runs on across units:
+//   warps 0-3        producers: the A tile is gathered with 16-byte cp.async (8 per thread and stage, a full 128-byte line
+//                    per quarter warp; rows past M are zero-filled) into the 128-byte-swizzle K-major layout
+//                    (conflict-free on the shared-memory side), the pre-packed W tile arrives as four bulk copies; a
+//                    stage is handed to the tensor core two iterations after its copies were issued
+//                    (cp.async.wait_group 2), so three gathers are in flight behind the stage being multiplied
+//   warp 12          MMA issuer (one thread): 4 tcgen05.mma (M = 128, N = 256, K = 16) per stage; tcgen05.commit signals
 //                    "stage free" and "accumulator complete"
-//   warps 8-15       epilogue: tcgen05.ld (lane = row, 32 columns at a time), bias / gelu / relu / residual / row mask,
-//                    64-byte (bf16) or 128-byte (fp32) stores per thread
+//   warps 4-11       epilogue: tcgen05.ld (lane = row, 32 columns at a time), bias / gelu / relu / residual / row mask,
+//                    residual loads and output stores staged through shared memory so that global memory sees whole
+//                    sectors (4 lanes per row, 64 contiguous bytes)
 #include "common.cuh"
 
 namespace cb {
 
-constexpr int GR_M = 128, GR_NC = 256, GR_KB = 128;
-constexpr int GR_A_BYTES = GR_M * GR_KB * 2;         // 32 KB
-constexpr int GR_W_BYTES = GR_NC * GR_KB * 2;        // 64 KB
-constexpr int GR_STAGE = GR_A_BYTES + GR_W_BYTES;    // 96 KB
-constexpr int GR_THREADS = 17 * 32;
-constexpr int GR_SMEM = 2 * GR_STAGE + 256;
+constexpr int GR_M = 128, GR_NC = 256, GR_KB = 64, GR_NS = 4;
+constexpr int GR_A_BYTES = GR_M * GR_KB * 2;         // 16 KB: one 128-byte-swizzle atom column (64 k) of 128 rows
+constexpr int GR_W_BYTES = GR_NC * GR_KB * 2;        // 32 KB
+constexpr int GR_STAGE = GR_A_BYTES + GR_W_BYTES;    // 48 KB
+constexpr int GR_THREADS = 13 * 32;
+constexpr int GR_STG = 32 * 80;                       // epilogue staging block of a warp: 32 rows x (64 + 16) bytes
+constexpr int GR_SMEM = GR_NS * GR_STAGE + 256 + 8 * GR_STG;
 
 __device__ __forceinline__ void gr_mbar_init(uint32_t bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -112,10 +116,12 @@ struct GemmRowsArgs {
 __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmRowsArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t s_base = smem_u32(smem);
-  const uint32_t s_bar = s_base + 2 * GR_STAGE;
+  const uint32_t s_bar = s_base + GR_NS * GR_STAGE;
+  const uint32_t BAR_A = s_bar, BAR_W = s_bar + 8 * GR_NS, BAR_FREE = s_bar + 16 * GR_NS, BAR_ACC = s_bar + 24 * GR_NS,
+                 BAR_ACCF = BAR_ACC + 16;
   // barriers: [0,1] a_full (128 gather threads), [2,3] w_full (4 issuing lanes + bytes), [4,5] stage free (MMAs done),
   //           [6,7] acc_full, [8,9] acc_free (8 epilogue warps)
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + 2 * GR_STAGE + 128);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + GR_NS * GR_STAGE + 192);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // persistent: this CTA owns the row tiles blockIdx.x, blockIdx.x + gridDim.x, ...; a work unit is (row tile, 256-column
   // chunk), the stage ring and the two accumulators run on across units so the epilogue of one overlaps the next one's MMAs
@@ -126,11 +132,13 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
   const int nit = nunit * KB;                           // ring iterations
 
   if (tid == 0) {
-    gr_mbar_init(s_bar, 128); gr_mbar_init(s_bar + 8, 128);
-    gr_mbar_init(s_bar + 16, 4); gr_mbar_init(s_bar + 24, 4);
-    gr_mbar_init(s_bar + 32, 1); gr_mbar_init(s_bar + 40, 1);
-    gr_mbar_init(s_bar + 48, 1); gr_mbar_init(s_bar + 56, 1);
-    gr_mbar_init(s_bar + 64, 8); gr_mbar_init(s_bar + 72, 8);
+    for (int i = 0; i < GR_NS; ++i) {
+      gr_mbar_init(BAR_A + 8 * i, 128);                 // A tile of the stage gathered (128 producer threads)
+      gr_mbar_init(BAR_W + 8 * i, 4);                   // W tile landed (4 issuing lanes + bytes)
+      gr_mbar_init(BAR_FREE + 8 * i, 1);                // the MMAs that read the stage are done
+    }
+    gr_mbar_init(BAR_ACC, 1); gr_mbar_init(BAR_ACC + 8, 1);           // accumulator of a unit complete
+    gr_mbar_init(BAR_ACCF, 8); gr_mbar_init(BAR_ACCF + 8, 8);         // ... drained by the 8 epilogue warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -143,138 +151,176 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
   const uint32_t tmem = *s_tmem;
   pdl_wait();
 
-  if (warp < 8) {
-    // ================= producers: group g = warp / 4 feeds the stages it with (it & 1) == g
-    const int g = warp >> 2, w4 = warp & 3;
-    const uint32_t s_a = s_base + g * GR_STAGE, s_w = s_a + GR_A_BYTES;
+  if (warp < 4) {
+    // ================= producers (4 warps): stage it & 1 is filled while the copies of stage (it - 1) & 1 land
+    const int w4 = warp;
     // gather role: a quarter warp (8 lanes) copies one 128-byte run of a source row - one full cache line per request - into
     // the 128-byte-swizzle layout, where its eight 16-byte chunks land in eight different bank groups
     const int rq = w4 * 4 + (lane >> 3), ch = lane & 7;
-    for (int it = g; it < nit; it += 2) {
-      const int u = it / KB, kb = it - u * KB, use = it >> 1;
+    for (int it = 0; it < nit; ++it) {
+      const int g = it % GR_NS, use = it / GR_NS;
+      const uint32_t s_a = s_base + g * GR_STAGE, s_w = s_a + GR_A_BYTES;
+      const int u = it / KB, kb = it - u * KB;
       const int mt = u / nchunk, c = u - mt * nchunk;
       const long long m0 = ((long long)blockIdx.x + (long long)mt * gridDim.x) * GR_M;
-      if (use >= 1) gr_wait(s_bar + 32 + 8 * g, (uint32_t)(use - 1) & 1u);      // the MMAs of this stage's previous use are done
+      if (use >= 1) gr_wait(BAR_FREE + 8 * g, (uint32_t)(use - 1) & 1u);        // the MMAs of this stage's previous use are done
       if (lane == 0) {
         const char* src = reinterpret_cast<const char*>(a.Wp) + ((size_t)kb * nchunk + c) * GR_W_BYTES + (size_t)w4 * (GR_W_BYTES / 4);
-        gr_expect_tx(s_bar + 16 + 8 * g, GR_W_BYTES / 4);
-        gr_bulk(s_w + w4 * (GR_W_BYTES / 4), src, GR_W_BYTES / 4, s_bar + 16 + 8 * g);
+        gr_expect_tx(BAR_W + 8 * g, GR_W_BYTES / 4);
+        gr_bulk(s_w + w4 * (GR_W_BYTES / 4), src, GR_W_BYTES / 4, BAR_W + 8 * g);
       }
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {                      // the two 64-wide K atoms of the stage
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = i * 16 + rq;
-          const long long m = m0 + row;
-          const bf16* src = a.X + (size_t)(m < a.M ? m : 0) * a.K + kb * GR_KB + h * 64 + ch * 8;
-          const uint32_t dst = s_a + h * (GR_A_BYTES / 2) + (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4);
-          const int nbytes = m < a.M ? 16 : 0;           // rows past M are zero-filled
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
-        }
+      for (int i = 0; i < 8; ++i) {
+        const int row = i * 16 + rq;
+        const long long m = m0 + row;
+        const bf16* src = a.X + (size_t)(m < a.M ? m : 0) * a.K + kb * GR_KB + ch * 8;
+        const uint32_t dst = s_a + (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4);
+        const int nbytes = m < a.M ? 16 : 0;             // rows past M are zero-filled
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-      gr_arrive(s_bar + 8 * g);
+      if (it >= GR_NS - 2) {                             // GR_NS - 1 gathers stay in flight behind the one handed over
+        asm volatile("cp.async.wait_group %0;" ::"n"(GR_NS - 2) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        gr_arrive(BAR_A + 8 * ((it - (GR_NS - 2)) % GR_NS));
+      }
     }
-  } else if (warp == 16) {
+    // drain: the last GR_NS - 2 stages
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int it = (nit > GR_NS - 2 ? nit - (GR_NS - 2) : 0); it < nit; ++it) gr_arrive(BAR_A + 8 * (it % GR_NS));
+  } else if (warp == 12) {
     // ================= MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = gr_idesc(GR_M, GR_NC);
       int it = 0;
       for (int c = 0; c < nunit; ++c) {
         const int tb = c & 1;
-        if (c >= 2) gr_wait(s_bar + 64 + 8 * tb, (uint32_t)((c >> 1) - 1) & 1u);      // epilogue of unit c - 2 done
+        if (c >= 2) gr_wait(BAR_ACCF + 8 * tb, (uint32_t)((c >> 1) - 1) & 1u);        // epilogue of unit c - 2 done
         for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int g = it & 1;
-          const uint32_t par = (uint32_t)(it >> 1) & 1u;
-          gr_wait(s_bar + 8 * g, par);
-          gr_wait(s_bar + 16 + 8 * g, par);
+          const int g = it % GR_NS;
+          const uint32_t par = (uint32_t)(it / GR_NS) & 1u;
+          gr_wait(BAR_A + 8 * g, par);
+          gr_wait(BAR_W + 8 * g, par);
           gr_fence_after();
           const uint32_t s_a = s_base + g * GR_STAGE, s_w = s_a + GR_A_BYTES;
 #pragma unroll
           for (int ks = 0; ks < GR_KB / 16; ++ks) {
             const int kc = ks * 2;
-            const uint64_t ad = gr_desc_sw128(s_a + (ks >> 2) * (GR_A_BYTES / 2) + (ks & 3) * 32);
+            const uint64_t ad = gr_desc_sw128(s_a + ks * 32);
             const uint64_t bd = gr_desc(s_w + kc * (GR_NC / 8) * 128, (GR_NC / 8) * 128, 128);
             gr_umma(tmem + tb * GR_NC, ad, bd, idesc, (kb | ks) != 0);
           }
-          gr_commit(s_bar + 32 + 8 * g);                 // stage free once these MMAs have read it
+          gr_commit(BAR_FREE + 8 * g);                   // stage free once these MMAs have read it
         }
-        gr_commit(s_bar + 48 + 8 * tb);                  // accumulator of the chunk complete
+        gr_commit(BAR_ACC + 8 * tb);                     // accumulator of the unit complete
       }
     }
   } else {
-    // ================= epilogue (warps 8-15): warp & 3 = TMEM lane quarter, (warp - 8) >> 2 = which 32-column groups
-    const int q = warp & 3, hh = (warp - 8) >> 2;
+    // ================= epilogue (warps 4-11): warp & 3 = TMEM lane quarter, (warp - 4) >> 2 = which 32-column groups
+    const int q = warp & 3, hh = (warp - 4) >> 2;
+    unsigned char* stg = smem + GR_NS * GR_STAGE + 256 + (warp - 4) * GR_STG;      // this warp's staging block
     for (int u = 0; u < nunit; ++u) {
       const int mt = u / nchunk, c = u - mt * nchunk;
       const long long m = ((long long)blockIdx.x + (long long)mt * gridDim.x) * GR_M + q * 32 + lane;
       const bool rowok = m < a.M;
       const bool keep = rowok && (a.row_mask == nullptr || a.row_mask[m] != 0);
       const int tb = u & 1;
-      gr_wait(s_bar + 48 + 8 * tb, (uint32_t)(u >> 1) & 1u);
+      gr_wait(BAR_ACC + 8 * tb, (uint32_t)(u >> 1) & 1u);
       gr_fence_after();
+      const long long mw = m - lane;                   // first row of the warp's 32
       for (int cg = hh; cg < GR_NC / 32; cg += 2) {
         const int n0 = c * GR_NC + cg * 32;
         uint32_t acc[32];
         gr_tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + tb * GR_NC + cg * 32, acc);
         gr_tmem_ld_wait();
-        if (rowok) {
-          float v[32];
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + j));
-            v[j] = __uint_as_float(acc[j]) + b4.x; v[j + 1] = __uint_as_float(acc[j + 1]) + b4.y;
-            v[j + 2] = __uint_as_float(acc[j + 2]) + b4.z; v[j + 3] = __uint_as_float(acc[j + 3]) + b4.w;
-          }
-          if (a.act == 1) {
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + j));
+          v[j] = __uint_as_float(acc[j]) + b4.x; v[j + 1] = __uint_as_float(acc[j + 1]) + b4.y;
+          v[j + 2] = __uint_as_float(acc[j + 2]) + b4.z; v[j + 3] = __uint_as_float(acc[j + 3]) + b4.w;
+        }
+        if (a.act == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          } else if (a.act == 2) {
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (a.act == 2) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (a.res != nullptr) {
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        // Residual and output go through the warp's staging block (32 rows x 64 bytes, 80-byte row stride): global memory
+        // is touched with 4 lanes per row and 8 rows per instruction - whole 32-byte sectors, 64 contiguous bytes per row -
+        // while a lane reads / writes its own row in shared memory.
+        if (a.res != nullptr) {
+          const int nsb = a.res_bf16 ? 1 : 2;            // 64-byte sub-blocks per 32 columns
+          const size_t rstride = (size_t)a.N * (a.res_bf16 ? 2 : 4);
+          const char* rbase = reinterpret_cast<const char*>(a.res) + (size_t)n0 * (a.res_bf16 ? 2 : 4);
+          for (int sb = 0; sb < nsb; ++sb) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int r = it * 8 + (lane >> 2);
+              if (mw + r < a.M)
+                *reinterpret_cast<uint4*>(stg + r * 80 + (lane & 3) * 16) =
+                    __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(mw + r) * rstride + sb * 64 + (lane & 3) * 16));
+            }
+            __syncwarp();
             if (a.res_bf16) {
-              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.res) + (size_t)m * a.N + n0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const uint4 w = rp[j];
+                const uint4 w = *reinterpret_cast<const uint4*>(stg + lane * 80 + j * 16);
                 v[8 * j] += __uint_as_float(w.x << 16); v[8 * j + 1] += __uint_as_float(w.x & 0xffff0000u);
                 v[8 * j + 2] += __uint_as_float(w.y << 16); v[8 * j + 3] += __uint_as_float(w.y & 0xffff0000u);
                 v[8 * j + 4] += __uint_as_float(w.z << 16); v[8 * j + 5] += __uint_as_float(w.z & 0xffff0000u);
                 v[8 * j + 6] += __uint_as_float(w.w << 16); v[8 * j + 7] += __uint_as_float(w.w & 0xffff0000u);
               }
             } else {
-              const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.res) + (size_t)m * a.N + n0);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 w = rp[j];
-                v[4 * j] += w.x; v[4 * j + 1] += w.y; v[4 * j + 2] += w.z; v[4 * j + 3] += w.w;
+              for (int j = 0; j < 4; ++j) {
+                const float4 w = *reinterpret_cast<const float4*>(stg + lane * 80 + j * 16);
+                float* t = v + (sb ? 16 : 0) + 4 * j;
+                t[0] += w.x; t[1] += w.y; t[2] += w.z; t[3] += w.w;
               }
             }
+            __syncwarp();
           }
-          if (!keep) {
+        }
+        if (!keep) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-          }
-          if (a.y_bf16) {
-            uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(a.Y) + (size_t)m * a.N + n0);
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        {
+          const int nsb = a.y_bf16 ? 1 : 2;
+          const size_t ystride = (size_t)a.N * (a.y_bf16 ? 2 : 4);
+          char* ybase = reinterpret_cast<char*>(a.Y) + (size_t)n0 * (a.y_bf16 ? 2 : 4);
+          for (int sb = 0; sb < nsb; ++sb) {
+            if (a.y_bf16) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)     // streaming stores: Y passes through L2 once, X and W tiles are re-read from it
-              __stcs(yp + j, make_uint4(gr_pk2(v[8 * j], v[8 * j + 1]), gr_pk2(v[8 * j + 2], v[8 * j + 3]),
-                                        gr_pk2(v[8 * j + 4], v[8 * j + 5]), gr_pk2(v[8 * j + 6], v[8 * j + 7])));
-          } else {
-            float4* yp = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.Y) + (size_t)m * a.N + n0);
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(stg + lane * 80 + j * 16) =
+                    make_uint4(gr_pk2(v[8 * j], v[8 * j + 1]), gr_pk2(v[8 * j + 2], v[8 * j + 3]),
+                               gr_pk2(v[8 * j + 4], v[8 * j + 5]), gr_pk2(v[8 * j + 6], v[8 * j + 7]));
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) __stcs(yp + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+              for (int j = 0; j < 4; ++j) {
+                const float* t = v + (sb ? 16 : 0) + 4 * j;
+                *reinterpret_cast<float4*>(stg + lane * 80 + j * 16) = make_float4(t[0], t[1], t[2], t[3]);
+              }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {             // streaming stores: Y passes through L2 once
+              const int r = it * 8 + (lane >> 2);
+              if (mw + r < a.M)
+                __stcs(reinterpret_cast<uint4*>(ybase + (size_t)(mw + r) * ystride + sb * 64 + (lane & 3) * 16),
+                       *reinterpret_cast<const uint4*>(stg + r * 80 + (lane & 3) * 16));
+            }
+            __syncwarp();
           }
         }
       }
       gr_fence_before();
       __syncwarp();
-      if (lane == 0) gr_arrive(s_bar + 64 + 8 * tb);
+      if (lane == 0) gr_arrive(BAR_ACCF + 8 * tb);
     }
   }
   gr_fence_before();
@@ -287,7 +333,7 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
 
 using namespace cb;
 
-/* packed weight bytes for an [N][K] Linear: K / 128 blocks x N / 256 tiles of 64 KB */
+/* packed weight bytes for an [N][K] Linear: K / 64 blocks x N / 256 tiles of 32 KB */
 extern "C" size_t case_gemm_rows_packed_weight_bytes(int N, int K) {
   return (size_t)(K / GR_KB) * ((N + GR_NC - 1) / GR_NC) * GR_W_BYTES;
 }
@@ -296,7 +342,7 @@ extern "C" int case_gemm_rows_tc(const void* X, const void* Wp, const float* bia
                                  const void* residual, int residual_dtype, const uint8_t* row_mask, void* Y, int y_dtype,
                                  case_stream_t stream) {
   CB_REQUIRE(X && Wp && bias && Y && M > 0, "case_gemm_rows_tc: null pointer");
-  CB_REQUIRE(N > 0 && N % GR_NC == 0 && K > 0 && K % GR_KB == 0, "case_gemm_rows_tc: N must be a multiple of 256 and K of 128");
+  CB_REQUIRE(N > 0 && N % GR_NC == 0 && K > 0 && K % GR_KB == 0, "case_gemm_rows_tc: N must be a multiple of 256 and K of 64");
   CB_REQUIRE(act >= 0 && act <= 2, "case_gemm_rows_tc: act is 0 (none), 1 (gelu) or 2 (relu)");
   CB_REQUIRE(((uintptr_t)X % 16 == 0) && ((uintptr_t)Wp % 16 == 0) && ((uintptr_t)Y % 16 == 0) && ((uintptr_t)bias % 16 == 0) &&
                  ((uintptr_t)residual % 16 == 0),

@@ -32,17 +32,17 @@ def _u8(mask):
 
 
 class _Linear:
-    """nn.Linear weights for case_gemm_rows_tc: the [N, K] matrix packed per 128-wide K block into 256-row tiles of the
+    """nn.Linear weights for case_gemm_rows_tc: the [N, K] matrix packed per 64-wide K block into 256-row tiles of the
     UMMA canonical layout (engine.pack_vocab_tc), bias fp32; the plain bf16 matrix is kept for the cuBLAS A/B path."""
 
     def __init__(self, w, b, dev):
         from .engine import pack_vocab_tc
         w = w.detach().to(dev, torch.float32)
         self.N, self.K = w.shape
-        if self.K % 128 or self.N % 256:
-            raise ValueError(f'Linear needs in_features % 128 == 0 and out_features % 256 == 0, got {self.N} x {self.K}')
+        if self.K % 64 or self.N % 256:
+            raise ValueError(f'Linear needs in_features % 64 == 0 and out_features % 256 == 0, got {self.N} x {self.K}')
         self.w16 = w.to(torch.bfloat16).contiguous()
-        self.wp = torch.stack([pack_vocab_tc(w[:, 128 * kb:128 * (kb + 1)], rows=256) for kb in range(self.K // 128)]).contiguous()
+        self.wp = torch.stack([pack_vocab_tc(w[:, 64 * kb:64 * (kb + 1)], rows=256) for kb in range(self.K // 64)]).contiguous()
         self.b = (b.detach().to(dev, torch.float32) if b is not None else torch.zeros(self.N, device=dev)).contiguous()
 
 

@@ -501,9 +501,9 @@ int case_prior_answer(const float* pscore, const float* tscore, const uint8_t* p
                       int Lp, float* prior, float* answer, case_stream_t stream);
 
 /* Y[M][N] = mask_rows( act( X[M][K] . W[N][K]^T + bias ) + residual ) on tcgen05 / TMEM.  X bf16 row-major; Wp = the
- * nn.Linear weight packed per 128-wide K block into 256-row tiles of the UMMA K-major no-swizzle canonical layout (element
- * (n, k) of a tile at byte (k/8)*4096 + (n/8)*128 + (n%8)*16 + (k%8)*2; [K/128][N/256][64 KB],
- * case_gemm_rows_packed_weight_bytes); N % 256 == 0, K % 128 == 0; act: 0 none, 1 gelu (erf),
+ * nn.Linear weight packed per 64-wide K block into 256-row tiles of the UMMA K-major no-swizzle canonical layout (element
+ * (n, k) of a tile at byte (k/8)*4096 + (n/8)*128 + (n%8)*16 + (k%8)*2; [K/64][N/256][32 KB],
+ * case_gemm_rows_packed_weight_bytes); N % 256 == 0, K % 64 == 0; act: 0 none, 1 gelu (erf),
  * 2 relu; residual [M][N] fp32 / bf16 or NULL; row_mask uint8 [M] or NULL (masked rows are written as zeros); Y bf16 or
  * fp32 (y_dtype). */
 int case_gemm_rows_tc(const void* X, const void* Wp, const float* bias, long long M, int N, int K, int act,

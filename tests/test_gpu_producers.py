@@ -73,10 +73,12 @@ def test_enc_attention_vs_torch(C, L_, nseq):
 @pytest.mark.parametrize('M,N,K,act,res,mask,out32', [(300, 256, 256, 0, None, False, False), (1000, 768, 256, 0, None, False, False),
                                                       (515, 256, 256, 1, 'f32', False, True), (260, 3840, 1280, 0, None, False, False),
                                                       (129, 1280, 1280, 0, 'bf16', False, False), (700, 256, 1280, 2, None, True, True),
-                                                      (128, 256, 256, 2, 'f32', True, True)])
+                                                      (128, 256, 256, 2, 'f32', True, True), (20000, 256, 256, 0, 'bf16', True, False),
+                                                      (200, 256, 64, 0, None, False, True), (333, 512, 192, 1, 'f32', False, False)])
 def test_gemm_rows_tc_vs_torch(M, N, K, act, res, mask, out32):
     """case_gemm_rows_tc (tcgen05 / TMEM, bias + activation + residual + row mask epilogue) against torch fp32 on the same
-    bf16-rounded operands: partial last row tile, 1 and 5 K blocks, 2 .. 30 column blocks."""
+    bf16-rounded operands: partial last row tile, 1 .. 20 K stages (shorter than,
+    equal to and longer than the four-stage ring), 1 .. 15 column chunks, more row tiles than CTAs (persistent loop)."""
     from case_rg_b200 import _lib as L
     from case_rg_b200.producers import _Linear
     g = torch.Generator().manual_seed(M + N + K)
