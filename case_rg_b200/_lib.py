@@ -138,7 +138,7 @@ _PROTOS = {
     'case_enc_embed': [vp, vp, vp, C.c_longlong, i32, C.c_float, vp, vp],
     'case_ln_rows_wide': [vp, vp, i32, vp, vp, vp, vp, C.c_longlong, i32, vp],
     'case_enc_attention': [vp, vp, i32, i32, i32, i32, vp, vp],
-    'case_interaction': [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp],
+    'case_interaction': [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp],
     'case_rows_dot': [vp, vp, vp, C.c_longlong, C.c_longlong, vp, vp],
     'case_prior_answer': [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp],
     'case_gemm_rows_tc': [vp, vp, vp, C.c_longlong, i32, i32, i32, vp, i32, vp, vp, i32, vp],

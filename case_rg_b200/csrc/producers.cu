@@ -279,251 +279,297 @@ __global__ __launch_bounds__(128) void enc_attention_kernel(const bf16* __restri
 //   A1 = A E_q, B1 = B^T E_p, A2 = A B1, B2 = B^T A1                                     (:51-55)
 //   G_q_p[i] = [E_p, A1, A2, E_p*A1, E_p*A2] (bf16, zero for PAD rows)                   (:68, 74)
 //   G_p_q[j] = [E_q, B1, B2, E_q*B1, E_q*B2] (fp32 per passage, zero for PAD columns; max over passages follows)
-// Row-local products (A1, A2) are computed by the warp that owns row i; the reductions over i (B1, B2) by the warp that
-// owns the column: warp w owns columns w, w + 8, ... and walks all rows with its 8-wide slice of the hidden dimension
-// per lane.  A1 goes through a global scratch (fp32 [B*NP*Lp][H]) between the two.
+// All five products run on mma.sync.m16n8k16 (bf16 operands, fp32 accumulation) over passage tiles of 64 rows; the score
+// matrix is never stored - its 64 x 64 tile is recomputed from the operands where it is needed, directly in the fragment
+// layout of the product that consumes it (U for the row softmax A, U^T for the column softmax B^T):
+//   pass 1  B1: FlashAttention over the passage rows with the query positions as "queries" (online column max / sum,
+//           rescaled accumulator); leaves the final column statistics for pass 2
+//   pass 2  per tile: A (row softmax, complete within the tile's 64 columns) -> A1 = A E_q and A2 = A B1 -> the tile's
+//           G_q_p rows; B^T from the final column statistics -> B2 += B^T A1
+// Warp w: rows 16 (w & 3) .. + 15 of the 64-row operand, hidden dimensions 128 (w >> 2) .. + 127 of the products.
 constexpr int IT_LQ = 64;                           // largest Lq
-constexpr int IT_EQLD = H + 8;                      // bf16 row stride of E_q / B1 in shared memory: 16-byte aligned rows, and
-                                                    // lane j reading 16 bytes of row j is conflict-free (132 words: 8 lanes, 8 bank groups)
-__global__ __launch_bounds__(256) void interaction_kernel(const float* __restrict__ Eq, const float* __restrict__ Ep,
-                                                          const uint8_t* __restrict__ qmask, const uint8_t* __restrict__ pmask,
-                                                          const float* __restrict__ w, int NP, int Lq, int Lp,
-                                                          float* __restrict__ A1s, float* __restrict__ Gq,
-                                                          bf16* __restrict__ Gp) {
+constexpr int IT_LD = H + 8;                        // bf16 row stride in shared memory (528 bytes: conflict-free ldmatrix)
+constexpr int IT_BUF = IT_LQ * IT_LD;               // elements of one [64][IT_LD] operand buffer
+constexpr int IT_SMEM = 6 * IT_BUF * 2 + 4 * 64 * 4 + 128;
+
+__global__ __launch_bounds__(256, 1) void interaction_kernel(const float* __restrict__ Eq, const float* __restrict__ Ep,
+                                                             const uint8_t* __restrict__ qmask, const uint8_t* __restrict__ pmask,
+                                                             const float* __restrict__ w, int NP, int Lq, int Lp,
+                                                             float* __restrict__ Gq, bf16* __restrict__ Gp) {
   extern __shared__ __align__(128) unsigned char sm[];
-  bf16* eq = reinterpret_cast<bf16*>(sm);                               // [Lq][IT_EQLD]
-  bf16* b1 = eq + IT_LQ * IT_EQLD;                                      // [Lq][IT_EQLD]
-  float* U = reinterpret_cast<float*>(b1 + IT_LQ * IT_EQLD);            // [Lp][Lq + 1]
-  const int UL = Lq + 1;
-  float* rowb = U + (((size_t)Lp * UL + 3) & ~(size_t)3);               // [8][H]  w3 * E_p[i] of the warp's current row (16-byte aligned)
-  float* aj = rowb + 8 * H;                                             // [IT_LQ]
-  float* cmax = aj + IT_LQ;                                             // [IT_LQ]
-  float* csum = cmax + IT_LQ;                                           // [IT_LQ]
-  float* rmax = csum + IT_LQ;                                           // [Lp]
-  float* rsum = rmax + Lp;                                              // [Lp]
-  int* vidx = reinterpret_cast<int*>(rsum + Lp);                        // [Lp] indices of the valid passage rows
-  int* nvalid = vidx + Lp;
+  bf16* EqS = reinterpret_cast<bf16*>(sm);          // E_q
+  bf16* EqW = EqS + IT_BUF;                         // E_q * w3
+  bf16* EpT = EqW + IT_BUF;                         // the current tile of E_p
+  bf16* B1S = EpT + IT_BUF;
+  bf16* A1T = B1S + IT_BUF;                         // A1 / A2 rows of the current tile
+  bf16* A2T = A1T + IT_BUF;
+  float* c1 = reinterpret_cast<float*>(A2T + IT_BUF);   // [64] w1 . E_q[j]
+  float* r2 = c1 + 64;                              // [64] w2 . E_p[i] of the tile
+  float* cmax = r2 + 64;                            // [64] column max / 1 / column sum (final, after pass 1)
+  float* cinv = cmax + 64;
+  uint8_t* qm = reinterpret_cast<uint8_t*>(cinv + 64);  // [64]
+  uint8_t* pmt = qm + 64;                           // [64] mask of the tile's rows
   pdl_wait();
-  const int s = blockIdx.x, b = s / NP;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float* Eqb = Eq + (size_t)b * Lq * H;
-  const float* Epb = Ep + (size_t)s * Lp * H;
-  const uint8_t* qm = qmask + (size_t)b * Lq;
-  const uint8_t* pm = pmask + (size_t)s * Lp;
-  // ---- P0: E_q -> shared (bf16), a_j = w1 . E_q[j]
-  for (int j = warp; j < Lq; j += 8) {
-    const float4 x0 = *reinterpret_cast<const float4*>(Eqb + (size_t)j * H + lane * 8);
-    const float4 x1 = *reinterpret_cast<const float4*>(Eqb + (size_t)j * H + lane * 8 + 4);
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + lane * 8)), w1 = __ldg(reinterpret_cast<const float4*>(w + lane * 8 + 4));
-    uint32_t* d = reinterpret_cast<uint32_t*>(eq + j * IT_EQLD + lane * 8);
-    d[0] = pk2(x0.x, x0.y); d[1] = pk2(x0.z, x0.w); d[2] = pk2(x1.x, x1.y); d[3] = pk2(x1.z, x1.w);
-    float a = x0.x * w0.x + x0.y * w0.y + x0.z * w0.z + x0.w * w0.w + x1.x * w1.x + x1.y * w1.y + x1.z * w1.z + x1.w * w1.w;
-    a = warp_sum(a);
-    if (lane == 0) aj[j] = a;
-  }
-  __syncthreads();
-  // ---- P1: U and the row statistics
-  for (int i = warp; i < Lp; i += 8) {
-    if (pm[i] == 0) {
-      for (int j = lane; j < Lq; j += 32) U[i * UL + j] = -INFINITY;
-      if (lane == 0) { rmax[i] = -INFINITY; rsum[i] = 0.f; }
-      continue;
+  const int pair = blockIdx.x, b = pair / NP;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+  const int mt = warp & 3, dh = warp >> 2;
+  const float* eqg = Eq + (size_t)b * Lq * H;
+  const float* epg = Ep + (size_t)pair * Lp * H;
+  const uint8_t* pmg = pmask + (size_t)pair * Lp;
+  auto pack8 = [](const float4& x0, const float4& x1) {
+    return make_uint4(pk2(x0.x, x0.y), pk2(x0.z, x0.w), pk2(x1.x, x1.y), pk2(x1.z, x1.w));
+  };
+  auto dot8 = [](const float4& x0, const float4& x1, const float4& w0, const float4& w1) {
+    return x0.x * w0.x + x0.y * w0.y + x0.z * w0.z + x0.w * w0.w + x1.x * w1.x + x1.y * w1.y + x1.z * w1.z + x1.w * w1.w;
+  };
+  // ---- E_q -> bf16 (plain and scaled by w3), c1[j] = w1 . E_q[j]; rows >= Lq are zero
+  {
+    const float4 wa0 = __ldg(reinterpret_cast<const float4*>(w + lane * 8)), wa1 = __ldg(reinterpret_cast<const float4*>(w + lane * 8 + 4));
+    const float4 wc0 = __ldg(reinterpret_cast<const float4*>(w + 2 * H + lane * 8)),
+                 wc1 = __ldg(reinterpret_cast<const float4*>(w + 2 * H + lane * 8 + 4));
+    for (int j = warp; j < IT_LQ; j += 8) {
+      float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+      if (j < Lq) {
+        x0 = *reinterpret_cast<const float4*>(eqg + (size_t)j * H + lane * 8);
+        x1 = *reinterpret_cast<const float4*>(eqg + (size_t)j * H + lane * 8 + 4);
+      }
+      const float d = warp_sum(dot8(x0, x1, wa0, wa1));
+      *reinterpret_cast<uint4*>(EqS + j * IT_LD + lane * 8) = pack8(x0, x1);
+      const float4 y0 = make_float4(x0.x * wc0.x, x0.y * wc0.y, x0.z * wc0.z, x0.w * wc0.w),
+                   y1 = make_float4(x1.x * wc1.x, x1.y * wc1.y, x1.z * wc1.z, x1.w * wc1.w);
+      *reinterpret_cast<uint4*>(EqW + j * IT_LD + lane * 8) = pack8(y0, y1);
+      if (lane == 0) { c1[j] = d; qm[j] = j < Lq ? qmask[(size_t)b * Lq + j] : 0; }
     }
-    const float4 x0 = *reinterpret_cast<const float4*>(Epb + (size_t)i * H + lane * 8);
-    const float4 x1 = *reinterpret_cast<const float4*>(Epb + (size_t)i * H + lane * 8 + 4);
-    const float4 u0 = __ldg(reinterpret_cast<const float4*>(w + H + lane * 8)), u1 = __ldg(reinterpret_cast<const float4*>(w + H + lane * 8 + 4));
-    const float4 t0 = __ldg(reinterpret_cast<const float4*>(w + 2 * H + lane * 8)), t1 = __ldg(reinterpret_cast<const float4*>(w + 2 * H + lane * 8 + 4));
-    float bi = x0.x * u0.x + x0.y * u0.y + x0.z * u0.z + x0.w * u0.w + x1.x * u1.x + x1.y * u1.y + x1.z * u1.z + x1.w * u1.w;
-    bi = warp_sum(bi);
-    float* rb = rowb + warp * H + lane * 8;
-    *reinterpret_cast<float4*>(rb) = make_float4(x0.x * t0.x, x0.y * t0.y, x0.z * t0.z, x0.w * t0.w);
-    *reinterpret_cast<float4*>(rb + 4) = make_float4(x1.x * t1.x, x1.y * t1.y, x1.z * t1.z, x1.w * t1.w);
-    __syncwarp();
-    float uv[2];
-    float mx = -INFINITY;
+  }
+  const float4 wb0 = __ldg(reinterpret_cast<const float4*>(w + H + lane * 8)), wb1 = __ldg(reinterpret_cast<const float4*>(w + H + lane * 8 + 4));
+  // tile t of E_p -> bf16 rows, r2[i] = w2 . E_p[i], row masks (8 rows per warp, all 16 loads of a lane in flight)
+  auto load_tile = [&](int t) {
+    float4 x0[8], x1[8];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int j = lane + 32 * c;
-      uv[c] = -INFINITY;
-      if (j < Lq && qm[j] != 0) {
-        const uint4* er = reinterpret_cast<const uint4*>(eq + j * IT_EQLD);
-        const float4* rr = reinterpret_cast<const float4*>(rowb + warp * H);
-        float d0 = 0.f, d1 = 0.f;
+    for (int k = 0; k < 8; ++k) {
+      const int i = t * 64 + warp * 8 + k;
+      x0[k] = make_float4(0.f, 0.f, 0.f, 0.f); x1[k] = x0[k];
+      if (i < Lp) {
+        x0[k] = *reinterpret_cast<const float4*>(epg + (size_t)i * H + lane * 8);
+        x1[k] = *reinterpret_cast<const float4*>(epg + (size_t)i * H + lane * 8 + 4);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r = warp * 8 + k, i = t * 64 + r;
+      const float d = warp_sum(dot8(x0[k], x1[k], wb0, wb1));
+      *reinterpret_cast<uint4*>(EpT + r * IT_LD + lane * 8) = pack8(x0[k], x1[k]);
+      if (lane == 0) { r2[r] = d; pmt[r] = i < Lp ? pmg[i] : 0; }
+    }
+  };
+  // 64 x 64 score tile in accumulator layout: rows (16 mt + g, + 8) of the operand `rows`, columns 8 nt + 2 tq (+ 1) = rows
+  // of the operand `cols`; + the two rank-1 terms; -inf outside the mask
+  auto score_tile = [&](const bf16* rows, const bf16* cols, const float* rterm, const float* cterm, const uint8_t* rmask,
+                        const uint8_t* cmask, float (&s)[8][4]) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
 #pragma unroll 4
-        for (int k = 0; k < H / 8; ++k) {
-          const uint4 e = er[k];
-          const float4 r0 = rr[2 * k], r1 = rr[2 * k + 1];
-          d0 = fmaf(r0.x, bf_lo(e.x), d0); d1 = fmaf(r0.y, bf_hi(e.x), d1);
-          d0 = fmaf(r0.z, bf_lo(e.y), d0); d1 = fmaf(r0.w, bf_hi(e.y), d1);
-          d0 = fmaf(r1.x, bf_lo(e.z), d0); d1 = fmaf(r1.y, bf_hi(e.z), d1);
-          d0 = fmaf(r1.z, bf_lo(e.w), d0); d1 = fmaf(r1.w, bf_hi(e.w), d1);
-        }
-        uv[c] = aj[j] + bi + d0 + d1;
+    for (int ks = 0; ks < H / 16; ++ks) {
+      uint32_t af[4];
+      pa_ldsm4(af, smem_u32(rows + (16 * mt + (lane & 15)) * IT_LD + ks * 16 + (lane >> 4) * 8));
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t bb[4];
+        pa_ldsm4(bb, smem_u32(cols + (16 * np + (lane & 7) + ((lane >> 4) << 3)) * IT_LD + ks * 16 + ((lane >> 3) & 1) * 8));
+        pa_mma(s[2 * np], af[0], af[1], af[2], af[3], bb[0], bb[1]);
+        pa_mma(s[2 * np + 1], af[0], af[1], af[2], af[3], bb[2], bb[3]);
       }
-      if (j < Lq) U[i * UL + j] = uv[c];
-      mx = fmaxf(mx, uv[c]);
     }
-    mx = warp_max(mx);
-    float se = 0.f;
+    const int ra = 16 * mt + g, rb = ra + 8;
+    const float ta = rterm[ra], tb = rterm[rb];
+    const bool oka = rmask[ra] != 0, okb = rmask[rb] != 0;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) se += (uv[c] == -INFINITY) ? 0.f : __expf(uv[c] - mx);
-    se = warp_sum(se);
-    if (lane == 0) { rmax[i] = mx; rsum[i] = se; }
-    __syncwarp();
-  }
-  __syncthreads();
-  // ---- P2: column statistics; list of the valid rows (warp 7: ballot compaction, order kept)
-  if (warp == 7) {
-    int n = 0;
-    for (int i0 = 0; i0 < Lp; i0 += 32) {
-      const int i = i0 + lane;
-      const bool ok = i < Lp && pm[i] != 0;
-      const unsigned bal = __ballot_sync(0xffffffffu, ok);
-      if (ok) vidx[n + __popc(bal & ((1u << lane) - 1u))] = i;
-      n += __popc(bal);
-    }
-    if (lane == 0) *nvalid = n;
-  }
-  if (tid < Lq) {
-    float mx = -INFINITY;
-    for (int i = 0; i < Lp; ++i) mx = fmaxf(mx, U[i * UL + tid]);
-    float se = 0.f;
-    if (mx > -INFINITY)
-      for (int i = 0; i < Lp; ++i) { const float u = U[i * UL + tid]; se += (u == -INFINITY) ? 0.f : __expf(u - mx); }
-    cmax[tid] = mx; csum[tid] = se;
-  }
-  __syncthreads();
-  // row-local product with a [Lq][H] bf16 operand in shared memory: acc[8 dims of the lane] = sum_j A[i][j] * X[j]
-  auto row_prod = [&](int i, const bf16* X, float (&acc)[8]) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    const float mxr = rmax[i], inv = rsum[i] > 0.f ? 1.f / rsum[i] : 0.f;
-    for (int j = 0; j < Lq; ++j) {
-      const float u = U[i * UL + j];
-      if (u == -INFINITY) continue;                                     // uniform over the warp
-      const float a = __expf(u - mxr) * inv;
-      const uint4 x = *reinterpret_cast<const uint4*>(X + j * IT_EQLD + lane * 8);
-      acc[0] = fmaf(a, bf_lo(x.x), acc[0]); acc[1] = fmaf(a, bf_hi(x.x), acc[1]);
-      acc[2] = fmaf(a, bf_lo(x.y), acc[2]); acc[3] = fmaf(a, bf_hi(x.y), acc[3]);
-      acc[4] = fmaf(a, bf_lo(x.z), acc[4]); acc[5] = fmaf(a, bf_hi(x.z), acc[5]);
-      acc[6] = fmaf(a, bf_lo(x.w), acc[6]); acc[7] = fmaf(a, bf_hi(x.w), acc[7]);
+    for (int nt = 0; nt < 8; ++nt) {
+      const int ca = 8 * nt + 2 * tq;
+      const float u0 = cterm[ca], u1 = cterm[ca + 1];
+      const bool k0 = cmask[ca] != 0, k1 = cmask[ca + 1] != 0;
+      s[nt][0] = (oka && k0) ? s[nt][0] + ta + u0 : -INFINITY; s[nt][1] = (oka && k1) ? s[nt][1] + ta + u1 : -INFINITY;
+      s[nt][2] = (okb && k0) ? s[nt][2] + tb + u0 : -INFINITY; s[nt][3] = (okb && k1) ? s[nt][3] + tb + u1 : -INFINITY;
     }
   };
-  // reduction over the rows for the warp's columns: acc[c][8 dims] = sum_i B[i][j_c] * X[i]  (X fp32 rows in global memory).
-  // Only the valid rows are walked (vidx: their indices, built once), four at a time with all eight 16-byte loads of the
-  // batch in flight together - the loop is bound by the latency of these loads otherwise.
-  auto col_prod = [&](const float* X, float (&acc)[8][8]) {
-    float cm[8], ci[8];
+  // acc[16][4] (rows 16 mt + g / + 8, dims 128 dh + 8 nd + 2 tq / + 1) += P (A fragments over the 64 k rows) . X[k][dims]
+  auto prod_tile = [&](const uint32_t (&pf)[4][4], const bf16* X, float (&acc)[16][4]) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int j = warp + 8 * c;
-      cm[c] = j < Lq ? cmax[j] : 0.f;
-      ci[c] = (j < Lq && csum[j] > 0.f) ? 1.f / csum[j] : 0.f;
+    for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[c][k] = 0.f;
-    }
-    const int nv = *nvalid;
-    for (int i0 = 0; i0 < nv; i0 += 4) {
-      int ii[4];
-      float4 x0[4], x1[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        ii[u] = vidx[min(i0 + u, nv - 1)];
-        x0[u] = *reinterpret_cast<const float4*>(X + (size_t)ii[u] * H + lane * 8);
-        x1[u] = *reinterpret_cast<const float4*>(X + (size_t)ii[u] * H + lane * 8 + 4);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (i0 + u >= nv) break;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int j = warp + 8 * c;
-          if (j >= Lq) break;
-          const float uu = U[ii[u] * UL + j];
-          const float bw = (uu == -INFINITY) ? 0.f : __expf(uu - cm[c]) * ci[c];
-          acc[c][0] = fmaf(bw, x0[u].x, acc[c][0]); acc[c][1] = fmaf(bw, x0[u].y, acc[c][1]);
-          acc[c][2] = fmaf(bw, x0[u].z, acc[c][2]); acc[c][3] = fmaf(bw, x0[u].w, acc[c][3]);
-          acc[c][4] = fmaf(bw, x1[u].x, acc[c][4]); acc[c][5] = fmaf(bw, x1[u].y, acc[c][5]);
-          acc[c][6] = fmaf(bw, x1[u].z, acc[c][6]); acc[c][7] = fmaf(bw, x1[u].w, acc[c][7]);
-        }
+      for (int dp = 0; dp < 8; ++dp) {
+        uint32_t bb[4];
+        pa_ldsm4t(bb, smem_u32(X + (16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8) * IT_LD + 128 * dh + 16 * dp + (lane >> 4) * 8));
+        pa_mma(acc[2 * dp], pf[kk][0], pf[kk][1], pf[kk][2], pf[kk][3], bb[0], bb[1]);
+        pa_mma(acc[2 * dp + 1], pf[kk][0], pf[kk][1], pf[kk][2], pf[kk][3], bb[2], bb[3]);
       }
     }
   };
-  float* A1b = A1s + (size_t)s * Lp * H;
-  float* Gqb = Gq + (size_t)s * Lq * 5 * H;
-  // ---- P3a: A1 = A E_q (row-local) -> scratch
-  for (int i = warp; i < Lp; i += 8) {
-    if (pm[i] == 0) continue;
-    float acc[8];
-    row_prod(i, eq, acc);
-    *reinterpret_cast<float4*>(A1b + (size_t)i * H + lane * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    *reinterpret_cast<float4*>(A1b + (size_t)i * H + lane * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-  }
-  // ---- P3b: B1 = B^T E_p for the warp's columns -> shared (bf16) + G_p_q slot 1
-  {
-    float acc[8][8];
-    col_prod(Epb, acc);
+  auto quad_max = [](float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  };
+  auto quad_sum = [](float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+  };
+  const int ntile = (Lp + 63) / 64;
+  const int ja = 16 * mt + g, jb = ja + 8;           // the warp's query positions in the column-side products
+  // G_p_q segments seg0 / seg1 of rows ja, jb: value and E_q * value (zeros for PAD columns)
+  auto write_gq = [&](const float (&acc)[16][4], float sa, float sb, int seg0, int seg1) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int j = warp + 8 * c;
-      if (j >= Lq) break;
-      uint32_t* d = reinterpret_cast<uint32_t*>(b1 + j * IT_EQLD + lane * 8);
-      d[0] = pk2(acc[c][0], acc[c][1]); d[1] = pk2(acc[c][2], acc[c][3]); d[2] = pk2(acc[c][4], acc[c][5]); d[3] = pk2(acc[c][6], acc[c][7]);
-      float* o = Gqb + (size_t)j * 5 * H + H + lane * 8;
-      *reinterpret_cast<float4*>(o) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
-      *reinterpret_cast<float4*>(o + 4) = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
-    }
-  }
-  __syncthreads();                 // A1 (global, written by this CTA) and B1 (shared) are complete
-  // ---- P4a: A2 = A B1 (row-local) and the passage-side output rows
-  for (int i = warp; i < Lp; i += 8) {
-    bf16* gp = Gp + ((size_t)s * Lp + i) * 5 * H;
-    if (pm[i] == 0) {
-      for (int k = lane; k < 5 * H / 8; k += 32) reinterpret_cast<uint4*>(gp)[k] = make_uint4(0, 0, 0, 0);
-      continue;
-    }
-    float a2[8];
-    row_prod(i, b1, a2);
-    const float4 e0 = *reinterpret_cast<const float4*>(Epb + (size_t)i * H + lane * 8);
-    const float4 e1 = *reinterpret_cast<const float4*>(Epb + (size_t)i * H + lane * 8 + 4);
-    const float4 p0 = *reinterpret_cast<const float4*>(A1b + (size_t)i * H + lane * 8);
-    const float4 p1 = *reinterpret_cast<const float4*>(A1b + (size_t)i * H + lane * 8 + 4);
-    const float e[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-    const float a1[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-    auto st = [&](int slot, const float (&v)[8]) {
-      *reinterpret_cast<uint4*>(gp + slot * H + lane * 8) = make_uint4(pk2(v[0], v[1]), pk2(v[2], v[3]), pk2(v[4], v[5]), pk2(v[6], v[7]));
-    };
-    float m1[8], m2[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { m1[k] = e[k] * a1[k]; m2[k] = e[k] * a2[k]; }
-    st(0, e); st(1, a1); st(2, a2); st(3, m1); st(4, m2);
-  }
-  // ---- P4b: B2 = B^T A1 for the warp's columns and the query-side output rows (fp32, per passage)
-  {
-    float acc[8][8];
-    col_prod(A1b, acc);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int j = warp + 8 * c;
-      if (j >= Lq) break;
-      float* o = Gqb + (size_t)j * 5 * H;
-      const float4 q0 = *reinterpret_cast<const float4*>(Eqb + (size_t)j * H + lane * 8);
-      const float4 q1 = *reinterpret_cast<const float4*>(Eqb + (size_t)j * H + lane * 8 + 4);
-      const float4 c0 = *reinterpret_cast<const float4*>(o + H + lane * 8), c1 = *reinterpret_cast<const float4*>(o + H + lane * 8 + 4);
+    for (int half = 0; half < 2; ++half) {
+      const int j = half ? jb : ja;
+      if (j >= Lq) continue;
       const bool ok = qm[j] != 0;
-      const float e[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-      const float bb1[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-      auto st = [&](int slot, const float (&v)[8]) {
-        float* d = o + slot * H + lane * 8;
-        *reinterpret_cast<float4*>(d) = ok ? make_float4(v[0], v[1], v[2], v[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(d + 4) = ok ? make_float4(v[4], v[5], v[6], v[7]) : make_float4(0.f, 0.f, 0.f, 0.f);
-      };
-      float m1[8], m2[8];
+      const float sc = half ? sb : sa;
+      float* o = Gq + ((size_t)pair * Lq + j) * (5 * H);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { m1[k] = e[k] * bb1[k]; m2[k] = e[k] * acc[c][k]; }
-      st(0, e); st(1, bb1); st(2, acc[c]); st(3, m1); st(4, m2);
+      for (int nd = 0; nd < 16; ++nd) {
+        const int col = 128 * dh + 8 * nd + 2 * tq;
+        const float2 e = *reinterpret_cast<const float2*>(eqg + (size_t)j * H + col);
+        const float v0 = ok ? acc[nd][2 * half] * sc : 0.f, v1 = ok ? acc[nd][2 * half + 1] * sc : 0.f;
+        *reinterpret_cast<float2*>(o + seg0 * H + col) = make_float2(v0, v1);
+        *reinterpret_cast<float2*>(o + seg1 * H + col) = make_float2(ok ? e.x * v0 : 0.f, ok ? e.y * v1 : 0.f);
+        if (seg0 == 1) *reinterpret_cast<float2*>(o + col) = ok ? e : make_float2(0.f, 0.f);
+      }
+    }
+  };
+
+  // =============================== pass 1: B1 = B^T E_p with an online column softmax
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  {
+    float b1[16][4];
+#pragma unroll
+    for (int nd = 0; nd < 16; ++nd) { b1[nd][0] = b1[nd][1] = b1[nd][2] = b1[nd][3] = 0.f; }
+    for (int t = 0; t < ntile; ++t) {
+      __syncthreads();                               // the previous tile is consumed (t = 0: nothing yet)
+      load_tile(t);
+      __syncthreads();
+      float s[8][4];
+      score_tile(EqW, EpT, c1, r2, qm, pmt, s);      // U^T: rows j, columns i
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      mx0 = quad_max(mx0); mx1 = quad_max(mx1);
+      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+      const float c0 = (m0 == -INFINITY) ? 0.f : fexp(m0 - mn0), cc1 = (m1 == -INFINITY) ? 0.f : fexp(m1 - mn1);
+      const float e0 = (mn0 == -INFINITY) ? 0.f : mn0, e1 = (mn1 == -INFINITY) ? 0.f : mn1;
+      float rs0 = 0.f, rs1 = 0.f;
+      uint32_t pf[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float p0 = fexp(s[nt][0] - e0), p1 = fexp(s[nt][1] - e0), p2 = fexp(s[nt][2] - e1), p3 = fexp(s[nt][3] - e1);
+        rs0 += p0 + p1; rs1 += p2 + p3;
+        pf[nt >> 1][(nt & 1) * 2] = pk2(p0, p1);
+        pf[nt >> 1][(nt & 1) * 2 + 1] = pk2(p2, p3);
+      }
+      rs0 = quad_sum(rs0); rs1 = quad_sum(rs1);
+      l0 = fmaf(l0, c0, rs0); l1 = fmaf(l1, cc1, rs1);
+      m0 = mn0; m1 = mn1;
+#pragma unroll
+      for (int nd = 0; nd < 16; ++nd) { b1[nd][0] *= c0; b1[nd][1] *= c0; b1[nd][2] *= cc1; b1[nd][3] *= cc1; }
+      prod_tile(pf, EpT, b1);
+    }
+    const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+#pragma unroll
+    for (int nd = 0; nd < 16; ++nd) {
+      const int col = 128 * dh + 8 * nd + 2 * tq;
+      *reinterpret_cast<uint32_t*>(B1S + ja * IT_LD + col) = pk2(b1[nd][0] * i0, b1[nd][1] * i0);
+      *reinterpret_cast<uint32_t*>(B1S + jb * IT_LD + col) = pk2(b1[nd][2] * i1, b1[nd][3] * i1);
+    }
+    if (dh == 0 && tq == 0) { cmax[ja] = m0; cinv[ja] = i0; cmax[jb] = m1; cinv[jb] = i1; }
+    write_gq(b1, i0, i1, 1, 3);
+  }
+
+  // =============================== pass 2: A1, A2 and the G_q_p rows per tile; B2 = B^T A1
+  float b2[16][4];
+#pragma unroll
+  for (int nd = 0; nd < 16; ++nd) { b2[nd][0] = b2[nd][1] = b2[nd][2] = b2[nd][3] = 0.f; }
+  const float e0 = (m0 == -INFINITY) ? 0.f : m0, e1 = (m1 == -INFINITY) ? 0.f : m1;
+  const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+  for (int t = 0; t < ntile; ++t) {
+    __syncthreads();                                 // the previous tile's buffers are consumed; B1S is complete
+    load_tile(t);
+    __syncthreads();
+    {
+      float s[8][4];
+      score_tile(EpT, EqW, r2, c1, pmt, qm, s);      // U: rows i, columns j (the whole row: Lq <= 64)
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      mx0 = quad_max(mx0); mx1 = quad_max(mx1);
+      const float f0 = (mx0 == -INFINITY) ? 0.f : mx0, f1 = (mx1 == -INFINITY) ? 0.f : mx1;
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = fexp(s[nt][0] - f0); s[nt][1] = fexp(s[nt][1] - f0); s[nt][2] = fexp(s[nt][2] - f1); s[nt][3] = fexp(s[nt][3] - f1);
+        rs0 += s[nt][0] + s[nt][1]; rs1 += s[nt][2] + s[nt][3];
+      }
+      rs0 = quad_sum(rs0); rs1 = quad_sum(rs1);
+      const float n0 = rs0 > 0.f ? 1.f / rs0 : 0.f, n1 = rs1 > 0.f ? 1.f / rs1 : 0.f;
+      uint32_t pf[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        pf[nt >> 1][(nt & 1) * 2] = pk2(s[nt][0] * n0, s[nt][1] * n0);
+        pf[nt >> 1][(nt & 1) * 2 + 1] = pk2(s[nt][2] * n1, s[nt][3] * n1);
+      }
+      const int ra = 16 * mt + g, rb = ra + 8;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {      // A1 = A E_q, A2 = A B1
+        float a[16][4];
+#pragma unroll
+        for (int nd = 0; nd < 16; ++nd) { a[nd][0] = a[nd][1] = a[nd][2] = a[nd][3] = 0.f; }
+        prod_tile(pf, which ? B1S : EqS, a);
+        bf16* dst = which ? A2T : A1T;
+#pragma unroll
+        for (int nd = 0; nd < 16; ++nd) {
+          const int col = 128 * dh + 8 * nd + 2 * tq;
+          *reinterpret_cast<uint32_t*>(dst + ra * IT_LD + col) = pk2(a[nd][0], a[nd][1]);
+          *reinterpret_cast<uint32_t*>(dst + rb * IT_LD + col) = pk2(a[nd][2], a[nd][3]);
+        }
+      }
+    }
+    __syncthreads();                                 // A1T / A2T complete
+    {
+      float s[8][4];
+      score_tile(EqW, EpT, c1, r2, qm, pmt, s);      // U^T again, now against the final column statistics
+      uint32_t pf[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        pf[nt >> 1][(nt & 1) * 2] = pk2(fexp(s[nt][0] - e0) * i0, fexp(s[nt][1] - e0) * i0);
+        pf[nt >> 1][(nt & 1) * 2 + 1] = pk2(fexp(s[nt][2] - e1) * i1, fexp(s[nt][3] - e1) * i1);
+      }
+      prod_tile(pf, A1T, b2);
+    }
+    // the tile's G_q_p rows: [E_p, A1, A2, E_p * A1, E_p * A2], 16 bytes per lane and segment
+#pragma unroll 2
+    for (int k = 0; k < 8; ++k) {
+      const int r = warp * 8 + k, i = t * 64 + r;
+      if (i >= Lp) break;
+      uint4* o = reinterpret_cast<uint4*>(Gp + ((size_t)pair * Lp + i) * (5 * H) + lane * 8);
+      if (pmt[r] == 0) {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int sgi = 0; sgi < 5; ++sgi) o[sgi * (H / 8)] = z;
+        continue;
+      }
+      const uint4 e = *reinterpret_cast<const uint4*>(EpT + r * IT_LD + lane * 8);
+      const uint4 x1 = *reinterpret_cast<const uint4*>(A1T + r * IT_LD + lane * 8);
+      const uint4 x2 = *reinterpret_cast<const uint4*>(A2T + r * IT_LD + lane * 8);
+      auto mul2 = [](uint32_t p, uint32_t q) { return pk2(bf_lo(p) * bf_lo(q), bf_hi(p) * bf_hi(q)); };
+      o[0] = e; o[H / 8] = x1; o[2 * (H / 8)] = x2;
+      o[3 * (H / 8)] = make_uint4(mul2(e.x, x1.x), mul2(e.y, x1.y), mul2(e.z, x1.z), mul2(e.w, x1.w));
+      o[4 * (H / 8)] = make_uint4(mul2(e.x, x2.x), mul2(e.y, x2.y), mul2(e.z, x2.z), mul2(e.w, x2.w));
     }
   }
+  write_gq(b2, 1.f, 1.f, 2, 4);
 }
 
 // G_p_q[b][j][c] = max over the NP passages of Gq[b][p][j][c]   (Interaction.py:73-74) -> bf16 rows
@@ -644,19 +690,18 @@ extern "C" int case_enc_attention(const void* qkv, const uint8_t* kmask, int nse
 }
 
 extern "C" size_t case_interaction_smem_bytes(int Lq, int Lp) {
-  return (size_t)2 * IT_LQ * IT_EQLD * 2 + ((((size_t)Lp * (Lq + 1) + 3) & ~(size_t)3) + 8 * H + 3 * IT_LQ + 3 * (size_t)Lp + 4) * 4;
+  (void)Lq; (void)Lp;                              // six 64-row operand buffers, whatever the passage length
+  return IT_SMEM;
 }
 
 extern "C" int case_interaction(const float* Eq, const float* Ep, const uint8_t* qmask, const uint8_t* pmask, const float* w,
-                                int B, int NP, int Lq, int Lp, float* A1_scratch, float* Gq_scratch, void* Gq_out, void* Gp_out,
+                                int B, int NP, int Lq, int Lp, float* Gq_scratch, void* Gq_out, void* Gp_out,
                                 case_stream_t stream) {
-  CB_REQUIRE(Eq && Ep && qmask && pmask && w && A1_scratch && Gq_scratch && Gq_out && Gp_out, "case_interaction: null pointer");
+  CB_REQUIRE(Eq && Ep && qmask && pmask && w && Gq_scratch && Gq_out && Gp_out, "case_interaction: null pointer");
   CB_REQUIRE(B > 0 && NP > 0 && Lq >= 1 && Lq <= IT_LQ && Lp >= 1, "case_interaction: Lq must be 1..64");
-  const size_t smem = case_interaction_smem_bytes(Lq, Lp);
-  CB_REQUIRE(smem <= 227 * 1024, "case_interaction: passage too long for the shared-memory score matrix");
   cudaStream_t st = (cudaStream_t)stream;
-  ensure_smem<interaction_kernel>(227 * 1024);
-  launch_k(interaction_kernel, B * NP, 256, smem, st, Eq, Ep, qmask, pmask, w, NP, Lq, Lp, A1_scratch, Gq_scratch, (bf16*)Gp_out);
+  ensure_smem<interaction_kernel>(IT_SMEM);
+  launch_k(interaction_kernel, B * NP, 256, IT_SMEM, st, Eq, Ep, qmask, pmask, w, NP, Lq, Lp, Gq_scratch, (bf16*)Gp_out);
   int rc = check_launch("case_interaction");
   if (rc) return rc;
   const long long per = (long long)Lq * 5 * H, total = (long long)B * per;

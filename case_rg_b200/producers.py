@@ -152,12 +152,11 @@ class CaseProducers:
 
     def _interaction(self, w, Eq, Ep, qmask, pmask, B, NP, Lq, Lp):
         dev = self.device
-        A1 = torch.empty(B * NP * Lp, H, dtype=torch.float32, device=dev)
         Gq_t = torch.empty(B * NP * Lq, 5 * H, dtype=torch.float32, device=dev)
         Gq = torch.empty(B * Lq, 5 * H, dtype=torch.bfloat16, device=dev)
         Gp = torch.empty(B * NP * Lp, 5 * H, dtype=torch.bfloat16, device=dev)
         L.call('case_interaction', Eq.data_ptr(), Ep.data_ptr(), qmask.data_ptr(), pmask.data_ptr(), w.data_ptr(), B, NP, Lq, Lp,
-               A1.data_ptr(), Gq_t.data_ptr(), Gq.data_ptr(), Gp.data_ptr(), self._st())
+               Gq_t.data_ptr(), Gq.data_ptr(), Gp.data_ptr(), self._st())
         return Gq, Gp
 
     @torch.no_grad()

@@ -484,11 +484,11 @@ int case_enc_attention(const void* qkv, const uint8_t* kmask, int nseq, int L, i
 /* Interaction.forward (common/Interaction.py:15-76) for B queries x NP passages without its [B*NP][Lp][Lq][3H] tensor:
  * Eq fp32 [B][Lq][256] (one query sequence per query), Ep fp32 [B*NP][Lp][256], masks uint8, w fp32 [768] =
  * dual_att_linear.weight.  Outputs: Gp bf16 [B*NP*Lp][1280] (G_q_p, PAD rows zero) and Gq bf16 [B*Lq][1280] (G_p_q after
- * the max over the passages).  Scratch: A1 fp32 [B*NP*Lp][256], Gq_scratch fp32 [B*NP*Lq][1280].  Lq <= 64; the score
- * matrix [Lp][Lq] of a pair lives in shared memory (case_interaction_smem_bytes <= 227 KB). */
+ * the max over the passages).  Scratch: Gq_scratch fp32 [B*NP*Lq][1280].  Lq <= 64, any Lp: the five products run on
+ * mma.sync over passage tiles of 64 rows and the score matrix is never stored (case_interaction_smem_bytes: six 64-row
+ * bf16 operand buffers, 199 KB). */
 int case_interaction(const float* Eq, const float* Ep, const uint8_t* qmask, const uint8_t* pmask, const float* w, int B,
-                     int NP, int Lq, int Lp, float* A1_scratch, float* Gq_scratch, void* Gq_out, void* Gp_out,
-                     case_stream_t stream);
+                     int NP, int Lq, int Lp, float* Gq_scratch, void* Gq_out, void* Gp_out, case_stream_t stream);
 size_t case_interaction_smem_bytes(int Lq, int Lp);
 
 /* y[r] = w . x[r * row_stride] + b over fp32 rows of width 256 (the scorer Linear(H, 1): CaSE/Model.py:164, 203). */

@@ -113,16 +113,18 @@ def _pipeline_inputs(B=3, Lq=20, NP=4, Lp=50, V=900, seed=5):
     return sd, inp
 
 
-def test_interaction_vs_oracle():
+@pytest.mark.parametrize('Lq,Lp', [(20, 50), (33, 150), (64, 256), (7, 64)])
+def test_interaction_vs_oracle(Lq, Lp):
     """The Interaction kernel on fp32 encoder-like inputs against the oracle's Interaction (Interaction.py:15-76): both
-    5H-wide outputs, PAD rows / columns zero, the max over the passages; an all-PAD-but-two passage included."""
+    5H-wide outputs, PAD rows / columns zero, the max over the passages; an all-PAD-but-two passage included; one to four
+    passage tiles, a partial last tile, the longest query."""
     from case_rg_b200 import _lib as L
     from oracle.producers import interaction
-    B, NP, Lq, Lp = 3, 4, 20, 50
+    B, NP = 3, 4
     g = torch.Generator().manual_seed(9)
     Eq, Ep = torch.randn(B, 1, Lq, H, generator=g), torch.randn(B, NP, Lp, H, generator=g)
     w = torch.randn(1, 3 * H, generator=g) * 0.05
-    qm = torch.arange(Lq)[None, None, :] < torch.tensor([20, 13, 7])[:, None, None]
+    qm = torch.arange(Lq)[None, None, :] < torch.tensor([Lq, (2 * Lq) // 3, max(1, Lq // 3)])[:, None, None]
     pl = torch.randint(5, Lp + 1, (B, NP), generator=g)
     pl[1, 2] = 2
     pm = torch.arange(Lp)[None, None, :] < pl[:, :, None]
@@ -132,16 +134,15 @@ def test_interaction_vs_oracle():
     def d(t):
         keep.append(t.to(DEV).contiguous())
         return keep[-1]
-    A1 = torch.empty(B * NP * Lp, H, device=DEV)
     Gqt = torch.empty(B * NP * Lq, 5 * H, device=DEV)
     Gq = torch.empty(B * Lq, 5 * H, dtype=torch.bfloat16, device=DEV)
     Gp = torch.full((B * NP * Lp, 5 * H), float('nan'), dtype=torch.bfloat16, device=DEV)
     L.call('case_interaction', d(Eq).data_ptr(), d(Ep).data_ptr(), d(qm.reshape(-1).to(torch.uint8)).data_ptr(),
-           d(pm.reshape(-1).to(torch.uint8)).data_ptr(), d(w.reshape(-1)).data_ptr(), B, NP, Lq, Lp, A1.data_ptr(), Gqt.data_ptr(),
+           d(pm.reshape(-1).to(torch.uint8)).data_ptr(), d(w.reshape(-1)).data_ptr(), B, NP, Lq, Lp, Gqt.data_ptr(),
            Gq.data_ptr(), Gp.data_ptr(), _st())
     torch.cuda.synchronize()
     assert torch.isfinite(Gp.float()).all() and torch.isfinite(Gq.float()).all()
-    # E_q / B1 are held in bf16 in shared memory and the outputs are bf16
+    # all five products take bf16 operands (fp32 accumulation) and the outputs are bf16
     assert rel(Gp.view(B, NP, Lp, -1), want_p) < 1.5e-2, rel(Gp.view(B, NP, Lp, -1), want_p)
     assert rel(Gq.view(B, 1, Lq, -1), want_q) < 1.5e-2, rel(Gq.view(B, 1, Lq, -1), want_q)
     assert float(Gp.view(B, NP, Lp, -1)[~pm.to(DEV)].abs().max()) == 0.0
