@@ -364,19 +364,14 @@ class Workload:
         return outs[-1]
 
     def step_e2e(self, n=1):
-        """n passes through the public API from pinned host buffers: CaSE uses the streaming face (the copy of batch i+1
-        overlaps the decode of batch i), GTTP copies, searches and reads back batch by batch."""
+        """n passes through the public API from pinned host buffers: the streaming face (the copy of batch i+1 overlaps the
+        decode of batch i) for the beam configurations; the in-module greedy loop copies, searches and reads back batch
+        by batch."""
         torch = self.torch
         out = None
         for _ in range(n if self.strong else 1):
             reps = 1 if self.strong else n
-            if self.family == 'gttp':
-                outs = []
-                for _r in range(reps):
-                    for hb in self.host:
-                        d = {k: v.to(self.dev, non_blocking=True) for k, v in hb.items()}
-                        outs.append(self.search(d).cpu())
-            elif self.greedy:
+            if self.greedy:
                 outs = []
                 for _r in range(reps):
                     for hb in self.host:

@@ -123,12 +123,13 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
   //           [6,7] acc_full, [8,9] acc_free (8 epilogue warps)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + GR_NS * GR_STAGE + 192);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // persistent: this CTA owns the row tiles blockIdx.x, blockIdx.x + gridDim.x, ...; a work unit is (row tile, 256-column
-  // chunk), the stage ring and the two accumulators run on across units so the epilogue of one overlaps the next one's MMAs
+  // persistent: a work unit is (row tile, 256-column chunk); this CTA owns the units blockIdx.x, blockIdx.x + gridDim.x, ...
+  // of the chunk-minor unit list (neighbouring CTAs share a row tile and all of them share the few weight chunks in
+  // flight, so both operands are L2 hits); the stage ring and the two accumulators run on across units, so the epilogue
+  // of one overlaps the next one's MMAs
   const int KB = a.K / GR_KB, nchunk = a.N / GR_NC;
-  const int ntile = (int)((a.M + GR_M - 1) / GR_M);
-  const int mine = ((int)blockIdx.x < ntile) ? (ntile - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const int nunit = mine * nchunk;
+  const long long total = ((a.M + GR_M - 1) / GR_M) * nchunk;
+  const int nunit = (long long)blockIdx.x < total ? (int)((total - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
   const int nit = nunit * KB;                           // ring iterations
 
   if (tid == 0) {
@@ -161,8 +162,10 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
       const int g = it % GR_NS, use = it / GR_NS;
       const uint32_t s_a = s_base + g * GR_STAGE, s_w = s_a + GR_A_BYTES;
       const int u = it / KB, kb = it - u * KB;
-      const int mt = u / nchunk, c = u - mt * nchunk;
-      const long long m0 = ((long long)blockIdx.x + (long long)mt * gridDim.x) * GR_M;
+      const long long ug = (long long)blockIdx.x + (long long)u * gridDim.x;
+      const long long mt = ug / nchunk;
+      const int c = (int)(ug - mt * nchunk);
+      const long long m0 = mt * GR_M;
       if (use >= 1) gr_wait(BAR_FREE + 8 * g, (uint32_t)(use - 1) & 1u);        // the MMAs of this stage's previous use are done
       if (lane == 0) {
         const char* src = reinterpret_cast<const char*>(a.Wp) + ((size_t)kb * nchunk + c) * GR_W_BYTES + (size_t)w4 * (GR_W_BYTES / 4);
@@ -221,8 +224,10 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
     const int q = warp & 3, hh = (warp - 4) >> 2;
     unsigned char* stg = smem + GR_NS * GR_STAGE + 256 + (warp - 4) * GR_STG;      // this warp's staging block
     for (int u = 0; u < nunit; ++u) {
-      const int mt = u / nchunk, c = u - mt * nchunk;
-      const long long m = ((long long)blockIdx.x + (long long)mt * gridDim.x) * GR_M + q * 32 + lane;
+      const long long ug = (long long)blockIdx.x + (long long)u * gridDim.x;
+      const long long mt = ug / nchunk;
+      const int c = (int)(ug - mt * nchunk);
+      const long long m = mt * GR_M + q * 32 + lane;
       const bool rowok = m < a.M;
       const bool keep = rowok && (a.row_mask == nullptr || a.row_mask[m] != 0);
       const int tb = u & 1;
@@ -354,7 +359,7 @@ extern "C" int case_gemm_rows_tc(const void* X, const void* Wp, const float* bia
   a.X = (const bf16*)X; a.Wp = (const bf16*)Wp; a.bias = bias; a.M = M; a.N = N; a.K = K; a.act = act;
   a.res = residual; a.res_bf16 = residual_dtype == CASE_BF16; a.row_mask = row_mask; a.Y = Y; a.y_bf16 = y_dtype == CASE_BF16;
   ensure_smem<gemm_rows_tc_kernel>(GR_SMEM);
-  const long long ntile = (M + GR_M - 1) / GR_M;
+  const long long ntile = ((M + GR_M - 1) / GR_M) * (N / GR_NC);        // work units
   int dev = 0, nsm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);

@@ -797,6 +797,12 @@ class GttpDecodeEngine(_EngineBase):
 
     @torch.no_grad()
     def decode(self, max_len: int, mode: int = L.MODE_PROTO_GREEDY, use_graph: bool = True) -> torch.Tensor:
+        self.launch(max_len, mode, use_graph)
+        return self._finish_tokens(max_len, mode)
+
+    @torch.no_grad()
+    def launch(self, max_len: int, mode: int = L.MODE_PROTO_GREEDY, use_graph: bool = True) -> None:
+        """Enqueue a whole decode on the current stream without any host synchronisation (see CaseDecodeEngine.launch)."""
         if max_len > self.Tmax:
             raise ValueError('max_len exceeds the engine Tmax')
         if mode != L.MODE_BEAM and self.W != 1:
@@ -810,7 +816,6 @@ class GttpDecodeEngine(_EngineBase):
             self._graphs[(max_len, mode)].replay()
         else:
             self._run_steps(max_len)
-        return self._finish_tokens(max_len, mode)
 
     def _reset(self):
         self.state.reset()

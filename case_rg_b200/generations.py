@@ -84,6 +84,88 @@ class _FastModel:
             raise ValueError('set model.id2vocab before calling to_sentence')
         return to_sentence(batch_indices, self.id2vocab)
 
+    # ---- streamed batches (beam_batches / greedy_batches)
+    def search_batches(self, batches, max_len, width, mode):
+        """Generator behind beam_batches / greedy_batches."""
+        dev = self.weights.device
+        main = torch.cuda.current_stream(dev)
+        # the copy stream and the two staging sets live as long as the model: allocating 2 x 175 MB on a
+        # fresh stream per call costs tens of milliseconds of cudaMalloc
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream, self._staging = torch.cuda.Stream(dev), [None, None]
+        copy, staging = self._copy_stream, self._staging
+        copy.wait_stream(main)              # earlier readers of the staging sets (previous call) are done
+        prefilled = [None, None]            # event: the prefill that last read staging set k has finished
+
+        def stage(k, host):
+            shapes = {n: (tuple(host[n].shape), host[n].dtype) for n in self._KEYS}
+            with torch.cuda.stream(copy):
+                if staging[k] is None or staging[k][0] != shapes:
+                    # allocated ON the copy stream: a block the allocator recycles from the main stream's pool
+                    # (e.g. a prefill temporary that was freed on the host but is still being read on the
+                    # device) must never be handed to a buffer the copy stream writes
+                    staging[k] = (shapes, {n: torch.empty(host[n].shape, dtype=host[n].dtype, device=dev)
+                                           for n in self._KEYS})
+                if prefilled[k] is not None:
+                    copy.wait_event(prefilled[k])
+                for n in self._KEYS:
+                    staging[k][1][n].copy_(host[n], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return ev
+
+        it = iter(batches)
+        nxt = next(it, None)
+        k = 0
+        ready = stage(0, nxt) if nxt is not None else None
+        pending = None                      # engine whose decode is in flight
+        while nxt is not None:
+            d = staging[k][1]
+            # stream order: decode(i-1) -> prefill(i); the host enqueues prefill(i) while decode(i-1) runs.
+            # (prefill never touches the search state the pending answers are read from; an engine that is still
+            # decoding is never prefilled: engine_for returns the SAME engine for equal shapes, and its decode is
+            # ahead of this prefill on the main stream)
+            main.wait_event(ready)
+            eng = self._prefill_staged(d, width, max_len)
+            prefilled[k] = torch.cuda.Event()
+            prefilled[k].record(main)
+            nxt = next(it, None)
+            if nxt is not None:             # the next batch starts crossing PCIe before this one decodes
+                ready = stage(k ^ 1, nxt)
+            if mode != L.MODE_BEAM and eng.W != 1:
+                raise ValueError('greedy modes need an engine built with W == 1')
+            if pending is not None:
+                # answers of the previous batch: snapshot them on the device (stream-ordered after its decode), put
+                # THIS batch's decode behind the snapshot right away, and only then wait for the snapshot on a side
+                # stream - the device never idles while the host reads answers
+                snap = (pending.state.out_tokens[:, :max_len].clone(), pending.state.best_len.clone())
+                ev = torch.cuda.Event()
+                ev.record(main)
+                eng.launch(max_len, mode, use_graph=self.use_graph)
+                yield self._read_snapshot(snap, ev, mode)
+            else:
+                eng.launch(max_len, mode, use_graph=self.use_graph)
+            self.last_engine = pending = eng
+            k ^= 1
+        if pending is not None:
+            yield pending._finish_tokens(max_len, mode).cpu()
+
+    def _read_snapshot(self, snap, ev, mode):
+        """Device snapshot (tokens [B, T] int32, best_len [B]) -> host int64 tokens, trimmed like _finish_tokens."""
+        dev = self.weights.device
+        if getattr(self, '_d2h_stream', None) is None:
+            self._d2h_stream = torch.cuda.Stream(dev)
+        d2h = self._d2h_stream
+        d2h.wait_event(ev)
+        with torch.cuda.stream(d2h):
+            toks = snap[0].to('cpu', non_blocking=True)
+            blen = snap[1].to('cpu', non_blocking=True)
+        d2h.synchronize()
+        out = toks.to(torch.int64)
+        if mode == L.MODE_BEAM:             # merge1D (Utils.py:366-377): pad to the longest answer of the batch
+            out = out[:, :max(int(blen.max()), 1)]
+        return out
+
 
 class FastCaSE(_FastModel):
     """EncDecModel-protocol driver for the CaSE decoder.
@@ -148,89 +230,14 @@ class FastCaSE(_FastModel):
 
     _KEYS = ('mem_q', 'mem_p', 'query', 'passage', 'prior_q', 'prior_p', 'answer_rep', 'source_map')
 
-    def search_batches(self, batches, max_len, width, mode):
-        """Generator behind beam_batches / greedy_batches."""
-        dev = self.weights.device
-        main = torch.cuda.current_stream(dev)
-        # the copy stream and the two staging sets live as long as the model: allocating 2 x 175 MB on a
-        # fresh stream per call costs tens of milliseconds of cudaMalloc
-        if getattr(self, '_copy_stream', None) is None:
-            self._copy_stream, self._staging = torch.cuda.Stream(dev), [None, None]
-        copy, staging = self._copy_stream, self._staging
-        copy.wait_stream(main)              # earlier readers of the staging sets (previous call) are done
-        prefilled = [None, None]            # event: the prefill that last read staging set k has finished
-
-        def stage(k, host):
-            shapes = {n: (tuple(host[n].shape), host[n].dtype) for n in self._KEYS}
-            with torch.cuda.stream(copy):
-                if staging[k] is None or staging[k][0] != shapes:
-                    # allocated ON the copy stream: a block the allocator recycles from the main stream's pool
-                    # (e.g. a prefill temporary that was freed on the host but is still being read on the
-                    # device) must never be handed to a buffer the copy stream writes
-                    staging[k] = (shapes, {n: torch.empty(host[n].shape, dtype=host[n].dtype, device=dev)
-                                           for n in self._KEYS})
-                if prefilled[k] is not None:
-                    copy.wait_event(prefilled[k])
-                for n in self._KEYS:
-                    staging[k][1][n].copy_(host[n], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy)
-            return ev
-
-        it = iter(batches)
-        nxt = next(it, None)
-        k = 0
-        ready = stage(0, nxt) if nxt is not None else None
-        pending = None                      # engine whose decode is in flight
-        while nxt is not None:
-            d = staging[k][1]
-            B = d['source_map'].size(0)
-            S0 = d['mem_q'].reshape(B, -1, L.H).size(1)
-            S1 = d['mem_p'].reshape(B, -1, L.H).size(1)
-            eng = self.engine_for(B, width, S0, S1, max_len)
-            # stream order: decode(i-1) -> prefill(i); the host enqueues prefill(i) while decode(i-1) runs.
-            # (prefill never touches the search state the pending answers are read from)
-            main.wait_event(ready)
-            eng.prefill(d['mem_q'], d['mem_p'], d['query'].ne(0), d['passage'].ne(0), d['prior_q'], d['prior_p'],
-                        d['answer_rep'], d['source_map'])
-            prefilled[k] = torch.cuda.Event()
-            prefilled[k].record(main)
-            nxt = next(it, None)
-            if nxt is not None:             # the next batch starts crossing PCIe before this one decodes
-                ready = stage(k ^ 1, nxt)
-            if mode != L.MODE_BEAM and eng.W != 1:
-                raise ValueError('greedy modes need an engine built with W == 1')
-            if pending is not None:
-                # answers of the previous batch: snapshot them on the device (stream-ordered after its decode), put
-                # THIS batch's decode behind the snapshot right away, and only then wait for the snapshot on a side
-                # stream - the device never idles while the host reads answers
-                snap = (pending.state.out_tokens[:, :max_len].clone(), pending.state.best_len.clone())
-                ev = torch.cuda.Event()
-                ev.record(main)
-                eng.launch(max_len, mode, use_graph=self.use_graph)
-                yield self._read_snapshot(snap, ev, mode)
-            else:
-                eng.launch(max_len, mode, use_graph=self.use_graph)
-            self.last_engine = pending = eng
-            k ^= 1
-        if pending is not None:
-            yield pending._finish_tokens(max_len, mode).cpu()
-
-    def _read_snapshot(self, snap, ev, mode):
-        """Device snapshot (tokens [B, T] int32, best_len [B]) -> host int64 tokens, trimmed like _finish_tokens."""
-        dev = self.weights.device
-        if getattr(self, '_d2h_stream', None) is None:
-            self._d2h_stream = torch.cuda.Stream(dev)
-        d2h = self._d2h_stream
-        d2h.wait_event(ev)
-        with torch.cuda.stream(d2h):
-            toks = snap[0].to('cpu', non_blocking=True)
-            blen = snap[1].to('cpu', non_blocking=True)
-        d2h.synchronize()
-        out = toks.to(torch.int64)
-        if mode == L.MODE_BEAM:             # merge1D (Utils.py:366-377): pad to the longest answer of the batch
-            out = out[:, :max(int(blen.max()), 1)]
-        return out
+    def _prefill_staged(self, d, width, max_len):
+        B = d['source_map'].size(0)
+        S0 = d['mem_q'].reshape(B, -1, L.H).size(1)
+        S1 = d['mem_p'].reshape(B, -1, L.H).size(1)
+        eng = self.engine_for(B, width, S0, S1, max_len)
+        eng.prefill(d['mem_q'], d['mem_p'], d['query'].ne(0), d['passage'].ne(0), d['prior_q'], d['prior_p'],
+                    d['answer_rep'], d['source_map'])
+        return eng
 
     def module_greedy(self, data, max_len):
         """The in-module loop of CaSETransformerSeqDecoder.forward (no EOS handling, Model.py:91-123)."""
@@ -264,10 +271,16 @@ class FastGTTP(_FastModel):
             d.update(encode_outputs)
         if init_decoder_states is not None:
             d['init_state'] = init_decoder_states
+        eng = self._prefill_staged(d, width, max_len)
+        self.last_engine = eng
+        return eng.decode(max_len, mode, use_graph=self.use_graph)
+
+    _KEYS = ('context', 'background', 'background_map', 'src_output', 'bg_output', 'init_state')
+
+    def _prefill_staged(self, d, width, max_len):
         B, Lc = d['context'].shape
         Lb = d['background'].size(1)
         eng = self.engine_for(B, width, Lc, Lb, max_len)
         eng.prefill(d['src_output'], d['bg_output'], d['context'], d['background'], d['background_map'],
                     d['init_state'])
-        self.last_engine = eng
-        return eng.decode(max_len, mode, use_graph=self.use_graph)
+        return eng

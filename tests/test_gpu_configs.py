@@ -126,6 +126,31 @@ def test_streamed_batches_equal_single_calls():
         assert g.device.type == 'cpu' and torch.equal(g, w), (g, w)
 
 
+def test_streamed_gttp_batches_equal_single_calls():
+    """The same streaming face over GTTP batches (beam and protocol greedy): answers equal the one-call-per-batch path.
+    GTTP's row tail sums the copy mass of repeated ids with float atomics, so two decodes of one batch may differ on an
+    exact tie - the comparison allows a token or two."""
+    from case_rg_b200 import generations as FG
+    V, T, W, B = 2000, 8, 4, 5
+    sd = syn.make_gttp_state(91, V, 256, 256)
+    model = FG.FastGTTP(sd, device='cuda:0', dtype='bf16', max_dec_len=T, beam_width=W)
+    keys = ('context', 'background', 'background_map', 'src_output', 'bg_output', 'init_state')
+    hosts = []
+    for i in range(3):
+        inp = syn.make_gttp_inputs(92 + i, B, 20, 3, 40, V, 256)
+        hosts.append({k: getattr(inp, k).pin_memory() for k in keys})
+    want = [FG.beam(model, {k: v.cuda() for k, v in h.items()}, None, T, W).cpu() for h in hosts]
+    got = list(FG.beam_batches(model, iter(hosts), None, T, W))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        n = min(g.size(1), w.size(1))
+        assert g.device.type == 'cpu' and (g[:, :n] == w[:, :n]).float().mean() > 0.95, (g, w)
+    want = [FG.greedy(model, {k: v.cuda() for k, v in h.items()}, None, T).cpu() for h in hosts]
+    got = list(FG.greedy_batches(model, iter(hosts), None, T))
+    for g, w in zip(got, want):
+        assert (g == w).float().mean() > 0.95, (g, w)
+
+
 @pytest.mark.timeout(300)
 def test_long_decode_over_long_compacted_memory_uses_row_block_kernels():
     """max_target_length above the cluster kernels' 48-position history with a long passage memory (S1 = 10,240: 34
