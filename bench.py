@@ -358,7 +358,12 @@ class Workload:
         return gather_answers(ids, toks, self.T, self.n_total)
 
     def step_resident(self):
-        outs = [self.search(d) for d in self.resident]
+        if len(self.resident) > 1 and not self.greedy:
+            # several local batches: the streaming face over the device-resident copies, so that the host reads the
+            # answers of batch i while batch i+1 decodes (no per-batch host synchronisation between the decodes)
+            outs = list(self.FG.beam_batches(self.model, iter(self.resident), None, self.T, self.W))
+        else:
+            outs = [self.search(d) for d in self.resident]
         if self.strong:
             return self.gather(outs)[1]
         return outs[-1]
