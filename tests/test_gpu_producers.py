@@ -74,7 +74,8 @@ def test_enc_attention_vs_torch(C, L_, nseq):
                                                       (515, 256, 256, 1, 'f32', False, True), (260, 3840, 1280, 0, None, False, False),
                                                       (129, 1280, 1280, 0, 'bf16', False, False), (700, 256, 1280, 2, None, True, True),
                                                       (128, 256, 256, 2, 'f32', True, True), (20000, 256, 256, 0, 'bf16', True, False),
-                                                      (200, 256, 64, 0, None, False, True), (333, 512, 192, 1, 'f32', False, False)])
+                                                      (200, 256, 64, 0, None, False, True), (333, 512, 192, 1, 'f32', False, False),
+                                                      (1, 256, 256, 0, 'f32', True, True), (127, 1280, 1280, 2, None, False, False)])
 def test_gemm_rows_tc_vs_torch(M, N, K, act, res, mask, out32):
     """case_gemm_rows_tc (tcgen05 / TMEM, bias + activation + residual + row mask epilogue) against torch fp32 on the same
     bf16-rounded operands: partial last row tile, 1 .. 20 K stages (shorter than,
@@ -103,7 +104,7 @@ def test_gemm_rows_tc_vs_torch(M, N, K, act, res, mask, out32):
         want = want * rm.view(-1, 1).float()
     assert torch.isfinite(y.float()).all()
     assert rel(y, want) < (2e-5 if out32 else 5e-3), rel(y, want)
-    if rm is not None:
+    if rm is not None and int((rm == 0).sum()) > 0:
         assert float(y[rm == 0].abs().max()) == 0.0
 
 
@@ -166,6 +167,42 @@ def test_producers_vs_oracle(gemm):
     assert rel(got['rank'], want['passage_score']) < 5e-2
     assert torch.allclose(got['prior_p'].reshape(3, -1).sum(1), torch.ones(3, device=DEV), atol=1e-4)
     assert float(got['prior_p'][~inp.passage.ne(0).to(DEV)].abs().max()) == 0.0
+
+
+def test_producers_edge_cases_vs_oracle():
+    """Ragged edge of the pipeline: a one-token query next to the longest one (Lq = 64), a passage length that is not a
+    multiple of any tile - against the oracle; and a passage that is all PAD, where the reference's encoder softmax over
+    zero valid keys yields NaN for the whole query (torch semantics): here the padded passage contributes zeros, every
+    output stays finite, and the other queries are not affected."""
+    from case_rg_b200.producers import CaseProducers
+    from oracle.producers import producers
+    V, B, Lq, NP, Lp = 700, 2, 64, 3, 77
+    sd = syn.make_case_producer_state(15, V, H)
+    inp = syn.make_case_inputs(16, B, Lq, NP, Lp, V, H)
+    query, passage = inp.query.clone(), inp.passage.clone()
+    g = torch.Generator().manual_seed(17)
+    query[0, 0] = torch.randint(305, V, (Lq,), generator=g)              # the longest query: no PAD at all
+    query[1, 0, 1:] = 0                                                  # a one-token query
+    want = producers(sd, query, passage)
+    prod = CaseProducers(sd, device=DEV)
+    got = prod(query, passage)
+    torch.cuda.synchronize()
+    for k, tol in (('enc_p', 2e-2), ('enc_q', 2e-2), ('ps_p', 3e-2), ('mem_q', 3e-2), ('mem_p', 3e-2), ('answer_rep', 3e-2),
+                   ('prior_p', 5e-2)):
+        assert torch.isfinite(want[k]).all() and torch.isfinite(got[k]).all(), k
+        assert rel(got[k], want[k]) < tol, (k, rel(got[k], want[k]))
+    assert rel(got['rank'], want['passage_score']) < 5e-2
+    # an all-PAD passage in query 1
+    passage2 = passage.clone()
+    passage2[1, 2] = 0
+    assert not torch.isfinite(producers(sd, query, passage2)['mem_p'][1]).all()      # the reference's answer: NaN
+    got2 = prod(query, passage2)
+    torch.cuda.synchronize()
+    for k in ('enc_p', 'ps_p', 'mem_q', 'mem_p', 'answer_rep', 'prior_p', 'rank'):
+        assert torch.isfinite(got2[k]).all(), k
+    assert float(got2['ps_p'][1, 2].abs().max()) == 0.0 and float(got2['prior_p'][1, 2].abs().max()) == 0.0
+    for k in ('mem_p', 'mem_q', 'prior_p', 'answer_rep'):
+        assert torch.equal(got2[k][0], got[k][0]), k                                  # query 0 is untouched
 
 
 def test_decode_from_token_ids_matches_reference_golden():
