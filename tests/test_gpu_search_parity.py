@@ -145,6 +145,13 @@ def test_c2_search_path_vs_oracle(dtype):
         _record('c2_bf16_logits_step0', dict(rel_err=err))
 
 
+@pytest.mark.parametrize('wseed,iseed', [(151, 161), (251, 261), (351, 361)])
+def test_c2_search_path_other_seeds_bf16(wseed, iseed):
+    """The C2 case again on three more weight / input seeds (bf16 storage): the zero-miss result does not hang on one
+    draw.  Records under c2s<wseed>_*."""
+    _run_case(f'c2s{wseed}', 'bf16', 64, 4, 60, 10, 256, 40, wseed, iseed)
+
+
 def test_c5_share_search_path_vs_oracle():
     """Per-GPU share of BASELINE configs[4]: B=32, beam 8, 20 x 512 passages (S = 10,300), T=40, bf16."""
     _run_case('c5', 'bf16', 32, 8, 60, 20, 512, 40, 52, 62)
