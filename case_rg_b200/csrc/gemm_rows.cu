@@ -23,13 +23,21 @@
 
 namespace cb {
 
-constexpr int GR_M = 128, GR_NC = 256, GR_KB = 64, GR_NS = 4;
+constexpr int GR_M = 128, GR_NC = 256, GR_KB = 64;
 constexpr int GR_A_BYTES = GR_M * GR_KB * 2;         // 16 KB: one 128-byte-swizzle atom column (64 k) of 128 rows
 constexpr int GR_W_BYTES = GR_NC * GR_KB * 2;        // 32 KB
-constexpr int GR_STAGE = GR_A_BYTES + GR_W_BYTES;    // 48 KB
+// MT = row tiles of 128 per work unit.  MT = 1: 48 KB stages x 4, the two halves of tensor memory alternate between units.
+// MT = 2: 64 KB stages x 3, both halves hold the unit's two accumulators: a W stage is read from L2 once for 256 rows, which
+// is what the 1280-wide layers need - at MT = 1 they sit on the L2 -> SM throughput cap (960 KB per 128 x 256 x 1280 unit =
+// 12 TB/s over 148 SMs at 1.05 PFLOP/s).
+template <int MT> struct GrCfg {
+  static constexpr int NS = MT == 1 ? 4 : 3;
+  static constexpr int STAGE = MT * GR_A_BYTES + GR_W_BYTES;
+};
 constexpr int GR_THREADS = 13 * 32;
 constexpr int GR_STG = 32 * 80;                       // epilogue staging block of a warp: 32 rows x (64 + 16) bytes
-constexpr int GR_SMEM = GR_NS * GR_STAGE + 256 + 8 * GR_STG;
+constexpr int GR_RING = 192 * 1024;                   // NS x STAGE for both configurations
+constexpr int GR_SMEM = GR_RING + 256 + 8 * GR_STG;
 
 __device__ __forceinline__ void gr_mbar_init(uint32_t bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -113,33 +121,37 @@ struct GemmRowsArgs {
   void* Y; int y_bf16;
 };
 
+template <int MT>
 __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmRowsArgs a) {
+  constexpr int GR_NS = GrCfg<MT>::NS, GR_STAGE = GrCfg<MT>::STAGE;
+  static_assert(GR_NS * GR_STAGE == GR_RING, "ring size");
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t s_base = smem_u32(smem);
-  const uint32_t s_bar = s_base + GR_NS * GR_STAGE;
+  const uint32_t s_bar = s_base + GR_RING;
   const uint32_t BAR_A = s_bar, BAR_W = s_bar + 8 * GR_NS, BAR_FREE = s_bar + 16 * GR_NS, BAR_ACC = s_bar + 24 * GR_NS,
                  BAR_ACCF = BAR_ACC + 16;
-  // barriers: [0,1] a_full (128 gather threads), [2,3] w_full (4 issuing lanes + bytes), [4,5] stage free (MMAs done),
-  //           [6,7] acc_full, [8,9] acc_free (8 epilogue warps)
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + GR_NS * GR_STAGE + 192);
+  // barriers: per stage a_full (128 gather threads), w_full (4 issuing lanes + bytes), free (MMAs done); per accumulator
+  // slot acc_full and acc_free (the epilogue warps that drain the slot)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + GR_RING + 192);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // persistent: a work unit is (row tile, 256-column chunk); this CTA owns the units blockIdx.x, blockIdx.x + gridDim.x, ...
-  // of the chunk-minor unit list (neighbouring CTAs share a row tile and all of them share the few weight chunks in
-  // flight, so both operands are L2 hits); the stage ring and the two accumulators run on across units, so the epilogue
-  // of one overlaps the next one's MMAs
+  // persistent: a work unit is (MT row tiles, 256-column chunk); this CTA owns the units blockIdx.x, blockIdx.x + gridDim.x,
+  // ... of the chunk-minor unit list (neighbouring CTAs share the row tiles and all of them share the few weight chunks in
+  // flight, so both operands are L2 hits); the stage ring runs on across units.  Accumulator slots (256 TMEM columns each):
+  // MT = 1: slot = unit parity, drained by all 8 epilogue warps, so the epilogue of one unit overlaps the next one's MMAs;
+  // MT = 2: slot = row tile of the unit, drained by 4 warps each.
   const int KB = a.K / GR_KB, nchunk = a.N / GR_NC;
-  const long long total = ((a.M + GR_M - 1) / GR_M) * nchunk;
+  const long long total = ((a.M + MT * GR_M - 1) / (MT * GR_M)) * nchunk;
   const int nunit = (long long)blockIdx.x < total ? (int)((total - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
   const int nit = nunit * KB;                           // ring iterations
 
   if (tid == 0) {
     for (int i = 0; i < GR_NS; ++i) {
-      gr_mbar_init(BAR_A + 8 * i, 128);                 // A tile of the stage gathered (128 producer threads)
+      gr_mbar_init(BAR_A + 8 * i, 128);                 // A tiles of the stage gathered (128 producer threads)
       gr_mbar_init(BAR_W + 8 * i, 4);                   // W tile landed (4 issuing lanes + bytes)
       gr_mbar_init(BAR_FREE + 8 * i, 1);                // the MMAs that read the stage are done
     }
-    gr_mbar_init(BAR_ACC, 1); gr_mbar_init(BAR_ACC + 8, 1);           // accumulator of a unit complete
-    gr_mbar_init(BAR_ACCF, 8); gr_mbar_init(BAR_ACCF + 8, 8);         // ... drained by the 8 epilogue warps
+    gr_mbar_init(BAR_ACC, 1); gr_mbar_init(BAR_ACC + 8, 1);                       // accumulator slot complete
+    gr_mbar_init(BAR_ACCF, 8 / MT); gr_mbar_init(BAR_ACCF + 8, 8 / MT);           // ... drained by its epilogue warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -153,19 +165,19 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
   pdl_wait();
 
   if (warp < 4) {
-    // ================= producers (4 warps): stage it & 1 is filled while the copies of stage (it - 1) & 1 land
+    // ================= producers (4 warps): a stage is handed over GR_NS - 2 iterations after its copies were issued
     const int w4 = warp;
     // gather role: a quarter warp (8 lanes) copies one 128-byte run of a source row - one full cache line per request - into
     // the 128-byte-swizzle layout, where its eight 16-byte chunks land in eight different bank groups
     const int rq = w4 * 4 + (lane >> 3), ch = lane & 7;
     for (int it = 0; it < nit; ++it) {
       const int g = it % GR_NS, use = it / GR_NS;
-      const uint32_t s_a = s_base + g * GR_STAGE, s_w = s_a + GR_A_BYTES;
+      const uint32_t s_a = s_base + g * GR_STAGE, s_w = s_a + MT * GR_A_BYTES;
       const int u = it / KB, kb = it - u * KB;
       const long long ug = (long long)blockIdx.x + (long long)u * gridDim.x;
       const long long mt = ug / nchunk;
       const int c = (int)(ug - mt * nchunk);
-      const long long m0 = mt * GR_M;
+      const long long m0 = mt * (MT * GR_M);
       if (use >= 1) gr_wait(BAR_FREE + 8 * g, (uint32_t)(use - 1) & 1u);        // the MMAs of this stage's previous use are done
       if (lane == 0) {
         const char* src = reinterpret_cast<const char*>(a.Wp) + ((size_t)kb * nchunk + c) * GR_W_BYTES + (size_t)w4 * (GR_W_BYTES / 4);
@@ -173,8 +185,8 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
         gr_bulk(s_w + w4 * (GR_W_BYTES / 4), src, GR_W_BYTES / 4, BAR_W + 8 * g);
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = i * 16 + rq;
+      for (int i = 0; i < 8 * MT; ++i) {
+        const int row = i * 16 + rq;                     // 0 .. 128 MT - 1; tile = row >> 7
         const long long m = m0 + row;
         const bf16* src = a.X + (size_t)(m < a.M ? m : 0) * a.K + kb * GR_KB + ch * 8;
         const uint32_t dst = s_a + (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4);
@@ -198,43 +210,53 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
       constexpr uint32_t idesc = gr_idesc(GR_M, GR_NC);
       int it = 0;
       for (int c = 0; c < nunit; ++c) {
-        const int tb = c & 1;
-        if (c >= 2) gr_wait(BAR_ACCF + 8 * tb, (uint32_t)((c >> 1) - 1) & 1u);        // epilogue of unit c - 2 done
+        if (MT == 1 && c >= 2) gr_wait(BAR_ACCF + 8 * (c & 1), (uint32_t)((c >> 1) - 1) & 1u);    // epilogue of unit c - 2 done
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int g = it % GR_NS;
           const uint32_t par = (uint32_t)(it / GR_NS) & 1u;
           gr_wait(BAR_A + 8 * g, par);
           gr_wait(BAR_W + 8 * g, par);
           gr_fence_after();
-          const uint32_t s_a = s_base + g * GR_STAGE, s_w = s_a + GR_A_BYTES;
+          const uint32_t s_a = s_base + g * GR_STAGE, s_w = s_a + MT * GR_A_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < GR_KB / 16; ++ks) {
-            const int kc = ks * 2;
-            const uint64_t ad = gr_desc_sw128(s_a + ks * 32);
-            const uint64_t bd = gr_desc(s_w + kc * (GR_NC / 8) * 128, (GR_NC / 8) * 128, 128);
-            gr_umma(tmem + tb * GR_NC, ad, bd, idesc, (kb | ks) != 0);
+          for (int tile = 0; tile < MT; ++tile) {
+            const int slot = MT == 1 ? (c & 1) : tile;
+            // MT = 2: the slot still holds unit c - 1 until its four epilogue warps have drained it
+            if (MT == 2 && kb == 0 && c >= 1) { gr_wait(BAR_ACCF + 8 * slot, (uint32_t)(c - 1) & 1u); gr_fence_after(); }
+#pragma unroll
+            for (int ks = 0; ks < GR_KB / 16; ++ks) {
+              const int kc = ks * 2;
+              const uint64_t ad = gr_desc_sw128(s_a + tile * GR_A_BYTES + ks * 32);
+              const uint64_t bd = gr_desc(s_w + kc * (GR_NC / 8) * 128, (GR_NC / 8) * 128, 128);
+              gr_umma(tmem + slot * GR_NC, ad, bd, idesc, (kb | ks) != 0);
+            }
           }
           gr_commit(BAR_FREE + 8 * g);                   // stage free once these MMAs have read it
         }
-        gr_commit(BAR_ACC + 8 * tb);                     // accumulator of the unit complete
+        if (MT == 1) {
+          gr_commit(BAR_ACC + 8 * (c & 1));              // accumulator of the unit complete
+        } else {
+          gr_commit(BAR_ACC); gr_commit(BAR_ACC + 8);    // both row tiles of the unit complete
+        }
       }
     }
   } else {
-    // ================= epilogue (warps 4-11): warp & 3 = TMEM lane quarter, (warp - 4) >> 2 = which 32-column groups
+    // ================= epilogue (warps 4-11): warp & 3 = TMEM lane quarter; hh = (warp - 4) >> 2 is, for MT = 1, the parity
+    // of the 32-column groups the warp takes and, for MT = 2, the row tile (= accumulator slot) it drains
     const int q = warp & 3, hh = (warp - 4) >> 2;
-    unsigned char* stg = smem + GR_NS * GR_STAGE + 256 + (warp - 4) * GR_STG;      // this warp's staging block
+    unsigned char* stg = smem + GR_RING + 256 + (warp - 4) * GR_STG;      // this warp's staging block
     for (int u = 0; u < nunit; ++u) {
       const long long ug = (long long)blockIdx.x + (long long)u * gridDim.x;
       const long long mt = ug / nchunk;
       const int c = (int)(ug - mt * nchunk);
-      const long long m = mt * GR_M + q * 32 + lane;
+      const long long m = mt * (MT * GR_M) + (MT == 2 ? hh * GR_M : 0) + q * 32 + lane;
       const bool rowok = m < a.M;
       const bool keep = rowok && (a.row_mask == nullptr || a.row_mask[m] != 0);
-      const int tb = u & 1;
-      gr_wait(BAR_ACC + 8 * tb, (uint32_t)(u >> 1) & 1u);
+      const int tb = MT == 1 ? (u & 1) : hh;           // accumulator slot
+      gr_wait(BAR_ACC + 8 * tb, (uint32_t)(MT == 1 ? (u >> 1) : u) & 1u);
       gr_fence_after();
       const long long mw = m - lane;                   // first row of the warp's 32
-      for (int cg = hh; cg < GR_NC / 32; cg += 2) {
+      for (int cg = (MT == 1 ? hh : 0); cg < GR_NC / 32; cg += (MT == 1 ? 2 : 1)) {
         const int n0 = c * GR_NC + cg * 32;
         uint32_t acc[32];
         gr_tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + tb * GR_NC + cg * 32, acc);
@@ -358,12 +380,22 @@ extern "C" int case_gemm_rows_tc(const void* X, const void* Wp, const float* bia
   GemmRowsArgs a;
   a.X = (const bf16*)X; a.Wp = (const bf16*)Wp; a.bias = bias; a.M = M; a.N = N; a.K = K; a.act = act;
   a.res = residual; a.res_bf16 = residual_dtype == CASE_BF16; a.row_mask = row_mask; a.Y = Y; a.y_bf16 = y_dtype == CASE_BF16;
-  ensure_smem<gemm_rows_tc_kernel>(GR_SMEM);
-  const long long ntile = ((M + GR_M - 1) / GR_M) * (N / GR_NC);        // work units
+  // two row tiles per unit where the weight stream is what bounds the launch: the 1280-deep, wide layers (3840 x 1280:
+  // 1.58 -> 1.35 ms at M = 163,840; with a single 256-column chunk the un-overlapped epilogue of this form costs more
+  // than the shared weight stage saves)
+  const bool mt2 = K >= 1024 && N >= 2 * GR_NC && M >= 2 * GR_M;
+  const long long units = ((M + (mt2 ? 2 : 1) * GR_M - 1) / ((mt2 ? 2 : 1) * GR_M)) * (N / GR_NC);
   int dev = 0, nsm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   if (nsm <= 0) nsm = 148;
-  launch_k(gemm_rows_tc_kernel, (unsigned)(ntile < nsm ? ntile : nsm), GR_THREADS, GR_SMEM, (cudaStream_t)stream, a);
+  const unsigned grid = (unsigned)(units < nsm ? units : nsm);
+  if (mt2) {
+    ensure_smem<gemm_rows_tc_kernel<2>>(GR_SMEM);
+    launch_k(gemm_rows_tc_kernel<2>, grid, GR_THREADS, GR_SMEM, (cudaStream_t)stream, a);
+  } else {
+    ensure_smem<gemm_rows_tc_kernel<1>>(GR_SMEM);
+    launch_k(gemm_rows_tc_kernel<1>, grid, GR_THREADS, GR_SMEM, (cudaStream_t)stream, a);
+  }
   return check_launch("case_gemm_rows_tc");
 }

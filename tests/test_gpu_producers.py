@@ -75,11 +75,13 @@ def test_enc_attention_vs_torch(C, L_, nseq):
                                                       (129, 1280, 1280, 0, 'bf16', False, False), (700, 256, 1280, 2, None, True, True),
                                                       (128, 256, 256, 2, 'f32', True, True), (20000, 256, 256, 0, 'bf16', True, False),
                                                       (200, 256, 64, 0, None, False, True), (333, 512, 192, 1, 'f32', False, False),
-                                                      (1, 256, 256, 0, 'f32', True, True), (127, 1280, 1280, 2, None, False, False)])
+                                                      (1, 256, 256, 0, 'f32', True, True), (127, 1280, 1280, 2, None, False, False),
+                                                      (40000, 512, 1024, 0, 'bf16', True, False), (257, 768, 1280, 1, 'f32', False, True)])
 def test_gemm_rows_tc_vs_torch(M, N, K, act, res, mask, out32):
     """case_gemm_rows_tc (tcgen05 / TMEM, bias + activation + residual + row mask epilogue) against torch fp32 on the same
     bf16-rounded operands: partial last row tile, 1 .. 20 K stages (shorter than,
-    equal to and longer than the four-stage ring), 1 .. 15 column chunks, more row tiles than CTAs (persistent loop)."""
+    equal to and longer than the four-stage ring), 1 .. 15 column chunks, more row tiles than CTAs (persistent loop), both unit shapes (one and
+    two row tiles per unit, the latter with an odd tile count and more units than CTAs)."""
     from case_rg_b200 import _lib as L
     from case_rg_b200.producers import _Linear
     g = torch.Generator().manual_seed(M + N + K)
