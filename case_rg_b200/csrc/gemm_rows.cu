@@ -4,17 +4,18 @@
 //
 // X: bf16 row-major (the LayerNorm / attention / previous GEMM output), K % 64 == 0; W: the nn.Linear weight packed per
 // 64-wide K block into 256-row tiles of the UMMA K-major no-swizzle canonical layout ([K/64][N/256][32 KB]); Y: bf16 or
-// fp32 row-major.  Persistent grid (one CTA per SM): a CTA takes row tiles of 128 (UMMA M = 128 = the TMEM lanes) and walks
-// N in chunks of 256 columns (UMMA N = 256: 96 B/clk of shared-memory operand reads, against 128 B/clk at N = 128); the
-// accumulator D[128 x 256] (fp32) of a (row tile, chunk) unit lives in one half of tensor memory while the epilogue drains
-// the other half.  The K loop runs over a four-stage ring of (A tile 128 x 64, W tile 256 x 64) = 48 KB per stage that
-// runs on across units:
-//   warps 0-3        producers: the A tile is gathered with 16-byte cp.async (8 per thread and stage, a full 128-byte line
+// fp32 row-major.  Persistent grid (one CTA per SM): a work unit is MT row tiles of 128 (UMMA M = 128 = the TMEM lanes) x one
+// chunk of 256 columns (UMMA N = 256: 96 B/clk of shared-memory operand reads, against 128 B/clk at N = 128); CTAs stride
+// over the chunk-minor unit list.  MT = 1: the accumulator D[128 x 256] (fp32) of a unit lives in one half of tensor memory
+// while the epilogue drains the other half; MT = 2 (wide 1280-deep layers): both halves hold the unit's two accumulators,
+// one W stage feeds 256 rows.  The K loop runs over a ring of (MT A tiles 128 x 64, W tile 256 x 64) stages - 4 x 48 KB or
+// 3 x 64 KB - that runs on across units:
+//   warps 0-3        producers: the A tiles are gathered with 16-byte cp.async (8 MT per thread and stage, a full 128-byte line
 //                    per quarter warp; rows past M are zero-filled) into the 128-byte-swizzle K-major layout
 //                    (conflict-free on the shared-memory side), the pre-packed W tile arrives as four bulk copies; a
 //                    stage is handed to the tensor core two iterations after its copies were issued
-//                    (cp.async.wait_group 2), so three gathers are in flight behind the stage being multiplied
-//   warp 12          MMA issuer (one thread): 4 tcgen05.mma (M = 128, N = 256, K = 16) per stage; tcgen05.commit signals
+//                    (cp.async.wait_group), so the other stages' gathers are in flight behind the one being multiplied
+//   warp 12          MMA issuer (one thread): 4 MT tcgen05.mma (M = 128, N = 256, K = 16) per stage; tcgen05.commit signals
 //                    "stage free" and "accumulator complete"
 //   warps 4-11       epilogue: tcgen05.ld (lane = row, 32 columns at a time), bias / gelu / relu / residual / row mask,
 //                    residual loads and output stores staged through shared memory so that global memory sees whole
