@@ -746,7 +746,8 @@ def roofline(wl, eng, ms_per_decode_step, torch, dev):
         return dict(kernel=None, bound='hbm', achieved=None, peak=hbm, unit='GB/s', frac=None, traffic=None,
                     peak_source=which, kernels=kernels, step=step, step_shares=shares)
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at c2 from the committed `ncu --set full` capture
-    # (profiles/r1_top_kernels_ncu_summary.txt: 114.3 MB read + 3.1 MB written per launch); other shapes: not captured
+    # (profiles/r2_top_kernels_ncu_summary.txt, same in round 1: 114.3 MB read + 3-6 MB written per launch); other shapes:
+    # not captured
     traffic = 117.4e6 if (B, W, S1) == (64, 4, 2560) else None
     return dict(kernel='cross_attn_part_kernel (passage memory, valid keys; timed in the decode graph)', bound='hbm',
                 achieved=top['achieved'], peak=hbm, unit='GB/s', frac=top['frac'], traffic=traffic, peak_source=which,
