@@ -116,6 +116,6 @@ def producers(sd: Dict[str, torch.Tensor], query, passage):
     prior_p = prior_p / (1e-8 + prior_p.sum(dim=-1, keepdim=True))
     answer_rep = torch.bmm(prior_p.unsqueeze(1), mem_p.reshape(B, -1, mem_p.size(-1))).squeeze(1)
     prior_p = prior_p.view(B, NP, Lp)
-    prior_q = torch.ones(B, 1, Lq)
+    prior_q = torch.ones(B, 1, Lq, device=query.device)
     return dict(enc_q=enc_q, enc_p=enc_p, G_p_q=G_p_q, G_q_p=G_q_p, ps_q=ps_q, ps_p=ps_p, passage_score=passage_score,
                 token_score=token_score, mem_q=mem_q, mem_p=mem_p, prior_q=prior_q, prior_p=prior_p, answer_rep=answer_rep)

@@ -15,7 +15,11 @@ def main():
         d = json.load(open(f))
         name = os.path.basename(f)[len('parity_'):-len('.json')]
         if 'rel_err' in d:
-            rows.append((name, 'logits of step 0', f"rel. error {d['rel_err']:.2e}", '', '', '', ''))
+            if isinstance(d['rel_err'], dict):         # producers at the full C2 size: max relative error per output
+                txt = ', '.join(f'{k} {v:.1e}' for k, v in d['rel_err'].items())
+                rows.append((name, 'pre-decode producers, rel. error vs the fp32 oracle', txt, '', '', '', ''))
+            else:
+                rows.append((name, 'logits of step 0', f"rel. error {d['rel_err']:.2e}", '', '', '', ''))
             continue
         n = d.get('rows', d.get('queries'))
         kind = 'greedy rows' if 'rows' in d else 'beam queries'

@@ -5,6 +5,7 @@ the answers decoded FROM TOKEN IDS (producers + decoder) against the reference's
 
 bf16 GEMM operands with fp32 accumulation / statistics / residual streams: north_star's bf16 band (2e-2 relative) is the
 tolerance of everything that went through a GEMM; the kernels themselves are checked tighter on exact operands."""
+import json
 import os
 
 import numpy as np
@@ -205,6 +206,42 @@ def test_producers_edge_cases_vs_oracle():
     assert float(got2['ps_p'][1, 2].abs().max()) == 0.0 and float(got2['prior_p'][1, 2].abs().max()) == 0.0
     for k in ('mem_p', 'mem_q', 'prior_p', 'answer_rep'):
         assert torch.equal(got2[k][0], got[k][0]), k                                  # query 0 is untouched
+
+
+@pytest.mark.timeout(600)
+def test_producers_full_size_c2_vs_oracle():
+    """The pipeline at BASELINE configs[1]'s full size (B = 64, 10 x 256 passages, Lq = 60, V = 30522) against the oracle
+    evaluated on the same GPU in strict fp32 (TF32 off): the decoder's inputs - memories, prior, answer representation -
+    and the passage ranks within the bf16 band; the ranking of the passages of every query agrees wherever the oracle's
+    margin between neighbours exceeds the band."""
+    from case_rg_b200.producers import CaseProducers
+    from oracle.case_decoder import strict_fp32
+    from oracle.producers import producers
+    strict_fp32()
+    V, B, Lq, NP, Lp = syn.BERT_VOCAB, 64, 60, 10, 256
+    sd = syn.make_case_producer_state(25, V, H)
+    inp = syn.make_case_inputs(26, B, Lq, NP, Lp, V, H)
+    q, p = inp.query.to(DEV), inp.passage.to(DEV)
+    want = producers({k: v.to(DEV) for k, v in sd.items()}, q, p)
+    got = CaseProducers(sd, device=DEV)(q, p)
+    torch.cuda.synchronize()
+    res = {}
+    for k, tol in (('enc_p', 2e-2), ('enc_q', 2e-2), ('ps_p', 3e-2), ('mem_q', 3e-2), ('mem_p', 3e-2), ('answer_rep', 3e-2),
+                   ('prior_p', 5e-2)):
+        assert torch.isfinite(got[k]).all(), k
+        res[k] = rel(got[k], want[k])
+        assert res[k] < tol, (k, res[k])
+    res['rank'] = rel(got['rank'], want['passage_score'])
+    assert res['rank'] < 5e-2
+    ws, gs = want['passage_score'].cpu(), got['rank'].cpu()
+    order = ws.argsort(1, descending=True)
+    margin = (ws.gather(1, order)[:, :-1] - ws.gather(1, order)[:, 1:])
+    gsorted = gs.gather(1, order)
+    clear = margin > 5e-2 * float(ws.abs().max())
+    assert bool(((gsorted[:, :-1] - gsorted[:, 1:]) > 0)[clear].all())
+    os.makedirs('gpurun_out', exist_ok=True)
+    with open('gpurun_out/parity_producers_c2.json', 'w') as f:
+        json.dump(dict(rel_err=res, clear_neighbour_pairs=int(clear.sum()), pairs=int(clear.numel())), f)
 
 
 def test_decode_from_token_ids_matches_reference_golden():
