@@ -142,6 +142,7 @@ _PROTOS = {
     'case_rows_dot': [vp, vp, vp, C.c_longlong, C.c_longlong, vp, vp],
     'case_prior_answer': [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp],
     'case_gemm_rows_tc': [vp, vp, vp, C.c_longlong, i32, i32, i32, vp, i32, vp, vp, i32, vp],
+    'case_ffn_rows_tc': [vp, vp, vp, i32, i32, vp, vp, C.c_longlong, vp, i32, vp, vp, i32, vp],
     'case_thread_options': [i32],
     'case_fork_create': [C.POINTER(vp)],
     'case_fork_destroy': [vp],

@@ -113,6 +113,78 @@ __device__ __forceinline__ uint32_t gr_pk2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Tail of the epilogue for one 32-column group of a warp's 32 rows (v: this lane's row): + residual, row mask, store.
+// Residual and output go through the warp's staging block (32 rows x 64 bytes, 80-byte row stride): global memory is
+// touched with 4 lanes per row and 8 rows per instruction - whole 32-byte sectors, 64 contiguous bytes per row - while a
+// lane reads / writes its own row in shared memory.
+__device__ __forceinline__ void gr_finish_group(float (&v)[32], unsigned char* stg, int lane, long long mw, long long M, int N,
+                                                int n0, const void* res, int res_bf16, bool keep, void* Y, int y_bf16) {
+  if (res != nullptr) {
+    const int nsb = res_bf16 ? 1 : 2;            // 64-byte sub-blocks per 32 columns
+    const size_t rstride = (size_t)N * (res_bf16 ? 2 : 4);
+    const char* rbase = reinterpret_cast<const char*>(res) + (size_t)n0 * (res_bf16 ? 2 : 4);
+    for (int sb = 0; sb < nsb; ++sb) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2);
+        if (mw + r < M)
+          *reinterpret_cast<uint4*>(stg + r * 80 + (lane & 3) * 16) =
+              __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(mw + r) * rstride + sb * 64 + (lane & 3) * 16));
+      }
+      __syncwarp();
+      if (res_bf16) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 w = *reinterpret_cast<const uint4*>(stg + lane * 80 + j * 16);
+          v[8 * j] += __uint_as_float(w.x << 16); v[8 * j + 1] += __uint_as_float(w.x & 0xffff0000u);
+          v[8 * j + 2] += __uint_as_float(w.y << 16); v[8 * j + 3] += __uint_as_float(w.y & 0xffff0000u);
+          v[8 * j + 4] += __uint_as_float(w.z << 16); v[8 * j + 5] += __uint_as_float(w.z & 0xffff0000u);
+          v[8 * j + 6] += __uint_as_float(w.w << 16); v[8 * j + 7] += __uint_as_float(w.w & 0xffff0000u);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 w = *reinterpret_cast<const float4*>(stg + lane * 80 + j * 16);
+          if (sb == 0) { v[4 * j] += w.x; v[4 * j + 1] += w.y; v[4 * j + 2] += w.z; v[4 * j + 3] += w.w; }
+          else { v[16 + 4 * j] += w.x; v[16 + 4 * j + 1] += w.y; v[16 + 4 * j + 2] += w.z; v[16 + 4 * j + 3] += w.w; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (!keep) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  }
+  const int nsb = y_bf16 ? 1 : 2;
+  const size_t ystride = (size_t)N * (y_bf16 ? 2 : 4);
+  char* ybase = reinterpret_cast<char*>(Y) + (size_t)n0 * (y_bf16 ? 2 : 4);
+  for (int sb = 0; sb < nsb; ++sb) {
+    if (y_bf16) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(stg + lane * 80 + j * 16) =
+            make_uint4(gr_pk2(v[8 * j], v[8 * j + 1]), gr_pk2(v[8 * j + 2], v[8 * j + 3]), gr_pk2(v[8 * j + 4], v[8 * j + 5]),
+                       gr_pk2(v[8 * j + 6], v[8 * j + 7]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (sb == 0) *reinterpret_cast<float4*>(stg + lane * 80 + j * 16) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        else *reinterpret_cast<float4*>(stg + lane * 80 + j * 16) = make_float4(v[16 + 4 * j], v[16 + 4 * j + 1], v[16 + 4 * j + 2], v[16 + 4 * j + 3]);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {             // streaming stores: Y passes through L2 once
+      const int r = it * 8 + (lane >> 2);
+      if (mw + r < M)
+        __stcs(reinterpret_cast<uint4*>(ybase + (size_t)(mw + r) * ystride + sb * 64 + (lane & 3) * 16),
+               *reinterpret_cast<const uint4*>(stg + r * 80 + (lane & 3) * 16));
+    }
+    __syncwarp();
+  }
+}
+
 struct GemmRowsArgs {
   const bf16* X; const bf16* Wp; const float* bias;
   long long M; int N, K;
@@ -276,79 +348,204 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        // Residual and output go through the warp's staging block (32 rows x 64 bytes, 80-byte row stride): global memory
-        // is touched with 4 lanes per row and 8 rows per instruction - whole 32-byte sectors, 64 contiguous bytes per row -
-        // while a lane reads / writes its own row in shared memory.
-        if (a.res != nullptr) {
-          const int nsb = a.res_bf16 ? 1 : 2;            // 64-byte sub-blocks per 32 columns
-          const size_t rstride = (size_t)a.N * (a.res_bf16 ? 2 : 4);
-          const char* rbase = reinterpret_cast<const char*>(a.res) + (size_t)n0 * (a.res_bf16 ? 2 : 4);
-          for (int sb = 0; sb < nsb; ++sb) {
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int r = it * 8 + (lane >> 2);
-              if (mw + r < a.M)
-                *reinterpret_cast<uint4*>(stg + r * 80 + (lane & 3) * 16) =
-                    __ldg(reinterpret_cast<const uint4*>(rbase + (size_t)(mw + r) * rstride + sb * 64 + (lane & 3) * 16));
-            }
-            __syncwarp();
-            if (a.res_bf16) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 w = *reinterpret_cast<const uint4*>(stg + lane * 80 + j * 16);
-                v[8 * j] += __uint_as_float(w.x << 16); v[8 * j + 1] += __uint_as_float(w.x & 0xffff0000u);
-                v[8 * j + 2] += __uint_as_float(w.y << 16); v[8 * j + 3] += __uint_as_float(w.y & 0xffff0000u);
-                v[8 * j + 4] += __uint_as_float(w.z << 16); v[8 * j + 5] += __uint_as_float(w.z & 0xffff0000u);
-                v[8 * j + 6] += __uint_as_float(w.w << 16); v[8 * j + 7] += __uint_as_float(w.w & 0xffff0000u);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 w = *reinterpret_cast<const float4*>(stg + lane * 80 + j * 16);
-                float* t = v + (sb ? 16 : 0) + 4 * j;
-                t[0] += w.x; t[1] += w.y; t[2] += w.z; t[3] += w.w;
-              }
-            }
-            __syncwarp();
-          }
-        }
-        if (!keep) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        }
-        {
-          const int nsb = a.y_bf16 ? 1 : 2;
-          const size_t ystride = (size_t)a.N * (a.y_bf16 ? 2 : 4);
-          char* ybase = reinterpret_cast<char*>(a.Y) + (size_t)n0 * (a.y_bf16 ? 2 : 4);
-          for (int sb = 0; sb < nsb; ++sb) {
-            if (a.y_bf16) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint4*>(stg + lane * 80 + j * 16) =
-                    make_uint4(gr_pk2(v[8 * j], v[8 * j + 1]), gr_pk2(v[8 * j + 2], v[8 * j + 3]),
-                               gr_pk2(v[8 * j + 4], v[8 * j + 5]), gr_pk2(v[8 * j + 6], v[8 * j + 7]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float* t = v + (sb ? 16 : 0) + 4 * j;
-                *reinterpret_cast<float4*>(stg + lane * 80 + j * 16) = make_float4(t[0], t[1], t[2], t[3]);
-              }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {             // streaming stores: Y passes through L2 once
-              const int r = it * 8 + (lane >> 2);
-              if (mw + r < a.M)
-                __stcs(reinterpret_cast<uint4*>(ybase + (size_t)(mw + r) * ystride + sb * 64 + (lane & 3) * 16),
-                       *reinterpret_cast<const uint4*>(stg + r * 80 + (lane & 3) * 16));
-            }
-            __syncwarp();
-          }
-        }
+        gr_finish_group(v, stg, lane, mw, a.M, a.N, n0, a.res, a.res_bf16, keep, a.Y, a.y_bf16);
       }
       gr_fence_before();
       __syncwarp();
       if (lane == 0) gr_arrive(BAR_ACCF + 8 * tb);
+    }
+  }
+  gr_fence_before();
+  __syncthreads();
+  gr_fence_after();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
+
+// ------------------------------------------------------------------------------------------ fused feed-forward
+//   Y[M][256] = mask_rows( act( X[M][K1] . W1[256][K1]^T + b1 ) . W2[256][256]^T + b2 + residual )
+// TransformerEncoderLayer / TransformerBlock feed-forward (common/TransformerEncoder.py:73-76, TransformerBlock.py:30-32) in
+// one launch: the hidden activations [M][256] never leave the SM (84 MB written + 84 MB read per call at the BASELINE
+// shape otherwise).  Same roles and ring as gemm_rows_tc_kernel<1>; a unit = 128 rows runs KB1 = K1 / 64 ring stages of
+// (A gathered, W1 block) into accumulator 1 (TMEM columns 0-255), the epilogue warps turn it into the bf16 hidden tile -
+// written, 64-wide K block by K block, straight into the A halves of the four ring stages the second product uses (their
+// W halves receive the four W2 blocks meanwhile) - and four more stages accumulate hidden . W2^T into accumulator 2
+// (columns 256-511), whose epilogue (+ b2, residual, row mask, store) runs under the first product of the next unit.
+struct FfnRowsArgs {
+  const bf16* X; const bf16* W1p; const float* b1; const bf16* W2p; const float* b2;
+  long long M; int K1; int act;
+  const void* res; int res_bf16; const uint8_t* row_mask; void* Y; int y_bf16;
+};
+
+__global__ __launch_bounds__(GR_THREADS, 1) void ffn_rows_tc_kernel(const FfnRowsArgs a) {
+  constexpr int NS = GrCfg<1>::NS, STAGE = GrCfg<1>::STAGE, KB2 = GR_NC / GR_KB;      // 4 stages of 48 KB; 4 K blocks of the hidden
+  static_assert(KB2 == NS, "the hidden tile lives in the A halves of exactly one ring round");
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t s_bar = s_base + GR_RING;
+  const uint32_t BAR_A = s_bar, BAR_W = s_bar + 32, BAR_FREE = s_bar + 64, BAR_ACC1 = s_bar + 96, BAR_ACC2 = s_bar + 104,
+                 BAR_H = s_bar + 112, BAR_ACC2F = s_bar + 120;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + GR_RING + 192);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KB1 = a.K1 / GR_KB, KU = KB1 + KB2;          // ring iterations per unit
+  const long long total = (a.M + GR_M - 1) / GR_M;
+  const int nunit = (long long)blockIdx.x < total ? (int)((total - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  const int nit = nunit * KU;
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) {
+      gr_mbar_init(BAR_A + 8 * i, 128);
+      gr_mbar_init(BAR_W + 8 * i, 4);
+      gr_mbar_init(BAR_FREE + 8 * i, 1);
+    }
+    gr_mbar_init(BAR_ACC1, 1); gr_mbar_init(BAR_ACC2, 1);
+    gr_mbar_init(BAR_H, 8);                               // hidden tile written (8 epilogue warps) = accumulator 1 drained
+    gr_mbar_init(BAR_ACC2F, 8);                           // accumulator 2 drained
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  gr_fence_before();
+  __syncthreads();
+  gr_fence_after();
+  const uint32_t tmem = *s_tmem;
+  pdl_wait();
+
+  if (warp < 4) {
+    // ================= producers
+    const int w4 = warp;
+    const int rq = w4 * 4 + (lane >> 3), ch = lane & 7;
+    for (int it = 0; it < nit; ++it) {
+      const int g = it % NS, use = it / NS;
+      const uint32_t s_a = s_base + g * STAGE, s_w = s_a + GR_A_BYTES;
+      const int u = it / KU, j = it - u * KU;
+      const long long m0 = ((long long)blockIdx.x + (long long)u * gridDim.x) * GR_M;
+      if (use >= 1) gr_wait(BAR_FREE + 8 * g, (uint32_t)(use - 1) & 1u);
+      if (lane == 0) {
+        const char* wsrc = j < KB1 ? reinterpret_cast<const char*>(a.W1p) + (size_t)j * GR_W_BYTES
+                                   : reinterpret_cast<const char*>(a.W2p) + (size_t)(j - KB1) * GR_W_BYTES;
+        gr_expect_tx(BAR_W + 8 * g, GR_W_BYTES / 4);
+        gr_bulk(s_w + w4 * (GR_W_BYTES / 4), wsrc + (size_t)w4 * (GR_W_BYTES / 4), GR_W_BYTES / 4, BAR_W + 8 * g);
+      }
+      if (j < KB1) {                                     // second product: the A half is written by the epilogue warps
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 16 + rq;
+          const long long m = m0 + row;
+          const bf16* src = a.X + (size_t)(m < a.M ? m : 0) * a.K1 + j * GR_KB + ch * 8;
+          const uint32_t dst = s_a + (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4);
+          const int nbytes = m < a.M ? 16 : 0;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (it >= NS - 2) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(NS - 2) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        gr_arrive(BAR_A + 8 * ((it - (NS - 2)) % NS));
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int it = (nit > NS - 2 ? nit - (NS - 2) : 0); it < nit; ++it) gr_arrive(BAR_A + 8 * (it % NS));
+  } else if (warp == 12) {
+    // ================= MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = gr_idesc(GR_M, GR_NC);
+      int it = 0;
+      for (int u = 0; u < nunit; ++u) {
+        for (int j = 0; j < KU; ++j, ++it) {
+          const int g = it % NS;
+          const uint32_t par = (uint32_t)(it / NS) & 1u;
+          gr_wait(BAR_A + 8 * g, par);
+          gr_wait(BAR_W + 8 * g, par);
+          if (j == KB1) {
+            gr_wait(BAR_H, (uint32_t)u & 1u);            // hidden tile in place (and accumulator 1 drained)
+            if (u >= 1) gr_wait(BAR_ACC2F, (uint32_t)(u - 1) & 1u);      // accumulator 2 of the previous unit drained
+          }
+          gr_fence_after();
+          const uint32_t s_a = s_base + g * STAGE, s_w = s_a + GR_A_BYTES;
+          const bool second = j >= KB1;
+          const int jj = second ? j - KB1 : j;
+#pragma unroll
+          for (int ks = 0; ks < GR_KB / 16; ++ks) {
+            const int kc = ks * 2;
+            const uint64_t ad = gr_desc_sw128(s_a + ks * 32);
+            const uint64_t bd = gr_desc(s_w + kc * (GR_NC / 8) * 128, (GR_NC / 8) * 128, 128);
+            gr_umma(tmem + (second ? GR_NC : 0), ad, bd, idesc, (jj | ks) != 0);
+          }
+          gr_commit(BAR_FREE + 8 * g);
+          if (j == KB1 - 1) gr_commit(BAR_ACC1);
+          if (j == KU - 1) gr_commit(BAR_ACC2);
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps: hidden tile, then the output
+    const int q = warp & 3, hh = (warp - 4) >> 2;
+    unsigned char* stg = smem + GR_RING + 256 + (warp - 4) * GR_STG;
+    const int row = q * 32 + lane;                       // row of the tile = TMEM lane
+    for (int u = 0; u < nunit; ++u) {
+      const long long m = ((long long)blockIdx.x + (long long)u * gridDim.x) * GR_M + row;
+      const bool rowok = m < a.M;
+      const bool keep = rowok && (a.row_mask == nullptr || a.row_mask[m] != 0);
+      const long long mw = m - lane;
+      // ---- accumulator 1 -> act(. + b1) -> bf16 hidden tile in the A halves of the second product's stages
+      gr_wait(BAR_ACC1, (uint32_t)u & 1u);
+      gr_fence_after();
+      for (int cg = hh; cg < GR_NC / 32; cg += 2) {
+        uint32_t acc[32];
+        gr_tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cg * 32, acc);
+        gr_tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.b1 + cg * 32 + j));
+          v[j] = __uint_as_float(acc[j]) + b4.x; v[j + 1] = __uint_as_float(acc[j + 1]) + b4.y;
+          v[j + 2] = __uint_as_float(acc[j + 2]) + b4.z; v[j + 3] = __uint_as_float(acc[j + 3]) + b4.w;
+        }
+        if (a.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (a.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        const int g2 = (u * KU + KB1 + (cg >> 1)) % NS;  // the stage whose A half holds hidden columns 64 (cg >> 1) ..
+        unsigned char* hb = smem + g2 * STAGE + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const int kk8 = (cg & 1) * 4 + c4;             // 16-byte chunk of the 64-wide K block
+          *reinterpret_cast<uint4*>(hb + ((kk8 ^ (row & 7)) << 4)) =
+              make_uint4(gr_pk2(v[8 * c4], v[8 * c4 + 1]), gr_pk2(v[8 * c4 + 2], v[8 * c4 + 3]), gr_pk2(v[8 * c4 + 4], v[8 * c4 + 5]),
+                         gr_pk2(v[8 * c4 + 6], v[8 * c4 + 7]));
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
+      gr_fence_before();
+      __syncwarp();
+      if (lane == 0) gr_arrive(BAR_H);
+      // ---- accumulator 2 -> + b2, residual, row mask -> Y
+      gr_wait(BAR_ACC2, (uint32_t)u & 1u);
+      gr_fence_after();
+      for (int cg = hh; cg < GR_NC / 32; cg += 2) {
+        uint32_t acc[32];
+        gr_tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + GR_NC + cg * 32, acc);
+        gr_tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.b2 + cg * 32 + j));
+          v[j] = __uint_as_float(acc[j]) + b4.x; v[j + 1] = __uint_as_float(acc[j + 1]) + b4.y;
+          v[j + 2] = __uint_as_float(acc[j + 2]) + b4.z; v[j + 3] = __uint_as_float(acc[j + 3]) + b4.w;
+        }
+        gr_finish_group(v, stg, lane, mw, a.M, GR_NC, cg * 32, a.res, a.res_bf16, keep, a.Y, a.y_bf16);
+      }
+      gr_fence_before();
+      __syncwarp();
+      if (lane == 0) gr_arrive(BAR_ACC2F);
     }
   }
   gr_fence_before();
@@ -399,4 +596,28 @@ extern "C" int case_gemm_rows_tc(const void* X, const void* Wp, const float* bia
     launch_k(gemm_rows_tc_kernel<1>, grid, GR_THREADS, GR_SMEM, (cudaStream_t)stream, a);
   }
   return check_launch("case_gemm_rows_tc");
+}
+
+extern "C" int case_ffn_rows_tc(const void* X, const void* W1p, const float* b1, int K1, int act, const void* W2p, const float* b2,
+                                long long M, const void* residual, int residual_dtype, const uint8_t* row_mask, void* Y,
+                                int y_dtype, case_stream_t stream) {
+  CB_REQUIRE(X && W1p && b1 && W2p && b2 && Y && M > 0, "case_ffn_rows_tc: null pointer");
+  CB_REQUIRE(K1 > 0 && K1 % GR_KB == 0, "case_ffn_rows_tc: K1 must be a multiple of 64");
+  CB_REQUIRE(act == 1 || act == 2, "case_ffn_rows_tc: act is 1 (gelu) or 2 (relu)");
+  CB_REQUIRE(((uintptr_t)X % 16 == 0) && ((uintptr_t)W1p % 16 == 0) && ((uintptr_t)W2p % 16 == 0) && ((uintptr_t)Y % 16 == 0) &&
+                 ((uintptr_t)b1 % 16 == 0) && ((uintptr_t)b2 % 16 == 0) && ((uintptr_t)residual % 16 == 0),
+             "case_ffn_rows_tc: 16-byte alignment required");
+  CB_REQUIRE((y_dtype == CASE_F32 || y_dtype == CASE_BF16) && (!residual || residual_dtype == CASE_F32 || residual_dtype == CASE_BF16),
+             "case_ffn_rows_tc: dtypes are CASE_F32 / CASE_BF16");
+  FfnRowsArgs a;
+  a.X = (const bf16*)X; a.W1p = (const bf16*)W1p; a.b1 = b1; a.W2p = (const bf16*)W2p; a.b2 = b2; a.M = M; a.K1 = K1; a.act = act;
+  a.res = residual; a.res_bf16 = residual_dtype == CASE_BF16; a.row_mask = row_mask; a.Y = Y; a.y_bf16 = y_dtype == CASE_BF16;
+  const long long units = (M + GR_M - 1) / GR_M;
+  int dev = 0, nsm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  if (nsm <= 0) nsm = 148;
+  ensure_smem<ffn_rows_tc_kernel>(GR_SMEM);
+  launch_k(ffn_rows_tc_kernel, (unsigned)(units < nsm ? units : nsm), GR_THREADS, GR_SMEM, (cudaStream_t)stream, a);
+  return check_launch("case_ffn_rows_tc");
 }

@@ -117,6 +117,18 @@ class CaseProducers:
                y.data_ptr(), L.F32 if out32 else L.BF16, self._st())
         return y
 
+    def _ffn(self, x16, l1, l2, act, residual=None, row_mask=None):
+        """linear2(act(linear1(x))) (+ residual) (masked rows -> 0) -> fp32 [M, 256]: one launch (case_ffn_rows_tc), the hidden
+        activations stay on the SM.  cuBLAS mode: two _linear calls."""
+        if self.gemm == 'cublas' or l1.N != H or l2.N != H or l2.K != H:
+            return self._linear(self._linear(x16, l1, act=act), l2, residual=residual, row_mask=row_mask, out32=True)
+        M = x16.size(0)
+        y = torch.empty(M, H, dtype=torch.float32, device=self.device)
+        L.call('case_ffn_rows_tc', x16.data_ptr(), l1.wp.data_ptr(), l1.b.data_ptr(), l1.K, act, l2.wp.data_ptr(), l2.b.data_ptr(),
+               M, L.ptr(residual), (L.BF16 if residual.dtype == torch.bfloat16 else L.F32) if residual is not None else 0,
+               L.ptr(row_mask), y.data_ptr(), L.F32, self._st())
+        return y
+
     def _attention(self, qkv, kmask, nseq, Lx, C):
         out = torch.empty(nseq * Lx, C, dtype=torch.bfloat16, device=self.device)
         L.call('case_enc_attention', qkv.data_ptr(), kmask.data_ptr(), nseq, Lx, C, 8, out.data_ptr(), self._st())
@@ -136,8 +148,7 @@ class CaseProducers:
             att = self._attention(self._linear(a16, ly['att']['inp']), kmask, N, Lx, H)
             x = self._linear(att, ly['att']['out'], residual=a32, out32=True)      # src = src + attn
             b16, b32 = self._ln(x, ly['n2'], H, want32=True)                       # src = norm2(src)
-            hmid = self._linear(b16, ly['l1'], act=1)
-            x = self._linear(hmid, ly['l2'], residual=b32, out32=True)             # src = src + ffn
+            x = self._ffn(b16, ly['l1'], ly['l2'], 1, residual=b32)                # src = src + ffn
         return x
 
     def _block(self, bl, x, kmask, nseq, Lx):
@@ -147,8 +158,7 @@ class CaseProducers:
         att = self._attention(self._linear(a16, bl['att']['inp']), kmask, nseq, Lx, C)
         r3 = self._linear(att, bl['att']['out'], residual=x, out32=(C == H))       # reps_temp3 = reps_temp1 + attention
         n16, _ = self._ln(r3, bl['n2'], C)
-        hmid = self._linear(n16, bl['l1'], act=2)
-        return self._linear(hmid, bl['l2'], row_mask=kmask, out32=True)
+        return self._ffn(n16, bl['l1'], bl['l2'], 2, row_mask=kmask)
 
     def _interaction(self, w, Eq, Ep, qmask, pmask, B, NP, Lq, Lp):
         dev = self.device

@@ -511,6 +511,15 @@ int case_gemm_rows_tc(const void* X, const void* Wp, const float* bias, long lon
                       case_stream_t stream);
 size_t case_gemm_rows_packed_weight_bytes(int N, int K);
 
+/* Feed-forward of a TransformerEncoderLayer / TransformerBlock in one launch (common/TransformerEncoder.py:73-76,
+ * TransformerBlock.py:30-32):  Y[M][256] = mask_rows( act( X[M][K1] . W1^T + b1 ) . W2^T + b2 + residual ), hidden and output
+ * width 256; X bf16 row-major, W1p / W2p packed as for case_gemm_rows_tc ([K1/64][1][32 KB] and [4][1][32 KB]); act: 1 gelu
+ * (erf), 2 relu; residual [M][256] fp32 / bf16 or NULL; row_mask uint8 [M] or NULL; Y bf16 or fp32.  The hidden activations
+ * stay in shared memory (they become the A operand of the second product in place). */
+int case_ffn_rows_tc(const void* X, const void* W1p, const float* b1, int K1, int act, const void* W2p, const float* b2,
+                     long long M, const void* residual, int residual_dtype, const uint8_t* row_mask, void* Y, int y_dtype,
+                     case_stream_t stream);
+
 /* ---------------------------------------------------------------- whole-step orchestrators */
 
 typedef struct {

@@ -50,5 +50,36 @@ def main():
         print(f'{N:6d} {K:6d} {ep:>22} | {ms:8.3f} {fl / ms / 1e9:7.0f} | {ms2:9.3f} {fl / ms2 / 1e9:7.0f}')
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and not (len(sys.argv) > 1 and sys.argv[1] == 'ffn'):
     main()
+
+
+def ffn_main():
+    """The fused feed-forward against its two separate launches (same shapes as the producers' layers)."""
+    dev = torch.device('cuda')
+    M = 64 * 10 * 256
+    st = torch.cuda.current_stream().cuda_stream
+    print(f'{"K1":>6} {"epilogue":>22} | {"fused ms":>8} | {"lin1 + lin2 ms":>14}')
+    for K1, act, res in ((256, 1, 'f32'), (256, 2, None), (1280, 2, None)):
+        x = torch.randn(M, K1, device=dev).bfloat16()
+        l1 = _Linear(torch.randn(256, K1) / K1 ** 0.5, torch.randn(256) * 0.1, dev)
+        l2 = _Linear(torch.randn(256, 256) / 16, torch.randn(256) * 0.1, dev)
+        r = torch.randn(M, 256, device=dev) if res else None
+        rm = torch.ones(M, dtype=torch.uint8, device=dev)
+        y = torch.empty(M, 256, device=dev)
+        h = torch.empty(M, 256, dtype=torch.bfloat16, device=dev)
+
+        def fused():
+            L.call('case_ffn_rows_tc', x.data_ptr(), l1.wp.data_ptr(), l1.b.data_ptr(), K1, act, l2.wp.data_ptr(), l2.b.data_ptr(), M,
+                   L.ptr(r), L.F32 if res else 0, rm.data_ptr(), y.data_ptr(), L.F32, st)
+
+        def two():
+            L.call('case_gemm_rows_tc', x.data_ptr(), l1.wp.data_ptr(), l1.b.data_ptr(), M, 256, K1, act, None, 0, None, h.data_ptr(),
+                   L.BF16, st)
+            L.call('case_gemm_rows_tc', h.data_ptr(), l2.wp.data_ptr(), l2.b.data_ptr(), M, 256, 256, 0, L.ptr(r), L.F32 if res else 0,
+                   rm.data_ptr(), y.data_ptr(), L.F32, st)
+        print(f'{K1:6d} {"act=%d res=%s" % (act, res):>22} | {timeit(fused):8.3f} | {timeit(two):14.3f}')
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'ffn':
+    ffn_main()

@@ -111,6 +111,40 @@ def test_gemm_rows_tc_vs_torch(M, N, K, act, res, mask, out32):
         assert float(y[rm == 0].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize('M,K1,act,res,mask', [(300, 256, 1, 'f32', False), (1000, 1280, 2, None, True), (129, 64, 2, None, False),
+                                               (20000, 256, 2, None, True), (40000, 1280, 1, 'f32', True), (1, 128, 1, 'bf16', False)])
+def test_ffn_rows_tc_vs_torch(M, K1, act, res, mask):
+    """case_ffn_rows_tc (linear1 -> gelu / relu -> linear2 in one launch, hidden tile kept in shared memory) against torch
+    fp32 on the same bf16-rounded operands and a bf16-rounded hidden: 1 .. 20 K stages of the first product, partial last row
+    tile, more row tiles than CTAs, residual and row mask."""
+    from case_rg_b200 import _lib as L
+    from case_rg_b200.producers import _Linear
+    g = torch.Generator().manual_seed(M + K1)
+    x = torch.randn(M, K1, generator=g).to(DEV).bfloat16()
+    l1 = _Linear(torch.randn(H, K1, generator=g) / K1 ** 0.5, torch.randn(H, generator=g) * 0.1, torch.device(DEV))
+    l2 = _Linear(torch.randn(H, H, generator=g) / H ** 0.5, torch.randn(H, generator=g) * 0.1, torch.device(DEV))
+    r = None
+    if res:
+        r = torch.randn(M, H, generator=g).to(DEV)
+        r = r.bfloat16() if res == 'bf16' else r
+    rm = (torch.rand(M, generator=g) > 0.3).to(torch.uint8).to(DEV) if mask else None
+    y = torch.full((M, H), float('nan'), device=DEV)
+    L.call('case_ffn_rows_tc', x.data_ptr(), l1.wp.data_ptr(), l1.b.data_ptr(), K1, act, l2.wp.data_ptr(), l2.b.data_ptr(), M,
+           L.ptr(r), (L.BF16 if res == 'bf16' else L.F32) if res else 0, L.ptr(rm), y.data_ptr(), L.F32, _st())
+    torch.cuda.synchronize()
+    hid = x.float() @ l1.w16.float().t() + l1.b
+    hid = (F.gelu(hid) if act == 1 else torch.relu(hid)).bfloat16().float()
+    want = hid @ l2.w16.float().t() + l2.b
+    if r is not None:
+        want = want + r.float()
+    if rm is not None:
+        want = want * rm.view(-1, 1).float()
+    assert torch.isfinite(y).all()
+    assert rel(y, want) < 1e-3, rel(y, want)
+    if rm is not None and int((rm == 0).sum()) > 0:
+        assert float(y[rm == 0].abs().max()) == 0.0
+
+
 def _pipeline_inputs(B=3, Lq=20, NP=4, Lp=50, V=900, seed=5):
     sd = syn.make_case_producer_state(seed, V, H)
     inp = syn.make_case_inputs(seed + 1, B, Lq, NP, Lp, V, H)
