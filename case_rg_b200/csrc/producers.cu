@@ -151,12 +151,13 @@ __global__ __launch_bounds__(128) void enc_attention_kernel(const bf16* __restri
   extern __shared__ __align__(128) unsigned char sm[];
   bf16* Qs = reinterpret_cast<bf16*>(sm);
   bf16* KV = Qs + 64 * LD;                          // two stages of (K tile, V tile), 64 x LD each
-  uint8_t* msk = reinterpret_cast<uint8_t*>(KV + 4 * 64 * LD);     // [2][64]
+  float* msk = reinterpret_cast<float*>(KV + 4 * 64 * LD);         // [2][64] additive key bias: 0 (valid) or -inf (padding)
   pdl_wait();
   const int qt = blockIdx.x, h = blockIdx.y, seq = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
   const size_t row0 = (size_t)seq * L;
   const int ld = 3 * C;
+  const float sc2 = scale * 1.4426950408889634f;     // softmax in the base-2 domain
   // 16-byte cp.async with zero fill for the positions past the sequence
   auto cp16 = [](const bf16* dst, const bf16* src, bool ok) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(ok ? 16 : 0) : "memory");
@@ -171,7 +172,7 @@ __global__ __launch_bounds__(128) void enc_attention_kernel(const bf16* __restri
       cp16(Kd + r * LD + c * 8, src, ok);
       cp16(Vd + r * LD + c * 8, src + C, ok);
     }
-    if (tid < 64) { const int pos = kt * 64 + tid; msk[(kt & 1) * 64 + tid] = pos < L ? kmask[row0 + pos] : 0; }
+    if (tid < 64) { const int pos = kt * 64 + tid; msk[(kt & 1) * 64 + tid] = (pos < L && kmask[row0 + pos] != 0) ? 0.f : -INFINITY; }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   // Q tile, then the first key tile; the loop keeps one tile in flight behind the one it computes on
@@ -204,7 +205,7 @@ __global__ __launch_bounds__(128) void enc_attention_kernel(const bf16* __restri
     __syncthreads();
     const bf16* Ks = KV + (kt & 1) * 2 * 64 * LD;
     const bf16* Vs = Ks + 64 * LD;
-    const uint8_t* ms = msk + (kt & 1) * 64;
+    const float* ms = msk + (kt & 1) * 64;
     // ---- S = Q K^T for the 64 keys of the tile (8 n-tiles)
     float s[8][4];
 #pragma unroll
@@ -220,26 +221,27 @@ __global__ __launch_bounds__(128) void enc_attention_kernel(const bf16* __restri
         pa_mma(s[2 * np + 1], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b[2], b[3]);
       }
     }
-    // ---- mask, online softmax (rows g and g + 8; a row's 64 scores sit in the 4 lanes of a quad)
+    // ---- mask, online softmax (rows g and g + 8; a row's 64 scores sit in the 4 lanes of a quad).  Scores are taken to
+    // the base-2 domain with the padding mask in one FFMA each: t = s * (scale * log2 e) + bias_key (0 or -inf)
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const bool ok0 = ms[8 * nt + 2 * tq] != 0, ok1 = ms[8 * nt + 2 * tq + 1] != 0;
-      s[nt][0] = ok0 ? s[nt][0] * scale : -INFINITY; s[nt][1] = ok1 ? s[nt][1] * scale : -INFINITY;
-      s[nt][2] = ok0 ? s[nt][2] * scale : -INFINITY; s[nt][3] = ok1 ? s[nt][3] * scale : -INFINITY;
+      const float2 kb = *reinterpret_cast<const float2*>(ms + 8 * nt + 2 * tq);
+      s[nt][0] = fmaf(s[nt][0], sc2, kb.x); s[nt][1] = fmaf(s[nt][1], sc2, kb.y);
+      s[nt][2] = fmaf(s[nt][2], sc2, kb.x); s[nt][3] = fmaf(s[nt][3], sc2, kb.y);
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
       mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-    const float c0 = (m0 == -INFINITY) ? 0.f : fexp(m0 - mn0), c1 = (m1 == -INFINITY) ? 0.f : fexp(m1 - mn1);
+    const float c0 = (m0 == -INFINITY) ? 0.f : exp2f(m0 - mn0), c1 = (m1 == -INFINITY) ? 0.f : exp2f(m1 - mn1);
     const float e0 = (mn0 == -INFINITY) ? 0.f : mn0, e1 = (mn1 == -INFINITY) ? 0.f : mn1;   // all-masked tile: p = 0
     float rs0 = 0.f, rs1 = 0.f;
     uint32_t pf[4][4];                              // P as bf16 A fragments, k-step kk = keys 16 kk .. 16 kk + 15
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = fexp(s[nt][0] - e0), p1 = fexp(s[nt][1] - e0), p2 = fexp(s[nt][2] - e1), p3 = fexp(s[nt][3] - e1);
+      const float p0 = exp2f(s[nt][0] - e0), p1 = exp2f(s[nt][1] - e0), p2 = exp2f(s[nt][2] - e1), p3 = exp2f(s[nt][3] - e1);
       rs0 += p0 + p1; rs1 += p2 + p3;
       pf[nt >> 1][(nt & 1) * 2] = pk2(p0, p1);
       pf[nt >> 1][(nt & 1) * 2 + 1] = pk2(p2, p3);
@@ -679,7 +681,7 @@ extern "C" int case_enc_attention(const void* qkv, const uint8_t* kmask, int nse
   const float scale = 1.f / sqrtf((float)hd);
   dim3 grid((L + 63) / 64, nhead, nseq);
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = (size_t)5 * 64 * (hd + 8) * 2 + 128;
+  const size_t smem = (size_t)5 * 64 * (hd + 8) * 2 + 512;
   if (hd == 32) {
     launch_k(enc_attention_kernel<32>, grid, 128, smem, st, (const bf16*)qkv, kmask, L, C, scale, (bf16*)out);
   } else {
