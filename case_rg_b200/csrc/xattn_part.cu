@@ -205,6 +205,7 @@ __global__ __launch_bounds__(XP_WARPS * 32) void cross_attn_part_kernel(
       const float scale = (m == -INFINITY) ? 0.f : fexp(m - mn);
       m = mn;
       l *= scale;
+      const float mnl = -mn * 1.4426950408889634f;
 #pragma unroll
       for (int nb = 0; nb < 4; ++nb) { o[nb][0] *= scale; o[nb][1] *= scale; }
 #pragma unroll
@@ -212,8 +213,9 @@ __global__ __launch_bounds__(XP_WARPS * 32) void cross_attn_part_kernel(
         float p[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const float sv = sc[2 * kk + (u >> 1)][u & 1];
-          p[u] = (sv == -INFINITY) ? 0.f : fexp(sv - mn);
+          // exp(sv - mn) as one FFMA + ex2; a key past the end has sv = -inf -> 0 (mn is finite: every tile of the
+          // compacted stream holds at least one valid key)
+          p[u] = exp2f(fmaf(sc[2 * kk + (u >> 1)][u & 1], 1.4426950408889634f, mnl));
           l += p[u];
         }
         const uint32_t pa0 = xp_pack(p[0], p[1]), pa2 = xp_pack(p[2], p[3]);
