@@ -194,11 +194,19 @@ __global__ __launch_bounds__(XP_WARPS * 32) void cross_attn_part_kernel(
         float c[4] = {0.f, 0.f, 0.f, 0.f};
         xp_mma(c, qa[0][0], 0u, qa[0][1], 0u, kf[0], kf[1]);
         xp_mma(c, qa[1][0], 0u, qa[1][1], 0u, kf[2], kf[3]);
-        const int kcol = kb * 8 + 2 * t4;
-        sc[kb][0] = kcol < nkey ? c[0] : -INFINITY;
-        sc[kb][1] = kcol + 1 < nkey ? c[1] : -INFINITY;
-        tmax = fmaxf(tmax, fmaxf(sc[kb][0], sc[kb][1]));
+        sc[kb][0] = c[0];
+        sc[kb][1] = c[1];
       }
+      if (nkey < XP_TILE) {                      // only the last tile of a query has keys past its end (warp-uniform)
+#pragma unroll
+        for (int kb = 0; kb < XP_TILE / 8; ++kb) {
+          const int kcol = kb * 8 + 2 * t4;
+          if (kcol >= nkey) sc[kb][0] = -INFINITY;
+          if (kcol + 1 >= nkey) sc[kb][1] = -INFINITY;
+        }
+      }
+#pragma unroll
+      for (int kb = 0; kb < XP_TILE / 8; ++kb) tmax = fmaxf(tmax, fmaxf(sc[kb][0], sc[kb][1]));
       tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
       tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 2));
       const float mn = fmaxf(m, tmax);
