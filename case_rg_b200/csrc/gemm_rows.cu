@@ -10,16 +10,18 @@
 // while the epilogue drains the other half; MT = 2 (wide 1280-deep layers): both halves hold the unit's two accumulators,
 // one W stage feeds 256 rows.  The K loop runs over a ring of (MT A tiles 128 x 64, W tile 256 x 64) stages - 4 x 48 KB or
 // 3 x 64 KB - that runs on across units:
-//   warps 0-3        producers: the A tiles are gathered with 16-byte cp.async (8 MT per thread and stage, a full 128-byte line
-//                    per quarter warp; rows past M are zero-filled) into the 128-byte-swizzle K-major layout
-//                    (conflict-free on the shared-memory side), the pre-packed W tile arrives as four bulk copies; a
-//                    stage is handed to the tensor core two iterations after its copies were issued
-//                    (cp.async.wait_group), so the other stages' gathers are in flight behind the one being multiplied
-//   warp 12          MMA issuer (one thread): 4 MT tcgen05.mma (M = 128, N = 256, K = 16) per stage; tcgen05.commit signals
+//   warp 0           producer (one thread): per stage one TMA tensor load of the X box (64 k x 128 MT rows; the tensor map
+//                    carries the 128-byte swizzle the UMMA descriptor of the A operand expects, rows past M arrive as
+//                    zeros) and one bulk copy of the pre-packed W tile, both credited to the stage's "full" mbarrier
+//   warp 1           MMA issuer (one thread): 4 MT tcgen05.mma (M = 128, N = 256, K = 16) per stage; tcgen05.commit signals
 //                    "stage free" and "accumulator complete"
-//   warps 4-11       epilogue: tcgen05.ld (lane = row, 32 columns at a time), bias / gelu / relu / residual / row mask,
+//   warps 2-9        epilogue: tcgen05.ld (lane = row, 32 columns at a time), bias / gelu / relu / residual / row mask,
 //                    residual loads and output stores staged through shared memory so that global memory sees whole
 //                    sectors (4 lanes per row, 64 contiguous bytes)
+// (First versions gathered A with 16-byte cp.async from four producer warps: 552 TFLOP/s with a no-swizzle layout - half-used
+// sectors, L1TEX-bound - 1.0-1.19 PFLOP/s with the swizzled layout; the TMA load reaches 1.25 PFLOP/s on 3840 x 1280.)
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace cb {
@@ -35,7 +37,7 @@ template <int MT> struct GrCfg {
   static constexpr int NS = MT == 1 ? 4 : 3;
   static constexpr int STAGE = MT * GR_A_BYTES + GR_W_BYTES;
 };
-constexpr int GR_THREADS = 13 * 32;
+constexpr int GR_THREADS = 10 * 32;                  // warp 0: producer, warp 1: MMA issuer, warps 2-9: epilogue
 constexpr int GR_STG = 32 * 80;                       // epilogue staging block of a warp: 32 rows x (64 + 16) bytes
 constexpr int GR_RING = 192 * 1024;                   // NS x STAGE for both configurations
 constexpr int GR_SMEM = GR_RING + 256 + 8 * GR_STG;
@@ -52,6 +54,13 @@ __device__ __forceinline__ void gr_arrive(uint32_t bar) {
 __device__ __forceinline__ void gr_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// 2-D TMA tile load (box of the tensor map at element coordinates (c0 = k, c1 = row)) into shared memory; the bytes of the
+// whole box - rows past the end of the tensor arrive as zeros - are credited to the mbarrier
+__device__ __forceinline__ void gr_tma_2d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
                : "memory");
 }
 __device__ __forceinline__ void gr_wait(uint32_t bar, uint32_t parity) {
@@ -195,7 +204,7 @@ struct GemmRowsArgs {
 };
 
 template <int MT>
-__global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmRowsArgs a) {
+__global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmRowsArgs a, const __grid_constant__ CUtensorMap tmA) {
   constexpr int GR_NS = GrCfg<MT>::NS, GR_STAGE = GrCfg<MT>::STAGE;
   static_assert(GR_NS * GR_STAGE == GR_RING, "ring size");
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -219,8 +228,8 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
 
   if (tid == 0) {
     for (int i = 0; i < GR_NS; ++i) {
-      gr_mbar_init(BAR_A + 8 * i, 128);                 // A tiles of the stage gathered (128 producer threads)
-      gr_mbar_init(BAR_W + 8 * i, 4);                   // W tile landed (4 issuing lanes + bytes)
+      gr_mbar_init(BAR_A + 8 * i, 1);                   // stage full: one issuing thread + the bytes of the A box and the W tile
+      gr_mbar_init(BAR_W + 8 * i, 1);                   // (unused)
       gr_mbar_init(BAR_FREE + 8 * i, 1);                // the MMAs that read the stage are done
     }
     gr_mbar_init(BAR_ACC, 1); gr_mbar_init(BAR_ACC + 8, 1);                       // accumulator slot complete
@@ -237,47 +246,25 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
   const uint32_t tmem = *s_tmem;
   pdl_wait();
 
-  if (warp < 4) {
-    // ================= producers (4 warps): a stage is handed over GR_NS - 2 iterations after its copies were issued
-    const int w4 = warp;
-    // gather role: a quarter warp (8 lanes) copies one 128-byte run of a source row - one full cache line per request - into
-    // the 128-byte-swizzle layout, where its eight 16-byte chunks land in eight different bank groups
-    const int rq = w4 * 4 + (lane >> 3), ch = lane & 7;
-    for (int it = 0; it < nit; ++it) {
-      const int g = it % GR_NS, use = it / GR_NS;
-      const uint32_t s_a = s_base + g * GR_STAGE, s_w = s_a + MT * GR_A_BYTES;
-      const int u = it / KB, kb = it - u * KB;
-      const long long ug = (long long)blockIdx.x + (long long)u * gridDim.x;
-      const long long mt = ug / nchunk;
-      const int c = (int)(ug - mt * nchunk);
-      const long long m0 = mt * (MT * GR_M);
-      if (use >= 1) gr_wait(BAR_FREE + 8 * g, (uint32_t)(use - 1) & 1u);        // the MMAs of this stage's previous use are done
-      if (lane == 0) {
-        const char* src = reinterpret_cast<const char*>(a.Wp) + ((size_t)kb * nchunk + c) * GR_W_BYTES + (size_t)w4 * (GR_W_BYTES / 4);
-        gr_expect_tx(BAR_W + 8 * g, GR_W_BYTES / 4);
-        gr_bulk(s_w + w4 * (GR_W_BYTES / 4), src, GR_W_BYTES / 4, BAR_W + 8 * g);
-      }
-#pragma unroll
-      for (int i = 0; i < 8 * MT; ++i) {
-        const int row = i * 16 + rq;                     // 0 .. 128 MT - 1; tile = row >> 7
-        const long long m = m0 + row;
-        const bf16* src = a.X + (size_t)(m < a.M ? m : 0) * a.K + kb * GR_KB + ch * 8;
-        const uint32_t dst = s_a + (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4);
-        const int nbytes = m < a.M ? 16 : 0;             // rows past M are zero-filled
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      if (it >= GR_NS - 2) {                             // GR_NS - 1 gathers stay in flight behind the one handed over
-        asm volatile("cp.async.wait_group %0;" ::"n"(GR_NS - 2) : "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-        gr_arrive(BAR_A + 8 * ((it - (GR_NS - 2)) % GR_NS));
+  if (warp == 0) {
+    // ================= producer: one thread feeds the ring - a TMA box (MT x 128 rows x 64 k of X, landed in the 128-byte-
+    // swizzle K-major layout by the copy engine; rows past M arrive as zeros) and the pre-packed W tile as a bulk copy, both
+    // credited to the stage's "full" barrier
+    if (lane == 0) {
+      for (int it = 0; it < nit; ++it) {
+        const int g = it % GR_NS, use = it / GR_NS;
+        const uint32_t s_a = s_base + g * GR_STAGE, s_w = s_a + MT * GR_A_BYTES;
+        const int u = it / KB, kb = it - u * KB;
+        const long long ug = (long long)blockIdx.x + (long long)u * gridDim.x;
+        const long long mt = ug / nchunk;
+        const int c = (int)(ug - mt * nchunk);
+        if (use >= 1) gr_wait(BAR_FREE + 8 * g, (uint32_t)(use - 1) & 1u);      // the MMAs of this stage's previous use are done
+        gr_expect_tx(BAR_A + 8 * g, MT * GR_A_BYTES + GR_W_BYTES);
+        gr_tma_2d(s_a, &tmA, kb * GR_KB, (int)(mt * (MT * GR_M)), BAR_A + 8 * g);
+        gr_bulk(s_w, reinterpret_cast<const char*>(a.Wp) + ((size_t)kb * nchunk + c) * GR_W_BYTES, GR_W_BYTES, BAR_A + 8 * g);
       }
     }
-    // drain: the last GR_NS - 2 stages
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (int it = (nit > GR_NS - 2 ? nit - (GR_NS - 2) : 0); it < nit; ++it) gr_arrive(BAR_A + 8 * (it % GR_NS));
-  } else if (warp == 12) {
+  } else if (warp == 1) {
     // ================= MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = gr_idesc(GR_M, GR_NC);
@@ -288,7 +275,6 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
           const int g = it % GR_NS;
           const uint32_t par = (uint32_t)(it / GR_NS) & 1u;
           gr_wait(BAR_A + 8 * g, par);
-          gr_wait(BAR_W + 8 * g, par);
           gr_fence_after();
           const uint32_t s_a = s_base + g * GR_STAGE, s_w = s_a + MT * GR_A_BYTES;
 #pragma unroll
@@ -314,10 +300,10 @@ __global__ __launch_bounds__(GR_THREADS, 1) void gemm_rows_tc_kernel(const GemmR
       }
     }
   } else {
-    // ================= epilogue (warps 4-11): warp & 3 = TMEM lane quarter; hh = (warp - 4) >> 2 is, for MT = 1, the parity
+    // ================= epilogue (warps 2-9): warp & 3 = TMEM lane quarter; hh = (warp - 2) >> 2 is, for MT = 1, the parity
     // of the 32-column groups the warp takes and, for MT = 2, the row tile (= accumulator slot) it drains
-    const int q = warp & 3, hh = (warp - 4) >> 2;
-    unsigned char* stg = smem + GR_RING + 256 + (warp - 4) * GR_STG;      // this warp's staging block
+    const int q = warp & 3, hh = (warp - 2) >> 2;
+    unsigned char* stg = smem + GR_RING + 256 + (warp - 2) * GR_STG;      // this warp's staging block
     for (int u = 0; u < nunit; ++u) {
       const long long ug = (long long)blockIdx.x + (long long)u * gridDim.x;
       const long long mt = ug / nchunk;
@@ -377,7 +363,7 @@ struct FfnRowsArgs {
   const void* res; int res_bf16; const uint8_t* row_mask; void* Y; int y_bf16;
 };
 
-__global__ __launch_bounds__(GR_THREADS, 1) void ffn_rows_tc_kernel(const FfnRowsArgs a) {
+__global__ __launch_bounds__(GR_THREADS, 1) void ffn_rows_tc_kernel(const FfnRowsArgs a, const __grid_constant__ CUtensorMap tmA) {
   constexpr int NS = GrCfg<1>::NS, STAGE = GrCfg<1>::STAGE, KB2 = GR_NC / GR_KB;      // 4 stages of 48 KB; 4 K blocks of the hidden
   static_assert(KB2 == NS, "the hidden tile lives in the A halves of exactly one ring round");
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -394,8 +380,8 @@ __global__ __launch_bounds__(GR_THREADS, 1) void ffn_rows_tc_kernel(const FfnRow
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
-      gr_mbar_init(BAR_A + 8 * i, 128);
-      gr_mbar_init(BAR_W + 8 * i, 4);
+      gr_mbar_init(BAR_A + 8 * i, 1);                     // stage full: one issuing thread + bytes
+      gr_mbar_init(BAR_W + 8 * i, 1);                     // (unused)
       gr_mbar_init(BAR_FREE + 8 * i, 1);
     }
     gr_mbar_init(BAR_ACC1, 1); gr_mbar_init(BAR_ACC2, 1);
@@ -413,44 +399,27 @@ __global__ __launch_bounds__(GR_THREADS, 1) void ffn_rows_tc_kernel(const FfnRow
   const uint32_t tmem = *s_tmem;
   pdl_wait();
 
-  if (warp < 4) {
-    // ================= producers
-    const int w4 = warp;
-    const int rq = w4 * 4 + (lane >> 3), ch = lane & 7;
-    for (int it = 0; it < nit; ++it) {
-      const int g = it % NS, use = it / NS;
-      const uint32_t s_a = s_base + g * STAGE, s_w = s_a + GR_A_BYTES;
-      const int u = it / KU, j = it - u * KU;
-      const long long m0 = ((long long)blockIdx.x + (long long)u * gridDim.x) * GR_M;
-      if (use >= 1) gr_wait(BAR_FREE + 8 * g, (uint32_t)(use - 1) & 1u);
-      if (lane == 0) {
-        const char* wsrc = j < KB1 ? reinterpret_cast<const char*>(a.W1p) + (size_t)j * GR_W_BYTES
-                                   : reinterpret_cast<const char*>(a.W2p) + (size_t)(j - KB1) * GR_W_BYTES;
-        gr_expect_tx(BAR_W + 8 * g, GR_W_BYTES / 4);
-        gr_bulk(s_w + w4 * (GR_W_BYTES / 4), wsrc + (size_t)w4 * (GR_W_BYTES / 4), GR_W_BYTES / 4, BAR_W + 8 * g);
-      }
-      if (j < KB1) {                                     // second product: the A half is written by the epilogue warps
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = i * 16 + rq;
-          const long long m = m0 + row;
-          const bf16* src = a.X + (size_t)(m < a.M ? m : 0) * a.K1 + j * GR_KB + ch * 8;
-          const uint32_t dst = s_a + (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4);
-          const int nbytes = m < a.M ? 16 : 0;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+  if (warp == 0) {
+    // ================= producer (one thread): first product - TMA box of X + W1 block; second product - the W2 block only
+    // (its A half is written by the epilogue warps)
+    if (lane == 0) {
+      for (int it = 0; it < nit; ++it) {
+        const int g = it % NS, use = it / NS;
+        const uint32_t s_a = s_base + g * STAGE, s_w = s_a + GR_A_BYTES;
+        const int u = it / KU, j = it - u * KU;
+        const long long m0 = ((long long)blockIdx.x + (long long)u * gridDim.x) * GR_M;
+        if (use >= 1) gr_wait(BAR_FREE + 8 * g, (uint32_t)(use - 1) & 1u);
+        if (j < KB1) {
+          gr_expect_tx(BAR_A + 8 * g, GR_A_BYTES + GR_W_BYTES);
+          gr_tma_2d(s_a, &tmA, j * GR_KB, (int)m0, BAR_A + 8 * g);
+          gr_bulk(s_w, reinterpret_cast<const char*>(a.W1p) + (size_t)j * GR_W_BYTES, GR_W_BYTES, BAR_A + 8 * g);
+        } else {
+          gr_expect_tx(BAR_A + 8 * g, GR_W_BYTES);
+          gr_bulk(s_w, reinterpret_cast<const char*>(a.W2p) + (size_t)(j - KB1) * GR_W_BYTES, GR_W_BYTES, BAR_A + 8 * g);
         }
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      if (it >= NS - 2) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(NS - 2) : "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        gr_arrive(BAR_A + 8 * ((it - (NS - 2)) % NS));
-      }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (int it = (nit > NS - 2 ? nit - (NS - 2) : 0); it < nit; ++it) gr_arrive(BAR_A + 8 * (it % NS));
-  } else if (warp == 12) {
+  } else if (warp == 1) {
     // ================= MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = gr_idesc(GR_M, GR_NC);
@@ -460,7 +429,6 @@ __global__ __launch_bounds__(GR_THREADS, 1) void ffn_rows_tc_kernel(const FfnRow
           const int g = it % NS;
           const uint32_t par = (uint32_t)(it / NS) & 1u;
           gr_wait(BAR_A + 8 * g, par);
-          gr_wait(BAR_W + 8 * g, par);
           if (j == KB1) {
             gr_wait(BAR_H, (uint32_t)u & 1u);            // hidden tile in place (and accumulator 1 drained)
             if (u >= 1) gr_wait(BAR_ACC2F, (uint32_t)(u - 1) & 1u);      // accumulator 2 of the previous unit drained
@@ -484,8 +452,8 @@ __global__ __launch_bounds__(GR_THREADS, 1) void ffn_rows_tc_kernel(const FfnRow
     }
   } else {
     // ================= epilogue warps: hidden tile, then the output
-    const int q = warp & 3, hh = (warp - 4) >> 2;
-    unsigned char* stg = smem + GR_RING + 256 + (warp - 4) * GR_STG;
+    const int q = warp & 3, hh = (warp - 2) >> 2;
+    unsigned char* stg = smem + GR_RING + 256 + (warp - 2) * GR_STG;
     const int row = q * 32 + lane;                       // row of the tile = TMEM lane
     for (int u = 0; u < nunit; ++u) {
       const long long m = ((long long)blockIdx.x + (long long)u * gridDim.x) * GR_M + row;
@@ -558,6 +526,37 @@ __global__ __launch_bounds__(GR_THREADS, 1) void ffn_rows_tc_kernel(const FfnRow
 
 using namespace cb;
 
+// TMA descriptor of X [M][K] bf16 row-major: boxes of 64 k x box_rows rows, 128-byte swizzle (what the UMMA descriptors of the
+// A operand expect), zero fill past the end.  cuTensorMapEncodeTiled is fetched through the runtime (no libcuda link).
+static int gr_make_tmap(CUtensorMap* tm, const void* X, long long M, int K, int box_rows) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn enc = nullptr;
+  if (enc == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr ||
+        qres != cudaDriverEntryPointSuccess) {
+      cb::set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return (int)cudaErrorNotSupported;
+    }
+    enc = (encode_fn)fn;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
+  const cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)GR_KB, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(X), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    cb::set_error("cuTensorMapEncodeTiled failed for the row GEMM's X operand");
+    return (int)cudaErrorNotSupported;
+  }
+  return 0;
+}
+
 /* packed weight bytes for an [N][K] Linear: K / 64 blocks x N / 256 tiles of 32 KB */
 extern "C" size_t case_gemm_rows_packed_weight_bytes(int N, int K) {
   return (size_t)(K / GR_KB) * ((N + GR_NC - 1) / GR_NC) * GR_W_BYTES;
@@ -588,12 +587,14 @@ extern "C" int case_gemm_rows_tc(const void* X, const void* Wp, const float* bia
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   if (nsm <= 0) nsm = 148;
   const unsigned grid = (unsigned)(units < nsm ? units : nsm);
+  CUtensorMap tm;
+  if (int rc = gr_make_tmap(&tm, X, M, K, (mt2 ? 2 : 1) * GR_M)) return rc;
   if (mt2) {
     ensure_smem<gemm_rows_tc_kernel<2>>(GR_SMEM);
-    launch_k(gemm_rows_tc_kernel<2>, grid, GR_THREADS, GR_SMEM, (cudaStream_t)stream, a);
+    launch_k(gemm_rows_tc_kernel<2>, grid, GR_THREADS, GR_SMEM, (cudaStream_t)stream, a, tm);
   } else {
     ensure_smem<gemm_rows_tc_kernel<1>>(GR_SMEM);
-    launch_k(gemm_rows_tc_kernel<1>, grid, GR_THREADS, GR_SMEM, (cudaStream_t)stream, a);
+    launch_k(gemm_rows_tc_kernel<1>, grid, GR_THREADS, GR_SMEM, (cudaStream_t)stream, a, tm);
   }
   return check_launch("case_gemm_rows_tc");
 }
@@ -617,7 +618,9 @@ extern "C" int case_ffn_rows_tc(const void* X, const void* W1p, const float* b1,
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   if (nsm <= 0) nsm = 148;
+  CUtensorMap tm;
+  if (int rc = gr_make_tmap(&tm, X, M, K1, GR_M)) return rc;
   ensure_smem<ffn_rows_tc_kernel>(GR_SMEM);
-  launch_k(ffn_rows_tc_kernel, (unsigned)(units < nsm ? units : nsm), GR_THREADS, GR_SMEM, (cudaStream_t)stream, a);
+  launch_k(ffn_rows_tc_kernel, (unsigned)(units < nsm ? units : nsm), GR_THREADS, GR_SMEM, (cudaStream_t)stream, a, tm);
   return check_launch("case_ffn_rows_tc");
 }
