@@ -51,6 +51,16 @@ def test_sass_is_sm100a_only():
     assert archs == {'sm_100a'}, archs
 
 
+def test_sass_carries_the_blackwell_instructions_the_design_claims():
+    """SASS of the shipped library: tcgen05 MMAs (UTCHMMA) with TMEM loads (LDTM), TMA tensor loads (UTMALDG) of the
+    producers' GEMM operands, bulk copies (UBLKCP) of the pre-packed tiles, cluster DSMEM stores of the layer kernels -
+    and no Hopper wgmma."""
+    out = subprocess.run(['cuobjdump', '-sass', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ('UTCHMMA', 'LDTM', 'UTMALDG', 'UBLKCP', 'HMMA.16816'):
+        assert mnemonic in out, mnemonic
+    assert 'HGMMA' not in out and 'WGMMA' not in out.upper().replace('UTCHMMA', '')
+
+
 def test_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip('GPU present')
