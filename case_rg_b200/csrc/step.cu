@@ -453,7 +453,22 @@ extern "C" int gttp_decode_step(const gttp_step_args_t* a, int t, case_stream_t 
   }
   TRY(case_vocab_gemm(a->feat, a->Wv, a->bv, a->logits, R, a->V, a->ldv, dt, a->vocab_impl, a->vocab_ws, st));
   TRY(case_gttp_gates(a->feat, a->wc, a->bc, a->gates, a->fac, CASE_MAX_SPLIT, ns[1], R, st));
-  if (use_tail && a->V <= case_row_tail_max_vocab()) {
+  // search path: the sparse tail of the CaSE step (base statistics of the logits + the copy mass hashed by vocabulary id,
+  // accumulated in fixed point: the top-k never needs the [R, V] mixture and is reproducible run to run)
+  const int k2 = 2 * W <= 2 * CASE_MAX_W ? 2 * W : 2 * CASE_MAX_W;
+  const bool sparse = use_tail && !(opt & CASE_OPT_DENSE_TAIL) && !a->materialize_only && a->base_ms && a->base_e && a->base_i &&
+                      a->V >= k2 && a->Lb <= case_sparse_tail_max_sources();
+  if (sparse) {
+    TRY(case_vocab_base(a->logits, a->ldv, R, a->V, 1, k2, a->base_ms, a->base_e, a->base_i, st));
+    case_tail_args_t ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.R = R; ta.V = a->V; ta.W = W; ta.K = W; ta.ldl = a->ldv; ta.ldd = a->ldv; ta.mask_col0 = 1; ta.nmem = 1;
+    ta.do_finalize = 0; ta.fac_ld = CASE_MAX_SPLIT; ta.map_ld = a->map_ld;
+    ta.logits = a->logits; ta.gates = a->gates; ta.fac = a->fac; ta.map = a->map;
+    ta.S[0] = a->Lb; ta.attn_un[0] = a->attn_un[1];
+    ta.top_vals = a->top_vals; ta.top_idx = a->top_idx;
+    TRY(case_sparse_tail(&ta, a->base_ms, a->base_e, a->base_i, k2, nullptr, nullptr, st));
+  } else if (use_tail && a->V <= case_row_tail_max_vocab()) {
     case_tail_args_t ta;
     memset(&ta, 0, sizeof(ta));
     ta.R = R; ta.V = a->V; ta.W = W; ta.K = W; ta.ldl = a->ldv; ta.ldd = a->ldv; ta.mask_col0 = 1; ta.nmem = 1;

@@ -751,6 +751,8 @@ class GttpDecodeEngine(_EngineBase):
         self.logits, self.dist = z(R, self.ldv), z(R, self.ldv)
         self.top_vals = z(R, W)
         self.top_idx = torch.zeros(R, W, dtype=torch.int32, device=dev)
+        self.base_ms, self.base_e = z(R, 4, 2), z(R, 4, 16)          # case_vocab_base statistics (sparse tail)
+        self.base_i = torch.zeros(R, 4, 16, dtype=torch.int32, device=dev)
         self._graphs = {}
         self._step_fn = L.load().gttp_decode_step
         self._step_name = 'gttp_decode_step'
@@ -777,7 +779,8 @@ class GttpDecodeEngine(_EngineBase):
         for i in range(2):
             a.attn_un[i], a.stats[i], a.ctxp[i], a.ctx[i] = (self.attn_un[i].data_ptr(), self.stats[i].data_ptr(),
                                                              self.ctxp[i].data_ptr(), self.ctx[i].data_ptr())
-        for n in ('emb', 'qa', 'gi', 'gh', 'feat', 'gates', 'fac', 'logits', 'dist', 'top_vals', 'top_idx'):
+        for n in ('emb', 'qa', 'gi', 'gh', 'feat', 'gates', 'fac', 'logits', 'dist', 'top_vals', 'top_idx', 'base_ms', 'base_e',
+                  'base_i'):
             setattr(a, n, getattr(self, n).data_ptr())
 
     @torch.no_grad()
@@ -823,5 +826,7 @@ class GttpDecodeEngine(_EngineBase):
         self.gstate[1].zero_()
 
     def kernel_launches_per_step(self) -> int:
-        # embed, 2 x (query linear, additive, merge), gi, gh, gru, readout, vocab, gates, row_tail, select
-        return 1 + 2 * 3 + 3 + 1 + 1 + 1 + 1 + 1
+        # embed, 2 x (query linear, additive, merge), gi, gh, gru, readout, vocab, gates, vocab_base + sparse_tail (or the
+        # dense row_tail), select
+        sparse = not (self.args.opt & (L.OPT_DENSE_TAIL | L.OPT_UNFUSED_TAIL)) and self.Lb <= L.load().case_sparse_tail_max_sources()
+        return 1 + 2 * 3 + 3 + 1 + 1 + 1 + (2 if sparse else 1) + 1

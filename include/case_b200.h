@@ -597,7 +597,10 @@ typedef struct {
   float* gi; float* gh; float* feat; float* gates; float* fac; float* logits; float* dist;
   float* top_vals; int32_t* top_idx;
   void* vocab_ws;
-  int32_t opt;                                           /* CASE_OPT_NO_PDL / CASE_OPT_UNFUSED_TAIL */
+  int32_t opt;                                           /* CASE_OPT_NO_PDL / CASE_OPT_UNFUSED_TAIL / CASE_OPT_DENSE_TAIL */
+  /* statistics of case_vocab_base for the sparse tail (search path): base_ms [R][4][2], base_e / base_i [R][4][16];
+   * NULL: the dense case_row_tail is used */
+  float* base_ms; float* base_e; int32_t* base_i;
 } gttp_step_args_t;
 
 /* One GTTP decode step (GTTP/Model.py:176-193 -> BBCDecoder.forward :113-131 ->

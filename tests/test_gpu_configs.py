@@ -127,9 +127,9 @@ def test_streamed_batches_equal_single_calls():
 
 
 def test_streamed_gttp_batches_equal_single_calls():
-    """The same streaming face over GTTP batches (beam and protocol greedy): answers equal the one-call-per-batch path.
-    GTTP's row tail sums the copy mass of repeated ids with float atomics, so two decodes of one batch may differ on an
-    exact tie - the comparison allows a token or two."""
+    """The same streaming face over GTTP batches (beam and protocol greedy): answers equal the one-call-per-batch path,
+    token for token (the GTTP search path runs on the sparse tail, whose copy mass is accumulated in fixed point, so a
+    decode is reproducible run to run)."""
     from case_rg_b200 import generations as FG
     V, T, W, B = 2000, 8, 4, 5
     sd = syn.make_gttp_state(91, V, 256, 256)
@@ -144,11 +144,11 @@ def test_streamed_gttp_batches_equal_single_calls():
     assert len(got) == len(want)
     for g, w in zip(got, want):
         n = min(g.size(1), w.size(1))
-        assert g.device.type == 'cpu' and (g[:, :n] == w[:, :n]).float().mean() > 0.95, (g, w)
+        assert g.device.type == 'cpu' and g.shape == w.shape and torch.equal(g[:, :n], w[:, :n]), (g, w)
     want = [FG.greedy(model, {k: v.cuda() for k, v in h.items()}, None, T).cpu() for h in hosts]
     got = list(FG.greedy_batches(model, iter(hosts), None, T))
     for g, w in zip(got, want):
-        assert (g == w).float().mean() > 0.95, (g, w)
+        assert torch.equal(g, w), (g, w)
 
 
 @pytest.mark.timeout(300)
