@@ -90,7 +90,7 @@ class GttpStepArgs(C.Structure):
                                   'out_tokens', 'n_live', 'emb', 'qa')] + \
                [('attn_un', vp * 2), ('stats', vp * 2), ('ctxp', vp * 2), ('ctx', vp * 2)] + \
                [(n, vp) for n in ('gi', 'gh', 'feat', 'gates', 'fac', 'logits', 'dist', 'top_vals', 'top_idx', 'vocab_ws')] + \
-               [('opt', i32)] + [(n, vp) for n in ('base_ms', 'base_e', 'base_i')]
+               [('opt', i32)] + [(n, vp) for n in ('base_ms', 'base_e', 'base_i', 'fork', 'qa1')]
 
 
 # name -> argtypes (return type is int for all but the three listed below)

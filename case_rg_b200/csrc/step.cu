@@ -411,17 +411,33 @@ extern "C" int gttp_decode_step(const gttp_step_args_t* a, int t, case_stream_t 
   const uint8_t* mk[2] = {a->mask_c, a->mask_b};
   const int L[2] = {a->Lc, a->Lb};
   const int ns[2] = {a->nsplit_c, a->nsplit_b};
+  // the two attentions are independent: with a fork handle the (short) context memory runs on the side stream beside the
+  // background memory; the join is an event edge before the GRU cell (captured into the graph like any other edge)
+  const bool fork = !(opt & CASE_OPT_NO_FORK) && a->fork != nullptr && a->qa1 != nullptr;
+  if (fork) {
+    int dev = -1;
+    CUTRY(cudaGetDevice(&dev));
+    CB_REQUIRE(dev == a->fork->device, "gttp_decode_step: the fork handle was created on another device");
+    CUTRY(cudaEventRecord(a->fork->ev_fork[0], st));
+    CUTRY(cudaStreamWaitEvent(a->fork->aux, a->fork->ev_fork[0], 0));
+  }
   for (int i = 0; i < 2; ++i) {
+    cudaStream_t si = (fork && i == 0) ? a->fork->aux : st;
+    float* qbuf = (fork && i == 0) ? a->qa1 : a->qa;
     case_rowlin_args_t q;
     memset(&q, 0, sizeof(q));
     q.seg[0] = seg(s_in, H, H, 1, 1);
-    q.nseg = 1; q.K = H; q.Wt = Wq[i]; q.bias = bq[i]; q.N = H; q.out = a->qa; q.ldo = H;
+    q.nseg = 1; q.K = H; q.Wt = Wq[i]; q.bias = bq[i]; q.N = H; q.out = qbuf; q.ldo = H;
     q.gather_idx = a->parent; q.R = R; q.dtype = dt;
-    TRY(case_row_linear(&q, st));
-    TRY(case_additive_attn(a->qa, U[i], M[i], vv[i], mk[i], nullptr, nullptr, 0, t, B, W, L[i], 2 * H, ns[i],
-                           a->attn_un[i], a->stats[i], a->ctxp[i], a->fast_tanh, dt, st));
+    TRY(case_row_linear(&q, si));
+    TRY(case_additive_attn(qbuf, U[i], M[i], vv[i], mk[i], nullptr, nullptr, 0, t, B, W, L[i], 2 * H, ns[i],
+                           a->attn_un[i], a->stats[i], a->ctxp[i], a->fast_tanh, dt, si));
     TRY(case_attn_merge(a->stats[i], a->ctxp[i], ns[i], 2 * H, a->ctx[i], i == 1 ? a->fac : nullptr, CASE_MAX_SPLIT,
-                        R, st));
+                        R, si));
+  }
+  if (fork) {
+    CUTRY(cudaEventRecord(a->fork->ev_join[0], a->fork->aux));
+    CUTRY(cudaStreamWaitEvent(st, a->fork->ev_join[0], 0));
   }
   {  // GRU cell on [emb ; src_ctx ; bg_ctx]   (Model.py:124-126)
     case_rowlin_args_t g;

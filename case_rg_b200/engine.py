@@ -751,6 +751,8 @@ class GttpDecodeEngine(_EngineBase):
         self.logits, self.dist = z(R, self.ldv), z(R, self.ldv)
         self.top_vals = z(R, W)
         self.top_idx = torch.zeros(R, W, dtype=torch.int32, device=dev)
+        self.qa1 = z(R, H)                                            # query of the context attention when it runs on the side stream
+        self._fork = _Fork(dev)
         self.base_ms, self.base_e = z(R, 4, 2), z(R, 4, 16)          # case_vocab_base statistics (sparse tail)
         self.base_i = torch.zeros(R, 4, 16, dtype=torch.int32, device=dev)
         self._graphs = {}
@@ -779,7 +781,8 @@ class GttpDecodeEngine(_EngineBase):
         for i in range(2):
             a.attn_un[i], a.stats[i], a.ctxp[i], a.ctx[i] = (self.attn_un[i].data_ptr(), self.stats[i].data_ptr(),
                                                              self.ctxp[i].data_ptr(), self.ctx[i].data_ptr())
-        for n in ('emb', 'qa', 'gi', 'gh', 'feat', 'gates', 'fac', 'logits', 'dist', 'top_vals', 'top_idx', 'base_ms', 'base_e',
+        a.fork = self._fork.h
+        for n in ('emb', 'qa', 'qa1', 'gi', 'gh', 'feat', 'gates', 'fac', 'logits', 'dist', 'top_vals', 'top_idx', 'base_ms', 'base_e',
                   'base_i'):
             setattr(a, n, getattr(self, n).data_ptr())
 

@@ -601,6 +601,9 @@ typedef struct {
   /* statistics of case_vocab_base for the sparse tail (search path): base_ms [R][4][2], base_e / base_i [R][4][16];
    * NULL: the dense case_row_tail is used */
   float* base_ms; float* base_e; int32_t* base_i;
+  /* optional: with a fork handle and a second query buffer qa1 [R][H] the attention over the context memory runs on the
+   * handle's side stream beside the attention over the background (CASE_OPT_NO_FORK switches it off) */
+  case_fork_t* fork; float* qa1;
 } gttp_step_args_t;
 
 /* One GTTP decode step (GTTP/Model.py:176-193 -> BBCDecoder.forward :113-131 ->
