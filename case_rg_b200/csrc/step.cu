@@ -389,6 +389,16 @@ extern "C" int case_decode_step(const case_step_args_t* a, int t, case_stream_t 
   }
 }
 
+// gh = Whh . h_prev + bhh (GRU hidden-side gates, GTTP/Model.py:124-126): depends on the previous state only
+static int gttp_hidden_gates(const gttp_step_args_t* a, const float* s_in, int R, int dt, cudaStream_t st) {
+  case_rowlin_args_t hh;
+  memset(&hh, 0, sizeof(hh));
+  hh.seg[0] = seg(s_in, H, H, 1, 1);
+  hh.nseg = 1; hh.K = H; hh.Wt = a->Whh_t; hh.bias = a->bhh; hh.N = 3 * H; hh.out = a->gh; hh.ldo = 3 * H;
+  hh.gather_idx = a->parent; hh.R = R; hh.dtype = dt;
+  return case_row_linear(&hh, st);
+}
+
 extern "C" int gttp_decode_step(const gttp_step_args_t* a, int t, case_stream_t stream) {
   CB_REQUIRE(a, "gttp_decode_step: null args");
   CB_REQUIRE(a->R == a->B * a->W && a->W >= 1 && a->W <= CASE_MAX_W, "gttp_decode_step: R != B*W or W out of range");
@@ -436,6 +446,7 @@ extern "C" int gttp_decode_step(const gttp_step_args_t* a, int t, case_stream_t 
                         R, si));
   }
   if (fork) {
+    TRY(gttp_hidden_gates(a, s_in, R, dt, a->fork->aux));          // the side stream has time to spare: the GRU's hidden-side gates
     CUTRY(cudaEventRecord(a->fork->ev_join[0], a->fork->aux));
     CUTRY(cudaStreamWaitEvent(st, a->fork->ev_join[0], 0));
   }
@@ -448,12 +459,7 @@ extern "C" int gttp_decode_step(const gttp_step_args_t* a, int t, case_stream_t 
     g.nseg = 3; g.K = 5 * H; g.Wt = a->Wih_t; g.bias = a->bih; g.N = 3 * H; g.out = a->gi; g.ldo = 3 * H;
     g.R = R; g.dtype = dt;
     TRY(case_row_linear(&g, st));
-    case_rowlin_args_t hh;
-    memset(&hh, 0, sizeof(hh));
-    hh.seg[0] = seg(s_in, H, H, 1, 1);
-    hh.nseg = 1; hh.K = H; hh.Wt = a->Whh_t; hh.bias = a->bhh; hh.N = 3 * H; hh.out = a->gh; hh.ldo = 3 * H;
-    hh.gather_idx = a->parent; hh.R = R; hh.dtype = dt;
-    TRY(case_row_linear(&hh, st));
+    if (!fork) TRY(gttp_hidden_gates(a, s_in, R, dt, st));
     TRY(case_gru_cell(a->gi, a->gh, s_in, a->parent, s_out, R, st));
   }
   {  // readout on [emb ; h' ; src_ctx ; bg_ctx]   (Model.py:128-130)
