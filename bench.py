@@ -800,7 +800,8 @@ def sample_parity(args, cfg, wl, torch, ref_line):
                token_agreement=float((got == want).float().mean()),
                note='xavier random-init weights give a near-flat 30,522-way softmax, so free-running searches leave the fp32 '
                     'trajectory at the first storage-precision tie; tests/test_gpu_search_parity.py holds the full-size '
-                    'parity cases on peaked weights (identical greedy, >= 99 % of beam queries)')
+                    'parity cases on peaked weights (fp32 storage: identical; bf16 storage: zero misses under the oracle-'
+                    'scored tie criterion, profiles/r2_parity.md)')
     return res
 
 
