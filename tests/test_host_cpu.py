@@ -196,3 +196,25 @@ def test_torch_custom_op_layer_registers_and_has_no_cpu_kernels():
         ops.decode_step(torch.zeros(16, dtype=torch.uint8), 0)
     schema = torch.ops.case_b200.copy_scatter_.default._schema
     assert schema.arguments[0].alias_info is not None and schema.arguments[0].alias_info.is_write
+
+
+@pytest.mark.timeout(300)
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the arm the driver runs next to the B200 arm) on a tiny budget: exactly one JSON line on
+    stdout carrying the contract's keys, produced by the unmodified reference when its sources are at hand (else by the
+    oracle port), without touching a GPU."""
+    import json
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES='')
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--config', 'c1', '--steps', '1',
+                          '--warmup', '0', '--cpu-budget', '6'], capture_output=True, text=True, env=env, timeout=280)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip().startswith('{')]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'dtype',
+              'data', 'config', 'impl', 'cpu_baseline', 'e2e'):
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['metric'] == 'answer_tokens_per_s' and d['unit'] == 'tokens/s'
+    assert d['cpu_baseline']['kind'] in ('reference', 'port') and d['cpu_baseline']['cores'] >= 1
+    assert d['value'] > 0 and d['e2e']['h2d_bytes_per_step'] == 0
